@@ -1,0 +1,106 @@
+"""Deterministic synthetic genomes / reads for the BASELINE configs.
+
+Counter-based SplitMix64 so every element is a pure function of (seed, index): the same
+definition is evaluated by numpy here and could be evaluated per-thread on the device.
+Base codes follow the reference alphabet A=0 C=1 T=2 G=3 (crates/utils/src/lib.rs:17,44-46).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+_GOLDEN = np.uint64(0x9E3779B97F4A7C15)
+_LETTERS = np.frombuffer(b"ACTG", dtype=np.uint8)
+
+
+def splitmix64(seed: int, start: int, n: int) -> np.ndarray:
+    """n outputs of SplitMix64 for counters start+1 .. start+n (wrapping u64 arithmetic)."""
+    with np.errstate(over="ignore"):
+        idx = np.arange(start + 1, start + n + 1, dtype=np.uint64)
+        z = np.uint64(seed) + idx * _GOLDEN
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        return z ^ (z >> np.uint64(31))
+
+
+def genome_codes(seed: int, length: int) -> np.ndarray:
+    """Uniform iid 2-bit codes, 32 bases per SplitMix64 output."""
+    nw = (length + 31) // 32
+    out = np.empty(nw * 32, np.uint8)
+    step = 1 << 20
+    shifts = (np.arange(32, dtype=np.uint64) * np.uint64(2))[None, :]
+    for w0 in range(0, nw, step):
+        w = splitmix64(seed, w0, min(step, nw - w0))
+        out[w0 * 32:(w0 + w.size) * 32] = ((w[:, None] >> shifts) & np.uint64(3)).astype(np.uint8).reshape(-1)
+    return out[:length]
+
+
+def codes_to_ascii(codes: np.ndarray) -> np.ndarray:
+    return _LETTERS[codes]
+
+
+def simulate_reads(genome: np.ndarray, n_reads: int, read_len: int, err_rate: float, seed: int,
+                   first_read: int = 0) -> np.ndarray:
+    """(n_reads, read_len) uint8 codes.  Read r (global index first_read + r): start uniform in
+    [0, G-read_len], strand uniform, iid substitution errors (uniform over the 3 other bases)."""
+    G = genome.size
+    out = np.empty((n_reads, read_len), np.uint8)
+    thr = np.uint64(int(err_rate * (1 << 24)))
+    step = 1 << 18
+    ar = np.arange(read_len, dtype=np.int64)[None, :]
+    for r0 in range(0, n_reads, step):
+        nr = min(step, n_reads - r0)
+        r = splitmix64(seed, first_read + r0, nr)
+        start = ((r >> np.uint64(1)) % np.uint64(G - read_len + 1)).astype(np.int64)
+        strand = (r & np.uint64(1)).astype(bool)
+        b = genome[start[:, None] + ar]
+        b[strand] = b[strand, ::-1] ^ 2
+        if err_rate > 0:
+            e = splitmix64(seed ^ 0x5EED0E44, (first_read + r0) * read_len, nr * read_len).reshape(nr, read_len)
+            hit = (e & np.uint64(0xFFFFFF)) < thr
+            delta = (((e >> np.uint64(24)) % np.uint64(3)) + np.uint64(1)).astype(np.uint8)
+            b = np.where(hit, (b + delta) & 3, b).astype(np.uint8)
+        out[r0:r0 + nr] = b
+    return out
+
+
+def reads_to_ascii_batch(codes2d: np.ndarray):
+    """-> (concatenated ASCII bytes, offsets[n+1] uint64)"""
+    n, L = codes2d.shape
+    data = _LETTERS[codes2d].reshape(-1)
+    offsets = (np.arange(n + 1, dtype=np.uint64) * np.uint64(L))
+    return np.ascontiguousarray(data), offsets
+
+
+# ---- named BASELINE configs ---------------------------------------------------------------
+def config_c2(n_reads: int = 1_000_000, genome_len: int = 5_000_000, read_len: int = 150, err: float = 0.01,
+              seed: int = 0xC2, first_read: int = 0):
+    """BASELINE configs[1]: synthetic 5 Mbp bacterial genome, 150 bp reads at 30x with 1% errors."""
+    g = genome_codes(seed, genome_len)
+    r = simulate_reads(g, n_reads, read_len, err, seed + 1, first_read)
+    return reads_to_ascii_batch(r)
+
+
+def config_c3(n_genomes: int = 100, genome_len: int = 5_000_000, n_shared: int = 20, shared_len: int = 200_000,
+              mut: float = 0.001, seed: int = 0xC3):
+    """BASELINE configs[2]: n genomes sharing mutated segments of an ancestor; colour = genome index.
+    Returns (data, offsets, colors)."""
+    anc = genome_codes(seed, genome_len)
+    seqs = []
+    for gidx in range(n_genomes):
+        g = genome_codes(seed + 1 + gidx, genome_len)
+        # shared segments: evenly spaced windows copied from the ancestor, mutated at `mut`
+        stride = genome_len // n_shared
+        for s in range(n_shared):
+            a = s * stride
+            b = min(a + shared_len, genome_len)
+            seg = anc[a:b].copy()
+            e = splitmix64((seed + 1 + gidx) ^ 0xABCD, a, b - a)
+            hit = (e & np.uint64(0xFFFFFF)) < np.uint64(int(mut * (1 << 24)))
+            delta = (((e >> np.uint64(24)) % np.uint64(3)) + np.uint64(1)).astype(np.uint8)
+            seg = np.where(hit, (seg + delta) & 3, seg).astype(np.uint8)
+            g[a:b] = seg
+        seqs.append(g)
+    data = _LETTERS[np.concatenate(seqs)]
+    offsets = np.arange(n_genomes + 1, dtype=np.uint64) * np.uint64(genome_len)
+    colors = np.arange(n_genomes, dtype=np.uint32)
+    return np.ascontiguousarray(data), offsets, colors

@@ -1,0 +1,305 @@
+"""ctypes front end of the CPU oracle (oracle/ggcat_oracle.c).
+
+TEST INFRASTRUCTURE ONLY -- see the header of ggcat_oracle.c.  Nothing under ggcat_b200/
+may import this module; only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs do.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+_HERE = Path(__file__).resolve().parent
+_SRC = _HERE / "ggcat_oracle.c"
+_LIB = _HERE / "_build" / "libggcat_oracle.so"
+
+HASH_SEQ = 1
+HASH_RK128 = 4
+
+SUPERKMER_DTYPE = np.dtype(
+    [
+        ("read_index", "<u4"),
+        ("start", "<u4"),
+        ("len", "<u4"),
+        ("color", "<u4"),
+        ("bucket", "<u2"),
+        ("minimizer_pos", "<u2"),
+        ("second_bucket", "u1"),
+        ("flags", "u1"),
+        ("rc", "u1"),
+        ("pad", "u1"),
+    ]
+)
+
+TABLE_DTYPE = np.dtype(
+    [
+        ("key_lo", "<u8"),
+        ("key_hi", "<u8"),
+        ("counter", "<u8"),
+        ("multiplicity", "<u8"),
+        ("color_off", "<u4"),
+        ("color_len", "<u4"),
+        ("flags", "u1"),
+        ("kept", "u1"),
+        ("pad", "u1", (6,)),
+    ]
+)
+
+NAIVE_DTYPE = np.dtype([("key_lo", "<u8"), ("key_hi", "<u8"), ("count", "<u8")])
+
+
+def build(force: bool = False) -> Path:
+    """Compile the C restatement with gcc (no external deps)."""
+    if _LIB.exists() and not force and _LIB.stat().st_mtime >= _SRC.stat().st_mtime:
+        return _LIB
+    _LIB.parent.mkdir(parents=True, exist_ok=True)
+    cmd = ["gcc", "-O2", "-fopenmp", "-shared", "-fPIC", "-o", str(_LIB), str(_SRC)]
+    subprocess.check_call(cmd)
+    return _LIB
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(str(_LIB))
+        _lib.orc_sizeof_superkmer.restype = C.c_size_t
+        _lib.orc_sizeof_table_entry.restype = C.c_size_t
+        assert _lib.orc_sizeof_superkmer() == SUPERKMER_DTYPE.itemsize
+        assert _lib.orc_sizeof_table_entry() == TABLE_DTYPE.itemsize
+        for name in (
+            "orc_split_segments",
+            "orc_compress_from_plain",
+            "orc_compress_from_plain_rc",
+            "orc_encode_varint",
+            "orc_encode_varint_flags",
+            "orc_decode_varint_flags",
+            "orc_decode_varint",
+            "orc_nthash_iter",
+            "orc_window_minima",
+            "orc_bucketing",
+            "orc_superkmer_packed",
+            "orc_superkmer_record",
+            "orc_kmer_hashes",
+            "orc_merge_unit",
+            "orc_naive_count",
+            "orc_compute_best_m",
+        ):
+            getattr(_lib, name).restype = C.c_size_t
+        _lib.orc_seqhash64_get_bucket.restype = C.c_uint16
+    return _lib
+
+
+def _p(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _bytes_arr(b) -> np.ndarray:
+    if isinstance(b, np.ndarray):
+        return np.ascontiguousarray(b, dtype=np.uint8)
+    return np.frombuffer(bytes(b), dtype=np.uint8).copy()
+
+
+# ---------------------------------------------------------------------------- primitives
+def normalize(seq: bytes) -> bytes:
+    a = _bytes_arr(seq)
+    lib().orc_normalize(_p(a), C.c_size_t(a.size))
+    return a.tobytes()
+
+
+def split_segments(seq: bytes, k: int):
+    a = _bytes_arr(seq)
+    cap = a.size // max(k, 1) + 2
+    st = np.zeros(cap, np.uint64)
+    en = np.zeros(cap, np.uint64)
+    n = lib().orc_split_segments(_p(a), C.c_size_t(a.size), C.c_size_t(k), _p(st), _p(en), C.c_size_t(cap))
+    return [(int(st[i]), int(en[i])) for i in range(n)]
+
+
+def compress_from_plain(seq: bytes, rc: bool = False) -> bytes:
+    a = _bytes_arr(seq)
+    out = np.zeros(a.size // 4 + 8, np.uint8)
+    f = lib().orc_compress_from_plain_rc if rc else lib().orc_compress_from_plain
+    n = f(_p(a), C.c_size_t(a.size), _p(out))
+    return out[:n].tobytes()
+
+
+def unpack(packed: bytes, start: int, n: int) -> bytes:
+    a = _bytes_arr(packed)
+    out = np.zeros(n, np.uint8)
+    lib().orc_unpack(_p(a), C.c_size_t(start), C.c_size_t(n), _p(out))
+    return out.tobytes()
+
+
+def encode_varint(v: int) -> bytes:
+    out = np.zeros(16, np.uint8)
+    n = lib().orc_encode_varint(C.c_uint64(v), _p(out))
+    return out[:n].tobytes()
+
+
+def decode_varint(b: bytes):
+    a = _bytes_arr(b)
+    v = C.c_uint64(0)
+    n = lib().orc_decode_varint(_p(a), C.c_size_t(a.size), C.byref(v))
+    return v.value, n
+
+
+def encode_varint_flags(v: int, flags: int, flags_count: int = 2) -> bytes:
+    out = np.zeros(16, np.uint8)
+    n = lib().orc_encode_varint_flags(C.c_uint64(v), C.c_uint8(flags), C.c_int(flags_count), _p(out))
+    return out[:n].tobytes()
+
+
+def decode_varint_flags(b: bytes, flags_count: int = 2):
+    a = _bytes_arr(b)
+    v = C.c_uint64(0)
+    f = C.c_uint8(0)
+    n = lib().orc_decode_varint_flags(_p(a), C.c_size_t(a.size), C.c_int(flags_count), C.byref(v), C.byref(f))
+    return v.value, f.value, n
+
+
+def nthash(seq: bytes, m: int):
+    a = _bytes_arr(seq)
+    n = a.size - m + 1
+    fw = np.zeros(max(n, 0), np.uint64)
+    rc = np.zeros(max(n, 0), np.uint64)
+    if n > 0:
+        lib().orc_nthash_iter(_p(a), C.c_size_t(a.size), C.c_size_t(m), _p(fw), _p(rc))
+    return fw, rc
+
+
+def window_minima(vals: np.ndarray, w: int):
+    vals = np.ascontiguousarray(vals, np.uint64)
+    n = vals.size
+    ov = np.zeros(max(n, 1), np.uint64)
+    oi = np.zeros(max(n, 1), np.uint32)
+    cnt = lib().orc_window_minima(_p(vals), C.c_size_t(n), C.c_size_t(w), _p(ov), _p(oi))
+    return ov[:cnt], oi[:cnt]
+
+
+def kmer_hashes(seq: bytes, k: int, hash_type: int = HASH_SEQ, forward_only: bool = False):
+    a = _bytes_arr(seq)
+    n = max(a.size - k + 1, 0)
+    lo = np.zeros(n, np.uint64)
+    hi = np.zeros(n, np.uint64)
+    fw = np.zeros(n, np.uint8)
+    if n:
+        lib().orc_kmer_hashes(_p(a), C.c_size_t(a.size), C.c_size_t(k), C.c_int(hash_type), C.c_int(forward_only), _p(lo), _p(hi), _p(fw))
+    return lo, hi, fw
+
+
+def rk_constants(k: int):
+    out = np.zeros(14, np.uint64)
+    lib().orc_rk_constants(_p(out), C.c_size_t(k))
+    names = ["MULTIPLIER", "MULT_INV", "MULT_A", "MULT_C", "MULT_G", "MULT_T", "RMMULT"]
+    return {n: int(out[2 * i]) | (int(out[2 * i + 1]) << 64) for i, n in enumerate(names)}
+
+
+def bucket_counts(bases_count: int):
+    a = C.c_uint(0)
+    b = C.c_uint(0)
+    lib().orc_bucket_counts(C.c_uint64(bases_count), C.byref(a), C.byref(b))
+    return a.value, b.value
+
+
+def compute_best_m(k: int) -> int:
+    return int(lib().orc_compute_best_m(C.c_size_t(k)))
+
+
+# ---------------------------------------------------------------------------- pipeline
+class Reads:
+    """Concatenated raw ASCII records + offsets (+ optional per-record colour)."""
+
+    def __init__(self, data: np.ndarray, offsets: np.ndarray, colors: np.ndarray | None = None):
+        self.data = np.ascontiguousarray(data, np.uint8)
+        self.offsets = np.ascontiguousarray(offsets, np.uint64)
+        self.colors = None if colors is None else np.ascontiguousarray(colors, np.uint32)
+        assert self.offsets[-1] == self.data.size
+
+    @classmethod
+    def from_list(cls, seqs, colors=None):
+        lens = np.array([len(s) for s in seqs], np.uint64)
+        offs = np.zeros(len(seqs) + 1, np.uint64)
+        np.cumsum(lens, out=offs[1:])
+        data = np.frombuffer(b"".join(bytes(s) for s in seqs), np.uint8).copy() if len(seqs) else np.zeros(0, np.uint8)
+        return cls(data, offs, None if colors is None else np.array(colors, np.uint32))
+
+    @property
+    def n(self):
+        return self.offsets.size - 1
+
+
+def bucketing(reads: Reads, k: int, m: int, b1: int, b2: int, forward_only: bool = False):
+    """Phase 1 -> structured array of super-k-mers in emission order, valid base count."""
+    L = lib()
+    cap = max(1024, int(reads.data.size // 4) + reads.n + 16)
+    vb = C.c_uint64(0)
+    while True:
+        out = np.zeros(cap, SUPERKMER_DTYPE)
+        n = L.orc_bucketing(
+            _p(reads.data), _p(reads.offsets), C.c_size_t(reads.n),
+            _p(reads.colors) if reads.colors is not None else None,
+            C.c_size_t(k), C.c_size_t(m), C.c_uint(b1), C.c_uint(b2), C.c_int(forward_only),
+            _p(out), C.c_size_t(cap), C.byref(vb),
+        )
+        if n <= cap:
+            return out[:n].copy(), vb.value
+        cap = n
+
+
+def superkmer_packed(reads: Reads, sk_row) -> bytes:
+    row = np.array([sk_row], SUPERKMER_DTYPE)
+    out = np.zeros(int(row["len"][0]) // 4 + 8, np.uint8)
+    n = lib().orc_superkmer_packed(_p(reads.data), _p(reads.offsets), _p(row), _p(out))
+    return out[:n].tobytes()
+
+
+def superkmer_record(reads: Reads, sk_row, k: int) -> bytes:
+    row = np.array([sk_row], SUPERKMER_DTYPE)
+    out = np.zeros(int(row["len"][0]) // 4 + 32, np.uint8)
+    n = lib().orc_superkmer_record(_p(reads.data), _p(reads.offsets), _p(row), C.c_size_t(k), _p(out))
+    return out[:n].tobytes()
+
+
+def merge_unit(reads: Reads, sk: np.ndarray, bucket: int, second_bucket: int, k: int, min_multiplicity: int,
+               hash_type: int = HASH_SEQ, forward_only: bool = False, with_color: bool = False):
+    """Phase 2 for one unit (second_bucket=-1 folds the whole first-level bucket).
+    Returns (table sorted by key incl. non-kept entries, colours array, total k-mer occurrences)."""
+    L = lib()
+    sk = np.ascontiguousarray(sk, SUPERKMER_DTYPE)
+    sel = sk["bucket"] == bucket
+    if second_bucket >= 0:
+        sel &= sk["second_bucket"] == second_bucket
+    sub = np.ascontiguousarray(sk[sel])
+    total = int((sub["len"].astype(np.int64) - k + 1).sum())
+    cap = max(total, 1)
+    ccap = max(total, 1) if with_color else 1
+    out = np.zeros(cap, TABLE_DTYPE)
+    cols = np.zeros(ccap, np.uint32)
+    ncol = C.c_uint64(0)
+    tk = C.c_uint64(0)
+    n = L.orc_merge_unit(
+        _p(reads.data), _p(reads.offsets), _p(sub), C.c_size_t(sub.size), C.c_int(bucket), C.c_int(second_bucket),
+        C.c_size_t(k), C.c_uint64(min_multiplicity), C.c_int(hash_type), C.c_int(forward_only), C.c_int(with_color),
+        _p(out), C.c_size_t(cap), _p(cols), C.c_size_t(ccap), C.byref(ncol), C.byref(tk),
+    )
+    assert n <= cap and ncol.value <= ccap
+    return out[:n].copy(), cols[: ncol.value].copy(), tk.value
+
+
+def naive_count(reads: Reads, k: int, hash_type: int = HASH_SEQ, forward_only: bool = False):
+    L = lib()
+    lens = (reads.offsets[1:] - reads.offsets[:-1]).astype(np.int64)
+    cap = int(np.maximum(lens - k + 1, 0).sum()) + 1
+    out = np.zeros(cap, NAIVE_DTYPE)
+    tot = C.c_uint64(0)
+    n = L.orc_naive_count(_p(reads.data), _p(reads.offsets), C.c_size_t(reads.n), C.c_size_t(k), C.c_int(hash_type),
+                          C.c_int(forward_only), _p(out), C.c_size_t(cap), C.byref(tot))
+    return out[:n].copy(), tot.value
