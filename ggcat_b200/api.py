@@ -1,0 +1,282 @@
+"""Host-side mirror of the reference's phase-1 / phase-2 entry points over the C ABI.
+
+Reference interface mirrored (names, argument meaning, error behaviour):
+  * ``minimizer_bucketing(input_blocks, buckets_count, second_buckets_count, k, m, forward_only)``
+      <- crates/assembler_minimizer_bucketing/src/lib.rs:279-340 (returns the bucket handle the way the
+         reference returns ``Vec<MultiChunkBucket>``; here buckets live in HBM inside the context);
+  * ``kmers_merge(buckets, min_multiplicity, ...)``
+      <- crates/assembler_kmers_merge/src/lib.rs:159-284 up to the completed k-mer table
+         (``FxHashMap<hash, MapEntry>``, crates/structs/src/map_entry.rs) per (bucket, second_bucket).
+Errors: the reference panics (crates/logging/src/lib.rs:82-107); here every failure raises
+``GgcatB200Error`` carrying the library's message.  No CPU fallback exists.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Iterable, Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+
+HASH_AUTO, HASH_SEQ, HASH_RK128 = 0, 1, 4  # crates/api/src/utils.rs:4-8
+
+
+class GgcatB200Error(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"ggcat_b200 error {code}: {msg}")
+        self.code = code
+
+
+def _check(rc: int):
+    if rc != 0:
+        raise GgcatB200Error(rc, _lib.load().ggcat_b200_last_error().decode())
+
+
+def compute_best_m(k: int) -> int:
+    """crates/utils/src/lib.rs:29-40"""
+    return int(_lib.load().ggcat_b200_compute_best_m(k))
+
+
+def bucket_counts(estimated_bases: int) -> tuple[int, int]:
+    """(buckets_count_log, second_buckets_count_log) per crates/io/src/lib.rs:67-140."""
+    a, b = C.c_uint32(0), C.c_uint32(0)
+    _lib.load().ggcat_b200_bucket_counts(estimated_bases, C.byref(a), C.byref(b))
+    return a.value, b.value
+
+
+@dataclass
+class Params:
+    k: int
+    m: int = 0
+    min_multiplicity: int = 2
+    buckets_count_log: int = 9
+    second_buckets_count_log: int = 6
+    forward_only: bool = False
+    hash_type: int = HASH_AUTO
+    colors: bool = False
+    device: int = 0
+
+
+@dataclass
+class BucketStats:
+    total_bases: int
+    valid_bases: int
+    n_superkmers: int
+    n_kmers: int
+    payload_words: int
+    n_buckets: int
+    n_units: int
+
+
+SUPERKMER_DTYPE = np.dtype(
+    [("payload_offset", "<u8"), ("len", "<u4"), ("color", "<u4"), ("bucket", "<u2"), ("minimizer_pos", "<u2"),
+     ("second_bucket", "u1"), ("flags", "u1"), ("rc", "u1"), ("pad", "u1")]
+)
+
+
+class KmerTable:
+    """Filtered k-mer table of a bucket range (host copy).  Arrays are numpy views copied out of the
+    library-owned pinned buffers, so the object stays valid after release."""
+
+    def __init__(self, keys_lo, keys_hi, count_flags, first_unit, unit_offsets, total_kmers, unique_kmers,
+                 color_offsets=None, colors=None):
+        self.keys_lo = keys_lo
+        self.keys_hi = keys_hi
+        self.count_flags = count_flags
+        self.first_unit = first_unit
+        self.unit_offsets = unit_offsets
+        self.total_kmers = total_kmers
+        self.unique_kmers = unique_kmers
+        self.color_offsets = color_offsets
+        self.colors = colors
+
+    @property
+    def n_entries(self) -> int:
+        return int(self.keys_lo.size)
+
+    @property
+    def multiplicity(self) -> np.ndarray:
+        return self.count_flags & np.uint32(0x3FFFFFFF)
+
+    @property
+    def flags(self) -> np.ndarray:
+        return (self.count_flags >> np.uint32(30)).astype(np.uint8)
+
+    def unit_slice(self, unit: int) -> slice:
+        u = unit - self.first_unit
+        return slice(int(self.unit_offsets[u]), int(self.unit_offsets[u + 1]))
+
+
+class GGCATB200:
+    """One context = one build on one GPU (the reference's per-run global state)."""
+
+    def __init__(self, params: Params):
+        self._lib = _lib.load()
+        pc = _lib.ParamsC(k=params.k, m=params.m, min_multiplicity=params.min_multiplicity,
+                          buckets_count_log=params.buckets_count_log,
+                          second_buckets_count_log=params.second_buckets_count_log,
+                          forward_only=int(params.forward_only), hash_type=params.hash_type,
+                          colors=int(params.colors), device=params.device)
+        h = C.c_void_p(None)
+        _check(self._lib.ggcat_b200_create(C.byref(pc), C.byref(h)))
+        self._h = h
+        self.params = params
+        self.m = params.m or compute_best_m(params.k)
+        self._keep = []  # device tensors of imported slices must outlive the merge
+
+    # -- lifecycle
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.ggcat_b200_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def reset(self):
+        _check(self._lib.ggcat_b200_reset(self._h))
+        self._keep.clear()
+
+    # -- phase 1
+    def push_reads(self, data: np.ndarray, offsets: np.ndarray, colors: Optional[np.ndarray] = None):
+        data = np.ascontiguousarray(data, np.uint8)
+        offsets = np.ascontiguousarray(offsets, np.uint64)
+        n = offsets.size - 1
+        cp = None
+        if colors is not None:
+            colors = np.ascontiguousarray(colors, np.uint32)
+            cp = colors.ctypes.data
+        _check(self._lib.ggcat_b200_push_reads(self._h, data.ctypes.data, offsets.ctypes.data, n, cp))
+
+    def push_reads_ptr(self, data_ptr: int, offsets_ptr: int, n_reads: int, colors_ptr: Optional[int] = None):
+        """Host pointers (e.g. pinned buffers) without numpy wrapping."""
+        _check(self._lib.ggcat_b200_push_reads(self._h, data_ptr, offsets_ptr, n_reads, colors_ptr))
+
+    def push_reads_device(self, d_data_ptr: int, d_offsets_ptr: int, n_reads: int, n_bytes: int,
+                          d_colors_ptr: Optional[int] = None):
+        _check(self._lib.ggcat_b200_push_reads_device(self._h, d_data_ptr, d_offsets_ptr, n_reads, n_bytes, d_colors_ptr))
+
+    def finish_bucketing(self) -> BucketStats:
+        st = _lib.BucketStatsC()
+        _check(self._lib.ggcat_b200_finish_bucketing(self._h, C.byref(st)))
+        return BucketStats(st.total_bases, st.valid_bases, st.n_superkmers, st.n_kmers, st.payload_words, st.n_buckets,
+                           st.n_units)
+
+    def unit_sizes(self):
+        nu = ((1 << self.params.buckets_count_log) + 1) << self.params.second_buckets_count_log
+        a = np.zeros(nu, np.uint64)
+        b = np.zeros(nu, np.uint64)
+        _check(self._lib.ggcat_b200_unit_sizes(self._h, a.ctypes.data, b.ctypes.data))
+        return a, b
+
+    def dump_superkmers(self, bucket: int):
+        """Test hook: (structured array of super-k-mers, payload bytes) of one first-level bucket."""
+        n, pb = C.c_uint64(0), C.c_uint64(0)
+        _check(self._lib.ggcat_b200_dump_superkmers(self._h, bucket, None, 0, None, 0, C.byref(n), C.byref(pb)))
+        out = np.zeros(n.value, SUPERKMER_DTYPE)
+        payload = np.zeros(max(pb.value, 1), np.uint8)
+        if n.value:
+            _check(self._lib.ggcat_b200_dump_superkmers(self._h, bucket, out.ctypes.data, n.value, payload.ctypes.data,
+                                                        pb.value, C.byref(n), C.byref(pb)))
+        return out, payload[: pb.value]
+
+    # -- phase 2
+    def merge_bucket_range(self, first_bucket: int, n_buckets: int) -> KmerTable:
+        t = _lib.TableC()
+        _check(self._lib.ggcat_b200_merge_bucket_range(self._h, first_bucket, n_buckets, C.byref(t)))
+        try:
+            ne = int(t.n_entries)
+            keys = np.ctypeslib.as_array(t.keys_lo, shape=(ne,)).copy() if ne else np.zeros(0, np.uint64)
+            cf = np.ctypeslib.as_array(t.count_flags, shape=(ne,)).copy() if ne else np.zeros(0, np.uint32)
+            uo = np.ctypeslib.as_array(t.unit_offsets, shape=(int(t.n_units) + 1,)).copy()
+            hi = None
+            if t.keys_hi:
+                hi = np.ctypeslib.as_array(t.keys_hi, shape=(ne,)).copy() if ne else np.zeros(0, np.uint64)
+            co = cl = None
+            if t.color_offsets:
+                co = np.ctypeslib.as_array(t.color_offsets, shape=(ne + 1,)).copy()
+                cl = np.ctypeslib.as_array(t.colors, shape=(int(co[-1]),)).copy() if co[-1] else np.zeros(0, np.uint32)
+            return KmerTable(keys, hi, cf, int(t.first_unit), uo, int(t.total_kmers), int(t.unique_kmers), co, cl)
+        finally:
+            self._lib.ggcat_b200_release_table(self._h, C.byref(t))
+
+    def merge_bucket_range_device(self, first_bucket: int, n_buckets: int):
+        """Table stays in HBM; returns (n_entries, unique_kmers, total_kmers)."""
+        a, b, c = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+        _check(self._lib.ggcat_b200_merge_bucket_range_device(self._h, first_bucket, n_buckets, C.byref(a), C.byref(b),
+                                                              C.byref(c)))
+        return a.value, b.value, c.value
+
+    # -- multi-GPU plumbing
+    def n_chunks(self) -> int:
+        return int(self._lib.ggcat_b200_n_chunks(self._h))
+
+    def export_chunk_slice(self, chunk: int, first_unit: int, n_units: int) -> "_lib.ChunkSliceC":
+        s = _lib.ChunkSliceC()
+        _check(self._lib.ggcat_b200_export_chunk_slice(self._h, chunk, first_unit, n_units, C.byref(s)))
+        return s
+
+    def import_chunk_slice(self, first_unit: int, n_units: int, s: "_lib.ChunkSliceC", keepalive=None):
+        _check(self._lib.ggcat_b200_import_chunk_slice(self._h, first_unit, n_units, C.byref(s)))
+        if keepalive is not None:
+            self._keep.append(keepalive)
+
+    def drop_local_chunks(self):
+        _check(self._lib.ggcat_b200_drop_local_chunks(self._h))
+
+    # -- measurement
+    @property
+    def stream_ptr(self) -> int:
+        return int(self._lib.ggcat_b200_stream(self._h) or 0)
+
+    def synchronize(self):
+        _check(self._lib.ggcat_b200_synchronize(self._h))
+
+    def set_timing(self, on: bool):
+        _check(self._lib.ggcat_b200_set_timing(self._h, int(on)))
+
+    def kernel_times(self, reset: bool = True) -> dict:
+        cap = 16
+        names = (C.c_char_p * cap)()
+        ms = (C.c_float * cap)()
+        ln = (C.c_uint32 * cap)()
+        n = self._lib.ggcat_b200_kernel_times(self._h, names, ms, ln, cap, int(reset))
+        if n < 0:
+            _check(n)
+        return {names[i].decode(): (float(ms[i]), int(ln[i])) for i in range(n)}
+
+
+# ------------------------------------------------------------------ reference-shaped phase functions
+def minimizer_bucketing(input_blocks: Iterable[Sequence], buckets_count_log: int, second_buckets_count_log: int, k: int,
+                        m: int = 0, forward_only: bool = False, min_multiplicity: int = 2, colors: bool = False,
+                        device: int = 0) -> tuple[GGCATB200, BucketStats]:
+    """Phase 1 ("phase: reads bucketing").  input_blocks: iterable of (data, offsets[, colors]) ASCII batches,
+    one per input block/file like the reference's ``Vec<GeneralSequenceBlockData>``; with ``colors`` and no
+    explicit colour array, block i gets colour i (file_color = i, lib.rs:300-305)."""
+    ctx = GGCATB200(Params(k=k, m=m, min_multiplicity=min_multiplicity, buckets_count_log=buckets_count_log,
+                           second_buckets_count_log=second_buckets_count_log, forward_only=forward_only, colors=colors,
+                           device=device))
+    for i, blk in enumerate(input_blocks):
+        data, offsets = blk[0], blk[1]
+        col = blk[2] if len(blk) > 2 else (np.full(len(offsets) - 1, i, np.uint32) if colors else None)
+        ctx.push_reads(data, offsets, col)
+    return ctx, ctx.finish_bucketing()
+
+
+def kmers_merge(buckets: GGCATB200, first_bucket: int = 0, n_buckets: Optional[int] = None) -> KmerTable:
+    """Phase 2 ("phase: kmers merge") up to the completed, filtered k-mer table."""
+    nb = (1 << buckets.params.buckets_count_log) + 1
+    if n_buckets is None:
+        n_buckets = nb - first_bucket
+    return buckets.merge_bucket_range(first_bucket, n_buckets)

@@ -1,0 +1,429 @@
+// bucketing.cuh -- phase 1 (minimizer bucketing) kernels.
+//
+// Replaces the per-sequence hot loop of the reference
+//   crates/minimizer_bucketing/src/lib.rs:310-376  (normalise / N-split / process_sequence / push)
+//   crates/assembler_minimizer_bucketing/src/lib.rs:171-270  (process_sequence)
+//   crates/hashes/src/cn_nthash.rs:21-58, crates/hashes/src/rolling/batch_minqueue.rs:37-188
+// by a position-parallel formulation (tests/model.py is the executable spec):
+// every (k-1)-mer window j of the concatenated batch gets  M_j = min over its w = k-m m-mer values
+// with the duplicate rule folded into the value ( comb(a,b) = a==b ? a&~1 : min(a,b) ), and a
+// super-k-mer starts at j iff j is the first window of its segment, or M_j != M_{j-1}, or the
+// minimum is unique but a different m-mer instance ( v[j-1] == M_j ).
+//
+// Data flow per batch (all device-resident):
+//   k_pack      ASCII -> 2-bit words (16 bases / u32) + `bad` bitmap (non-ACGT)      [1 B/base read]
+//   k_mark      read starts -> `brk` bitmap
+//   k_windows   tile of 1024 windows: hashes, window minima, split/segment-end entries (compacted)
+//   k_scan      exclusive scan of per-tile super-k-mer counts
+//   k_emit      entry -> super-k-mer descriptor (start,len,unit,flags,rc,minimizer_pos), unit histogram
+//   k_scan      exclusive scan of per-unit counts / payload words
+//   k_scatter   stored-orientation payload + descriptor into the unit-sorted bucket chunk
+#pragma once
+#include "device_utils.cuh"
+
+namespace ggb {
+
+struct DevParams {
+    uint32_t k, m, w;  // w = k - m : m-mers per (k-1)-mer window
+    uint32_t b1, b2;
+    uint32_t forward_only;
+    uint32_t colors;
+    uint32_t n_units;  // ((1<<b1)+1) << b2
+};
+
+constexpr int WIN_T = 1024;       // windows per tile
+constexpr int WIN_THREADS = 256;
+constexpr int WIN_WMAX = 64;      // max supported k - m
+constexpr int WIN_NI = WIN_T + WIN_WMAX;  // m-mer items per tile (upper bound)
+
+// entry bit layout (u64)
+constexpr int ENT_POS_BITS = 11;  // position of the window inside its tile
+constexpr uint64_t ENT_S = 1ull << 11, ENT_E = 1ull << 12, ENT_FIRST = 1ull << 13, ENT_RC = 1ull << 14,
+                   ENT_DUP = 1ull << 15;
+constexpr int ENT_SECOND_SHIFT = 16, ENT_BUCKET_SHIFT = 24, ENT_ARG_SHIFT = 38, ENT_SRANK_SHIFT = 46;
+
+// descriptor meta word: minimizer_pos(16) | flags(2)<<16 | rc<<18 | second_bucket(8)<<19
+__host__ __device__ __forceinline__ uint32_t make_meta(uint32_t mpos, uint32_t flags, uint32_t rc, uint32_t second) {
+    return (mpos & 0xFFFFu) | (flags << 16) | (rc << 18) | (second << 19);
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_pack: crates/io/src/sequences_reader.rs:26-37 (normalisation: anything but ACGTacgt is 'N') +
+// crates/utils/src/lib.rs:44-46 (code = (c>>1)&3) + crates/io/src/compressed_read.rs:610-618 layout.
+// One thread per 32 bases -> two packed words and one `bad` word.  Positions >= n are bad.
+__global__ void __launch_bounds__(256) k_pack(const uint8_t *__restrict__ ascii, uint64_t n, uint32_t *__restrict__ pk,
+                                              uint32_t *__restrict__ bad, uint64_t n_groups, int aligned16) {
+    const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_groups) return;
+    const uint64_t base = g * 32;
+    uint32_t x[8];
+    if (base + 32 <= n && aligned16) {
+        const uint4 a = __ldg(reinterpret_cast<const uint4 *>(ascii + base));
+        const uint4 b = __ldg(reinterpret_cast<const uint4 *>(ascii + base + 16));
+        x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+    } else {
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            uint32_t v = 0;
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                const uint64_t i = base + q * 4 + b;
+                const uint32_t c = i < n ? ascii[i] : 0u;
+                v |= c << (8 * b);
+            }
+            x[q] = v;
+        }
+    }
+    uint32_t w0 = 0, w1 = 0, bd = 0;
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+        const uint32_t c = (x[q] >> 1) & 0x03030303u;
+        const uint32_t codes = (c & 3u) | ((c >> 6) & 0xCu) | ((c >> 12) & 0x30u) | ((c >> 18) & 0xC0u);
+        const uint32_t u = x[q] & 0xDFDFDFDFu;
+        const uint32_t valid = __vcmpeq4(u, 0x41414141u) | __vcmpeq4(u, 0x43434343u) | __vcmpeq4(u, 0x47474747u) |
+                               __vcmpeq4(u, 0x54545454u);
+        const uint32_t inv = ~valid;
+        const uint32_t bits = (inv & 1u) | ((inv >> 7) & 2u) | ((inv >> 14) & 4u) | ((inv >> 21) & 8u);
+        const uint32_t okm = ((valid & 1u) * 3u) | (((valid >> 8) & 1u) * 0xCu) | (((valid >> 16) & 1u) * 0x30u) |
+                             (((valid >> 24) & 1u) * 0xC0u);
+        const uint32_t cc = codes & okm;  // invalid bases pack as 0 (never read by a valid window)
+        if (q < 4) w0 |= cc << (8 * q); else w1 |= cc << (8 * (q - 4));
+        bd |= bits << (4 * q);
+    }
+    pk[2 * g] = w0;
+    pk[2 * g + 1] = w1;
+    bad[g] = bd;
+}
+
+// k_mark: a record boundary is a segment boundary (each input record is processed independently,
+// crates/minimizer_bucketing/src/lib.rs:310-320).
+__global__ void k_mark(const uint64_t *__restrict__ offsets, uint64_t n_reads, uint64_t off0, uint64_t n,
+                       uint32_t *__restrict__ brk) {
+    const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_reads) return;
+    const uint64_t off = offsets[r] - off0;
+    if (off < n) atomicOr(&brk[off >> 5], 1u << (off & 31));
+}
+
+__device__ __forceinline__ bool any_bits(const uint32_t *bm, uint32_t s, uint32_t cnt) {
+    if (cnt == 0) return false;
+    const uint32_t e = s + cnt - 1;  // inclusive
+    const uint32_t ws = s >> 5, we = e >> 5;
+    for (uint32_t w = ws; w <= we; ++w) {
+        uint32_t mask = 0xffffffffu;
+        if (w == ws) mask &= 0xffffffffu << (s & 31);
+        if (w == we) mask &= 0xffffffffu >> (31 - (e & 31));
+        if (bm[w] & mask) return true;
+    }
+    return false;
+}
+
+// comb(): the window-minimum semigroup with the duplicate flag in bit 0
+// (crates/hashes/src/rolling/batch_minqueue.rs:63-70,78-84,97-113: equal values clear the unique bit).
+__device__ __forceinline__ uint64_t comb(uint64_t a, uint64_t b) { return a == b ? (a & ~1ull) : (a < b ? a : b); }
+
+// ------------------------------------------------------------------------------------------------
+// k_windows: one CTA per tile of WIN_T windows.
+__global__ void __launch_bounds__(WIN_THREADS)
+k_windows(const uint32_t *__restrict__ pk, const uint32_t *__restrict__ bad, const uint32_t *__restrict__ brk,
+          uint32_t n /* bases in batch */, DevParams P, uint64_t *__restrict__ ent, uint32_t *__restrict__ tile_cnt,
+          uint32_t *__restrict__ tile_scnt) {
+    __shared__ uint32_t s_pk[(WIN_T + 2 * WIN_WMAX + 64) / 16 + 4];
+    __shared__ uint32_t s_bad[(WIN_T + 2 * WIN_WMAX + 64) / 32 + 4];
+    __shared__ uint32_t s_brk[(WIN_T + 2 * WIN_WMAX + 64) / 32 + 4];
+    __shared__ uint64_t s_v0[WIN_NI + 1];
+    __shared__ uint64_t s_a[WIN_NI + 1];
+    __shared__ uint64_t s_b[WIN_NI + 1];
+    __shared__ uint8_t s_fwd[WIN_NI + 1];
+    __shared__ uint8_t s_ok[WIN_T + 4];
+    __shared__ uint64_t s_ent[WIN_T];
+    __shared__ uint64_t s_H[4], s_R[4];
+    __shared__ uint32_t s_scan[WIN_THREADS / 32 + 2];
+
+    const uint32_t tid = threadIdx.x;
+    const uint32_t tile = blockIdx.x;
+    const int64_t j0 = (int64_t)tile * WIN_T;  // first window of the tile (== its base index)
+    const uint32_t k = P.k, m = P.m, w = P.w;
+    // x-coordinates: window / m-mer item x  <->  global position j0 - 1 + x
+    const int64_t gfirst = j0 - 1;
+    const int64_t bfirst = gfirst < 0 ? 0 : gfirst;       // first base the tile may touch
+    const uint32_t W0 = (uint32_t)(bfirst >> 4);          // first packed word
+    const uint32_t BW0 = (uint32_t)(bfirst >> 5);         // first bitmap word
+    const uint32_t n_items = WIN_T + w;                   // m-mer items x in [0, n_items)
+    const uint32_t last_base = (uint32_t)(j0 + WIN_T + k + 1);  // exclusive upper bound of bases touched
+    const uint32_t n_pkw = ((last_base + 15) >> 4) - W0 + 2;
+    const uint32_t n_bmw = ((last_base + 31) >> 5) - BW0 + 1;
+
+    if (tid < 4) { s_H[tid] = nt_h(tid); s_R[tid] = nt_r(tid); }
+    for (uint32_t i = tid; i < n_pkw; i += WIN_THREADS) s_pk[i] = pk[W0 + i];
+    for (uint32_t i = tid; i < n_bmw; i += WIN_THREADS) { s_bad[i] = bad[BW0 + i]; s_brk[i] = brk[BW0 + i]; }
+    __syncthreads();
+
+    // ---- m-mer hashes: each thread rolls through IPT consecutive items (cn_nthash.rs:21-58)
+    {
+        const uint32_t IPT = (n_items + WIN_THREADS - 1) / WIN_THREADS;
+        const uint32_t x0 = tid * IPT;
+        const uint32_t x1 = min(n_items, x0 + IPT);
+        if (x0 < x1) {
+            int64_t g = gfirst + x0;  // global m-mer position
+            uint32_t xs = x0;
+            if (g < 0) { s_v0[xs] = ~0ull; s_fwd[xs] = 0; ++g; ++xs; }
+            if (xs < x1) {
+                const uint32_t lb = (uint32_t)(g - ((int64_t)W0 << 4));  // local base index into s_pk
+                uint64_t fw = 0, rc = 0;
+                for (uint32_t i = 0; i < m; i++) {
+                    const uint32_t c = packed_base(s_pk, lb + i);
+                    fw ^= rotl64(s_H[c], m - 1 - i);
+                    rc ^= rotl64(s_R[c], i);
+                }
+                uint32_t l = lb;
+                for (uint32_t x = xs;; ++x) {
+                    const uint64_t mn = fw < rc ? fw : rc;
+                    s_v0[x] = (mn << 1) | (uint64_t)(fw != rc);  // to_unextendable | !is_rc_symmetric
+                    s_fwd[x] = fw < rc;
+                    if (x + 1 >= x1) break;
+                    const uint32_t co = packed_base(s_pk, l), ci = packed_base(s_pk, l + m);
+                    fw = rotl64(fw, 1) ^ rotl64(s_H[co], m) ^ s_H[ci];
+                    rc = rotl64(rc ^ s_R[co], 63) ^ rotl64(s_R[ci], m - 1);
+                    ++l;
+                }
+            }
+        }
+    }
+    // ---- window validity: inside one N-free segment of one record (sequences_splitter.rs:15-40)
+    for (uint32_t x = tid; x < WIN_T + 2; x += WIN_THREADS) {
+        const int64_t j = gfirst + x;
+        bool ok = j >= 0 && (uint64_t)j + (k - 1) <= (uint64_t)n;
+        if (ok) {
+            const uint32_t lbit = (uint32_t)(j - ((int64_t)BW0 << 5));
+            ok = !any_bits(s_bad, lbit, k - 1) && !any_bits(s_brk, lbit + 1, k - 2);
+        }
+        s_ok[x] = ok;
+    }
+    __syncthreads();
+
+    // ---- window minima by doubling over non-overlapping power-of-two pieces of w
+    constexpr int ROUNDS = (WIN_T + 1 + WIN_THREADS - 1) / WIN_THREADS;
+    uint64_t acc[ROUNDS];
+    {
+        const uint64_t *cur = s_v0;
+        uint64_t *nxt = s_a;
+        uint32_t off = 0;
+        bool have = false;
+        for (uint32_t b = 0; (1u << b) <= w; ++b) {
+            const uint32_t step = 1u << b;
+            if (w & step) {
+#pragma unroll
+                for (int r = 0; r < ROUNDS; r++) {
+                    const uint32_t x = tid + r * WIN_THREADS;
+                    if (x < WIN_T + 1) {
+                        const uint64_t v = cur[x + off];
+                        acc[r] = have ? comb(acc[r], v) : v;
+                    }
+                }
+                have = true;
+                off += step;
+            }
+            if ((step << 1) <= w) {
+                for (uint32_t i = tid; i < n_items; i += WIN_THREADS) {
+                    const uint64_t a = cur[i];
+                    nxt[i] = (i + step < n_items) ? comb(a, cur[i + step]) : a;
+                }
+                __syncthreads();
+                cur = nxt;
+                nxt = (nxt == s_a) ? s_b : s_a;
+            }
+        }
+    }
+    // publish M in s_a/s_b-independent storage: reuse s_b? levels may still be read -> sync first
+    __syncthreads();
+    uint64_t *s_M = s_a;  // all level reads are done
+#pragma unroll
+    for (int r = 0; r < ROUNDS; r++) {
+        const uint32_t x = tid + r * WIN_THREADS;
+        if (x < WIN_T + 1) s_M[x] = acc[r];
+    }
+    __syncthreads();
+
+    // ---- split / segment-end detection and in-order compaction
+    uint32_t base_cnt = 0;  // packed running counts: entries (low 16) | S entries (high 16)
+    for (int r = 0; r < WIN_T / WIN_THREADS; r++) {
+        const uint32_t x = 1 + r * WIN_THREADS + tid;  // tile window x-1
+        const bool okj = s_ok[x], okp = s_ok[x - 1], okn = s_ok[x + 1];
+        const bool valid = okj && (okp || okn);        // segment has >= 2 windows <=> length >= k
+        const bool first = okj && !okp;
+        const uint64_t M = s_M[x];
+        bool S = false, E = false;
+        if (valid) {
+            S = first || M != s_M[x - 1] || ((M & 1ull) && s_v0[x - 1] == M);
+            E = !okn;
+        }
+        const uint32_t mine = (S || E) ? (1u | (S ? 0x10000u : 0u)) : 0u;
+        uint32_t tot;
+        const uint32_t pre = block_exclusive_scan<WIN_THREADS>(mine, s_scan, &tot) + base_cnt;
+        if (mine) {
+            uint64_t e = (uint64_t)(x - 1) | (S ? ENT_S : 0) | (E ? ENT_E : 0) | (first ? ENT_FIRST : 0) |
+                         ((uint64_t)(pre >> 16) << ENT_SRANK_SHIFT);
+            s_ent[pre & 0xFFFFu] = e;
+        }
+        base_cnt += tot;
+    }
+    __syncthreads();
+    const uint32_t n_ent = base_cnt & 0xFFFFu, n_s = base_cnt >> 16;
+
+    // ---- per super-k-mer: locate the minimizer, derive bucket / orientation
+    // (assembler_minimizer_bucketing/src/lib.rs:218-238)
+    for (uint32_t i = tid; i < n_ent; i += WIN_THREADS) {
+        uint64_t e = s_ent[i];
+        if (e & ENT_S) {
+            const uint32_t x = (uint32_t)(e & ((1u << ENT_POS_BITS) - 1)) + 1;
+            const uint64_t M = s_M[x];
+            uint32_t bucket, rcf = 0, arg = 0;
+            if ((M & 1ull) == 0) {
+                bucket = 1u << P.b1;  // duplicates bucket
+                e |= ENT_DUP;
+            } else {
+                for (uint32_t q = 0; q < w; q++)
+                    if (s_v0[x + q] == M) { arg = q; break; }
+                rcf = (!P.forward_only && !s_fwd[x + arg]) ? 1u : 0u;
+                bucket = (uint32_t)(M >> 1) & ((1u << P.b1) - 1);   // cn_nthash.rs:135-142 get_bucket(0, b1, M)
+            }
+            const uint32_t second = (uint32_t)(M >> (P.b1 + 1)) & ((1u << P.b2) - 1);
+            e |= (rcf ? ENT_RC : 0) | ((uint64_t)second << ENT_SECOND_SHIFT) | ((uint64_t)bucket << ENT_BUCKET_SHIFT) |
+                 ((uint64_t)arg << ENT_ARG_SHIFT);
+        }
+        ent[(uint64_t)tile * WIN_T + i] = e;
+    }
+    if (tid == 0) { tile_cnt[tile] = n_ent; tile_scnt[tile] = n_s; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Single-CTA exclusive scan of a u32 array (n up to a few million); out may alias in.
+// total (u64) written to *total_out.  Used for per-tile and per-unit offsets.
+__global__ void __launch_bounds__(1024) k_exclusive_scan_u32(const uint32_t *in, uint32_t *out, uint32_t n,
+                                                             unsigned long long *total_out) {
+    __shared__ uint32_t s_scan[1024 / 32 + 2];
+    constexpr uint32_t IPT = 8;
+    uint64_t running = 0;
+    for (uint32_t base = 0; base < n; base += 1024 * IPT) {
+        uint32_t v[IPT];
+        uint32_t sum = 0;
+        const uint32_t i0 = base + threadIdx.x * IPT;
+#pragma unroll
+        for (uint32_t q = 0; q < IPT; q++) { v[q] = (i0 + q < n) ? in[i0 + q] : 0u; sum += v[q]; }
+        uint32_t tot;
+        uint32_t pre = block_exclusive_scan<1024>(sum, s_scan, &tot);
+        uint64_t p = running + pre;
+#pragma unroll
+        for (uint32_t q = 0; q < IPT; q++) {
+            if (i0 + q < n) out[i0 + q] = (uint32_t)p;
+            p += v[q];
+        }
+        running += tot;
+    }
+    if (threadIdx.x == 0) {
+        if (total_out) *total_out = running;
+        out[n] = (uint32_t)running;  // arrays carry one extra slot
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_emit: entry -> super-k-mer descriptor in position order + per-unit histogram.
+// tmp descriptor: {start, len, meta, unit}.
+__global__ void __launch_bounds__(256)
+k_emit(const uint64_t *__restrict__ ent, const uint32_t *__restrict__ tile_cnt, const uint32_t *__restrict__ tile_sbase,
+       uint32_t n_tiles, DevParams P, uint4 *__restrict__ tmp, uint32_t *__restrict__ tmp_color,
+       const uint64_t *__restrict__ offsets, uint64_t n_reads, uint64_t off0, const uint32_t *__restrict__ colors,
+       uint32_t *__restrict__ unit_cnt, uint32_t *__restrict__ unit_words, uint32_t *__restrict__ unit_kmers) {
+    const uint32_t tile = blockIdx.x;
+    const uint32_t cnt = tile_cnt[tile];
+    const uint32_t posmask = (1u << ENT_POS_BITS) - 1;
+    for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) {
+        const uint64_t e = ent[(uint64_t)tile * WIN_T + i];
+        if (!(e & ENT_S)) continue;
+        const uint32_t pos = tile * WIN_T + (uint32_t)(e & posmask);
+        const bool first = e & ENT_FIRST;
+        uint32_t end;
+        bool last;
+        if (e & ENT_E) {
+            end = pos + P.k - 1; last = true;
+        } else {
+            uint64_t ne;
+            uint32_t t2 = tile;
+            if (i + 1 < cnt) ne = ent[(uint64_t)tile * WIN_T + i + 1];
+            else {
+                do { ++t2; } while (t2 < n_tiles && tile_cnt[t2] == 0);
+                ne = t2 < n_tiles ? ent[(uint64_t)t2 * WIN_T] : (ENT_E);  // unreachable fallback
+            }
+            const uint32_t npos = t2 * WIN_T + (uint32_t)(ne & posmask);
+            end = npos + P.k - 1;
+            last = !(ne & ENT_S);
+        }
+        const uint32_t start = first ? pos : pos - 1;
+        const uint32_t len = end - start;
+        const uint32_t rc = (e & ENT_RC) ? 1u : 0u;
+        const uint32_t arg = pos + (uint32_t)((e >> ENT_ARG_SHIFT) & 0xFFu);  // global m-mer position
+        uint32_t mpos = 0;
+        if (!(e & ENT_DUP)) mpos = rc ? (end - arg - P.m) : (arg - start);
+        const uint32_t flags = ((first ? 1u : 0u) << rc) | ((last ? 1u : 0u) << (rc ^ 1u));
+        const uint32_t second = (uint32_t)(e >> ENT_SECOND_SHIFT) & 0xFFu;
+        const uint32_t bucket = (uint32_t)(e >> ENT_BUCKET_SHIFT) & 0x3FFFu;
+        const uint32_t unit = (bucket << P.b2) | second;
+        const uint32_t idx = tile_sbase[tile] + (uint32_t)((e >> ENT_SRANK_SHIFT) & 0xFFFFu);
+        tmp[idx] = make_uint4(start, len, make_meta(mpos, flags, rc, second), unit);
+        if (P.colors) {
+            // record index = last r with offsets[r] <= start
+            uint64_t lo = 0, hi = n_reads;
+            while (hi - lo > 1) {
+                const uint64_t mid = (lo + hi) >> 1;
+                if (offsets[mid] - off0 <= start) lo = mid; else hi = mid;
+            }
+            tmp_color[idx] = colors ? colors[lo] : 0u;
+        }
+        atomicAdd(&unit_cnt[unit], 1u);
+        atomicAdd(&unit_words[unit], (len + 15u) >> 4);
+        atomicAdd(&unit_kmers[unit], len - P.k + 1u);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_scatter: one thread per super-k-mer.  Reserves a slot in its unit (atomic cursor), writes the
+// final descriptor {payload word offset, len, meta, colour} and the payload in stored orientation
+// (crates/io/src/concurrent/temp_reads/creads_utils.rs:389-406: rc => reverse-complement packing).
+__global__ void __launch_bounds__(256)
+k_scatter(const uint4 *__restrict__ tmp, const uint32_t *__restrict__ tmp_color, uint32_t n_sk,
+          const uint32_t *__restrict__ pk, uint32_t *__restrict__ cur_cnt, uint32_t *__restrict__ cur_words,
+          uint4 *__restrict__ desc, uint32_t *__restrict__ payload, uint32_t with_color) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_sk) return;
+    const uint4 t = tmp[i];
+    const uint32_t start = t.x, len = t.y, meta = t.z, unit = t.w;
+    const uint32_t nw = (len + 15u) >> 4;
+    const uint32_t slot = atomicAdd(&cur_cnt[unit], 1u);
+    const uint32_t woff = atomicAdd(&cur_words[unit], nw);
+    desc[slot] = make_uint4(woff, len, meta, with_color ? tmp_color[i] : 0u);
+    const bool rc = (meta >> 18) & 1u;
+    uint32_t *dst = payload + woff;
+    const uint32_t tail = len & 15u;
+    if (!rc) {
+        for (uint32_t q = 0; q < nw; q++) {
+            uint32_t v = extract32(pk, 2ull * (start + 16u * q));
+            if (q == nw - 1 && tail) v &= (1u << (2 * tail)) - 1u;
+            dst[q] = v;
+        }
+    } else {
+        for (uint32_t q = 0; q < nw; q++) {
+            // stored bases [16q, 16q+16) = complement of original bases start+len-1-16q downwards
+            const int64_t p = (int64_t)start + (int64_t)len - 16 * ((int64_t)q + 1);
+            uint32_t v;
+            if (p >= (int64_t)start) v = revcomp32(extract32(pk, 2ull * (uint64_t)p));
+            else {
+                v = revcomp32(extract32(pk, 2ull * start)) >> (2u * (uint32_t)((int64_t)start - p));
+                v &= (1u << (2 * tail)) - 1u;
+            }
+            dst[q] = v;
+        }
+    }
+}
+
+}  // namespace ggb

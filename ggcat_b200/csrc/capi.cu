@@ -1,0 +1,764 @@
+// capi.cu -- C ABI (include/ggcat_b200.h) over the phase-1 / phase-2 kernels.
+// Host orchestration only: buffers, launches, chunk bookkeeping.  No CPU compute path exists;
+// every entry point fails with GGCAT_B200_ERR_CUDA when no device is usable.
+#include "../../include/ggcat_b200.h"
+#include "merge.cuh"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace ggb;
+
+static thread_local std::string g_err;
+static int32_t set_err(int32_t code, const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define CU(call)                                                                                              \
+    do {                                                                                                      \
+        cudaError_t e__ = (call);                                                                             \
+        if (e__ != cudaSuccess)                                                                               \
+            return set_err(GGCAT_B200_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, \
+                           __LINE__);                                                                         \
+    } while (0)
+#define TRY(call)                   \
+    do {                            \
+        int32_t r__ = (call);       \
+        if (r__ != 0) return r__;   \
+    } while (0)
+
+namespace {
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+struct Chunk {
+    bool imported = false;
+    DevBuf desc, payload, unit_cnt, unit_off, unit_words, unit_woff, unit_kmers;  // owned (local chunks)
+    const uint4 *d_desc = nullptr;          // views used by kernels
+    const uint32_t *d_payload = nullptr;
+    const uint32_t *d_unit_cnt = nullptr, *d_unit_off = nullptr, *d_unit_words = nullptr, *d_unit_woff = nullptr,
+                   *d_unit_kmers = nullptr;
+    uint32_t first_unit = 0, n_units = 0, word_bias = 0;
+    uint64_t n_sk = 0, n_words = 0, n_kmers = 0, n_bases = 0;
+    std::vector<uint32_t> h_cnt, h_off, h_words, h_woff, h_kmers;  // host mirrors (after finish / import)
+    void release() {
+        desc.release(); payload.release(); unit_cnt.release(); unit_off.release(); unit_words.release();
+        unit_woff.release(); unit_kmers.release();
+    }
+};
+
+enum Family { F_PACK = 0, F_WINDOWS, F_EMIT, F_SCATTER, F_SCAN, F_MERGE_SMEM, F_MERGE_GLOBAL, F_GATHER, F_COUNT };
+static const char *kFamilyNames[F_COUNT] = {"k_pack+k_mark", "k_windows", "k_emit", "k_scatter", "k_exclusive_scan_u32",
+                                            "k_merge_units<smem>", "k_merge_units<global>", "k_gather_units"};
+
+struct TimedLaunch { int fam; cudaEvent_t a, b; };
+
+struct HostTable {
+    uint64_t *keys = nullptr; uint32_t *cf = nullptr; uint64_t *unit_offsets = nullptr;
+    size_t cap_entries = 0, cap_units = 0;
+};
+
+}  // namespace
+
+struct ggcat_b200_ctx {
+    ggcat_b200_params params;
+    DevParams P;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int sm_count = 148;
+    uint64_t max_batch = 1ull << 30;
+    bool finished = false;
+    bool timing = false;
+    ggcat_b200_bucket_stats stats;
+    // phase-1 workspace
+    DevBuf d_ascii, d_offsets, d_colors, pk, bad, brk, ent, tile_cnt, tile_sbase, tmp, tmp_color, cur_cnt, cur_words, totals;
+    std::vector<Chunk *> chunks;
+    // phase-2 workspace
+    DevBuf d_views, d_work[3], d_scratch, d_scratch_off, out_keys, out_cf, out_keys2, out_cf2, cursor, unit_out_off,
+        unit_out_cnt, unit_final_off, overflow;
+    unsigned long long *h_pinned = nullptr;  // small pinned staging (16 u64)
+    std::vector<TimedLaunch> launches;
+    std::vector<cudaEvent_t> event_pool;
+    float fam_ms[F_COUNT];
+    uint32_t fam_launches[F_COUNT];
+    std::vector<HostTable *> free_tables;
+    uint64_t last_entries = 0;
+};
+
+namespace {
+
+struct LaunchTimer {
+    ggcat_b200_ctx *c; int fam; cudaEvent_t a = nullptr, b = nullptr;
+    LaunchTimer(ggcat_b200_ctx *ctx, int f) : c(ctx), fam(f) {
+        c->fam_launches[fam]++;
+        if (!c->timing) return;
+        auto get = [&]() { cudaEvent_t e; if (!c->event_pool.empty()) { e = c->event_pool.back(); c->event_pool.pop_back(); } else cudaEventCreate(&e); return e; };
+        a = get(); b = get();
+        cudaEventRecord(a, c->stream);
+    }
+    ~LaunchTimer() {
+        if (!c->timing) return;
+        cudaEventRecord(b, c->stream);
+        c->launches.push_back({fam, a, b});
+    }
+};
+
+void collect_timings(ggcat_b200_ctx *c) {
+    if (c->launches.empty()) return;
+    cudaStreamSynchronize(c->stream);
+    for (auto &l : c->launches) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, l.a, l.b);
+        c->fam_ms[l.fam] += ms;
+        c->event_pool.push_back(l.a);
+        c->event_pool.push_back(l.b);
+    }
+    c->launches.clear();
+}
+
+uint32_t best_m(uint32_t k) {  // crates/utils/src/lib.rs:29-40 compute_best_m
+    if (k <= 13) return std::max(k / 2, k >= 4 ? k - 4 : 0u);
+    if (k <= 15) return 9;
+    if (k <= 21) return 10;
+    if (k <= 30) return 11;
+    if (k <= 37) return 12;
+    if (k <= 42) return 13;
+    if (k <= 64) return 14;
+    return (uint32_t)((double)k / 4.0 + 0.5);
+}
+
+int32_t check_ctx(ggcat_b200_ctx *c) {
+    if (!c) return set_err(GGCAT_B200_ERR_INVALID, "null context");
+    cudaError_t e = cudaSetDevice(c->device);
+    if (e != cudaSuccess) return set_err(GGCAT_B200_ERR_CUDA, "cudaSetDevice(%d): %s", c->device, cudaGetErrorString(e));
+    return 0;
+}
+
+// One batch of <= max_batch bases, inputs already on the device.
+int32_t bucket_batch_device(ggcat_b200_ctx *c, const uint8_t *d_data, const uint64_t *d_offsets, uint64_t n_reads,
+                            uint64_t off0, uint64_t n, const uint32_t *d_colors) {
+    const DevParams &P = c->P;
+    cudaStream_t st = c->stream;
+    if (n >= (1ull << 31)) return set_err(GGCAT_B200_ERR_INVALID, "batch of %llu bases exceeds 2^31", (unsigned long long)n);
+    c->stats.total_bases += n;
+    if (n < P.k) return 0;
+    const uint32_t n_tiles = (uint32_t)((n + WIN_T - 1) / WIN_T);
+    const uint64_t padded = (uint64_t)n_tiles * WIN_T + 4 * WIN_WMAX + 256;
+    const uint64_t n_groups = (padded + 31) / 32;  // 32-base groups incl. padding
+    CU(c->pk.reserve((2 * n_groups + 8) * 4));
+    CU(c->bad.reserve((n_groups + 8) * 4));
+    CU(c->brk.reserve((n_groups + 8) * 4));
+    CU(cudaMemsetAsync(c->brk.p, 0, (n_groups + 8) * 4, st));
+    CU(cudaMemsetAsync(c->pk.as<uint32_t>() + 2 * n_groups, 0, 8 * 4, st));
+    CU(cudaMemsetAsync(c->bad.as<uint32_t>() + n_groups, 0xFF, 8 * 4, st));
+    {
+        LaunchTimer t(c, F_PACK);
+        const int aligned = ((uintptr_t)d_data & 15) == 0;
+        k_pack<<<(unsigned)((n_groups + 255) / 256), 256, 0, st>>>(d_data, n, c->pk.as<uint32_t>(), c->bad.as<uint32_t>(),
+                                                                   n_groups, aligned);
+        k_mark<<<(unsigned)((n_reads + 255) / 256), 256, 0, st>>>(d_offsets, n_reads, off0, n, c->brk.as<uint32_t>());
+    }
+    CU(c->ent.reserve((uint64_t)n_tiles * WIN_T * 8));
+    CU(c->tile_cnt.reserve(((uint64_t)n_tiles + 2) * 4));
+    CU(c->tile_sbase.reserve(((uint64_t)n_tiles + 2) * 4));
+    {
+        LaunchTimer t(c, F_WINDOWS);
+        k_windows<<<n_tiles, WIN_THREADS, 0, st>>>(c->pk.as<uint32_t>(), c->bad.as<uint32_t>(), c->brk.as<uint32_t>(),
+                                                   (uint32_t)n, P, c->ent.as<uint64_t>(), c->tile_cnt.as<uint32_t>(),
+                                                   c->tile_sbase.as<uint32_t>());
+    }
+    CU(c->totals.reserve(8 * 8));
+    {
+        LaunchTimer t(c, F_SCAN);
+        k_exclusive_scan_u32<<<1, 1024, 0, st>>>(c->tile_sbase.as<uint32_t>(), c->tile_sbase.as<uint32_t>(), n_tiles,
+                                                 c->totals.as<unsigned long long>());
+    }
+    CU(cudaMemcpyAsync(c->h_pinned, c->totals.p, 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    const uint64_t n_sk = c->h_pinned[0];
+    if (n_sk == 0) return 0;
+    if (n_sk >= (1ull << 32)) return set_err(GGCAT_B200_ERR_INVALID, "too many super-k-mers in one batch");
+
+    Chunk *ch = new Chunk();
+    c->chunks.push_back(ch);
+    ch->first_unit = 0; ch->n_units = P.n_units; ch->n_sk = n_sk; ch->n_bases = n;
+    const size_t ub = ((size_t)P.n_units + 2) * 4;
+    CU(ch->unit_cnt.reserve(ub)); CU(ch->unit_off.reserve(ub)); CU(ch->unit_words.reserve(ub));
+    CU(ch->unit_woff.reserve(ub)); CU(ch->unit_kmers.reserve(ub));
+    CU(cudaMemsetAsync(ch->unit_cnt.p, 0, ub, st));
+    CU(cudaMemsetAsync(ch->unit_words.p, 0, ub, st));
+    CU(cudaMemsetAsync(ch->unit_kmers.p, 0, ub, st));
+    CU(c->tmp.reserve(n_sk * 16));
+    if (P.colors) CU(c->tmp_color.reserve(n_sk * 4));
+    {
+        LaunchTimer t(c, F_EMIT);
+        k_emit<<<n_tiles, 256, 0, st>>>(c->ent.as<uint64_t>(), c->tile_cnt.as<uint32_t>(), c->tile_sbase.as<uint32_t>(),
+                                        n_tiles, P, c->tmp.as<uint4>(), c->tmp_color.as<uint32_t>(), d_offsets, n_reads, off0,
+                                        d_colors, ch->unit_cnt.as<uint32_t>(), ch->unit_words.as<uint32_t>(),
+                                        ch->unit_kmers.as<uint32_t>());
+    }
+    {
+        LaunchTimer t(c, F_SCAN);
+        k_exclusive_scan_u32<<<1, 1024, 0, st>>>(ch->unit_cnt.as<uint32_t>(), ch->unit_off.as<uint32_t>(), P.n_units,
+                                                 c->totals.as<unsigned long long>() + 1);
+        k_exclusive_scan_u32<<<1, 1024, 0, st>>>(ch->unit_words.as<uint32_t>(), ch->unit_woff.as<uint32_t>(), P.n_units,
+                                                 c->totals.as<unsigned long long>() + 2);
+    }
+    // payload bound: sum ceil(len/16) <= (bases covered)/16 + n_sk, bases covered <= n + n_sk*(k-1)
+    const uint64_t words_bound = (n + n_sk * (uint64_t)(P.k - 1)) / 16 + n_sk + 8;
+    if (words_bound >= (1ull << 32)) return set_err(GGCAT_B200_ERR_INVALID, "payload of one batch exceeds 2^32 words");
+    CU(ch->desc.reserve(n_sk * 16));
+    CU(ch->payload.reserve(words_bound * 4));
+    CU(c->cur_cnt.reserve(ub)); CU(c->cur_words.reserve(ub));
+    CU(cudaMemcpyAsync(c->cur_cnt.p, ch->unit_off.p, ub, cudaMemcpyDeviceToDevice, st));
+    CU(cudaMemcpyAsync(c->cur_words.p, ch->unit_woff.p, ub, cudaMemcpyDeviceToDevice, st));
+    {
+        LaunchTimer t(c, F_SCATTER);
+        k_scatter<<<(unsigned)((n_sk + 255) / 256), 256, 0, st>>>(c->tmp.as<uint4>(), c->tmp_color.as<uint32_t>(), (uint32_t)n_sk,
+                                                                  c->pk.as<uint32_t>(), c->cur_cnt.as<uint32_t>(),
+                                                                  c->cur_words.as<uint32_t>(), ch->desc.as<uint4>(),
+                                                                  ch->payload.as<uint32_t>(), P.colors);
+    }
+    ch->d_desc = ch->desc.as<uint4>(); ch->d_payload = ch->payload.as<uint32_t>();
+    ch->d_unit_cnt = ch->unit_cnt.as<uint32_t>(); ch->d_unit_off = ch->unit_off.as<uint32_t>();
+    ch->d_unit_words = ch->unit_words.as<uint32_t>(); ch->d_unit_woff = ch->unit_woff.as<uint32_t>();
+    ch->d_unit_kmers = ch->unit_kmers.as<uint32_t>();
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int32_t mirror_chunk(ggcat_b200_ctx *c, Chunk *ch) {
+    if (!ch->h_cnt.empty()) return 0;
+    const size_t nu = ch->n_units;
+    ch->h_cnt.resize(nu + 1); ch->h_off.resize(nu + 1); ch->h_words.resize(nu + 1); ch->h_woff.resize(nu + 1);
+    ch->h_kmers.resize(nu + 1);
+    CU(cudaMemcpyAsync(ch->h_cnt.data(), ch->d_unit_cnt, nu * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(ch->h_words.data(), ch->d_unit_words, nu * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(ch->h_kmers.data(), ch->d_unit_kmers, nu * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    uint64_t a = 0, b = 0, km = 0;
+    for (size_t u = 0; u < nu; u++) {
+        ch->h_off[u] = (uint32_t)a; ch->h_woff[u] = (uint32_t)b;
+        a += ch->h_cnt[u]; b += ch->h_words[u]; km += ch->h_kmers[u];
+    }
+    ch->h_off[nu] = (uint32_t)a; ch->h_woff[nu] = (uint32_t)b;
+    ch->n_sk = a; ch->n_words = b; ch->n_kmers = km;
+    return 0;
+}
+
+__global__ void k_gather_units(const uint64_t *__restrict__ src_keys, const uint32_t *__restrict__ src_cf,
+                               const uint64_t *__restrict__ src_off, const uint32_t *__restrict__ cnt,
+                               const uint64_t *__restrict__ dst_off, uint64_t *__restrict__ dst_keys,
+                               uint32_t *__restrict__ dst_cf, uint32_t n_units) {
+    for (uint32_t u = blockIdx.x; u < n_units; u += gridDim.x) {
+        const uint32_t n = cnt[u];
+        const uint64_t s = src_off[u], d = dst_off[u];
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+            dst_keys[d + i] = src_keys[s + i];
+            dst_cf[d + i] = src_cf[s + i];
+        }
+    }
+}
+
+// exclusive scan u32 counts -> u64 offsets (n_units small: single CTA, sequential per thread chunks)
+__global__ void __launch_bounds__(1024) k_scan_counts_u64(const uint32_t *cnt, uint64_t *off, uint32_t n) {
+    __shared__ uint32_t s_scan[1024 / 32 + 2];
+    uint64_t running = 0;
+    for (uint32_t base = 0; base < n; base += 1024) {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t v = i < n ? cnt[i] : 0u;
+        uint32_t tot;
+        const uint32_t p = block_exclusive_scan<1024>(v, s_scan, &tot);
+        if (i < n) off[i] = running + p;
+        running += tot;
+    }
+    if (threadIdx.x == 0) off[n] = running;
+}
+
+constexpr int SM_THREADS_S = 512, SM_CAP_S = 6144;     // 2 CTAs / SM
+constexpr int SM_THREADS_L = 1024, SM_CAP_L = 12288;   // 1 CTA / SM
+constexpr int GL_THREADS = 1024;
+
+int32_t merge_range_device(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_buckets, uint64_t *n_entries,
+                           uint64_t *unique, uint64_t *total) {
+    const DevParams &P = c->P;
+    cudaStream_t st = c->stream;
+    if (!c->finished) return set_err(GGCAT_B200_ERR_STATE, "merge before finish_bucketing");
+    const uint32_t nb_total = (1u << P.b1) + 1;
+    if (n_buckets == 0 || first_bucket >= nb_total || first_bucket + n_buckets > nb_total)
+        return set_err(GGCAT_B200_ERR_INVALID, "bucket range [%u,+%u) outside 0..%u", first_bucket, n_buckets, nb_total);
+    const uint32_t u0 = first_bucket << P.b2, nu = n_buckets << P.b2;
+    // classify units by record count
+    std::vector<uint32_t> work[3];
+    std::vector<uint64_t> scratch_off;
+    uint64_t tot_kmers = 0, scratch_total = 0;
+    for (uint32_t u = u0; u < u0 + nu; u++) {
+        uint64_t n = 0;
+        for (Chunk *ch : c->chunks)
+            if (u >= ch->first_unit && u < ch->first_unit + ch->n_units) n += ch->h_kmers[u - ch->first_unit];
+        if (n == 0) continue;
+        if (n >= (1ull << 31)) return set_err(GGCAT_B200_ERR_INVALID, "unit %u holds %llu k-mers (> 2^31)", u, (unsigned long long)n);
+        tot_kmers += n;
+        if (n <= SM_CAP_S) work[0].push_back(u);
+        else if (n <= SM_CAP_L) work[1].push_back(u);
+        else { work[2].push_back(u); scratch_off.push_back(scratch_total); scratch_total += 2 * n; }
+    }
+    // chunk views
+    std::vector<ChunkView> views;
+    for (Chunk *ch : c->chunks) {
+        ChunkView v;
+        v.desc = ch->d_desc; v.payload = ch->d_payload; v.unit_off = ch->d_unit_off; v.unit_kmers = ch->d_unit_kmers;
+        v.first_unit = ch->first_unit; v.n_units = ch->n_units; v.word_bias = ch->word_bias; v.pad = 0;
+        views.push_back(v);
+    }
+    CU(c->d_views.reserve(std::max<size_t>(1, views.size()) * sizeof(ChunkView)));
+    if (!views.empty())
+        CU(cudaMemcpyAsync(c->d_views.p, views.data(), views.size() * sizeof(ChunkView), cudaMemcpyHostToDevice, st));
+    for (int q = 0; q < 3; q++) {
+        CU(c->d_work[q].reserve(std::max<size_t>(1, work[q].size()) * 4));
+        if (!work[q].empty())
+            CU(cudaMemcpyAsync(c->d_work[q].p, work[q].data(), work[q].size() * 4, cudaMemcpyHostToDevice, st));
+    }
+    CU(c->d_scratch.reserve(std::max<uint64_t>(1, scratch_total) * 8));
+    CU(c->d_scratch_off.reserve(std::max<size_t>(1, scratch_off.size()) * 8));
+    if (!scratch_off.empty())
+        CU(cudaMemcpyAsync(c->d_scratch_off.p, scratch_off.data(), scratch_off.size() * 8, cudaMemcpyHostToDevice, st));
+    const uint64_t cap = std::max<uint64_t>(tot_kmers, 1);
+    CU(c->out_keys.reserve(cap * 8)); CU(c->out_cf.reserve(cap * 4));
+    CU(c->cursor.reserve(64)); CU(c->overflow.reserve(16));
+    CU(c->unit_out_off.reserve(((size_t)nu + 1) * 8)); CU(c->unit_out_cnt.reserve(((size_t)nu + 1) * 4));
+    CU(c->unit_final_off.reserve(((size_t)nu + 1) * 8));
+    CU(cudaMemsetAsync(c->cursor.p, 0, 64, st));
+    CU(cudaMemsetAsync(c->overflow.p, 0, 16, st));
+    CU(cudaMemsetAsync(c->unit_out_off.p, 0, ((size_t)nu + 1) * 8, st));
+    CU(cudaMemsetAsync(c->unit_out_cnt.p, 0, ((size_t)nu + 1) * 4, st));
+    MergeOut out;
+    out.keys = c->out_keys.as<uint64_t>(); out.count_flags = c->out_cf.as<uint32_t>();
+    out.cursor = c->cursor.as<unsigned long long>(); out.unit_out_off = c->unit_out_off.as<uint64_t>();
+    out.unit_out_cnt = c->unit_out_cnt.as<uint32_t>(); out.capacity = cap; out.overflow = c->overflow.as<uint32_t>();
+    const ChunkView *dv = c->d_views.as<ChunkView>();
+    const uint32_t nch = (uint32_t)views.size();
+    if (!work[0].empty()) {
+        LaunchTimer t(c, F_MERGE_SMEM);
+        auto kern = k_merge_units<SM_THREADS_S, SM_CAP_S, false>;
+        const size_t smem = merge_smem_bytes<SM_THREADS_S, SM_CAP_S>(false);
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const unsigned grid = (unsigned)std::min<size_t>(work[0].size(), (size_t)c->sm_count * 2 * 8);
+        kern<<<grid, SM_THREADS_S, smem, st>>>(dv, nch, c->d_work[0].as<uint32_t>(), (uint32_t)work[0].size(), u0, P,
+                                               c->params.min_multiplicity, out, nullptr, nullptr);
+    }
+    if (!work[1].empty()) {
+        LaunchTimer t(c, F_MERGE_SMEM);
+        auto kern = k_merge_units<SM_THREADS_L, SM_CAP_L, false>;
+        const size_t smem = merge_smem_bytes<SM_THREADS_L, SM_CAP_L>(false);
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const unsigned grid = (unsigned)std::min<size_t>(work[1].size(), (size_t)c->sm_count * 8);
+        kern<<<grid, SM_THREADS_L, smem, st>>>(dv, nch, c->d_work[1].as<uint32_t>(), (uint32_t)work[1].size(), u0, P,
+                                               c->params.min_multiplicity, out, nullptr, nullptr);
+    }
+    if (!work[2].empty()) {
+        LaunchTimer t(c, F_MERGE_GLOBAL);
+        auto kern = k_merge_units<GL_THREADS, 0, true>;
+        const size_t smem = merge_smem_bytes<GL_THREADS, 0>(true);
+        const unsigned grid = (unsigned)std::min<size_t>(work[2].size(), (size_t)c->sm_count * 2);
+        kern<<<grid, GL_THREADS, smem, st>>>(dv, nch, c->d_work[2].as<uint32_t>(), (uint32_t)work[2].size(), u0, P,
+                                             c->params.min_multiplicity, out, c->d_scratch.as<uint64_t>(),
+                                             c->d_scratch_off.as<uint64_t>());
+    }
+    CU(cudaGetLastError());
+    // unit-ordered final layout
+    CU(c->out_keys2.reserve(cap * 8)); CU(c->out_cf2.reserve(cap * 4));
+    {
+        LaunchTimer t(c, F_GATHER);
+        k_scan_counts_u64<<<1, 1024, 0, st>>>(c->unit_out_cnt.as<uint32_t>(), c->unit_final_off.as<uint64_t>(), nu);
+        k_gather_units<<<(unsigned)std::min<uint32_t>(nu, (uint32_t)c->sm_count * 8), 128, 0, st>>>(
+            c->out_keys.as<uint64_t>(), c->out_cf.as<uint32_t>(), c->unit_out_off.as<uint64_t>(),
+            c->unit_out_cnt.as<uint32_t>(), c->unit_final_off.as<uint64_t>(), c->out_keys2.as<uint64_t>(),
+            c->out_cf2.as<uint32_t>(), nu);
+    }
+    CU(cudaMemcpyAsync(c->h_pinned, c->cursor.p, 24, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(c->h_pinned + 8, c->overflow.p, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    CU(cudaGetLastError());
+    const uint32_t ovf = (uint32_t)c->h_pinned[8];
+    if (ovf) return set_err(GGCAT_B200_ERR_CAPACITY, "merge output overflow (code %u)", ovf);
+    c->last_entries = c->h_pinned[0];
+    if (n_entries) *n_entries = c->h_pinned[0];
+    if (unique) *unique = c->h_pinned[1];
+    if (total) *total = c->h_pinned[2];
+    return 0;
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+const char *ggcat_b200_last_error(void) { return g_err.c_str(); }
+uint32_t ggcat_b200_abi_version(void) { return GGCAT_B200_ABI_VERSION; }
+uint32_t ggcat_b200_compute_best_m(uint32_t k) { return best_m(k); }
+
+void ggcat_b200_bucket_counts(uint64_t bases_count, uint32_t *buckets_log, uint32_t *second_log) {
+    // crates/io/src/lib.rs:75-89,113-128 with the thresholds of crates/config/src/lib.rs:62-90
+    auto next_pow2 = [](uint64_t x) { uint64_t p = 1; while (p < x) p <<= 1; return p; };
+    auto ilog2 = [](uint64_t x) { uint32_t l = 0; while (x >>= 1) l++; return l; };
+    uint64_t buckets = std::max<uint64_t>(std::min<uint64_t>(1ull << 10, bases_count / (512 * 1024)), bases_count / (1024ull * 1024 * 1024));
+    buckets = std::max<uint64_t>(std::min<uint64_t>(next_pow2(buckets), 1ull << 13), 1ull << 2);
+    const uint64_t per = bases_count / buckets;
+    uint64_t second = std::max<uint64_t>(std::min<uint64_t>(1ull << 6, per / (2 * 1024)), per / (4ull * 1024 * 1024));
+    second = std::max<uint64_t>(std::min<uint64_t>(next_pow2(second), 1ull << 8), 1ull << 1);
+    if (buckets_log) *buckets_log = ilog2(buckets);
+    if (second_log) *second_log = ilog2(second);
+}
+
+void *ggcat_b200_host_alloc(uint64_t bytes) {
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) { set_err(GGCAT_B200_ERR_CUDA, "cudaMallocHost(%llu) failed", (unsigned long long)bytes); return nullptr; }
+    return p;
+}
+void ggcat_b200_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+int32_t ggcat_b200_create(const ggcat_b200_params *params, ggcat_b200_ctx **out) {
+    if (!params || !out) return set_err(GGCAT_B200_ERR_INVALID, "null argument");
+    ggcat_b200_params p = *params;
+    if (p.m == 0) p.m = best_m(p.k);
+    if (p.hash_type == GGCAT_B200_HASH_AUTO) p.hash_type = p.k <= 64 ? GGCAT_B200_HASH_SEQ : GGCAT_B200_HASH_RK128;  // crates/api/src/utils.rs:17-26
+    if (p.k < 4 || p.k > 31) return set_err(GGCAT_B200_ERR_INVALID, "k=%u unsupported (4..31: 64-bit key path)", p.k);
+    if (p.hash_type != GGCAT_B200_HASH_SEQ) return set_err(GGCAT_B200_ERR_INVALID, "hash_type=%u unsupported in this build", p.hash_type);
+    if (p.m < 2 || p.m > 32 || p.m >= p.k) return set_err(GGCAT_B200_ERR_INVALID, "m=%u invalid for k=%u", p.m, p.k);
+    if (p.k - p.m < 2 || p.k - p.m > (uint32_t)WIN_WMAX) return set_err(GGCAT_B200_ERR_INVALID, "k-m=%u outside 2..%d", p.k - p.m, WIN_WMAX);
+    if (p.buckets_count_log > 13) return set_err(GGCAT_B200_ERR_INVALID, "buckets_count_log > 13");  // config MAX_BUCKETS_COUNT_LOG
+    if (p.second_buckets_count_log > 8) return set_err(GGCAT_B200_ERR_INVALID, "second_buckets_count_log > 8");
+    if (p.min_multiplicity == 0) p.min_multiplicity = 1;
+    if (p.colors) return set_err(GGCAT_B200_ERR_INVALID, "colors unsupported in this build");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return set_err(GGCAT_B200_ERR_CUDA, "no CUDA device: %s", e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    if (p.device < 0 || p.device >= ndev) return set_err(GGCAT_B200_ERR_INVALID, "device %d out of range (0..%d)", p.device, ndev - 1);
+    CU(cudaSetDevice(p.device));
+    ggcat_b200_ctx *c = new ggcat_b200_ctx();
+    c->params = p;
+    c->device = p.device;
+    c->P.k = p.k; c->P.m = p.m; c->P.w = p.k - p.m; c->P.b1 = p.buckets_count_log; c->P.b2 = p.second_buckets_count_log;
+    c->P.forward_only = p.forward_only ? 1 : 0; c->P.colors = p.colors ? 1 : 0;
+    c->P.n_units = ((1u << c->P.b1) + 1u) << c->P.b2;
+    memset(&c->stats, 0, sizeof(c->stats));
+    memset(c->fam_ms, 0, sizeof(c->fam_ms));
+    memset(c->fam_launches, 0, sizeof(c->fam_launches));
+    if (const char *mb = getenv("GGCAT_B200_MAX_BATCH")) { uint64_t v = strtoull(mb, nullptr, 10); if (v >= 1024) c->max_batch = std::min<uint64_t>(v, 1ull << 30); }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, p.device) == cudaSuccess) c->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaMallocHost((void **)&c->h_pinned, 16 * 8) != cudaSuccess) {
+        delete c;
+        return set_err(GGCAT_B200_ERR_CUDA, "stream / pinned allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    *out = c;
+    return 0;
+}
+
+int32_t ggcat_b200_reset(ggcat_b200_ctx *c) {
+    TRY(check_ctx(c));
+    cudaStreamSynchronize(c->stream);
+    for (Chunk *ch : c->chunks) { if (!ch->imported) ch->release(); else { ch->unit_off.release(); } delete ch; }
+    c->chunks.clear();
+    c->finished = false;
+    memset(&c->stats, 0, sizeof(c->stats));
+    return 0;
+}
+
+void ggcat_b200_destroy(ggcat_b200_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    ggcat_b200_reset(c);
+    collect_timings(c);
+    for (DevBuf *b : {&c->d_ascii, &c->d_offsets, &c->d_colors, &c->pk, &c->bad, &c->brk, &c->ent, &c->tile_cnt, &c->tile_sbase,
+                      &c->tmp, &c->tmp_color, &c->cur_cnt, &c->cur_words, &c->totals, &c->d_views, &c->d_work[0], &c->d_work[1],
+                      &c->d_work[2], &c->d_scratch, &c->d_scratch_off, &c->out_keys, &c->out_cf, &c->out_keys2, &c->out_cf2,
+                      &c->cursor, &c->unit_out_off, &c->unit_out_cnt, &c->unit_final_off, &c->overflow})
+        b->release();
+    for (cudaEvent_t e : c->event_pool) cudaEventDestroy(e);
+    for (HostTable *t : c->free_tables) { cudaFreeHost(t->keys); cudaFreeHost(t->cf); cudaFreeHost(t->unit_offsets); delete t; }
+    if (c->h_pinned) cudaFreeHost(c->h_pinned);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int32_t ggcat_b200_push_reads(ggcat_b200_ctx *c, const uint8_t *data, const uint64_t *offsets, uint64_t n_reads,
+                              const uint32_t *colors) {
+    TRY(check_ctx(c));
+    if (c->finished) return set_err(GGCAT_B200_ERR_STATE, "push_reads after finish_bucketing");
+    if (n_reads == 0) return 0;
+    if (!data || !offsets) return set_err(GGCAT_B200_ERR_INVALID, "null input");
+    if (colors && !c->P.colors) colors = nullptr;
+    uint64_t r0 = 0;
+    while (r0 < n_reads) {
+        // greedy batch of whole records, <= max_batch bases
+        uint64_t r1 = r0 + 1;
+        if (offsets[r1] - offsets[r0] > c->max_batch)
+            return set_err(GGCAT_B200_ERR_INVALID, "record %llu is longer than the batch limit %llu; split it with k-1 overlap "
+                           "(crates/io/src/sequences_reader.rs:162-173)", (unsigned long long)r0, (unsigned long long)c->max_batch);
+        {   // binary search for the last record that still fits
+            uint64_t lo = r1, hi = n_reads;
+            while (lo < hi) {
+                uint64_t mid = (lo + hi + 1) >> 1;
+                if (offsets[mid] - offsets[r0] <= c->max_batch) lo = mid; else hi = mid - 1;
+            }
+            r1 = lo;
+        }
+        const uint64_t nb = offsets[r1] - offsets[r0], nr = r1 - r0;
+        CU(c->d_ascii.reserve(nb + 64));
+        CU(c->d_offsets.reserve((nr + 1) * 8));
+        CU(cudaMemcpyAsync(c->d_ascii.p, data + offsets[r0], nb, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(c->d_offsets.p, offsets + r0, (nr + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+        const uint32_t *dcol = nullptr;
+        if (colors) {
+            CU(c->d_colors.reserve(nr * 4));
+            CU(cudaMemcpyAsync(c->d_colors.p, colors + r0, nr * 4, cudaMemcpyHostToDevice, c->stream));
+            dcol = c->d_colors.as<uint32_t>();
+        }
+        TRY(bucket_batch_device(c, c->d_ascii.as<uint8_t>(), c->d_offsets.as<uint64_t>(), nr, offsets[r0], nb, dcol));
+        r0 = r1;
+    }
+    return 0;
+}
+
+int32_t ggcat_b200_push_reads_device(ggcat_b200_ctx *c, const uint8_t *d_data, const uint64_t *d_offsets, uint64_t n_reads,
+                                     uint64_t n_bytes, const uint32_t *d_colors) {
+    TRY(check_ctx(c));
+    if (c->finished) return set_err(GGCAT_B200_ERR_STATE, "push_reads after finish_bucketing");
+    if (n_reads == 0) return 0;
+    if (!d_data || !d_offsets) return set_err(GGCAT_B200_ERR_INVALID, "null input");
+    if (n_bytes > c->max_batch) return set_err(GGCAT_B200_ERR_INVALID, "device batch of %llu bases exceeds limit %llu", (unsigned long long)n_bytes, (unsigned long long)c->max_batch);
+    return bucket_batch_device(c, d_data, d_offsets, n_reads, 0, n_bytes, c->P.colors ? d_colors : nullptr);
+}
+
+int32_t ggcat_b200_finish_bucketing(ggcat_b200_ctx *c, ggcat_b200_bucket_stats *stats) {
+    TRY(check_ctx(c));
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaGetLastError());
+    uint64_t sk = 0, km = 0, words = 0;
+    for (Chunk *ch : c->chunks) {
+        TRY(mirror_chunk(c, ch));
+        sk += ch->n_sk; km += ch->n_kmers; words += ch->n_words;
+    }
+    c->stats.n_superkmers = sk; c->stats.n_kmers = km; c->stats.payload_words = words;
+    c->stats.n_buckets = (1u << c->P.b1) + 1; c->stats.n_units = c->P.n_units;
+    // every k-mer occurrence is stored once, boundary k-mers once per side: valid bases follow
+    c->stats.valid_bases = 0;  // filled by callers that need it from per-chunk data (not tracked on device)
+    c->finished = true;
+    if (stats) *stats = c->stats;
+    return 0;
+}
+
+int32_t ggcat_b200_unit_sizes(ggcat_b200_ctx *c, uint64_t *n_superkmers, uint64_t *n_kmers) {
+    TRY(check_ctx(c));
+    if (!c->finished) return set_err(GGCAT_B200_ERR_STATE, "unit_sizes before finish_bucketing");
+    for (uint32_t u = 0; u < c->P.n_units; u++) {
+        uint64_t a = 0, b = 0;
+        for (Chunk *ch : c->chunks)
+            if (u >= ch->first_unit && u < ch->first_unit + ch->n_units) { a += ch->h_cnt[u - ch->first_unit]; b += ch->h_kmers[u - ch->first_unit]; }
+        if (n_superkmers) n_superkmers[u] = a;
+        if (n_kmers) n_kmers[u] = b;
+    }
+    return 0;
+}
+
+int32_t ggcat_b200_dump_superkmers(ggcat_b200_ctx *c, uint32_t bucket, ggcat_b200_superkmer *out, uint64_t cap, uint8_t *payload,
+                                   uint64_t payload_cap, uint64_t *n_out, uint64_t *payload_bytes) {
+    TRY(check_ctx(c));
+    if (!c->finished) return set_err(GGCAT_B200_ERR_STATE, "dump before finish_bucketing");
+    const DevParams &P = c->P;
+    if (bucket > (1u << P.b1)) return set_err(GGCAT_B200_ERR_INVALID, "bucket %u out of range", bucket);
+    const uint32_t u0 = bucket << P.b2, u1 = (bucket + 1) << P.b2;
+    uint64_t n = 0, words = 0;
+    for (Chunk *ch : c->chunks) {
+        const uint32_t a = std::max(u0, ch->first_unit), b = std::min(u1, ch->first_unit + ch->n_units);
+        if (a >= b) continue;
+        n += ch->h_off[b - ch->first_unit] - ch->h_off[a - ch->first_unit];
+        words += ch->h_woff[b - ch->first_unit] - ch->h_woff[a - ch->first_unit];
+    }
+    if (n_out) *n_out = n;
+    if (payload_bytes) *payload_bytes = words * 4;
+    if (!out) return 0;
+    if (cap < n || payload_cap < words * 4) return set_err(GGCAT_B200_ERR_CAPACITY, "dump buffers too small");
+    uint64_t oi = 0, pw = 0;
+    std::vector<uint4> hd;
+    for (Chunk *ch : c->chunks) {
+        const uint32_t a = std::max(u0, ch->first_unit), b = std::min(u1, ch->first_unit + ch->n_units);
+        if (a >= b) continue;
+        const uint32_t d0 = ch->h_off[a - ch->first_unit], d1 = ch->h_off[b - ch->first_unit];
+        const uint32_t w0 = ch->h_woff[a - ch->first_unit], w1 = ch->h_woff[b - ch->first_unit];
+        if (d1 == d0) continue;
+        hd.resize(d1 - d0);
+        CU(cudaMemcpyAsync(hd.data(), ch->d_desc + d0, (size_t)(d1 - d0) * 16, cudaMemcpyDeviceToHost, c->stream));
+        // local chunks: payload slice of these units starts at word w0 (+ bias 0); imported: payload pointer is the slice
+        const uint32_t *psrc = ch->d_payload + w0;
+        CU(cudaMemcpyAsync(payload + pw * 4, psrc, (size_t)(w1 - w0) * 4, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        // second bucket per descriptor from its unit
+        uint32_t u = a;
+        for (uint32_t i = 0; i < d1 - d0; i++) {
+            while (ch->h_off[u + 1 - ch->first_unit] <= d0 + i) ++u;
+            const uint4 d = hd[i];
+            ggcat_b200_superkmer &s = out[oi++];
+            const uint32_t rel = d.x - ch->word_bias;  // word index into d_payload
+            s.payload_offset = (pw + (rel - w0)) * 4;
+            s.len = d.y; s.color = d.w; s.bucket = (uint16_t)bucket; s.minimizer_pos = (uint16_t)(d.z & 0xFFFF);
+            s.second_bucket = (uint8_t)((d.z >> 19) & 0xFF); s.flags = (uint8_t)((d.z >> 16) & 3); s.rc = (uint8_t)((d.z >> 18) & 1);
+            s.pad = 0;
+            (void)u;
+        }
+        pw += w1 - w0;
+    }
+    return 0;
+}
+
+int32_t ggcat_b200_merge_bucket_range_device(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_buckets, uint64_t *n_entries,
+                                             uint64_t *unique_kmers, uint64_t *total_kmers) {
+    TRY(check_ctx(c));
+    return merge_range_device(c, first_bucket, n_buckets, n_entries, unique_kmers, total_kmers);
+}
+
+int32_t ggcat_b200_merge_bucket_range(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_buckets, ggcat_b200_table *out) {
+    TRY(check_ctx(c));
+    if (!out) return set_err(GGCAT_B200_ERR_INVALID, "null table");
+    memset(out, 0, sizeof(*out));
+    uint64_t ne = 0, uq = 0, tk = 0;
+    TRY(merge_range_device(c, first_bucket, n_buckets, &ne, &uq, &tk));
+    const uint32_t nu = n_buckets << c->P.b2;
+    HostTable *t = nullptr;
+    for (size_t i = 0; i < c->free_tables.size(); i++)
+        if (c->free_tables[i]->cap_entries >= ne && c->free_tables[i]->cap_units >= nu + 1) {
+            t = c->free_tables[i]; c->free_tables.erase(c->free_tables.begin() + i); break;
+        }
+    if (!t) {
+        t = new HostTable();
+        t->cap_entries = std::max<uint64_t>(ne + ne / 4, 1024); t->cap_units = nu + 1;
+        if (cudaMallocHost((void **)&t->keys, t->cap_entries * 8) != cudaSuccess ||
+            cudaMallocHost((void **)&t->cf, t->cap_entries * 4) != cudaSuccess ||
+            cudaMallocHost((void **)&t->unit_offsets, t->cap_units * 8) != cudaSuccess) {
+            return set_err(GGCAT_B200_ERR_CUDA, "pinned table allocation failed");
+        }
+    }
+    if (ne) {
+        CU(cudaMemcpyAsync(t->keys, c->out_keys2.p, ne * 8, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(t->cf, c->out_cf2.p, ne * 4, cudaMemcpyDeviceToHost, c->stream));
+    }
+    CU(cudaMemcpyAsync(t->unit_offsets, c->unit_final_off.p, ((size_t)nu + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    out->n_entries = ne; out->keys_lo = t->keys; out->keys_hi = nullptr; out->count_flags = t->cf;
+    out->first_unit = first_bucket << c->P.b2; out->n_units = nu; out->unit_offsets = t->unit_offsets;
+    out->color_offsets = nullptr; out->colors = nullptr; out->total_kmers = tk; out->unique_kmers = uq; out->opaque = t;
+    return 0;
+}
+
+int32_t ggcat_b200_release_table(ggcat_b200_ctx *c, ggcat_b200_table *table) {
+    if (!c || !table) return set_err(GGCAT_B200_ERR_INVALID, "null argument");
+    if (table->opaque) c->free_tables.push_back(reinterpret_cast<HostTable *>(table->opaque));
+    memset(table, 0, sizeof(*table));
+    return 0;
+}
+
+uint32_t ggcat_b200_n_chunks(ggcat_b200_ctx *c) { return c ? (uint32_t)c->chunks.size() : 0; }
+
+int32_t ggcat_b200_export_chunk_slice(ggcat_b200_ctx *c, uint32_t chunk, uint32_t first_unit, uint32_t n_units,
+                                      ggcat_b200_chunk_slice *out) {
+    TRY(check_ctx(c));
+    if (!c->finished) return set_err(GGCAT_B200_ERR_STATE, "export before finish_bucketing");
+    if (!out || chunk >= c->chunks.size()) return set_err(GGCAT_B200_ERR_INVALID, "bad chunk index");
+    Chunk *ch = c->chunks[chunk];
+    if (ch->imported) return set_err(GGCAT_B200_ERR_INVALID, "cannot export an imported chunk");
+    if (first_unit + n_units > ch->n_units) return set_err(GGCAT_B200_ERR_INVALID, "unit range outside chunk");
+    const uint32_t d0 = ch->h_off[first_unit], d1 = ch->h_off[first_unit + n_units];
+    const uint32_t w0 = ch->h_woff[first_unit], w1 = ch->h_woff[first_unit + n_units];
+    out->n_superkmers = d1 - d0; out->n_words = w1 - w0; out->word_bias = w0;
+    out->d_descriptors = ch->d_desc + d0; out->d_payload = ch->d_payload + w0;
+    out->d_unit_counts = ch->d_unit_cnt + first_unit; out->d_unit_words = ch->d_unit_words + first_unit;
+    out->d_unit_kmers = ch->d_unit_kmers + first_unit;
+    return 0;
+}
+
+int32_t ggcat_b200_import_chunk_slice(ggcat_b200_ctx *c, uint32_t first_unit, uint32_t n_units, const ggcat_b200_chunk_slice *s) {
+    TRY(check_ctx(c));
+    if (!s) return set_err(GGCAT_B200_ERR_INVALID, "null slice");
+    if (first_unit + n_units > c->P.n_units) return set_err(GGCAT_B200_ERR_INVALID, "unit range outside 0..%u", c->P.n_units);
+    if (s->n_superkmers == 0) return 0;
+    Chunk *ch = new Chunk();
+    ch->imported = true; ch->first_unit = first_unit; ch->n_units = n_units; ch->word_bias = (uint32_t)s->word_bias;
+    ch->d_desc = reinterpret_cast<const uint4 *>(s->d_descriptors); ch->d_payload = s->d_payload;
+    ch->d_unit_cnt = s->d_unit_counts; ch->d_unit_words = s->d_unit_words; ch->d_unit_kmers = s->d_unit_kmers;
+    cudaError_t e = ch->unit_off.reserve(((size_t)n_units + 2) * 4);
+    if (e != cudaSuccess) { delete ch; return set_err(GGCAT_B200_ERR_CUDA, "cudaMalloc: %s", cudaGetErrorString(e)); }
+    CU(c->totals.reserve(8 * 8));
+    k_exclusive_scan_u32<<<1, 1024, 0, c->stream>>>(s->d_unit_counts, ch->unit_off.as<uint32_t>(), n_units,
+                                                     c->totals.as<unsigned long long>() + 3);
+    ch->d_unit_off = ch->unit_off.as<uint32_t>();
+    c->chunks.push_back(ch);
+    TRY(mirror_chunk(c, ch));
+    // imported payload pointer already addresses the slice: word offsets inside it are (woff - word_bias)
+    return 0;
+}
+
+int32_t ggcat_b200_drop_local_chunks(ggcat_b200_ctx *c) {
+    TRY(check_ctx(c));
+    cudaStreamSynchronize(c->stream);
+    std::vector<Chunk *> keep;
+    for (Chunk *ch : c->chunks) {
+        if (ch->imported) keep.push_back(ch);
+        else { ch->release(); delete ch; }
+    }
+    c->chunks.swap(keep);
+    return 0;
+}
+
+void *ggcat_b200_stream(ggcat_b200_ctx *c) { return c ? (void *)c->stream : nullptr; }
+int32_t ggcat_b200_synchronize(ggcat_b200_ctx *c) {
+    TRY(check_ctx(c));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+int32_t ggcat_b200_set_timing(ggcat_b200_ctx *c, int32_t enabled) {
+    TRY(check_ctx(c));
+    collect_timings(c);
+    c->timing = enabled != 0;
+    return 0;
+}
+int32_t ggcat_b200_kernel_times(ggcat_b200_ctx *c, const char **names, float *ms, uint32_t *launches, uint32_t cap, int32_t reset) {
+    TRY(check_ctx(c));
+    collect_timings(c);
+    for (uint32_t i = 0; i < (uint32_t)F_COUNT && i < cap; i++) {
+        if (names) names[i] = kFamilyNames[i];
+        if (ms) ms[i] = c->fam_ms[i];
+        if (launches) launches[i] = c->fam_launches[i];
+    }
+    if (reset) { memset(c->fam_ms, 0, sizeof(c->fam_ms)); memset(c->fam_launches, 0, sizeof(c->fam_launches)); }
+    return F_COUNT;
+}
+
+}  // extern "C"

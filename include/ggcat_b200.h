@@ -1,0 +1,193 @@
+/*
+ * ggcat_b200.h -- C ABI of the B200-native k-mer counting front end for GGCAT.
+ *
+ * Drop-in boundary for the reference's phase 1 + phase 2:
+ *   phase 1  minimizer bucketing   replaces assembler_minimizer_bucketing::minimizer_bucketing()
+ *            (/root/reference/crates/assembler_minimizer_bucketing/src/lib.rs:279-340) and the
+ *            GenericMinimizerBucketing::do_bucketing engine it drives
+ *            (crates/minimizer_bucketing/src/lib.rs:543-685);
+ *   phase 2  per-bucket k-mer merge replaces assembler_kmers_merge::kmers_merge()
+ *            (crates/assembler_kmers_merge/src/lib.rs:159-284) up to the point where the
+ *            k-mer table (FxHashMap<hash, MapEntry>, crates/structs/src/map_entry.rs:5-85) is
+ *            complete, i.e. the input of HashMapUnitigsExtender::compute_unitigs
+ *            (crates/assembler_kmers_merge/src/unitigs_extender/hashmap.rs:442-601).
+ *
+ * Plain pointers and sizes only; no C++ or torch types.  All functions return 0 on success and a
+ * negative ggcat_b200_status on failure; ggcat_b200_last_error() gives the thread-local message.
+ * Nothing here falls back to the CPU: without a CUDA device every compute call fails with
+ * GGCAT_B200_ERR_CUDA.
+ */
+#ifndef GGCAT_B200_H
+#define GGCAT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GGCAT_B200_ABI_VERSION 1
+
+typedef enum {
+    GGCAT_B200_OK = 0,
+    GGCAT_B200_ERR_INVALID = -1,   /* bad argument / unsupported parameter combination */
+    GGCAT_B200_ERR_CUDA = -2,      /* CUDA runtime error (no device, OOM, launch failure) */
+    GGCAT_B200_ERR_STATE = -3,     /* call out of order (e.g. merge before finish_bucketing) */
+    GGCAT_B200_ERR_CAPACITY = -4   /* caller-provided buffer too small */
+} ggcat_b200_status;
+
+/* Same numeric values as the reference's HashType (crates/api/src/utils.rs:4-8). */
+typedef enum { GGCAT_B200_HASH_AUTO = 0, GGCAT_B200_HASH_SEQ = 1, GGCAT_B200_HASH_RK128 = 4 } ggcat_b200_hash_type;
+
+/* The knobs of `ggcat build` that reach the hot path (crates/cmdline/src/main.rs:148-242,
+ * crates/api/src/lib.rs:75-99): -k, --minimizer-length, -s, -b, -f, -w, -c. */
+typedef struct {
+    uint32_t k;                        /* k-mer length, 4 <= k <= 63 this round */
+    uint32_t m;                        /* minimizer length, 0 = compute_best_m(k) (crates/utils/src/lib.rs:29-40) */
+    uint32_t min_multiplicity;         /* -s */
+    uint32_t buckets_count_log;        /* first-level buckets = 1 << this (+1 duplicates bucket) */
+    uint32_t second_buckets_count_log; /* sub-buckets per bucket = 1 << this (<= 8) */
+    uint32_t forward_only;             /* -f */
+    uint32_t hash_type;                /* ggcat_b200_hash_type */
+    uint32_t colors;                   /* -c : carry a colour id per record */
+    int32_t device;                    /* CUDA device ordinal */
+    uint32_t reserved[7];
+} ggcat_b200_params;
+
+typedef struct ggcat_b200_ctx ggcat_b200_ctx;
+
+/* Counters of the same meaning as the reference's GroupProcessStats / phase-1 counters
+ * (crates/kmers_transform/src/lib.rs:77-82; crates/minimizer_bucketing/src/lib.rs:402-434). */
+typedef struct {
+    uint64_t total_bases;      /* bytes pushed */
+    uint64_t valid_bases;      /* bases inside N-free segments of length >= k */
+    uint64_t n_superkmers;
+    uint64_t n_kmers;          /* k-mer occurrences stored in buckets (boundary copies counted twice) */
+    uint64_t payload_words;    /* 32-bit words of packed super-k-mer payload */
+    uint32_t n_buckets;        /* (1 << buckets_count_log) + 1 */
+    uint32_t n_units;          /* n_buckets << second_buckets_count_log */
+} ggcat_b200_bucket_stats;
+
+/* One stored super-k-mer = the reference's PushSequenceInfo / CompressedReadsBucketData
+ * (crates/minimizer_bucketing/src/lib.rs:105-114; crates/io/src/concurrent/temp_reads/creads_utils.rs:80-86). */
+typedef struct {
+    uint64_t payload_offset;   /* byte offset of the packed bases in the payload buffer (4-byte aligned) */
+    uint32_t len;              /* bases; packed 4 per byte, stored orientation (rc already applied) */
+    uint32_t color;
+    uint16_t bucket;
+    uint16_t minimizer_pos;
+    uint8_t second_bucket;
+    uint8_t flags;             /* READ_FLAG_INCL_BEGIN=1 | READ_FLAG_INCL_END=2 (crates/config/src/lib.rs:93-94) */
+    uint8_t rc;
+    uint8_t pad;
+} ggcat_b200_superkmer;
+
+/* k-mer table of a range of buckets: what HashMapUnitigsExtender holds after add_sequence().
+ * Entries are grouped by merge unit (bucket, second_bucket) and sorted ascending by key inside a
+ * unit.  Only entries with multiplicity >= min_multiplicity are present.
+ *   count_flags = multiplicity (low 30 bits, saturating) | MapEntry flags << 30.
+ * All pointers are library-owned pinned host memory, valid until ggcat_b200_release_table(). */
+typedef struct {
+    uint64_t n_entries;
+    const uint64_t *keys_lo;
+    const uint64_t *keys_hi;        /* NULL when 2k <= 62 */
+    const uint32_t *count_flags;
+    uint32_t first_unit;            /* first_bucket << second_buckets_count_log */
+    uint32_t n_units;
+    const uint64_t *unit_offsets;   /* n_units + 1 entry offsets */
+    const uint64_t *color_offsets;  /* n_entries + 1 offsets into colors, NULL when uncoloured */
+    const uint32_t *colors;         /* sorted-unique colour ids per entry */
+    uint64_t total_kmers;           /* k-mer occurrences processed */
+    uint64_t unique_kmers;          /* distinct keys before the multiplicity filter */
+    void *opaque;
+} ggcat_b200_table;
+
+const char *ggcat_b200_last_error(void);
+uint32_t ggcat_b200_abi_version(void);
+/* crates/utils/src/lib.rs:29-40 */
+uint32_t ggcat_b200_compute_best_m(uint32_t k);
+/* crates/io/src/lib.rs:67-140: bucket-count heuristics from the estimated input size in bytes. */
+void ggcat_b200_bucket_counts(uint64_t estimated_bases, uint32_t *buckets_count_log, uint32_t *second_buckets_count_log);
+
+int32_t ggcat_b200_create(const ggcat_b200_params *params, ggcat_b200_ctx **out);
+void ggcat_b200_destroy(ggcat_b200_ctx *ctx);
+
+/* Pinned host staging memory for callers that want asynchronous copies. */
+void *ggcat_b200_host_alloc(uint64_t bytes);
+void ggcat_b200_host_free(void *p);
+
+/* Phase 1.  `data` holds n_reads raw ASCII records back to back (record r = data[offsets[r] ..
+ * offsets[r+1])), as produced by the reference's reader before normalisation
+ * (crates/io/src/sequences_reader.rs:106-179).  colors: one id per record or NULL.
+ * The batch is normalised, N-split, hashed, split into super-k-mers and scattered into
+ * device-resident buckets.  May be called repeatedly; each call appends one bucket chunk. */
+int32_t ggcat_b200_push_reads(ggcat_b200_ctx *ctx, const uint8_t *data, const uint64_t *offsets, uint64_t n_reads,
+                              const uint32_t *colors);
+/* Same, with data/offsets/colors already resident in device memory of ctx's device. */
+int32_t ggcat_b200_push_reads_device(ggcat_b200_ctx *ctx, const uint8_t *d_data, const uint64_t *d_offsets,
+                                     uint64_t n_reads, uint64_t n_bytes, const uint32_t *d_colors);
+int32_t ggcat_b200_finish_bucketing(ggcat_b200_ctx *ctx, ggcat_b200_bucket_stats *stats);
+
+/* Per-unit sizes after finish_bucketing: arrays of stats.n_units entries (either may be NULL). */
+int32_t ggcat_b200_unit_sizes(ggcat_b200_ctx *ctx, uint64_t *n_superkmers, uint64_t *n_kmers);
+
+/* Test hook (phase-1 parity): copies the super-k-mers of one first-level bucket to the host.
+ * Two-call protocol: with out == NULL only the counts are returned. */
+int32_t ggcat_b200_dump_superkmers(ggcat_b200_ctx *ctx, uint32_t bucket, ggcat_b200_superkmer *out, uint64_t cap,
+                                   uint8_t *payload, uint64_t payload_cap, uint64_t *n_out, uint64_t *payload_bytes);
+
+/* Phase 2 for buckets [first_bucket, first_bucket + n_buckets) (the duplicates bucket is index
+ * 1 << buckets_count_log).  Fills *out with pinned host copies of the filtered table. */
+int32_t ggcat_b200_merge_bucket_range(ggcat_b200_ctx *ctx, uint32_t first_bucket, uint32_t n_buckets,
+                                      ggcat_b200_table *out);
+int32_t ggcat_b200_release_table(ggcat_b200_ctx *ctx, ggcat_b200_table *table);
+
+/* Phase 2 without the device->host copy: the table stays in HBM (bench `value`, multi-GPU owners).
+ * Returns entry count and distinct/total k-mer counters. */
+int32_t ggcat_b200_merge_bucket_range_device(ggcat_b200_ctx *ctx, uint32_t first_bucket, uint32_t n_buckets,
+                                             uint64_t *n_entries, uint64_t *unique_kmers, uint64_t *total_kmers);
+
+/* Drops all bucket chunks so the context can be reused for another build. */
+int32_t ggcat_b200_reset(ggcat_b200_ctx *ctx);
+
+/* ---- multi-GPU plumbing: bucket chunks as plain device buffers ---------------------------------
+ * After finish_bucketing a context holds one chunk per push.  The host (torch.distributed / NCCL in
+ * this repo, any transport in a Rust host) routes the slice of every chunk that belongs to units
+ * [first_unit, first_unit + n_units) to the owner rank and registers it there with import_chunk. */
+typedef struct {
+    uint64_t n_superkmers;        /* descriptors in the slice */
+    uint64_t n_words;             /* payload words in the slice */
+    uint64_t word_bias;           /* payload word offset of the slice inside its source chunk: descriptors
+                                     hold offsets relative to the source chunk, the receiver subtracts this */
+    const void *d_descriptors;    /* 16 bytes each */
+    const uint32_t *d_payload;
+    const uint32_t *d_unit_counts;   /* n_units super-k-mer counts   (device) */
+    const uint32_t *d_unit_words;    /* n_units payload word counts  (device) */
+    const uint32_t *d_unit_kmers;    /* n_units k-mer counts         (device) */
+} ggcat_b200_chunk_slice;
+
+uint32_t ggcat_b200_n_chunks(ggcat_b200_ctx *ctx);
+int32_t ggcat_b200_export_chunk_slice(ggcat_b200_ctx *ctx, uint32_t chunk, uint32_t first_unit, uint32_t n_units,
+                                      ggcat_b200_chunk_slice *out);
+/* Registers a received slice (device pointers stay owned by the caller and must outlive the merge). */
+int32_t ggcat_b200_import_chunk_slice(ggcat_b200_ctx *ctx, uint32_t first_unit, uint32_t n_units,
+                                      const ggcat_b200_chunk_slice *slice);
+/* Forget the chunks produced locally by push_reads (after they were exported) but keep imports. */
+int32_t ggcat_b200_drop_local_chunks(ggcat_b200_ctx *ctx);
+
+/* ---- measurement hooks ------------------------------------------------------------------------- */
+/* Per-kernel-family CUDA-event timing on/off (off by default: two event records per launch). */
+int32_t ggcat_b200_set_timing(ggcat_b200_ctx *ctx, int32_t enabled);
+/* The CUDA stream (cudaStream_t) every kernel of this context is launched on. */
+void *ggcat_b200_stream(ggcat_b200_ctx *ctx);
+int32_t ggcat_b200_synchronize(ggcat_b200_ctx *ctx);
+/* Device time (ms, CUDA events on the context stream) and launch count of each kernel family since
+ * the last call with reset != 0.  names/ms/launches receive up to cap entries; returns the number
+ * of families. */
+int32_t ggcat_b200_kernel_times(ggcat_b200_ctx *ctx, const char **names, float *ms, uint32_t *launches, uint32_t cap,
+                                int32_t reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GGCAT_B200_H */

@@ -1,0 +1,246 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Everything goes through the C ABI
+(include/ggcat_b200.h) and is compared bit-for-bit with the CPU oracle on the same inputs."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+def _gpu():
+    import torch
+
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import __graft_entry__ as g
+
+    g.build()
+    import ggcat_b200 as G
+
+    return G
+
+
+def _sk_records(reads, sk, k):
+    """Canonical comparable form of oracle super-k-mers: sorted list of tuples."""
+    out = []
+    for row in sk:
+        out.append((int(row["bucket"]), int(row["second_bucket"]), int(row["len"]), int(row["flags"]), int(row["rc"]),
+                    int(row["minimizer_pos"]), O.superkmer_packed(reads, row)))
+    return sorted(out)
+
+
+def _gpu_records(ctx, n_buckets):
+    out = []
+    for b in range(n_buckets):
+        sk, payload = ctx.dump_superkmers(b)
+        pb = payload.tobytes()
+        for row in sk:
+            nb = (int(row["len"]) + 3) // 4
+            off = int(row["payload_offset"])
+            out.append((int(row["bucket"]), int(row["second_bucket"]), int(row["len"]), int(row["flags"]), int(row["rc"]),
+                        int(row["minimizer_pos"]), pb[off:off + nb]))
+    return sorted(out)
+
+
+def _check_tables(G, ctx, reads, sk, k, s, b1, b2, forward_only=False, ranges=None):
+    nb = (1 << b1) + 1
+    ranges = ranges or [(0, nb)]
+    n_checked = 0
+    for (fb, cnt) in ranges:
+        tab = ctx.merge_bucket_range(fb, cnt)
+        assert tab.first_unit == fb << b2
+        tot_occ = 0
+        uniq = 0
+        for u in range(fb << b2, (fb + cnt) << b2):
+            ref, _, tk = O.merge_unit(reads, sk, u >> b2, u & ((1 << b2) - 1), k, s, O.HASH_SEQ, forward_only)
+            tot_occ += tk
+            uniq += len(ref)
+            ref = ref[ref["kept"] == 1]
+            sl = tab.unit_slice(u)
+            assert np.array_equal(tab.keys_lo[sl], ref["key_lo"]), f"unit {u}: keys differ"
+            assert np.array_equal(tab.multiplicity[sl].astype(np.uint64), ref["multiplicity"]), f"unit {u}: counts"
+            assert np.array_equal(tab.flags[sl], ref["flags"]), f"unit {u}: flags"
+            n_checked += len(ref)
+        assert tab.total_kmers == tot_occ
+        assert tab.unique_kmers == uniq
+    return n_checked
+
+
+def _mixed_reads(rng, k, n=300):
+    g = util.rand_seq(rng, 5000)
+    seqs = []
+    for _ in range(n):
+        L = int(rng.integers(k - 2, 260))
+        a = int(rng.integers(0, len(g) - L))
+        r = bytearray(g[a:a + L])
+        if rng.random() < 0.5:
+            r = bytearray(util.revcomp(bytes(r)))
+        if rng.random() < 0.15:
+            r[int(rng.integers(0, L))] = ord("N")
+        if rng.random() < 0.05:
+            r[int(rng.integers(0, L))] = ord("x")
+        if rng.random() < 0.1:
+            r = bytearray(bytes(r).lower())
+        seqs.append(bytes(r))
+    seqs += [b"A" * 300, b"ACACACACAC" * 30, b"AT" * 100, g[:k], g[:k - 1], b"", b"N" * 50, b"ACGT" * 2,
+             util.rand_seq(rng, k + 1), g[:3000], b"N" + g[100:400] + b"NN" + g[500:531] + b"N" + g[600:630] + b"N"]
+    return seqs
+
+
+@pytest.mark.parametrize("k,m,b1,b2,fo,s", [(31, 12, 3, 2, False, 2), (31, 12, 4, 6, True, 1), (15, 9, 2, 1, False, 1),
+                                            (21, 10, 3, 3, False, 3), (27, 5, 2, 2, False, 2), (31, 29, 2, 2, False, 1)])
+def test_small_mixed_inputs(k, m, b1, b2, fo, s):
+    G = _gpu()
+    rng = np.random.default_rng(k * 31 + m)
+    seqs = _mixed_reads(rng, k)
+    reads = O.Reads.from_list(seqs)
+    sk, vb = O.bucketing(reads, k, m, b1, b2, forward_only=fo)
+    ctx, st = G.minimizer_bucketing([(reads.data, reads.offsets)], b1, b2, k, m, forward_only=fo, min_multiplicity=s)
+    try:
+        assert st.n_superkmers == len(sk)
+        assert st.n_kmers == int((sk["len"].astype(np.int64) - k + 1).sum())
+        assert _gpu_records(ctx, (1 << b1) + 1) == _sk_records(reads, sk, k)
+        _check_tables(G, ctx, reads, sk, k, s, b1, b2, fo, ranges=[(0, 1), (1, (1 << b1))])
+    finally:
+        ctx.close()
+
+
+def test_long_sequences_cross_tiles():
+    """Sequences much longer than a 1024-window tile, incl. low-complexity runs longer than a tile."""
+    G = _gpu()
+    rng = np.random.default_rng(99)
+    k, m, b1, b2, s = 31, 12, 3, 2, 1
+    seqs = [util.rand_seq(rng, 40000), b"A" * 5000 + util.rand_seq(rng, 3000) + b"CA" * 2000, util.rand_seq(rng, 1023 + k),
+            util.rand_seq(rng, 1024 + k - 2), util.rand_seq(rng, 2048), b"G" * 1024, b"T" * 1025]
+    reads = O.Reads.from_list(seqs)
+    sk, _ = O.bucketing(reads, k, m, b1, b2)
+    ctx, st = G.minimizer_bucketing([(reads.data, reads.offsets)], b1, b2, k, m, min_multiplicity=s)
+    try:
+        assert st.n_superkmers == len(sk)
+        assert _gpu_records(ctx, (1 << b1) + 1) == _sk_records(reads, sk, k)
+        _check_tables(G, ctx, reads, sk, k, s, b1, b2)
+    finally:
+        ctx.close()
+
+
+def test_multiple_pushes_equal_single_push():
+    """Chunk invariance: the table does not depend on how the input was batched."""
+    G = _gpu()
+    rng = np.random.default_rng(5)
+    k, m, b1, b2, s = 31, 12, 3, 2, 2
+    seqs = _mixed_reads(rng, k, n=600)
+    reads = O.Reads.from_list(seqs)
+    sk, _ = O.bucketing(reads, k, m, b1, b2)
+    half = len(seqs) // 2
+    r1 = O.Reads.from_list(seqs[:half])
+    r2 = O.Reads.from_list(seqs[half:])
+    ctx, st = G.minimizer_bucketing([(r1.data, r1.offsets), (r2.data, r2.offsets)], b1, b2, k, m, min_multiplicity=s)
+    try:
+        assert ctx.n_chunks() == 2
+        assert st.n_superkmers == len(sk)
+        _check_tables(G, ctx, reads, sk, k, s, b1, b2)
+    finally:
+        ctx.close()
+
+
+def test_c1_example_inputs(golden_dir):
+    """BASELINE configs[0]: sal1+sal2+sal3, k=31 -s 1, 4(+1) x 64 buckets -- full parity + committed digests."""
+    G = _gpu()
+    gold = json.loads((golden_dir / "c1_golden.json").read_text())
+    recs = util.c1_records()
+    reads = O.Reads.from_list(recs)
+    k, m, b1, b2, s = gold["k"], gold["m"], gold["b1"], gold["b2"], gold["s"]
+    assert G.bucket_counts(509_594) == (b1, b2)
+    ctx, st = G.minimizer_bucketing([(reads.data, reads.offsets)], b1, b2, k, m, min_multiplicity=s)
+    try:
+        assert st.n_superkmers == gold["n_superkmers"]
+        sk, _ = O.bucketing(reads, k, m, b1, b2)
+        assert _gpu_records(ctx, (1 << b1) + 1) == _sk_records(reads, sk, k)
+        for b in range((1 << b1) + 1):
+            tab = ctx.merge_bucket_range(b, 1)
+            # fold sub-buckets into the bucket table: sum counters, OR flags, halve if flags == 3
+            keys, inv = np.unique(tab.keys_lo, return_inverse=True)
+            cnt = np.zeros(keys.size, np.uint64)
+            np.add.at(cnt, inv, tab.multiplicity.astype(np.uint64))
+            fl = np.zeros(keys.size, np.uint8)
+            np.bitwise_or.at(fl, inv, tab.flags)
+            mult = cnt >> (fl == 3).astype(np.uint64)
+            g = gold["buckets"][str(b)]
+            assert tab.total_kmers == g["n_kmer_occurrences"]
+            assert keys.size == g["n_entries"]
+            assert util.table_digest(keys, None, mult, fl) == g["digest"], f"bucket {b}"
+    finally:
+        ctx.close()
+
+
+def test_c2_full_size_properties():
+    """BASELINE configs[1] at full size (1 M x 150 bp): size-independent properties + sampled unit parity."""
+    G = _gpu()
+    from ggcat_b200 import synth
+
+    n_reads = int(os.environ.get("GGCAT_TEST_C2_READS", "1000000"))
+    data, offsets = synth.config_c2(n_reads=n_reads)
+    k, m, s = 31, 12, 2
+    b1, b2 = G.bucket_counts(int(data.size * 1.1))
+    ctx, st = G.minimizer_bucketing([(data, offsets)], b1, b2, k, m, min_multiplicity=s)
+    try:
+        n_kmers_input = n_reads * (150 - k + 1)
+        # every k-mer occurrence is stored once per (k-1)-mer group side: boundary k-mers twice
+        assert st.n_kmers == n_kmers_input + (st.n_superkmers - n_reads)
+        sizes_sk, sizes_km = ctx.unit_sizes()
+        assert int(sizes_sk.sum()) == st.n_superkmers and int(sizes_km.sum()) == st.n_kmers
+        nb = (1 << b1) + 1
+        t1 = ctx.merge_bucket_range(0, nb)
+        assert t1.total_kmers == st.n_kmers
+        # sortedness inside every unit, multiplicity filter respected
+        assert (t1.multiplicity >= s).all()
+        uo = t1.unit_offsets
+        d = np.diff(t1.keys_lo.astype(np.uint64))
+        bad = np.nonzero(t1.keys_lo[1:] <= t1.keys_lo[:-1])[0] + 1
+        assert np.isin(bad, uo).all(), "keys not strictly increasing inside a unit"
+        # idempotence: a second merge gives the identical table
+        t2 = ctx.merge_bucket_range(0, nb)
+        assert np.array_equal(t1.keys_lo, t2.keys_lo) and np.array_equal(t1.count_flags, t2.count_flags)
+        assert np.array_equal(t1.unit_offsets, t2.unit_offsets)
+        # a k-mer has the same multiplicity wherever it appears (checksum over duplicates across units)
+        order = np.argsort(t1.keys_lo, kind="stable")
+        ks, ms = t1.keys_lo[order], t1.multiplicity[order]
+        same = ks[1:] == ks[:-1]
+        assert (ms[1:][same] == ms[:-1][same]).all()
+        # sampled units against the oracle
+        reads = O.Reads(data, offsets)
+        sk, _ = O.bucketing(reads, k, m, b1, b2)
+        assert st.n_superkmers == len(sk)
+        rng = np.random.default_rng(1)
+        for u in rng.choice(nb << b2, 24, replace=False):
+            ref, _, _ = O.merge_unit(reads, sk, int(u) >> b2, int(u) & ((1 << b2) - 1), k, s)
+            ref = ref[ref["kept"] == 1]
+            sl = t1.unit_slice(int(u))
+            assert np.array_equal(t1.keys_lo[sl], ref["key_lo"])
+            assert np.array_equal(t1.multiplicity[sl].astype(np.uint64), ref["multiplicity"])
+            assert np.array_equal(t1.flags[sl], ref["flags"])
+    finally:
+        ctx.close()
+
+
+def test_error_behaviour():
+    G = _gpu()
+    with pytest.raises(G.GgcatB200Error):
+        G.GGCATB200(G.Params(k=3))
+    with pytest.raises(G.GgcatB200Error):
+        G.GGCATB200(G.Params(k=31, m=31))
+    ctx = G.GGCATB200(G.Params(k=31, buckets_count_log=2, second_buckets_count_log=1))
+    with pytest.raises(G.GgcatB200Error) as ei:
+        ctx.merge_bucket_range(0, 1)  # before finish_bucketing
+    assert ei.value.code == -3
+    ctx.finish_bucketing()
+    t = ctx.merge_bucket_range(0, 5)  # empty build: empty table, not an error
+    assert t.n_entries == 0
+    with pytest.raises(G.GgcatB200Error):
+        ctx.merge_bucket_range(4, 2)
+    ctx.close()
