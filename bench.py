@@ -1,0 +1,355 @@
+#!/usr/bin/env python
+"""bench.py -- build Gbases/s (minimizer bucketing + k-mer merge) on N B200s.
+
+    python bench.py --gpus N --steps K --warmup W            # our CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port, all host cores)
+
+A "step" is one full pass of the hot path (phase 1 + phase 2) over one batch of synthetic reads.
+Workload at N=1: BASELINE configs[1] (C2): synthetic 5 Mbp genome, 1 M x 150 bp reads (30x), 1 % errors, k=31 -s 2,
+seq-hash, buckets 512(+1) x 64 as the reference would choose (crates/io/src/lib.rs:67-140).
+At N>1 every rank holds its own 1 M-read slice of a 5N Mbp genome (weak scaling); buckets are owned by
+contiguous ranges, super-k-mers are routed with one all-to-all (NCCL) and each owner merges locally.
+
+Printed JSON line (rank 0): see DESIGN.md "Measurement".
+  value    device-timed (CUDA events on the library's stream), inputs resident in HBM
+  e2e      same metric through the C ABI with HOST buffers (H2D of reads, D2H of the table inside the timed region)
+  roofline dominant kernel (k_merge_units<smem>) against the measured HBM peak
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+K, M, S = 31, 12, 2
+READ_LEN = 150
+READS_PER_GPU = 1_000_000
+GENOME_PER_GPU = 5_000_000
+ERR = 0.01
+
+
+def measured_peak():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_reads(rank: int, world: int, n_reads: int):
+    from ggcat_b200 import synth
+
+    g = synth.genome_codes(0xC2, GENOME_PER_GPU * world)
+    r = synth.simulate_reads(g, n_reads, READ_LEN, ERR, 0xC2 + 1, first_read=rank * n_reads)
+    return synth.reads_to_ascii_batch(r)
+
+
+# ------------------------------------------------------------------------------------------- reference arm
+def run_reference(args):
+    """The reference's own CPU implementation of the path: Rust cannot be built here, so this is
+    the oracle port (oracle/ggcat_oracle.c, OpenMP over all host cores) on a bounded sample of the workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as O
+
+    import ggcat_b200  # noqa: F401  (only for bucket_counts parity with our arm; no GPU work)
+    from ggcat_b200 import synth
+
+    sample_reads = args.sample_reads
+    cores = os.cpu_count() or 1
+    data, offsets = make_reads(0, max(args.gpus, 1), sample_reads)
+    b1, b2 = O.bucket_counts(int(READS_PER_GPU * (READ_LEN + 15)))  # same bucket counts as the full workload
+    reads = O.Reads(data, offsets)
+    times = []
+    st = None
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        st = O.pipeline(reads, K, M, b1, b2, S, n_threads=cores)
+        dt = time.perf_counter() - t0
+        if i >= args.warmup:
+            times.append(dt)
+    bases = int(data.size)
+    ms = 1e3 * float(np.mean(times))
+    val = bases / (ms * 1e-3) / 1e9
+    line = {
+        "impl": "reference", "metric": "build Gbases/s (bucketing+k-mer merge)", "value": val, "unit": "Gbases/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": f"C2 sample: {sample_reads} x {READ_LEN} bp reads of the 5 Mbp/30x/1% set, k={K} m={M} -s {S}, "
+                               f"buckets {1 << b1}(+1) x {1 << b2}"},
+        "cpu_baseline": {"value": val, "unit": "Gbases/s", "cores": int(st.threads), "kind": "port",
+                         "sample": f"{sample_reads} reads ({bases} bases); phase1 {st.t_bucketing:.3f}s phase2 {st.t_merge:.3f}s"},
+        "e2e": {"value": val, "unit": "Gbases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import __graft_entry__ as ge
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the ggcat_b200 path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if rank == 0:
+        ge.build()
+    if world > 1:
+        dist.barrier()
+    import ggcat_b200 as G
+    from ggcat_b200 import dist as gdist
+
+    n_reads = args.reads_per_gpu
+    data, offsets = make_reads(rank, world, n_reads)
+    n_bases = int(data.size)
+    b1, b2 = G.bucket_counts(int(READS_PER_GPU * (READ_LEN + 15)))  # the FASTA size the reference would see per GPU slice
+    nb = (1 << b1) + 1
+    ctx = G.GGCATB200(G.Params(k=K, m=M, min_multiplicity=S, buckets_count_log=b1, second_buckets_count_log=b2,
+                               device=local_rank))
+    ext = torch.cuda.ExternalStream(ctx.stream_ptr, device=torch.device("cuda", local_rank))
+    # inputs: pinned host copies (e2e) and device-resident copies (value)
+    h_data = torch.from_numpy(data).pin_memory()
+    h_off = torch.from_numpy(offsets.view(np.int64)).pin_memory()
+    d_data = h_data.cuda(non_blocking=True)
+    d_off = h_off.cuda(non_blocking=True)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+    torch.cuda.synchronize()
+    owner = gdist.OwnerMap(b1, b2, world)
+
+    def step_device():
+        ctx.reset()
+        ctx.push_reads_device(d_data.data_ptr(), d_off.data_ptr(), n_reads, n_bases)
+        ctx.finish_bucketing()
+        if world > 1:
+            gdist.exchange_and_import(ctx, owner, rank, world, ext)
+        fb, cnt = owner.bucket_range(rank)
+        return ctx.merge_bucket_range_device(fb, cnt)
+
+    def step_host():
+        ctx.reset()
+        ctx.push_reads_ptr(h_data.data_ptr(), h_off.data_ptr(), n_reads)
+        ctx.finish_bucketing()
+        if world > 1:
+            gdist.exchange_and_import(ctx, owner, rank, world, ext)
+        fb, cnt = owner.bucket_range(rank)
+        return ctx.merge_bucket_range(fb, cnt)
+
+    def l2_flush():
+        with torch.cuda.stream(ext):
+            flush.fill_(rank & 0xFF)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+        l2_flush()
+    # ---- timed region: K steps, device time on the library stream, L2 flushed between steps (not timed)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    ctx.kernel_times(reset=True)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    res = None
+    for i in range(args.steps):
+        l2_flush()
+        barrier()
+        ev[i][0].record(ext)
+        res = step_device()
+        ev[i][1].record(ext)
+    barrier()
+    clocks = sampler.stop()
+    launches = sum(v[1] for v in ctx.kernel_times(reset=True).values())
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = float(sum(step_ms))
+    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = (n_bases * world) / (ms_per_step * 1e-3) / 1e9
+
+    # ---- per-kernel timing pass (events around every launch; separate from the timed region)
+    ctx.set_timing(True)
+    n_prof = 3
+    ctx.kernel_times(reset=True)
+    for _ in range(n_prof):
+        l2_flush()
+        step_device()
+    kt = ctx.kernel_times(reset=True)
+    ctx.set_timing(False)
+    st = ctx.finish_bucketing()
+    n_entries, unique, total_kmers = res
+
+    # ---- e2e through the C ABI with host buffers
+    for _ in range(2):
+        step_host()
+    e2e_times = []
+    tab = None
+    for _ in range(args.steps):
+        l2_flush()
+        barrier()
+        t0 = time.perf_counter()
+        tab = step_host()
+        torch.cuda.synchronize()
+        e2e_times.append(time.perf_counter() - t0)
+    e2e_ms = float(np.mean(e2e_times)) * 1e3
+    t = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item())
+    e2e_val = (n_bases * world) / (e2e_ms * 1e-3) / 1e9
+    h2d = int(data.nbytes + offsets.nbytes)
+    d2h = int(tab.keys_lo.nbytes + tab.count_flags.nbytes + tab.unit_offsets.nbytes)
+
+    # ---- roofline of the dominant kernel
+    peak, peak_kind = measured_peak()
+    merge_ms, merge_launches = kt.get("k_merge_units<smem>", (0.0, 0))
+    per_launch_ms = merge_ms / max(merge_launches, 1)
+    launches_per_step = max(merge_launches // n_prof, 1)
+    # algorithmic bytes (SURVEY 8(d) merge model with this build's record size W+P = 8 B, R = 8 LSD passes):
+    #   B_s + N_k*8*(1 expand write + 2R sort + 1 reduce read) + S*12
+    B_s = st.payload_words * 4 + st.n_superkmers * 16
+    N_k = st.n_kmers
+    model_bytes = B_s + N_k * 8 * (1 + 2 * 8 + 1) + n_entries * 12
+    compulsory = B_s + n_entries * 12  # what this kernel must move: super-k-mers in, survivors out
+    achieved = model_bytes / launches_per_step / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": "k_merge_units<smem>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_kind": peak_kind,
+                "model": "SURVEY 8(d) DRAM-LSD-equivalent bytes (W+P=8, R=8); the kernel sorts in shared memory",
+                "algorithmic_bytes_per_launch": model_bytes / launches_per_step,
+                "compulsory_bytes_per_launch": compulsory / launches_per_step, "ms_per_launch": per_launch_ms,
+                "kernel_share_of_step": merge_ms / max(sum(v[0] for v in kt.values()), 1e-9)}
+    tr = ROOT / "profiles" / "traffic.json"
+    if tr.exists():
+        try:
+            roofline["traffic"] = json.loads(tr.read_text()).get("k_merge_units_smem_dram_bytes_per_launch")
+        except Exception:
+            pass
+
+    line = {
+        "metric": "build Gbases/s (bucketing+k-mer merge)", "value": value, "unit": "Gbases/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": f"C2 per GPU: {n_reads} x {READ_LEN} bp reads (30x of {GENOME_PER_GPU * world} bp genome, 1% errors), "
+                               f"k={K} m={M} -s {S} seq-hash, buckets {1 << b1}(+1) x {1 << b2}",
+                   "l2": "flushed (256 MB write) between timed steps", "reads_per_gpu": n_reads,
+                   "parallelism": f"bucket-owner x{world}" if world > 1 else "single GPU"},
+        "e2e": {"value": e2e_val, "unit": "Gbases/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_ms},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": roofline,
+        "kernels_ms_per_step": {k: round(v[0] / n_prof, 4) for k, v in kt.items()},
+        "counts": {"bases_per_gpu": n_bases, "superkmers": int(st.n_superkmers), "kmer_records": int(st.n_kmers),
+                   "unique": int(unique), "kept": int(n_entries)},
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import oracle as O
+
+        sr = args.sample_reads
+        cdata, coff = make_reads(0, 1, sr)
+        t0 = time.perf_counter()
+        pst = O.pipeline(O.Reads(cdata, coff), K, M, b1, b2, S, n_threads=os.cpu_count() or 1)
+        dt = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": cdata.size / dt / 1e9, "unit": "Gbases/s", "cores": int(pst.threads), "kind": "port",
+                                "sample": f"{sr} reads ({cdata.size} bases) of the same workload, oracle C port with OpenMP; "
+                                          f"phase1 {pst.t_bucketing:.3f}s phase2 {pst.t_merge:.3f}s"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--reads-per-gpu", type=int, default=READS_PER_GPU)
+    ap.add_argument("--sample-reads", type=int, default=200_000, help="bounded CPU sample (reads)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

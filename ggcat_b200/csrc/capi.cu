@@ -97,6 +97,7 @@ struct ggcat_b200_ctx {
     // phase-1 workspace
     DevBuf d_ascii, d_offsets, d_colors, pk, bad, brk, ent, tile_cnt, tile_sbase, tmp, tmp_color, cur_cnt, cur_words, totals;
     std::vector<Chunk *> chunks;
+    std::vector<Chunk *> chunk_pool;  // recycled local chunks (device buffers kept)
     // phase-2 workspace
     DevBuf d_views, d_work[3], d_scratch, d_scratch_off, out_keys, out_cf, out_keys2, out_cf2, cursor, unit_out_off,
         unit_out_cnt, unit_final_off, overflow;
@@ -113,8 +114,8 @@ namespace {
 
 struct LaunchTimer {
     ggcat_b200_ctx *c; int fam; cudaEvent_t a = nullptr, b = nullptr;
-    LaunchTimer(ggcat_b200_ctx *ctx, int f) : c(ctx), fam(f) {
-        c->fam_launches[fam]++;
+    LaunchTimer(ggcat_b200_ctx *ctx, int f, uint32_t n_kernels = 1) : c(ctx), fam(f) {
+        c->fam_launches[fam] += n_kernels;
         if (!c->timing) return;
         auto get = [&]() { cudaEvent_t e; if (!c->event_pool.empty()) { e = c->event_pool.back(); c->event_pool.pop_back(); } else cudaEventCreate(&e); return e; };
         a = get(); b = get();
@@ -176,7 +177,7 @@ int32_t bucket_batch_device(ggcat_b200_ctx *c, const uint8_t *d_data, const uint
     CU(cudaMemsetAsync(c->pk.as<uint32_t>() + 2 * n_groups, 0, 8 * 4, st));
     CU(cudaMemsetAsync(c->bad.as<uint32_t>() + n_groups, 0xFF, 8 * 4, st));
     {
-        LaunchTimer t(c, F_PACK);
+        LaunchTimer t(c, F_PACK, 2);
         const int aligned = ((uintptr_t)d_data & 15) == 0;
         k_pack<<<(unsigned)((n_groups + 255) / 256), 256, 0, st>>>(d_data, n, c->pk.as<uint32_t>(), c->bad.as<uint32_t>(),
                                                                    n_groups, aligned);
@@ -203,8 +204,12 @@ int32_t bucket_batch_device(ggcat_b200_ctx *c, const uint8_t *d_data, const uint
     if (n_sk == 0) return 0;
     if (n_sk >= (1ull << 32)) return set_err(GGCAT_B200_ERR_INVALID, "too many super-k-mers in one batch");
 
-    Chunk *ch = new Chunk();
+    Chunk *ch;
+    if (!c->chunk_pool.empty()) { ch = c->chunk_pool.back(); c->chunk_pool.pop_back(); }
+    else ch = new Chunk();
     c->chunks.push_back(ch);
+    ch->imported = false; ch->word_bias = 0;
+    ch->h_cnt.clear(); ch->h_off.clear(); ch->h_words.clear(); ch->h_woff.clear(); ch->h_kmers.clear();
     ch->first_unit = 0; ch->n_units = P.n_units; ch->n_sk = n_sk; ch->n_bases = n;
     const size_t ub = ((size_t)P.n_units + 2) * 4;
     CU(ch->unit_cnt.reserve(ub)); CU(ch->unit_off.reserve(ub)); CU(ch->unit_words.reserve(ub));
@@ -222,7 +227,7 @@ int32_t bucket_batch_device(ggcat_b200_ctx *c, const uint8_t *d_data, const uint
                                         ch->unit_kmers.as<uint32_t>());
     }
     {
-        LaunchTimer t(c, F_SCAN);
+        LaunchTimer t(c, F_SCAN, 2);
         k_exclusive_scan_u32<<<1, 1024, 0, st>>>(ch->unit_cnt.as<uint32_t>(), ch->unit_off.as<uint32_t>(), P.n_units,
                                                  c->totals.as<unsigned long long>() + 1);
         k_exclusive_scan_u32<<<1, 1024, 0, st>>>(ch->unit_words.as<uint32_t>(), ch->unit_woff.as<uint32_t>(), P.n_units,
@@ -393,7 +398,7 @@ int32_t merge_range_device(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_
     // unit-ordered final layout
     CU(c->out_keys2.reserve(cap * 8)); CU(c->out_cf2.reserve(cap * 4));
     {
-        LaunchTimer t(c, F_GATHER);
+        LaunchTimer t(c, F_GATHER, 2);
         k_scan_counts_u64<<<1, 1024, 0, st>>>(c->unit_out_cnt.as<uint32_t>(), c->unit_final_off.as<uint64_t>(), nu);
         k_gather_units<<<(unsigned)std::min<uint32_t>(nu, (uint32_t)c->sm_count * 8), 128, 0, st>>>(
             c->out_keys.as<uint64_t>(), c->out_cf.as<uint32_t>(), c->unit_out_off.as<uint64_t>(),
@@ -485,7 +490,10 @@ int32_t ggcat_b200_create(const ggcat_b200_params *params, ggcat_b200_ctx **out)
 int32_t ggcat_b200_reset(ggcat_b200_ctx *c) {
     TRY(check_ctx(c));
     cudaStreamSynchronize(c->stream);
-    for (Chunk *ch : c->chunks) { if (!ch->imported) ch->release(); else { ch->unit_off.release(); } delete ch; }
+    for (Chunk *ch : c->chunks) {
+        if (!ch->imported) c->chunk_pool.push_back(ch);  // keep the device buffers for the next build
+        else { ch->unit_off.release(); delete ch; }
+    }
     c->chunks.clear();
     c->finished = false;
     memset(&c->stats, 0, sizeof(c->stats));
@@ -496,6 +504,8 @@ void ggcat_b200_destroy(ggcat_b200_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     ggcat_b200_reset(c);
+    for (Chunk *ch : c->chunk_pool) { ch->release(); delete ch; }
+    c->chunk_pool.clear();
     collect_timings(c);
     for (DevBuf *b : {&c->d_ascii, &c->d_offsets, &c->d_colors, &c->pk, &c->bad, &c->brk, &c->ent, &c->tile_cnt, &c->tile_sbase,
                       &c->tmp, &c->tmp_color, &c->cur_cnt, &c->cur_words, &c->totals, &c->d_views, &c->d_work[0], &c->d_work[1],
@@ -731,7 +741,7 @@ int32_t ggcat_b200_drop_local_chunks(ggcat_b200_ctx *c) {
     std::vector<Chunk *> keep;
     for (Chunk *ch : c->chunks) {
         if (ch->imported) keep.push_back(ch);
-        else { ch->release(); delete ch; }
+        else c->chunk_pool.push_back(ch);  // recycle the device buffers
     }
     c->chunks.swap(keep);
     return 0;

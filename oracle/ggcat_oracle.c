@@ -881,3 +881,109 @@ size_t orc_compute_best_m(size_t k) {
 
 size_t orc_sizeof_superkmer(void) { return sizeof(orc_superkmer); }
 size_t orc_sizeof_table_entry(void) { return sizeof(orc_table_entry); }
+
+/* ------------------------------------------------------------------------------------------
+ * Whole-path driver used as the CPU baseline (bench.py cpu_baseline / --impl reference):
+ * phase 1 over all records, then phase 2 over every (bucket, second_bucket) unit, OpenMP over
+ * records / units the way the reference parallelises over input blocks and bucket jobs
+ * (minimizer_bucketing/src/lib.rs:566-567; kmers_transform/src/lib.rs:332-370).
+ * ---------------------------------------------------------------------------------------- */
+#include <time.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+typedef struct {
+    uint64_t n_superkmers, n_kmers, n_unique, n_kept, valid_bases, checksum;
+    double t_bucketing, t_merge;
+    int threads;
+} orc_pipeline_stats;
+
+static double now_s(void) {
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+
+int orc_pipeline(const uint8_t *reads, const uint64_t *offsets, size_t n_reads, size_t k, size_t m, unsigned b1,
+                 unsigned b2, int forward_only, uint64_t min_multiplicity, int hash_type, int n_threads,
+                 orc_pipeline_stats *st) {
+    memset(st, 0, sizeof(*st));
+#ifdef _OPENMP
+    if (n_threads > 0) omp_set_num_threads(n_threads);
+    st->threads = omp_get_max_threads();
+#else
+    st->threads = 1;
+#endif
+    const size_t BLOCK = 2048;
+    size_t n_blocks = (n_reads + BLOCK - 1) / BLOCK;
+    orc_superkmer **blk_sk = (orc_superkmer **)calloc(n_blocks ? n_blocks : 1, sizeof(orc_superkmer *));
+    size_t *blk_n = (size_t *)calloc(n_blocks ? n_blocks : 1, sizeof(size_t));
+    uint64_t *blk_vb = (uint64_t *)calloc(n_blocks ? n_blocks : 1, sizeof(uint64_t));
+    double t0 = now_s();
+#pragma omp parallel for schedule(dynamic, 1)
+    for (long bi = 0; bi < (long)n_blocks; bi++) {
+        size_t r0 = (size_t)bi * BLOCK, r1 = r0 + BLOCK < n_reads ? r0 + BLOCK : n_reads;
+        size_t bases = offsets[r1] - offsets[r0];
+        size_t cap = bases / 4 + (r1 - r0) + 16;
+        orc_superkmer *out = (orc_superkmer *)malloc(sizeof(orc_superkmer) * cap);
+        uint64_t vb = 0;
+        /* offsets are absolute: orc_bucketing indexes reads[offsets[r]] */
+        size_t n = orc_bucketing(reads, offsets + r0, r1 - r0, NULL, k, m, b1, b2, forward_only, out, cap, &vb);
+        if (n > cap) {
+            out = (orc_superkmer *)realloc(out, sizeof(orc_superkmer) * n);
+            n = orc_bucketing(reads, offsets + r0, r1 - r0, NULL, k, m, b1, b2, forward_only, out, n, &vb);
+        }
+        for (size_t i = 0; i < n; i++) out[i].read_index += (uint32_t)r0;
+        blk_sk[bi] = out; blk_n[bi] = n; blk_vb[bi] = vb;
+    }
+    size_t n_sk = 0;
+    for (size_t b = 0; b < n_blocks; b++) { n_sk += blk_n[b]; st->valid_bases += blk_vb[b]; }
+    /* "write to bucket": counting sort of the super-k-mers by unit */
+    size_t n_units = (((size_t)1 << b1) + 1) << b2;
+    size_t *unit_off = (size_t *)calloc(n_units + 1, sizeof(size_t));
+    for (size_t b = 0; b < n_blocks; b++)
+        for (size_t i = 0; i < blk_n[b]; i++) unit_off[(((size_t)blk_sk[b][i].bucket << b2) | blk_sk[b][i].second_bucket) + 1]++;
+    for (size_t u = 0; u < n_units; u++) unit_off[u + 1] += unit_off[u];
+    orc_superkmer *sorted = (orc_superkmer *)malloc(sizeof(orc_superkmer) * (n_sk ? n_sk : 1));
+    size_t *cursor = (size_t *)malloc(sizeof(size_t) * (n_units + 1));
+    memcpy(cursor, unit_off, sizeof(size_t) * (n_units + 1));
+    for (size_t b = 0; b < n_blocks; b++) {
+        for (size_t i = 0; i < blk_n[b]; i++) {
+            size_t u = ((size_t)blk_sk[b][i].bucket << b2) | blk_sk[b][i].second_bucket;
+            sorted[cursor[u]++] = blk_sk[b][i];
+        }
+        free(blk_sk[b]);
+    }
+    double t1 = now_s();
+    uint64_t n_kmers = 0, n_unique = 0, n_kept = 0, checksum = 0;
+#pragma omp parallel for schedule(dynamic, 4) reduction(+ : n_kmers, n_unique, n_kept, checksum)
+    for (long u = 0; u < (long)n_units; u++) {
+        size_t a = unit_off[u], e = unit_off[u + 1];
+        if (a == e) continue;
+        tbl t;
+        tbl_init(&t, 1024);
+        size_t maxlen = 0;
+        for (size_t i = a; i < e; i++) if (sorted[i].len > maxlen) maxlen = sorted[i].len;
+        uint8_t *packed = (uint8_t *)malloc(maxlen / 4 + 8);
+        kmer_hash *scratch = (kmer_hash *)malloc(sizeof(kmer_hash) * (maxlen + 1));
+        for (size_t i = a; i < e; i++) {
+            orc_superkmer_packed(reads, offsets, &sorted[i], packed);
+            n_kmers += sorted[i].len - k + 1;
+            add_sequence(&t, packed, sorted[i].len, sorted[i].flags, 1, 0, 0, k, hash_type, forward_only, scratch);
+        }
+        for (size_t i = 0; i < t.cap; i++) {
+            tbl_entry *en = &t.slots[i];
+            if (!en->used) continue;
+            n_unique++;
+            uint64_t mult = en->counter >> (en->flags == 3);
+            if (mult >= min_multiplicity) { n_kept++; checksum += (uint64_t)en->key * 0x9E3779B97F4A7C15ULL + mult + ((uint64_t)en->flags << 40); }
+        }
+        free(t.slots); free(packed); free(scratch);
+    }
+    double t2 = now_s();
+    st->n_superkmers = n_sk; st->n_kmers = n_kmers; st->n_unique = n_unique; st->n_kept = n_kept; st->checksum = checksum;
+    st->t_bucketing = t1 - t0; st->t_merge = t2 - t1;
+    free(blk_sk); free(blk_n); free(blk_vb); free(unit_off); free(sorted); free(cursor);
+    return 0;
+}

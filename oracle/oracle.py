@@ -303,3 +303,30 @@ def naive_count(reads: Reads, k: int, hash_type: int = HASH_SEQ, forward_only: b
     n = L.orc_naive_count(_p(reads.data), _p(reads.offsets), C.c_size_t(reads.n), C.c_size_t(k), C.c_int(hash_type),
                           C.c_int(forward_only), _p(out), C.c_size_t(cap), C.byref(tot))
     return out[:n].copy(), tot.value
+
+
+class PipelineStats(C.Structure):
+    _fields_ = [("n_superkmers", C.c_uint64), ("n_kmers", C.c_uint64), ("n_unique", C.c_uint64), ("n_kept", C.c_uint64),
+                ("valid_bases", C.c_uint64), ("checksum", C.c_uint64), ("t_bucketing", C.c_double), ("t_merge", C.c_double),
+                ("threads", C.c_int)]
+
+
+def pipeline(reads: Reads, k: int, m: int, b1: int, b2: int, min_multiplicity: int, hash_type: int = HASH_SEQ,
+             forward_only: bool = False, n_threads: int = 0) -> PipelineStats:
+    """Whole CPU path (phase 1 + phase 2 over all units) with OpenMP: the cpu_baseline of bench.py."""
+    st = PipelineStats()
+    L = lib()
+    L.orc_pipeline.restype = C.c_int
+    rc = L.orc_pipeline(_p(reads.data), _p(reads.offsets), C.c_size_t(reads.n), C.c_size_t(k), C.c_size_t(m), C.c_uint(b1),
+                        C.c_uint(b2), C.c_int(forward_only), C.c_uint64(min_multiplicity), C.c_int(hash_type),
+                        C.c_int(n_threads), C.byref(st))
+    assert rc == 0
+    return st
+
+
+def table_checksum(keys_lo, mult, flags) -> int:
+    """Same order-free checksum orc_pipeline accumulates over kept entries (64-bit keys)."""
+    with np.errstate(over="ignore"):
+        k = np.asarray(keys_lo, np.uint64) * np.uint64(0x9E3779B97F4A7C15)
+        v = k + np.asarray(mult, np.uint64) + (np.asarray(flags, np.uint64) << np.uint64(40))
+        return int(v.sum(dtype=np.uint64))
