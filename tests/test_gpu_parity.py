@@ -128,6 +128,25 @@ def test_long_sequences_cross_tiles():
         ctx.close()
 
 
+@pytest.mark.parametrize("n_bases", [3000, 8000, 14000, 60000, 400000])
+def test_unit_size_paths(n_bases):
+    """Units sized for each merge variant: <= 6144 records (512-thread smem), <= 12288 (1024-thread smem),
+    larger (global-scratch sort)."""
+    G = _gpu()
+    rng = np.random.default_rng(n_bases)
+    k, m, b1, b2, s = 31, 12, 0, 0, 1
+    g = util.rand_seq(rng, n_bases // 3)
+    seqs = [g, util.revcomp(g[: len(g) // 2]), g[len(g) // 4:], util.rand_seq(rng, n_bases // 6)]
+    reads = O.Reads.from_list(seqs)
+    sk, _ = O.bucketing(reads, k, m, b1, b2)
+    ctx, st = G.minimizer_bucketing([(reads.data, reads.offsets)], b1, b2, k, m, min_multiplicity=s)
+    try:
+        assert st.n_superkmers == len(sk)
+        _check_tables(G, ctx, reads, sk, k, s, b1, b2)
+    finally:
+        ctx.close()
+
+
 def test_multiple_pushes_equal_single_push():
     """Chunk invariance: the table does not depend on how the input was batched."""
     G = _gpu()
@@ -166,7 +185,9 @@ def test_c1_example_inputs(golden_dir):
             # fold sub-buckets into the bucket table: sum counters, OR flags, halve if flags == 3
             keys, inv = np.unique(tab.keys_lo, return_inverse=True)
             cnt = np.zeros(keys.size, np.uint64)
-            np.add.at(cnt, inv, tab.multiplicity.astype(np.uint64))
+            # a unit's raw MapEntry counter is its multiplicity un-halved
+            raw = tab.multiplicity.astype(np.uint64) << (tab.flags == 3).astype(np.uint64)
+            np.add.at(cnt, inv, raw)
             fl = np.zeros(keys.size, np.uint8)
             np.bitwise_or.at(fl, inv, tab.flags)
             mult = cnt >> (fl == 3).astype(np.uint64)
