@@ -275,28 +275,35 @@ def run_ours(args):
     h2d = int(data.nbytes + offsets.nbytes)
     d2h = int(tab.keys_lo.nbytes + tab.count_flags.nbytes + tab.unit_offsets.nbytes)
 
-    # ---- roofline of the dominant kernel
+    # ---- roofline of the dominant kernel (largest device time in the per-kernel pass)
     peak, peak_kind = measured_peak()
-    merge_ms, merge_launches = kt.get("k_merge_units<smem>", (0.0, 0))
-    per_launch_ms = merge_ms / max(merge_launches, 1)
-    launches_per_step = max(merge_launches // n_prof, 1)
-    # algorithmic bytes (SURVEY 8(d) merge model with this build's record size W+P = 8 B, R = 8 LSD passes):
-    #   B_s + N_k*8*(1 expand write + 2R sort + 1 reduce read) + S*12
-    B_s = st.payload_words * 4 + st.n_superkmers * 16
+    total_kernel_ms = max(sum(v[0] for v in kt.values()), 1e-9)
+    dom = max(kt, key=lambda name: kt[name][0])
+    dom_ms, dom_launches = kt[dom]
+    per_launch_ms = dom_ms / max(dom_launches, 1)
+    launches_per_step = max(dom_launches / n_prof, 1)
+    B_s = st.payload_words * 4 + st.n_superkmers * 16       # super-k-mer payload + descriptors
     N_k = st.n_kmers
-    model_bytes = B_s + N_k * 8 * (1 + 2 * 8 + 1) + n_entries * 12
-    compulsory = B_s + n_entries * 12  # what this kernel must move: super-k-mers in, survivors out
+    if dom.startswith("k_merge"):
+        # SURVEY 8(d) merge model with this build's record size W+P = 8 B and R = 8 LSD passes:
+        #   B_s + N_k*8*(1 expand write + 2R sort + 1 reduce read) + S*12
+        model_bytes = B_s + N_k * 8 * (1 + 2 * 8 + 1) + n_entries * 12
+        compulsory = B_s + n_entries * 12                   # what the kernel must move: super-k-mers in, table out
+        model = "SURVEY 8(d) DRAM-LSD-equivalent bytes (W+P=8, R=8); the kernel counts in shared memory"
+    else:
+        # bucketing kernels: packed bases + 2 bitmaps in, entries out (SURVEY 8(d) bucketing model share)
+        model_bytes = compulsory = n_bases // 4 + 2 * (n_bases // 8) + st.n_superkmers * 8
+        model = "compulsory bytes: packed bases + bad/brk bitmaps in, split entries out"
     achieved = model_bytes / launches_per_step / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": "k_merge_units<smem>", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_kind": peak_kind,
-                "model": "SURVEY 8(d) DRAM-LSD-equivalent bytes (W+P=8, R=8); the kernel sorts in shared memory",
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_kind": peak_kind, "model": model,
                 "algorithmic_bytes_per_launch": model_bytes / launches_per_step,
                 "compulsory_bytes_per_launch": compulsory / launches_per_step, "ms_per_launch": per_launch_ms,
-                "kernel_share_of_step": merge_ms / max(sum(v[0] for v in kt.values()), 1e-9)}
+                "kernel_share_of_step": dom_ms / total_kernel_ms}
     tr = ROOT / "profiles" / "traffic.json"
     if tr.exists():
         try:
-            roofline["traffic"] = json.loads(tr.read_text()).get("k_merge_units_smem_dram_bytes_per_launch")
+            roofline["traffic"] = json.loads(tr.read_text()).get(dom)
         except Exception:
             pass
 

@@ -105,39 +105,40 @@ __global__ void k_mark(const uint64_t *__restrict__ offsets, uint64_t n_reads, u
     if (off < n) atomicOr(&brk[off >> 5], 1u << (off & 31));
 }
 
-__device__ __forceinline__ bool any_bits(const uint32_t *bm, uint32_t s, uint32_t cnt) {
-    if (cnt == 0) return false;
-    const uint32_t e = s + cnt - 1;  // inclusive
-    const uint32_t ws = s >> 5, we = e >> 5;
-    for (uint32_t w = ws; w <= we; ++w) {
-        uint32_t mask = 0xffffffffu;
-        if (w == ws) mask &= 0xffffffffu << (s & 31);
-        if (w == we) mask &= 0xffffffffu >> (31 - (e & 31));
-        if (bm[w] & mask) return true;
-    }
-    return false;
-}
-
 // comb(): the window-minimum semigroup with the duplicate flag in bit 0
 // (crates/hashes/src/rolling/batch_minqueue.rs:63-70,78-84,97-113: equal values clear the unique bit).
 __device__ __forceinline__ uint64_t comb(uint64_t a, uint64_t b) { return a == b ? (a & ~1ull) : (a < b ? a : b); }
 
+// `cnt` (<= 64) bits of a shared-memory bitmap starting at bit `s`, as a u64.
+__device__ __forceinline__ uint64_t bits64(const uint32_t *bm, uint32_t s, uint32_t cnt) {
+    const uint64_t v = extract64(bm, s);
+    return cnt >= 64 ? v : (v & ((1ull << cnt) - 1ull));
+}
+
 // ------------------------------------------------------------------------------------------------
 // k_windows: one CTA per tile of WIN_T windows.
+//   A  stage packed bases + bitmaps in shared memory, build the per-position rotation tables
+//   B  m-mer hashes by rolling (cn_nthash.rs:43-57), IPT consecutive items per thread; window validity
+//   C  window minima, van Herk / Gil-Werman: per block of w items a suffix scan and a prefix scan with
+//      comb() -- exactly the two arrays the reference's BatchMinQueue keeps (batch_minqueue.rs:58-113)
+//   D  M_x = comb(suffix[x], prefix[x+w-1])
+//   E  split-start / segment-end flags, F in-order compaction (one block scan), G per-entry minimizer lookup
 __global__ void __launch_bounds__(WIN_THREADS)
 k_windows(const uint32_t *__restrict__ pk, const uint32_t *__restrict__ bad, const uint32_t *__restrict__ brk,
           uint32_t n /* bases in batch */, DevParams P, uint64_t *__restrict__ ent, uint32_t *__restrict__ tile_cnt,
           uint32_t *__restrict__ tile_scnt) {
     __shared__ uint32_t s_pk[(WIN_T + 2 * WIN_WMAX + 64) / 16 + 4];
-    __shared__ uint32_t s_bad[(WIN_T + 2 * WIN_WMAX + 64) / 32 + 4];
-    __shared__ uint32_t s_brk[(WIN_T + 2 * WIN_WMAX + 64) / 32 + 4];
+    __shared__ uint32_t s_bad[(WIN_T + 2 * WIN_WMAX + 64) / 32 + 6];
+    __shared__ uint32_t s_brk[(WIN_T + 2 * WIN_WMAX + 64) / 32 + 6];
     __shared__ uint64_t s_v0[WIN_NI + 1];
-    __shared__ uint64_t s_a[WIN_NI + 1];
-    __shared__ uint64_t s_b[WIN_NI + 1];
+    __shared__ uint64_t s_suf[WIN_NI + 1];   // suffix minima inside w-blocks; later M per window
+    __shared__ uint64_t s_pre[WIN_NI + 1];   // prefix minima inside w-blocks
     __shared__ uint8_t s_fwd[WIN_NI + 1];
     __shared__ uint8_t s_ok[WIN_T + 4];
+    __shared__ __align__(4) uint8_t s_flag[WIN_T];
     __shared__ uint64_t s_ent[WIN_T];
-    __shared__ uint64_t s_H[4], s_R[4];
+    __shared__ uint64_t s_TF[32][4], s_TR[32][4];  // rotl(h(c), m-1-i), rotl(r(c), i)
+    __shared__ uint64_t s_H[4], s_R[4], s_HM[4], s_RM1[4];
     __shared__ uint32_t s_scan[WIN_THREADS / 32 + 2];
 
     const uint32_t tid = threadIdx.x;
@@ -152,14 +153,23 @@ k_windows(const uint32_t *__restrict__ pk, const uint32_t *__restrict__ bad, con
     const uint32_t n_items = WIN_T + w;                   // m-mer items x in [0, n_items)
     const uint32_t last_base = (uint32_t)(j0 + WIN_T + k + 1);  // exclusive upper bound of bases touched
     const uint32_t n_pkw = ((last_base + 15) >> 4) - W0 + 2;
-    const uint32_t n_bmw = ((last_base + 31) >> 5) - BW0 + 1;
+    const uint32_t n_bmw = ((last_base + 31) >> 5) - BW0 + 3;
 
-    if (tid < 4) { s_H[tid] = nt_h(tid); s_R[tid] = nt_r(tid); }
+    // ---- A
+    if (tid < 4) {
+        s_H[tid] = nt_h(tid); s_R[tid] = nt_r(tid);
+        s_HM[tid] = rotl64(nt_h(tid), m); s_RM1[tid] = rotl64(nt_r(tid), m - 1);
+    }
+    if (tid < 4 * m) {
+        const uint32_t i = tid >> 2, c = tid & 3;
+        s_TF[i][c] = rotl64(nt_h(c), m - 1 - i);
+        s_TR[i][c] = rotl64(nt_r(c), i);
+    }
     for (uint32_t i = tid; i < n_pkw; i += WIN_THREADS) s_pk[i] = pk[W0 + i];
     for (uint32_t i = tid; i < n_bmw; i += WIN_THREADS) { s_bad[i] = bad[BW0 + i]; s_brk[i] = brk[BW0 + i]; }
     __syncthreads();
 
-    // ---- m-mer hashes: each thread rolls through IPT consecutive items (cn_nthash.rs:21-58)
+    // ---- B: hashes
     {
         const uint32_t IPT = (n_items + WIN_THREADS - 1) / WIN_THREADS;
         const uint32_t x0 = tid * IPT;
@@ -173,8 +183,8 @@ k_windows(const uint32_t *__restrict__ pk, const uint32_t *__restrict__ bad, con
                 uint64_t fw = 0, rc = 0;
                 for (uint32_t i = 0; i < m; i++) {
                     const uint32_t c = packed_base(s_pk, lb + i);
-                    fw ^= rotl64(s_H[c], m - 1 - i);
-                    rc ^= rotl64(s_R[c], i);
+                    fw ^= s_TF[i][c];
+                    rc ^= s_TR[i][c];
                 }
                 uint32_t l = lb;
                 for (uint32_t x = xs;; ++x) {
@@ -183,95 +193,94 @@ k_windows(const uint32_t *__restrict__ pk, const uint32_t *__restrict__ bad, con
                     s_fwd[x] = fw < rc;
                     if (x + 1 >= x1) break;
                     const uint32_t co = packed_base(s_pk, l), ci = packed_base(s_pk, l + m);
-                    fw = rotl64(fw, 1) ^ rotl64(s_H[co], m) ^ s_H[ci];
-                    rc = rotl64(rc ^ s_R[co], 63) ^ rotl64(s_R[ci], m - 1);
+                    fw = ((fw << 1) | (fw >> 63)) ^ s_HM[co] ^ s_H[ci];
+                    rc = rc ^ s_R[co];
+                    rc = ((rc >> 1) | (rc << 63)) ^ s_RM1[ci];
                     ++l;
                 }
             }
         }
     }
-    // ---- window validity: inside one N-free segment of one record (sequences_splitter.rs:15-40)
+    // ---- B: window validity: inside one N-free segment of one record (sequences_splitter.rs:15-40):
+    //      no bad base in [j, j+k-1) and no record start in (j, j+k-1)
     for (uint32_t x = tid; x < WIN_T + 2; x += WIN_THREADS) {
         const int64_t j = gfirst + x;
         bool ok = j >= 0 && (uint64_t)j + (k - 1) <= (uint64_t)n;
         if (ok) {
             const uint32_t lbit = (uint32_t)(j - ((int64_t)BW0 << 5));
-            ok = !any_bits(s_bad, lbit, k - 1) && !any_bits(s_brk, lbit + 1, k - 2);
+            ok = (bits64(s_bad, lbit, k - 1) | bits64(s_brk, lbit + 1, k - 2)) == 0;
         }
         s_ok[x] = ok;
     }
     __syncthreads();
 
-    // ---- window minima by doubling over non-overlapping power-of-two pieces of w
-    constexpr int ROUNDS = (WIN_T + 1 + WIN_THREADS - 1) / WIN_THREADS;
-    uint64_t acc[ROUNDS];
+    // ---- C: suffix / prefix minima inside blocks of w items (warps 0-1: suffix, warps 2-3: prefix)
     {
-        const uint64_t *cur = s_v0;
-        uint64_t *nxt = s_a;
-        uint32_t off = 0;
-        bool have = false;
-        for (uint32_t b = 0; (1u << b) <= w; ++b) {
-            const uint32_t step = 1u << b;
-            if (w & step) {
-#pragma unroll
-                for (int r = 0; r < ROUNDS; r++) {
-                    const uint32_t x = tid + r * WIN_THREADS;
-                    if (x < WIN_T + 1) {
-                        const uint64_t v = cur[x + off];
-                        acc[r] = have ? comb(acc[r], v) : v;
-                    }
-                }
-                have = true;
-                off += step;
+        const uint32_t n_blocks = (n_items + w - 1) / w;
+        if (tid < 64) {
+            for (uint32_t b = tid; b < n_blocks; b += 64) {
+                const uint32_t lo = b * w, hi = min(n_items, lo + w);
+                uint64_t sfx = s_v0[hi - 1];
+                s_suf[hi - 1] = sfx;
+                for (uint32_t x = hi - 1; x-- > lo;) { sfx = comb(s_v0[x], sfx); s_suf[x] = sfx; }
             }
-            if ((step << 1) <= w) {
-                for (uint32_t i = tid; i < n_items; i += WIN_THREADS) {
-                    const uint64_t a = cur[i];
-                    nxt[i] = (i + step < n_items) ? comb(a, cur[i + step]) : a;
-                }
-                __syncthreads();
-                cur = nxt;
-                nxt = (nxt == s_a) ? s_b : s_a;
+        } else if (tid < 128) {
+            for (uint32_t b = tid - 64; b < n_blocks; b += 64) {
+                const uint32_t lo = b * w, hi = min(n_items, lo + w);
+                uint64_t pfx = s_v0[lo];
+                s_pre[lo] = pfx;
+                for (uint32_t x = lo + 1; x < hi; ++x) { pfx = comb(pfx, s_v0[x]); s_pre[x] = pfx; }
             }
         }
     }
-    // publish M in s_a/s_b-independent storage: reuse s_b? levels may still be read -> sync first
     __syncthreads();
-    uint64_t *s_M = s_a;  // all level reads are done
-#pragma unroll
-    for (int r = 0; r < ROUNDS; r++) {
-        const uint32_t x = tid + r * WIN_THREADS;
-        if (x < WIN_T + 1) s_M[x] = acc[r];
+    // ---- D: M for windows x in [0, WIN_T]; a window aligned with a block is that block's suffix minimum
+    uint64_t *s_M = s_suf;  // in place: only thread x touches s_suf[x]
+    for (uint32_t x = tid; x < WIN_T + 1; x += WIN_THREADS) {
+        if (x % w != 0) s_M[x] = comb(s_suf[x], s_pre[x + w - 1]);
     }
     __syncthreads();
 
-    // ---- split / segment-end detection and in-order compaction
-    uint32_t base_cnt = 0;  // packed running counts: entries (low 16) | S entries (high 16)
-    for (int r = 0; r < WIN_T / WIN_THREADS; r++) {
-        const uint32_t x = 1 + r * WIN_THREADS + tid;  // tile window x-1
+    // ---- E: split / segment-end flags
+    for (uint32_t x = 1 + tid; x < WIN_T + 1; x += WIN_THREADS) {
         const bool okj = s_ok[x], okp = s_ok[x - 1], okn = s_ok[x + 1];
         const bool valid = okj && (okp || okn);        // segment has >= 2 windows <=> length >= k
         const bool first = okj && !okp;
-        const uint64_t M = s_M[x];
-        bool S = false, E = false;
+        uint32_t f = 0;
         if (valid) {
-            S = first || M != s_M[x - 1] || ((M & 1ull) && s_v0[x - 1] == M);
-            E = !okn;
+            const uint64_t M = s_M[x];
+            const bool S = first || M != s_M[x - 1] || ((M & 1ull) && s_v0[x - 1] == M);
+            f = (S ? 1u : 0u) | (!okn ? 2u : 0u) | (first ? 4u : 0u);
         }
-        const uint32_t mine = (S || E) ? (1u | (S ? 0x10000u : 0u)) : 0u;
-        uint32_t tot;
-        const uint32_t pre = block_exclusive_scan<WIN_THREADS>(mine, s_scan, &tot) + base_cnt;
-        if (mine) {
-            uint64_t e = (uint64_t)(x - 1) | (S ? ENT_S : 0) | (E ? ENT_E : 0) | (first ? ENT_FIRST : 0) |
-                         ((uint64_t)(pre >> 16) << ENT_SRANK_SHIFT);
-            s_ent[pre & 0xFFFFu] = e;
-        }
-        base_cnt += tot;
+        s_flag[x - 1] = (uint8_t)f;
     }
     __syncthreads();
-    const uint32_t n_ent = base_cnt & 0xFFFFu, n_s = base_cnt >> 16;
+    // ---- F: in-order compaction, 4 consecutive windows per thread
+    uint32_t n_ent, n_s;
+    {
+        const uint32_t f4 = reinterpret_cast<const uint32_t *>(s_flag)[tid];
+        uint32_t mine = 0;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const uint32_t f = (f4 >> (8 * q)) & 0xFFu;
+            if (f & 3u) mine += 1u + ((f & 1u) << 16);
+        }
+        uint32_t tot;
+        uint32_t pre = block_exclusive_scan<WIN_THREADS>(mine, s_scan, &tot);
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const uint32_t f = (f4 >> (8 * q)) & 0xFFu;
+            if (f & 3u) {
+                s_ent[pre & 0xFFFFu] = (uint64_t)(4 * tid + q) | ((f & 1u) ? ENT_S : 0) | ((f & 2u) ? ENT_E : 0) |
+                                       ((f & 4u) ? ENT_FIRST : 0) | ((uint64_t)(pre >> 16) << ENT_SRANK_SHIFT);
+                pre += 1u + ((f & 1u) << 16);
+            }
+        }
+        n_ent = tot & 0xFFFFu; n_s = tot >> 16;
+    }
+    __syncthreads();
 
-    // ---- per super-k-mer: locate the minimizer, derive bucket / orientation
+    // ---- G: per super-k-mer: locate the minimizer, derive bucket / orientation
     // (assembler_minimizer_bucketing/src/lib.rs:218-238)
     for (uint32_t i = tid; i < n_ent; i += WIN_THREADS) {
         uint64_t e = s_ent[i];

@@ -71,9 +71,9 @@ struct Chunk {
     }
 };
 
-enum Family { F_PACK = 0, F_WINDOWS, F_EMIT, F_SCATTER, F_SCAN, F_MERGE_SMEM, F_MERGE_GLOBAL, F_GATHER, F_COUNT };
+enum Family { F_PACK = 0, F_WINDOWS, F_EMIT, F_SCATTER, F_SCAN, F_MERGE_HASH, F_MERGE_SMEM, F_MERGE_GLOBAL, F_GATHER, F_COUNT };
 static const char *kFamilyNames[F_COUNT] = {"k_pack+k_mark", "k_windows", "k_emit", "k_scatter", "k_exclusive_scan_u32",
-                                            "k_merge_units<smem>", "k_merge_units<global>", "k_gather_units"};
+                                            "k_merge_hash", "k_merge_units<smem>", "k_merge_units<global>", "k_gather_units"};
 
 struct TimedLaunch { int fam; cudaEvent_t a, b; };
 
@@ -93,6 +93,7 @@ struct ggcat_b200_ctx {
     uint64_t max_batch = 1ull << 30;
     bool finished = false;
     bool timing = false;
+    int merge_mode = 1;  // 1 = shared-memory hash table (default), 0 = LSD radix sort (GGCAT_B200_MERGE=sort)
     ggcat_b200_bucket_stats stats;
     // phase-1 workspace
     DevBuf d_ascii, d_offsets, d_colors, pk, bad, brk, ent, tile_cnt, tile_sbase, tmp, tmp_color, cur_cnt, cur_words, totals;
@@ -100,7 +101,7 @@ struct ggcat_b200_ctx {
     std::vector<Chunk *> chunk_pool;  // recycled local chunks (device buffers kept)
     // phase-2 workspace
     DevBuf d_views, d_work[3], d_scratch, d_scratch_off, out_keys, out_cf, out_keys2, out_cf2, cursor, unit_out_off,
-        unit_out_cnt, unit_final_off, overflow;
+        unit_out_cnt, unit_final_off, overflow, d_retry;
     unsigned long long *h_pinned = nullptr;  // small pinned staging (16 u64)
     std::vector<TimedLaunch> launches;
     std::vector<cudaEvent_t> event_pool;
@@ -307,6 +308,7 @@ __global__ void __launch_bounds__(1024) k_scan_counts_u64(const uint32_t *cnt, u
 constexpr int SM_THREADS_S = 512, SM_CAP_S = 6144;     // 2 CTAs / SM
 constexpr int SM_THREADS_L = 1024, SM_CAP_L = 12288;   // 1 CTA / SM
 constexpr int GL_THREADS = 1024;
+constexpr int HASH_TS_S = 8192, HASH_TS_L = 16384;       // hash-table slots: unit records <= 3/4 of the slots
 
 int32_t merge_range_device(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_buckets, uint64_t *n_entries,
                            uint64_t *unique, uint64_t *total) {
@@ -355,6 +357,8 @@ int32_t merge_range_device(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_
     const uint64_t cap = std::max<uint64_t>(tot_kmers, 1);
     CU(c->out_keys.reserve(cap * 8)); CU(c->out_cf.reserve(cap * 4));
     CU(c->cursor.reserve(64)); CU(c->overflow.reserve(16));
+    CU(c->d_retry.reserve(((size_t)nu + 2) * 4));  // [0] = count, [1..] = unit ids
+    CU(cudaMemsetAsync(c->d_retry.p, 0, 4, st));
     CU(c->unit_out_off.reserve(((size_t)nu + 1) * 8)); CU(c->unit_out_cnt.reserve(((size_t)nu + 1) * 4));
     CU(c->unit_final_off.reserve(((size_t)nu + 1) * 8));
     CU(cudaMemsetAsync(c->cursor.p, 0, 64, st));
@@ -367,6 +371,37 @@ int32_t merge_range_device(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_
     out.unit_out_cnt = c->unit_out_cnt.as<uint32_t>(); out.capacity = cap; out.overflow = c->overflow.as<uint32_t>();
     const ChunkView *dv = c->d_views.as<ChunkView>();
     const uint32_t nch = (uint32_t)views.size();
+    if (c->merge_mode == 1) {
+        uint32_t *retry_cnt = c->d_retry.as<uint32_t>(), *retry = retry_cnt + 1;
+        if (!work[0].empty()) {
+            LaunchTimer t(c, F_MERGE_HASH);
+            auto kern = k_merge_hash<SM_THREADS_S, HASH_TS_S>;
+            const size_t smem = merge_hash_smem_bytes<SM_THREADS_S, HASH_TS_S>();
+            CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            const unsigned grid = (unsigned)std::min<size_t>(work[0].size(), (size_t)c->sm_count * 2 * 8);
+            kern<<<grid, SM_THREADS_S, smem, st>>>(dv, nch, c->d_work[0].as<uint32_t>(), (uint32_t)work[0].size(), u0, P,
+                                                   c->params.min_multiplicity, out, retry, retry_cnt);
+        }
+        if (!work[1].empty()) {
+            LaunchTimer t(c, F_MERGE_HASH);
+            auto kern = k_merge_hash<SM_THREADS_L, HASH_TS_L>;
+            const size_t smem = merge_hash_smem_bytes<SM_THREADS_L, HASH_TS_L>();
+            CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            const unsigned grid = (unsigned)std::min<size_t>(work[1].size(), (size_t)c->sm_count * 8);
+            kern<<<grid, SM_THREADS_L, smem, st>>>(dv, nch, c->d_work[1].as<uint32_t>(), (uint32_t)work[1].size(), u0, P,
+                                                   c->params.min_multiplicity, out, retry, retry_cnt);
+        }
+        if (!work[0].empty() || !work[1].empty()) {
+            // units whose survivors did not leave room for the in-table sort: redo with the sort kernel
+            LaunchTimer t(c, F_MERGE_SMEM);
+            auto kern = k_merge_units<SM_THREADS_L, SM_CAP_L, false>;
+            const size_t smem = merge_smem_bytes<SM_THREADS_L, SM_CAP_L>(false);
+            CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<(unsigned)c->sm_count, SM_THREADS_L, smem, st>>>(dv, nch, retry, 0u, u0, P, c->params.min_multiplicity, out,
+                                                                    nullptr, nullptr, retry_cnt);
+        }
+        work[0].clear(); work[1].clear();
+    }
     if (!work[0].empty()) {
         LaunchTimer t(c, F_MERGE_SMEM);
         auto kern = k_merge_units<SM_THREADS_S, SM_CAP_S, false>;
@@ -374,7 +409,7 @@ int32_t merge_range_device(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const unsigned grid = (unsigned)std::min<size_t>(work[0].size(), (size_t)c->sm_count * 2 * 8);
         kern<<<grid, SM_THREADS_S, smem, st>>>(dv, nch, c->d_work[0].as<uint32_t>(), (uint32_t)work[0].size(), u0, P,
-                                               c->params.min_multiplicity, out, nullptr, nullptr);
+                                               c->params.min_multiplicity, out, nullptr, nullptr, nullptr);
     }
     if (!work[1].empty()) {
         LaunchTimer t(c, F_MERGE_SMEM);
@@ -383,7 +418,7 @@ int32_t merge_range_device(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const unsigned grid = (unsigned)std::min<size_t>(work[1].size(), (size_t)c->sm_count * 8);
         kern<<<grid, SM_THREADS_L, smem, st>>>(dv, nch, c->d_work[1].as<uint32_t>(), (uint32_t)work[1].size(), u0, P,
-                                               c->params.min_multiplicity, out, nullptr, nullptr);
+                                               c->params.min_multiplicity, out, nullptr, nullptr, nullptr);
     }
     if (!work[2].empty()) {
         LaunchTimer t(c, F_MERGE_GLOBAL);
@@ -392,7 +427,7 @@ int32_t merge_range_device(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_
         const unsigned grid = (unsigned)std::min<size_t>(work[2].size(), (size_t)c->sm_count * 2);
         kern<<<grid, GL_THREADS, smem, st>>>(dv, nch, c->d_work[2].as<uint32_t>(), (uint32_t)work[2].size(), u0, P,
                                              c->params.min_multiplicity, out, c->d_scratch.as<uint64_t>(),
-                                             c->d_scratch_off.as<uint64_t>());
+                                             c->d_scratch_off.as<uint64_t>(), nullptr);
     }
     CU(cudaGetLastError());
     // unit-ordered final layout
@@ -475,6 +510,7 @@ int32_t ggcat_b200_create(const ggcat_b200_params *params, ggcat_b200_ctx **out)
     memset(&c->stats, 0, sizeof(c->stats));
     memset(c->fam_ms, 0, sizeof(c->fam_ms));
     memset(c->fam_launches, 0, sizeof(c->fam_launches));
+    if (const char *mm = getenv("GGCAT_B200_MERGE")) c->merge_mode = (strcmp(mm, "sort") == 0) ? 0 : 1;
     if (const char *mb = getenv("GGCAT_B200_MAX_BATCH")) { uint64_t v = strtoull(mb, nullptr, 10); if (v >= 1024) c->max_batch = std::min<uint64_t>(v, 1ull << 30); }
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, p.device) == cudaSuccess) c->sm_count = prop.multiProcessorCount;
@@ -510,7 +546,7 @@ void ggcat_b200_destroy(ggcat_b200_ctx *c) {
     for (DevBuf *b : {&c->d_ascii, &c->d_offsets, &c->d_colors, &c->pk, &c->bad, &c->brk, &c->ent, &c->tile_cnt, &c->tile_sbase,
                       &c->tmp, &c->tmp_color, &c->cur_cnt, &c->cur_words, &c->totals, &c->d_views, &c->d_work[0], &c->d_work[1],
                       &c->d_work[2], &c->d_scratch, &c->d_scratch_off, &c->out_keys, &c->out_cf, &c->out_keys2, &c->out_cf2,
-                      &c->cursor, &c->unit_out_off, &c->unit_out_cnt, &c->unit_final_off, &c->overflow})
+                      &c->cursor, &c->unit_out_off, &c->unit_out_cnt, &c->unit_final_off, &c->overflow, &c->d_retry})
         b->release();
     for (cudaEvent_t e : c->event_pool) cudaEventDestroy(e);
     for (HostTable *t : c->free_tables) { cudaFreeHost(t->keys); cudaFreeHost(t->cf); cudaFreeHost(t->unit_offsets); delete t; }

@@ -70,9 +70,10 @@ __device__ __forceinline__ void expand_superkmer64(const uint32_t *__restrict__ 
 // Stable LSD radix sort of n u64 records living in A (B = scratch of the same size); generic
 // pointers, so A/B may be shared or global memory.  hist: [WARPS][256] u32 in shared memory.
 // Returns the buffer that holds the sorted records.
-template <int THREADS>
+template <int THREADS, bool HAS_VAL = false>
 __device__ uint64_t *block_radix_sort64(uint64_t *A, uint64_t *B, uint32_t n, uint32_t first_bit, uint32_t end_bit,
-                                        uint32_t *hist, uint32_t *s_scan) {
+                                        uint32_t *hist, uint32_t *s_scan, uint32_t *Av = nullptr, uint32_t *Bv = nullptr,
+                                        uint32_t **vals_out = nullptr) {
     constexpr int WARPS = THREADS / 32;
     constexpr int EPT = WARPS * 256 / THREADS;  // scan entries per thread (= 8)
     const uint32_t tid = threadIdx.x, lane = lane_id(), warp = warp_id();
@@ -119,13 +120,16 @@ __device__ uint64_t *block_radix_sort64(uint64_t *A, uint64_t *B, uint32_t n, ui
             __syncwarp();
             if (valid) {
                 B[pos] = rec;
+                if (HAS_VAL) Bv[pos] = Av[i];
                 if (rank + 1 == (uint32_t)__popc(peers)) hist[warp * 256 + d] = pos + 1;
             }
             __syncwarp();
         }
         __syncthreads();
         uint64_t *t = A; A = B; B = t;
+        if (HAS_VAL) { uint32_t *tv = Av; Av = Bv; Bv = tv; }
     }
+    if (HAS_VAL && vals_out) *vals_out = Av;
     return A;
 }
 
@@ -197,7 +201,8 @@ template <int THREADS, int CAP, bool GLOBAL_SCRATCH>
 __global__ void __launch_bounds__(THREADS)
 k_merge_units(const ChunkView *__restrict__ chunks, uint32_t n_chunks, const uint32_t *__restrict__ work,
               uint32_t n_work, uint32_t first_unit, DevParams P, uint32_t min_mult, MergeOut out,
-              uint64_t *__restrict__ scratch, const uint64_t *__restrict__ scratch_off) {
+              uint64_t *__restrict__ scratch, const uint64_t *__restrict__ scratch_off,
+              const uint32_t *__restrict__ n_work_dev = nullptr) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int WARPS = THREADS / 32;
     uint32_t *hist = reinterpret_cast<uint32_t *>(smem_raw);                 // WARPS*256 u32
@@ -207,6 +212,7 @@ k_merge_units(const ChunkView *__restrict__ chunks, uint32_t n_chunks, const uin
     uint64_t *sB = sA + (GLOBAL_SCRATCH ? 0 : CAP);
 
     const uint32_t tid = threadIdx.x;
+    if (n_work_dev) n_work = *n_work_dev;  // retry list filled by k_merge_hash
     for (uint32_t wi = blockIdx.x; wi < n_work; wi += gridDim.x) {
         const uint32_t unit = work[wi];
         uint32_t n = 0;
@@ -253,6 +259,183 @@ k_merge_units(const ChunkView *__restrict__ chunks, uint32_t n_chunks, const uin
                                      s_base);
         __syncthreads();
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_merge_hash: the same unit semantics with a shared-memory hash table instead of a full sort --
+// the device analogue of the reference's FxHashMap<hash, MapEntry> (hashmap.rs:385-399):
+//   slot key  = canonical k-mer (CAS-claimed, linear probing, load <= 0.75),
+//   slot word = MapEntry: counter in bits 0..29 (atomicAdd), flags in bits 30..31 (atomicOr).
+// After all super-k-mers are inserted the table is scanned once: multiplicity = counter >> (flags==3),
+// survivors (multiplicity >= -s) are compacted in place and only THEY are radix-sorted (key order is
+// part of the output contract), so the sort cost scales with the table that leaves the GPU, not with
+// the k-mer occurrences.  Units whose survivors exceed half the table (no room for the sort's second
+// buffer) are appended to `retry` and re-done by the sort-based kernel.
+constexpr uint64_t HASH_EMPTY = ~0ull;
+
+template <int TS>
+__device__ __forceinline__ void hash_insert(uint64_t *K, uint32_t *C, uint64_t key, uint32_t fb) {
+    uint32_t slot = (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> 40) & (TS - 1);
+    while (true) {
+        const unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long *>(&K[slot]), HASH_EMPTY, key);
+        if (old == HASH_EMPTY || old == key) break;
+        slot = (slot + 1) & (TS - 1);
+    }
+    atomicAdd(&C[slot], 1u);
+    if (fb) atomicOr(&C[slot], fb << 30);
+}
+
+template <int TS>
+__device__ __forceinline__ void expand_insert64(const uint32_t *__restrict__ pl, uint32_t len, uint32_t flags, uint32_t k,
+                                                uint32_t forward_only, uint64_t *K, uint32_t *C) {
+    const uint64_t mask = (1ull << (2 * k)) - 1ull;
+    uint64_t fw = extract64(pl, 0) & mask;
+    uint64_t rc = revcomp64(fw) >> (64 - 2 * k);
+    const uint32_t last = len - k;
+    uint32_t cw = 0;
+    for (uint32_t i = 0;; ++i) {
+        const bool isf = forward_only ? true : (fw < rc);
+        const uint64_t key = forward_only ? fw : (fw < rc ? fw : rc);
+        const uint32_t bi = (!(flags & READ_FLAG_INCL_BEGIN) && i == 0) ? 1u : 0u;
+        const uint32_t ei = (!(flags & READ_FLAG_INCL_END) && i == last) ? 1u : 0u;
+        hash_insert<TS>(K, C, key, (bi << (isf ? 0 : 1)) | (ei << (isf ? 1 : 0)));
+        if (i == last) break;
+        const uint32_t nb = i + k;
+        if ((nb & 15u) == 0 || i == 0) cw = pl[nb >> 4];
+        const uint64_t b = (cw >> (2u * (nb & 15u))) & 3u;
+        fw = (fw >> 2) | (b << (2 * (k - 1)));
+        rc = ((rc << 2) | (b ^ 2ull)) & mask;
+    }
+}
+
+template <int THREADS, int TS>
+__global__ void __launch_bounds__(THREADS)
+k_merge_hash(const ChunkView *__restrict__ chunks, uint32_t n_chunks, const uint32_t *__restrict__ work, uint32_t n_work,
+             uint32_t first_unit, DevParams P, uint32_t min_mult, MergeOut out, uint32_t *__restrict__ retry,
+             uint32_t *__restrict__ retry_count) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int WARPS = THREADS / 32;
+    uint64_t *K = reinterpret_cast<uint64_t *>(smem_raw);                      // TS keys
+    uint32_t *C = reinterpret_cast<uint32_t *>(K + TS);                        // TS counters|flags
+    uint32_t *hist = C + TS;                                                   // WARPS*256
+    uint32_t *s_scan = hist + WARPS * 256;                                     // 40
+    unsigned long long *s_base = reinterpret_cast<unsigned long long *>(s_scan + 40);
+    const uint32_t tid = threadIdx.x;
+    for (uint32_t wi = blockIdx.x; wi < n_work; wi += gridDim.x) {
+        const uint32_t unit = work[wi];
+        for (uint32_t i = tid; i < TS; i += THREADS) { K[i] = HASH_EMPTY; C[i] = 0u; }
+        __syncthreads();
+        uint32_t n = 0;
+        for (uint32_t c = 0; c < n_chunks; c++) {
+            const ChunkView cv = chunks[c];
+            if (unit < cv.first_unit || unit >= cv.first_unit + cv.n_units) continue;
+            n += cv.unit_kmers[unit - cv.first_unit];
+            const uint32_t d0 = cv.unit_off[unit - cv.first_unit], d1 = cv.unit_off[unit - cv.first_unit + 1];
+            for (uint32_t di = d0 + tid; di < d1; di += THREADS) {
+                const uint4 d = cv.desc[di];
+                expand_insert64<TS>(cv.payload + (d.x - cv.word_bias), d.y, (d.z >> 16) & 3u, P.k, P.forward_only, K, C);
+            }
+        }
+        __syncthreads();
+        // ---- scan the table once: MapEntry -> multiplicity, filter; survivors are appended to a small
+        //      staging area (aliasing the radix histogram) in arbitrary order
+        constexpr uint32_t STAGE_CAP = (uint32_t)(WARPS * 256 * 4) / 12;   // entries of (u64 key|flags, u32 count|flags)
+        constexpr uint32_t RANK_MAX = 512;                                  // rank-sort threshold
+        uint64_t *stage_k = reinterpret_cast<uint64_t *>(hist);
+        uint32_t *stage_c = reinterpret_cast<uint32_t *>(stage_k + STAGE_CAP);
+        uint32_t *s_cnt = s_scan + 36;  // [0] survivors, [1] occupied slots
+        if (tid < 2) s_cnt[tid] = 0;
+        __syncthreads();
+        {
+            uint32_t my_occ = 0;
+            for (uint32_t i = tid; i < TS; i += THREADS) {
+                const uint64_t kk = K[i];
+                if (kk == HASH_EMPTY) continue;
+                ++my_occ;
+                const uint32_t cc = C[i];
+                const uint32_t cnt = cc & 0x3FFFFFFFu, fl = cc >> 30;
+                const uint32_t mult = cnt >> ((fl == (READ_FLAG_INCL_BEGIN | READ_FLAG_INCL_END)) ? 1 : 0);  // map_entry.rs:79-84
+                if (mult >= min_mult) {
+                    const uint32_t idx = atomicAdd(&s_cnt[0], 1u);
+                    if (idx < STAGE_CAP) { stage_k[idx] = (kk << 2) | fl; stage_c[idx] = mult | (fl << 30); }
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) my_occ += __shfl_xor_sync(0xffffffffu, my_occ, o);
+            if (lane_id() == 0 && my_occ) atomicAdd(&s_cnt[1], my_occ);
+        }
+        __syncthreads();
+        const uint32_t S = s_cnt[0], n_occ = s_cnt[1];
+        const uint32_t end_bit = min(64u, (2 * P.k + 2 + 7) & ~7u);
+        if (S > STAGE_CAP && S > TS / 2) {  // no room for the sort's second buffer: hand the unit to the sort-based kernel
+            if (tid == 0) retry[atomicAdd(retry_count, 1u)] = unit;
+            __syncthreads();
+            continue;
+        }
+        if (tid == 0) {
+            const unsigned long long b = atomicAdd(&out.cursor[0], (unsigned long long)S);
+            atomicAdd(&out.cursor[1], (unsigned long long)n_occ);
+            atomicAdd(&out.cursor[2], (unsigned long long)n);
+            *s_base = b;
+            out.unit_out_off[unit - first_unit] = b;
+            out.unit_out_cnt[unit - first_unit] = S;
+            if (b + S > out.capacity) *out.overflow = 1u;
+        }
+        __syncthreads();
+        const unsigned long long gbase = *s_base;
+        const bool room = gbase + S <= out.capacity;
+        if (S <= RANK_MAX) {
+            // rank sort: keys are distinct, so rank = number of smaller keys is the sorted position
+            if (room) {
+                for (uint32_t i = tid; i < S; i += THREADS) {
+                    const uint64_t r = stage_k[i];
+                    uint32_t rank = 0;
+                    for (uint32_t j = 0; j < S; j++) rank += stage_k[j] < r ? 1u : 0u;
+                    out.keys[gbase + rank] = r >> 2;
+                    out.count_flags[gbase + rank] = stage_c[i];
+                }
+            }
+        } else {
+            if (S <= STAGE_CAP) {  // staging -> table memory (the table is dead now), then key-value radix sort
+                for (uint32_t i = tid; i < S; i += THREADS) { K[i] = stage_k[i]; C[i] = stage_c[i]; }
+                __syncthreads();
+            } else {
+                // many survivors: in-place block-scan compaction of the table itself
+                uint32_t running = 0;
+                for (uint32_t base = 0; base < TS; base += THREADS) {
+                    const uint32_t i = base + tid;
+                    const uint64_t kk = K[i];
+                    const uint32_t cc = C[i];
+                    uint32_t cf = 0, fl = 0;
+                    if (kk != HASH_EMPTY) {
+                        const uint32_t cnt = cc & 0x3FFFFFFFu;
+                        fl = cc >> 30;
+                        const uint32_t mult = cnt >> ((fl == (READ_FLAG_INCL_BEGIN | READ_FLAG_INCL_END)) ? 1 : 0);
+                        if (mult >= min_mult) cf = mult | (fl << 30);
+                    }
+                    uint32_t tot;
+                    const uint32_t p = block_exclusive_scan<THREADS>(cf ? 1u : 0u, s_scan, &tot);  // all reads precede writes
+                    if (cf) { K[running + p] = (kk << 2) | fl; C[running + p] = cf; }
+                    running += tot;
+                }
+                __syncthreads();
+            }
+            uint32_t *Vs = nullptr;
+            uint64_t *Ss = block_radix_sort64<THREADS, true>(K, K + TS / 2, S, 0, end_bit, hist, s_scan, C, C + TS / 2, &Vs);
+            if (room) {
+                for (uint32_t i = tid; i < S; i += THREADS) {
+                    out.keys[gbase + i] = Ss[i] >> 2;
+                    out.count_flags[gbase + i] = Vs[i];
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+template <int THREADS, int TS>
+constexpr size_t merge_hash_smem_bytes() {
+    return (size_t)TS * 12 + (size_t)(THREADS / 32) * 256 * 4 + 40 * 4 + 16;
 }
 
 template <int THREADS, int CAP>
