@@ -91,6 +91,14 @@ class KmerTable:
         self.unique_kmers = unique_kmers
         self.color_offsets = color_offsets
         self.colors = colors
+        self._release = None
+
+    def release(self):
+        """Return zero-copy buffers to the library (no-op for copied tables)."""
+        if self._release is not None:
+            self._release()
+            self._release = None
+            self.keys_lo = self.keys_hi = self.count_flags = self.unit_offsets = None
 
     @property
     def n_entries(self) -> int:
@@ -192,24 +200,37 @@ class GGCATB200:
         return out, payload[: pb.value]
 
     # -- phase 2
-    def merge_bucket_range(self, first_bucket: int, n_buckets: int) -> KmerTable:
+    def merge_bucket_range(self, first_bucket: int, n_buckets: int, copy: bool = True) -> KmerTable:
+        """copy=True: numpy copies, table released immediately.  copy=False: zero-copy views of the library's
+        pinned buffers, valid until ``table.release()`` (what a Rust/C host gets from the C ABI)."""
         t = _lib.TableC()
         _check(self._lib.ggcat_b200_merge_bucket_range(self._h, first_bucket, n_buckets, C.byref(t)))
+
+        def arr(ptr, n, dt):
+            if not n:
+                return np.zeros(0, dt)
+            a = np.ctypeslib.as_array(ptr, shape=(n,))
+            return a.copy() if copy else a
+
         try:
             ne = int(t.n_entries)
-            keys = np.ctypeslib.as_array(t.keys_lo, shape=(ne,)).copy() if ne else np.zeros(0, np.uint64)
-            cf = np.ctypeslib.as_array(t.count_flags, shape=(ne,)).copy() if ne else np.zeros(0, np.uint32)
-            uo = np.ctypeslib.as_array(t.unit_offsets, shape=(int(t.n_units) + 1,)).copy()
-            hi = None
-            if t.keys_hi:
-                hi = np.ctypeslib.as_array(t.keys_hi, shape=(ne,)).copy() if ne else np.zeros(0, np.uint64)
+            keys = arr(t.keys_lo, ne, np.uint64)
+            cf = arr(t.count_flags, ne, np.uint32)
+            uo = arr(t.unit_offsets, int(t.n_units) + 1, np.uint64)
+            hi = arr(t.keys_hi, ne, np.uint64) if t.keys_hi else None
             co = cl = None
             if t.color_offsets:
-                co = np.ctypeslib.as_array(t.color_offsets, shape=(ne + 1,)).copy()
-                cl = np.ctypeslib.as_array(t.colors, shape=(int(co[-1]),)).copy() if co[-1] else np.zeros(0, np.uint32)
-            return KmerTable(keys, hi, cf, int(t.first_unit), uo, int(t.total_kmers), int(t.unique_kmers), co, cl)
-        finally:
+                co = arr(t.color_offsets, ne + 1, np.uint64)
+                cl = arr(t.colors, int(co[-1]), np.uint32)
+            tab = KmerTable(keys, hi, cf, int(t.first_unit), uo, int(t.total_kmers), int(t.unique_kmers), co, cl)
+        except Exception:
             self._lib.ggcat_b200_release_table(self._h, C.byref(t))
+            raise
+        if copy:
+            self._lib.ggcat_b200_release_table(self._h, C.byref(t))
+        else:
+            tab._release = lambda: self._lib.ggcat_b200_release_table(self._h, C.byref(t))
+        return tab
 
     def merge_bucket_range_device(self, first_bucket: int, n_buckets: int):
         """Table stays in HBM; returns (n_entries, unique_kmers, total_kmers)."""

@@ -71,9 +71,11 @@ struct Chunk {
     }
 };
 
-enum Family { F_PACK = 0, F_WINDOWS, F_EMIT, F_SCATTER, F_SCAN, F_MERGE_HASH, F_MERGE_SMEM, F_MERGE_GLOBAL, F_GATHER, F_COUNT };
+enum Family { F_PACK = 0, F_WINDOWS, F_EMIT, F_SCATTER, F_SCAN, F_MERGE_HASH, F_MERGE_HASH_GLOBAL, F_MERGE_SMEM, F_MERGE_GLOBAL,
+              F_GATHER, F_COUNT };
 static const char *kFamilyNames[F_COUNT] = {"k_pack+k_mark", "k_windows", "k_emit", "k_scatter", "k_exclusive_scan_u32",
-                                            "k_merge_hash", "k_merge_units<smem>", "k_merge_units<global>", "k_gather_units"};
+                                            "k_merge_hash<smem>", "k_merge_hash<global>", "k_merge_units<smem>",
+                                            "k_merge_units<global>", "k_gather_units"};
 
 struct TimedLaunch { int fam; cudaEvent_t a, b; };
 
@@ -100,7 +102,7 @@ struct ggcat_b200_ctx {
     std::vector<Chunk *> chunks;
     std::vector<Chunk *> chunk_pool;  // recycled local chunks (device buffers kept)
     // phase-2 workspace
-    DevBuf d_views, d_work[3], d_scratch, d_scratch_off, out_keys, out_cf, out_keys2, out_cf2, cursor, unit_out_off,
+    DevBuf d_views, d_work[3], d_scratch, out_keys, out_cf, out_keys2, out_cf2, cursor, unit_out_off,
         unit_out_cnt, unit_final_off, overflow, d_retry;
     unsigned long long *h_pinned = nullptr;  // small pinned staging (16 u64)
     std::vector<TimedLaunch> launches;
@@ -321,8 +323,8 @@ int32_t merge_range_device(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_
     const uint32_t u0 = first_bucket << P.b2, nu = n_buckets << P.b2;
     // classify units by record count
     std::vector<uint32_t> work[3];
-    std::vector<uint64_t> scratch_off;
-    uint64_t tot_kmers = 0, scratch_total = 0;
+    std::vector<std::pair<uint64_t, uint32_t>> large;  // (records, unit)
+    uint64_t tot_kmers = 0;
     for (uint32_t u = u0; u < u0 + nu; u++) {
         uint64_t n = 0;
         for (Chunk *ch : c->chunks)
@@ -332,7 +334,7 @@ int32_t merge_range_device(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_
         tot_kmers += n;
         if (n <= SM_CAP_S) work[0].push_back(u);
         else if (n <= SM_CAP_L) work[1].push_back(u);
-        else { work[2].push_back(u); scratch_off.push_back(scratch_total); scratch_total += 2 * n; }
+        else large.push_back({n, u});
     }
     // chunk views
     std::vector<ChunkView> views;
@@ -350,15 +352,35 @@ int32_t merge_range_device(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_
         if (!work[q].empty())
             CU(cudaMemcpyAsync(c->d_work[q].p, work[q].data(), work[q].size() * 4, cudaMemcpyHostToDevice, st));
     }
-    CU(c->d_scratch.reserve(std::max<uint64_t>(1, scratch_total) * 8));
-    CU(c->d_scratch_off.reserve(std::max<size_t>(1, scratch_off.size()) * 8));
-    if (!scratch_off.empty())
-        CU(cudaMemcpyAsync(c->d_scratch_off.p, scratch_off.data(), scratch_off.size() * 8, cudaMemcpyHostToDevice, st));
+    // large units: biggest first (one CTA each), split in two tiers so that ordinary large units do not
+    // inherit the per-CTA scratch size of a giant one
+    std::sort(large.begin(), large.end(), [](const auto &a, const auto &b) { return a.first > b.first; });
+    const uint64_t TIER = 1ull << 20;
+    size_t n_giant = 0;
+    while (n_giant < large.size() && large[n_giant].first > TIER) n_giant++;
+    for (auto &pr : large) work[2].push_back(pr.second);
+    struct Tier { size_t first, count; uint64_t per_cta; unsigned grid; };
+    std::vector<Tier> tiers;
+    uint64_t scratch_u64 = 1;
+    for (int t = 0; t < 2; t++) {
+        const size_t first = t == 0 ? 0 : n_giant, count = t == 0 ? n_giant : large.size() - n_giant;
+        if (!count) continue;
+        const uint64_t nmax = large[first].first;
+        const uint64_t per_cta = (uint64_t)hash_table_slots((uint32_t)nmax) * 3 / 2 + 16;  // keys + counters; >= 2n for the sort variant
+        const uint64_t budget = 12ull << 30;
+        uint64_t g = std::min<uint64_t>(std::min<uint64_t>(count, (uint64_t)c->sm_count * 2), std::max<uint64_t>(1, budget / (per_cta * 8)));
+        tiers.push_back({first, count, per_cta, (unsigned)g});
+        scratch_u64 = std::max(scratch_u64, per_cta * g);
+    }
+    CU(c->d_scratch.reserve(scratch_u64 * 8));
     const uint64_t cap = std::max<uint64_t>(tot_kmers, 1);
     CU(c->out_keys.reserve(cap * 8)); CU(c->out_cf.reserve(cap * 4));
     CU(c->cursor.reserve(64)); CU(c->overflow.reserve(16));
-    CU(c->d_retry.reserve(((size_t)nu + 2) * 4));  // [0] = count, [1..] = unit ids
-    CU(cudaMemsetAsync(c->d_retry.p, 0, 4, st));
+    CU(c->d_retry.reserve(((size_t)nu + 2) * 4 * 2));  // two lists: [0] = count, [1..] = unit ids
+    uint32_t *retry_cnt = c->d_retry.as<uint32_t>(), *retry = retry_cnt + 1;
+    uint32_t *retry2_cnt = retry_cnt + nu + 2, *retry2 = retry2_cnt + 1;
+    CU(cudaMemsetAsync(retry_cnt, 0, 4, st));
+    CU(cudaMemsetAsync(retry2_cnt, 0, 4, st));
     CU(c->unit_out_off.reserve(((size_t)nu + 1) * 8)); CU(c->unit_out_cnt.reserve(((size_t)nu + 1) * 4));
     CU(c->unit_final_off.reserve(((size_t)nu + 1) * 8));
     CU(cudaMemsetAsync(c->cursor.p, 0, 64, st));
@@ -372,7 +394,6 @@ int32_t merge_range_device(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_
     const ChunkView *dv = c->d_views.as<ChunkView>();
     const uint32_t nch = (uint32_t)views.size();
     if (c->merge_mode == 1) {
-        uint32_t *retry_cnt = c->d_retry.as<uint32_t>(), *retry = retry_cnt + 1;
         if (!work[0].empty()) {
             LaunchTimer t(c, F_MERGE_HASH);
             auto kern = k_merge_hash<SM_THREADS_S, HASH_TS_S>;
@@ -380,7 +401,7 @@ int32_t merge_range_device(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_
             CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             const unsigned grid = (unsigned)std::min<size_t>(work[0].size(), (size_t)c->sm_count * 2 * 8);
             kern<<<grid, SM_THREADS_S, smem, st>>>(dv, nch, c->d_work[0].as<uint32_t>(), (uint32_t)work[0].size(), u0, P,
-                                                   c->params.min_multiplicity, out, retry, retry_cnt);
+                                                   c->params.min_multiplicity, out, retry, retry_cnt, nullptr, 0);
         }
         if (!work[1].empty()) {
             LaunchTimer t(c, F_MERGE_HASH);
@@ -389,7 +410,7 @@ int32_t merge_range_device(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_
             CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             const unsigned grid = (unsigned)std::min<size_t>(work[1].size(), (size_t)c->sm_count * 8);
             kern<<<grid, SM_THREADS_L, smem, st>>>(dv, nch, c->d_work[1].as<uint32_t>(), (uint32_t)work[1].size(), u0, P,
-                                                   c->params.min_multiplicity, out, retry, retry_cnt);
+                                                   c->params.min_multiplicity, out, retry, retry_cnt, nullptr, 0);
         }
         if (!work[0].empty() || !work[1].empty()) {
             // units whose survivors did not leave room for the in-table sort: redo with the sort kernel
@@ -398,7 +419,7 @@ int32_t merge_range_device(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_
             const size_t smem = merge_smem_bytes<SM_THREADS_L, SM_CAP_L>(false);
             CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             kern<<<(unsigned)c->sm_count, SM_THREADS_L, smem, st>>>(dv, nch, retry, 0u, u0, P, c->params.min_multiplicity, out,
-                                                                    nullptr, nullptr, retry_cnt);
+                                                                    nullptr, 0, retry_cnt);
         }
         work[0].clear(); work[1].clear();
     }
@@ -409,7 +430,7 @@ int32_t merge_range_device(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const unsigned grid = (unsigned)std::min<size_t>(work[0].size(), (size_t)c->sm_count * 2 * 8);
         kern<<<grid, SM_THREADS_S, smem, st>>>(dv, nch, c->d_work[0].as<uint32_t>(), (uint32_t)work[0].size(), u0, P,
-                                               c->params.min_multiplicity, out, nullptr, nullptr, nullptr);
+                                               c->params.min_multiplicity, out, nullptr, 0, nullptr);
     }
     if (!work[1].empty()) {
         LaunchTimer t(c, F_MERGE_SMEM);
@@ -418,16 +439,31 @@ int32_t merge_range_device(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const unsigned grid = (unsigned)std::min<size_t>(work[1].size(), (size_t)c->sm_count * 8);
         kern<<<grid, SM_THREADS_L, smem, st>>>(dv, nch, c->d_work[1].as<uint32_t>(), (uint32_t)work[1].size(), u0, P,
-                                               c->params.min_multiplicity, out, nullptr, nullptr, nullptr);
+                                               c->params.min_multiplicity, out, nullptr, 0, nullptr);
     }
-    if (!work[2].empty()) {
-        LaunchTimer t(c, F_MERGE_GLOBAL);
-        auto kern = k_merge_units<GL_THREADS, 0, true>;
-        const size_t smem = merge_smem_bytes<GL_THREADS, 0>(true);
-        const unsigned grid = (unsigned)std::min<size_t>(work[2].size(), (size_t)c->sm_count * 2);
-        kern<<<grid, GL_THREADS, smem, st>>>(dv, nch, c->d_work[2].as<uint32_t>(), (uint32_t)work[2].size(), u0, P,
-                                             c->params.min_multiplicity, out, c->d_scratch.as<uint64_t>(),
-                                             c->d_scratch_off.as<uint64_t>(), nullptr);
+    for (const Tier &tr : tiers) {
+        const uint32_t *wl = c->d_work[2].as<uint32_t>() + tr.first;
+        auto sortk = k_merge_units<GL_THREADS, 0, true>;
+        const size_t smem_sort = merge_smem_bytes<GL_THREADS, 0>(true);
+        if (c->merge_mode == 1) {
+            {
+                LaunchTimer t(c, F_MERGE_HASH_GLOBAL);
+                auto kern = k_merge_hash<GL_THREADS, 0>;
+                kern<<<tr.grid, GL_THREADS, merge_hash_smem_bytes<GL_THREADS, 0>(), st>>>(
+                    dv, nch, wl, (uint32_t)tr.count, u0, P, c->params.min_multiplicity, out, retry2, retry2_cnt,
+                    c->d_scratch.as<uint64_t>(), tr.per_cta);
+            }
+            {   // survivors > half the table: redo those units with the global-scratch sort
+                LaunchTimer t(c, F_MERGE_GLOBAL);
+                sortk<<<tr.grid, GL_THREADS, smem_sort, st>>>(dv, nch, retry2, 0u, u0, P, c->params.min_multiplicity, out,
+                                                             c->d_scratch.as<uint64_t>(), tr.per_cta, retry2_cnt);
+            }
+            CU(cudaMemsetAsync(retry2_cnt, 0, 4, st));
+        } else {
+            LaunchTimer t(c, F_MERGE_GLOBAL);
+            sortk<<<tr.grid, GL_THREADS, smem_sort, st>>>(dv, nch, wl, (uint32_t)tr.count, u0, P, c->params.min_multiplicity, out,
+                                                         c->d_scratch.as<uint64_t>(), tr.per_cta, nullptr);
+        }
     }
     CU(cudaGetLastError());
     // unit-ordered final layout
@@ -545,7 +581,7 @@ void ggcat_b200_destroy(ggcat_b200_ctx *c) {
     collect_timings(c);
     for (DevBuf *b : {&c->d_ascii, &c->d_offsets, &c->d_colors, &c->pk, &c->bad, &c->brk, &c->ent, &c->tile_cnt, &c->tile_sbase,
                       &c->tmp, &c->tmp_color, &c->cur_cnt, &c->cur_words, &c->totals, &c->d_views, &c->d_work[0], &c->d_work[1],
-                      &c->d_work[2], &c->d_scratch, &c->d_scratch_off, &c->out_keys, &c->out_cf, &c->out_keys2, &c->out_cf2,
+                      &c->d_work[2], &c->d_scratch, &c->out_keys, &c->out_cf, &c->out_keys2, &c->out_cf2,
                       &c->cursor, &c->unit_out_off, &c->unit_out_cnt, &c->unit_final_off, &c->overflow, &c->d_retry})
         b->release();
     for (cudaEvent_t e : c->event_pool) cudaEventDestroy(e);

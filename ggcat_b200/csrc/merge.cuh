@@ -201,7 +201,7 @@ template <int THREADS, int CAP, bool GLOBAL_SCRATCH>
 __global__ void __launch_bounds__(THREADS)
 k_merge_units(const ChunkView *__restrict__ chunks, uint32_t n_chunks, const uint32_t *__restrict__ work,
               uint32_t n_work, uint32_t first_unit, DevParams P, uint32_t min_mult, MergeOut out,
-              uint64_t *__restrict__ scratch, const uint64_t *__restrict__ scratch_off,
+              uint64_t *__restrict__ scratch, uint64_t per_cta_u64,
               const uint32_t *__restrict__ n_work_dev = nullptr) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int WARPS = THREADS / 32;
@@ -226,7 +226,7 @@ k_merge_units(const ChunkView *__restrict__ chunks, uint32_t n_chunks, const uin
         }
         uint64_t *A, *B;
         if (GLOBAL_SCRATCH) {
-            A = scratch + scratch_off[wi];
+            A = scratch + (uint64_t)blockIdx.x * per_cta_u64;  // this CTA's slice: >= 2n records
             B = A + n;
         } else {
             A = sA; B = sB;
@@ -273,21 +273,19 @@ k_merge_units(const ChunkView *__restrict__ chunks, uint32_t n_chunks, const uin
 // buffer) are appended to `retry` and re-done by the sort-based kernel.
 constexpr uint64_t HASH_EMPTY = ~0ull;
 
-template <int TS>
-__device__ __forceinline__ void hash_insert(uint64_t *K, uint32_t *C, uint64_t key, uint32_t fb) {
-    uint32_t slot = (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> 40) & (TS - 1);
+__device__ __forceinline__ void hash_insert(uint64_t *K, uint32_t *C, uint32_t mask, uint64_t key, uint32_t fb) {
+    uint32_t slot = (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> 33) & mask;
     while (true) {
         const unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long *>(&K[slot]), HASH_EMPTY, key);
         if (old == HASH_EMPTY || old == key) break;
-        slot = (slot + 1) & (TS - 1);
+        slot = (slot + 1) & mask;
     }
     atomicAdd(&C[slot], 1u);
     if (fb) atomicOr(&C[slot], fb << 30);
 }
 
-template <int TS>
 __device__ __forceinline__ void expand_insert64(const uint32_t *__restrict__ pl, uint32_t len, uint32_t flags, uint32_t k,
-                                                uint32_t forward_only, uint64_t *K, uint32_t *C) {
+                                                uint32_t forward_only, uint64_t *K, uint32_t *C, uint32_t tmask) {
     const uint64_t mask = (1ull << (2 * k)) - 1ull;
     uint64_t fw = extract64(pl, 0) & mask;
     uint64_t rc = revcomp64(fw) >> (64 - 2 * k);
@@ -298,7 +296,7 @@ __device__ __forceinline__ void expand_insert64(const uint32_t *__restrict__ pl,
         const uint64_t key = forward_only ? fw : (fw < rc ? fw : rc);
         const uint32_t bi = (!(flags & READ_FLAG_INCL_BEGIN) && i == 0) ? 1u : 0u;
         const uint32_t ei = (!(flags & READ_FLAG_INCL_END) && i == last) ? 1u : 0u;
-        hash_insert<TS>(K, C, key, (bi << (isf ? 0 : 1)) | (ei << (isf ? 1 : 0)));
+        hash_insert(K, C, tmask, key, (bi << (isf ? 0 : 1)) | (ei << (isf ? 1 : 0)));
         if (i == last) break;
         const uint32_t nb = i + k;
         if ((nb & 15u) == 0 || i == 0) cw = pl[nb >> 4];
@@ -308,32 +306,51 @@ __device__ __forceinline__ void expand_insert64(const uint32_t *__restrict__ pl,
     }
 }
 
-template <int THREADS, int TS>
+// TS_STATIC > 0: table of TS_STATIC slots in shared memory.  TS_STATIC == 0: table in this CTA's slice of a
+// global scratch buffer (L2-resident for typical units), sized per unit: hash_table_slots(n).
+__host__ __device__ __forceinline__ uint32_t hash_table_slots(uint32_t n) {  // power of two >= 1.5 n
+    uint32_t t = 1024;
+    const uint64_t want = (uint64_t)n + n / 2;
+    while (t < want) t <<= 1;
+    return t;
+}
+
+template <int THREADS, int TS_STATIC>
 __global__ void __launch_bounds__(THREADS)
 k_merge_hash(const ChunkView *__restrict__ chunks, uint32_t n_chunks, const uint32_t *__restrict__ work, uint32_t n_work,
              uint32_t first_unit, DevParams P, uint32_t min_mult, MergeOut out, uint32_t *__restrict__ retry,
-             uint32_t *__restrict__ retry_count) {
+             uint32_t *__restrict__ retry_count, uint64_t *__restrict__ scratch, uint64_t per_cta_u64) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int WARPS = THREADS / 32;
     uint64_t *K = reinterpret_cast<uint64_t *>(smem_raw);                      // TS keys
-    uint32_t *C = reinterpret_cast<uint32_t *>(K + TS);                        // TS counters|flags
-    uint32_t *hist = C + TS;                                                   // WARPS*256
+    uint32_t *C = reinterpret_cast<uint32_t *>(K + TS_STATIC);                 // TS counters|flags
+    uint32_t *hist = C + TS_STATIC;                                            // WARPS*256
     uint32_t *s_scan = hist + WARPS * 256;                                     // 40
     unsigned long long *s_base = reinterpret_cast<unsigned long long *>(s_scan + 40);
     const uint32_t tid = threadIdx.x;
     for (uint32_t wi = blockIdx.x; wi < n_work; wi += gridDim.x) {
         const uint32_t unit = work[wi];
+        uint32_t n = 0;
+        for (uint32_t c = 0; c < n_chunks; c++) {
+            const ChunkView &cv = chunks[c];
+            if (unit >= cv.first_unit && unit < cv.first_unit + cv.n_units) n += cv.unit_kmers[unit - cv.first_unit];
+        }
+        uint32_t TS = TS_STATIC;
+        if (TS_STATIC == 0) {
+            TS = hash_table_slots(n);
+            K = scratch + (uint64_t)blockIdx.x * per_cta_u64;
+            C = reinterpret_cast<uint32_t *>(K + TS);
+        }
+        const uint32_t tmask = TS - 1;
         for (uint32_t i = tid; i < TS; i += THREADS) { K[i] = HASH_EMPTY; C[i] = 0u; }
         __syncthreads();
-        uint32_t n = 0;
         for (uint32_t c = 0; c < n_chunks; c++) {
             const ChunkView cv = chunks[c];
             if (unit < cv.first_unit || unit >= cv.first_unit + cv.n_units) continue;
-            n += cv.unit_kmers[unit - cv.first_unit];
             const uint32_t d0 = cv.unit_off[unit - cv.first_unit], d1 = cv.unit_off[unit - cv.first_unit + 1];
             for (uint32_t di = d0 + tid; di < d1; di += THREADS) {
                 const uint4 d = cv.desc[di];
-                expand_insert64<TS>(cv.payload + (d.x - cv.word_bias), d.y, (d.z >> 16) & 3u, P.k, P.forward_only, K, C);
+                expand_insert64(cv.payload + (d.x - cv.word_bias), d.y, (d.z >> 16) & 3u, P.k, P.forward_only, K, C, tmask);
             }
         }
         __syncthreads();
@@ -433,9 +450,9 @@ k_merge_hash(const ChunkView *__restrict__ chunks, uint32_t n_chunks, const uint
     }
 }
 
-template <int THREADS, int TS>
+template <int THREADS, int TS_STATIC>
 constexpr size_t merge_hash_smem_bytes() {
-    return (size_t)TS * 12 + (size_t)(THREADS / 32) * 256 * 4 + 40 * 4 + 16;
+    return (size_t)TS_STATIC * 12 + (size_t)(THREADS / 32) * 256 * 4 + 40 * 4 + 16;
 }
 
 template <int THREADS, int CAP>

@@ -147,6 +147,22 @@ def test_unit_size_paths(n_bases):
         ctx.close()
 
 
+@pytest.mark.parametrize("n_bases", [5800, 11500, 20000, 45000])
+def test_all_distinct_units_retry_paths(n_bases):
+    """-s 1 on a single random sequence: nearly every k-mer survives, so the hash kernels cannot sort the
+    survivors inside their table and hand the unit to the sort-based kernels (smem and global retry lists)."""
+    G = _gpu()
+    rng = np.random.default_rng(n_bases + 1)
+    k, m, b1, b2, s = 31, 12, 0, 0, 1
+    reads = O.Reads.from_list([util.rand_seq(rng, n_bases)])
+    sk, _ = O.bucketing(reads, k, m, b1, b2)
+    ctx, st = G.minimizer_bucketing([(reads.data, reads.offsets)], b1, b2, k, m, min_multiplicity=s)
+    try:
+        _check_tables(G, ctx, reads, sk, k, s, b1, b2)
+    finally:
+        ctx.close()
+
+
 def test_multiple_pushes_equal_single_push():
     """Chunk invariance: the table does not depend on how the input was batched."""
     G = _gpu()
