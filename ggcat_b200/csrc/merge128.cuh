@@ -1,0 +1,417 @@
+// merge128.cuh -- phase 2 for wide keys: 128-bit k-mer identities and coloured builds.
+//
+// Same unit semantics as merge.cuh (hashmap.rs:361-409 add_sequence + map_entry.rs:33-84), for the key
+// families the 64-bit path cannot hold:
+//   MODE_SEQ128  canonical / forward seq-hash of 32 <= k <= 64 (crates/hashes/src/base/cn_seqhash_base.rs:22-70,
+//                fw_seqhash_base.rs:91-107, u128 instantiation cn_seqhash.rs:15-27)
+//   MODE_RK128   canonical / forward Rabin-Karp mod 2^128 (crates/hashes/src/base/cn_rkhash_base.rs:64-110,
+//                fw_rkhash_base.rs:57-69, constants cn_rkhash.rs:65-78, M^(k-1) from hashes/src/lib.rs:169-191)
+//   MODE_COLOR   seq-hash key of k <= 48 with the colour id of the super-k-mer appended:
+//                slot key = (k-mer << 32) | colour, so the table holds one entry per distinct (k-mer, colour)
+//                -- the device form of "colours appended per occurrence, sort_unstable + dedup"
+//                (crates/colors/src/managers/multiple.rs:198-203,221-223).
+// Pipeline per bucket range:
+//   k_merge_hash128   one CTA per unit: 128-bit CAS hash table (shared memory, or an L2/HBM scratch slice for big
+//                     units), MapEntry word per slot; surviving slots are appended UNSORTED to the range output
+//   k_sort_units128   one CTA per unit: LSD radix sort of the unit's entries by key (shared memory when they fit,
+//                     global ping-pong otherwise) into the unit-ordered final table
+//   k_color_count / k_color_write   (MODE_COLOR) fold the (k-mer, colour) entries of each k-mer: sum counters, OR
+//                     flags, halve if flags == 3, apply -s, emit CSR colour lists
+#pragma once
+#include "merge.cuh"
+
+namespace ggb {
+
+typedef unsigned __int128 u128;
+
+struct __align__(16) K128 {
+    unsigned long long lo, hi;
+};
+
+enum { MODE_SEQ128 = 0, MODE_RK128 = 1, MODE_COLOR = 2 };
+
+// Rabin-Karp tables, indexed by 2-bit base code (A0 C1 T2 G3): cn_rkhash_base.rs:10-44 + cn_rkhash.rs:69-75.
+struct RkTables {
+    K128 mult;          // MULTIPLIER
+    K128 mult_inv;      // MULT_INV
+    K128 fwd[4];        // L[c]
+    K128 bkw[4];        // L[c ^ 2]
+    K128 fwd_mk[4];     // L[c] * M^k        (leaving base, forward hash)
+    K128 bkw_mk1[4];    // L[c ^ 2] * M^(k-1) (entering base, reverse hash)
+};
+
+__host__ __device__ __forceinline__ u128 to_u128(K128 v) { return ((u128)v.hi << 64) | (u128)v.lo; }
+__host__ __device__ __forceinline__ K128 to_k128(u128 v) { return K128{(unsigned long long)v, (unsigned long long)(v >> 64)}; }
+
+struct MergeOut128 {
+    uint64_t *keys_lo, *keys_hi;
+    uint32_t *count_flags;
+    unsigned long long *cursor;   // [0] entries written, [1] distinct slot keys, [2] k-mer occurrences
+    uint64_t *unit_out_off;
+    uint32_t *unit_out_cnt;
+    uint64_t capacity;
+    uint32_t *overflow;
+};
+
+constexpr unsigned long long EMPTY64 = ~0ull;
+
+__device__ __forceinline__ uint32_t mix128(unsigned long long lo, unsigned long long hi) {
+    unsigned long long x = (lo ^ (hi * 0x9E3779B97F4A7C15ull)) * 0xD6E8FEB86659FD93ull;
+    return (uint32_t)(x >> 32);
+}
+
+// Insert one k-mer occurrence: claim / find the slot with a 128-bit CAS (ATOMS.CAS.128 / ATOMG.CAS.128),
+// then MapEntry::incr_by_and_check + update_flags on the slot word.
+__device__ __forceinline__ void hash_insert128(K128 *K, uint32_t *C, uint32_t mask, u128 key, uint32_t fb) {
+    const K128 want = to_k128(key);
+    const K128 empty = K128{EMPTY64, EMPTY64};
+    uint32_t slot = mix128(want.lo, want.hi) & mask;
+    while (true) {
+        const K128 old = atomicCAS(&K[slot], empty, want);
+        if ((old.lo == EMPTY64 && old.hi == EMPTY64) || (old.lo == want.lo && old.hi == want.hi)) break;
+        slot = (slot + 1) & mask;
+    }
+    atomicAdd(&C[slot], 1u);
+    if (fb) atomicOr(&C[slot], fb << 30);
+}
+
+__device__ __forceinline__ u128 revcomp128(u128 x) {
+    return ((u128)revcomp64((uint64_t)x) << 64) | (u128)revcomp64((uint64_t)(x >> 64));
+}
+
+__device__ __forceinline__ uint32_t flag_bits(uint32_t flags, uint32_t i, uint32_t last, bool isf) {
+    const uint32_t bi = (!(flags & READ_FLAG_INCL_BEGIN) && i == 0) ? 1u : 0u;
+    const uint32_t ei = (!(flags & READ_FLAG_INCL_END) && i == last) ? 1u : 0u;
+    return (bi << (isf ? 0 : 1)) | (ei << (isf ? 1 : 0));  // hashmap.rs:385-399
+}
+
+// All k-mers of one stored super-k-mer -> f(key, flag bits).
+template <int MODE, typename F>
+__device__ __forceinline__ void for_each_kmer128(const uint32_t *__restrict__ pl, uint32_t len, uint32_t flags, uint32_t k,
+                                                 uint32_t forward_only, const RkTables &T, F f) {
+    const uint32_t last = len - k;
+    if (MODE != MODE_RK128) {
+        const u128 mask = (k >= 64) ? ~(u128)0 : ((((u128)1) << (2 * k)) - 1);
+        u128 fw = 0;
+        const uint32_t nw = (2 * k + 31) >> 5;
+        for (uint32_t w = 0; w < nw; w++) fw |= (u128)pl[w] << (32 * w);
+        fw &= mask;
+        u128 rc = revcomp128(fw) >> (128 - 2 * k);
+        uint32_t cw = 0;
+        for (uint32_t i = 0;; ++i) {
+            const bool isf = forward_only ? true : (fw < rc);
+            const u128 key = forward_only ? fw : (fw < rc ? fw : rc);
+            f(key, flag_bits(flags, i, last, isf));
+            if (i == last) break;
+            const uint32_t nb = i + k;
+            if ((nb & 15u) == 0 || i == 0) cw = pl[nb >> 4];
+            const u128 b = (cw >> (2u * (nb & 15u))) & 3u;
+            fw = (fw >> 2) | (b << (2 * (k - 1)));
+            rc = ((rc << 2) | (b ^ (u128)2)) & mask;
+        }
+    } else {
+        const u128 M = to_u128(T.mult), MI = to_u128(T.mult_inv);
+        u128 fw = 0, rc = 0;
+        for (uint32_t i = 0; i < k; i++) fw = fw * M + to_u128(T.fwd[packed_base(pl, i)]);
+        for (uint32_t i = k; i-- > 0;) rc = rc * M + to_u128(T.bkw[packed_base(pl, i)]);
+        for (uint32_t i = 0;; ++i) {
+            const bool isf = forward_only ? true : (fw < rc);
+            const u128 key = forward_only ? fw : (fw < rc ? fw : rc);
+            f(key, flag_bits(flags, i, last, isf));
+            if (i == last) break;
+            const uint32_t co = packed_base(pl, i), ci = packed_base(pl, i + k);
+            fw = fw * M - to_u128(T.fwd_mk[co]) + to_u128(T.fwd[ci]);
+            rc = (rc - to_u128(T.bkw[co])) * MI + to_u128(T.bkw_mk1[ci]);
+        }
+    }
+}
+
+template <int THREADS, int TS_STATIC>
+constexpr size_t merge_hash128_smem_bytes() {
+    return (size_t)TS_STATIC * 20 + 64;
+}
+
+// TS_STATIC > 0: table in shared memory (units with <= 3/4 TS_STATIC records).  TS_STATIC == 0: table in this CTA's
+// slice of `scratch` (hash_table_slots(n) slots of 20 bytes).
+template <int THREADS, int TS_STATIC, int MODE>
+__global__ void __launch_bounds__(THREADS)
+k_merge_hash128(const ChunkView *__restrict__ chunks, uint32_t n_chunks, const uint32_t *__restrict__ work, uint32_t n_work,
+                uint32_t first_unit, DevParams P, RkTables T, uint32_t min_mult, MergeOut128 out,
+                uint64_t *__restrict__ scratch, uint64_t per_cta_u64) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    K128 *K = reinterpret_cast<K128 *>(smem_raw);
+    uint32_t *C = reinterpret_cast<uint32_t *>(K + TS_STATIC);
+    __shared__ uint32_t s_cnt[2];
+    __shared__ unsigned long long s_base;
+    const uint32_t tid = threadIdx.x;
+    for (uint32_t wi = blockIdx.x; wi < n_work; wi += gridDim.x) {
+        const uint32_t unit = work[wi];
+        uint32_t n = 0;
+        for (uint32_t c = 0; c < n_chunks; c++) {
+            const ChunkView &cv = chunks[c];
+            if (unit >= cv.first_unit && unit < cv.first_unit + cv.n_units) n += cv.unit_kmers[unit - cv.first_unit];
+        }
+        uint32_t TS = TS_STATIC;
+        if (TS_STATIC == 0) {
+            TS = hash_table_slots(n);
+            K = reinterpret_cast<K128 *>(scratch + (uint64_t)blockIdx.x * per_cta_u64);
+            C = reinterpret_cast<uint32_t *>(K + TS);
+        }
+        const uint32_t tmask = TS - 1;
+        for (uint32_t i = tid; i < TS; i += THREADS) { K[i] = K128{EMPTY64, EMPTY64}; C[i] = 0u; }
+        if (tid < 2) s_cnt[tid] = 0;
+        __syncthreads();
+        for (uint32_t c = 0; c < n_chunks; c++) {
+            const ChunkView cv = chunks[c];
+            if (unit < cv.first_unit || unit >= cv.first_unit + cv.n_units) continue;
+            const uint32_t d0 = cv.unit_off[unit - cv.first_unit], d1 = cv.unit_off[unit - cv.first_unit + 1];
+            for (uint32_t di = d0 + tid; di < d1; di += THREADS) {
+                const uint4 d = cv.desc[di];
+                const uint32_t color = d.w;
+                for_each_kmer128<MODE>(cv.payload + (d.x - cv.word_bias), d.y, (d.z >> 16) & 3u, P.k, P.forward_only, T,
+                                       [&](u128 key, uint32_t fb) {
+                                           if (MODE == MODE_COLOR) key = (key << 32) | (u128)color;
+                                           hash_insert128(K, C, tmask, key, fb);
+                                       });
+            }
+        }
+        __syncthreads();
+        // ---- pass 1 over the table: count survivors (MODE_COLOR: every occupied slot; the -s filter needs the
+        //      per-k-mer fold, done after the sort)
+        {
+            uint32_t my_keep = 0, my_occ = 0;
+            for (uint32_t i = tid; i < TS; i += THREADS) {
+                const K128 kk = K[i];
+                if (kk.lo == EMPTY64 && kk.hi == EMPTY64) continue;
+                ++my_occ;
+                if (MODE == MODE_COLOR) { ++my_keep; continue; }
+                const uint32_t cc = C[i];
+                const uint32_t cnt = cc & 0x3FFFFFFFu, fl = cc >> 30;
+                const uint32_t mult = cnt >> ((fl == 3u) ? 1 : 0);  // map_entry.rs:79-84
+                if (mult >= min_mult) ++my_keep;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                my_keep += __shfl_xor_sync(0xffffffffu, my_keep, o);
+                my_occ += __shfl_xor_sync(0xffffffffu, my_occ, o);
+            }
+            if (lane_id() == 0) { if (my_keep) atomicAdd(&s_cnt[0], my_keep); if (my_occ) atomicAdd(&s_cnt[1], my_occ); }
+        }
+        __syncthreads();
+        const uint32_t S = s_cnt[0];
+        if (tid == 0) {
+            const unsigned long long b = atomicAdd(&out.cursor[0], (unsigned long long)S);
+            atomicAdd(&out.cursor[1], (unsigned long long)s_cnt[1]);
+            atomicAdd(&out.cursor[2], (unsigned long long)n);
+            s_base = b;
+            out.unit_out_off[unit - first_unit] = b;
+            out.unit_out_cnt[unit - first_unit] = S;
+            if (b + S > out.capacity) *out.overflow = 1u;
+        }
+        __syncthreads();
+        const unsigned long long gbase = s_base;
+        if (tid == 0) s_cnt[0] = 0;
+        __syncthreads();
+        // ---- pass 2: append survivors (arbitrary order inside the unit's range; k_sort_units128 orders them)
+        if (gbase + S <= out.capacity) {
+            for (uint32_t base = 0; base < TS; base += THREADS) {
+                const uint32_t i = base + tid;
+                bool keep = false;
+                K128 kk = K128{0, 0};
+                uint32_t cf = 0;
+                if (i < TS) {
+                    kk = K[i];
+                    if (!(kk.lo == EMPTY64 && kk.hi == EMPTY64)) {
+                        const uint32_t cc = C[i];
+                        if (MODE == MODE_COLOR) { keep = true; cf = cc; }
+                        else {
+                            const uint32_t cnt = cc & 0x3FFFFFFFu, fl = cc >> 30;
+                            const uint32_t mult = cnt >> ((fl == 3u) ? 1 : 0);
+                            if (mult >= min_mult) { keep = true; cf = mult | (fl << 30); }
+                        }
+                    }
+                }
+                const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+                uint32_t wbase = 0;
+                if (lane_id() == 0 && bal) wbase = atomicAdd(&s_cnt[0], (uint32_t)__popc(bal));
+                wbase = __shfl_sync(0xffffffffu, wbase, 0);
+                if (keep) {
+                    const unsigned long long o = gbase + wbase + __popc(bal & ((1u << lane_id()) - 1u));
+                    out.keys_lo[o] = kk.lo; out.keys_hi[o] = kk.hi; out.count_flags[o] = cf;
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stable LSD radix sort of n (lo, hi, val) records, 8-bit digits of the 128-bit key from first_bit to end_bit;
+// passes whose digit is constant over the unit are skipped.  Generic pointers (shared or global memory).
+// Returns 0 if the result is in (Alo, Ahi, Av), 1 if in (Blo, Bhi, Bv).
+template <int THREADS>
+__device__ int block_radix_sort128(uint64_t *Alo, uint64_t *Ahi, uint32_t *Av, uint64_t *Blo, uint64_t *Bhi, uint32_t *Bv,
+                                   uint32_t n, uint32_t first_bit, uint32_t end_bit, uint32_t *hist, uint32_t *s_scan) {
+    constexpr int WARPS = THREADS / 32;
+    constexpr int EPT = WARPS * 256 / THREADS;
+    const uint32_t tid = threadIdx.x, lane = lane_id(), warp = warp_id();
+    uint32_t chunk = (n + WARPS - 1) / WARPS;
+    chunk = (chunk + 31u) & ~31u;
+    const uint32_t wbeg = min(n, warp * chunk), wend = min(n, wbeg + chunk);
+    int where = 0;
+    for (uint32_t shift = first_bit; shift < end_bit; shift += 8) {
+        const uint64_t *src = shift < 64 ? Alo : Ahi;
+        const uint32_t sh = shift & 63u;
+        for (uint32_t i = tid; i < WARPS * 256; i += THREADS) hist[i] = 0;
+        __syncthreads();
+        for (uint32_t i = wbeg + lane; i < wend; i += 32) atomicAdd(&hist[warp * 256 + ((uint32_t)(src[i] >> sh) & 255u)], 1u);
+        __syncthreads();
+        uint32_t single;
+        {
+            uint32_t v[EPT];
+            uint32_t sum = 0, digit_tot = 0, one = 0;
+#pragma unroll
+            for (int q = 0; q < EPT; q++) {
+                const uint32_t e = tid * EPT + q;
+                v[q] = hist[(e % WARPS) * 256 + (e / WARPS)];
+                sum += v[q];
+            }
+            // EPT consecutive entries of one thread belong to one digit when WARPS % EPT == 0 (16/8, 32/8)
+            digit_tot = sum;
+            for (int o = 1; o < WARPS / EPT; o <<= 1) digit_tot += __shfl_xor_sync(0xffffffffu, digit_tot, o);
+            one = (digit_tot == n) ? 1u : 0u;
+            uint32_t tot;
+            uint32_t p = block_exclusive_scan<THREADS>(sum, s_scan, &tot);
+#pragma unroll
+            for (int q = 0; q < EPT; q++) {
+                const uint32_t e = tid * EPT + q;
+                hist[(e % WARPS) * 256 + (e / WARPS)] = p;
+                p += v[q];
+            }
+            single = __syncthreads_or((int)one);
+        }
+        if (single) continue;  // every record has the same digit: the pass is the identity
+        for (uint32_t base = wbeg; base < wend; base += 32) {
+            const uint32_t i = base + lane;
+            const bool valid = i < wend;
+            const uint64_t lo = valid ? Alo[i] : 0ull, hi = valid ? Ahi[i] : 0ull;
+            const uint32_t d = valid ? ((uint32_t)((shift < 64 ? lo : hi) >> sh) & 255u) : (256u + lane);
+            const uint32_t peers = __match_any_sync(0xffffffffu, d);
+            const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+            uint32_t pos = 0;
+            if (valid) pos = hist[warp * 256 + d] + rank;
+            __syncwarp();
+            if (valid) {
+                Blo[pos] = lo; Bhi[pos] = hi; Bv[pos] = Av[i];
+                if (rank + 1 == (uint32_t)__popc(peers)) hist[warp * 256 + d] = pos + 1;
+            }
+            __syncwarp();
+        }
+        __syncthreads();
+        uint64_t *t = Alo; Alo = Blo; Blo = t;
+        t = Ahi; Ahi = Bhi; Bhi = t;
+        uint32_t *tv = Av; Av = Bv; Bv = tv;
+        where ^= 1;
+    }
+    return where;
+}
+
+template <int THREADS, int CAP>
+constexpr size_t sort_units128_smem_bytes() {
+    return (size_t)(THREADS / 32) * 256 * 4 + 48 * 4 + (size_t)CAP * 40;
+}
+
+// One CTA per unit: entries [unit_out_off, +cnt) of src -> sorted at [unit_final_off, +cnt) of dst.
+// The src range is scratch after this kernel (used as the ping-pong partner for big units).
+template <int THREADS, int CAP>
+__global__ void __launch_bounds__(THREADS)
+k_sort_units128(uint64_t *__restrict__ src_lo, uint64_t *__restrict__ src_hi, uint32_t *__restrict__ src_cf,
+                const uint64_t *__restrict__ unit_out_off, const uint32_t *__restrict__ unit_out_cnt,
+                const uint64_t *__restrict__ unit_final_off, uint64_t *__restrict__ dst_lo, uint64_t *__restrict__ dst_hi,
+                uint32_t *__restrict__ dst_cf, uint32_t n_units, uint32_t first_bit, uint32_t end_bit) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int WARPS = THREADS / 32;
+    uint64_t *sAlo = reinterpret_cast<uint64_t *>(smem_raw);
+    uint64_t *sAhi = sAlo + CAP, *sBlo = sAhi + CAP, *sBhi = sBlo + CAP;
+    uint32_t *sAv = reinterpret_cast<uint32_t *>(sBhi + CAP), *sBv = sAv + CAP;
+    uint32_t *hist = sBv + CAP;
+    uint32_t *s_scan = hist + WARPS * 256;
+    const uint32_t tid = threadIdx.x;
+    for (uint32_t u = blockIdx.x; u < n_units; u += gridDim.x) {
+        const uint32_t n = unit_out_cnt[u];
+        if (n == 0) continue;
+        const uint64_t so = unit_out_off[u], fo = unit_final_off[u];
+        if (n <= (uint32_t)CAP) {
+            for (uint32_t i = tid; i < n; i += THREADS) { sAlo[i] = src_lo[so + i]; sAhi[i] = src_hi[so + i]; sAv[i] = src_cf[so + i]; }
+            __syncthreads();
+            const int w = block_radix_sort128<THREADS>(sAlo, sAhi, sAv, sBlo, sBhi, sBv, n, first_bit, end_bit, hist, s_scan);
+            const uint64_t *rl = w ? sBlo : sAlo, *rh = w ? sBhi : sAhi;
+            const uint32_t *rv = w ? sBv : sAv;
+            for (uint32_t i = tid; i < n; i += THREADS) { dst_lo[fo + i] = rl[i]; dst_hi[fo + i] = rh[i]; dst_cf[fo + i] = rv[i]; }
+        } else {
+            const int w = block_radix_sort128<THREADS>(src_lo + so, src_hi + so, src_cf + so, dst_lo + fo, dst_hi + fo, dst_cf + fo,
+                                                       n, first_bit, end_bit, hist, s_scan);
+            if (w == 0)
+                for (uint32_t i = tid; i < n; i += THREADS) { dst_lo[fo + i] = src_lo[so + i]; dst_hi[fo + i] = src_hi[so + i]; dst_cf[fo + i] = src_cf[so + i]; }
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// MODE_COLOR fold.  Sorted entries of a unit: slot key = (k-mer << 32) | colour, value = counter | flags << 30.
+// A k-mer's entries are adjacent; head = first entry of a k-mer.
+__device__ __forceinline__ bool same_kmer(uint64_t alo, uint64_t ahi, uint64_t blo, uint64_t bhi) {
+    return ahi == bhi && (alo >> 32) == (blo >> 32);
+}
+
+// WRITE == false: per-unit counts of kept k-mers / kept colour entries.  WRITE == true: emit them.
+template <int THREADS, bool WRITE>
+__global__ void __launch_bounds__(THREADS)
+k_color_fold(const uint64_t *__restrict__ lo, const uint64_t *__restrict__ hi, const uint32_t *__restrict__ cf,
+             const uint64_t *__restrict__ unit_off /* n_units+1, sorted layout */, uint32_t n_units, uint32_t min_mult,
+             uint32_t *__restrict__ unit_keys, uint32_t *__restrict__ unit_cols,              // counts (out when !WRITE)
+             const uint64_t *__restrict__ key_off, const uint64_t *__restrict__ col_off,      // scanned (in when WRITE)
+             uint64_t *__restrict__ o_lo, uint64_t *__restrict__ o_hi, uint32_t *__restrict__ o_cf,
+             uint64_t *__restrict__ o_coloff, uint32_t *__restrict__ o_colors) {
+    __shared__ uint32_t s_scan[THREADS / 32 + 2];
+    const uint32_t tid = threadIdx.x;
+    for (uint32_t u = blockIdx.x; u < n_units; u += gridDim.x) {
+        const uint64_t b = unit_off[u], e = unit_off[u + 1];
+        uint32_t run_keys = 0, run_cols = 0;  // running totals inside the unit (block-uniform)
+        for (uint64_t base = b; base < e; base += THREADS) {
+            const uint64_t i = base + tid;
+            uint32_t keep = 0, ncol = 0, cfo = 0;
+            if (i < e) {
+                const uint64_t l = lo[i], h = hi[i];
+                if (i == b || !same_kmer(l, h, lo[i - 1], hi[i - 1])) {
+                    uint64_t cnt = 0;
+                    uint32_t fl = 0, len = 0;
+                    for (uint64_t j = i; j < e; ++j) {
+                        if (j > i && !same_kmer(l, h, lo[j], hi[j])) break;
+                        const uint32_t c = cf[j];
+                        cnt += c & 0x3FFFFFFFu; fl |= c >> 30; ++len;
+                    }
+                    const uint64_t mult = cnt >> ((fl == 3u) ? 1 : 0);  // map_entry.rs:79-84 on the folded entry
+                    if (mult >= min_mult) { keep = 1; ncol = len; cfo = (uint32_t)(mult > 0x3FFFFFFFull ? 0x3FFFFFFFull : mult) | (fl << 30); }
+                }
+            }
+            uint32_t tk, tc;
+            const uint32_t pk = block_exclusive_scan<THREADS>(keep, s_scan, &tk);
+            const uint32_t pc = block_exclusive_scan<THREADS>(ncol, s_scan, &tc);
+            if (WRITE && keep) {
+                const uint64_t ko = key_off[u] + run_keys + pk, co = col_off[u] + run_cols + pc;
+                const uint64_t l = lo[i], h = hi[i];
+                o_lo[ko] = (l >> 32) | (h << 32);
+                o_hi[ko] = h >> 32;
+                o_cf[ko] = cfo;
+                o_coloff[ko] = co;
+                for (uint32_t q = 0; q < ncol; q++) o_colors[co + q] = (uint32_t)lo[i + q];
+            }
+            run_keys += tk; run_cols += tc;
+        }
+        if (!WRITE && tid == 0) { unit_keys[u] = run_keys; unit_cols[u] = run_cols; }
+    }
+}
+
+}  // namespace ggb
