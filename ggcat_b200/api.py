@@ -112,6 +112,10 @@ class KmerTable:
     def flags(self) -> np.ndarray:
         return (self.count_flags >> np.uint32(30)).astype(np.uint8)
 
+    def colors_of(self, entry: int) -> np.ndarray:
+        """Sorted-unique colour ids of one entry (coloured builds)."""
+        return self.colors[int(self.color_offsets[entry]):int(self.color_offsets[entry + 1])]
+
     def unit_slice(self, unit: int) -> slice:
         u = unit - self.first_unit
         return slice(int(self.unit_offsets[u]), int(self.unit_offsets[u + 1]))
@@ -281,13 +285,13 @@ class GGCATB200:
 # ------------------------------------------------------------------ reference-shaped phase functions
 def minimizer_bucketing(input_blocks: Iterable[Sequence], buckets_count_log: int, second_buckets_count_log: int, k: int,
                         m: int = 0, forward_only: bool = False, min_multiplicity: int = 2, colors: bool = False,
-                        device: int = 0) -> tuple[GGCATB200, BucketStats]:
+                        device: int = 0, hash_type: int = HASH_AUTO) -> tuple[GGCATB200, BucketStats]:
     """Phase 1 ("phase: reads bucketing").  input_blocks: iterable of (data, offsets[, colors]) ASCII batches,
     one per input block/file like the reference's ``Vec<GeneralSequenceBlockData>``; with ``colors`` and no
     explicit colour array, block i gets colour i (file_color = i, lib.rs:300-305)."""
     ctx = GGCATB200(Params(k=k, m=m, min_multiplicity=min_multiplicity, buckets_count_log=buckets_count_log,
                            second_buckets_count_log=second_buckets_count_log, forward_only=forward_only, colors=colors,
-                           device=device))
+                           device=device, hash_type=hash_type))
     for i, blk in enumerate(input_blocks):
         data, offsets = blk[0], blk[1]
         col = blk[2] if len(blk) > 2 else (np.full(len(offsets) - 1, i, np.uint32) if colors else None)

@@ -29,6 +29,7 @@ struct DevParams {
     uint32_t forward_only;
     uint32_t colors;
     uint32_t n_units;  // ((1<<b1)+1) << b2
+    uint32_t hash_type;  // ggcat_b200_hash_type (k-mer identity hash of phase 2)
 };
 
 constexpr int WIN_T = 1024;       // windows per tile

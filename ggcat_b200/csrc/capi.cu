@@ -2,7 +2,7 @@
 // Host orchestration only: buffers, launches, chunk bookkeeping.  No CPU compute path exists;
 // every entry point fails with GGCAT_B200_ERR_CUDA when no device is usable.
 #include "../../include/ggcat_b200.h"
-#include "merge.cuh"
+#include "merge128.cuh"
 
 #include <algorithm>
 #include <cstdarg>
@@ -72,16 +72,32 @@ struct Chunk {
 };
 
 enum Family { F_PACK = 0, F_WINDOWS, F_EMIT, F_SCATTER, F_SCAN, F_MERGE_HASH, F_MERGE_HASH_GLOBAL, F_MERGE_SMEM, F_MERGE_GLOBAL,
-              F_GATHER, F_COUNT };
+              F_GATHER, F_MERGE_HASH128, F_SORT128, F_COLOR_FOLD, F_COUNT };
 static const char *kFamilyNames[F_COUNT] = {"k_pack+k_mark", "k_windows", "k_emit", "k_scatter", "k_exclusive_scan_u32",
                                             "k_merge_hash<smem>", "k_merge_hash<global>", "k_merge_units<smem>",
-                                            "k_merge_units<global>", "k_gather_units"};
+                                            "k_merge_units<global>", "k_gather_units", "k_merge_hash128", "k_sort_units128",
+                                            "k_color_fold"};
 
 struct TimedLaunch { int fam; cudaEvent_t a, b; };
 
 struct HostTable {
-    uint64_t *keys = nullptr; uint32_t *cf = nullptr; uint64_t *unit_offsets = nullptr;
-    size_t cap_entries = 0, cap_units = 0;
+    uint64_t *keys = nullptr, *keys_hi = nullptr; uint32_t *cf = nullptr; uint64_t *unit_offsets = nullptr;
+    uint64_t *color_offsets = nullptr; uint32_t *colors = nullptr;
+    size_t cap_entries = 0, cap_units = 0, cap_colors = 0;
+    bool wide = false, colored = false;
+    void release() {
+        cudaFreeHost(keys); cudaFreeHost(keys_hi); cudaFreeHost(cf); cudaFreeHost(unit_offsets); cudaFreeHost(color_offsets);
+        cudaFreeHost(colors);
+    }
+};
+
+// where the finished table of the last merge lives on the device
+struct FinalTable {
+    const uint64_t *keys_lo = nullptr, *keys_hi = nullptr; const uint32_t *cf = nullptr;
+    const uint64_t *unit_off = nullptr;      // n_units + 1
+    const uint64_t *color_off = nullptr;     // n_entries (+1 implied = n_colors)
+    const uint32_t *colors = nullptr;
+    uint64_t n_entries = 0, n_colors = 0;
 };
 
 }  // namespace
@@ -96,6 +112,9 @@ struct ggcat_b200_ctx {
     bool finished = false;
     bool timing = false;
     int merge_mode = 1;  // 1 = shared-memory hash table (default), 0 = LSD radix sort (GGCAT_B200_MERGE=sort)
+    int wide_mode = -1;  // -1: 64-bit key path (merge.cuh); else MODE_SEQ128 / MODE_RK128 / MODE_COLOR (merge128.cuh)
+    RkTables rk;
+    FinalTable fin;
     ggcat_b200_bucket_stats stats;
     // phase-1 workspace
     DevBuf d_ascii, d_offsets, d_colors, pk, bad, brk, ent, tile_cnt, tile_sbase, tmp, tmp_color, cur_cnt, cur_words, totals;
@@ -103,7 +122,7 @@ struct ggcat_b200_ctx {
     std::vector<Chunk *> chunk_pool;  // recycled local chunks (device buffers kept)
     // phase-2 workspace
     DevBuf d_views, d_work[3], d_scratch, out_keys, out_cf, out_keys2, out_cf2, cursor, unit_out_off,
-        unit_out_cnt, unit_final_off, overflow, d_retry;
+        unit_out_cnt, unit_final_off, overflow, d_retry, out_hi, out_hi2, unit_keys, unit_cols, col_off, out_coloff, out_colors;
     unsigned long long *h_pinned = nullptr;  // small pinned staging (16 u64)
     std::vector<TimedLaunch> launches;
     std::vector<cudaEvent_t> event_pool;
@@ -312,6 +331,9 @@ constexpr int SM_THREADS_L = 1024, SM_CAP_L = 12288;   // 1 CTA / SM
 constexpr int GL_THREADS = 1024;
 constexpr int HASH_TS_S = 8192, HASH_TS_L = 16384;       // hash-table slots: unit records <= 3/4 of the slots
 
+int32_t merge_range_device_wide(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_buckets, uint64_t *n_entries,
+                                uint64_t *unique, uint64_t *total);
+
 int32_t merge_range_device(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_buckets, uint64_t *n_entries,
                            uint64_t *unique, uint64_t *total) {
     const DevParams &P = c->P;
@@ -320,6 +342,7 @@ int32_t merge_range_device(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_
     const uint32_t nb_total = (1u << P.b1) + 1;
     if (n_buckets == 0 || first_bucket >= nb_total || first_bucket + n_buckets > nb_total)
         return set_err(GGCAT_B200_ERR_INVALID, "bucket range [%u,+%u) outside 0..%u", first_bucket, n_buckets, nb_total);
+    if (c->wide_mode >= 0) return merge_range_device_wide(c, first_bucket, n_buckets, n_entries, unique, total);
     const uint32_t u0 = first_bucket << P.b2, nu = n_buckets << P.b2;
     // classify units by record count
     std::vector<uint32_t> work[3];
@@ -483,8 +506,179 @@ int32_t merge_range_device(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_
     const uint32_t ovf = (uint32_t)c->h_pinned[8];
     if (ovf) return set_err(GGCAT_B200_ERR_CAPACITY, "merge output overflow (code %u)", ovf);
     c->last_entries = c->h_pinned[0];
+    c->fin = FinalTable();
+    c->fin.keys_lo = c->out_keys2.as<uint64_t>(); c->fin.cf = c->out_cf2.as<uint32_t>();
+    c->fin.unit_off = c->unit_final_off.as<uint64_t>(); c->fin.n_entries = c->h_pinned[0];
     if (n_entries) *n_entries = c->h_pinned[0];
     if (unique) *unique = c->h_pinned[1];
+    if (total) *total = c->h_pinned[2];
+    return 0;
+}
+
+// ---- wide path (merge128.cuh): 128-bit keys and coloured builds --------------------------------------------------
+constexpr int W_THREADS_S = 512, W_TS_S = 4096;    // 80 KB table: 2 CTAs / SM, units <= 3072 records
+constexpr int W_THREADS_L = 1024, W_TS_L = 8192;   // 160 KB table: 1 CTA / SM, units <= 6144 records
+constexpr int W_SORT_THREADS = 512, W_SORT_CAP = 2048;
+
+template <int MODE>
+int32_t launch_hash128(ggcat_b200_ctx *c, const ChunkView *dv, uint32_t nch, std::vector<uint32_t> *work, uint32_t u0,
+                       const MergeOut128 &out, const std::vector<std::pair<uint64_t, uint32_t>> &large) {
+    const DevParams &P = c->P;
+    cudaStream_t st = c->stream;
+    if (!work[0].empty()) {
+        LaunchTimer t(c, F_MERGE_HASH128);
+        auto kern = k_merge_hash128<W_THREADS_S, W_TS_S, MODE>;
+        const size_t smem = merge_hash128_smem_bytes<W_THREADS_S, W_TS_S>();
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const unsigned grid = (unsigned)std::min<size_t>(work[0].size(), (size_t)c->sm_count * 2 * 8);
+        kern<<<grid, W_THREADS_S, smem, st>>>(dv, nch, c->d_work[0].as<uint32_t>(), (uint32_t)work[0].size(), u0, P, c->rk,
+                                               c->params.min_multiplicity, out, nullptr, 0);
+    }
+    if (!work[1].empty()) {
+        LaunchTimer t(c, F_MERGE_HASH128);
+        auto kern = k_merge_hash128<W_THREADS_L, W_TS_L, MODE>;
+        const size_t smem = merge_hash128_smem_bytes<W_THREADS_L, W_TS_L>();
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const unsigned grid = (unsigned)std::min<size_t>(work[1].size(), (size_t)c->sm_count * 8);
+        kern<<<grid, W_THREADS_L, smem, st>>>(dv, nch, c->d_work[1].as<uint32_t>(), (uint32_t)work[1].size(), u0, P, c->rk,
+                                               c->params.min_multiplicity, out, nullptr, 0);
+    }
+    // large units: table in a per-CTA slice of global scratch, biggest first, two tiers (see merge_range_device)
+    const uint64_t TIER = 1ull << 20;
+    size_t n_giant = 0;
+    while (n_giant < large.size() && large[n_giant].first > TIER) n_giant++;
+    for (int tr = 0; tr < 2; tr++) {
+        const size_t first = tr == 0 ? 0 : n_giant, count = tr == 0 ? n_giant : large.size() - n_giant;
+        if (!count) continue;
+        const uint64_t nmax = large[first].first;
+        uint64_t per_cta = ((uint64_t)hash_table_slots((uint32_t)nmax) * 20 + 15) / 16 * 2 + 2;  // u64 words, 16-byte multiple
+        const uint64_t budget = 12ull << 30;
+        const uint64_t g = std::min<uint64_t>(std::min<uint64_t>(count, (uint64_t)c->sm_count * 2), std::max<uint64_t>(1, budget / (per_cta * 8)));
+        CU(c->d_scratch.reserve(per_cta * g * 8));
+        LaunchTimer t(c, F_MERGE_HASH128);
+        auto kern = k_merge_hash128<W_THREADS_L, 0, MODE>;
+        kern<<<(unsigned)g, W_THREADS_L, merge_hash128_smem_bytes<W_THREADS_L, 0>(), st>>>(
+            dv, nch, c->d_work[2].as<uint32_t>() + first, (uint32_t)count, u0, P, c->rk, c->params.min_multiplicity, out,
+            c->d_scratch.as<uint64_t>(), per_cta);
+    }
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int32_t merge_range_device_wide(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_buckets, uint64_t *n_entries,
+                                uint64_t *unique, uint64_t *total) {
+    const DevParams &P = c->P;
+    cudaStream_t st = c->stream;
+    const uint32_t u0 = first_bucket << P.b2, nu = n_buckets << P.b2;
+    std::vector<uint32_t> work[3];
+    std::vector<std::pair<uint64_t, uint32_t>> large;
+    uint64_t tot_kmers = 0;
+    for (uint32_t u = u0; u < u0 + nu; u++) {
+        uint64_t n = 0;
+        for (Chunk *ch : c->chunks)
+            if (u >= ch->first_unit && u < ch->first_unit + ch->n_units) n += ch->h_kmers[u - ch->first_unit];
+        if (n == 0) continue;
+        if (n >= (1ull << 30)) return set_err(GGCAT_B200_ERR_INVALID, "unit %u holds %llu k-mers (> 2^30)", u, (unsigned long long)n);
+        tot_kmers += n;
+        if (n <= W_TS_S * 3 / 4) work[0].push_back(u);
+        else if (n <= W_TS_L * 3 / 4) work[1].push_back(u);
+        else large.push_back({n, u});
+    }
+    std::sort(large.begin(), large.end(), [](const auto &a, const auto &b) { return a.first > b.first; });
+    for (auto &pr : large) work[2].push_back(pr.second);
+    std::vector<ChunkView> views;
+    for (Chunk *ch : c->chunks) {
+        ChunkView v;
+        v.desc = ch->d_desc; v.payload = ch->d_payload; v.unit_off = ch->d_unit_off; v.unit_kmers = ch->d_unit_kmers;
+        v.first_unit = ch->first_unit; v.n_units = ch->n_units; v.word_bias = ch->word_bias; v.pad = 0;
+        views.push_back(v);
+    }
+    CU(c->d_views.reserve(std::max<size_t>(1, views.size()) * sizeof(ChunkView)));
+    if (!views.empty())
+        CU(cudaMemcpyAsync(c->d_views.p, views.data(), views.size() * sizeof(ChunkView), cudaMemcpyHostToDevice, st));
+    for (int q = 0; q < 3; q++) {
+        CU(c->d_work[q].reserve(std::max<size_t>(1, work[q].size()) * 4));
+        if (!work[q].empty())
+            CU(cudaMemcpyAsync(c->d_work[q].p, work[q].data(), work[q].size() * 4, cudaMemcpyHostToDevice, st));
+    }
+    const uint64_t cap = std::max<uint64_t>(tot_kmers, 1);
+    CU(c->out_keys.reserve(cap * 8)); CU(c->out_hi.reserve(cap * 8)); CU(c->out_cf.reserve(cap * 4));
+    CU(c->out_keys2.reserve(cap * 8)); CU(c->out_hi2.reserve(cap * 8)); CU(c->out_cf2.reserve(cap * 4));
+    CU(c->cursor.reserve(64)); CU(c->overflow.reserve(16));
+    CU(c->unit_out_off.reserve(((size_t)nu + 1) * 8)); CU(c->unit_out_cnt.reserve(((size_t)nu + 1) * 4));
+    CU(c->unit_final_off.reserve(((size_t)nu + 1) * 8));
+    CU(cudaMemsetAsync(c->cursor.p, 0, 64, st));
+    CU(cudaMemsetAsync(c->overflow.p, 0, 16, st));
+    CU(cudaMemsetAsync(c->unit_out_off.p, 0, ((size_t)nu + 1) * 8, st));
+    CU(cudaMemsetAsync(c->unit_out_cnt.p, 0, ((size_t)nu + 1) * 4, st));
+    MergeOut128 out;
+    out.keys_lo = c->out_keys.as<uint64_t>(); out.keys_hi = c->out_hi.as<uint64_t>(); out.count_flags = c->out_cf.as<uint32_t>();
+    out.cursor = c->cursor.as<unsigned long long>(); out.unit_out_off = c->unit_out_off.as<uint64_t>();
+    out.unit_out_cnt = c->unit_out_cnt.as<uint32_t>(); out.capacity = cap; out.overflow = c->overflow.as<uint32_t>();
+    const ChunkView *dv = c->d_views.as<ChunkView>();
+    const uint32_t nch = (uint32_t)views.size();
+    if (c->wide_mode == MODE_SEQ128) TRY(launch_hash128<MODE_SEQ128>(c, dv, nch, work, u0, out, large));
+    else if (c->wide_mode == MODE_RK128) TRY(launch_hash128<MODE_RK128>(c, dv, nch, work, u0, out, large));
+    else TRY(launch_hash128<MODE_COLOR>(c, dv, nch, work, u0, out, large));
+    // ---- order every unit's entries by key into the unit-ordered layout
+    uint32_t end_bit = 128;
+    if (c->wide_mode == MODE_SEQ128) end_bit = std::min(128u, (2 * P.k + 7) & ~7u);
+    else if (c->wide_mode == MODE_COLOR) end_bit = std::min(128u, (32 + 2 * P.k + 7) & ~7u);
+    {
+        LaunchTimer t(c, F_SORT128, 2);
+        k_scan_counts_u64<<<1, 1024, 0, st>>>(c->unit_out_cnt.as<uint32_t>(), c->unit_final_off.as<uint64_t>(), nu);
+        auto kern = k_sort_units128<W_SORT_THREADS, W_SORT_CAP>;
+        const size_t smem = sort_units128_smem_bytes<W_SORT_THREADS, W_SORT_CAP>();
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<(unsigned)std::min<uint32_t>(nu, (uint32_t)c->sm_count * 2 * 8), W_SORT_THREADS, smem, st>>>(
+            c->out_keys.as<uint64_t>(), c->out_hi.as<uint64_t>(), c->out_cf.as<uint32_t>(), c->unit_out_off.as<uint64_t>(),
+            c->unit_out_cnt.as<uint32_t>(), c->unit_final_off.as<uint64_t>(), c->out_keys2.as<uint64_t>(),
+            c->out_hi2.as<uint64_t>(), c->out_cf2.as<uint32_t>(), nu, 0u, end_bit);
+    }
+    CU(cudaGetLastError());
+    c->fin = FinalTable();
+    if (c->wide_mode == MODE_COLOR) {
+        // fold the (k-mer, colour) entries of every k-mer; the unsorted buffers are free again and take the result
+        const size_t ub = ((size_t)nu + 2);
+        CU(c->unit_keys.reserve(ub * 4)); CU(c->unit_cols.reserve(ub * 4)); CU(c->col_off.reserve(ub * 8));
+        CU(c->out_coloff.reserve((cap + 1) * 8)); CU(c->out_colors.reserve(cap * 4));
+        LaunchTimer t(c, F_COLOR_FOLD, 4);
+        const unsigned grid = (unsigned)std::min<uint32_t>(nu, (uint32_t)c->sm_count * 8);
+        k_color_fold<256, false><<<grid, 256, 0, st>>>(
+            c->out_keys2.as<uint64_t>(), c->out_hi2.as<uint64_t>(), c->out_cf2.as<uint32_t>(), c->unit_final_off.as<uint64_t>(), nu,
+            c->params.min_multiplicity, c->unit_keys.as<uint32_t>(), c->unit_cols.as<uint32_t>(), nullptr, nullptr, nullptr, nullptr,
+            nullptr, nullptr, nullptr);
+        // unit_out_off is free now: it receives the per-unit key offsets of the folded table
+        k_scan_counts_u64<<<1, 1024, 0, st>>>(c->unit_keys.as<uint32_t>(), c->unit_out_off.as<uint64_t>(), nu);
+        k_scan_counts_u64<<<1, 1024, 0, st>>>(c->unit_cols.as<uint32_t>(), c->col_off.as<uint64_t>(), nu);
+        k_color_fold<256, true><<<grid, 256, 0, st>>>(
+            c->out_keys2.as<uint64_t>(), c->out_hi2.as<uint64_t>(), c->out_cf2.as<uint32_t>(), c->unit_final_off.as<uint64_t>(), nu,
+            c->params.min_multiplicity, nullptr, nullptr, c->unit_out_off.as<uint64_t>(), c->col_off.as<uint64_t>(),
+            c->out_keys.as<uint64_t>(), c->out_hi.as<uint64_t>(), c->out_cf.as<uint32_t>(), c->out_coloff.as<uint64_t>(),
+            c->out_colors.as<uint32_t>());
+        CU(cudaMemcpyAsync(c->h_pinned + 4, c->unit_out_off.as<uint64_t>() + nu, 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(c->h_pinned + 5, c->col_off.as<uint64_t>() + nu, 8, cudaMemcpyDeviceToHost, st));
+        c->fin.keys_lo = c->out_keys.as<uint64_t>(); c->fin.keys_hi = c->out_hi.as<uint64_t>(); c->fin.cf = c->out_cf.as<uint32_t>();
+        c->fin.unit_off = c->unit_out_off.as<uint64_t>(); c->fin.color_off = c->out_coloff.as<uint64_t>();
+        c->fin.colors = c->out_colors.as<uint32_t>();
+    } else {
+        c->fin.keys_lo = c->out_keys2.as<uint64_t>(); c->fin.keys_hi = c->out_hi2.as<uint64_t>(); c->fin.cf = c->out_cf2.as<uint32_t>();
+        c->fin.unit_off = c->unit_final_off.as<uint64_t>();
+    }
+    CU(cudaMemcpyAsync(c->h_pinned, c->cursor.p, 24, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(c->h_pinned + 8, c->overflow.p, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    CU(cudaGetLastError());
+    const uint32_t ovf = (uint32_t)c->h_pinned[8];
+    if (ovf) return set_err(GGCAT_B200_ERR_CAPACITY, "merge output overflow (code %u)", ovf);
+    uint64_t uq = c->h_pinned[1];
+    if (c->wide_mode == MODE_COLOR) {
+        c->fin.n_entries = c->h_pinned[4]; c->fin.n_colors = c->h_pinned[5];
+        uq = 0;  // distinct (k-mer, colour) pairs are not the reference's distinct k-mers; not tracked for coloured builds
+    } else c->fin.n_entries = c->h_pinned[0];
+    c->last_entries = c->fin.n_entries;
+    if (n_entries) *n_entries = c->fin.n_entries;
+    if (unique) *unique = uq;
     if (total) *total = c->h_pinned[2];
     return 0;
 }
@@ -523,14 +717,16 @@ int32_t ggcat_b200_create(const ggcat_b200_params *params, ggcat_b200_ctx **out)
     ggcat_b200_params p = *params;
     if (p.m == 0) p.m = best_m(p.k);
     if (p.hash_type == GGCAT_B200_HASH_AUTO) p.hash_type = p.k <= 64 ? GGCAT_B200_HASH_SEQ : GGCAT_B200_HASH_RK128;  // crates/api/src/utils.rs:17-26
-    if (p.k < 4 || p.k > 31) return set_err(GGCAT_B200_ERR_INVALID, "k=%u unsupported (4..31: 64-bit key path)", p.k);
-    if (p.hash_type != GGCAT_B200_HASH_SEQ) return set_err(GGCAT_B200_ERR_INVALID, "hash_type=%u unsupported in this build", p.hash_type);
+    if (p.hash_type != GGCAT_B200_HASH_SEQ && p.hash_type != GGCAT_B200_HASH_RK128)
+        return set_err(GGCAT_B200_ERR_INVALID, "hash_type=%u unsupported (1 = seq-hash, 4 = rabin-karp128)", p.hash_type);
+    if (p.k < 4 || p.k > 64) return set_err(GGCAT_B200_ERR_INVALID, "k=%u unsupported (4..64)", p.k);
     if (p.m < 2 || p.m > 32 || p.m >= p.k) return set_err(GGCAT_B200_ERR_INVALID, "m=%u invalid for k=%u", p.m, p.k);
     if (p.k - p.m < 2 || p.k - p.m > (uint32_t)WIN_WMAX) return set_err(GGCAT_B200_ERR_INVALID, "k-m=%u outside 2..%d", p.k - p.m, WIN_WMAX);
     if (p.buckets_count_log > 13) return set_err(GGCAT_B200_ERR_INVALID, "buckets_count_log > 13");  // config MAX_BUCKETS_COUNT_LOG
     if (p.second_buckets_count_log > 8) return set_err(GGCAT_B200_ERR_INVALID, "second_buckets_count_log > 8");
     if (p.min_multiplicity == 0) p.min_multiplicity = 1;
-    if (p.colors) return set_err(GGCAT_B200_ERR_INVALID, "colors unsupported in this build");
+    if (p.colors && (p.hash_type != GGCAT_B200_HASH_SEQ || p.k > 48))
+        return set_err(GGCAT_B200_ERR_INVALID, "colors need seq-hash and k <= 48 (k-mer and colour id share one 128-bit slot key)");
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0)
@@ -546,6 +742,28 @@ int32_t ggcat_b200_create(const ggcat_b200_params *params, ggcat_b200_ctx **out)
     memset(&c->stats, 0, sizeof(c->stats));
     memset(c->fam_ms, 0, sizeof(c->fam_ms));
     memset(c->fam_launches, 0, sizeof(c->fam_launches));
+    c->P.hash_type = p.hash_type;
+    if (p.colors) c->wide_mode = MODE_COLOR;
+    else if (p.hash_type == GGCAT_B200_HASH_RK128) c->wide_mode = MODE_RK128;
+    else if (p.k > 31) c->wide_mode = MODE_SEQ128;
+    memset(&c->rk, 0, sizeof(c->rk));
+    if (c->wide_mode == MODE_RK128) {
+        // crates/hashes/src/cn_rkhash.rs:69-75 (u128 module); M^(k-1) as crates/hashes/src/lib.rs:169-191 (fastexp)
+        const u128 M = ((u128)0x3eb9402f3e733993ULL << 64) | 0xadd64d3ca00e1b6bULL;
+        const u128 MI = ((u128)0x09cb6ff6f1b1a6d7ULL << 64) | 0x33e0952e899c3943ULL;
+        const u128 LA = ((u128)0x4751137d01d863c5ULL << 64) | 0xb8c36de2b7d399dfULL;
+        const u128 LC = ((u128)0x37ea3a13226503fbULL << 64) | 0x783f5cb69f4552bdULL;
+        const u128 LG = ((u128)0x50796b285343f09aULL << 64) | 0x0c53113ae736572bULL;
+        const u128 LT = ((u128)0x1e62d96a5e1f5adeULL << 64) | 0x2d4e68d8f88110b7ULL;
+        const u128 L[4] = {LA, LC, LT, LG};  // 2-bit codes A0 C1 T2 G3 (cn_rkhash_base.rs:10-44)
+        u128 mk1 = 1, sq = M;
+        for (uint32_t e = p.k - 1; e > 0; e >>= 1) { if (e & 1) mk1 *= sq; sq *= sq; }
+        c->rk.mult = to_k128(M); c->rk.mult_inv = to_k128(MI);
+        for (int b = 0; b < 4; b++) {
+            c->rk.fwd[b] = to_k128(L[b]); c->rk.bkw[b] = to_k128(L[b ^ 2]);
+            c->rk.fwd_mk[b] = to_k128(L[b] * mk1 * M); c->rk.bkw_mk1[b] = to_k128(L[b ^ 2] * mk1);
+        }
+    }
     if (const char *mm = getenv("GGCAT_B200_MERGE")) c->merge_mode = (strcmp(mm, "sort") == 0) ? 0 : 1;
     if (const char *mb = getenv("GGCAT_B200_MAX_BATCH")) { uint64_t v = strtoull(mb, nullptr, 10); if (v >= 1024) c->max_batch = std::min<uint64_t>(v, 1ull << 30); }
     cudaDeviceProp prop;
@@ -582,10 +800,11 @@ void ggcat_b200_destroy(ggcat_b200_ctx *c) {
     for (DevBuf *b : {&c->d_ascii, &c->d_offsets, &c->d_colors, &c->pk, &c->bad, &c->brk, &c->ent, &c->tile_cnt, &c->tile_sbase,
                       &c->tmp, &c->tmp_color, &c->cur_cnt, &c->cur_words, &c->totals, &c->d_views, &c->d_work[0], &c->d_work[1],
                       &c->d_work[2], &c->d_scratch, &c->out_keys, &c->out_cf, &c->out_keys2, &c->out_cf2,
-                      &c->cursor, &c->unit_out_off, &c->unit_out_cnt, &c->unit_final_off, &c->overflow, &c->d_retry})
+                      &c->cursor, &c->unit_out_off, &c->unit_out_cnt, &c->unit_final_off, &c->overflow, &c->d_retry,
+                      &c->out_hi, &c->out_hi2, &c->unit_keys, &c->unit_cols, &c->col_off, &c->out_coloff, &c->out_colors})
         b->release();
     for (cudaEvent_t e : c->event_pool) cudaEventDestroy(e);
-    for (HostTable *t : c->free_tables) { cudaFreeHost(t->keys); cudaFreeHost(t->cf); cudaFreeHost(t->unit_offsets); delete t; }
+    for (HostTable *t : c->free_tables) { t->release(); delete t; }
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -734,29 +953,42 @@ int32_t ggcat_b200_merge_bucket_range(ggcat_b200_ctx *c, uint32_t first_bucket, 
     uint64_t ne = 0, uq = 0, tk = 0;
     TRY(merge_range_device(c, first_bucket, n_buckets, &ne, &uq, &tk));
     const uint32_t nu = n_buckets << c->P.b2;
+    const FinalTable &f = c->fin;
+    const bool wide = f.keys_hi != nullptr, colored = f.color_off != nullptr;
+    const uint64_t ncol = f.n_colors;
     HostTable *t = nullptr;
-    for (size_t i = 0; i < c->free_tables.size(); i++)
-        if (c->free_tables[i]->cap_entries >= ne && c->free_tables[i]->cap_units >= nu + 1) {
-            t = c->free_tables[i]; c->free_tables.erase(c->free_tables.begin() + i); break;
+    for (size_t i = 0; i < c->free_tables.size(); i++) {
+        HostTable *q = c->free_tables[i];
+        if (q->cap_entries >= ne && q->cap_units >= nu + 1 && q->wide == wide && q->colored == colored && q->cap_colors >= ncol) {
+            t = q; c->free_tables.erase(c->free_tables.begin() + i); break;
         }
+    }
     if (!t) {
         t = new HostTable();
-        t->cap_entries = std::max<uint64_t>(ne + ne / 4, 1024); t->cap_units = nu + 1;
-        if (cudaMallocHost((void **)&t->keys, t->cap_entries * 8) != cudaSuccess ||
-            cudaMallocHost((void **)&t->cf, t->cap_entries * 4) != cudaSuccess ||
-            cudaMallocHost((void **)&t->unit_offsets, t->cap_units * 8) != cudaSuccess) {
-            return set_err(GGCAT_B200_ERR_CUDA, "pinned table allocation failed");
-        }
+        t->cap_entries = std::max<uint64_t>(ne + ne / 4, 1024); t->cap_units = nu + 1; t->wide = wide; t->colored = colored;
+        t->cap_colors = colored ? std::max<uint64_t>(ncol + ncol / 4, 1024) : 0;
+        bool ok = cudaMallocHost((void **)&t->keys, t->cap_entries * 8) == cudaSuccess &&
+                  cudaMallocHost((void **)&t->cf, t->cap_entries * 4) == cudaSuccess &&
+                  cudaMallocHost((void **)&t->unit_offsets, t->cap_units * 8) == cudaSuccess;
+        if (ok && wide) ok = cudaMallocHost((void **)&t->keys_hi, t->cap_entries * 8) == cudaSuccess;
+        if (ok && colored) ok = cudaMallocHost((void **)&t->color_offsets, (t->cap_entries + 1) * 8) == cudaSuccess &&
+                                cudaMallocHost((void **)&t->colors, t->cap_colors * 4) == cudaSuccess;
+        if (!ok) { t->release(); delete t; return set_err(GGCAT_B200_ERR_CUDA, "pinned table allocation failed"); }
     }
     if (ne) {
-        CU(cudaMemcpyAsync(t->keys, c->out_keys2.p, ne * 8, cudaMemcpyDeviceToHost, c->stream));
-        CU(cudaMemcpyAsync(t->cf, c->out_cf2.p, ne * 4, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(t->keys, f.keys_lo, ne * 8, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(t->cf, f.cf, ne * 4, cudaMemcpyDeviceToHost, c->stream));
+        if (wide) CU(cudaMemcpyAsync(t->keys_hi, f.keys_hi, ne * 8, cudaMemcpyDeviceToHost, c->stream));
+        if (colored) CU(cudaMemcpyAsync(t->color_offsets, f.color_off, ne * 8, cudaMemcpyDeviceToHost, c->stream));
+        if (colored && ncol) CU(cudaMemcpyAsync(t->colors, f.colors, ncol * 4, cudaMemcpyDeviceToHost, c->stream));
     }
-    CU(cudaMemcpyAsync(t->unit_offsets, c->unit_final_off.p, ((size_t)nu + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(t->unit_offsets, f.unit_off, ((size_t)nu + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
-    out->n_entries = ne; out->keys_lo = t->keys; out->keys_hi = nullptr; out->count_flags = t->cf;
+    if (colored) t->color_offsets[ne] = ncol;
+    out->n_entries = ne; out->keys_lo = t->keys; out->keys_hi = wide ? t->keys_hi : nullptr; out->count_flags = t->cf;
     out->first_unit = first_bucket << c->P.b2; out->n_units = nu; out->unit_offsets = t->unit_offsets;
-    out->color_offsets = nullptr; out->colors = nullptr; out->total_kmers = tk; out->unique_kmers = uq; out->opaque = t;
+    out->color_offsets = colored ? t->color_offsets : nullptr; out->colors = colored ? t->colors : nullptr;
+    out->total_kmers = tk; out->unique_kmers = uq; out->opaque = t;
     return 0;
 }
 

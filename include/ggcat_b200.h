@@ -42,14 +42,14 @@ typedef enum { GGCAT_B200_HASH_AUTO = 0, GGCAT_B200_HASH_SEQ = 1, GGCAT_B200_HAS
 /* The knobs of `ggcat build` that reach the hot path (crates/cmdline/src/main.rs:148-242,
  * crates/api/src/lib.rs:75-99): -k, --minimizer-length, -s, -b, -f, -w, -c. */
 typedef struct {
-    uint32_t k;                        /* k-mer length, 4 <= k <= 63 this round */
+    uint32_t k;                        /* k-mer length, 4 <= k <= 64 (k <= 31: 64-bit keys; else 128-bit keys) */
     uint32_t m;                        /* minimizer length, 0 = compute_best_m(k) (crates/utils/src/lib.rs:29-40) */
     uint32_t min_multiplicity;         /* -s */
     uint32_t buckets_count_log;        /* first-level buckets = 1 << this (+1 duplicates bucket) */
     uint32_t second_buckets_count_log; /* sub-buckets per bucket = 1 << this (<= 8) */
     uint32_t forward_only;             /* -f */
-    uint32_t hash_type;                /* ggcat_b200_hash_type */
-    uint32_t colors;                   /* -c : carry a colour id per record */
+    uint32_t hash_type;                /* ggcat_b200_hash_type; AUTO = seq-hash (crates/api/src/utils.rs:17-26 for k <= 64) */
+    uint32_t colors;                   /* -c : carry a colour id per record (seq-hash, k <= 48) */
     int32_t device;                    /* CUDA device ordinal */
     uint32_t reserved[7];
 } ggcat_b200_params;
@@ -90,7 +90,7 @@ typedef struct {
 typedef struct {
     uint64_t n_entries;
     const uint64_t *keys_lo;
-    const uint64_t *keys_hi;        /* NULL when 2k <= 62 */
+    const uint64_t *keys_hi;        /* high 64 bits of the key; NULL on the 64-bit key path (seq-hash, k <= 31, no colours) */
     const uint32_t *count_flags;
     uint32_t first_unit;            /* first_bucket << second_buckets_count_log */
     uint32_t n_units;
@@ -98,7 +98,7 @@ typedef struct {
     const uint64_t *color_offsets;  /* n_entries + 1 offsets into colors, NULL when uncoloured */
     const uint32_t *colors;         /* sorted-unique colour ids per entry */
     uint64_t total_kmers;           /* k-mer occurrences processed */
-    uint64_t unique_kmers;          /* distinct keys before the multiplicity filter */
+    uint64_t unique_kmers;          /* distinct keys before the multiplicity filter (0 = not tracked, coloured builds) */
     void *opaque;
 } ggcat_b200_table;
 

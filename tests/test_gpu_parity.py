@@ -47,7 +47,7 @@ def _gpu_records(ctx, n_buckets):
     return sorted(out)
 
 
-def _check_tables(G, ctx, reads, sk, k, s, b1, b2, forward_only=False, ranges=None):
+def _check_tables(G, ctx, reads, sk, k, s, b1, b2, forward_only=False, ranges=None, hash_type=O.HASH_SEQ, colors=False):
     nb = (1 << b1) + 1
     ranges = ranges or [(0, nb)]
     n_checked = 0
@@ -57,17 +57,28 @@ def _check_tables(G, ctx, reads, sk, k, s, b1, b2, forward_only=False, ranges=No
         tot_occ = 0
         uniq = 0
         for u in range(fb << b2, (fb + cnt) << b2):
-            ref, _, tk = O.merge_unit(reads, sk, u >> b2, u & ((1 << b2) - 1), k, s, O.HASH_SEQ, forward_only)
+            ref, rcols, tk = O.merge_unit(reads, sk, u >> b2, u & ((1 << b2) - 1), k, s, hash_type, forward_only, with_color=colors)
             tot_occ += tk
             uniq += len(ref)
             ref = ref[ref["kept"] == 1]
             sl = tab.unit_slice(u)
             assert np.array_equal(tab.keys_lo[sl], ref["key_lo"]), f"unit {u}: keys differ"
+            if tab.keys_hi is not None:
+                assert np.array_equal(tab.keys_hi[sl], ref["key_hi"]), f"unit {u}: high key words differ"
+            else:
+                assert not ref["key_hi"].any()
             assert np.array_equal(tab.multiplicity[sl].astype(np.uint64), ref["multiplicity"]), f"unit {u}: counts"
             assert np.array_equal(tab.flags[sl], ref["flags"]), f"unit {u}: flags"
+            if colors:
+                for j, e in enumerate(range(sl.start, sl.stop)):
+                    want = rcols[int(ref["color_off"][j]):int(ref["color_off"][j]) + int(ref["color_len"][j])]
+                    assert np.array_equal(tab.colors_of(e), want), f"unit {u} entry {j}: colour sets differ"
             n_checked += len(ref)
         assert tab.total_kmers == tot_occ
-        assert tab.unique_kmers == uniq
+        if not colors:
+            assert tab.unique_kmers == uniq
+        if colors:
+            assert int(tab.color_offsets[-1]) == tab.colors.size
     return n_checked
 
 
@@ -265,10 +276,102 @@ def test_c2_full_size_properties():
         ctx.close()
 
 
+@pytest.mark.parametrize("k,m,b1,b2,fo,s,ht", [
+    (63, 14, 3, 2, False, 2, O.HASH_RK128),    # BASELINE configs[4] parameters
+    (63, 14, 2, 1, True, 1, O.HASH_RK128),
+    (31, 12, 2, 2, False, 2, O.HASH_RK128),    # -w rabin-karp128 at small k
+    (63, 14, 3, 2, False, 2, O.HASH_SEQ),      # the reference's automatic choice for 32 < k <= 64: seq-hash u128
+    (33, 12, 2, 2, False, 1, O.HASH_SEQ),
+    (32, 12, 2, 1, False, 2, O.HASH_SEQ),      # even k: 64-bit key needs the wide path (no room for flag bits)
+    (64, 14, 1, 1, True, 1, O.HASH_SEQ),
+    (47, 13, 2, 3, True, 3, O.HASH_SEQ),
+])
+def test_wide_keys(k, m, b1, b2, fo, s, ht):
+    """128-bit key path: seq-hash u128 and rabin-karp128, forward-only and canonical."""
+    G = _gpu()
+    rng = np.random.default_rng(k * 131 + m + ht)
+    seqs = _mixed_reads(rng, k, n=250)
+    if k % 2 == 0 and not fo:
+        # even k: self-complementary k-mers get special trimming in the reference (final_executor.rs:322-352);
+        # table semantics are unaffected, inputs here simply may contain them
+        pass
+    reads = O.Reads.from_list(seqs)
+    sk, _ = O.bucketing(reads, k, m, b1, b2, forward_only=fo)
+    ctx, st = G.minimizer_bucketing([(reads.data, reads.offsets)], b1, b2, k, m, forward_only=fo, min_multiplicity=s, hash_type=ht)
+    try:
+        assert st.n_superkmers == len(sk)
+        assert _gpu_records(ctx, (1 << b1) + 1) == _sk_records(reads, sk, k)
+        n = _check_tables(G, ctx, reads, sk, k, s, b1, b2, fo, ranges=[(0, 1 << b1), (1 << b1, 1)], hash_type=ht)
+        assert n > 0
+    finally:
+        ctx.close()
+
+
+@pytest.mark.parametrize("n_bases,ht", [(9000, O.HASH_RK128), (30000, O.HASH_SEQ), (120000, O.HASH_RK128)])
+def test_wide_unit_size_paths(n_bases, ht):
+    """Wide path unit classes: <= 3072 records (512-thread table), <= 6144 (1024-thread table), global-scratch table;
+    survivor counts above and below the shared-memory sort capacity (2048)."""
+    G = _gpu()
+    rng = np.random.default_rng(n_bases)
+    k, m, b1, b2 = 63, 14, 0, 0
+    g = util.rand_seq(rng, n_bases // 3)
+    seqs = [g, util.revcomp(g[: len(g) // 2]), g[len(g) // 4:], util.rand_seq(rng, n_bases // 6)]
+    reads = O.Reads.from_list(seqs)
+    sk, _ = O.bucketing(reads, k, m, b1, b2)
+    for s in (1, 2):
+        ctx, st = G.minimizer_bucketing([(reads.data, reads.offsets)], b1, b2, k, m, min_multiplicity=s, hash_type=ht)
+        try:
+            assert st.n_superkmers == len(sk)
+            _check_tables(G, ctx, reads, sk, k, s, b1, b2, hash_type=ht)
+        finally:
+            ctx.close()
+
+
+@pytest.mark.parametrize("k,m,b1,b2,s,fo", [(31, 12, 2, 2, 1, False), (31, 12, 1, 1, 2, False), (21, 10, 2, 1, 1, True),
+                                             (41, 13, 1, 1, 1, False)])
+def test_colored_build(k, m, b1, b2, s, fo):
+    """-c: per k-mer the sorted-unique set of colours of all its occurrences (BASELINE configs[2] semantics at small
+    scale: genomes sharing mutated segments, colour = input index)."""
+    G = _gpu()
+    rng = np.random.default_rng(k + 7 * s)
+    anc = bytearray(util.rand_seq(rng, 6000))
+    seqs, cols = [], []
+    for c in range(9):
+        g = bytearray(util.rand_seq(rng, 6000))
+        for a in range(0, 6000, 1500):
+            seg = bytearray(anc[a:a + 900])
+            for _ in range(3):
+                seg[int(rng.integers(0, len(seg)))] = ord("ACGT"[int(rng.integers(0, 4))])
+            g[a:a + 900] = seg
+        if c % 3 == 0:
+            g = bytearray(util.revcomp(bytes(g)))
+        if c == 4:
+            g[100] = ord("N")
+        seqs.append(bytes(g))
+        cols.append(c if c != 7 else 1000003)   # colour ids need not be dense
+        if c == 2:                               # two records of the same colour
+            seqs.append(bytes(g[:2000]))
+            cols.append(c)
+    reads = O.Reads.from_list(seqs, colors=cols)
+    sk, _ = O.bucketing(reads, k, m, b1, b2, forward_only=fo)
+    ctx, st = G.minimizer_bucketing([(reads.data, reads.offsets, reads.colors)], b1, b2, k, m, forward_only=fo,
+                                    min_multiplicity=s, colors=True)
+    try:
+        assert st.n_superkmers == len(sk)
+        n = _check_tables(G, ctx, reads, sk, k, s, b1, b2, fo, colors=True)
+        assert n > 0
+    finally:
+        ctx.close()
+
+
 def test_error_behaviour():
     G = _gpu()
     with pytest.raises(G.GgcatB200Error):
         G.GGCATB200(G.Params(k=3))
+    with pytest.raises(G.GgcatB200Error):
+        G.GGCATB200(G.Params(k=65))
+    with pytest.raises(G.GgcatB200Error):
+        G.GGCATB200(G.Params(k=63, colors=True))
     with pytest.raises(G.GgcatB200Error):
         G.GGCATB200(G.Params(k=31, m=31))
     ctx = G.GGCATB200(G.Params(k=31, buckets_count_log=2, second_buckets_count_log=1))
