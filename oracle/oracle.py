@@ -15,6 +15,7 @@ import numpy as np
 
 _HERE = Path(__file__).resolve().parent
 _SRC = _HERE / "ggcat_oracle.c"
+_SRC2 = _HERE / "ggcat_unitigs.c"
 _LIB = _HERE / "_build" / "libggcat_oracle.so"
 
 HASH_SEQ = 1
@@ -54,10 +55,10 @@ NAIVE_DTYPE = np.dtype([("key_lo", "<u8"), ("key_hi", "<u8"), ("count", "<u8")])
 
 def build(force: bool = False) -> Path:
     """Compile the C restatement with gcc (no external deps)."""
-    if _LIB.exists() and not force and _LIB.stat().st_mtime >= _SRC.stat().st_mtime:
+    if _LIB.exists() and not force and _LIB.stat().st_mtime >= max(_SRC.stat().st_mtime, _SRC2.stat().st_mtime):
         return _LIB
     _LIB.parent.mkdir(parents=True, exist_ok=True)
-    cmd = ["gcc", "-O2", "-fopenmp", "-shared", "-fPIC", "-o", str(_LIB), str(_SRC)]
+    cmd = ["gcc", "-O2", "-fopenmp", "-shared", "-fPIC", "-o", str(_LIB), str(_SRC), str(_SRC2)]
     subprocess.check_call(cmd)
     return _LIB
 
@@ -322,6 +323,29 @@ def pipeline(reads: Reads, k: int, m: int, b1: int, b2: int, min_multiplicity: i
                         C.c_int(n_threads), C.byref(st))
     assert rc == 0
     return st
+
+
+def unitigs_from_tables(keys_lo, keys_hi, count_flags, unit_offsets, k: int, forward_only: bool = False):
+    """Maximal unitigs from per-unit k-mer tables (the layout of include/ggcat_b200.h): partial unitigs per unit as
+    hashmap.rs:442-601, open ends joined.  Returns dict(n_unitigs, n_partial, lengths (sorted), kmers_lo, kmers_hi (sorted))."""
+    L = lib()
+    keys_lo = np.ascontiguousarray(keys_lo, np.uint64)
+    kh = None if keys_hi is None else np.ascontiguousarray(keys_hi, np.uint64)
+    cf = np.ascontiguousarray(count_flags, np.uint32)
+    uo = np.ascontiguousarray(unit_offsets, np.uint64)
+    n = keys_lo.size
+    lengths = np.zeros(n + 1, np.uint64)
+    klo = np.zeros(n + 1, np.uint64)
+    khi = np.zeros(n + 1, np.uint64)
+    nu, npart, nk = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+    L.orc_unitigs_from_tables.restype = C.c_int
+    rc = L.orc_unitigs_from_tables(_p(keys_lo), _p(kh) if kh is not None else None, _p(cf), _p(uo), C.c_size_t(uo.size - 1),
+                                   C.c_uint(k), C.c_int(forward_only), C.byref(nu), C.byref(npart), C.byref(nk), _p(lengths),
+                                   C.c_size_t(n + 1), _p(klo), _p(khi), C.c_size_t(n + 1))
+    if rc != 0:
+        raise AssertionError(f"unitig join inconsistent (code {rc})")
+    return {"n_unitigs": nu.value, "n_partial": npart.value, "lengths": lengths[: nu.value].copy(),
+            "kmers_lo": klo[: nk.value].copy(), "kmers_hi": khi[: nk.value].copy()}
 
 
 def table_checksum(keys_lo, mult, flags) -> int:

@@ -30,6 +30,10 @@ def main():
             "n_entries": int(len(tab)),
             "digest": util.table_digest(tab["key_lo"], None, tab["multiplicity"], tab["flags"]),
         }
+    # maximal unitigs of the whole input (consumer restatement, oracle/ggcat_unitigs.c) from the global k-mer set
+    U = O.unitigs_from_tables(nv["key_lo"], nv["key_hi"], nv["count"].astype(np.uint32), np.array([0, len(nv)], np.uint64), k)
+    out["n_unitigs"] = int(U["n_unitigs"])
+    out["unitig_bases"] = int(U["lengths"].sum())
     (ROOT / "tests" / "golden" / "c1_golden.json").write_text(json.dumps(out, indent=1) + "\n")
     print(json.dumps(out, indent=1))
 

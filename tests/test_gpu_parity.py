@@ -364,6 +364,54 @@ def test_colored_build(k, m, b1, b2, s, fo):
         ctx.close()
 
 
+@pytest.mark.parametrize("k,m,b1,b2,s,fo", [(31, 12, 3, 2, 1, False), (31, 12, 2, 2, 2, False), (21, 10, 2, 2, 1, True),
+                                             (41, 13, 2, 1, 1, False)])
+def test_maximal_unitigs_from_gpu_tables(k, m, b1, b2, s, fo):
+    """North-star check 2: maximal unitigs built by the reference's consumer logic (oracle restatement of
+    hashmap.rs compute_unitigs per unit + join of open ends) from the GPU tables equal the unitigs of the
+    independently counted global k-mer set: same unitig count, length multiset and canonical k-mer set."""
+    G = _gpu()
+    rng = np.random.default_rng(k * 3 + s)
+    g = util.rand_seq(rng, 20000)
+    cyc = util.rand_seq(rng, 400)
+    seqs = [g, util.revcomp(g[3000:9000]), g[8000:15000], g[:700] + g[1500:3000], util.rand_seq(rng, 900),
+            g[15000:16000] + g[100:1100], cyc + cyc[:k], b"ACACACACAC" * 12, g[4000:4100] + b"N" + g[4101:4300]]
+    if s == 2:
+        seqs = seqs + seqs[:5]
+    reads = O.Reads.from_list(seqs)
+    ctx, st = G.minimizer_bucketing([(reads.data, reads.offsets)], b1, b2, k, m, forward_only=fo, min_multiplicity=s)
+    try:
+        tab = ctx.merge_bucket_range(0, (1 << b1) + 1)
+    finally:
+        ctx.close()
+    A = O.unitigs_from_tables(tab.keys_lo, tab.keys_hi, tab.count_flags, tab.unit_offsets, k, fo)
+    nv, _ = O.naive_count(reads, k, O.HASH_SEQ, fo)
+    nv = nv[nv["count"] >= s]
+    B = O.unitigs_from_tables(nv["key_lo"], nv["key_hi"], nv["count"].astype(np.uint32), np.array([0, len(nv)], np.uint64), k, fo)
+    assert A["n_unitigs"] == B["n_unitigs"] and A["n_partial"] > B["n_partial"]
+    assert np.array_equal(A["lengths"], B["lengths"])
+    assert np.array_equal(A["kmers_lo"], nv["key_lo"]) and np.array_equal(A["kmers_hi"], nv["key_hi"])
+
+
+def test_c1_maximal_unitigs(golden_dir):
+    """BASELINE configs[0] end to end: unitigs of sal1+sal2+sal3 (k=31 -s 1) from the GPU tables vs the global set."""
+    G = _gpu()
+    reads = O.Reads.from_list(util.c1_records())
+    k, m, b1, b2, s = 31, 12, 2, 6, 1
+    ctx, st = G.minimizer_bucketing([(reads.data, reads.offsets)], b1, b2, k, m, min_multiplicity=s)
+    try:
+        tab = ctx.merge_bucket_range(0, (1 << b1) + 1)
+    finally:
+        ctx.close()
+    A = O.unitigs_from_tables(tab.keys_lo, tab.keys_hi, tab.count_flags, tab.unit_offsets, k)
+    nv, _ = O.naive_count(reads, k)
+    B = O.unitigs_from_tables(nv["key_lo"], nv["key_hi"], nv["count"].astype(np.uint32), np.array([0, len(nv)], np.uint64), k)
+    gold = json.loads((golden_dir / "c1_golden.json").read_text())
+    assert A["n_unitigs"] == B["n_unitigs"] == gold["n_unitigs"]
+    assert np.array_equal(A["lengths"], B["lengths"])
+    assert np.array_equal(A["kmers_lo"], nv["key_lo"])
+
+
 def test_error_behaviour():
     G = _gpu()
     with pytest.raises(G.GgcatB200Error):

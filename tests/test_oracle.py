@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 from oracle import oracle as O
-from tests import model
+from tests import model, util
 
 RNG = np.random.default_rng(773)
 
@@ -280,3 +280,40 @@ def test_colors_sets():
         for e in tab:
             got = cols[e["color_off"]:e["color_off"] + e["color_len"]].tolist()
             assert got == sorted(truth[int(e["key_lo"])])
+
+
+def _oracle_tables(reads, k, m, b1, b2, s, fo):
+    sk, _ = O.bucketing(reads, k, m, b1, b2, forward_only=fo)
+    nu = ((1 << b1) + 1) << b2
+    kl, kh, cf, uo = [], [], [], [0]
+    for u in range(nu):
+        ref, _, _ = O.merge_unit(reads, sk, u >> b2, u & ((1 << b2) - 1), k, s, O.HASH_SEQ, fo)
+        ref = ref[ref["kept"] == 1]
+        kl.append(ref["key_lo"]); kh.append(ref["key_hi"])
+        cf.append(ref["multiplicity"].astype(np.uint32) | (ref["flags"].astype(np.uint32) << 30))
+        uo.append(uo[-1] + len(ref))
+    return np.concatenate(kl), np.concatenate(kh), np.concatenate(cf), np.array(uo, np.uint64)
+
+
+@pytest.mark.parametrize("k,m,b1,b2,s,fo", [(31, 12, 3, 2, 1, False), (31, 12, 2, 1, 2, False), (21, 10, 2, 2, 1, True),
+                                             (15, 9, 1, 1, 1, False), (41, 13, 2, 2, 1, False)])
+def test_unitigs_per_unit_join_equals_global(k, m, b1, b2, s, fo):
+    """Consumer restatement (hashmap.rs:162-297,442-601): partial unitigs per unit with contig breaks at flagged
+    k-mers, joined at their shared end k-mers, equal the maximal unitigs of the flag-free global k-mer set
+    (independent naive counter): same count, same length multiset, same canonical k-mer set."""
+    rng = np.random.default_rng(k + s)
+    g = util.rand_seq(rng, 6000)
+    cyc = util.rand_seq(rng, 300)
+    seqs = [g, util.revcomp(g[1000:3000]), g[2500:5000], g[:200] + g[400:900], util.rand_seq(rng, 500),
+            g[5000:5600] + g[100:700], cyc + cyc[:k]]
+    if s == 2:
+        seqs = seqs + seqs[:4]
+    reads = O.Reads.from_list(seqs)
+    A = O.unitigs_from_tables(*_oracle_tables(reads, k, m, b1, b2, s, fo), k, fo)
+    nv, _ = O.naive_count(reads, k, O.HASH_SEQ, fo)
+    nv = nv[nv["count"] >= s]
+    B = O.unitigs_from_tables(nv["key_lo"], nv["key_hi"], nv["count"].astype(np.uint32), np.array([0, len(nv)], np.uint64), k, fo)
+    assert A["n_partial"] > A["n_unitigs"] == B["n_unitigs"] == B["n_partial"]
+    assert np.array_equal(A["lengths"], B["lengths"])
+    assert np.array_equal(A["kmers_lo"], nv["key_lo"]) and np.array_equal(A["kmers_hi"], nv["key_hi"])
+    assert np.array_equal(B["kmers_lo"], nv["key_lo"])
