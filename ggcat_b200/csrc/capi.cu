@@ -83,7 +83,7 @@ struct TimedLaunch { int fam; cudaEvent_t a, b; };
 struct HostTable {
     uint64_t *keys = nullptr, *keys_hi = nullptr; uint32_t *cf = nullptr; uint64_t *unit_offsets = nullptr;
     uint64_t *color_offsets = nullptr; uint32_t *colors = nullptr;
-    size_t cap_entries = 0, cap_units = 0, cap_colors = 0;
+    size_t cap_entries = 0, cap_units = 0, cap_colors = 0, cap_coloff = 0;
     bool wide = false, colored = false;
     void release() {
         cudaFreeHost(keys); cudaFreeHost(keys_hi); cudaFreeHost(cf); cudaFreeHost(unit_offsets); cudaFreeHost(color_offsets);
@@ -109,6 +109,11 @@ struct ggcat_b200_ctx {
     cudaStream_t stream = nullptr;
     int sm_count = 148;
     uint64_t max_batch = 1ull << 30;
+    uint64_t host_batch = 40ull << 20;   // push_reads(host): H2D of batch i+1 overlaps the kernels of batch i
+    uint64_t part_kmers = 36ull << 20;   // merge_bucket_range(host): D2H of part j overlaps the merge of part j+1
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr}, ev_part = nullptr;
+    DevBuf st_ascii[2], st_off[2], st_col[2];
     bool finished = false;
     bool timing = false;
     int merge_mode = 1;  // 1 = shared-memory hash table (default), 0 = LSD radix sort (GGCAT_B200_MERGE=sort)
@@ -312,9 +317,9 @@ __global__ void k_gather_units(const uint64_t *__restrict__ src_keys, const uint
 }
 
 // exclusive scan u32 counts -> u64 offsets (n_units small: single CTA, sequential per thread chunks)
-__global__ void __launch_bounds__(1024) k_scan_counts_u64(const uint32_t *cnt, uint64_t *off, uint32_t n) {
+__global__ void __launch_bounds__(1024) k_scan_counts_u64(const uint32_t *cnt, uint64_t *off, uint32_t n, uint64_t base = 0) {
     __shared__ uint32_t s_scan[1024 / 32 + 2];
-    uint64_t running = 0;
+    uint64_t running = base;
     for (uint32_t base = 0; base < n; base += 1024) {
         const uint32_t i = base + threadIdx.x;
         const uint32_t v = i < n ? cnt[i] : 0u;
@@ -331,18 +336,22 @@ constexpr int SM_THREADS_L = 1024, SM_CAP_L = 12288;   // 1 CTA / SM
 constexpr int GL_THREADS = 1024;
 constexpr int HASH_TS_S = 8192, HASH_TS_L = 16384;       // hash-table slots: unit records <= 3/4 of the slots
 
+// A bucket range may be merged in several parts that append to one final table (merge_range_parts): `eb` = entries
+// already in the table, `ub` = units already in unit_final_off, `cap_total` = final-buffer capacity for the whole range.
+struct PartBase { uint64_t eb = 0; uint32_t ub = 0; uint64_t cap_total = 0; };
+
 int32_t merge_range_device_wide(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_buckets, uint64_t *n_entries,
-                                uint64_t *unique, uint64_t *total);
+                                uint64_t *unique, uint64_t *total, PartBase pb);
 
 int32_t merge_range_device(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_buckets, uint64_t *n_entries,
-                           uint64_t *unique, uint64_t *total) {
+                           uint64_t *unique, uint64_t *total, PartBase pb = PartBase()) {
     const DevParams &P = c->P;
     cudaStream_t st = c->stream;
     if (!c->finished) return set_err(GGCAT_B200_ERR_STATE, "merge before finish_bucketing");
     const uint32_t nb_total = (1u << P.b1) + 1;
     if (n_buckets == 0 || first_bucket >= nb_total || first_bucket + n_buckets > nb_total)
         return set_err(GGCAT_B200_ERR_INVALID, "bucket range [%u,+%u) outside 0..%u", first_bucket, n_buckets, nb_total);
-    if (c->wide_mode >= 0) return merge_range_device_wide(c, first_bucket, n_buckets, n_entries, unique, total);
+    if (c->wide_mode >= 0) return merge_range_device_wide(c, first_bucket, n_buckets, n_entries, unique, total, pb);
     const uint32_t u0 = first_bucket << P.b2, nu = n_buckets << P.b2;
     // classify units by record count
     std::vector<uint32_t> work[3];
@@ -405,7 +414,7 @@ int32_t merge_range_device(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_
     CU(cudaMemsetAsync(retry_cnt, 0, 4, st));
     CU(cudaMemsetAsync(retry2_cnt, 0, 4, st));
     CU(c->unit_out_off.reserve(((size_t)nu + 1) * 8)); CU(c->unit_out_cnt.reserve(((size_t)nu + 1) * 4));
-    CU(c->unit_final_off.reserve(((size_t)nu + 1) * 8));
+    if (pb.ub == 0) CU(c->unit_final_off.reserve(((size_t)c->P.n_units + 2) * 8));
     CU(cudaMemsetAsync(c->cursor.p, 0, 64, st));
     CU(cudaMemsetAsync(c->overflow.p, 0, 16, st));
     CU(cudaMemsetAsync(c->unit_out_off.p, 0, ((size_t)nu + 1) * 8, st));
@@ -489,14 +498,17 @@ int32_t merge_range_device(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_
         }
     }
     CU(cudaGetLastError());
-    // unit-ordered final layout
-    CU(c->out_keys2.reserve(cap * 8)); CU(c->out_cf2.reserve(cap * 4));
+    // unit-ordered final layout (parts append at entry pb.eb / unit pb.ub)
+    if (pb.ub == 0) {
+        const uint64_t fc = std::max(cap, pb.cap_total);
+        CU(c->out_keys2.reserve(fc * 8)); CU(c->out_cf2.reserve(fc * 4));
+    }
     {
         LaunchTimer t(c, F_GATHER, 2);
-        k_scan_counts_u64<<<1, 1024, 0, st>>>(c->unit_out_cnt.as<uint32_t>(), c->unit_final_off.as<uint64_t>(), nu);
+        k_scan_counts_u64<<<1, 1024, 0, st>>>(c->unit_out_cnt.as<uint32_t>(), c->unit_final_off.as<uint64_t>() + pb.ub, nu, pb.eb);
         k_gather_units<<<(unsigned)std::min<uint32_t>(nu, (uint32_t)c->sm_count * 8), 128, 0, st>>>(
             c->out_keys.as<uint64_t>(), c->out_cf.as<uint32_t>(), c->unit_out_off.as<uint64_t>(),
-            c->unit_out_cnt.as<uint32_t>(), c->unit_final_off.as<uint64_t>(), c->out_keys2.as<uint64_t>(),
+            c->unit_out_cnt.as<uint32_t>(), c->unit_final_off.as<uint64_t>() + pb.ub, c->out_keys2.as<uint64_t>(),
             c->out_cf2.as<uint32_t>(), nu);
     }
     CU(cudaMemcpyAsync(c->h_pinned, c->cursor.p, 24, cudaMemcpyDeviceToHost, st));
@@ -508,7 +520,7 @@ int32_t merge_range_device(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_
     c->last_entries = c->h_pinned[0];
     c->fin = FinalTable();
     c->fin.keys_lo = c->out_keys2.as<uint64_t>(); c->fin.cf = c->out_cf2.as<uint32_t>();
-    c->fin.unit_off = c->unit_final_off.as<uint64_t>(); c->fin.n_entries = c->h_pinned[0];
+    c->fin.unit_off = c->unit_final_off.as<uint64_t>(); c->fin.n_entries = pb.eb + c->h_pinned[0];
     if (n_entries) *n_entries = c->h_pinned[0];
     if (unique) *unique = c->h_pinned[1];
     if (total) *total = c->h_pinned[2];
@@ -566,7 +578,7 @@ int32_t launch_hash128(ggcat_b200_ctx *c, const ChunkView *dv, uint32_t nch, std
 }
 
 int32_t merge_range_device_wide(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_buckets, uint64_t *n_entries,
-                                uint64_t *unique, uint64_t *total) {
+                                uint64_t *unique, uint64_t *total, PartBase pb) {
     const DevParams &P = c->P;
     cudaStream_t st = c->stream;
     const uint32_t u0 = first_bucket << P.b2, nu = n_buckets << P.b2;
@@ -603,10 +615,13 @@ int32_t merge_range_device_wide(ggcat_b200_ctx *c, uint32_t first_bucket, uint32
     }
     const uint64_t cap = std::max<uint64_t>(tot_kmers, 1);
     CU(c->out_keys.reserve(cap * 8)); CU(c->out_hi.reserve(cap * 8)); CU(c->out_cf.reserve(cap * 4));
-    CU(c->out_keys2.reserve(cap * 8)); CU(c->out_hi2.reserve(cap * 8)); CU(c->out_cf2.reserve(cap * 4));
+    if (pb.ub == 0) {
+        const uint64_t fc = std::max(cap, pb.cap_total);
+        CU(c->out_keys2.reserve(fc * 8)); CU(c->out_hi2.reserve(fc * 8)); CU(c->out_cf2.reserve(fc * 4));
+        CU(c->unit_final_off.reserve(((size_t)c->P.n_units + 2) * 8));
+    }
     CU(c->cursor.reserve(64)); CU(c->overflow.reserve(16));
     CU(c->unit_out_off.reserve(((size_t)nu + 1) * 8)); CU(c->unit_out_cnt.reserve(((size_t)nu + 1) * 4));
-    CU(c->unit_final_off.reserve(((size_t)nu + 1) * 8));
     CU(cudaMemsetAsync(c->cursor.p, 0, 64, st));
     CU(cudaMemsetAsync(c->overflow.p, 0, 16, st));
     CU(cudaMemsetAsync(c->unit_out_off.p, 0, ((size_t)nu + 1) * 8, st));
@@ -626,13 +641,13 @@ int32_t merge_range_device_wide(ggcat_b200_ctx *c, uint32_t first_bucket, uint32
     else if (c->wide_mode == MODE_COLOR) end_bit = std::min(128u, (32 + 2 * P.k + 7) & ~7u);
     {
         LaunchTimer t(c, F_SORT128, 2);
-        k_scan_counts_u64<<<1, 1024, 0, st>>>(c->unit_out_cnt.as<uint32_t>(), c->unit_final_off.as<uint64_t>(), nu);
+        k_scan_counts_u64<<<1, 1024, 0, st>>>(c->unit_out_cnt.as<uint32_t>(), c->unit_final_off.as<uint64_t>() + pb.ub, nu, pb.eb);
         auto kern = k_sort_units128<W_SORT_THREADS, W_SORT_CAP>;
         const size_t smem = sort_units128_smem_bytes<W_SORT_THREADS, W_SORT_CAP>();
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<(unsigned)std::min<uint32_t>(nu, (uint32_t)c->sm_count * 2 * 8), W_SORT_THREADS, smem, st>>>(
             c->out_keys.as<uint64_t>(), c->out_hi.as<uint64_t>(), c->out_cf.as<uint32_t>(), c->unit_out_off.as<uint64_t>(),
-            c->unit_out_cnt.as<uint32_t>(), c->unit_final_off.as<uint64_t>(), c->out_keys2.as<uint64_t>(),
+            c->unit_out_cnt.as<uint32_t>(), c->unit_final_off.as<uint64_t>() + pb.ub, c->out_keys2.as<uint64_t>(),
             c->out_hi2.as<uint64_t>(), c->out_cf2.as<uint32_t>(), nu, 0u, end_bit);
     }
     CU(cudaGetLastError());
@@ -675,9 +690,9 @@ int32_t merge_range_device_wide(ggcat_b200_ctx *c, uint32_t first_bucket, uint32
     if (c->wide_mode == MODE_COLOR) {
         c->fin.n_entries = c->h_pinned[4]; c->fin.n_colors = c->h_pinned[5];
         uq = 0;  // distinct (k-mer, colour) pairs are not the reference's distinct k-mers; not tracked for coloured builds
-    } else c->fin.n_entries = c->h_pinned[0];
+    } else c->fin.n_entries = pb.eb + c->h_pinned[0];
     c->last_entries = c->fin.n_entries;
-    if (n_entries) *n_entries = c->fin.n_entries;
+    if (n_entries) *n_entries = c->wide_mode == MODE_COLOR ? c->fin.n_entries : c->h_pinned[0];
     if (unique) *unique = uq;
     if (total) *total = c->h_pinned[2];
     return 0;
@@ -768,8 +783,16 @@ int32_t ggcat_b200_create(const ggcat_b200_params *params, ggcat_b200_ctx **out)
     if (const char *mb = getenv("GGCAT_B200_MAX_BATCH")) { uint64_t v = strtoull(mb, nullptr, 10); if (v >= 1024) c->max_batch = std::min<uint64_t>(v, 1ull << 30); }
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, p.device) == cudaSuccess) c->sm_count = prop.multiProcessorCount;
-    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaMallocHost((void **)&c->h_pinned, 16 * 8) != cudaSuccess) {
+    if (const char *hb = getenv("GGCAT_B200_HOST_BATCH")) { uint64_t v = strtoull(hb, nullptr, 10); if (v >= 1024) c->host_batch = std::min<uint64_t>(v, c->max_batch); }
+    if (const char *pk = getenv("GGCAT_B200_PART_KMERS")) { uint64_t v = strtoull(pk, nullptr, 10); if (v >= 1024) c->part_kmers = v; }
+    c->host_batch = std::min(c->host_batch, c->max_batch);
+    bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaEventCreateWithFlags(&c->ev_part, cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; i < 2 && ok; i++)
+        ok = cudaEventCreateWithFlags(&c->ev_h2d[i], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&c->ev_free[i], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok || cudaMallocHost((void **)&c->h_pinned, 16 * 8) != cudaSuccess) {
         delete c;
         return set_err(GGCAT_B200_ERR_CUDA, "stream / pinned allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
     }
@@ -806,6 +829,13 @@ void ggcat_b200_destroy(ggcat_b200_ctx *c) {
     for (cudaEvent_t e : c->event_pool) cudaEventDestroy(e);
     for (HostTable *t : c->free_tables) { t->release(); delete t; }
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
+    for (int i = 0; i < 2; i++) {
+        c->st_ascii[i].release(); c->st_off[i].release(); c->st_col[i].release();
+        if (c->ev_h2d[i]) cudaEventDestroy(c->ev_h2d[i]);
+        if (c->ev_free[i]) cudaEventDestroy(c->ev_free[i]);
+    }
+    if (c->ev_part) cudaEventDestroy(c->ev_part);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -817,34 +847,46 @@ int32_t ggcat_b200_push_reads(ggcat_b200_ctx *c, const uint8_t *data, const uint
     if (n_reads == 0) return 0;
     if (!data || !offsets) return set_err(GGCAT_B200_ERR_INVALID, "null input");
     if (colors && !c->P.colors) colors = nullptr;
-    uint64_t r0 = 0;
-    while (r0 < n_reads) {
-        // greedy batch of whole records, <= max_batch bases
-        uint64_t r1 = r0 + 1;
-        if (offsets[r1] - offsets[r0] > c->max_batch)
+    // greedy batches of whole records, <= host_batch bases (a longer single record gets its own batch, <= max_batch)
+    std::vector<std::pair<uint64_t, uint64_t>> batches;
+    for (uint64_t r0 = 0; r0 < n_reads;) {
+        if (offsets[r0 + 1] - offsets[r0] > c->max_batch)
             return set_err(GGCAT_B200_ERR_INVALID, "record %llu is longer than the batch limit %llu; split it with k-1 overlap "
                            "(crates/io/src/sequences_reader.rs:162-173)", (unsigned long long)r0, (unsigned long long)c->max_batch);
-        {   // binary search for the last record that still fits
-            uint64_t lo = r1, hi = n_reads;
-            while (lo < hi) {
-                uint64_t mid = (lo + hi + 1) >> 1;
-                if (offsets[mid] - offsets[r0] <= c->max_batch) lo = mid; else hi = mid - 1;
-            }
-            r1 = lo;
+        uint64_t lo = r0 + 1, hi = n_reads;
+        while (lo < hi) {  // last record that still fits
+            const uint64_t mid = (lo + hi + 1) >> 1;
+            if (offsets[mid] - offsets[r0] <= c->host_batch) lo = mid; else hi = mid - 1;
         }
+        batches.push_back({r0, lo});
+        r0 = lo;
+    }
+    // double-buffered staging: copy stream fills slot (i+1)&1 while the compute stream works on slot i&1
+    auto issue_copy = [&](size_t bi) -> int32_t {
+        const int sl = (int)(bi & 1);
+        const uint64_t r0 = batches[bi].first, r1 = batches[bi].second;
         const uint64_t nb = offsets[r1] - offsets[r0], nr = r1 - r0;
-        CU(c->d_ascii.reserve(nb + 64));
-        CU(c->d_offsets.reserve((nr + 1) * 8));
-        CU(cudaMemcpyAsync(c->d_ascii.p, data + offsets[r0], nb, cudaMemcpyHostToDevice, c->stream));
-        CU(cudaMemcpyAsync(c->d_offsets.p, offsets + r0, (nr + 1) * 8, cudaMemcpyHostToDevice, c->stream));
-        const uint32_t *dcol = nullptr;
+        CU(cudaStreamWaitEvent(c->copy_stream, c->ev_free[sl], 0));
+        CU(c->st_ascii[sl].reserve(nb + 64));
+        CU(c->st_off[sl].reserve((nr + 1) * 8));
+        CU(cudaMemcpyAsync(c->st_ascii[sl].p, data + offsets[r0], nb, cudaMemcpyHostToDevice, c->copy_stream));
+        CU(cudaMemcpyAsync(c->st_off[sl].p, offsets + r0, (nr + 1) * 8, cudaMemcpyHostToDevice, c->copy_stream));
         if (colors) {
-            CU(c->d_colors.reserve(nr * 4));
-            CU(cudaMemcpyAsync(c->d_colors.p, colors + r0, nr * 4, cudaMemcpyHostToDevice, c->stream));
-            dcol = c->d_colors.as<uint32_t>();
+            CU(c->st_col[sl].reserve(nr * 4));
+            CU(cudaMemcpyAsync(c->st_col[sl].p, colors + r0, nr * 4, cudaMemcpyHostToDevice, c->copy_stream));
         }
-        TRY(bucket_batch_device(c, c->d_ascii.as<uint8_t>(), c->d_offsets.as<uint64_t>(), nr, offsets[r0], nb, dcol));
-        r0 = r1;
+        CU(cudaEventRecord(c->ev_h2d[sl], c->copy_stream));
+        return 0;
+    };
+    TRY(issue_copy(0));
+    for (size_t bi = 0; bi < batches.size(); bi++) {
+        const int sl = (int)(bi & 1);
+        if (bi + 1 < batches.size()) TRY(issue_copy(bi + 1));
+        const uint64_t r0 = batches[bi].first, r1 = batches[bi].second;
+        CU(cudaStreamWaitEvent(c->stream, c->ev_h2d[sl], 0));
+        TRY(bucket_batch_device(c, c->st_ascii[sl].as<uint8_t>(), c->st_off[sl].as<uint64_t>(), r1 - r0, offsets[r0],
+                                offsets[r1] - offsets[r0], colors ? c->st_col[sl].as<uint32_t>() : nullptr));
+        CU(cudaEventRecord(c->ev_free[sl], c->stream));
     }
     return 0;
 }
@@ -946,47 +988,115 @@ int32_t ggcat_b200_merge_bucket_range_device(ggcat_b200_ctx *c, uint32_t first_b
     return merge_range_device(c, first_bucket, n_buckets, n_entries, unique_kmers, total_kmers);
 }
 
+// Host-table growth for the part-wise D2H: keeps what was already copied.
+static int32_t host_table_reserve(ggcat_b200_ctx *c, HostTable *t, uint64_t need_entries, uint64_t copied, bool wide) {
+    if (need_entries <= t->cap_entries) return 0;
+    CU(cudaStreamSynchronize(c->copy_stream));
+    const uint64_t cap = std::max<uint64_t>(need_entries + need_entries / 2, 1024);
+    uint64_t *nk = nullptr, *nh = nullptr; uint32_t *nc = nullptr;
+    bool ok = cudaMallocHost((void **)&nk, cap * 8) == cudaSuccess && cudaMallocHost((void **)&nc, cap * 4) == cudaSuccess;
+    if (ok && wide) ok = cudaMallocHost((void **)&nh, cap * 8) == cudaSuccess;
+    if (!ok) { cudaFreeHost(nk); cudaFreeHost(nc); cudaFreeHost(nh); return set_err(GGCAT_B200_ERR_CUDA, "pinned table allocation failed"); }
+    if (copied) {
+        memcpy(nk, t->keys, copied * 8); memcpy(nc, t->cf, copied * 4);
+        if (wide) memcpy(nh, t->keys_hi, copied * 8);
+    }
+    cudaFreeHost(t->keys); cudaFreeHost(t->cf); cudaFreeHost(t->keys_hi);
+    t->keys = nk; t->cf = nc; t->keys_hi = nh; t->cap_entries = cap;
+    return 0;
+}
+
 int32_t ggcat_b200_merge_bucket_range(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_buckets, ggcat_b200_table *out) {
     TRY(check_ctx(c));
     if (!out) return set_err(GGCAT_B200_ERR_INVALID, "null table");
     memset(out, 0, sizeof(*out));
-    uint64_t ne = 0, uq = 0, tk = 0;
-    TRY(merge_range_device(c, first_bucket, n_buckets, &ne, &uq, &tk));
-    const uint32_t nu = n_buckets << c->P.b2;
-    const FinalTable &f = c->fin;
-    const bool wide = f.keys_hi != nullptr, colored = f.color_off != nullptr;
-    const uint64_t ncol = f.n_colors;
+    if (!c->finished) return set_err(GGCAT_B200_ERR_STATE, "merge before finish_bucketing");
+    const DevParams &P = c->P;
+    const uint32_t nb_total = (1u << P.b1) + 1;
+    if (n_buckets == 0 || first_bucket >= nb_total || first_bucket + n_buckets > nb_total)
+        return set_err(GGCAT_B200_ERR_INVALID, "bucket range [%u,+%u) outside 0..%u", first_bucket, n_buckets, nb_total);
+    const uint32_t nu = n_buckets << P.b2;
+    const bool colored = c->wide_mode == MODE_COLOR, wide = c->wide_mode >= 0;
+    // split the range into parts of ~part_kmers records (whole buckets); coloured builds fold in one piece
+    std::vector<uint64_t> bk(n_buckets, 0);
+    uint64_t tot = 0;
+    for (uint32_t b = 0; b < n_buckets; b++) {
+        for (uint32_t u = (first_bucket + b) << P.b2; u < ((first_bucket + b + 1) << P.b2); u++)
+            for (Chunk *ch : c->chunks)
+                if (u >= ch->first_unit && u < ch->first_unit + ch->n_units) bk[b] += ch->h_kmers[u - ch->first_unit];
+        tot += bk[b];
+    }
+    std::vector<std::pair<uint32_t, uint32_t>> parts;  // (first bucket, count)
+    if (colored || tot <= c->part_kmers + c->part_kmers / 2) parts.push_back({first_bucket, n_buckets});
+    else {
+        uint32_t b0 = 0; uint64_t acc = 0;
+        for (uint32_t b = 0; b < n_buckets; b++) {
+            acc += bk[b];
+            if (acc >= c->part_kmers || b + 1 == n_buckets) { parts.push_back({first_bucket + b0, b + 1 - b0}); b0 = b + 1; acc = 0; }
+        }
+    }
     HostTable *t = nullptr;
     for (size_t i = 0; i < c->free_tables.size(); i++) {
         HostTable *q = c->free_tables[i];
-        if (q->cap_entries >= ne && q->cap_units >= nu + 1 && q->wide == wide && q->colored == colored && q->cap_colors >= ncol) {
-            t = q; c->free_tables.erase(c->free_tables.begin() + i); break;
-        }
+        if (q->cap_units >= nu + 1 && q->wide == wide && q->colored == colored) { t = q; c->free_tables.erase(c->free_tables.begin() + i); break; }
     }
     if (!t) {
         t = new HostTable();
-        t->cap_entries = std::max<uint64_t>(ne + ne / 4, 1024); t->cap_units = nu + 1; t->wide = wide; t->colored = colored;
-        t->cap_colors = colored ? std::max<uint64_t>(ncol + ncol / 4, 1024) : 0;
-        bool ok = cudaMallocHost((void **)&t->keys, t->cap_entries * 8) == cudaSuccess &&
-                  cudaMallocHost((void **)&t->cf, t->cap_entries * 4) == cudaSuccess &&
-                  cudaMallocHost((void **)&t->unit_offsets, t->cap_units * 8) == cudaSuccess;
-        if (ok && wide) ok = cudaMallocHost((void **)&t->keys_hi, t->cap_entries * 8) == cudaSuccess;
-        if (ok && colored) ok = cudaMallocHost((void **)&t->color_offsets, (t->cap_entries + 1) * 8) == cudaSuccess &&
-                                cudaMallocHost((void **)&t->colors, t->cap_colors * 4) == cudaSuccess;
-        if (!ok) { t->release(); delete t; return set_err(GGCAT_B200_ERR_CUDA, "pinned table allocation failed"); }
+        t->cap_units = nu + 1; t->wide = wide; t->colored = colored;
+        if (cudaMallocHost((void **)&t->unit_offsets, t->cap_units * 8) != cudaSuccess) { delete t; return set_err(GGCAT_B200_ERR_CUDA, "pinned table allocation failed"); }
     }
-    if (ne) {
-        CU(cudaMemcpyAsync(t->keys, f.keys_lo, ne * 8, cudaMemcpyDeviceToHost, c->stream));
-        CU(cudaMemcpyAsync(t->cf, f.cf, ne * 4, cudaMemcpyDeviceToHost, c->stream));
-        if (wide) CU(cudaMemcpyAsync(t->keys_hi, f.keys_hi, ne * 8, cudaMemcpyDeviceToHost, c->stream));
-        if (colored) CU(cudaMemcpyAsync(t->color_offsets, f.color_off, ne * 8, cudaMemcpyDeviceToHost, c->stream));
-        if (colored && ncol) CU(cudaMemcpyAsync(t->colors, f.colors, ncol * 4, cudaMemcpyDeviceToHost, c->stream));
+    auto fail = [&](int32_t rc) { c->free_tables.push_back(t); return rc; };
+    uint64_t eb = 0, uq = 0, tk = 0;
+    uint32_t ub = 0;
+    for (size_t pi = 0; pi < parts.size(); pi++) {
+        PartBase pb; pb.eb = eb; pb.ub = ub; pb.cap_total = std::max<uint64_t>(tot, 1);
+        uint64_t ne = 0, u1 = 0, t1 = 0;
+        int32_t rc = merge_range_device(c, parts[pi].first, parts[pi].second, &ne, &u1, &t1, pb);  // ends with a stream sync
+        if (rc) return fail(rc);
+        uq += u1; tk += t1;
+        if (!colored) {
+            rc = host_table_reserve(c, t, eb + ne + (pi + 1 < parts.size() ? ne : 0), eb, wide);
+            if (rc) return fail(rc);
+            if (ne) {  // the part is complete on the compute stream (synchronised): copy it out while the next part merges
+                const FinalTable &f = c->fin;
+                CU(cudaMemcpyAsync(t->keys + eb, f.keys_lo + eb, ne * 8, cudaMemcpyDeviceToHost, c->copy_stream));
+                CU(cudaMemcpyAsync(t->cf + eb, f.cf + eb, ne * 4, cudaMemcpyDeviceToHost, c->copy_stream));
+                if (wide) CU(cudaMemcpyAsync(t->keys_hi + eb, f.keys_hi + eb, ne * 8, cudaMemcpyDeviceToHost, c->copy_stream));
+            }
+            eb += ne;
+        } else eb = ne;
+        ub += parts[pi].second << P.b2;
     }
-    CU(cudaMemcpyAsync(t->unit_offsets, f.unit_off, ((size_t)nu + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
+    const FinalTable &f = c->fin;
+    const uint64_t ne = eb, ncol = f.n_colors;
+    if (colored) {
+        int32_t rc = host_table_reserve(c, t, ne, 0, wide);
+        if (rc) return fail(rc);
+        if (t->cap_colors < ncol || !t->colors) {
+            cudaFreeHost(t->colors);
+            t->colors = nullptr;
+            t->cap_colors = std::max<uint64_t>(ncol + ncol / 4, 1024);
+            if (cudaMallocHost((void **)&t->colors, t->cap_colors * 4) != cudaSuccess) { t->cap_colors = 0; return fail(set_err(GGCAT_B200_ERR_CUDA, "pinned table allocation failed")); }
+        }
+        if (t->cap_coloff < ne + 1 || !t->color_offsets) {
+            cudaFreeHost(t->color_offsets);
+            t->color_offsets = nullptr;
+            t->cap_coloff = std::max<uint64_t>(ne + ne / 4 + 1, 1024);
+            if (cudaMallocHost((void **)&t->color_offsets, t->cap_coloff * 8) != cudaSuccess) { t->cap_coloff = 0; return fail(set_err(GGCAT_B200_ERR_CUDA, "pinned table allocation failed")); }
+        }
+        if (ne) {
+            CU(cudaMemcpyAsync(t->keys, f.keys_lo, ne * 8, cudaMemcpyDeviceToHost, c->copy_stream));
+            CU(cudaMemcpyAsync(t->cf, f.cf, ne * 4, cudaMemcpyDeviceToHost, c->copy_stream));
+            CU(cudaMemcpyAsync(t->keys_hi, f.keys_hi, ne * 8, cudaMemcpyDeviceToHost, c->copy_stream));
+            CU(cudaMemcpyAsync(t->color_offsets, f.color_off, ne * 8, cudaMemcpyDeviceToHost, c->copy_stream));
+            if (ncol) CU(cudaMemcpyAsync(t->colors, f.colors, ncol * 4, cudaMemcpyDeviceToHost, c->copy_stream));
+        }
+    }
+    CU(cudaMemcpyAsync(t->unit_offsets, f.unit_off, ((size_t)nu + 1) * 8, cudaMemcpyDeviceToHost, c->copy_stream));
+    CU(cudaStreamSynchronize(c->copy_stream));
     if (colored) t->color_offsets[ne] = ncol;
     out->n_entries = ne; out->keys_lo = t->keys; out->keys_hi = wide ? t->keys_hi : nullptr; out->count_flags = t->cf;
-    out->first_unit = first_bucket << c->P.b2; out->n_units = nu; out->unit_offsets = t->unit_offsets;
+    out->first_unit = first_bucket << P.b2; out->n_units = nu; out->unit_offsets = t->unit_offsets;
     out->color_offsets = colored ? t->color_offsets : nullptr; out->colors = colored ? t->colors : nullptr;
     out->total_kmers = tk; out->unique_kmers = uq; out->opaque = t;
     return 0;

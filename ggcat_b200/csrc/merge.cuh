@@ -267,47 +267,123 @@ k_merge_units(const ChunkView *__restrict__ chunks, uint32_t n_chunks, const uin
 //   slot key  = canonical k-mer (CAS-claimed, linear probing, load <= 0.75),
 //   slot word = MapEntry: counter in bits 0..29 (atomicAdd), flags in bits 30..31 (atomicOr).
 // After all super-k-mers are inserted the table is scanned once: multiplicity = counter >> (flags==3),
-// survivors (multiplicity >= -s) are compacted in place and only THEY are radix-sorted (key order is
-// part of the output contract), so the sort cost scales with the table that leaves the GPU, not with
-// the k-mer occurrences.  Units whose survivors exceed half the table (no room for the sort's second
-// buffer) are appended to `retry` and re-done by the sort-based kernel.
+// survivors (multiplicity >= -s) are ordered by key (part of the output contract) with a bin-rank sort, so the
+// sort cost scales with the table that leaves the GPU, not with the k-mer occurrences.
 constexpr uint64_t HASH_EMPTY = ~0ull;
 
 __device__ __forceinline__ void hash_insert(uint64_t *K, uint32_t *C, uint32_t mask, uint64_t key, uint32_t fb) {
     uint32_t slot = (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> 33) & mask;
     while (true) {
-        const unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long *>(&K[slot]), HASH_EMPTY, key);
-        if (old == HASH_EMPTY || old == key) break;
+        // most occurrences hit a key that is already there (coverage): look before the CAS
+        const uint64_t cur = *reinterpret_cast<volatile uint64_t *>(&K[slot]);
+        if (cur == key) break;
+        if (cur == HASH_EMPTY) {
+            const unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long *>(&K[slot]), HASH_EMPTY, key);
+            if (old == HASH_EMPTY || old == key) break;
+        }
         slot = (slot + 1) & mask;
     }
     atomicAdd(&C[slot], 1u);
     if (fb) atomicOr(&C[slot], fb << 30);
 }
 
-__device__ __forceinline__ void expand_insert64(const uint32_t *__restrict__ pl, uint32_t len, uint32_t flags, uint32_t k,
-                                                uint32_t forward_only, uint64_t *K, uint32_t *C, uint32_t tmask) {
+// ---- load-balanced expansion of a unit ---------------------------------------------------------------------------
+// The k-mer records of a unit are numbered 0..n over all its super-k-mers (all chunks); every thread takes `rpt`
+// CONSECUTIVE records: one binary search in the staged prefix sums finds its first (super-k-mer, offset), the first
+// k-mer is extracted at an arbitrary bit offset, the rest roll (cn_seqhash_base.rs:52-69) and step into the next
+// super-k-mer when one ends.  Work per thread is equal whatever the super-k-mer lengths are.
+constexpr int UNIT_MAXC = 32;   // chunks gathered per group
+constexpr int UNIT_DCAP = 512;  // descriptors staged per round
+
+struct UnitStage {                       // lives in the kernel's scratch area while records are inserted
+    const uint32_t *ptr[UNIT_DCAP];      // payload of the super-k-mer
+    uint32_t start[UNIT_DCAP + 1];       // first record number (exclusive prefix of k-mer counts)
+    uint32_t lenfl[UNIT_DCAP];           // len | flags << 30
+    uint32_t c_d0[UNIT_MAXC], c_cnt[UNIT_MAXC];
+};
+
+template <int THREADS, typename Emit>
+__device__ __forceinline__ void unit_for_each_kmer64(const ChunkView *__restrict__ chunks, uint32_t n_chunks, uint32_t unit,
+                                                     uint32_t k, uint32_t forward_only, UnitStage *S, uint32_t *s_scan,
+                                                     Emit emit) {
+    static_assert(THREADS >= UNIT_DCAP, "one staged descriptor per thread");
+    const uint32_t tid = threadIdx.x;
     const uint64_t mask = (1ull << (2 * k)) - 1ull;
-    uint64_t fw = extract64(pl, 0) & mask;
-    uint64_t rc = revcomp64(fw) >> (64 - 2 * k);
-    const uint32_t last = len - k;
-    uint32_t cw = 0;
-    for (uint32_t i = 0;; ++i) {
-        const bool isf = forward_only ? true : (fw < rc);
-        const uint64_t key = forward_only ? fw : (fw < rc ? fw : rc);
-        const uint32_t bi = (!(flags & READ_FLAG_INCL_BEGIN) && i == 0) ? 1u : 0u;
-        const uint32_t ei = (!(flags & READ_FLAG_INCL_END) && i == last) ? 1u : 0u;
-        hash_insert(K, C, tmask, key, (bi << (isf ? 0 : 1)) | (ei << (isf ? 1 : 0)));
-        if (i == last) break;
-        const uint32_t nb = i + k;
-        if ((nb & 15u) == 0 || i == 0) cw = pl[nb >> 4];
-        const uint64_t b = (cw >> (2u * (nb & 15u))) & 3u;
-        fw = (fw >> 2) | (b << (2 * (k - 1)));
-        rc = ((rc << 2) | (b ^ 2ull)) & mask;
+    for (uint32_t c0 = 0; c0 < n_chunks; c0 += UNIT_MAXC) {
+        const uint32_t nc = min((uint32_t)UNIT_MAXC, n_chunks - c0);
+        if (tid < nc) {
+            const ChunkView &cv = chunks[c0 + tid];
+            uint32_t d0 = 0, d1 = 0;
+            if (unit >= cv.first_unit && unit < cv.first_unit + cv.n_units) {
+                d0 = cv.unit_off[unit - cv.first_unit]; d1 = cv.unit_off[unit - cv.first_unit + 1];
+            }
+            S->c_d0[tid] = d0; S->c_cnt[tid] = d1 - d0;
+        }
+        __syncthreads();
+        uint32_t dtot = 0;
+        for (uint32_t c = 0; c < nc; c++) dtot += S->c_cnt[c];
+        for (uint32_t g0 = 0; g0 < dtot; g0 += UNIT_DCAP) {
+            const uint32_t dr = min((uint32_t)UNIT_DCAP, dtot - g0);
+            uint32_t cnt = 0;
+            if (tid < dr) {
+                uint32_t g = g0 + tid, c = 0;
+                while (g >= S->c_cnt[c]) { g -= S->c_cnt[c]; ++c; }
+                const ChunkView &cv = chunks[c0 + c];
+                const uint4 d = cv.desc[S->c_d0[c] + g];
+                S->ptr[tid] = cv.payload + (d.x - cv.word_bias);
+                S->lenfl[tid] = d.y | (((d.z >> 16) & 3u) << 30);
+                cnt = d.y - k + 1;
+            }
+            uint32_t tot;
+            const uint32_t p = block_exclusive_scan<THREADS>(cnt, s_scan, &tot);
+            if (tid < dr) S->start[tid] = p;
+            if (tid == 0) S->start[dr] = tot;
+            __syncthreads();
+            const uint32_t rpt = min(16u, max(1u, (tot + THREADS - 1) / THREADS));
+            for (uint32_t base = tid * rpt; base < tot; base += THREADS * rpt) {
+                uint32_t r = base;
+                const uint32_t rend = min(tot, base + rpt);
+                uint32_t lo = 0, hi = dr - 1;
+                while (lo < hi) {
+                    const uint32_t mid = (lo + hi + 1) >> 1;
+                    if (S->start[mid] <= r) lo = mid; else hi = mid - 1;
+                }
+                uint32_t j = lo, i = r - S->start[j];
+                const uint32_t *pl = S->ptr[j];
+                uint32_t lf = S->lenfl[j];
+                uint32_t last = (lf & 0x3FFFFFFFu) - k, flags = lf >> 30;
+                uint64_t fw = extract64(pl, 2ull * i) & mask;
+                uint64_t rc = revcomp64(fw) >> (64 - 2 * k);
+                uint32_t cw = i < last ? pl[(i + k) >> 4] : 0u;
+                while (true) {
+                    const bool isf = forward_only ? true : (fw < rc);
+                    const uint64_t key = forward_only ? fw : (fw < rc ? fw : rc);
+                    const uint32_t bi = (!(flags & READ_FLAG_INCL_BEGIN) && i == 0) ? 1u : 0u;
+                    const uint32_t ei = (!(flags & READ_FLAG_INCL_END) && i == last) ? 1u : 0u;
+                    emit(key, (bi << (isf ? 0 : 1)) | (ei << (isf ? 1 : 0)));  // hashmap.rs:385-399
+                    if (++r == rend) break;
+                    if (i == last) {  // next super-k-mer
+                        ++j; i = 0;
+                        pl = S->ptr[j]; lf = S->lenfl[j];
+                        last = (lf & 0x3FFFFFFFu) - k; flags = lf >> 30;
+                        fw = extract64(pl, 0) & mask;
+                        rc = revcomp64(fw) >> (64 - 2 * k);
+                        cw = last ? pl[k >> 4] : 0u;
+                    } else {
+                        const uint32_t nb = i + k;
+                        if ((nb & 15u) == 0) cw = pl[nb >> 4];
+                        const uint64_t b = (cw >> (2u * (nb & 15u))) & 3u;
+                        fw = (fw >> 2) | (b << (2 * (k - 1)));
+                        rc = ((rc << 2) | (b ^ 2ull)) & mask;
+                        ++i;
+                    }
+                }
+            }
+            __syncthreads();  // staging is rewritten by the next round
+        }
     }
 }
 
-// TS_STATIC > 0: table of TS_STATIC slots in shared memory.  TS_STATIC == 0: table in this CTA's slice of a
-// global scratch buffer (L2-resident for typical units), sized per unit: hash_table_slots(n).
 __host__ __device__ __forceinline__ uint32_t hash_table_slots(uint32_t n) {  // power of two >= 1.5 n
     uint32_t t = 1024;
     const uint64_t want = (uint64_t)n + n / 2;
@@ -315,6 +391,12 @@ __host__ __device__ __forceinline__ uint32_t hash_table_slots(uint32_t n) {  // 
     return t;
 }
 
+constexpr uint32_t SORT_BINS = 512;  // bin-rank sort: bins on the top 9 key bits
+
+// TS_STATIC > 0: table of up to TS_STATIC slots in shared memory (sized per unit: hash_table_slots(n)); survivors
+// ordered by a bin-rank sort.  TS_STATIC == 0: table in this CTA's slice of a global scratch buffer (L2-resident
+// for typical units); survivors ordered by the LSD radix sort.  Units whose survivors leave no room for the sort's
+// second buffer are appended to `retry` and re-done by the sort-based kernel.
 template <int THREADS, int TS_STATIC>
 __global__ void __launch_bounds__(THREADS)
 k_merge_hash(const ChunkView *__restrict__ chunks, uint32_t n_chunks, const uint32_t *__restrict__ work, uint32_t n_work,
@@ -322,45 +404,54 @@ k_merge_hash(const ChunkView *__restrict__ chunks, uint32_t n_chunks, const uint
              uint32_t *__restrict__ retry_count, uint64_t *__restrict__ scratch, uint64_t per_cta_u64) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int WARPS = THREADS / 32;
+    constexpr uint32_t SCR_BYTES = WARPS * 256 * 4;  // scratch area: descriptor staging / survivor staging + bins / radix histograms
+    static_assert(sizeof(UnitStage) <= SCR_BYTES, "descriptor staging must fit the scratch area");
     uint64_t *K = reinterpret_cast<uint64_t *>(smem_raw);                      // TS keys
     uint32_t *C = reinterpret_cast<uint32_t *>(K + TS_STATIC);                 // TS counters|flags
-    uint32_t *hist = C + TS_STATIC;                                            // WARPS*256
+    uint32_t *hist = C + TS_STATIC;                                            // scratch area (SCR_BYTES)
     uint32_t *s_scan = hist + WARPS * 256;                                     // 40
     unsigned long long *s_base = reinterpret_cast<unsigned long long *>(s_scan + 40);
+    UnitStage *stage = reinterpret_cast<UnitStage *>(hist);
     const uint32_t tid = threadIdx.x;
     for (uint32_t wi = blockIdx.x; wi < n_work; wi += gridDim.x) {
         const uint32_t unit = work[wi];
-        uint32_t n = 0;
-        for (uint32_t c = 0; c < n_chunks; c++) {
+        uint32_t *s_cnt = s_scan + 36;  // [0] survivors, [1] occupied slots, [2] records of the unit
+        if (tid == 0) s_cnt[2] = 0;
+        __syncthreads();
+        for (uint32_t c = tid; c < n_chunks; c += THREADS) {  // one round of load latency whatever the chunk count
             const ChunkView &cv = chunks[c];
-            if (unit >= cv.first_unit && unit < cv.first_unit + cv.n_units) n += cv.unit_kmers[unit - cv.first_unit];
+            if (unit >= cv.first_unit && unit < cv.first_unit + cv.n_units) {
+                const uint32_t v = cv.unit_kmers[unit - cv.first_unit];
+                if (v) atomicAdd(&s_cnt[2], v);
+            }
         }
-        uint32_t TS = TS_STATIC;
+        __syncthreads();
+        const uint32_t n = s_cnt[2];
+        uint32_t TS = hash_table_slots(n);
         if (TS_STATIC == 0) {
-            TS = hash_table_slots(n);
             K = scratch + (uint64_t)blockIdx.x * per_cta_u64;
             C = reinterpret_cast<uint32_t *>(K + TS);
+        } else {
+            if (n > (uint32_t)TS_STATIC / 4 * 3) {  // host routes such units elsewhere
+                if (tid == 0) *out.overflow = 2u;
+                continue;
+            }
+            TS = min(TS, (uint32_t)TS_STATIC);
         }
         const uint32_t tmask = TS - 1;
         for (uint32_t i = tid; i < TS; i += THREADS) { K[i] = HASH_EMPTY; C[i] = 0u; }
         __syncthreads();
-        for (uint32_t c = 0; c < n_chunks; c++) {
-            const ChunkView cv = chunks[c];
-            if (unit < cv.first_unit || unit >= cv.first_unit + cv.n_units) continue;
-            const uint32_t d0 = cv.unit_off[unit - cv.first_unit], d1 = cv.unit_off[unit - cv.first_unit + 1];
-            for (uint32_t di = d0 + tid; di < d1; di += THREADS) {
-                const uint4 d = cv.desc[di];
-                expand_insert64(cv.payload + (d.x - cv.word_bias), d.y, (d.z >> 16) & 3u, P.k, P.forward_only, K, C, tmask);
-            }
-        }
+        unit_for_each_kmer64<THREADS>(chunks, n_chunks, unit, P.k, P.forward_only, stage, s_scan,
+                                      [&](uint64_t key, uint32_t fb) { hash_insert(K, C, tmask, key, fb); });
         __syncthreads();
         // ---- scan the table once: MapEntry -> multiplicity, filter; survivors are appended to a small
-        //      staging area (aliasing the radix histogram) in arbitrary order
-        constexpr uint32_t STAGE_CAP = (uint32_t)(WARPS * 256 * 4) / 12;   // entries of (u64 key|flags, u32 count|flags)
-        constexpr uint32_t RANK_MAX = 512;                                  // rank-sort threshold
+        //      staging area (in the scratch area) in arbitrary order
+        constexpr uint32_t STAGE_CAP = TS_STATIC ? (SCR_BYTES - SORT_BINS * 8) / 12 : SCR_BYTES / 12;
+        constexpr uint32_t RANK_MAX = 512;                                  // rank-sort threshold (global-table variant)
         uint64_t *stage_k = reinterpret_cast<uint64_t *>(hist);
         uint32_t *stage_c = reinterpret_cast<uint32_t *>(stage_k + STAGE_CAP);
-        uint32_t *s_cnt = s_scan + 36;  // [0] survivors, [1] occupied slots
+        uint32_t *bin_start = stage_c + STAGE_CAP;                          // [SORT_BINS]   (shared-table variant)
+        uint32_t *bin_cur = bin_start + SORT_BINS;                          // [SORT_BINS]
         if (tid < 2) s_cnt[tid] = 0;
         __syncthreads();
         {
@@ -401,7 +492,65 @@ k_merge_hash(const ChunkView *__restrict__ chunks, uint32_t n_chunks, const uint
         __syncthreads();
         const unsigned long long gbase = *s_base;
         const bool room = gbase + S <= out.capacity;
-        if (S <= RANK_MAX) {
+        // many survivors: in-place block-scan compaction of the table itself -> K[0..S), C[0..S)
+        auto compact_table = [&]() {
+            uint32_t running = 0;
+            for (uint32_t base = 0; base < TS; base += THREADS) {
+                const uint32_t i = base + tid;
+                const uint64_t kk = K[i];
+                const uint32_t cc = C[i];
+                uint32_t cf = 0, fl = 0;
+                if (kk != HASH_EMPTY) {
+                    const uint32_t cnt = cc & 0x3FFFFFFFu;
+                    fl = cc >> 30;
+                    const uint32_t mult = cnt >> ((fl == (READ_FLAG_INCL_BEGIN | READ_FLAG_INCL_END)) ? 1 : 0);
+                    if (mult >= min_mult) cf = mult | (fl << 30);
+                }
+                uint32_t tot;
+                const uint32_t p = block_exclusive_scan<THREADS>(cf ? 1u : 0u, s_scan, &tot);  // all reads precede writes
+                if (cf) { K[running + p] = (kk << 2) | fl; C[running + p] = cf; }
+                running += tot;
+            }
+            __syncthreads();
+        };
+        if (TS_STATIC != 0) {
+            // ---- bin-rank sort: scatter the survivors into SORT_BINS bins on their top key bits (counting sort),
+            //      then every survivor's position = bin start + number of smaller keys inside its bin.
+            const uint64_t *src_k; const uint32_t *src_c;
+            uint64_t *dst_k; uint32_t *dst_c;
+            if (S <= STAGE_CAP) { src_k = stage_k; src_c = stage_c; dst_k = K; dst_c = C; }
+            else { compact_table(); src_k = K; src_c = C; dst_k = K + TS / 2; dst_c = C + TS / 2; }
+            const uint32_t bshift = 2 * P.k + 2 > 9 ? 2 * P.k + 2 - 9 : 0;  // staged keys carry 2 flag bits
+            for (uint32_t i = tid; i < SORT_BINS; i += THREADS) bin_cur[i] = 0;
+            __syncthreads();
+            for (uint32_t i = tid; i < S; i += THREADS) atomicAdd(&bin_cur[(uint32_t)(src_k[i] >> bshift) & (SORT_BINS - 1)], 1u);
+            __syncthreads();
+            {
+                uint32_t v = 0;
+                if (tid < SORT_BINS) v = bin_cur[tid];
+                uint32_t tot;
+                const uint32_t p = block_exclusive_scan<THREADS>(v, s_scan, &tot);
+                if (tid < SORT_BINS) { bin_start[tid] = p; bin_cur[tid] = p; }
+            }
+            __syncthreads();
+            for (uint32_t i = tid; i < S; i += THREADS) {
+                const uint64_t r = src_k[i];
+                const uint32_t pos = atomicAdd(&bin_cur[(uint32_t)(r >> bshift) & (SORT_BINS - 1)], 1u);
+                dst_k[pos] = r; dst_c[pos] = src_c[i];
+            }
+            __syncthreads();
+            if (room) {
+                for (uint32_t i = tid; i < S; i += THREADS) {
+                    const uint64_t r = dst_k[i];
+                    const uint32_t b = (uint32_t)(r >> bshift) & (SORT_BINS - 1);
+                    const uint32_t lo = bin_start[b], hi = bin_cur[b];   // bin_cur == end of the bin after the scatter
+                    uint32_t rank = lo;
+                    for (uint32_t j = lo; j < hi; j++) rank += dst_k[j] < r ? 1u : 0u;
+                    out.keys[gbase + rank] = r >> 2;
+                    out.count_flags[gbase + rank] = dst_c[i];
+                }
+            }
+        } else if (S <= RANK_MAX) {
             // rank sort: keys are distinct, so rank = number of smaller keys is the sorted position
             if (room) {
                 for (uint32_t i = tid; i < S; i += THREADS) {
@@ -416,27 +565,7 @@ k_merge_hash(const ChunkView *__restrict__ chunks, uint32_t n_chunks, const uint
             if (S <= STAGE_CAP) {  // staging -> table memory (the table is dead now), then key-value radix sort
                 for (uint32_t i = tid; i < S; i += THREADS) { K[i] = stage_k[i]; C[i] = stage_c[i]; }
                 __syncthreads();
-            } else {
-                // many survivors: in-place block-scan compaction of the table itself
-                uint32_t running = 0;
-                for (uint32_t base = 0; base < TS; base += THREADS) {
-                    const uint32_t i = base + tid;
-                    const uint64_t kk = K[i];
-                    const uint32_t cc = C[i];
-                    uint32_t cf = 0, fl = 0;
-                    if (kk != HASH_EMPTY) {
-                        const uint32_t cnt = cc & 0x3FFFFFFFu;
-                        fl = cc >> 30;
-                        const uint32_t mult = cnt >> ((fl == (READ_FLAG_INCL_BEGIN | READ_FLAG_INCL_END)) ? 1 : 0);
-                        if (mult >= min_mult) cf = mult | (fl << 30);
-                    }
-                    uint32_t tot;
-                    const uint32_t p = block_exclusive_scan<THREADS>(cf ? 1u : 0u, s_scan, &tot);  // all reads precede writes
-                    if (cf) { K[running + p] = (kk << 2) | fl; C[running + p] = cf; }
-                    running += tot;
-                }
-                __syncthreads();
-            }
+            } else compact_table();
             uint32_t *Vs = nullptr;
             uint64_t *Ss = block_radix_sort64<THREADS, true>(K, K + TS / 2, S, 0, end_bit, hist, s_scan, C, C + TS / 2, &Vs);
             if (room) {

@@ -194,6 +194,28 @@ def test_multiple_pushes_equal_single_push():
         ctx.close()
 
 
+@pytest.mark.parametrize("k,ht", [(31, O.HASH_SEQ), (63, O.HASH_RK128)])
+def test_pipelined_host_path_small_batches(k, ht, monkeypatch):
+    """push_reads splits the host input into double-buffered H2D batches and merge_bucket_range appends parts whose
+    D2H overlaps the next merge: force many small batches / parts and require the identical table."""
+    G = _gpu()
+    monkeypatch.setenv("GGCAT_B200_HOST_BATCH", "3000")
+    monkeypatch.setenv("GGCAT_B200_PART_KMERS", "2500")
+    rng = np.random.default_rng(17 + k)
+    m, b1, b2, s = (12 if k == 31 else 14), 3, 2, 2
+    seqs = _mixed_reads(rng, k, n=500)
+    reads = O.Reads.from_list(seqs)
+    sk, _ = O.bucketing(reads, k, m, b1, b2)
+    ctx, st = G.minimizer_bucketing([(reads.data, reads.offsets)], b1, b2, k, m, min_multiplicity=s, hash_type=ht)
+    try:
+        assert ctx.n_chunks() > 4
+        assert st.n_superkmers == len(sk)
+        _check_tables(G, ctx, reads, sk, k, s, b1, b2, hash_type=ht)
+        _check_tables(G, ctx, reads, sk, k, s, b1, b2, hash_type=ht, ranges=[(2, 5)])
+    finally:
+        ctx.close()
+
+
 def test_c1_example_inputs(golden_dir):
     """BASELINE configs[0]: sal1+sal2+sal3, k=31 -s 1, 4(+1) x 64 buckets -- full parity + committed digests."""
     G = _gpu()
