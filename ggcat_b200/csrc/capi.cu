@@ -379,11 +379,6 @@ int32_t merge_range_device(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_
     CU(c->d_views.reserve(std::max<size_t>(1, views.size()) * sizeof(ChunkView)));
     if (!views.empty())
         CU(cudaMemcpyAsync(c->d_views.p, views.data(), views.size() * sizeof(ChunkView), cudaMemcpyHostToDevice, st));
-    for (int q = 0; q < 3; q++) {
-        CU(c->d_work[q].reserve(std::max<size_t>(1, work[q].size()) * 4));
-        if (!work[q].empty())
-            CU(cudaMemcpyAsync(c->d_work[q].p, work[q].data(), work[q].size() * 4, cudaMemcpyHostToDevice, st));
-    }
     // large units: biggest first (one CTA each), split in two tiers so that ordinary large units do not
     // inherit the per-CTA scratch size of a giant one
     std::sort(large.begin(), large.end(), [](const auto &a, const auto &b) { return a.first > b.first; });
@@ -391,6 +386,11 @@ int32_t merge_range_device(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_
     size_t n_giant = 0;
     while (n_giant < large.size() && large[n_giant].first > TIER) n_giant++;
     for (auto &pr : large) work[2].push_back(pr.second);
+    for (int q = 0; q < 3; q++) {
+        CU(c->d_work[q].reserve(std::max<size_t>(1, work[q].size()) * 4));
+        if (!work[q].empty())
+            CU(cudaMemcpyAsync(c->d_work[q].p, work[q].data(), work[q].size() * 4, cudaMemcpyHostToDevice, st));
+    }
     struct Tier { size_t first, count; uint64_t per_cta; unsigned grid; };
     std::vector<Tier> tiers;
     uint64_t scratch_u64 = 1;

@@ -216,6 +216,73 @@ def test_pipelined_host_path_small_batches(k, ht, monkeypatch):
         ctx.close()
 
 
+def test_several_large_units_in_one_range():
+    """More than one unit above the shared-memory capacity in the same merge call (global-scratch tables, work list
+    of large units sorted by size)."""
+    G = _gpu()
+    rng = np.random.default_rng(4242)
+    k, m, b1, b2, s = 31, 12, 1, 1, 2
+    g = util.rand_seq(rng, 120000)
+    seqs = [g, util.revcomp(g[:90000]), g[20000:], util.rand_seq(rng, 30000)]
+    reads = O.Reads.from_list(seqs)
+    sk, _ = O.bucketing(reads, k, m, b1, b2)
+    ctx, st = G.minimizer_bucketing([(reads.data, reads.offsets)], b1, b2, k, m, min_multiplicity=s)
+    try:
+        _, km = ctx.unit_sizes()
+        assert (km > 12288).sum() >= 3
+        _check_tables(G, ctx, reads, sk, k, s, b1, b2)
+    finally:
+        ctx.close()
+
+
+@pytest.mark.parametrize("k,ht", [(31, O.HASH_SEQ), (63, O.HASH_RK128)])
+def test_owner_side_import_on_one_gpu(k, ht):
+    """The multi-GPU owner path on one device: context A buckets two pushes, its per-owner chunk slices are copied
+    (as the all-to-all would deliver them) and imported into a fresh context per owner, which merges its bucket
+    range; tables must equal the oracle's."""
+    G = _gpu()
+    import torch
+
+    from ggcat_b200 import _lib, dist as gdist
+
+    rng = np.random.default_rng(k)
+    m, b1, b2, s = (12 if k == 31 else 14), 3, 2, 2
+    seqs = _mixed_reads(rng, k, n=600) + [util.rand_seq(rng, 50000)]
+    reads = O.Reads.from_list(seqs)
+    sk, _ = O.bucketing(reads, k, m, b1, b2)
+    half = len(seqs) // 2
+    r1, r2 = O.Reads.from_list(seqs[:half]), O.Reads.from_list(seqs[half:])
+    A, _ = G.minimizer_bucketing([(r1.data, r1.offsets), (r2.data, r2.offsets)], b1, b2, k, m, min_multiplicity=s, hash_type=ht)
+    dev = torch.device("cuda", 0)
+    world = 3
+    owner = gdist.OwnerMap(b1, b2, world)
+    try:
+        for rank in range(world):
+            B = G.GGCATB200(G.Params(k=k, m=m, min_multiplicity=s, buckets_count_log=b1, second_buckets_count_log=b2, hash_type=ht))
+            try:
+                fu, nu = owner.unit_range(rank)
+                for c in range(A.n_chunks()):
+                    sl = A.export_chunk_slice(c, fu, nu)
+                    desc = gdist._view(sl.d_descriptors, int(sl.n_superkmers) * 16, torch.uint8, dev).clone()
+                    pay = torch.zeros(int(sl.n_words) + 8, dtype=torch.int32, device=dev)
+                    pay[: int(sl.n_words)] = gdist._view(sl.d_payload, int(sl.n_words), torch.int32, dev)
+                    uc = gdist._view(sl.d_unit_counts, nu, torch.int32, dev).clone()
+                    uw = gdist._view(sl.d_unit_words, nu, torch.int32, dev).clone()
+                    uk = gdist._view(sl.d_unit_kmers, nu, torch.int32, dev).clone()
+                    torch.cuda.synchronize()
+                    s2 = _lib.ChunkSliceC(n_superkmers=sl.n_superkmers, n_words=sl.n_words, word_bias=sl.word_bias,
+                                          d_descriptors=desc.data_ptr(), d_payload=pay.data_ptr(), d_unit_counts=uc.data_ptr(),
+                                          d_unit_words=uw.data_ptr(), d_unit_kmers=uk.data_ptr())
+                    B.import_chunk_slice(fu, nu, s2, keepalive=(desc, pay, uc, uw, uk))
+                B.finish_bucketing()
+                fb, nb = owner.bucket_range(rank)
+                _check_tables(G, B, reads, sk, k, s, b1, b2, ranges=[(fb, nb)], hash_type=ht)
+            finally:
+                B.close()
+    finally:
+        A.close()
+
+
 def test_c1_example_inputs(golden_dir):
     """BASELINE configs[0]: sal1+sal2+sal3, k=31 -s 1, 4(+1) x 64 buckets -- full parity + committed digests."""
     G = _gpu()
