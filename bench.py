@@ -120,7 +120,7 @@ def run_reference(args):
     sample_reads = args.sample_reads
     cores = os.cpu_count() or 1
     data, offsets = make_reads(0, max(args.gpus, 1), sample_reads)
-    b1, b2 = O.bucket_counts(int(READS_PER_GPU * (READ_LEN + 15)))  # same bucket counts as the full workload
+    b1, b2 = O.bucket_counts(int(READS_PER_GPU * max(args.gpus, 1) * (READ_LEN + 15)))  # same bucket counts as the full workload
     reads = O.Reads(data, offsets)
     times = []
     st = None
@@ -172,7 +172,11 @@ def run_ours(args):
     n_reads = args.reads_per_gpu
     data, offsets = make_reads(rank, world, n_reads)
     n_bases = int(data.size)
-    b1, b2 = G.bucket_counts(int(READS_PER_GPU * (READ_LEN + 15)))  # the FASTA size the reference would see per GPU slice
+    # bucket counts as the reference derives them from the size of the WHOLE input (all ranks' FASTA bytes,
+    # crates/io/src/lib.rs:67-140)
+    b1, b2 = G.bucket_counts(int(n_reads * world * (READ_LEN + 15)))
+    if args.b1 is not None:
+        b1 = args.b1
     nb = (1 << b1) + 1
     ctx = G.GGCATB200(G.Params(k=K, m=M, min_multiplicity=S, buckets_count_log=b1, second_buckets_count_log=b2,
                                device=local_rank))
@@ -352,6 +356,7 @@ def main():
     ap.add_argument("--reads-per-gpu", type=int, default=READS_PER_GPU)
     ap.add_argument("--sample-reads", type=int, default=200_000, help="bounded CPU sample (reads)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--b1", type=int, default=None, help="experiment: override buckets_count_log")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

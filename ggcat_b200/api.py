@@ -272,7 +272,7 @@ class GGCATB200:
         _check(self._lib.ggcat_b200_set_timing(self._h, int(on)))
 
     def kernel_times(self, reset: bool = True) -> dict:
-        cap = 16
+        cap = 32
         names = (C.c_char_p * cap)()
         ms = (C.c_float * cap)()
         ln = (C.c_uint32 * cap)()

@@ -72,11 +72,11 @@ struct Chunk {
 };
 
 enum Family { F_PACK = 0, F_WINDOWS, F_EMIT, F_SCATTER, F_SCAN, F_MERGE_HASH, F_MERGE_HASH_GLOBAL, F_MERGE_SMEM, F_MERGE_GLOBAL,
-              F_GATHER, F_MERGE_HASH128, F_SORT128, F_COLOR_FOLD, F_COUNT };
+              F_GATHER, F_MERGE_HASH128, F_SORT128, F_COLOR_FOLD, F_PARTITION, F_MERGE_HASH_PART, F_COUNT };
 static const char *kFamilyNames[F_COUNT] = {"k_pack+k_mark", "k_windows", "k_emit", "k_scatter", "k_exclusive_scan_u32",
                                             "k_merge_hash<smem>", "k_merge_hash<global>", "k_merge_units<smem>",
                                             "k_merge_units<global>", "k_gather_units", "k_merge_hash128", "k_sort_units128",
-                                            "k_color_fold"};
+                                            "k_color_fold", "k_partition_units", "k_merge_hash<partitions>"};
 
 struct TimedLaunch { int fam; cudaEvent_t a, b; };
 
@@ -117,6 +117,7 @@ struct ggcat_b200_ctx {
     bool finished = false;
     bool timing = false;
     int merge_mode = 1;  // 1 = shared-memory hash table (default), 0 = LSD radix sort (GGCAT_B200_MERGE=sort)
+    bool no_partition = false;  // GGCAT_B200_NO_PARTITION=1: big units use the global-scratch table (A/B switch)
     int wide_mode = -1;  // -1: 64-bit key path (merge.cuh); else MODE_SEQ128 / MODE_RK128 / MODE_COLOR (merge128.cuh)
     RkTables rk;
     FinalTable fin;
@@ -127,7 +128,7 @@ struct ggcat_b200_ctx {
     std::vector<Chunk *> chunk_pool;  // recycled local chunks (device buffers kept)
     // phase-2 workspace
     DevBuf d_views, d_work[3], d_scratch, out_keys, out_cf, out_keys2, out_cf2, cursor, unit_out_off,
-        unit_out_cnt, unit_final_off, overflow, d_retry, out_hi, out_hi2, unit_keys, unit_cols, col_off, out_coloff, out_colors;
+        unit_out_cnt, unit_final_off, overflow, d_retry, d_partmeta, d_recs, fin_tmp_keys, fin_tmp_cf, out_hi, out_hi2, unit_keys, unit_cols, col_off, out_coloff, out_colors;
     unsigned long long *h_pinned = nullptr;  // small pinned staging (16 u64)
     std::vector<TimedLaunch> launches;
     std::vector<cudaEvent_t> event_pool;
@@ -302,20 +303,6 @@ int32_t mirror_chunk(ggcat_b200_ctx *c, Chunk *ch) {
     return 0;
 }
 
-__global__ void k_gather_units(const uint64_t *__restrict__ src_keys, const uint32_t *__restrict__ src_cf,
-                               const uint64_t *__restrict__ src_off, const uint32_t *__restrict__ cnt,
-                               const uint64_t *__restrict__ dst_off, uint64_t *__restrict__ dst_keys,
-                               uint32_t *__restrict__ dst_cf, uint32_t n_units) {
-    for (uint32_t u = blockIdx.x; u < n_units; u += gridDim.x) {
-        const uint32_t n = cnt[u];
-        const uint64_t s = src_off[u], d = dst_off[u];
-        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
-            dst_keys[d + i] = src_keys[s + i];
-            dst_cf[d + i] = src_cf[s + i];
-        }
-    }
-}
-
 // exclusive scan u32 counts -> u64 offsets (n_units small: single CTA, sequential per thread chunks)
 __global__ void __launch_bounds__(1024) k_scan_counts_u64(const uint32_t *cnt, uint64_t *off, uint32_t n, uint64_t base = 0) {
     __shared__ uint32_t s_scan[1024 / 32 + 2];
@@ -343,6 +330,10 @@ struct PartBase { uint64_t eb = 0; uint32_t ub = 0; uint64_t cap_total = 0; };
 int32_t merge_range_device_wide(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_buckets, uint64_t *n_entries,
                                 uint64_t *unique, uint64_t *total, PartBase pb);
 
+constexpr uint32_t PART_CAP = 6144;       // records a key partition may hold (= capacity of the 8192-slot shared table)
+constexpr uint32_t PART_TARGET = 4096;    // partitions per big unit = pow2 >= records / PART_TARGET
+constexpr int FIN_THREADS = 512, FIN_SCAP = 3072;
+
 int32_t merge_range_device(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_buckets, uint64_t *n_entries,
                            uint64_t *unique, uint64_t *total, PartBase pb = PartBase()) {
     const DevParams &P = c->P;
@@ -353,22 +344,65 @@ int32_t merge_range_device(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_
         return set_err(GGCAT_B200_ERR_INVALID, "bucket range [%u,+%u) outside 0..%u", first_bucket, n_buckets, nb_total);
     if (c->wide_mode >= 0) return merge_range_device_wide(c, first_bucket, n_buckets, n_entries, unique, total, pb);
     const uint32_t u0 = first_bucket << P.b2, nu = n_buckets << P.b2;
-    // classify units by record count
+    const bool hash_mode = c->merge_mode == 1;
+    // ---- classify units by record count
+    //   work[0]  <= 6144 records : 512-thread CTA, shared table          work[1]  <= 12288 : 1024-thread CTA
+    //   big      <= PART_MAXP * PART_TARGET : key partitions in HBM, one shared-table CTA per partition
+    //   work[2]  giant units (and every large unit in sort mode) : table / sort buffers in a global scratch slice
     std::vector<uint32_t> work[3];
-    std::vector<std::pair<uint64_t, uint32_t>> large;  // (records, unit)
+    std::vector<std::pair<uint64_t, uint32_t>> large, big;  // (records, unit)
+    std::vector<uint64_t> unit_n(nu, 0);
     uint64_t tot_kmers = 0;
     for (uint32_t u = u0; u < u0 + nu; u++) {
         uint64_t n = 0;
         for (Chunk *ch : c->chunks)
             if (u >= ch->first_unit && u < ch->first_unit + ch->n_units) n += ch->h_kmers[u - ch->first_unit];
+        unit_n[u - u0] = n;
         if (n == 0) continue;
         if (n >= (1ull << 31)) return set_err(GGCAT_B200_ERR_INVALID, "unit %u holds %llu k-mers (> 2^31)", u, (unsigned long long)n);
         tot_kmers += n;
         if (n <= SM_CAP_S) work[0].push_back(u);
         else if (n <= SM_CAP_L) work[1].push_back(u);
+        else if (hash_mode && n <= (uint64_t)PART_MAXP * PART_TARGET && !c->no_partition) big.push_back({n, u});
         else large.push_back({n, u});
     }
-    // chunk views
+    // ---- key partitions of big units and the output-slot map
+    std::sort(big.begin(), big.end(), [](const auto &a, const auto &b) { return a.first > b.first; });
+    std::vector<uint32_t> big_unit, big_logp, big_pbase, part_slot, part_big, slot_of_unit;
+    uint32_t n_parts = 0, n_slots = nu;
+    if (!big.empty()) {
+        std::vector<uint32_t> logp_of(nu, 0);
+        for (auto &pr : big) {
+            uint32_t lp = 2;
+            while (((uint64_t)PART_TARGET << lp) < pr.first) lp++;
+            logp_of[pr.second - u0] = lp;
+        }
+        slot_of_unit.resize(nu + 1);
+        uint32_t sl = 0;
+        for (uint32_t i = 0; i < nu; i++) { slot_of_unit[i] = sl; sl += 1u << logp_of[i]; }
+        slot_of_unit[nu] = sl; n_slots = sl;
+        for (auto &pr : big) {
+            const uint32_t lp = logp_of[pr.second - u0];
+            big_unit.push_back(pr.second); big_logp.push_back(lp); big_pbase.push_back(n_parts);
+            for (uint32_t q = 0; q < (1u << lp); q++) { part_slot.push_back(slot_of_unit[pr.second - u0] + q); part_big.push_back((uint32_t)big_unit.size() - 1); }
+            n_parts += 1u << lp;
+        }
+    }
+    // ---- giant / sort-mode large units: biggest first (one CTA each), two tiers so that ordinary large units do not
+    //      inherit the per-CTA scratch size of a giant one
+    std::sort(large.begin(), large.end(), [](const auto &a, const auto &b) { return a.first > b.first; });
+    const uint64_t TIER = 1ull << 20;
+    size_t n_giant = 0;
+    while (n_giant < large.size() && large[n_giant].first > TIER) n_giant++;
+    for (auto &pr : large) work[2].push_back(pr.second);
+    struct Tier { const uint32_t *wl; size_t count; const uint32_t *count_dev; uint64_t per_cta; unsigned grid; };
+    auto make_tier = [&](const uint32_t *wl, size_t count, const uint32_t *count_dev, uint64_t nmax) {
+        const uint64_t per_cta = (uint64_t)hash_table_slots((uint32_t)nmax) * 3 / 2 + 16;  // keys + counters; >= 2n for the sort variant
+        const uint64_t budget = 12ull << 30;
+        const uint64_t g = std::min<uint64_t>(std::min<uint64_t>(count, (uint64_t)c->sm_count * 2), std::max<uint64_t>(1, budget / (per_cta * 8)));
+        return Tier{wl, count, count_dev, per_cta, (unsigned)g};
+    };
+    // ---- uploads
     std::vector<ChunkView> views;
     for (Chunk *ch : c->chunks) {
         ChunkView v;
@@ -379,61 +413,71 @@ int32_t merge_range_device(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_
     CU(c->d_views.reserve(std::max<size_t>(1, views.size()) * sizeof(ChunkView)));
     if (!views.empty())
         CU(cudaMemcpyAsync(c->d_views.p, views.data(), views.size() * sizeof(ChunkView), cudaMemcpyHostToDevice, st));
-    // large units: biggest first (one CTA each), split in two tiers so that ordinary large units do not
-    // inherit the per-CTA scratch size of a giant one
-    std::sort(large.begin(), large.end(), [](const auto &a, const auto &b) { return a.first > b.first; });
-    const uint64_t TIER = 1ull << 20;
-    size_t n_giant = 0;
-    while (n_giant < large.size() && large[n_giant].first > TIER) n_giant++;
-    for (auto &pr : large) work[2].push_back(pr.second);
     for (int q = 0; q < 3; q++) {
         CU(c->d_work[q].reserve(std::max<size_t>(1, work[q].size()) * 4));
         if (!work[q].empty())
             CU(cudaMemcpyAsync(c->d_work[q].p, work[q].data(), work[q].size() * 4, cudaMemcpyHostToDevice, st));
     }
-    struct Tier { size_t first, count; uint64_t per_cta; unsigned grid; };
+    uint32_t *d_big_unit = nullptr, *d_big_logp = nullptr, *d_big_pbase = nullptr, *d_big_ovf = nullptr, *d_part_slot = nullptr,
+             *d_part_big = nullptr, *d_pcount = nullptr, *d_slot_of_unit = nullptr;
+    if (!big.empty()) {
+        const size_t nbig = big.size();
+        // one metadata buffer: big_unit | big_logp | big_pbase | big_ovf | part_slot | part_big | pcount | slot_of_unit
+        const size_t words = 4 * nbig + 3 * (size_t)n_parts + nu + 1;
+        CU(c->d_partmeta.reserve(words * 4));
+        uint32_t *base = c->d_partmeta.as<uint32_t>();
+        d_big_unit = base; d_big_logp = base + nbig; d_big_pbase = base + 2 * nbig; d_big_ovf = base + 3 * nbig;
+        d_part_slot = base + 4 * nbig; d_part_big = d_part_slot + n_parts; d_pcount = d_part_big + n_parts;
+        d_slot_of_unit = d_pcount + n_parts;
+        CU(cudaMemcpyAsync(d_big_unit, big_unit.data(), nbig * 4, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(d_big_logp, big_logp.data(), nbig * 4, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(d_big_pbase, big_pbase.data(), nbig * 4, cudaMemcpyHostToDevice, st));
+        CU(cudaMemsetAsync(d_big_ovf, 0, nbig * 4, st));
+        CU(cudaMemcpyAsync(d_part_slot, part_slot.data(), (size_t)n_parts * 4, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(d_part_big, part_big.data(), (size_t)n_parts * 4, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(d_slot_of_unit, slot_of_unit.data(), ((size_t)nu + 1) * 4, cudaMemcpyHostToDevice, st));
+        CU(c->d_recs.reserve((size_t)n_parts * PART_CAP * 8));
+    }
     std::vector<Tier> tiers;
     uint64_t scratch_u64 = 1;
-    for (int t = 0; t < 2; t++) {
-        const size_t first = t == 0 ? 0 : n_giant, count = t == 0 ? n_giant : large.size() - n_giant;
-        if (!count) continue;
-        const uint64_t nmax = large[first].first;
-        const uint64_t per_cta = (uint64_t)hash_table_slots((uint32_t)nmax) * 3 / 2 + 16;  // keys + counters; >= 2n for the sort variant
-        const uint64_t budget = 12ull << 30;
-        uint64_t g = std::min<uint64_t>(std::min<uint64_t>(count, (uint64_t)c->sm_count * 2), std::max<uint64_t>(1, budget / (per_cta * 8)));
-        tiers.push_back({first, count, per_cta, (unsigned)g});
-        scratch_u64 = std::max(scratch_u64, per_cta * g);
-    }
-    CU(c->d_scratch.reserve(scratch_u64 * 8));
+    if (n_giant) tiers.push_back(make_tier(c->d_work[2].as<uint32_t>(), n_giant, nullptr, large[0].first));
+    if (large.size() > n_giant) tiers.push_back(make_tier(c->d_work[2].as<uint32_t>() + n_giant, large.size() - n_giant, nullptr, large[n_giant].first));
     const uint64_t cap = std::max<uint64_t>(tot_kmers, 1);
     CU(c->out_keys.reserve(cap * 8)); CU(c->out_cf.reserve(cap * 4));
     CU(c->cursor.reserve(64)); CU(c->overflow.reserve(16));
-    CU(c->d_retry.reserve(((size_t)nu + 2) * 4 * 2));  // two lists: [0] = count, [1..] = unit ids
+    CU(c->d_retry.reserve(((size_t)nu + 2) * 4 * 3));  // three lists: [0] = count, [1..] = unit ids
     uint32_t *retry_cnt = c->d_retry.as<uint32_t>(), *retry = retry_cnt + 1;
     uint32_t *retry2_cnt = retry_cnt + nu + 2, *retry2 = retry2_cnt + 1;
+    uint32_t *retry3_cnt = retry2_cnt + nu + 2, *retry3 = retry3_cnt + 1;   // big units with an overflowed partition
+    if (!big.empty()) tiers.push_back(make_tier(retry3, big.size(), retry3_cnt, big[0].first));
+    for (const Tier &tr : tiers) scratch_u64 = std::max(scratch_u64, tr.per_cta * tr.grid);
+    CU(c->d_scratch.reserve(scratch_u64 * 8));
     CU(cudaMemsetAsync(retry_cnt, 0, 4, st));
     CU(cudaMemsetAsync(retry2_cnt, 0, 4, st));
-    CU(c->unit_out_off.reserve(((size_t)nu + 1) * 8)); CU(c->unit_out_cnt.reserve(((size_t)nu + 1) * 4));
+    CU(cudaMemsetAsync(retry3_cnt, 0, 4, st));
+    CU(c->unit_out_off.reserve(((size_t)n_slots + 1) * 8)); CU(c->unit_out_cnt.reserve(((size_t)n_slots + 1) * 4));
     if (pb.ub == 0) CU(c->unit_final_off.reserve(((size_t)c->P.n_units + 2) * 8));
     CU(cudaMemsetAsync(c->cursor.p, 0, 64, st));
     CU(cudaMemsetAsync(c->overflow.p, 0, 16, st));
-    CU(cudaMemsetAsync(c->unit_out_off.p, 0, ((size_t)nu + 1) * 8, st));
-    CU(cudaMemsetAsync(c->unit_out_cnt.p, 0, ((size_t)nu + 1) * 4, st));
+    CU(cudaMemsetAsync(c->unit_out_off.p, 0, ((size_t)n_slots + 1) * 8, st));
+    CU(cudaMemsetAsync(c->unit_out_cnt.p, 0, ((size_t)n_slots + 1) * 4, st));
     MergeOut out;
     out.keys = c->out_keys.as<uint64_t>(); out.count_flags = c->out_cf.as<uint32_t>();
     out.cursor = c->cursor.as<unsigned long long>(); out.unit_out_off = c->unit_out_off.as<uint64_t>();
     out.unit_out_cnt = c->unit_out_cnt.as<uint32_t>(); out.capacity = cap; out.overflow = c->overflow.as<uint32_t>();
+    out.slot_of_unit = d_slot_of_unit;
     const ChunkView *dv = c->d_views.as<ChunkView>();
     const uint32_t nch = (uint32_t)views.size();
-    if (c->merge_mode == 1) {
+    const uint32_t ms = c->params.min_multiplicity;
+    if (hash_mode) {
         if (!work[0].empty()) {
             LaunchTimer t(c, F_MERGE_HASH);
             auto kern = k_merge_hash<SM_THREADS_S, HASH_TS_S>;
             const size_t smem = merge_hash_smem_bytes<SM_THREADS_S, HASH_TS_S>();
             CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             const unsigned grid = (unsigned)std::min<size_t>(work[0].size(), (size_t)c->sm_count * 2 * 8);
-            kern<<<grid, SM_THREADS_S, smem, st>>>(dv, nch, c->d_work[0].as<uint32_t>(), (uint32_t)work[0].size(), u0, P,
-                                                   c->params.min_multiplicity, out, retry, retry_cnt, nullptr, 0);
+            kern<<<grid, SM_THREADS_S, smem, st>>>(dv, nch, c->d_work[0].as<uint32_t>(), (uint32_t)work[0].size(), u0, P, ms, out,
+                                                   retry, retry_cnt, nullptr, 0, PartSrc(), nullptr);
         }
         if (!work[1].empty()) {
             LaunchTimer t(c, F_MERGE_HASH);
@@ -441,8 +485,8 @@ int32_t merge_range_device(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_
             const size_t smem = merge_hash_smem_bytes<SM_THREADS_L, HASH_TS_L>();
             CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             const unsigned grid = (unsigned)std::min<size_t>(work[1].size(), (size_t)c->sm_count * 8);
-            kern<<<grid, SM_THREADS_L, smem, st>>>(dv, nch, c->d_work[1].as<uint32_t>(), (uint32_t)work[1].size(), u0, P,
-                                                   c->params.min_multiplicity, out, retry, retry_cnt, nullptr, 0);
+            kern<<<grid, SM_THREADS_L, smem, st>>>(dv, nch, c->d_work[1].as<uint32_t>(), (uint32_t)work[1].size(), u0, P, ms, out,
+                                                   retry, retry_cnt, nullptr, 0, PartSrc(), nullptr);
         }
         if (!work[0].empty() || !work[1].empty()) {
             // units whose survivors did not leave room for the in-table sort: redo with the sort kernel
@@ -450,8 +494,26 @@ int32_t merge_range_device(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_
             auto kern = k_merge_units<SM_THREADS_L, SM_CAP_L, false>;
             const size_t smem = merge_smem_bytes<SM_THREADS_L, SM_CAP_L>(false);
             CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            kern<<<(unsigned)c->sm_count, SM_THREADS_L, smem, st>>>(dv, nch, retry, 0u, u0, P, c->params.min_multiplicity, out,
-                                                                    nullptr, 0, retry_cnt);
+            kern<<<(unsigned)c->sm_count, SM_THREADS_L, smem, st>>>(dv, nch, retry, 0u, u0, P, ms, out, nullptr, 0, retry_cnt);
+        }
+        if (!big.empty()) {
+            {
+                LaunchTimer t(c, F_PARTITION);
+                const unsigned grid = (unsigned)std::min<size_t>(big.size(), (size_t)c->sm_count * 2);
+                k_partition_units<1024><<<grid, 1024, 0, st>>>(dv, nch, d_big_unit, d_big_logp, d_big_pbase, (uint32_t)big.size(), P,
+                                                               c->d_recs.as<uint64_t>(), d_pcount, PART_CAP, d_big_ovf, retry3, retry3_cnt);
+            }
+            {
+                LaunchTimer t(c, F_MERGE_HASH_PART);
+                PartSrc ps;
+                ps.recs = c->d_recs.as<uint64_t>(); ps.pcount = d_pcount; ps.part_slot = d_part_slot; ps.part_big = d_part_big;
+                ps.big_ovf = d_big_ovf; ps.pcap = PART_CAP; ps.pad = 0;
+                auto kern = k_merge_hash<SM_THREADS_S, HASH_TS_S, SRC_RECORDS>;
+                const size_t smem = merge_hash_smem_bytes<SM_THREADS_S, HASH_TS_S>();
+                CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                const unsigned grid = (unsigned)std::min<size_t>(n_parts, (size_t)c->sm_count * 2 * 8);
+                kern<<<grid, SM_THREADS_S, smem, st>>>(dv, nch, nullptr, n_parts, u0, P, ms, out, nullptr, nullptr, nullptr, 0, ps, nullptr);
+            }
         }
         work[0].clear(); work[1].clear();
     }
@@ -461,8 +523,7 @@ int32_t merge_range_device(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_
         const size_t smem = merge_smem_bytes<SM_THREADS_S, SM_CAP_S>(false);
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const unsigned grid = (unsigned)std::min<size_t>(work[0].size(), (size_t)c->sm_count * 2 * 8);
-        kern<<<grid, SM_THREADS_S, smem, st>>>(dv, nch, c->d_work[0].as<uint32_t>(), (uint32_t)work[0].size(), u0, P,
-                                               c->params.min_multiplicity, out, nullptr, 0, nullptr);
+        kern<<<grid, SM_THREADS_S, smem, st>>>(dv, nch, c->d_work[0].as<uint32_t>(), (uint32_t)work[0].size(), u0, P, ms, out, nullptr, 0, nullptr);
     }
     if (!work[1].empty()) {
         LaunchTimer t(c, F_MERGE_SMEM);
@@ -470,46 +531,50 @@ int32_t merge_range_device(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_
         const size_t smem = merge_smem_bytes<SM_THREADS_L, SM_CAP_L>(false);
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const unsigned grid = (unsigned)std::min<size_t>(work[1].size(), (size_t)c->sm_count * 8);
-        kern<<<grid, SM_THREADS_L, smem, st>>>(dv, nch, c->d_work[1].as<uint32_t>(), (uint32_t)work[1].size(), u0, P,
-                                               c->params.min_multiplicity, out, nullptr, 0, nullptr);
+        kern<<<grid, SM_THREADS_L, smem, st>>>(dv, nch, c->d_work[1].as<uint32_t>(), (uint32_t)work[1].size(), u0, P, ms, out, nullptr, 0, nullptr);
     }
     for (const Tier &tr : tiers) {
-        const uint32_t *wl = c->d_work[2].as<uint32_t>() + tr.first;
         auto sortk = k_merge_units<GL_THREADS, 0, true>;
         const size_t smem_sort = merge_smem_bytes<GL_THREADS, 0>(true);
-        if (c->merge_mode == 1) {
+        if (hash_mode) {
             {
                 LaunchTimer t(c, F_MERGE_HASH_GLOBAL);
                 auto kern = k_merge_hash<GL_THREADS, 0>;
                 kern<<<tr.grid, GL_THREADS, merge_hash_smem_bytes<GL_THREADS, 0>(), st>>>(
-                    dv, nch, wl, (uint32_t)tr.count, u0, P, c->params.min_multiplicity, out, retry2, retry2_cnt,
-                    c->d_scratch.as<uint64_t>(), tr.per_cta);
+                    dv, nch, tr.wl, (uint32_t)tr.count, u0, P, ms, out, retry2, retry2_cnt, c->d_scratch.as<uint64_t>(), tr.per_cta,
+                    PartSrc(), tr.count_dev);
             }
             {   // survivors > half the table: redo those units with the global-scratch sort
                 LaunchTimer t(c, F_MERGE_GLOBAL);
-                sortk<<<tr.grid, GL_THREADS, smem_sort, st>>>(dv, nch, retry2, 0u, u0, P, c->params.min_multiplicity, out,
-                                                             c->d_scratch.as<uint64_t>(), tr.per_cta, retry2_cnt);
+                sortk<<<tr.grid, GL_THREADS, smem_sort, st>>>(dv, nch, retry2, 0u, u0, P, ms, out, c->d_scratch.as<uint64_t>(),
+                                                             tr.per_cta, retry2_cnt);
             }
             CU(cudaMemsetAsync(retry2_cnt, 0, 4, st));
         } else {
             LaunchTimer t(c, F_MERGE_GLOBAL);
-            sortk<<<tr.grid, GL_THREADS, smem_sort, st>>>(dv, nch, wl, (uint32_t)tr.count, u0, P, c->params.min_multiplicity, out,
-                                                         c->d_scratch.as<uint64_t>(), tr.per_cta, nullptr);
+            sortk<<<tr.grid, GL_THREADS, smem_sort, st>>>(dv, nch, tr.wl, (uint32_t)tr.count, u0, P, ms, out, c->d_scratch.as<uint64_t>(),
+                                                         tr.per_cta, nullptr);
         }
     }
     CU(cudaGetLastError());
-    // unit-ordered final layout (parts append at entry pb.eb / unit pb.ub)
+    // ---- unit-ordered final layout (parts append at entry pb.eb / unit pb.ub)
     if (pb.ub == 0) {
         const uint64_t fc = std::max(cap, pb.cap_total);
         CU(c->out_keys2.reserve(fc * 8)); CU(c->out_cf2.reserve(fc * 4));
     }
+    if (!big.empty()) { CU(c->fin_tmp_keys.reserve(c->out_keys2.cap)); CU(c->fin_tmp_cf.reserve(c->out_cf2.cap)); }
     {
         LaunchTimer t(c, F_GATHER, 2);
-        k_scan_counts_u64<<<1, 1024, 0, st>>>(c->unit_out_cnt.as<uint32_t>(), c->unit_final_off.as<uint64_t>() + pb.ub, nu, pb.eb);
-        k_gather_units<<<(unsigned)std::min<uint32_t>(nu, (uint32_t)c->sm_count * 8), 128, 0, st>>>(
-            c->out_keys.as<uint64_t>(), c->out_cf.as<uint32_t>(), c->unit_out_off.as<uint64_t>(),
-            c->unit_out_cnt.as<uint32_t>(), c->unit_final_off.as<uint64_t>() + pb.ub, c->out_keys2.as<uint64_t>(),
-            c->out_cf2.as<uint32_t>(), nu);
+        uint64_t *foff = c->unit_final_off.as<uint64_t>() + pb.ub;
+        k_scan_unit_slots<<<1, 1024, 0, st>>>(c->unit_out_cnt.as<uint32_t>(), d_slot_of_unit, foff, nu, pb.eb);
+        auto kern = k_finish_units<FIN_THREADS, FIN_SCAP>;
+        const size_t smem = finish_units_smem_bytes<FIN_THREADS, FIN_SCAP>();
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const uint32_t end_bit = std::min(64u, (2 * P.k + 7) & ~7u);
+        kern<<<(unsigned)std::min<uint32_t>(nu, (uint32_t)c->sm_count * 2 * 8), FIN_THREADS, smem, st>>>(
+            c->out_keys.as<uint64_t>(), c->out_cf.as<uint32_t>(), c->unit_out_off.as<uint64_t>(), c->unit_out_cnt.as<uint32_t>(),
+            d_slot_of_unit, foff, c->out_keys2.as<uint64_t>(), c->out_cf2.as<uint32_t>(), c->fin_tmp_keys.as<uint64_t>(),
+            c->fin_tmp_cf.as<uint32_t>(), nu, end_bit);
     }
     CU(cudaMemcpyAsync(c->h_pinned, c->cursor.p, 24, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(c->h_pinned + 8, c->overflow.p, 4, cudaMemcpyDeviceToHost, st));
@@ -779,6 +844,7 @@ int32_t ggcat_b200_create(const ggcat_b200_params *params, ggcat_b200_ctx **out)
             c->rk.fwd_mk[b] = to_k128(L[b] * mk1 * M); c->rk.bkw_mk1[b] = to_k128(L[b ^ 2] * mk1);
         }
     }
+    if (const char *np = getenv("GGCAT_B200_NO_PARTITION")) c->no_partition = atoi(np) != 0;
     if (const char *mm = getenv("GGCAT_B200_MERGE")) c->merge_mode = (strcmp(mm, "sort") == 0) ? 0 : 1;
     if (const char *mb = getenv("GGCAT_B200_MAX_BATCH")) { uint64_t v = strtoull(mb, nullptr, 10); if (v >= 1024) c->max_batch = std::min<uint64_t>(v, 1ull << 30); }
     cudaDeviceProp prop;
@@ -824,6 +890,7 @@ void ggcat_b200_destroy(ggcat_b200_ctx *c) {
                       &c->tmp, &c->tmp_color, &c->cur_cnt, &c->cur_words, &c->totals, &c->d_views, &c->d_work[0], &c->d_work[1],
                       &c->d_work[2], &c->d_scratch, &c->out_keys, &c->out_cf, &c->out_keys2, &c->out_cf2,
                       &c->cursor, &c->unit_out_off, &c->unit_out_cnt, &c->unit_final_off, &c->overflow, &c->d_retry,
+                      &c->d_partmeta, &c->d_recs, &c->fin_tmp_keys, &c->fin_tmp_cf,
                       &c->out_hi, &c->out_hi2, &c->unit_keys, &c->unit_cols, &c->col_off, &c->out_coloff, &c->out_colors})
         b->release();
     for (cudaEvent_t e : c->event_pool) cudaEventDestroy(e);

@@ -36,7 +36,29 @@ struct MergeOut {
     uint32_t *unit_out_cnt;             //                                                   count
     uint64_t capacity;                  // entries available in keys/count_flags
     uint32_t *overflow;                 // set to 1 if capacity was exceeded
+    const uint32_t *slot_of_unit;       // output slot of a unit (big units own several slots, one per key partition);
+                                        // NULL: slot = unit index relative to the first unit of the launch
+    __device__ __forceinline__ uint32_t slot(uint32_t unit_rel) const { return slot_of_unit ? slot_of_unit[unit_rel] : unit_rel; }
 };
+
+// Key partitions of big units (units that do not fit a shared-memory table): k_partition_units expands the unit once
+// and routes every k-mer record by a hash of its key into one of P partitions in HBM (all occurrences of a k-mer
+// land in the same partition, so partitions are counted independently, no fold); k_merge_hash<.., SRC_RECORDS>
+// counts one partition per CTA in shared memory; k_finish_units orders the unit's survivors.
+struct PartSrc {
+    const uint64_t *recs;        // [n_parts_total][pcap] records (key << 2 | flag bits)
+    const uint32_t *pcount;      // [n_parts_total] records per partition
+    const uint32_t *part_slot;   // work item -> output slot
+    const uint32_t *part_big;    // work item -> index of its big unit
+    const uint32_t *big_ovf;     // [n_big] 1 = a partition overflowed, the unit is redone by the global-table kernel
+    uint32_t pcap;
+    uint32_t pad;
+};
+enum { SRC_SUPERKMERS = 0, SRC_RECORDS = 1 };
+
+__device__ __forceinline__ uint32_t part_hash(uint64_t key) {   // independent of the in-table slot hash
+    return (uint32_t)((key * 0xD6E8FEB86659FD93ull) >> 40);
+}
 
 // ------------------------------------------------------------------------------------------------
 // Expansion of one super-k-mer into records (k <= 31: 62-bit key + 2 flag bits in one u64).
@@ -255,7 +277,7 @@ k_merge_units(const ChunkView *__restrict__ chunks, uint32_t n_chunks, const uin
         uint64_t *S = block_radix_sort64<THREADS>(A, B, n, 0, end_bit, hist, s_scan);
         uint64_t *other = (S == A) ? B : A;
         // ---- reduce + filter
-        block_reduce_filter<THREADS>(S, reinterpret_cast<uint32_t *>(other), n, min_mult, out, unit - first_unit, s_scan,
+        block_reduce_filter<THREADS>(S, reinterpret_cast<uint32_t *>(other), n, min_mult, out, out.slot(unit - first_unit), s_scan,
                                      s_base);
         __syncthreads();
     }
@@ -397,11 +419,12 @@ constexpr uint32_t SORT_BINS = 512;  // bin-rank sort: bins on the top 9 key bit
 // ordered by a bin-rank sort.  TS_STATIC == 0: table in this CTA's slice of a global scratch buffer (L2-resident
 // for typical units); survivors ordered by the LSD radix sort.  Units whose survivors leave no room for the sort's
 // second buffer are appended to `retry` and re-done by the sort-based kernel.
-template <int THREADS, int TS_STATIC>
+template <int THREADS, int TS_STATIC, int SRC = SRC_SUPERKMERS>
 __global__ void __launch_bounds__(THREADS)
 k_merge_hash(const ChunkView *__restrict__ chunks, uint32_t n_chunks, const uint32_t *__restrict__ work, uint32_t n_work,
              uint32_t first_unit, DevParams P, uint32_t min_mult, MergeOut out, uint32_t *__restrict__ retry,
-             uint32_t *__restrict__ retry_count, uint64_t *__restrict__ scratch, uint64_t per_cta_u64) {
+             uint32_t *__restrict__ retry_count, uint64_t *__restrict__ scratch, uint64_t per_cta_u64, PartSrc ps,
+             const uint32_t *__restrict__ n_work_dev) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int WARPS = THREADS / 32;
     constexpr uint32_t SCR_BYTES = WARPS * 256 * 4;  // scratch area: descriptor staging / survivor staging + bins / radix histograms
@@ -413,20 +436,30 @@ k_merge_hash(const ChunkView *__restrict__ chunks, uint32_t n_chunks, const uint
     unsigned long long *s_base = reinterpret_cast<unsigned long long *>(s_scan + 40);
     UnitStage *stage = reinterpret_cast<UnitStage *>(hist);
     const uint32_t tid = threadIdx.x;
+    if (n_work_dev) n_work = min(n_work, *n_work_dev);  // device-side list (big units whose partitions overflowed)
     for (uint32_t wi = blockIdx.x; wi < n_work; wi += gridDim.x) {
-        const uint32_t unit = work[wi];
         uint32_t *s_cnt = s_scan + 36;  // [0] survivors, [1] occupied slots, [2] records of the unit
-        if (tid == 0) s_cnt[2] = 0;
-        __syncthreads();
-        for (uint32_t c = tid; c < n_chunks; c += THREADS) {  // one round of load latency whatever the chunk count
-            const ChunkView &cv = chunks[c];
-            if (unit >= cv.first_unit && unit < cv.first_unit + cv.n_units) {
-                const uint32_t v = cv.unit_kmers[unit - cv.first_unit];
-                if (v) atomicAdd(&s_cnt[2], v);
+        uint32_t unit = 0, oslot, n;
+        if (SRC == SRC_RECORDS) {
+            if (ps.big_ovf[ps.part_big[wi]]) continue;   // the whole unit is redone from its super-k-mers
+            oslot = ps.part_slot[wi];
+            n = min(ps.pcount[wi], ps.pcap);
+            if (n == 0) continue;
+        } else {
+            unit = work[wi];
+            oslot = out.slot(unit - first_unit);
+            if (tid == 0) s_cnt[2] = 0;
+            __syncthreads();
+            for (uint32_t c = tid; c < n_chunks; c += THREADS) {  // one round of load latency whatever the chunk count
+                const ChunkView &cv = chunks[c];
+                if (unit >= cv.first_unit && unit < cv.first_unit + cv.n_units) {
+                    const uint32_t v = cv.unit_kmers[unit - cv.first_unit];
+                    if (v) atomicAdd(&s_cnt[2], v);
+                }
             }
+            __syncthreads();
+            n = s_cnt[2];
         }
-        __syncthreads();
-        const uint32_t n = s_cnt[2];
         uint32_t TS = hash_table_slots(n);
         if (TS_STATIC == 0) {
             K = scratch + (uint64_t)blockIdx.x * per_cta_u64;
@@ -441,8 +474,16 @@ k_merge_hash(const ChunkView *__restrict__ chunks, uint32_t n_chunks, const uint
         const uint32_t tmask = TS - 1;
         for (uint32_t i = tid; i < TS; i += THREADS) { K[i] = HASH_EMPTY; C[i] = 0u; }
         __syncthreads();
-        unit_for_each_kmer64<THREADS>(chunks, n_chunks, unit, P.k, P.forward_only, stage, s_scan,
-                                      [&](uint64_t key, uint32_t fb) { hash_insert(K, C, tmask, key, fb); });
+        if (SRC == SRC_RECORDS) {
+            const uint64_t *recs = ps.recs + (uint64_t)wi * ps.pcap;
+            for (uint32_t i = tid; i < n; i += THREADS) {
+                const uint64_t r = recs[i];
+                hash_insert(K, C, tmask, r >> 2, (uint32_t)r & 3u);
+            }
+        } else {
+            unit_for_each_kmer64<THREADS>(chunks, n_chunks, unit, P.k, P.forward_only, stage, s_scan,
+                                          [&](uint64_t key, uint32_t fb) { hash_insert(K, C, tmask, key, fb); });
+        }
         __syncthreads();
         // ---- scan the table once: MapEntry -> multiplicity, filter; survivors are appended to a small
         //      staging area (in the scratch area) in arbitrary order
@@ -475,7 +516,7 @@ k_merge_hash(const ChunkView *__restrict__ chunks, uint32_t n_chunks, const uint
         __syncthreads();
         const uint32_t S = s_cnt[0], n_occ = s_cnt[1];
         const uint32_t end_bit = min(64u, (2 * P.k + 2 + 7) & ~7u);
-        if (S > STAGE_CAP && S > TS / 2) {  // no room for the sort's second buffer: hand the unit to the sort-based kernel
+        if (SRC != SRC_RECORDS && S > STAGE_CAP && S > TS / 2) {  // no room for the sort's second buffer: hand the unit to the sort-based kernel
             if (tid == 0) retry[atomicAdd(retry_count, 1u)] = unit;
             __syncthreads();
             continue;
@@ -485,13 +526,45 @@ k_merge_hash(const ChunkView *__restrict__ chunks, uint32_t n_chunks, const uint
             atomicAdd(&out.cursor[1], (unsigned long long)n_occ);
             atomicAdd(&out.cursor[2], (unsigned long long)n);
             *s_base = b;
-            out.unit_out_off[unit - first_unit] = b;
-            out.unit_out_cnt[unit - first_unit] = S;
+            out.unit_out_off[oslot] = b;
+            out.unit_out_cnt[oslot] = S;
             if (b + S > out.capacity) *out.overflow = 1u;
         }
         __syncthreads();
         const unsigned long long gbase = *s_base;
         const bool room = gbase + S <= out.capacity;
+        if (SRC == SRC_RECORDS) {
+            // a key partition: survivors leave in any order, k_finish_units sorts the whole unit
+            if (room) {
+                if (S <= STAGE_CAP) {
+                    for (uint32_t i = tid; i < S; i += THREADS) { out.keys[gbase + i] = stage_k[i] >> 2; out.count_flags[gbase + i] = stage_c[i]; }
+                } else {
+                    if (tid == 0) s_cnt[0] = 0;
+                    __syncthreads();
+                    for (uint32_t base = 0; base < TS; base += THREADS) {
+                        const uint32_t i = base + tid;
+                        const uint64_t kk = K[i];
+                        uint32_t cf = 0;
+                        if (kk != HASH_EMPTY) {
+                            const uint32_t cc = C[i];
+                            const uint32_t cnt = cc & 0x3FFFFFFFu, fl = cc >> 30;
+                            const uint32_t mult = cnt >> ((fl == 3u) ? 1 : 0);
+                            if (mult >= min_mult) cf = mult | (fl << 30);
+                        }
+                        const uint32_t bal = __ballot_sync(0xffffffffu, cf != 0);
+                        uint32_t wb = 0;
+                        if (lane_id() == 0 && bal) wb = atomicAdd(&s_cnt[0], (uint32_t)__popc(bal));
+                        wb = __shfl_sync(0xffffffffu, wb, 0);
+                        if (cf) {
+                            const unsigned long long o = gbase + wb + __popc(bal & ((1u << lane_id()) - 1u));
+                            out.keys[o] = kk; out.count_flags[o] = cf;
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            continue;
+        }
         // many survivors: in-place block-scan compaction of the table itself -> K[0..S), C[0..S)
         auto compact_table = [&]() {
             uint32_t running = 0;
@@ -577,6 +650,112 @@ k_merge_hash(const ChunkView *__restrict__ chunks, uint32_t n_chunks, const uint
         }
         __syncthreads();
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_partition_units: one CTA per big unit.  Expands the unit (load-balanced, as k_merge_hash) and appends every record
+// to partition part_hash(key) & (P-1); the CTA owns all partitions of its unit, so the cursors live in shared memory.
+constexpr int PART_MAXP = 4096;
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
+k_partition_units(const ChunkView *__restrict__ chunks, uint32_t n_chunks, const uint32_t *__restrict__ big_unit,
+                  const uint32_t *__restrict__ big_logp, const uint32_t *__restrict__ big_pbase, uint32_t n_big, DevParams P,
+                  uint64_t *__restrict__ recs, uint32_t *__restrict__ pcount, uint32_t pcap, uint32_t *__restrict__ big_ovf,
+                  uint32_t *__restrict__ retry, uint32_t *__restrict__ retry_count) {
+    __shared__ uint32_t s_cur[PART_MAXP];
+    __shared__ __align__(16) unsigned char s_stage_raw[sizeof(UnitStage)];
+    __shared__ uint32_t s_scan[40];
+    __shared__ uint32_t s_ovf;
+    UnitStage *stage = reinterpret_cast<UnitStage *>(s_stage_raw);
+    const uint32_t tid = threadIdx.x;
+    for (uint32_t bi = blockIdx.x; bi < n_big; bi += gridDim.x) {
+        const uint32_t unit = big_unit[bi], np = 1u << big_logp[bi], pbase = big_pbase[bi];
+        for (uint32_t i = tid; i < np; i += THREADS) s_cur[i] = 0;
+        if (tid == 0) s_ovf = 0;
+        __syncthreads();
+        uint64_t *dst = recs + (uint64_t)pbase * pcap;
+        unit_for_each_kmer64<THREADS>(chunks, n_chunks, unit, P.k, P.forward_only, stage, s_scan, [&](uint64_t key, uint32_t fb) {
+            const uint32_t p = part_hash(key) & (np - 1);
+            const uint32_t pos = atomicAdd(&s_cur[p], 1u);
+            if (pos < pcap) dst[(uint64_t)p * pcap + pos] = (key << 2) | fb;
+            else s_ovf = 1u;
+        });
+        __syncthreads();
+        for (uint32_t i = tid; i < np; i += THREADS) pcount[pbase + i] = min(s_cur[i], pcap);
+        if (tid == 0 && s_ovf) { big_ovf[bi] = 1u; retry[atomicAdd(retry_count, 1u)] = unit; }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_finish_units: survivors of every unit -> unit-ordered final table.  A unit with one output slot is already
+// sorted (copy); a big unit's slots (one per key partition, unsorted) are concatenated and radix-sorted by key,
+// in shared memory when they fit, else between the final buffer and a global scratch of the same layout.
+template <int THREADS, int SCAP>
+constexpr size_t finish_units_smem_bytes() { return (size_t)(THREADS / 32) * 256 * 4 + 48 * 4 + (size_t)SCAP * 24; }
+
+template <int THREADS, int SCAP>
+__global__ void __launch_bounds__(THREADS)
+k_finish_units(const uint64_t *__restrict__ src_keys, const uint32_t *__restrict__ src_cf, const uint64_t *__restrict__ slot_off,
+               const uint32_t *__restrict__ slot_cnt, const uint32_t *__restrict__ slot_of_unit /* n_units + 1, or NULL */,
+               const uint64_t *__restrict__ dst_off, uint64_t *__restrict__ dst_keys, uint32_t *__restrict__ dst_cf,
+               uint64_t *__restrict__ tmp_keys, uint32_t *__restrict__ tmp_cf, uint32_t n_units, uint32_t end_bit) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int WARPS = THREADS / 32;
+    uint64_t *sA = reinterpret_cast<uint64_t *>(smem_raw), *sB = sA + SCAP;
+    uint32_t *sAv = reinterpret_cast<uint32_t *>(sB + SCAP), *sBv = sAv + SCAP;
+    uint32_t *hist = sBv + SCAP;
+    uint32_t *s_scan = hist + WARPS * 256;
+    const uint32_t tid = threadIdx.x;
+    for (uint32_t u = blockIdx.x; u < n_units; u += gridDim.x) {
+        const uint32_t s0 = slot_of_unit ? slot_of_unit[u] : u, s1 = slot_of_unit ? slot_of_unit[u + 1] : u + 1;
+        const uint64_t d = dst_off[u];
+        const uint32_t n = (uint32_t)(dst_off[u + 1] - d);
+        if (n == 0) continue;
+        if (s1 - s0 == 1) {
+            const uint64_t so = slot_off[s0];
+            for (uint32_t i = tid; i < n; i += THREADS) { dst_keys[d + i] = src_keys[so + i]; dst_cf[d + i] = src_cf[so + i]; }
+            continue;
+        }
+        const bool in_smem = n <= (uint32_t)SCAP;
+        uint64_t *A = in_smem ? sA : dst_keys + d;
+        uint32_t *Av = in_smem ? sAv : dst_cf + d;
+        uint32_t run = 0;
+        for (uint32_t sl = s0; sl < s1; sl++) {   // concatenate the partitions
+            const uint32_t c = slot_cnt[sl];
+            const uint64_t so = slot_off[sl];
+            for (uint32_t i = tid; i < c; i += THREADS) { A[run + i] = src_keys[so + i]; Av[run + i] = src_cf[so + i]; }
+            run += c;
+        }
+        __syncthreads();
+        uint64_t *B = in_smem ? sB : tmp_keys + d;
+        uint32_t *Bv = in_smem ? sBv : tmp_cf + d;
+        uint32_t *Vs = nullptr;
+        uint64_t *Ss = block_radix_sort64<THREADS, true>(A, B, n, 0, end_bit, hist, s_scan, Av, Bv, &Vs);
+        if (Ss != dst_keys + d)
+            for (uint32_t i = tid; i < n; i += THREADS) { dst_keys[d + i] = Ss[i]; dst_cf[d + i] = Vs[i]; }
+        __syncthreads();
+    }
+}
+
+// Exclusive scan of per-unit survivor totals (sum over the unit's output slots) -> u64 offsets, off[n] = total.
+__global__ void __launch_bounds__(1024) k_scan_unit_slots(const uint32_t *__restrict__ slot_cnt, const uint32_t *__restrict__ slot_of_unit,
+                                                           uint64_t *__restrict__ off, uint32_t n, uint64_t base) {
+    __shared__ uint32_t s_scan[1024 / 32 + 2];
+    uint64_t running = base;
+    for (uint32_t b0 = 0; b0 < n; b0 += 1024) {
+        const uint32_t i = b0 + threadIdx.x;
+        uint32_t v = 0;
+        if (i < n) {
+            if (slot_of_unit) { for (uint32_t s = slot_of_unit[i]; s < slot_of_unit[i + 1]; s++) v += slot_cnt[s]; }
+            else v = slot_cnt[i];
+        }
+        uint32_t tot;
+        const uint32_t p = block_exclusive_scan<1024>(v, s_scan, &tot);
+        if (i < n) off[i] = running + p;
+        running += tot;
+    }
+    if (threadIdx.x == 0) off[n] = running;
 }
 
 template <int THREADS, int TS_STATIC>

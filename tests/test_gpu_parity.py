@@ -235,6 +235,26 @@ def test_several_large_units_in_one_range():
         ctx.close()
 
 
+@pytest.mark.parametrize("s", [1, 2, 40])
+def test_key_partition_overflow_falls_back(s):
+    """A big unit whose k-mers are few but very frequent (a tandem repeat): some key partitions exceed their capacity,
+    the unit is redone by the global-table kernel; result must be identical.  Also a normal big unit beside it."""
+    G = _gpu()
+    rng = np.random.default_rng(77)
+    k, m, b1, b2 = 31, 12, 1, 0
+    motif = util.rand_seq(rng, 211)
+    seqs = [motif * 400, util.rand_seq(rng, 70000), util.revcomp(motif * 150)]
+    reads = O.Reads.from_list(seqs)
+    sk, _ = O.bucketing(reads, k, m, b1, b2)
+    ctx, st = G.minimizer_bucketing([(reads.data, reads.offsets)], b1, b2, k, m, min_multiplicity=s)
+    try:
+        _, km = ctx.unit_sizes()
+        assert (km > 12288).sum() >= 2
+        _check_tables(G, ctx, reads, sk, k, s, b1, b2)
+    finally:
+        ctx.close()
+
+
 @pytest.mark.parametrize("k,ht", [(31, O.HASH_SEQ), (63, O.HASH_RK128)])
 def test_owner_side_import_on_one_gpu(k, ht):
     """The multi-GPU owner path on one device: context A buckets two pushes, its per-owner chunk slices are copied
