@@ -161,6 +161,9 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device -- the ggcat_b200 path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        # the exchange is one large point-to-point all-to-all: let NCCL spread it over more channels
+        os.environ.setdefault("NCCL_MIN_P2P_NCHANNELS", "16")
+        os.environ.setdefault("NCCL_MAX_P2P_NCHANNELS", "32")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     if rank == 0:
         ge.build()

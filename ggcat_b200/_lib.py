@@ -46,6 +46,7 @@ class ChunkSliceC(C.Structure):
         ("n_superkmers", C.c_uint64), ("n_words", C.c_uint64), ("word_bias", C.c_uint64),
         ("d_descriptors", C.c_void_p), ("d_payload", C.c_void_p), ("d_unit_counts", C.c_void_p),
         ("d_unit_words", C.c_void_p), ("d_unit_kmers", C.c_void_p),
+        ("h_unit_counts", C.c_void_p), ("h_unit_words", C.c_void_p), ("h_unit_kmers", C.c_void_p),
     ]
 
 

@@ -1192,6 +1192,8 @@ int32_t ggcat_b200_export_chunk_slice(ggcat_b200_ctx *c, uint32_t chunk, uint32_
     out->d_descriptors = ch->d_desc + d0; out->d_payload = ch->d_payload + w0;
     out->d_unit_counts = ch->d_unit_cnt + first_unit; out->d_unit_words = ch->d_unit_words + first_unit;
     out->d_unit_kmers = ch->d_unit_kmers + first_unit;
+    out->h_unit_counts = ch->h_cnt.data() + first_unit; out->h_unit_words = ch->h_words.data() + first_unit;
+    out->h_unit_kmers = ch->h_kmers.data() + first_unit;
     return 0;
 }
 
@@ -1211,6 +1213,23 @@ int32_t ggcat_b200_import_chunk_slice(ggcat_b200_ctx *c, uint32_t first_unit, ui
                                                      c->totals.as<unsigned long long>() + 3);
     ch->d_unit_off = ch->unit_off.as<uint32_t>();
     c->chunks.push_back(ch);
+    if (s->h_unit_counts && s->h_unit_words && s->h_unit_kmers) {
+        // host copies supplied by the transport: no device read-back, no synchronisation
+        const size_t nu = n_units;
+        ch->h_cnt.assign(s->h_unit_counts, s->h_unit_counts + nu); ch->h_cnt.push_back(0);
+        ch->h_words.assign(s->h_unit_words, s->h_unit_words + nu); ch->h_words.push_back(0);
+        ch->h_kmers.assign(s->h_unit_kmers, s->h_unit_kmers + nu); ch->h_kmers.push_back(0);
+        ch->h_off.resize(nu + 1); ch->h_woff.resize(nu + 1);
+        uint64_t a = 0, b = 0, km = 0;
+        for (size_t u = 0; u < nu; u++) {
+            ch->h_off[u] = (uint32_t)a; ch->h_woff[u] = (uint32_t)b;
+            a += ch->h_cnt[u]; b += ch->h_words[u]; km += ch->h_kmers[u];
+        }
+        ch->h_off[nu] = (uint32_t)a; ch->h_woff[nu] = (uint32_t)b;
+        ch->n_sk = a; ch->n_words = b; ch->n_kmers = km;
+        if (a != s->n_superkmers) return set_err(GGCAT_B200_ERR_INVALID, "import: unit counts sum to %llu, slice holds %llu super-k-mers", (unsigned long long)a, (unsigned long long)s->n_superkmers);
+        return 0;
+    }
     TRY(mirror_chunk(c, ch));
     // imported payload pointer already addresses the slice: word offsets inside it are (woff - word_bias)
     return 0;

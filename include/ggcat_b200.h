@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define GGCAT_B200_ABI_VERSION 1
+#define GGCAT_B200_ABI_VERSION 2
 
 typedef enum {
     GGCAT_B200_OK = 0,
@@ -164,6 +164,11 @@ typedef struct {
     const uint32_t *d_unit_counts;   /* n_units super-k-mer counts   (device) */
     const uint32_t *d_unit_words;    /* n_units payload word counts  (device) */
     const uint32_t *d_unit_kmers;    /* n_units k-mer counts         (device) */
+    /* Host copies of the three per-unit arrays.  export fills them (library-owned, valid until reset/drop);
+     * import uses them instead of reading the device arrays back when all three are non-NULL. */
+    const uint32_t *h_unit_counts;
+    const uint32_t *h_unit_words;
+    const uint32_t *h_unit_kmers;
 } ggcat_b200_chunk_slice;
 
 uint32_t ggcat_b200_n_chunks(ggcat_b200_ctx *ctx);

@@ -29,7 +29,7 @@ def test_header_symbols_exported(lib):
     assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/ggcat_b200.h but not exported"
-    assert lib.ggcat_b200_abi_version() == 1
+    assert lib.ggcat_b200_abi_version() == 2
 
 
 def test_struct_layouts():
@@ -38,7 +38,7 @@ def test_struct_layouts():
     assert C.sizeof(_lib.ParamsC) == 64
     assert C.sizeof(_lib.SuperkmerC) == 24 == api.SUPERKMER_DTYPE.itemsize
     assert C.sizeof(_lib.BucketStatsC) == 48
-    assert C.sizeof(_lib.ChunkSliceC) == 64
+    assert C.sizeof(_lib.ChunkSliceC) == 88
 
 
 def test_host_helpers_match_oracle(lib):
