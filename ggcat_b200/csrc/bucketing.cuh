@@ -130,7 +130,7 @@ k_windows(const uint32_t *__restrict__ pk, const uint32_t *__restrict__ bad, con
           uint32_t *__restrict__ tile_scnt) {
     __shared__ uint32_t s_pk[(WIN_T + 2 * WIN_WMAX + 64) / 16 + 4];
     __shared__ uint32_t s_bad[(WIN_T + 2 * WIN_WMAX + 64) / 32 + 6];
-    __shared__ uint32_t s_brk[(WIN_T + 2 * WIN_WMAX + 64) / 32 + 6];
+    __shared__ uint32_t s_cmb[(WIN_T + 2 * WIN_WMAX + 64) / 32 + 6];   // bad | record-start
     __shared__ uint64_t s_v0[WIN_NI + 1];
     __shared__ uint64_t s_suf[WIN_NI + 1];   // suffix minima inside w-blocks; later M per window
     __shared__ uint64_t s_pre[WIN_NI + 1];   // prefix minima inside w-blocks
@@ -139,7 +139,7 @@ k_windows(const uint32_t *__restrict__ pk, const uint32_t *__restrict__ bad, con
     __shared__ __align__(4) uint8_t s_flag[WIN_T];
     __shared__ uint64_t s_ent[WIN_T];
     __shared__ uint64_t s_TF[32][4], s_TR[32][4];  // rotl(h(c), m-1-i), rotl(r(c), i)
-    __shared__ uint64_t s_H[4], s_R[4], s_HM[4], s_RM1[4];
+    __shared__ uint64_t s_T1[16], s_T2[16];        // roll tables indexed by (leaving base << 2 | entering base)
     __shared__ uint32_t s_scan[WIN_THREADS / 32 + 2];
 
     const uint32_t tid = threadIdx.x;
@@ -157,9 +157,12 @@ k_windows(const uint32_t *__restrict__ pk, const uint32_t *__restrict__ bad, con
     const uint32_t n_bmw = ((last_base + 31) >> 5) - BW0 + 3;
 
     // ---- A
-    if (tid < 4) {
-        s_H[tid] = nt_h(tid); s_R[tid] = nt_r(tid);
-        s_HM[tid] = rotl64(nt_h(tid), m); s_RM1[tid] = rotl64(nt_r(tid), m - 1);
+    if (tid >= 128 && tid < 144) {
+        // cn_nthash.rs:43-57 roll_hash with both table terms folded:
+        //   fw' = rotl(fw,1) ^ rotl(h(out), m) ^ h(in)          rc' = rotr(rc ^ r(out), 1) ^ rotl(r(in), m-1)
+        const uint32_t o = (tid - 128) >> 2, i = tid & 3;
+        s_T1[tid - 128] = rotl64(nt_h(o), m) ^ nt_h(i);
+        s_T2[tid - 128] = rotl64(nt_r(o), 63) ^ rotl64(nt_r(i), m - 1);
     }
     if (tid < 4 * m) {
         const uint32_t i = tid >> 2, c = tid & 3;
@@ -167,12 +170,13 @@ k_windows(const uint32_t *__restrict__ pk, const uint32_t *__restrict__ bad, con
         s_TR[i][c] = rotl64(nt_r(c), i);
     }
     for (uint32_t i = tid; i < n_pkw; i += WIN_THREADS) s_pk[i] = pk[W0 + i];
-    for (uint32_t i = tid; i < n_bmw; i += WIN_THREADS) { s_bad[i] = bad[BW0 + i]; s_brk[i] = brk[BW0 + i]; }
+    for (uint32_t i = tid; i < n_bmw; i += WIN_THREADS) { const uint32_t b = bad[BW0 + i]; s_bad[i] = b; s_cmb[i] = b | brk[BW0 + i]; }
     __syncthreads();
 
-    // ---- B: hashes
-    {
-        const uint32_t IPT = (n_items + WIN_THREADS - 1) / WIN_THREADS;
+    // ---- B: warps 0-3: m-mer hashes by rolling, IPT consecutive items per thread, bases kept in two 64-bit shift
+    //         registers (leaving / entering side);  warps 4-7: window validity
+    if (tid < 128) {
+        const uint32_t IPT = (n_items + 127) / 128;   // <= 9
         const uint32_t x0 = tid * IPT;
         const uint32_t x1 = min(n_items, x0 + IPT);
         if (x0 < x1) {
@@ -181,37 +185,43 @@ k_windows(const uint32_t *__restrict__ pk, const uint32_t *__restrict__ bad, con
             if (g < 0) { s_v0[xs] = ~0ull; s_fwd[xs] = 0; ++g; ++xs; }
             if (xs < x1) {
                 const uint32_t lb = (uint32_t)(g - ((int64_t)W0 << 4));  // local base index into s_pk
+                uint64_t outw = extract64(s_pk, 2ull * lb), inw = extract64(s_pk, 2ull * (lb + m));
                 uint64_t fw = 0, rc = 0;
-                for (uint32_t i = 0; i < m; i++) {
-                    const uint32_t c = packed_base(s_pk, lb + i);
-                    fw ^= s_TF[i][c];
-                    rc ^= s_TR[i][c];
+                {
+                    uint64_t t = outw;
+                    for (uint32_t i = 0; i < m; i++) {
+                        const uint32_t c = (uint32_t)t & 3u;
+                        t >>= 2;
+                        fw ^= s_TF[i][c];
+                        rc ^= s_TR[i][c];
+                    }
                 }
-                uint32_t l = lb;
                 for (uint32_t x = xs;; ++x) {
-                    const uint64_t mn = fw < rc ? fw : rc;
+                    const bool isf = fw < rc;
+                    const uint64_t mn = isf ? fw : rc;
                     s_v0[x] = (mn << 1) | (uint64_t)(fw != rc);  // to_unextendable | !is_rc_symmetric
-                    s_fwd[x] = fw < rc;
+                    s_fwd[x] = isf;
                     if (x + 1 >= x1) break;
-                    const uint32_t co = packed_base(s_pk, l), ci = packed_base(s_pk, l + m);
-                    fw = ((fw << 1) | (fw >> 63)) ^ s_HM[co] ^ s_H[ci];
-                    rc = rc ^ s_R[co];
-                    rc = ((rc >> 1) | (rc << 63)) ^ s_RM1[ci];
-                    ++l;
+                    const uint32_t idx = (((uint32_t)outw & 3u) << 2) | ((uint32_t)inw & 3u);
+                    outw >>= 2; inw >>= 2;
+                    fw = ((fw << 1) | (fw >> 63)) ^ s_T1[idx];
+                    rc = ((rc >> 1) | (rc << 63)) ^ s_T2[idx];
                 }
             }
         }
-    }
-    // ---- B: window validity: inside one N-free segment of one record (sequences_splitter.rs:15-40):
-    //      no bad base in [j, j+k-1) and no record start in (j, j+k-1)
-    for (uint32_t x = tid; x < WIN_T + 2; x += WIN_THREADS) {
-        const int64_t j = gfirst + x;
-        bool ok = j >= 0 && (uint64_t)j + (k - 1) <= (uint64_t)n;
-        if (ok) {
-            const uint32_t lbit = (uint32_t)(j - ((int64_t)BW0 << 5));
-            ok = (bits64(s_bad, lbit, k - 1) | bits64(s_brk, lbit + 1, k - 2)) == 0;
+    } else {
+        // window validity: inside one N-free segment of one record (sequences_splitter.rs:15-40):
+        //   no bad base in [j, j+k-1) and no record start in (j, j+k-1)  <=>  base j is good and
+        //   (bad | record-start) has no bit in (j, j+k-1)
+        for (uint32_t x = tid - 128; x < WIN_T + 2; x += 128) {
+            const int64_t j = gfirst + x;
+            bool ok = j >= 0 && (uint64_t)j + (k - 1) <= (uint64_t)n;
+            if (ok) {
+                const uint32_t lbit = (uint32_t)(j - ((int64_t)BW0 << 5));
+                ok = ((s_bad[lbit >> 5] >> (lbit & 31u)) & 1u) == 0 && bits64(s_cmb, lbit + 1, k - 2) == 0;
+            }
+            s_ok[x] = ok;
         }
-        s_ok[x] = ok;
     }
     __syncthreads();
 
@@ -231,15 +241,16 @@ k_windows(const uint32_t *__restrict__ pk, const uint32_t *__restrict__ bad, con
                 uint64_t pfx = s_v0[lo];
                 s_pre[lo] = pfx;
                 for (uint32_t x = lo + 1; x < hi; ++x) { pfx = comb(pfx, s_v0[x]); s_pre[x] = pfx; }
+                // a window aligned with a block is that block's suffix minimum alone: the prefix it would be
+                // combined with (this block's last position) is replaced by the identity of comb
+                if (hi - lo == w) s_pre[hi - 1] = ~0ull;
             }
         }
     }
     __syncthreads();
     // ---- D: M for windows x in [0, WIN_T]; a window aligned with a block is that block's suffix minimum
     uint64_t *s_M = s_suf;  // in place: only thread x touches s_suf[x]
-    for (uint32_t x = tid; x < WIN_T + 1; x += WIN_THREADS) {
-        if (x % w != 0) s_M[x] = comb(s_suf[x], s_pre[x + w - 1]);
-    }
+    for (uint32_t x = tid; x < WIN_T + 1; x += WIN_THREADS) s_M[x] = comb(s_suf[x], s_pre[x + w - 1]);
     __syncthreads();
 
     // ---- E: split / segment-end flags
