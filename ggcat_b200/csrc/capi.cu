@@ -109,7 +109,7 @@ struct ggcat_b200_ctx {
     cudaStream_t stream = nullptr;
     int sm_count = 148;
     uint64_t max_batch = 1ull << 30;
-    uint64_t host_batch = 40ull << 20;   // push_reads(host): H2D of batch i+1 overlaps the kernels of batch i
+    uint64_t host_batch = 48ull << 20;   // push_reads(host): H2D of batch i+1 overlaps the kernels of batch i
     uint64_t part_kmers = 36ull << 20;   // merge_bucket_range(host): D2H of part j overlaps the merge of part j+1
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr}, ev_part = nullptr;
@@ -920,10 +920,12 @@ int32_t ggcat_b200_push_reads(ggcat_b200_ctx *c, const uint8_t *data, const uint
         if (offsets[r0 + 1] - offsets[r0] > c->max_batch)
             return set_err(GGCAT_B200_ERR_INVALID, "record %llu is longer than the batch limit %llu; split it with k-1 overlap "
                            "(crates/io/src/sequences_reader.rs:162-173)", (unsigned long long)r0, (unsigned long long)c->max_batch);
+        // the first batch is a third of the others: its copy is the only one no kernel overlaps
+        const uint64_t limit = batches.empty() ? std::max<uint64_t>(c->host_batch / 3, 1024) : c->host_batch;
         uint64_t lo = r0 + 1, hi = n_reads;
         while (lo < hi) {  // last record that still fits
             const uint64_t mid = (lo + hi + 1) >> 1;
-            if (offsets[mid] - offsets[r0] <= c->host_batch) lo = mid; else hi = mid - 1;
+            if (offsets[mid] - offsets[r0] <= limit) lo = mid; else hi = mid - 1;
         }
         batches.push_back({r0, lo});
         r0 = lo;
@@ -945,15 +947,29 @@ int32_t ggcat_b200_push_reads(ggcat_b200_ctx *c, const uint8_t *data, const uint
         CU(cudaEventRecord(c->ev_h2d[sl], c->copy_stream));
         return 0;
     };
-    TRY(issue_copy(0));
+    const bool trace = getenv("GGCAT_B200_TRACE") != nullptr;
+    std::vector<cudaEvent_t> tev;   // trace: [origin, per batch: copy start, copy end, compute start, compute end]
+    auto tmark = [&](cudaStream_t s) { if (trace) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, s); tev.push_back(e); } };
+    tmark(c->copy_stream);
+    auto issue_copy_t = [&](size_t bi) -> int32_t { tmark(c->copy_stream); TRY(issue_copy(bi)); tmark(c->copy_stream); return 0; };
+    TRY(issue_copy_t(0));
     for (size_t bi = 0; bi < batches.size(); bi++) {
         const int sl = (int)(bi & 1);
-        if (bi + 1 < batches.size()) TRY(issue_copy(bi + 1));
+        if (bi + 1 < batches.size()) TRY(issue_copy_t(bi + 1));
         const uint64_t r0 = batches[bi].first, r1 = batches[bi].second;
         CU(cudaStreamWaitEvent(c->stream, c->ev_h2d[sl], 0));
+        tmark(c->stream);
         TRY(bucket_batch_device(c, c->st_ascii[sl].as<uint8_t>(), c->st_off[sl].as<uint64_t>(), r1 - r0, offsets[r0],
                                 offsets[r1] - offsets[r0], colors ? c->st_col[sl].as<uint32_t>() : nullptr));
         CU(cudaEventRecord(c->ev_free[sl], c->stream));
+        tmark(c->stream);
+    }
+    if (trace) {
+        cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->copy_stream);
+        fprintf(stderr, "[ggcat_b200 trace] push_reads: %zu batches; ms since first copy was queued:", batches.size());
+        for (size_t i = 1; i < tev.size(); i++) { float ms = 0; cudaEventElapsedTime(&ms, tev[0], tev[i]); fprintf(stderr, " %.2f", ms); }
+        fprintf(stderr, "\n  order: c0s c0e c1s c1e k0s k0e [c2s c2e k1s k1e ...]\n");
+        for (cudaEvent_t e : tev) cudaEventDestroy(e);
     }
     return 0;
 }

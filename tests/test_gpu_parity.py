@@ -521,6 +521,91 @@ def test_c1_maximal_unitigs(golden_dir):
     assert np.array_equal(A["kmers_lo"], nv["key_lo"])
 
 
+def test_c5_shape_rk128_properties():
+    """BASELINE configs[4] at reduced genome size (same read shape and parameters: 150 bp reads at 30x, k=63 m=14 -s 2,
+    rabin-karp128): size-independent properties on the whole table + sampled units against the oracle."""
+    G = _gpu()
+    from ggcat_b200 import synth
+
+    k, m, s = 63, 14, 2
+    g = synth.genome_codes(0xC5, 400_000)
+    r = synth.simulate_reads(g, 80_000, 150, 0.0, 0xC5 + 1)
+    data, offsets = synth.reads_to_ascii_batch(r)
+    b1, b2 = 5, 4
+    ctx, st = G.minimizer_bucketing([(data, offsets)], b1, b2, k, m, min_multiplicity=s, hash_type=O.HASH_RK128)
+    try:
+        n_reads = offsets.size - 1
+        assert st.n_kmers == n_reads * (150 - k + 1) + (st.n_superkmers - n_reads)
+        nb = (1 << b1) + 1
+        t1 = ctx.merge_bucket_range(0, nb)
+        assert t1.keys_hi is not None and t1.total_kmers == st.n_kmers
+        assert (t1.multiplicity >= s).all()
+        # strictly increasing u128 keys inside every unit
+        hi, lo = t1.keys_hi, t1.keys_lo
+        le = (hi[1:] < hi[:-1]) | ((hi[1:] == hi[:-1]) & (lo[1:] <= lo[:-1]))
+        assert np.isin(np.nonzero(le)[0] + 1, t1.unit_offsets).all()
+        t2 = ctx.merge_bucket_range(0, nb)
+        assert np.array_equal(t1.keys_lo, t2.keys_lo) and np.array_equal(t1.keys_hi, t2.keys_hi)
+        assert np.array_equal(t1.count_flags, t2.count_flags)
+        reads = O.Reads(data, offsets)
+        sk, _ = O.bucketing(reads, k, m, b1, b2)
+        assert st.n_superkmers == len(sk)
+        rng = np.random.default_rng(5)
+        for u in rng.choice(nb << b2, 12, replace=False):
+            ref, _, _ = O.merge_unit(reads, sk, int(u) >> b2, int(u) & ((1 << b2) - 1), k, s, O.HASH_RK128)
+            ref = ref[ref["kept"] == 1]
+            sl = t1.unit_slice(int(u))
+            assert np.array_equal(t1.keys_lo[sl], ref["key_lo"]) and np.array_equal(t1.keys_hi[sl], ref["key_hi"])
+            assert np.array_equal(t1.multiplicity[sl].astype(np.uint64), ref["multiplicity"])
+            assert np.array_equal(t1.flags[sl], ref["flags"])
+    finally:
+        ctx.close()
+
+
+def test_c3_shape_colored_properties():
+    """BASELINE configs[2] at reduced size (genomes sharing mutated segments of an ancestor, one colour per genome,
+    k=31 -s 1 -c): colour lists sorted-unique, a k-mer's colour set identical wherever it appears, colour sets of
+    sampled units equal to the oracle's, and per-colour k-mer totals equal to an independent per-genome count."""
+    G = _gpu()
+    from ggcat_b200 import synth
+
+    k, m, s = 31, 12, 1
+    data, offsets, colors = synth.config_c3(n_genomes=12, genome_len=60_000, n_shared=6, shared_len=6_000, mut=0.002)
+    b1, b2 = 4, 3
+    ctx, st = G.minimizer_bucketing([(data, offsets, colors)], b1, b2, k, m, min_multiplicity=s, colors=True)
+    try:
+        nb = (1 << b1) + 1
+        tab = ctx.merge_bucket_range(0, nb)
+        co = tab.color_offsets
+        assert int(co[-1]) == tab.colors.size and (np.diff(co.astype(np.int64)) >= 1).all()
+        # sorted-unique colour lists
+        inner = np.ones(tab.colors.size, bool)
+        inner[co[:-1].astype(np.int64)] = False
+        assert (tab.colors[1:][inner[1:]] > tab.colors[:-1][inner[1:]]).all()
+        # independent check: the number of distinct canonical k-mers of genome c == entries whose list holds c
+        # (boundary k-mers appear in two units: count distinct keys per colour)
+        ent = np.repeat(np.arange(tab.n_entries), np.diff(co.astype(np.int64)))
+        for c in (0, 5, 11):
+            keys_c = np.unique(tab.keys_lo[ent[tab.colors == c]])
+            gen = O.Reads(data[int(offsets[c]):int(offsets[c + 1])], np.array([0, int(offsets[c + 1] - offsets[c])], np.uint64))
+            nv, _ = O.naive_count(gen, k)
+            assert np.array_equal(keys_c, nv["key_lo"])
+        reads = O.Reads(data, offsets, colors)
+        sk, _ = O.bucketing(reads, k, m, b1, b2)
+        rng = np.random.default_rng(3)
+        for u in rng.choice(nb << b2, 6, replace=False):
+            ref, rcols, _ = O.merge_unit(reads, sk, int(u) >> b2, int(u) & ((1 << b2) - 1), k, s, with_color=True)
+            ref = ref[ref["kept"] == 1]
+            sl = tab.unit_slice(int(u))
+            assert np.array_equal(tab.keys_lo[sl], ref["key_lo"])
+            assert np.array_equal(tab.multiplicity[sl].astype(np.uint64), ref["multiplicity"])
+            got = tab.colors[int(co[sl.start]):int(co[sl.stop])]
+            want = np.concatenate([rcols[int(o):int(o) + int(n)] for o, n in zip(ref["color_off"], ref["color_len"])]) if len(ref) else np.zeros(0, np.uint32)
+            assert np.array_equal(got, want)
+    finally:
+        ctx.close()
+
+
 def test_error_behaviour():
     G = _gpu()
     with pytest.raises(G.GgcatB200Error):
