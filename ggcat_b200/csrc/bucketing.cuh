@@ -33,9 +33,10 @@ struct DevParams {
 };
 
 constexpr int WIN_T = 1024;       // windows per tile
-constexpr int WIN_THREADS = 256;
+constexpr int WIN_THREADS = 128;   // 8 windows per thread
 constexpr int WIN_WMAX = 64;      // max supported k - m
 constexpr int WIN_NI = WIN_T + WIN_WMAX;  // m-mer items per tile (upper bound)
+#define PADX(x) ((x) + ((x) >> 3))
 
 // entry bit layout (u64)
 constexpr int ENT_POS_BITS = 11;  // position of the window inside its tile
@@ -131,12 +132,11 @@ k_windows(const uint32_t *__restrict__ pk, const uint32_t *__restrict__ bad, con
     __shared__ uint32_t s_pk[(WIN_T + 2 * WIN_WMAX + 64) / 16 + 4];
     __shared__ uint32_t s_bad[(WIN_T + 2 * WIN_WMAX + 64) / 32 + 6];
     __shared__ uint32_t s_cmb[(WIN_T + 2 * WIN_WMAX + 64) / 32 + 6];   // bad | record-start
-    __shared__ uint64_t s_v0[WIN_NI + 1];
-    __shared__ uint64_t s_suf[WIN_NI + 1];   // suffix minima inside w-blocks; later M per window
-    __shared__ uint64_t s_pre[WIN_NI + 1];   // prefix minima inside w-blocks
+    // m-mer values and window minima: element x lives at PADX(x) = x + x/8, so that the 8-windows-per-thread phase
+    // (lane stride 8 elements) touches every 8-byte bank pair twice per warp instead of sixteen times
+    __shared__ uint64_t s_v0[PADX(WIN_NI + 16) + 1];
+    __shared__ uint64_t s_M[PADX(WIN_T + 8) + 1];
     __shared__ uint8_t s_fwd[WIN_NI + 1];
-    __shared__ uint8_t s_ok[WIN_T + 4];
-    __shared__ __align__(4) uint8_t s_flag[WIN_T];
     __shared__ uint64_t s_ent[WIN_T];
     __shared__ uint64_t s_TF[32][4], s_TR[32][4];  // rotl(h(c), m-1-i), rotl(r(c), i)
     __shared__ uint64_t s_T1[16], s_T2[16];        // roll tables indexed by (leaving base << 2 | entering base)
@@ -157,12 +157,12 @@ k_windows(const uint32_t *__restrict__ pk, const uint32_t *__restrict__ bad, con
     const uint32_t n_bmw = ((last_base + 31) >> 5) - BW0 + 3;
 
     // ---- A
-    if (tid >= 128 && tid < 144) {
+    if (tid < 16) {
         // cn_nthash.rs:43-57 roll_hash with both table terms folded:
         //   fw' = rotl(fw,1) ^ rotl(h(out), m) ^ h(in)          rc' = rotr(rc ^ r(out), 1) ^ rotl(r(in), m-1)
-        const uint32_t o = (tid - 128) >> 2, i = tid & 3;
-        s_T1[tid - 128] = rotl64(nt_h(o), m) ^ nt_h(i);
-        s_T2[tid - 128] = rotl64(nt_r(o), 63) ^ rotl64(nt_r(i), m - 1);
+        const uint32_t o = tid >> 2, i = tid & 3;
+        s_T1[tid] = rotl64(nt_h(o), m) ^ nt_h(i);
+        s_T2[tid] = rotl64(nt_r(o), 63) ^ rotl64(nt_r(i), m - 1);
     }
     if (tid < 4 * m) {
         const uint32_t i = tid >> 2, c = tid & 3;
@@ -173,16 +173,16 @@ k_windows(const uint32_t *__restrict__ pk, const uint32_t *__restrict__ bad, con
     for (uint32_t i = tid; i < n_bmw; i += WIN_THREADS) { const uint32_t b = bad[BW0 + i]; s_bad[i] = b; s_cmb[i] = b | brk[BW0 + i]; }
     __syncthreads();
 
-    // ---- B: warps 0-3: m-mer hashes by rolling, IPT consecutive items per thread, bases kept in two 64-bit shift
-    //         registers (leaving / entering side);  warps 4-7: window validity
-    if (tid < 128) {
-        const uint32_t IPT = (n_items + 127) / 128;   // <= 9
+    // ---- B: m-mer hashes by rolling, IPT consecutive items per thread, bases kept in two 64-bit shift registers
+    //         (leaving / entering side)
+    {
+        const uint32_t IPT = (n_items + WIN_THREADS - 1) / WIN_THREADS;   // <= 9
         const uint32_t x0 = tid * IPT;
         const uint32_t x1 = min(n_items, x0 + IPT);
         if (x0 < x1) {
             int64_t g = gfirst + x0;  // global m-mer position
             uint32_t xs = x0;
-            if (g < 0) { s_v0[xs] = ~0ull; s_fwd[xs] = 0; ++g; ++xs; }
+            if (g < 0) { s_v0[PADX(xs)] = ~0ull; s_fwd[xs] = 0; ++g; ++xs; }
             if (xs < x1) {
                 const uint32_t lb = (uint32_t)(g - ((int64_t)W0 << 4));  // local base index into s_pk
                 uint64_t outw = extract64(s_pk, 2ull * lb), inw = extract64(s_pk, 2ull * (lb + m));
@@ -199,7 +199,7 @@ k_windows(const uint32_t *__restrict__ pk, const uint32_t *__restrict__ bad, con
                 for (uint32_t x = xs;; ++x) {
                     const bool isf = fw < rc;
                     const uint64_t mn = isf ? fw : rc;
-                    s_v0[x] = (mn << 1) | (uint64_t)(fw != rc);  // to_unextendable | !is_rc_symmetric
+                    s_v0[PADX(x)] = (mn << 1) | (uint64_t)(fw != rc);  // to_unextendable | !is_rc_symmetric
                     s_fwd[x] = isf;
                     if (x + 1 >= x1) break;
                     const uint32_t idx = (((uint32_t)outw & 3u) << 2) | ((uint32_t)inw & 3u);
@@ -209,81 +209,101 @@ k_windows(const uint32_t *__restrict__ pk, const uint32_t *__restrict__ bad, con
                 }
             }
         }
+    }
+    __syncthreads();
+
+    // ---- C: 8 consecutive windows per thread (x0 .. x0+7, x0 = 1 + 8 tid), everything in registers.
+    //   window x = items [x, x+w-1].  The items [x0+7, x0+w-1] are common to the 8 windows; each window adds a suffix
+    //   of the 7 items before and a prefix of the 7 items after (a van Herk block of 8 held in registers).  The window
+    //   before the first (x0-1) is recomputed here too, so E needs nothing from other threads.
+    //   comb() is the reference's min-with-duplicate-flag semigroup (batch_minqueue.rs:63-113).
+    constexpr int WPT = 8;
+    static_assert(WPT * WIN_THREADS == WIN_T, "8 windows per thread cover the tile");
+    const uint32_t x0 = 1 + tid * WPT;
+    uint64_t Mreg[WPT], Mprev;
+    if (w >= (uint32_t)WPT) {
+        uint64_t common = s_v0[PADX(x0 + WPT - 1)], common_short = common;   // [x0+7, x0+w-1] and the same without the last item
+        for (uint32_t q = x0 + WPT; q < x0 + w; ++q) { common_short = common; common = comb(common, s_v0[PADX(q)]); }
+        uint64_t L[WPT - 1];
+        L[WPT - 2] = s_v0[PADX(x0 + WPT - 2)];
+#pragma unroll
+        for (int i = WPT - 3; i >= 0; --i) L[i] = comb(s_v0[PADX(x0 + i)], L[i + 1]);
+        // window x0-1 = item x0-1 + items [x0, x0+6] + items [x0+7, x0+w-2]
+        Mprev = comb(s_v0[PADX(x0 - 1)], L[0]);
+        if (w > (uint32_t)WPT) Mprev = comb(Mprev, common_short);
+        uint64_t R = 0;
+#pragma unroll
+        for (int i = 0; i < WPT; i++) {
+            uint64_t mi = (i < WPT - 1) ? comb(L[i], common) : common;
+            if (i > 0) {
+                const uint64_t nv = s_v0[PADX(x0 + w + i - 1)];
+                R = (i == 1) ? nv : comb(R, nv);
+                mi = comb(mi, R);
+            }
+            Mreg[i] = mi;
+        }
     } else {
-        // window validity: inside one N-free segment of one record (sequences_splitter.rs:15-40):
-        //   no bad base in [j, j+k-1) and no record start in (j, j+k-1)  <=>  base j is good and
-        //   (bad | record-start) has no bit in (j, j+k-1)
-        for (uint32_t x = tid - 128; x < WIN_T + 2; x += 128) {
-            const int64_t j = gfirst + x;
-            bool ok = j >= 0 && (uint64_t)j + (k - 1) <= (uint64_t)n;
-            if (ok) {
-                const uint32_t lbit = (uint32_t)(j - ((int64_t)BW0 << 5));
-                ok = ((s_bad[lbit >> 5] >> (lbit & 31u)) & 1u) == 0 && bits64(s_cmb, lbit + 1, k - 2) == 0;
-            }
-            s_ok[x] = ok;
+#pragma unroll
+        for (int i = 0; i < WPT; i++) {
+            uint64_t mi = s_v0[PADX(x0 + i)];
+            for (uint32_t q = 1; q < w; ++q) mi = comb(mi, s_v0[PADX(x0 + i + q)]);
+            Mreg[i] = mi;
         }
+        Mprev = s_v0[PADX(x0 - 1)];
+        for (uint32_t q = 1; q < w; ++q) Mprev = comb(Mprev, s_v0[PADX(x0 - 1 + q)]);
     }
-    __syncthreads();
-
-    // ---- C: suffix / prefix minima inside blocks of w items (warps 0-1: suffix, warps 2-3: prefix)
+#pragma unroll
+    for (int i = 0; i < WPT; i++) s_M[PADX(x0 + i)] = Mreg[i];
+    // window validity for x0-1 .. x0+8: inside one N-free segment of one record (sequences_splitter.rs:15-40):
+    //   no bad base in [j, j+k-1) and no record start in (j, j+k-1)  <=>  base j is good and
+    //   (bad | record-start) has no bit in (j, j+k-1)
+    uint32_t ok10 = 0;
     {
-        const uint32_t n_blocks = (n_items + w - 1) / w;
-        if (tid < 64) {
-            for (uint32_t b = tid; b < n_blocks; b += 64) {
-                const uint32_t lo = b * w, hi = min(n_items, lo + w);
-                uint64_t sfx = s_v0[hi - 1];
-                s_suf[hi - 1] = sfx;
-                for (uint32_t x = hi - 1; x-- > lo;) { sfx = comb(s_v0[x], sfx); s_suf[x] = sfx; }
-            }
-        } else if (tid < 128) {
-            for (uint32_t b = tid - 64; b < n_blocks; b += 64) {
-                const uint32_t lo = b * w, hi = min(n_items, lo + w);
-                uint64_t pfx = s_v0[lo];
-                s_pre[lo] = pfx;
-                for (uint32_t x = lo + 1; x < hi; ++x) { pfx = comb(pfx, s_v0[x]); s_pre[x] = pfx; }
-                // a window aligned with a block is that block's suffix minimum alone: the prefix it would be
-                // combined with (this block's last position) is replaced by the identity of comb
-                if (hi - lo == w) s_pre[hi - 1] = ~0ull;
-            }
+        const int64_t jf = gfirst + x0 - 1;                               // position of window x0-1 (>= -1)
+        const uint32_t rel = (uint32_t)(jf + 1 - ((int64_t)BW0 << 5));    // bit index of position jf + 1
+        const uint64_t clo = extract64(s_cmb, rel), chi = extract64(s_cmb, rel + 64);
+        const uint64_t kmask = (k - 2 >= 64) ? ~0ull : ((1ull << (k - 2)) - 1ull);
+        const uint32_t badn = extract32(s_bad, rel);                      // bad bits of positions jf+1 ..
+        const uint32_t bad0 = jf >= 0 ? ((s_bad[(rel - 1) >> 5] >> ((rel - 1) & 31u)) & 1u) : 1u;
+#pragma unroll
+        for (int i = 0; i < WPT + 2; i++) {
+            const int64_t j = jf + i;
+            const uint64_t bits = i == 0 ? clo : ((clo >> i) | (chi << (64 - i)));
+            const uint32_t bd = i == 0 ? bad0 : ((badn >> (i - 1)) & 1u);
+            const bool ok = j >= 0 && (uint64_t)j + (k - 1) <= (uint64_t)n && bd == 0 && (bits & kmask) == 0;
+            ok10 |= (ok ? 1u : 0u) << i;
         }
     }
-    __syncthreads();
-    // ---- D: M for windows x in [0, WIN_T]; a window aligned with a block is that block's suffix minimum
-    uint64_t *s_M = s_suf;  // in place: only thread x touches s_suf[x]
-    for (uint32_t x = tid; x < WIN_T + 1; x += WIN_THREADS) s_M[x] = comb(s_suf[x], s_pre[x + w - 1]);
-    __syncthreads();
 
-    // ---- E: split / segment-end flags
-    for (uint32_t x = 1 + tid; x < WIN_T + 1; x += WIN_THREADS) {
-        const bool okj = s_ok[x], okp = s_ok[x - 1], okn = s_ok[x + 1];
-        const bool valid = okj && (okp || okn);        // segment has >= 2 windows <=> length >= k
-        const bool first = okj && !okp;
-        uint32_t f = 0;
-        if (valid) {
-            const uint64_t M = s_M[x];
-            const bool S = first || M != s_M[x - 1] || ((M & 1ull) && s_v0[x - 1] == M);
-            f = (S ? 1u : 0u) | (!okn ? 2u : 0u) | (first ? 4u : 0u);
-        }
-        s_flag[x - 1] = (uint8_t)f;
-    }
-    __syncthreads();
-    // ---- F: in-order compaction, 4 consecutive windows per thread
+    // ---- E: split / segment-end flags of the thread's windows, F: in-order compaction (one block scan)
     uint32_t n_ent, n_s;
     {
-        const uint32_t f4 = reinterpret_cast<const uint32_t *>(s_flag)[tid];
+        uint32_t fl = 0;  // 3 flag bits per window
+#pragma unroll
+        for (int i = 0; i < WPT; i++) {
+            const uint32_t x = x0 + i;
+            const bool okp = (ok10 >> i) & 1u, okj = (ok10 >> (i + 1)) & 1u, okn = (ok10 >> (i + 2)) & 1u;
+            const bool valid = okj && (okp || okn);        // segment has >= 2 windows <=> length >= k
+            const bool first = okj && !okp;
+            if (valid) {
+                const uint64_t M = Mreg[i], Mp = i ? Mreg[i ? i - 1 : 0] : Mprev;
+                const bool S = first || M != Mp || ((M & 1ull) && s_v0[PADX(x - 1)] == M);
+                fl |= ((S ? 1u : 0u) | (!okn ? 2u : 0u) | (first ? 4u : 0u)) << (3 * i);
+            }
+        }
         uint32_t mine = 0;
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
-            const uint32_t f = (f4 >> (8 * q)) & 0xFFu;
+        for (int i = 0; i < WPT; i++) {
+            const uint32_t f = (fl >> (3 * i)) & 7u;
             if (f & 3u) mine += 1u + ((f & 1u) << 16);
         }
         uint32_t tot;
-        uint32_t pre = block_exclusive_scan<WIN_THREADS>(mine, s_scan, &tot);
+        uint32_t pre = block_exclusive_scan<WIN_THREADS>(mine, s_scan, &tot);   // its barriers also publish s_M
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
-            const uint32_t f = (f4 >> (8 * q)) & 0xFFu;
+        for (int i = 0; i < WPT; i++) {
+            const uint32_t f = (fl >> (3 * i)) & 7u;
             if (f & 3u) {
-                s_ent[pre & 0xFFFFu] = (uint64_t)(4 * tid + q) | ((f & 1u) ? ENT_S : 0) | ((f & 2u) ? ENT_E : 0) |
+                s_ent[pre & 0xFFFFu] = (uint64_t)(x0 + i - 1) | ((f & 1u) ? ENT_S : 0) | ((f & 2u) ? ENT_E : 0) |
                                        ((f & 4u) ? ENT_FIRST : 0) | ((uint64_t)(pre >> 16) << ENT_SRANK_SHIFT);
                 pre += 1u + ((f & 1u) << 16);
             }
@@ -298,14 +318,14 @@ k_windows(const uint32_t *__restrict__ pk, const uint32_t *__restrict__ bad, con
         uint64_t e = s_ent[i];
         if (e & ENT_S) {
             const uint32_t x = (uint32_t)(e & ((1u << ENT_POS_BITS) - 1)) + 1;
-            const uint64_t M = s_M[x];
+            const uint64_t M = s_M[PADX(x)];
             uint32_t bucket, rcf = 0, arg = 0;
             if ((M & 1ull) == 0) {
                 bucket = 1u << P.b1;  // duplicates bucket
                 e |= ENT_DUP;
             } else {
                 for (uint32_t q = 0; q < w; q++)
-                    if (s_v0[x + q] == M) { arg = q; break; }
+                    if (s_v0[PADX(x + q)] == M) { arg = q; break; }
                 rcf = (!P.forward_only && !s_fwd[x + arg]) ? 1u : 0u;
                 bucket = (uint32_t)(M >> 1) & ((1u << P.b1) - 1);   // cn_nthash.rs:135-142 get_bucket(0, b1, M)
             }
