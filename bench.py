@@ -192,11 +192,19 @@ def run_ours(args):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
     torch.cuda.synchronize()
     owner = gdist.OwnerMap(b1, b2, world)
+    transport = "none"
+    if world > 1:
+        transport = os.environ.get("GGCAT_B200_EXCHANGE", "peer")
+        if transport == "peer":
+            # receive arena: descriptors (16 B / super-k-mer) + payload ~ 2.4 B per input base, 2.5x headroom
+            gdist.peer_setup(ctx, rank, world, arena_bytes=max(6 * n_bases, 64 << 20))
+
+    last_stats = [None]
 
     def step_device():
         ctx.reset()
         ctx.push_reads_device(d_data.data_ptr(), d_off.data_ptr(), n_reads, n_bases)
-        ctx.finish_bucketing()
+        last_stats[0] = ctx.finish_bucketing()   # this rank's own super-k-mers (before the exchange adds imported chunks)
         if world > 1:
             gdist.exchange_and_import(ctx, owner, rank, world, ext)
         fb, cnt = owner.bucket_range(rank)
@@ -258,7 +266,7 @@ def run_ours(args):
         step_device()
     kt = ctx.kernel_times(reset=True)
     ctx.set_timing(False)
-    st = ctx.finish_bucketing()
+    st = last_stats[0]
     n_entries, unique, total_kmers = res
 
     # ---- e2e through the C ABI with host buffers
@@ -322,7 +330,9 @@ def run_ours(args):
         "config": {"workload": f"C2 per GPU: {n_reads} x {READ_LEN} bp reads (30x of {GENOME_PER_GPU * world} bp genome, 1% errors), "
                                f"k={K} m={M} -s {S} seq-hash, buckets {1 << b1}(+1) x {1 << b2}",
                    "l2": "flushed (256 MB write) between timed steps", "reads_per_gpu": n_reads,
-                   "parallelism": f"bucket-owner x{world}" if world > 1 else "single GPU"},
+                   "parallelism": f"bucket-owner x{world}" if world > 1 else "single GPU",
+                   "exchange": {"peer": "k_peer_push over NVLink peer memory (CUDA IPC)", "nccl": "NCCL all_to_all_single",
+                                "none": "none"}[transport]},
         "e2e": {"value": e2e_val, "unit": "Gbases/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms},
         "gpu_launches": int(launches),

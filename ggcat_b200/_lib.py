@@ -74,6 +74,10 @@ SYMBOLS = {
     "ggcat_b200_export_chunk_slice": (_i32, [_vp, _u32, _u32, _u32, C.POINTER(ChunkSliceC)]),
     "ggcat_b200_import_chunk_slice": (_i32, [_vp, _u32, _u32, C.POINTER(ChunkSliceC)]),
     "ggcat_b200_drop_local_chunks": (_i32, [_vp]),
+    "ggcat_b200_owner_range": (_i32, [_u32, _u32, _u32, C.POINTER(_u32), C.POINTER(_u32)]),
+    "ggcat_b200_peer_init": (_i32, [_vp, _u32, _u32, _u64, _vp]),
+    "ggcat_b200_peer_connect": (_i32, [_vp, _vp]),
+    "ggcat_b200_peer_exchange": (_i32, [_vp]),
     "ggcat_b200_stream": (_vp, [_vp]),
     "ggcat_b200_synchronize": (_i32, [_vp]),
     "ggcat_b200_set_timing": (_i32, [_vp, _i32]),

@@ -137,6 +137,7 @@ class GGCATB200:
         self.params = params
         self.m = params.m or compute_best_m(params.k)
         self._keep = []  # device tensors of imported slices must outlive the merge
+        self.peer_connected = False
 
     # -- lifecycle
     def close(self):
@@ -259,6 +260,23 @@ class GGCATB200:
 
     def drop_local_chunks(self):
         _check(self._lib.ggcat_b200_drop_local_chunks(self._h))
+
+    # -- multi-GPU exchange over NVLink peer memory (include/ggcat_b200.h, ggcat_b200_peer_*)
+    def peer_init(self, rank: int, world: int, arena_bytes: int) -> bytes:
+        """Allocates this rank's receive arena; returns its 64-byte CUDA IPC handle."""
+        h = (C.c_uint8 * 64)()
+        _check(self._lib.ggcat_b200_peer_init(self._h, rank, world, arena_bytes, C.cast(h, C.c_void_p)))
+        self.peer_world = world
+        return bytes(h)
+
+    def peer_connect(self, handles: Sequence[bytes]):
+        """handles: the IPC handles of all ranks, in rank order."""
+        buf = (C.c_uint8 * (64 * len(handles))).from_buffer_copy(b"".join(handles))
+        _check(self._lib.ggcat_b200_peer_connect(self._h, C.cast(buf, C.c_void_p)))
+        self.peer_connected = True
+
+    def peer_exchange(self):
+        _check(self._lib.ggcat_b200_peer_exchange(self._h))
 
     # -- measurement
     @property

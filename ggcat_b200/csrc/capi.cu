@@ -3,6 +3,7 @@
 // every entry point fails with GGCAT_B200_ERR_CUDA when no device is usable.
 #include "../../include/ggcat_b200.h"
 #include "merge128.cuh"
+#include "peer.cuh"
 
 #include <algorithm>
 #include <cstdarg>
@@ -72,11 +73,11 @@ struct Chunk {
 };
 
 enum Family { F_PACK = 0, F_WINDOWS, F_EMIT, F_SCATTER, F_SCAN, F_MERGE_HASH, F_MERGE_HASH_GLOBAL, F_MERGE_SMEM, F_MERGE_GLOBAL,
-              F_GATHER, F_MERGE_HASH128, F_SORT128, F_COLOR_FOLD, F_PARTITION, F_MERGE_HASH_PART, F_COUNT };
+              F_GATHER, F_MERGE_HASH128, F_SORT128, F_COLOR_FOLD, F_PARTITION, F_MERGE_HASH_PART, F_PEER, F_COUNT };
 static const char *kFamilyNames[F_COUNT] = {"k_pack+k_mark", "k_windows", "k_emit", "k_scatter", "k_exclusive_scan_u32",
                                             "k_merge_hash<smem>", "k_merge_hash<global>", "k_merge_units<smem>",
                                             "k_merge_units<global>", "k_gather_units", "k_merge_hash128", "k_sort_units128",
-                                            "k_color_fold", "k_partition_units", "k_merge_hash<partitions>"};
+                                            "k_color_fold", "k_partition_units", "k_merge_hash<partitions>", "k_peer_push+k_peer_sync"};
 
 struct TimedLaunch { int fam; cudaEvent_t a, b; };
 
@@ -98,6 +99,18 @@ struct FinalTable {
     const uint64_t *color_off = nullptr;     // n_entries (+1 implied = n_colors)
     const uint32_t *colors = nullptr;
     uint64_t n_entries = 0, n_colors = 0;
+};
+
+// NVLink peer exchange (peer.cuh): this rank's receive arena, the peers' arenas mapped through CUDA IPC, staging.
+struct PeerState {
+    bool inited = false, connected = false;
+    uint32_t rank = 0, world = 1, epoch = 0;
+    uint8_t *arena = nullptr;
+    uint64_t arena_bytes = 0, region_bytes = 0;
+    uint8_t *peer_arena[PEER_MAX_WORLD] = {};
+    DevBuf d_jobs, d_stage, d_err;
+    uint8_t *h_stage = nullptr; size_t h_stage_cap = 0;   // pinned: region headers + slice tables being sent, then the jobs
+    uint8_t *h_recv = nullptr; size_t h_recv_cap = 0;     // pinned: received headers, tables and per-unit counts
 };
 
 }  // namespace
@@ -136,6 +149,7 @@ struct ggcat_b200_ctx {
     uint32_t fam_launches[F_COUNT];
     std::vector<HostTable *> free_tables;
     uint64_t last_entries = 0;
+    PeerState peer;
 };
 
 namespace {
@@ -902,6 +916,15 @@ void ggcat_b200_destroy(ggcat_b200_ctx *c) {
         if (c->ev_free[i]) cudaEventDestroy(c->ev_free[i]);
     }
     if (c->ev_part) cudaEventDestroy(c->ev_part);
+    {
+        PeerState &ps = c->peer;
+        for (uint32_t r = 0; r < ps.world; r++)
+            if (ps.connected && r != ps.rank && ps.peer_arena[r]) cudaIpcCloseMemHandle(ps.peer_arena[r]);
+        if (ps.arena) cudaFree(ps.arena);
+        ps.d_jobs.release(); ps.d_stage.release(); ps.d_err.release();
+        if (ps.h_stage) cudaFreeHost(ps.h_stage);
+        if (ps.h_recv) cudaFreeHost(ps.h_recv);
+    }
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -1260,6 +1283,235 @@ int32_t ggcat_b200_drop_local_chunks(ggcat_b200_ctx *c) {
         else c->chunk_pool.push_back(ch);  // recycle the device buffers
     }
     c->chunks.swap(keep);
+    return 0;
+}
+
+
+// ---- NVLink peer exchange (peer.cuh) -----------------------------------------------------------------------------
+static uint32_t owner_first_bucket(uint32_t b1, uint32_t r, uint32_t world) {
+    const uint64_t nb = 1ull << b1;
+    if (r >= world) return (uint32_t)nb + 1;                      // the last rank also owns the duplicates bucket
+    return (uint32_t)(((uint64_t)r * nb + world - 1) / world);    // owner(b) = b * world >> b1
+}
+
+int32_t ggcat_b200_owner_range(uint32_t buckets_count_log, uint32_t rank, uint32_t world, uint32_t *first_bucket, uint32_t *n_buckets) {
+    if (world == 0 || rank >= world || buckets_count_log > 13 || world > (1u << buckets_count_log))
+        return set_err(GGCAT_B200_ERR_INVALID, "owner_range: rank %u of %u ranks for %u buckets", rank, world, 1u << buckets_count_log);
+    const uint32_t a = owner_first_bucket(buckets_count_log, rank, world), b = owner_first_bucket(buckets_count_log, rank + 1, world);
+    if (first_bucket) *first_bucket = a;
+    if (n_buckets) *n_buckets = b - a;
+    return 0;
+}
+
+int32_t ggcat_b200_peer_init(ggcat_b200_ctx *c, uint32_t rank, uint32_t world, uint64_t arena_bytes, ggcat_b200_peer_handle *out) {
+    TRY(check_ctx(c));
+    PeerState &ps = c->peer;
+    if (ps.inited) return set_err(GGCAT_B200_ERR_STATE, "peer_init called twice");
+    if (world == 0 || world > (uint32_t)PEER_MAX_WORLD || rank >= world || world > (1u << c->P.b1))
+        return set_err(GGCAT_B200_ERR_INVALID, "peer_init: rank %u of %u ranks (max %d, <= %u buckets)", rank, world, PEER_MAX_WORLD, 1u << c->P.b1);
+    if (!out) return set_err(GGCAT_B200_ERR_INVALID, "null handle");
+    static_assert(sizeof(cudaIpcMemHandle_t) <= sizeof(ggcat_b200_peer_handle), "IPC handle must fit the ABI struct");
+    memset(out, 0, sizeof(*out));
+    ps.rank = rank; ps.world = world;
+    if (world > 1) {
+        const uint64_t min_region = PEER_META_OFF + (1ull << 20);
+        ps.region_bytes = std::max<uint64_t>(arena_bytes / world, min_region) & ~255ull;
+        ps.arena_bytes = PEER_HDR_BYTES + ps.region_bytes * world;
+        CU(cudaMalloc((void **)&ps.arena, ps.arena_bytes));
+        CU(cudaMemset(ps.arena, 0, PEER_HDR_BYTES));
+        CU(cudaDeviceSynchronize());
+        cudaIpcMemHandle_t h;
+        CU(cudaIpcGetMemHandle(&h, ps.arena));
+        memcpy(out->bytes, &h, sizeof(h));
+        CU(ps.d_err.reserve(16));
+        CU(cudaMemset(ps.d_err.p, 0, 16));
+    }
+    ps.inited = true;
+    return 0;
+}
+
+int32_t ggcat_b200_peer_connect(ggcat_b200_ctx *c, const ggcat_b200_peer_handle *handles) {
+    TRY(check_ctx(c));
+    PeerState &ps = c->peer;
+    if (!ps.inited) return set_err(GGCAT_B200_ERR_STATE, "peer_connect before peer_init");
+    if (ps.connected) return set_err(GGCAT_B200_ERR_STATE, "peer_connect called twice");
+    if (ps.world > 1 && !handles) return set_err(GGCAT_B200_ERR_INVALID, "null handles");
+    for (uint32_t r = 0; r < ps.world && ps.world > 1; r++) {
+        if (r == ps.rank) { ps.peer_arena[r] = ps.arena; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles[r].bytes, sizeof(h));
+        void *p = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess)
+            return set_err(GGCAT_B200_ERR_CUDA, "cudaIpcOpenMemHandle(rank %u): %s (ranks must be separate processes on one NVLink box)", r,
+                           cudaGetErrorString(e));
+        ps.peer_arena[r] = reinterpret_cast<uint8_t *>(p);
+    }
+    ps.connected = true;
+    return 0;
+}
+
+static int32_t pinned_reserve(uint8_t **p, size_t *cap, size_t need) {
+    if (need <= *cap) return 0;
+    if (*p) cudaFreeHost(*p);
+    *p = nullptr; *cap = 0;
+    const size_t want = need + need / 4 + 4096;
+    if (cudaMallocHost((void **)p, want) != cudaSuccess) return set_err(GGCAT_B200_ERR_CUDA, "cudaMallocHost(%zu) failed", want);
+    *cap = want;
+    return 0;
+}
+
+int32_t ggcat_b200_peer_exchange(ggcat_b200_ctx *c) {
+    TRY(check_ctx(c));
+    PeerState &ps = c->peer;
+    if (!ps.connected) return set_err(GGCAT_B200_ERR_STATE, "peer_exchange before peer_connect");
+    if (!c->finished) return set_err(GGCAT_B200_ERR_STATE, "peer_exchange before finish_bucketing");
+    const uint32_t W = ps.world, me = ps.rank;
+    if (W == 1) return 0;
+    const DevParams &P = c->P;
+    cudaStream_t st = c->stream;
+    std::vector<Chunk *> local;
+    for (Chunk *ch : c->chunks) {
+        if (ch->imported) return set_err(GGCAT_B200_ERR_STATE, "peer_exchange: chunks were already exchanged");
+        TRY(mirror_chunk(c, ch));
+        local.push_back(ch);
+    }
+    const uint32_t nsl = (uint32_t)local.size();
+    if (nsl > (uint32_t)PEER_MAX_SLICES)
+        return set_err(GGCAT_B200_ERR_INVALID, "peer_exchange routes at most %d bucket chunks (pushes) per build, got %u", PEER_MAX_SLICES, nsl);
+    const uint32_t epoch = ++ps.epoch;
+    auto first_unit_of = [&](uint32_t r) { return owner_first_bucket(P.b1, r, W) << P.b2; };
+    auto align16 = [](uint64_t x) { return (x + 15) & ~15ull; };
+    // ---- plan: region header + slice table per destination, copy jobs
+    const size_t tbl = (size_t)PEER_META_OFF;
+    const size_t max_jobs = (size_t)W * (1 + 5 * (size_t)std::max<uint32_t>(nsl, 1));
+    TRY(pinned_reserve(&ps.h_stage, &ps.h_stage_cap, (size_t)W * tbl + max_jobs * sizeof(PeerJob)));
+    CU(ps.d_stage.reserve((size_t)W * tbl));
+    CU(ps.d_jobs.reserve(max_jobs * sizeof(PeerJob)));
+    PeerJob *jobs = reinterpret_cast<PeerJob *>(ps.h_stage + (size_t)W * tbl);
+    uint32_t n_jobs = 0;
+    bool sent_overflow = false;
+    for (uint32_t d = 0; d < W; d++) {
+        if (d == me) continue;
+        const uint32_t fu = first_unit_of(d), nu = first_unit_of(d + 1) - fu;
+        const uint64_t s_meta = align16(3ull * nu * 4), s_uoff = align16(((uint64_t)nu + 2) * 4);
+        uint8_t *hs = ps.h_stage + (size_t)d * tbl;
+        memset(hs, 0, tbl);
+        RegionHdr *rh = reinterpret_cast<RegionHdr *>(hs);
+        PeerSlice *tb = reinterpret_cast<PeerSlice *>(hs + PEER_TABLE_OFF);
+        uint8_t *dst = ps.peer_arena[d] + PEER_HDR_BYTES + (uint64_t)me * ps.region_bytes;
+        uint64_t cursor = PEER_META_OFF + (uint64_t)nsl * (s_meta + s_uoff);
+        for (uint32_t j = 0; j < nsl; j++) {
+            const Chunk *ch = local[j];
+            const uint64_t d0 = ch->h_off[fu], d1 = ch->h_off[fu + nu], w0 = ch->h_woff[fu], w1 = ch->h_woff[fu + nu];
+            tb[j].n_sk = d1 - d0; tb[j].n_words = w1 - w0; tb[j].word_bias = w0;
+            tb[j].desc_off = align16(cursor); cursor = tb[j].desc_off + (d1 - d0) * 16;
+            tb[j].pay_off = align16(cursor) + ((w0 * 4) & 15u); cursor = tb[j].pay_off + (w1 - w0 + 8) * 4;
+        }
+        rh->n_units = nu; rh->epoch = epoch;
+        if (cursor > ps.region_bytes) { rh->overflow = 1; rh->n_slices = 0; sent_overflow = true; }
+        else {
+            rh->n_slices = nsl;
+            for (uint32_t j = 0; j < nsl; j++) {
+                const Chunk *ch = local[j];
+                uint8_t *meta = dst + PEER_META_OFF + (uint64_t)j * s_meta;
+                jobs[n_jobs++] = {reinterpret_cast<const uint8_t *>(ch->d_unit_cnt + fu), meta, (uint64_t)nu * 4};
+                jobs[n_jobs++] = {reinterpret_cast<const uint8_t *>(ch->d_unit_words + fu), meta + (uint64_t)nu * 4, (uint64_t)nu * 4};
+                jobs[n_jobs++] = {reinterpret_cast<const uint8_t *>(ch->d_unit_kmers + fu), meta + (uint64_t)nu * 8, (uint64_t)nu * 4};
+                if (tb[j].n_sk) {
+                    jobs[n_jobs++] = {reinterpret_cast<const uint8_t *>(ch->d_desc + ch->h_off[fu]), dst + tb[j].desc_off, tb[j].n_sk * 16};
+                    jobs[n_jobs++] = {reinterpret_cast<const uint8_t *>(ch->d_payload + ch->h_woff[fu]), dst + tb[j].pay_off, tb[j].n_words * 4};
+                }
+            }
+        }
+        jobs[n_jobs++] = {ps.d_stage.as<uint8_t>() + (size_t)d * tbl, dst, (uint64_t)(PEER_TABLE_OFF + (uint64_t)nsl * 64)};
+    }
+    CU(cudaMemcpyAsync(ps.d_stage.p, ps.h_stage, (size_t)W * tbl, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(ps.d_jobs.p, jobs, (size_t)n_jobs * sizeof(PeerJob), cudaMemcpyHostToDevice, st));
+    PeerHdrPtrs hp;
+    memset(&hp, 0, sizeof(hp));
+    for (uint32_t r = 0; r < W; r++) hp.h[r] = reinterpret_cast<PeerHdr *>(ps.peer_arena[r]);
+    const unsigned long long timeout_ns = 20ull * 1000000000ull;
+    {
+        LaunchTimer t(c, F_PEER, 3);
+        // every peer has finished merging what we sent last time -> push -> tell the owners, wait for our sources
+        k_peer_sync<<<1, PEER_MAX_WORLD, 0, st>>>(hp, me, W, 0u, epoch - 1, ps.d_err.as<uint32_t>(), timeout_ns);
+        k_peer_push<<<(unsigned)c->sm_count * 4, 256, 0, st>>>(ps.d_jobs.as<PeerJob>(), n_jobs);
+        k_peer_sync<<<1, PEER_MAX_WORLD, 0, st>>>(hp, me, W, 1u, epoch, ps.d_err.as<uint32_t>(), timeout_ns);
+    }
+    // ---- receive: headers, slice tables and per-unit counts of every source, one read-back in the common case
+    const uint32_t my_fu = first_unit_of(me), my_nu = first_unit_of(me + 1) - my_fu;
+    const uint64_t s_meta = align16(3ull * my_nu * 4), s_uoff = align16(((uint64_t)my_nu + 2) * 4);
+    uint32_t guess = std::max<uint32_t>(nsl, 1);
+    for (int attempt = 0; attempt < 2; attempt++) {
+        const size_t stride = (size_t)(PEER_META_OFF + (uint64_t)guess * s_meta);
+        TRY(pinned_reserve(&ps.h_recv, &ps.h_recv_cap, (size_t)W * stride));
+        for (uint32_t s = 0; s < W; s++) {
+            if (s == me) continue;
+            const uint8_t *reg = ps.arena + PEER_HDR_BYTES + (uint64_t)s * ps.region_bytes;
+            CU(cudaMemcpyAsync(ps.h_recv + (size_t)s * stride, reg, std::min<uint64_t>(stride, ps.region_bytes), cudaMemcpyDeviceToHost, st));
+        }
+        CU(cudaMemcpyAsync(c->h_pinned + 9, ps.d_err.p, 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        CU(cudaGetLastError());
+        if ((uint32_t)c->h_pinned[9]) {
+            CU(cudaMemset(ps.d_err.p, 0, 16));
+            return set_err(GGCAT_B200_ERR_STATE, "peer_exchange: rank %u did not answer within 20 s", (uint32_t)c->h_pinned[9] - 1);
+        }
+        uint32_t need = 0;
+        for (uint32_t s = 0; s < W; s++) {
+            if (s == me) continue;
+            const RegionHdr *rh = reinterpret_cast<const RegionHdr *>(ps.h_recv + (size_t)s * stride);
+            if (rh->epoch != epoch) return set_err(GGCAT_B200_ERR_STATE, "peer_exchange: rank %u delivered epoch %u, expected %u", s, rh->epoch, epoch);
+            if (rh->overflow) return set_err(GGCAT_B200_ERR_CAPACITY, "peer_exchange: the slices of rank %u do not fit a %llu-byte arena region; "
+                                             "give peer_init a larger arena", s, (unsigned long long)ps.region_bytes);
+            if (rh->n_units != my_nu) return set_err(GGCAT_B200_ERR_INVALID, "peer_exchange: rank %u assumes %u units for this owner, expected %u", s, rh->n_units, my_nu);
+            need = std::max(need, rh->n_slices);
+        }
+        if (need <= guess) break;
+        guess = need;
+    }
+    if (sent_overflow) return set_err(GGCAT_B200_ERR_CAPACITY, "peer_exchange: local slices do not fit a %llu-byte arena region; give peer_init a larger arena",
+                                      (unsigned long long)ps.region_bytes);
+    const size_t stride = (size_t)(PEER_META_OFF + (uint64_t)guess * s_meta);
+    CU(c->totals.reserve(8 * 8));
+    for (uint32_t s = 0; s < W; s++) {
+        if (s == me) continue;
+        const uint8_t *hr = ps.h_recv + (size_t)s * stride;
+        const RegionHdr *rh = reinterpret_cast<const RegionHdr *>(hr);
+        const PeerSlice *tb = reinterpret_cast<const PeerSlice *>(hr + PEER_TABLE_OFF);
+        uint8_t *reg = ps.arena + PEER_HDR_BYTES + (uint64_t)s * ps.region_bytes;
+        for (uint32_t j = 0; j < rh->n_slices; j++) {
+            if (tb[j].n_sk == 0) continue;
+            Chunk *ch = new Chunk();
+            ch->imported = true; ch->first_unit = my_fu; ch->n_units = my_nu; ch->word_bias = (uint32_t)tb[j].word_bias;
+            ch->d_desc = reinterpret_cast<const uint4 *>(reg + tb[j].desc_off);
+            ch->d_payload = reinterpret_cast<const uint32_t *>(reg + tb[j].pay_off);
+            const uint32_t *dm = reinterpret_cast<const uint32_t *>(reg + PEER_META_OFF + (uint64_t)j * s_meta);
+            ch->d_unit_cnt = dm; ch->d_unit_words = dm + my_nu; ch->d_unit_kmers = dm + 2 * (size_t)my_nu;
+            uint32_t *uoff = reinterpret_cast<uint32_t *>(reg + PEER_META_OFF + (uint64_t)rh->n_slices * s_meta + (uint64_t)j * s_uoff);
+            k_exclusive_scan_u32<<<1, 1024, 0, st>>>(dm, uoff, my_nu, c->totals.as<unsigned long long>() + 3);
+            ch->d_unit_off = uoff;
+            const uint32_t *hm = reinterpret_cast<const uint32_t *>(hr + PEER_META_OFF + (uint64_t)j * s_meta);
+            const size_t nu = my_nu;
+            ch->h_cnt.assign(hm, hm + nu); ch->h_cnt.push_back(0);
+            ch->h_words.assign(hm + nu, hm + 2 * nu); ch->h_words.push_back(0);
+            ch->h_kmers.assign(hm + 2 * nu, hm + 3 * nu); ch->h_kmers.push_back(0);
+            ch->h_off.resize(nu + 1); ch->h_woff.resize(nu + 1);
+            uint64_t a = 0, b = 0, km = 0;
+            for (size_t u = 0; u < nu; u++) {
+                ch->h_off[u] = (uint32_t)a; ch->h_woff[u] = (uint32_t)b;
+                a += ch->h_cnt[u]; b += ch->h_words[u]; km += ch->h_kmers[u];
+            }
+            ch->h_off[nu] = (uint32_t)a; ch->h_woff[nu] = (uint32_t)b;
+            ch->n_sk = a; ch->n_words = b; ch->n_kmers = km;
+            c->chunks.push_back(ch);
+            if (a != tb[j].n_sk || b != tb[j].n_words)
+                return set_err(GGCAT_B200_ERR_INVALID, "peer_exchange: slice %u of rank %u: unit counts sum to %llu super-k-mers / %llu words, header says %llu / %llu",
+                               j, s, (unsigned long long)a, (unsigned long long)b, (unsigned long long)tb[j].n_sk, (unsigned long long)tb[j].n_words);
+        }
+    }
+    CU(cudaGetLastError());
     return 0;
 }
 

@@ -1,0 +1,120 @@
+// peer.cuh -- the one exchange step of the sharded path, over NVLink peer memory.
+//
+// Replaces the reference's "write bucket files / read bucket files" shuffle between phase 1 and phase 2
+//   crates/minimizer_bucketing/src/lib.rs:340-351   (per-bucket writers, one file per bucket)
+//   crates/kmers_transform/src/lib.rs:294-371       (readers that feed the merge workers)
+// for a build sharded over the GPUs of one NVSwitch box: rank g owns a contiguous range of
+// first-level buckets; after phase 1 every rank PUSHES the slice of its unit-sorted bucket chunks that belongs to
+// owner d straight into d's receive arena with 16-byte stores over NVLink (the arena is cudaMalloc memory shared
+// through CUDA IPC), then raises a flag in d's arena.  No NCCL, no packing pass (chunks are unit-sorted and owners
+// hold contiguous unit ranges, so a slice is a plain sub-array), no host round trip on the sender.
+//
+// Arena of rank X:   [PeerHdr 4 KiB] [region 0] ... [region world-1]      (region s is written by rank s only)
+// Region:            [RegionHdr 64 B] [PeerSlice table] [meta slots] [unit-offset slots] [descriptors / payload ...]
+// Flow control, all stream-ordered device code (k_peer_sync):
+//   released[d] on rank X = last epoch whose data rank d has finished merging  -> X may overwrite its region on d
+//   ready[s]    on rank X = last epoch whose push from rank s is complete      -> X may merge
+#pragma once
+#include "device_utils.cuh"
+
+namespace ggb {
+
+constexpr int PEER_MAX_WORLD = 64;
+constexpr int PEER_MAX_SLICES = 64;                 // local chunks (pushes) one exchange can route
+constexpr uint64_t PEER_HDR_BYTES = 4096;
+constexpr uint64_t PEER_TABLE_OFF = 64;
+constexpr uint64_t PEER_META_OFF = PEER_TABLE_OFF + (uint64_t)PEER_MAX_SLICES * 64;
+
+struct PeerHdr {
+    uint32_t ready[PEER_MAX_WORLD];
+    uint32_t released[PEER_MAX_WORLD];
+};
+
+struct RegionHdr {           // 64 bytes, written by the sender
+    uint32_t n_slices;
+    uint32_t overflow;       // 1 = the sender's slices did not fit the region: nothing was delivered
+    uint32_t n_units;        // units of the destination (sanity check)
+    uint32_t epoch;
+    uint32_t pad[12];
+};
+
+struct PeerSlice {           // 64 bytes: one local chunk's slice for this destination
+    uint64_t n_sk, n_words, word_bias;
+    uint64_t desc_off, pay_off;      // byte offsets from the region base
+    uint64_t pad[3];
+};
+
+struct PeerJob { const uint8_t *src; uint8_t *dst; uint64_t bytes; };   // 4-byte aligned, bytes % 4 == 0
+
+struct PeerHdrPtrs { PeerHdr *h[PEER_MAX_WORLD]; };
+
+__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// k_peer_push: bulk copies into peer memory.  Jobs whose source and destination agree modulo 16 move as uint4
+// (4 independent 16-byte loads in flight per thread, 512 contiguous bytes per warp store); the rest as u32.
+__global__ void __launch_bounds__(256) k_peer_push(const PeerJob *__restrict__ jobs, uint32_t n_jobs) {
+    const uint64_t gtid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t gsz = (uint64_t)gridDim.x * blockDim.x;
+    for (uint32_t j = 0; j < n_jobs; j++) {
+        const PeerJob job = jobs[j];
+        if (job.bytes == 0) continue;
+        const uintptr_t sa = (uintptr_t)job.src, da = (uintptr_t)job.dst;
+        if (((sa ^ da) & 15u) == 0) {
+            uint64_t head = (16u - (sa & 15u)) & 15u;
+            if (head > job.bytes) head = job.bytes;
+            const uint64_t nvec = (job.bytes - head) >> 4;
+            const uint64_t tail0 = head + (nvec << 4);
+            const uint4 *s4 = reinterpret_cast<const uint4 *>(job.src + head);
+            uint4 *d4 = reinterpret_cast<uint4 *>(job.dst + head);
+            uint64_t i = gtid;
+            for (; i + 3 * gsz < nvec; i += 4 * gsz) {
+                const uint4 a = __ldcs(s4 + i), b = __ldcs(s4 + i + gsz), c = __ldcs(s4 + i + 2 * gsz), d = __ldcs(s4 + i + 3 * gsz);
+                d4[i] = a; d4[i + gsz] = b; d4[i + 2 * gsz] = c; d4[i + 3 * gsz] = d;
+            }
+            for (; i < nvec; i += gsz) d4[i] = __ldcs(s4 + i);
+            if (blockIdx.x == 0) {
+                const uint32_t *s1 = reinterpret_cast<const uint32_t *>(job.src);
+                uint32_t *d1 = reinterpret_cast<uint32_t *>(job.dst);
+                for (uint64_t q = threadIdx.x; q < (head >> 2); q += blockDim.x) d1[q] = s1[q];
+                for (uint64_t q = (tail0 >> 2) + threadIdx.x; q < (job.bytes >> 2); q += blockDim.x) d1[q] = s1[q];
+            }
+        } else {
+            const uint32_t *s1 = reinterpret_cast<const uint32_t *>(job.src);
+            uint32_t *d1 = reinterpret_cast<uint32_t *>(job.dst);
+            for (uint64_t q = gtid; q < (job.bytes >> 2); q += gsz) d1[q] = s1[q];
+        }
+    }
+    __threadfence_system();
+}
+
+// k_peer_sync: thread t talks to rank t.  Stores `value` into this rank's slot of rank t's flag array (ready or
+// released), then waits until rank t's slot of the LOCAL flag array reaches `value`.  Bounded spin: on timeout
+// *err is set and the host reports GGCAT_B200_ERR_STATE instead of hanging.
+__global__ void k_peer_sync(PeerHdrPtrs peers, uint32_t me, uint32_t world, uint32_t which, uint32_t value, uint32_t *err,
+                            unsigned long long timeout_ns) {
+    const uint32_t t = threadIdx.x;
+    if (t >= world || t == me) return;
+    __threadfence_system();
+    uint32_t *theirs = which ? &peers.h[t]->ready[me] : &peers.h[t]->released[me];
+    st_release_sys(theirs, value);
+    const uint32_t *mine = which ? &peers.h[me]->ready[t] : &peers.h[me]->released[t];
+    const unsigned long long t0 = global_timer_ns();
+    while ((int32_t)(ld_acquire_sys(mine) - value) < 0) {
+        __nanosleep(200);
+        if (global_timer_ns() - t0 > timeout_ns) { atomicExch(err, 1u + t); return; }
+    }
+}
+
+}  // namespace ggb

@@ -195,10 +195,32 @@ def _host_u32(ptr: int, n: int) -> np.ndarray:
     return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint32)), shape=(n,))
 
 
+def peer_setup(ctx, rank: int, world: int, arena_bytes: int, group=None):
+    """Collective, once per context: allocate the NVLink receive arena (ggcat_b200_peer_init), all-gather the
+    64-byte CUDA IPC handles with torch.distributed and map every peer's arena (ggcat_b200_peer_connect).
+    Afterwards exchange_and_import() is one library call (copy kernel over peer memory, no NCCL)."""
+    handle = ctx.peer_init(rank, world, arena_bytes)
+    if world == 1:
+        ctx.peer_connect([handle])
+        return
+    dev = torch.device("cuda", ctx.params.device) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    mine = torch.frombuffer(bytearray(handle), dtype=torch.uint8).to(dev)
+    allh = torch.empty(64 * world, dtype=torch.uint8, device=dev)
+    dist.all_gather_into_tensor(allh, mine, group=group)
+    raw = allh.cpu().numpy().tobytes()
+    ctx.peer_connect([raw[64 * r:64 * (r + 1)] for r in range(world)])
+    dist.barrier(group=group)  # every arena is mapped everywhere before the first push
+
+
 def exchange_and_import(ctx, owner: OwnerMap, rank: int, world: int, stream: Optional[torch.cuda.Stream] = None, group=None):
     """GPU path: route every local chunk of `ctx` to the bucket owners and register what arrives.
-    Must be called after ctx.finish_bucketing() (which synchronises the library stream)."""
+    Must be called after ctx.finish_bucketing() (which synchronises the library stream).
+    With a connected peer arena (peer_setup) this is ggcat_b200_peer_exchange; otherwise the NCCL all-to-all."""
     from . import _lib  # noqa: F401
+
+    if getattr(ctx, "peer_connected", False):
+        ctx.peer_exchange()
+        return []
 
     dev = torch.device("cuda", ctx.params.device)
     n_units_total = ((1 << owner.b1) + 1) << owner.b2

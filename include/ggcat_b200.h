@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define GGCAT_B200_ABI_VERSION 2
+#define GGCAT_B200_ABI_VERSION 3
 
 typedef enum {
     GGCAT_B200_OK = 0,
@@ -179,6 +179,28 @@ int32_t ggcat_b200_import_chunk_slice(ggcat_b200_ctx *ctx, uint32_t first_unit, 
                                       const ggcat_b200_chunk_slice *slice);
 /* Forget the chunks produced locally by push_reads (after they were exported) but keep imports. */
 int32_t ggcat_b200_drop_local_chunks(ggcat_b200_ctx *ctx);
+
+/* ---- multi-GPU exchange over NVLink peer memory (one process per GPU, one NVSwitch box) --------------
+ * The sharded build's only exchange: the reference writes per-bucket temp files in phase 1
+ * (crates/minimizer_bucketing/src/lib.rs:340-351) and reads them back in phase 2
+ * (crates/kmers_transform/src/lib.rs:294-371); here rank r owns the contiguous bucket range
+ * ggcat_b200_owner_range(r) (the duplicates bucket goes to the last rank) and every rank pushes the slices of its
+ * bucket chunks straight into the owners' receive arenas with a copy kernel (CUDA IPC mapping, 16-byte stores over
+ * NVLink, device-side ready/released flags; ggcat_b200/csrc/peer.cuh).  Protocol, collective over all ranks:
+ *   peer_init (allocates the arena, returns its IPC handle)  ->  the host all-gathers the 64-byte handles with
+ *   any transport  ->  peer_connect(handles in rank order)  ->  per build: push_reads*, finish_bucketing,
+ *   peer_exchange, merge_bucket_range[_device](owner range).
+ * arena_bytes is split evenly into one region per source rank; a region must hold that rank's descriptors
+ * (16 B per super-k-mer) + payload + per-unit counts for this owner (GGCAT_B200_ERR_CAPACITY otherwise). */
+typedef struct { uint8_t bytes[64]; } ggcat_b200_peer_handle;
+int32_t ggcat_b200_owner_range(uint32_t buckets_count_log, uint32_t rank, uint32_t world, uint32_t *first_bucket,
+                               uint32_t *n_buckets);
+int32_t ggcat_b200_peer_init(ggcat_b200_ctx *ctx, uint32_t rank, uint32_t world, uint64_t arena_bytes,
+                             ggcat_b200_peer_handle *out_handle);
+int32_t ggcat_b200_peer_connect(ggcat_b200_ctx *ctx, const ggcat_b200_peer_handle *handles);
+/* After finish_bucketing on every rank.  Local chunks stay registered (the owner's own units are merged in
+ * place); the slices received from the other ranks are registered as imported chunks living in the arena. */
+int32_t ggcat_b200_peer_exchange(ggcat_b200_ctx *ctx);
 
 /* ---- measurement hooks ------------------------------------------------------------------------- */
 /* Per-kernel-family CUDA-event timing on/off (off by default: two event records per launch). */

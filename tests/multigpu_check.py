@@ -28,9 +28,17 @@ def main():
     data, offsets = slices[rank]
     ctx = G.GGCATB200(G.Params(k=k, m=m, min_multiplicity=s, buckets_count_log=b1, second_buckets_count_log=b2, device=lr))
     owner = gdist.OwnerMap(b1, b2, world)
-    for it in range(2):  # twice: exercises reset + buffer recycling with imported chunks
+    transport = os.environ.get("GGCAT_B200_EXCHANGE", "peer")
+    if transport == "peer":
+        gdist.peer_setup(ctx, rank, world, arena_bytes=64 << 20)
+    half = offsets.size // 2
+    for it in range(3):  # several rounds: reset + buffer recycling with imported chunks, arena reuse (flow control)
         ctx.reset()
-        ctx.push_reads(data, offsets)
+        if it == 1:      # two pushes -> two local chunks -> two slices per destination
+            ctx.push_reads(data[: int(offsets[half])], offsets[: half + 1])
+            ctx.push_reads(data[int(offsets[half]):], offsets[half:] - offsets[half])
+        else:
+            ctx.push_reads(data, offsets)
         ctx.finish_bucketing()
         gdist.exchange_and_import(ctx, owner, rank, world)
         fb, nb = owner.bucket_range(rank)
@@ -51,7 +59,7 @@ def main():
     t = torch.tensor([checked], device="cuda")
     dist.all_reduce(t)
     if rank == 0:
-        print(f"multigpu_check ok: world={world} entries checked={int(t.item())}")
+        print(f"multigpu_check ok: world={world} transport={transport} entries checked={int(t.item())}")
     ctx.close()
     dist.destroy_process_group()
 

@@ -29,7 +29,7 @@ def test_header_symbols_exported(lib):
     assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/ggcat_b200.h but not exported"
-    assert lib.ggcat_b200_abi_version() == 2
+    assert lib.ggcat_b200_abi_version() == 3
 
 
 def test_struct_layouts():
@@ -67,3 +67,23 @@ def test_product_never_imports_oracle():
     for p in (ROOT / "ggcat_b200").rglob("*"):
         if p.suffix in (".py", ".cu", ".cuh", ".h"):
             assert "oracle" not in p.read_text().replace("no oracle", ""), f"{p} references the oracle"
+
+
+def test_owner_range_matches_owner_map(lib):
+    """ggcat_b200_owner_range (the C side of the peer exchange) and dist.OwnerMap (the NCCL/gloo side) agree."""
+    from ggcat_b200.dist import OwnerMap
+
+    for b1 in (2, 5, 9, 10, 13):
+        for world in (1, 2, 3, 4, 8):
+            if world > (1 << b1):
+                continue
+            om = OwnerMap(b1, 6, world)
+            covered = 0
+            for r in range(world):
+                fb, nb = C.c_uint32(0), C.c_uint32(0)
+                assert lib.ggcat_b200_owner_range(b1, r, world, C.byref(fb), C.byref(nb)) == 0
+                assert (fb.value, nb.value) == om.bucket_range(r)
+                covered += nb.value
+            assert covered == (1 << b1) + 1
+    assert lib.ggcat_b200_owner_range(2, 0, 8, None, None) < 0     # more ranks than buckets
+    assert lib.ggcat_b200_owner_range(5, 4, 4, None, None) < 0     # rank out of range
