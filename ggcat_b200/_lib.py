@@ -78,6 +78,7 @@ SYMBOLS = {
     "ggcat_b200_peer_init": (_i32, [_vp, _u32, _u32, _u64, _vp]),
     "ggcat_b200_peer_connect": (_i32, [_vp, _vp]),
     "ggcat_b200_peer_exchange": (_i32, [_vp]),
+    "ggcat_b200_peer_stats": (_i32, [_vp, _vp, _vp]),
     "ggcat_b200_stream": (_vp, [_vp]),
     "ggcat_b200_synchronize": (_i32, [_vp]),
     "ggcat_b200_set_timing": (_i32, [_vp, _i32]),

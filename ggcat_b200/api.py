@@ -278,6 +278,12 @@ class GGCATB200:
     def peer_exchange(self):
         _check(self._lib.ggcat_b200_peer_exchange(self._h))
 
+    def peer_stats(self) -> tuple[int, int]:
+        """(bytes pushed to the other owners, bytes received) in the last peer_exchange."""
+        a, b = C.c_uint64(0), C.c_uint64(0)
+        _check(self._lib.ggcat_b200_peer_stats(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     # -- measurement
     @property
     def stream_ptr(self) -> int:

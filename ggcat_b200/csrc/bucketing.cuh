@@ -129,9 +129,12 @@ __global__ void __launch_bounds__(WIN_THREADS)
 k_windows(const uint32_t *__restrict__ pk, const uint32_t *__restrict__ bad, const uint32_t *__restrict__ brk,
           uint32_t n /* bases in batch */, DevParams P, uint64_t *__restrict__ ent, uint32_t *__restrict__ tile_cnt,
           uint32_t *__restrict__ tile_scnt) {
-    __shared__ uint32_t s_pk[(WIN_T + 2 * WIN_WMAX + 64) / 16 + 4];
-    __shared__ uint32_t s_bad[(WIN_T + 2 * WIN_WMAX + 64) / 32 + 6];
-    __shared__ uint32_t s_cmb[(WIN_T + 2 * WIN_WMAX + 64) / 32 + 6];   // bad | record-start
+    // TMA landing buffers (16-byte aligned; the tile's first word sits at offset (W0 & 3) / (BW0 & 3) because the
+    // bulk copy starts at the 16-byte boundary below it)
+    __shared__ __align__(16) uint32_t s_pk_raw[(WIN_T + 2 * WIN_WMAX + 64) / 16 + 12];
+    __shared__ __align__(16) uint32_t s_bad_raw[(WIN_T + 2 * WIN_WMAX + 64) / 32 + 12];
+    __shared__ __align__(16) uint32_t s_cmb_raw[(WIN_T + 2 * WIN_WMAX + 64) / 32 + 12];   // record starts, then bad | record-start
+    __shared__ __align__(8) uint64_t s_bar;
     // m-mer values and window minima: element x lives at PADX(x) = x + x/8, so that the 8-windows-per-thread phase
     // (lane stride 8 elements) touches every 8-byte bank pair twice per warp instead of sixteen times
     __shared__ uint64_t s_v0[PADX(WIN_NI + 16) + 1];
@@ -156,7 +159,17 @@ k_windows(const uint32_t *__restrict__ pk, const uint32_t *__restrict__ bad, con
     const uint32_t n_pkw = ((last_base + 15) >> 4) - W0 + 2;
     const uint32_t n_bmw = ((last_base + 31) >> 5) - BW0 + 3;
 
-    // ---- A
+    // ---- A: one elected thread issues three TMA bulk copies (packed bases, bad bitmap, record-start bitmap) that
+    //         land while the other threads build the hash tables
+    uint32_t *s_pk = s_pk_raw + (W0 & 3u), *s_bad = s_bad_raw + (BW0 & 3u), *s_cmb = s_cmb_raw + (BW0 & 3u);
+    const uint32_t pk_words = (n_pkw + (W0 & 3u) + 3u) & ~3u, bm_words = (n_bmw + (BW0 & 3u) + 3u) & ~3u;
+    if (tid == 0) {
+        mbar_init(&s_bar, 1);
+        mbar_expect_tx(&s_bar, (pk_words + 2 * bm_words) * 4);
+        tma_load_1d(s_pk_raw, pk + (W0 & ~3u), pk_words * 4, &s_bar);
+        tma_load_1d(s_bad_raw, bad + (BW0 & ~3u), bm_words * 4, &s_bar);
+        tma_load_1d(s_cmb_raw, brk + (BW0 & ~3u), bm_words * 4, &s_bar);
+    }
     if (tid < 16) {
         // cn_nthash.rs:43-57 roll_hash with both table terms folded:
         //   fw' = rotl(fw,1) ^ rotl(h(out), m) ^ h(in)          rc' = rotr(rc ^ r(out), 1) ^ rotl(r(in), m-1)
@@ -169,8 +182,9 @@ k_windows(const uint32_t *__restrict__ pk, const uint32_t *__restrict__ bad, con
         s_TF[i][c] = rotl64(nt_h(c), m - 1 - i);
         s_TR[i][c] = rotl64(nt_r(c), i);
     }
-    for (uint32_t i = tid; i < n_pkw; i += WIN_THREADS) s_pk[i] = pk[W0 + i];
-    for (uint32_t i = tid; i < n_bmw; i += WIN_THREADS) { const uint32_t b = bad[BW0 + i]; s_bad[i] = b; s_cmb[i] = b | brk[BW0 + i]; }
+    __syncthreads();          // barrier initialised (and tables written) before anyone polls it
+    mbar_wait(&s_bar, 0);
+    for (uint32_t i = tid; i < bm_words; i += WIN_THREADS) s_cmb_raw[i] |= s_bad_raw[i];
     __syncthreads();
 
     // ---- B: m-mer hashes by rolling, IPT consecutive items per thread, bases kept in two 64-bit shift registers

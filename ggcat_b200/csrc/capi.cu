@@ -66,9 +66,13 @@ struct Chunk {
     uint32_t first_unit = 0, n_units = 0, word_bias = 0;
     uint64_t n_sk = 0, n_words = 0, n_kmers = 0, n_bases = 0;
     std::vector<uint32_t> h_cnt, h_off, h_words, h_woff, h_kmers;  // host mirrors (after finish / import)
+    uint32_t *h_pin = nullptr; size_t h_pin_cap = 0;   // pinned landing area of the per-unit counts (cnt | words | kmers),
+    bool mirror_queued = false;                        // filled by copies queued right behind k_scatter
     void release() {
         desc.release(); payload.release(); unit_cnt.release(); unit_off.release(); unit_words.release();
         unit_woff.release(); unit_kmers.release();
+        if (h_pin) cudaFreeHost(h_pin);
+        h_pin = nullptr; h_pin_cap = 0;
     }
 };
 
@@ -111,6 +115,7 @@ struct PeerState {
     DevBuf d_jobs, d_stage, d_err;
     uint8_t *h_stage = nullptr; size_t h_stage_cap = 0;   // pinned: region headers + slice tables being sent, then the jobs
     uint8_t *h_recv = nullptr; size_t h_recv_cap = 0;     // pinned: received headers, tables and per-unit counts
+    uint64_t last_sent = 0, last_received = 0;            // payload + descriptor + metadata bytes of the last exchange
 };
 
 }  // namespace
@@ -250,7 +255,7 @@ int32_t bucket_batch_device(ggcat_b200_ctx *c, const uint8_t *d_data, const uint
     if (!c->chunk_pool.empty()) { ch = c->chunk_pool.back(); c->chunk_pool.pop_back(); }
     else ch = new Chunk();
     c->chunks.push_back(ch);
-    ch->imported = false; ch->word_bias = 0;
+    ch->imported = false; ch->word_bias = 0; ch->mirror_queued = false;
     ch->h_cnt.clear(); ch->h_off.clear(); ch->h_words.clear(); ch->h_woff.clear(); ch->h_kmers.clear();
     ch->first_unit = 0; ch->n_units = P.n_units; ch->n_sk = n_sk; ch->n_bases = n;
     const size_t ub = ((size_t)P.n_units + 2) * 4;
@@ -294,6 +299,20 @@ int32_t bucket_batch_device(ggcat_b200_ctx *c, const uint8_t *d_data, const uint
     ch->d_unit_cnt = ch->unit_cnt.as<uint32_t>(); ch->d_unit_off = ch->unit_off.as<uint32_t>();
     ch->d_unit_words = ch->unit_words.as<uint32_t>(); ch->d_unit_woff = ch->unit_woff.as<uint32_t>();
     ch->d_unit_kmers = ch->unit_kmers.as<uint32_t>();
+    // host mirror of the per-unit counts: queued here so that finish_bucketing only has to wait for the stream
+    {
+        const size_t nu = P.n_units;
+        if (ch->h_pin_cap < 3 * nu) {
+            if (ch->h_pin) cudaFreeHost(ch->h_pin);
+            ch->h_pin = nullptr; ch->h_pin_cap = 0;
+            CU(cudaHostAlloc(reinterpret_cast<void **>(&ch->h_pin), 3 * nu * 4, cudaHostAllocDefault));
+            ch->h_pin_cap = 3 * nu;
+        }
+        CU(cudaMemcpyAsync(ch->h_pin, ch->d_unit_cnt, nu * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(ch->h_pin + nu, ch->d_unit_words, nu * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(ch->h_pin + 2 * nu, ch->d_unit_kmers, nu * 4, cudaMemcpyDeviceToHost, st));
+        ch->mirror_queued = true;
+    }
     CU(cudaGetLastError());
     return 0;
 }
@@ -303,10 +322,17 @@ int32_t mirror_chunk(ggcat_b200_ctx *c, Chunk *ch) {
     const size_t nu = ch->n_units;
     ch->h_cnt.resize(nu + 1); ch->h_off.resize(nu + 1); ch->h_words.resize(nu + 1); ch->h_woff.resize(nu + 1);
     ch->h_kmers.resize(nu + 1);
-    CU(cudaMemcpyAsync(ch->h_cnt.data(), ch->d_unit_cnt, nu * 4, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaMemcpyAsync(ch->h_words.data(), ch->d_unit_words, nu * 4, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaMemcpyAsync(ch->h_kmers.data(), ch->d_unit_kmers, nu * 4, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
+    if (ch->mirror_queued && ch->h_pin && !ch->imported) {
+        CU(cudaStreamSynchronize(c->stream));   // no-op after finish_bucketing's own synchronisation
+        memcpy(ch->h_cnt.data(), ch->h_pin, nu * 4);
+        memcpy(ch->h_words.data(), ch->h_pin + nu, nu * 4);
+        memcpy(ch->h_kmers.data(), ch->h_pin + 2 * nu, nu * 4);
+    } else {
+        CU(cudaMemcpyAsync(ch->h_cnt.data(), ch->d_unit_cnt, nu * 4, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(ch->h_words.data(), ch->d_unit_words, nu * 4, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(ch->h_kmers.data(), ch->d_unit_kmers, nu * 4, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+    }
     uint64_t a = 0, b = 0, km = 0;
     for (size_t u = 0; u < nu; u++) {
         ch->h_off[u] = (uint32_t)a; ch->h_woff[u] = (uint32_t)b;
@@ -411,7 +437,7 @@ int32_t merge_range_device(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_
     for (auto &pr : large) work[2].push_back(pr.second);
     struct Tier { const uint32_t *wl; size_t count; const uint32_t *count_dev; uint64_t per_cta; unsigned grid; };
     auto make_tier = [&](const uint32_t *wl, size_t count, const uint32_t *count_dev, uint64_t nmax) {
-        const uint64_t per_cta = (uint64_t)hash_table_slots((uint32_t)nmax) * 3 / 2 + 16;  // keys + counters; >= 2n for the sort variant
+        const uint64_t per_cta = std::max<uint64_t>((uint64_t)hash_table_slots((uint32_t)nmax) * 3 / 2, 2 * nmax) + 16;  // table keys + counters, or 2n records for the sort variant
         const uint64_t budget = 12ull << 30;
         const uint64_t g = std::min<uint64_t>(std::min<uint64_t>(count, (uint64_t)c->sm_count * 2), std::max<uint64_t>(1, budget / (per_cta * 8)));
         return Tier{wl, count, count_dev, per_cta, (unsigned)g};
@@ -642,7 +668,7 @@ int32_t launch_hash128(ggcat_b200_ctx *c, const ChunkView *dv, uint32_t nch, std
         const size_t first = tr == 0 ? 0 : n_giant, count = tr == 0 ? n_giant : large.size() - n_giant;
         if (!count) continue;
         const uint64_t nmax = large[first].first;
-        uint64_t per_cta = ((uint64_t)hash_table_slots((uint32_t)nmax) * 20 + 15) / 16 * 2 + 2;  // u64 words, 16-byte multiple
+        uint64_t per_cta = ((uint64_t)hash_table_slots_pow2((uint32_t)nmax) * 20 + 15) / 16 * 2 + 2;  // u64 words, 16-byte multiple
         const uint64_t budget = 12ull << 30;
         const uint64_t g = std::min<uint64_t>(std::min<uint64_t>(count, (uint64_t)c->sm_count * 2), std::max<uint64_t>(1, budget / (per_cta * 8)));
         CU(c->d_scratch.reserve(per_cta * g * 8));
@@ -1391,6 +1417,7 @@ int32_t ggcat_b200_peer_exchange(ggcat_b200_ctx *c) {
     PeerJob *jobs = reinterpret_cast<PeerJob *>(ps.h_stage + (size_t)W * tbl);
     uint32_t n_jobs = 0;
     bool sent_overflow = false;
+    ps.last_sent = ps.last_received = 0;
     for (uint32_t d = 0; d < W; d++) {
         if (d == me) continue;
         const uint32_t fu = first_unit_of(d), nu = first_unit_of(d + 1) - fu;
@@ -1426,6 +1453,7 @@ int32_t ggcat_b200_peer_exchange(ggcat_b200_ctx *c) {
         }
         jobs[n_jobs++] = {ps.d_stage.as<uint8_t>() + (size_t)d * tbl, dst, (uint64_t)(PEER_TABLE_OFF + (uint64_t)nsl * 64)};
     }
+    for (uint32_t j = 0; j < n_jobs; j++) ps.last_sent += jobs[j].bytes;
     CU(cudaMemcpyAsync(ps.d_stage.p, ps.h_stage, (size_t)W * tbl, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(ps.d_jobs.p, jobs, (size_t)n_jobs * sizeof(PeerJob), cudaMemcpyHostToDevice, st));
     PeerHdrPtrs hp;
@@ -1505,6 +1533,7 @@ int32_t ggcat_b200_peer_exchange(ggcat_b200_ctx *c) {
             }
             ch->h_off[nu] = (uint32_t)a; ch->h_woff[nu] = (uint32_t)b;
             ch->n_sk = a; ch->n_words = b; ch->n_kmers = km;
+            ps.last_received += a * 16 + b * 4 + 3ull * nu * 4;
             c->chunks.push_back(ch);
             if (a != tb[j].n_sk || b != tb[j].n_words)
                 return set_err(GGCAT_B200_ERR_INVALID, "peer_exchange: slice %u of rank %u: unit counts sum to %llu super-k-mers / %llu words, header says %llu / %llu",
@@ -1512,6 +1541,13 @@ int32_t ggcat_b200_peer_exchange(ggcat_b200_ctx *c) {
         }
     }
     CU(cudaGetLastError());
+    return 0;
+}
+
+int32_t ggcat_b200_peer_stats(ggcat_b200_ctx *c, uint64_t *bytes_sent, uint64_t *bytes_received) {
+    TRY(check_ctx(c));
+    if (bytes_sent) *bytes_sent = c->peer.last_sent;
+    if (bytes_received) *bytes_received = c->peer.last_received;
     return 0;
 }
 

@@ -293,120 +293,110 @@ k_merge_units(const ChunkView *__restrict__ chunks, uint32_t n_chunks, const uin
 // sort cost scales with the table that leaves the GPU, not with the k-mer occurrences.
 constexpr uint64_t HASH_EMPTY = ~0ull;
 
-__device__ __forceinline__ void hash_insert(uint64_t *K, uint32_t *C, uint32_t mask, uint64_t key, uint32_t fb) {
-    uint32_t slot = (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> 33) & mask;
+// Slot of a key in a table of TS slots (any size, not only powers of two): multiply-shift on the high hash bits.
+__device__ __forceinline__ uint32_t hash_slot(uint64_t key, uint32_t TS) {
+    return __umulhi((uint32_t)((key * 0x9E3779B97F4A7C15ull) >> 32), TS);
+}
+
+// The counter word holds (occurrences - 1): the thread that claims a slot does not add its own occurrence, so a
+// distinct k-mer costs one CAS and every further occurrence one atomicAdd (shared-memory atomics are the kernel's
+// bound: ~2 cycles per lane).  Flag bits are OR-ed only when they are not set yet.
+__device__ __forceinline__ void hash_insert(uint64_t *K, uint32_t *C, uint32_t TS, uint64_t key, uint32_t fb) {
+    uint32_t slot = hash_slot(key, TS);
+    bool claimed = false;
     while (true) {
         // most occurrences hit a key that is already there (coverage): look before the CAS
         const uint64_t cur = *reinterpret_cast<volatile uint64_t *>(&K[slot]);
         if (cur == key) break;
         if (cur == HASH_EMPTY) {
             const unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long *>(&K[slot]), HASH_EMPTY, key);
-            if (old == HASH_EMPTY || old == key) break;
+            if (old == HASH_EMPTY) { claimed = true; break; }
+            if (old == key) break;
         }
-        slot = (slot + 1) & mask;
+        slot = slot + 1 == TS ? 0u : slot + 1;
     }
-    atomicAdd(&C[slot], 1u);
-    if (fb) atomicOr(&C[slot], fb << 30);
+    if (!claimed) atomicAdd(&C[slot], 1u);
+    if (fb && ((*reinterpret_cast<volatile uint32_t *>(&C[slot]) >> 30) & fb) != fb) atomicOr(&C[slot], fb << 30);
 }
+__device__ __forceinline__ uint32_t slot_count(uint32_t cc) { return (cc & 0x3FFFFFFFu) + 1u; }   // occurrences of an occupied slot
 
 // ---- load-balanced expansion of a unit ---------------------------------------------------------------------------
-// The k-mer records of a unit are numbered 0..n over all its super-k-mers (all chunks); every thread takes `rpt`
-// CONSECUTIVE records: one binary search in the staged prefix sums finds its first (super-k-mer, offset), the first
-// k-mer is extracted at an arbitrary bit offset, the rest roll (cn_seqhash_base.rs:52-69) and step into the next
-// super-k-mer when one ends.  Work per thread is equal whatever the super-k-mer lengths are.
-constexpr int UNIT_MAXC = 32;   // chunks gathered per group
-constexpr int UNIT_DCAP = 512;  // descriptors staged per round
-
-struct UnitStage {                       // lives in the kernel's scratch area while records are inserted
-    const uint32_t *ptr[UNIT_DCAP];      // payload of the super-k-mer
-    uint32_t start[UNIT_DCAP + 1];       // first record number (exclusive prefix of k-mer counts)
-    uint32_t lenfl[UNIT_DCAP];           // len | flags << 30
-    uint32_t c_d0[UNIT_MAXC], c_cnt[UNIT_MAXC];
-};
-
+// Warp-parallel, barrier-free: a warp takes 32 consecutive descriptors (one per lane, one coalesced 512-byte load),
+// numbers their k-mer records 0..T with a warp scan and then walks the records 32 at a time, ONE RECORD PER LANE:
+//   owner super-k-mer of record r  = number of super-k-mers starting at or before r  (warp-wide OR of the start bits
+//                                    that fall in the current window of 32 records + popc), fetched by shuffle;
+//   k-mer at offset i of the owner = 64 bits extracted at bit 2i of its payload (three cached word loads), canonical
+//                                    form by one bit-reversal (cn_seqhash_base.rs:27-69 evaluated directly, no rolling).
+// Every lane does the same work whatever the super-k-mer lengths are: no divergence, no binary search, no block
+// barrier between the table clear and the table scan.
 template <int THREADS, typename Emit>
 __device__ __forceinline__ void unit_for_each_kmer64(const ChunkView *__restrict__ chunks, uint32_t n_chunks, uint32_t unit,
-                                                     uint32_t k, uint32_t forward_only, UnitStage *S, uint32_t *s_scan,
-                                                     Emit emit) {
-    static_assert(THREADS >= UNIT_DCAP, "one staged descriptor per thread");
-    const uint32_t tid = threadIdx.x;
+                                                     uint32_t k, uint32_t forward_only, Emit emit) {
+    constexpr uint32_t WARPS = THREADS / 32;
+    const uint32_t lane = lane_id(), warp = warp_id();
     const uint64_t mask = (1ull << (2 * k)) - 1ull;
-    for (uint32_t c0 = 0; c0 < n_chunks; c0 += UNIT_MAXC) {
-        const uint32_t nc = min((uint32_t)UNIT_MAXC, n_chunks - c0);
-        if (tid < nc) {
-            const ChunkView &cv = chunks[c0 + tid];
-            uint32_t d0 = 0, d1 = 0;
-            if (unit >= cv.first_unit && unit < cv.first_unit + cv.n_units) {
-                d0 = cv.unit_off[unit - cv.first_unit]; d1 = cv.unit_off[unit - cv.first_unit + 1];
-            }
-            S->c_d0[tid] = d0; S->c_cnt[tid] = d1 - d0;
-        }
-        __syncthreads();
-        uint32_t dtot = 0;
-        for (uint32_t c = 0; c < nc; c++) dtot += S->c_cnt[c];
-        for (uint32_t g0 = 0; g0 < dtot; g0 += UNIT_DCAP) {
-            const uint32_t dr = min((uint32_t)UNIT_DCAP, dtot - g0);
-            uint32_t cnt = 0;
-            if (tid < dr) {
-                uint32_t g = g0 + tid, c = 0;
-                while (g >= S->c_cnt[c]) { g -= S->c_cnt[c]; ++c; }
-                const ChunkView &cv = chunks[c0 + c];
-                const uint4 d = cv.desc[S->c_d0[c] + g];
-                S->ptr[tid] = cv.payload + (d.x - cv.word_bias);
-                S->lenfl[tid] = d.y | (((d.z >> 16) & 3u) << 30);
+    const uint32_t le_mask = 0xFFFFFFFFu >> (31u - lane);
+    uint32_t gbase = 0;   // descriptor groups handed out so far: groups go to warps round-robin ACROSS chunks
+    for (uint32_t c = 0; c < n_chunks; c++) {
+        const ChunkView &cv = chunks[c];
+        const uint32_t fu = cv.first_unit;
+        if (unit < fu || unit >= fu + cv.n_units) continue;
+        const uint32_t d0 = cv.unit_off[unit - fu], d1 = cv.unit_off[unit - fu + 1];
+        const uint4 *__restrict__ desc = cv.desc;
+        const uint32_t *__restrict__ payload = cv.payload;
+        const uint32_t bias = cv.word_bias;
+        const uint32_t first = (warp + WARPS - gbase % WARPS) % WARPS;
+        gbase += (d1 - d0 + 31u) >> 5;
+        for (uint32_t g = d0 + first * 32u; g < d1; g += WARPS * 32u) {
+            const uint32_t di = g + lane;
+            const bool valid = di < d1;
+            uint32_t woff = 0, lf = 0, cnt = 0;
+            if (valid) {
+                const uint4 d = desc[di];
+                woff = d.x - bias;
+                lf = d.y | (((d.z >> 16) & 3u) << 30);
                 cnt = d.y - k + 1;
             }
-            uint32_t tot;
-            const uint32_t p = block_exclusive_scan<THREADS>(cnt, s_scan, &tot);
-            if (tid < dr) S->start[tid] = p;
-            if (tid == 0) S->start[dr] = tot;
-            __syncthreads();
-            const uint32_t rpt = min(16u, max(1u, (tot + THREADS - 1) / THREADS));
-            for (uint32_t base = tid * rpt; base < tot; base += THREADS * rpt) {
-                uint32_t r = base;
-                const uint32_t rend = min(tot, base + rpt);
-                uint32_t lo = 0, hi = dr - 1;
-                while (lo < hi) {
-                    const uint32_t mid = (lo + hi + 1) >> 1;
-                    if (S->start[mid] <= r) lo = mid; else hi = mid - 1;
-                }
-                uint32_t j = lo, i = r - S->start[j];
-                const uint32_t *pl = S->ptr[j];
-                uint32_t lf = S->lenfl[j];
-                uint32_t last = (lf & 0x3FFFFFFFu) - k, flags = lf >> 30;
-                uint64_t fw = extract64(pl, 2ull * i) & mask;
-                uint64_t rc = revcomp64(fw) >> (64 - 2 * k);
-                uint32_t cw = i < last ? pl[(i + k) >> 4] : 0u;
-                while (true) {
+            uint32_t incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= (uint32_t)o) incl += y;
+            }
+            const uint32_t excl = incl - cnt;
+            const uint32_t T = __shfl_sync(0xffffffffu, incl, 31);
+            uint32_t jbase = 0;
+            for (uint32_t w0 = 0; w0 < T; w0 += 32u) {
+                const uint32_t rel = excl - w0;                                  // wraps to a huge value when excl < w0
+                const uint32_t smask = __reduce_or_sync(0xffffffffu, (valid && rel < 32u) ? (1u << rel) : 0u);
+                const uint32_t j = (jbase + (uint32_t)__popc(smask & le_mask) - 1u) & 31u;
+                jbase += (uint32_t)__popc(smask);
+                const uint32_t sj = __shfl_sync(0xffffffffu, excl, j);
+                const uint32_t wj = __shfl_sync(0xffffffffu, woff, j);
+                const uint32_t lj = __shfl_sync(0xffffffffu, lf, j);
+                const uint32_t r = w0 + lane;
+                if (r < T) {
+                    const uint32_t i = r - sj, last = (lj & 0x3FFFFFFFu) - k, flags = lj >> 30;
+                    const uint64_t fw = extract64(payload + wj, 2ull * i) & mask;
+                    const uint64_t rc = revcomp64(fw) >> (64 - 2 * k);
                     const bool isf = forward_only ? true : (fw < rc);
-                    const uint64_t key = forward_only ? fw : (fw < rc ? fw : rc);
+                    const uint64_t key = isf ? fw : rc;
                     const uint32_t bi = (!(flags & READ_FLAG_INCL_BEGIN) && i == 0) ? 1u : 0u;
                     const uint32_t ei = (!(flags & READ_FLAG_INCL_END) && i == last) ? 1u : 0u;
                     emit(key, (bi << (isf ? 0 : 1)) | (ei << (isf ? 1 : 0)));  // hashmap.rs:385-399
-                    if (++r == rend) break;
-                    if (i == last) {  // next super-k-mer
-                        ++j; i = 0;
-                        pl = S->ptr[j]; lf = S->lenfl[j];
-                        last = (lf & 0x3FFFFFFFu) - k; flags = lf >> 30;
-                        fw = extract64(pl, 0) & mask;
-                        rc = revcomp64(fw) >> (64 - 2 * k);
-                        cw = last ? pl[k >> 4] : 0u;
-                    } else {
-                        const uint32_t nb = i + k;
-                        if ((nb & 15u) == 0) cw = pl[nb >> 4];
-                        const uint64_t b = (cw >> (2u * (nb & 15u))) & 3u;
-                        fw = (fw >> 2) | (b << (2 * (k - 1)));
-                        rc = ((rc << 2) | (b ^ 2ull)) & mask;
-                        ++i;
-                    }
                 }
             }
-            __syncthreads();  // staging is rewritten by the next round
         }
     }
 }
 
-__host__ __device__ __forceinline__ uint32_t hash_table_slots(uint32_t n) {  // power of two >= 1.5 n
+__host__ __device__ __forceinline__ uint32_t hash_table_slots(uint32_t n) {  // multiple of 512, >= 1.25 n + 64
+    const uint64_t want = (uint64_t)n + n / 4 + 64;
+    const uint64_t t = (want + 511) & ~511ull;
+    return (uint32_t)(t < 1024 ? 1024 : t);
+}
+
+__host__ __device__ __forceinline__ uint32_t hash_table_slots_pow2(uint32_t n) {  // power of two >= 1.5 n (mask-indexed tables, merge128.cuh)
     uint32_t t = 1024;
     const uint64_t want = (uint64_t)n + n / 2;
     while (t < want) t <<= 1;
@@ -428,13 +418,11 @@ k_merge_hash(const ChunkView *__restrict__ chunks, uint32_t n_chunks, const uint
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int WARPS = THREADS / 32;
     constexpr uint32_t SCR_BYTES = WARPS * 256 * 4;  // scratch area: descriptor staging / survivor staging + bins / radix histograms
-    static_assert(sizeof(UnitStage) <= SCR_BYTES, "descriptor staging must fit the scratch area");
     uint64_t *K = reinterpret_cast<uint64_t *>(smem_raw);                      // TS keys
     uint32_t *C = reinterpret_cast<uint32_t *>(K + TS_STATIC);                 // TS counters|flags
     uint32_t *hist = C + TS_STATIC;                                            // scratch area (SCR_BYTES)
     uint32_t *s_scan = hist + WARPS * 256;                                     // 40
     unsigned long long *s_base = reinterpret_cast<unsigned long long *>(s_scan + 40);
-    UnitStage *stage = reinterpret_cast<UnitStage *>(hist);
     const uint32_t tid = threadIdx.x;
     if (n_work_dev) n_work = min(n_work, *n_work_dev);  // device-side list (big units whose partitions overflowed)
     for (uint32_t wi = blockIdx.x; wi < n_work; wi += gridDim.x) {
@@ -465,24 +453,23 @@ k_merge_hash(const ChunkView *__restrict__ chunks, uint32_t n_chunks, const uint
             K = scratch + (uint64_t)blockIdx.x * per_cta_u64;
             C = reinterpret_cast<uint32_t *>(K + TS);
         } else {
-            if (n > (uint32_t)TS_STATIC / 4 * 3) {  // host routes such units elsewhere
+            if (TS > (uint32_t)TS_STATIC) {  // host routes such units elsewhere
                 if (tid == 0) *out.overflow = 2u;
                 continue;
             }
             TS = min(TS, (uint32_t)TS_STATIC);
         }
-        const uint32_t tmask = TS - 1;
-        for (uint32_t i = tid; i < TS; i += THREADS) { K[i] = HASH_EMPTY; C[i] = 0u; }
+                for (uint32_t i = tid; i < TS; i += THREADS) { K[i] = HASH_EMPTY; C[i] = 0u; }
         __syncthreads();
         if (SRC == SRC_RECORDS) {
             const uint64_t *recs = ps.recs + (uint64_t)wi * ps.pcap;
             for (uint32_t i = tid; i < n; i += THREADS) {
                 const uint64_t r = recs[i];
-                hash_insert(K, C, tmask, r >> 2, (uint32_t)r & 3u);
+                hash_insert(K, C, TS, r >> 2, (uint32_t)r & 3u);
             }
         } else {
-            unit_for_each_kmer64<THREADS>(chunks, n_chunks, unit, P.k, P.forward_only, stage, s_scan,
-                                          [&](uint64_t key, uint32_t fb) { hash_insert(K, C, tmask, key, fb); });
+            unit_for_each_kmer64<THREADS>(chunks, n_chunks, unit, P.k, P.forward_only,
+                                          [&](uint64_t key, uint32_t fb) { hash_insert(K, C, TS, key, fb); });
         }
         __syncthreads();
         // ---- scan the table once: MapEntry -> multiplicity, filter; survivors are appended to a small
@@ -502,7 +489,7 @@ k_merge_hash(const ChunkView *__restrict__ chunks, uint32_t n_chunks, const uint
                 if (kk == HASH_EMPTY) continue;
                 ++my_occ;
                 const uint32_t cc = C[i];
-                const uint32_t cnt = cc & 0x3FFFFFFFu, fl = cc >> 30;
+                const uint32_t cnt = slot_count(cc), fl = cc >> 30;
                 const uint32_t mult = cnt >> ((fl == (READ_FLAG_INCL_BEGIN | READ_FLAG_INCL_END)) ? 1 : 0);  // map_entry.rs:79-84
                 if (mult >= min_mult) {
                     const uint32_t idx = atomicAdd(&s_cnt[0], 1u);
@@ -547,7 +534,7 @@ k_merge_hash(const ChunkView *__restrict__ chunks, uint32_t n_chunks, const uint
                         uint32_t cf = 0;
                         if (kk != HASH_EMPTY) {
                             const uint32_t cc = C[i];
-                            const uint32_t cnt = cc & 0x3FFFFFFFu, fl = cc >> 30;
+                            const uint32_t cnt = slot_count(cc), fl = cc >> 30;
                             const uint32_t mult = cnt >> ((fl == 3u) ? 1 : 0);
                             if (mult >= min_mult) cf = mult | (fl << 30);
                         }
@@ -574,7 +561,7 @@ k_merge_hash(const ChunkView *__restrict__ chunks, uint32_t n_chunks, const uint
                 const uint32_t cc = C[i];
                 uint32_t cf = 0, fl = 0;
                 if (kk != HASH_EMPTY) {
-                    const uint32_t cnt = cc & 0x3FFFFFFFu;
+                    const uint32_t cnt = slot_count(cc);
                     fl = cc >> 30;
                     const uint32_t mult = cnt >> ((fl == (READ_FLAG_INCL_BEGIN | READ_FLAG_INCL_END)) ? 1 : 0);
                     if (mult >= min_mult) cf = mult | (fl << 30);
@@ -663,10 +650,7 @@ k_partition_units(const ChunkView *__restrict__ chunks, uint32_t n_chunks, const
                   uint64_t *__restrict__ recs, uint32_t *__restrict__ pcount, uint32_t pcap, uint32_t *__restrict__ big_ovf,
                   uint32_t *__restrict__ retry, uint32_t *__restrict__ retry_count) {
     __shared__ uint32_t s_cur[PART_MAXP];
-    __shared__ __align__(16) unsigned char s_stage_raw[sizeof(UnitStage)];
-    __shared__ uint32_t s_scan[40];
     __shared__ uint32_t s_ovf;
-    UnitStage *stage = reinterpret_cast<UnitStage *>(s_stage_raw);
     const uint32_t tid = threadIdx.x;
     for (uint32_t bi = blockIdx.x; bi < n_big; bi += gridDim.x) {
         const uint32_t unit = big_unit[bi], np = 1u << big_logp[bi], pbase = big_pbase[bi];
@@ -674,7 +658,7 @@ k_partition_units(const ChunkView *__restrict__ chunks, uint32_t n_chunks, const
         if (tid == 0) s_ovf = 0;
         __syncthreads();
         uint64_t *dst = recs + (uint64_t)pbase * pcap;
-        unit_for_each_kmer64<THREADS>(chunks, n_chunks, unit, P.k, P.forward_only, stage, s_scan, [&](uint64_t key, uint32_t fb) {
+        unit_for_each_kmer64<THREADS>(chunks, n_chunks, unit, P.k, P.forward_only, [&](uint64_t key, uint32_t fb) {
             const uint32_t p = part_hash(key) & (np - 1);
             const uint32_t pos = atomicAdd(&s_cur[p], 1u);
             if (pos < pcap) dst[(uint64_t)p * pcap + pos] = (key << 2) | fb;

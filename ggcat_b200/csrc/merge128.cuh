@@ -132,7 +132,7 @@ constexpr size_t merge_hash128_smem_bytes() {
 }
 
 // TS_STATIC > 0: table in shared memory (units with <= 3/4 TS_STATIC records).  TS_STATIC == 0: table in this CTA's
-// slice of `scratch` (hash_table_slots(n) slots of 20 bytes).
+// slice of `scratch` (hash_table_slots_pow2(n) slots of 20 bytes).
 template <int THREADS, int TS_STATIC, int MODE>
 __global__ void __launch_bounds__(THREADS)
 k_merge_hash128(const ChunkView *__restrict__ chunks, uint32_t n_chunks, const uint32_t *__restrict__ work, uint32_t n_work,
@@ -153,7 +153,7 @@ k_merge_hash128(const ChunkView *__restrict__ chunks, uint32_t n_chunks, const u
         }
         uint32_t TS = TS_STATIC;
         if (TS_STATIC == 0) {
-            TS = hash_table_slots(n);
+            TS = hash_table_slots_pow2(n);
             K = reinterpret_cast<K128 *>(scratch + (uint64_t)blockIdx.x * per_cta_u64);
             C = reinterpret_cast<uint32_t *>(K + TS);
         }

@@ -104,3 +104,66 @@ def config_c3(n_genomes: int = 100, genome_len: int = 5_000_000, n_shared: int =
     offsets = np.arange(n_genomes + 1, dtype=np.uint64) * np.uint64(genome_len)
     colors = np.arange(n_genomes, dtype=np.uint32)
     return np.ascontiguousarray(data), offsets, colors
+
+
+# ---- device-side generation (torch on the GPU) -------------------------------------------------------
+# The same counter-based definitions as above evaluated with wrapping int64 arithmetic on the device, for the
+# configs whose reads do not fit a host round trip (C4: "reads generated on device per GPU slice").
+def _s64(x: int) -> int:
+    x &= (1 << 64) - 1
+    return x - (1 << 64) if x >= (1 << 63) else x
+
+
+def _lsr(z, s: int):
+    return (z >> s) & ((1 << (64 - s)) - 1)
+
+
+def splitmix64_torch(seed: int, idx):
+    """idx: int64 tensor of counter values (numpy version: start+1 .. start+n).  Returns int64 (bit pattern of the u64)."""
+    z = idx * _s64(0x9E3779B97F4A7C15) + _s64(seed)
+    z = (z ^ _lsr(z, 30)) * _s64(0xBF58476D1CE4E5B9)
+    z = (z ^ _lsr(z, 27)) * _s64(0x94D049BB133111EB)
+    return z ^ _lsr(z, 31)
+
+
+def genome_codes_torch(seed: int, length: int, device):
+    import torch
+
+    nw = (length + 31) // 32
+    out = torch.empty(nw * 32, dtype=torch.uint8, device=device)
+    step = 1 << 22
+    shifts = (torch.arange(32, dtype=torch.int64, device=device) * 2)[None, :]
+    for w0 in range(0, nw, step):
+        n = min(step, nw - w0)
+        w = splitmix64_torch(seed, torch.arange(w0 + 1, w0 + n + 1, dtype=torch.int64, device=device))
+        out[w0 * 32:(w0 + n) * 32] = ((w[:, None] >> shifts) & 3).to(torch.uint8).reshape(-1)
+    return out[:length]
+
+
+def simulate_reads_torch(genome, n_reads: int, read_len: int, err_rate: float, seed: int, first_read: int = 0, out=None):
+    """ASCII reads (n_reads * read_len uint8, device) with the definition of simulate_reads()."""
+    import torch
+
+    dev = genome.device
+    G = genome.numel()
+    if out is None:
+        out = torch.empty(n_reads * read_len, dtype=torch.uint8, device=dev)
+    letters = torch.tensor(list(b"ACTG"), dtype=torch.uint8, device=dev)
+    ar = torch.arange(read_len, dtype=torch.int64, device=dev)[None, :]
+    thr = int(err_rate * (1 << 24))
+    step = 1 << 20
+    for r0 in range(0, n_reads, step):
+        nr = min(step, n_reads - r0)
+        r = splitmix64_torch(seed, torch.arange(first_read + r0 + 1, first_read + r0 + nr + 1, dtype=torch.int64, device=dev))
+        start = _lsr(r, 1) % (G - read_len + 1)
+        strand = (r & 1).bool()
+        b = genome[start[:, None] + ar]
+        b = torch.where(strand[:, None], b.flip(1) ^ 2, b)
+        if err_rate > 0:
+            c0 = (first_read + r0) * read_len
+            e = splitmix64_torch(seed ^ 0x5EED0E44, torch.arange(c0 + 1, c0 + nr * read_len + 1, dtype=torch.int64, device=dev)).view(nr, read_len)
+            hit = (e & 0xFFFFFF) < thr
+            delta = (_lsr(e, 24) % 3 + 1).to(torch.uint8)
+            b = torch.where(hit, (b + delta) & 3, b)
+        out[r0 * read_len:(r0 + nr) * read_len] = letters[b.long()].reshape(-1)
+    return out

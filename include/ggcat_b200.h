@@ -201,6 +201,9 @@ int32_t ggcat_b200_peer_connect(ggcat_b200_ctx *ctx, const ggcat_b200_peer_handl
 /* After finish_bucketing on every rank.  Local chunks stay registered (the owner's own units are merged in
  * place); the slices received from the other ranks are registered as imported chunks living in the arena. */
 int32_t ggcat_b200_peer_exchange(ggcat_b200_ctx *ctx);
+/* Bytes this rank pushed over NVLink / received into its arena in the last peer_exchange (descriptors, payload,
+ * per-unit counts): the numerator of the "all-to-all bytes against NVLink bandwidth" figure of the bench. */
+int32_t ggcat_b200_peer_stats(ggcat_b200_ctx *ctx, uint64_t *bytes_sent, uint64_t *bytes_received);
 
 /* ---- measurement hooks ------------------------------------------------------------------------- */
 /* Per-kernel-family CUDA-event timing on/off (off by default: two event records per launch). */

@@ -3,6 +3,7 @@
 usage: python profiles/sass_lines.py <report.ncu-rep> <ncu-kernel-regex> <mangled-name-regex> [top_n] [launch_skip]
 Needs ggcat_b200/libggcat_b200.so built from the same sources as the profiled run."""
 import csv
+import os
 import re
 import subprocess
 import sys
@@ -15,7 +16,7 @@ ROOT = Path(__file__).resolve().parent.parent
 
 def disasm_lines(func_regex):
     tmp = Path(tempfile.mkdtemp())
-    subprocess.check_call(["cuobjdump", "-xelf", "all", str(ROOT / "ggcat_b200" / "libggcat_b200.so")], cwd=tmp,
+    subprocess.check_call(["cuobjdump", "-xelf", "all", os.environ.get("GGCAT_B200_PROF_LIB", str(ROOT / "ggcat_b200" / "libggcat_b200.so"))], cwd=tmp,
                           stdout=subprocess.DEVNULL)
     cubin = next(tmp.glob("*.cubin"))
     txt = subprocess.run(["nvdisasm", "-g", "-c", str(cubin)], capture_output=True, text=True).stdout
