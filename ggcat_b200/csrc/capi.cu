@@ -129,6 +129,9 @@ struct ggcat_b200_ctx {
     uint64_t max_batch = 1ull << 30;
     uint64_t host_batch = 48ull << 20;   // push_reads(host): H2D of batch i+1 overlaps the kernels of batch i
     uint64_t part_kmers = 36ull << 20;   // merge_bucket_range(host): D2H of part j overlaps the merge of part j+1
+    uint64_t part_kmers_dev = 192ull << 20;  // merge_bucket_range_device: bounds the per-part scratch (12 B / record + key partitions)
+    uint64_t fin_cap = 0;                // entries the final table (out_keys2 / out_cf2 / out_hi2) can hold
+    uint64_t final_hint = 0;             // survivors of the previous build of this context (sizes the next final table)
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr}, ev_part = nullptr;
     DevBuf st_ascii[2], st_off[2], st_col[2];
@@ -367,6 +370,33 @@ constexpr int HASH_TS_S = 8192, HASH_TS_L = 16384;       // hash-table slots: un
 // already in the table, `ub` = units already in unit_final_off, `cap_total` = final-buffer capacity for the whole range.
 struct PartBase { uint64_t eb = 0; uint32_t ub = 0; uint64_t cap_total = 0; };
 
+// The final table is sized by the survivors actually seen, not by the k-mer occurrences (which are 10-25x more at
+// 30x coverage): it starts from an estimate and grows (keeping the first `keep` entries) when a part does not fit.
+int32_t final_reserve(ggcat_b200_ctx *c, uint64_t need, uint64_t keep, bool wide) {
+    if (need <= c->fin_cap && c->out_keys2.p && c->out_cf2.p && (!wide || c->out_hi2.p)) return 0;
+    CU(cudaStreamSynchronize(c->stream));
+    if (c->copy_stream) CU(cudaStreamSynchronize(c->copy_stream));   // copies of earlier parts read the old buffers
+    auto grow = [&](DevBuf &b, size_t elem) -> cudaError_t {
+        DevBuf nb;
+        cudaError_t e = nb.reserve(need * elem);
+        if (e != cudaSuccess) return e;
+        if (keep && b.p) { e = cudaMemcpy(nb.p, b.p, keep * elem, cudaMemcpyDeviceToDevice); if (e != cudaSuccess) { nb.release(); return e; } }
+        b.release();
+        b = nb;
+        return cudaSuccess;
+    };
+    CU(grow(c->out_keys2, 8));
+    CU(grow(c->out_cf2, 4));
+    if (wide) CU(grow(c->out_hi2, 8));
+    c->fin_cap = need;
+    return 0;
+}
+uint64_t final_estimate(const ggcat_b200_ctx *c, uint64_t records) {
+    if (const char *e = getenv("GGCAT_B200_FINAL_EST")) return std::max<uint64_t>(strtoull(e, nullptr, 10), 1);  // tests: force the growth path
+    const uint64_t est = c->final_hint ? c->final_hint + c->final_hint / 4 + 65536 : std::max<uint64_t>(records / 4, 1ull << 20);
+    return std::max<uint64_t>(std::min(est, records), 1);
+}
+
 int32_t merge_range_device_wide(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_buckets, uint64_t *n_entries,
                                 uint64_t *unique, uint64_t *total, PartBase pb);
 
@@ -598,29 +628,37 @@ int32_t merge_range_device(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_
     }
     CU(cudaGetLastError());
     // ---- unit-ordered final layout (parts append at entry pb.eb / unit pb.ub)
-    if (pb.ub == 0) {
-        const uint64_t fc = std::max(cap, pb.cap_total);
-        CU(c->out_keys2.reserve(fc * 8)); CU(c->out_cf2.reserve(fc * 4));
+    const uint64_t rec_total = std::max(cap, pb.cap_total);
+    if (pb.ub == 0) TRY(final_reserve(c, final_estimate(c, rec_total), 0, false));
+    if (!big.empty()) { CU(c->fin_tmp_keys.reserve(cap * 8)); CU(c->fin_tmp_cf.reserve(cap * 4)); }
+    uint32_t ovf = 0;
+    for (int attempt = 0;; attempt++) {
+        {
+            LaunchTimer t(c, F_GATHER, 2);
+            uint64_t *foff = c->unit_final_off.as<uint64_t>() + pb.ub;
+            k_scan_unit_slots<<<1, 1024, 0, st>>>(c->unit_out_cnt.as<uint32_t>(), d_slot_of_unit, foff, nu, pb.eb);
+            auto kern = k_finish_units<FIN_THREADS, FIN_SCAP>;
+            const size_t smem = finish_units_smem_bytes<FIN_THREADS, FIN_SCAP>();
+            CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            const uint32_t end_bit = std::min(64u, (2 * P.k + 7) & ~7u);
+            kern<<<(unsigned)std::min<uint32_t>(nu, (uint32_t)c->sm_count * 2 * 8), FIN_THREADS, smem, st>>>(
+                c->out_keys.as<uint64_t>(), c->out_cf.as<uint32_t>(), c->unit_out_off.as<uint64_t>(), c->unit_out_cnt.as<uint32_t>(),
+                d_slot_of_unit, foff, c->out_keys2.as<uint64_t>(), c->out_cf2.as<uint32_t>(), c->fin_tmp_keys.as<uint64_t>(),
+                c->fin_tmp_cf.as<uint32_t>(), nu, end_bit, c->fin_cap, c->overflow.as<uint32_t>());
+        }
+        CU(cudaMemcpyAsync(c->h_pinned, c->cursor.p, 24, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(c->h_pinned + 8, c->overflow.p, 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        CU(cudaGetLastError());
+        ovf = (uint32_t)c->h_pinned[8];
+        if (ovf == 4u && attempt == 0) {   // the part's survivors do not fit the final table: grow it, gather again
+            const uint64_t need = pb.eb + c->h_pinned[0];
+            TRY(final_reserve(c, std::max(need, std::min(rec_total, need + need / 2)), pb.eb, false));
+            CU(cudaMemsetAsync(c->overflow.p, 0, 16, st));
+            continue;
+        }
+        break;
     }
-    if (!big.empty()) { CU(c->fin_tmp_keys.reserve(c->out_keys2.cap)); CU(c->fin_tmp_cf.reserve(c->out_cf2.cap)); }
-    {
-        LaunchTimer t(c, F_GATHER, 2);
-        uint64_t *foff = c->unit_final_off.as<uint64_t>() + pb.ub;
-        k_scan_unit_slots<<<1, 1024, 0, st>>>(c->unit_out_cnt.as<uint32_t>(), d_slot_of_unit, foff, nu, pb.eb);
-        auto kern = k_finish_units<FIN_THREADS, FIN_SCAP>;
-        const size_t smem = finish_units_smem_bytes<FIN_THREADS, FIN_SCAP>();
-        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        const uint32_t end_bit = std::min(64u, (2 * P.k + 7) & ~7u);
-        kern<<<(unsigned)std::min<uint32_t>(nu, (uint32_t)c->sm_count * 2 * 8), FIN_THREADS, smem, st>>>(
-            c->out_keys.as<uint64_t>(), c->out_cf.as<uint32_t>(), c->unit_out_off.as<uint64_t>(), c->unit_out_cnt.as<uint32_t>(),
-            d_slot_of_unit, foff, c->out_keys2.as<uint64_t>(), c->out_cf2.as<uint32_t>(), c->fin_tmp_keys.as<uint64_t>(),
-            c->fin_tmp_cf.as<uint32_t>(), nu, end_bit);
-    }
-    CU(cudaMemcpyAsync(c->h_pinned, c->cursor.p, 24, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(c->h_pinned + 8, c->overflow.p, 4, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    CU(cudaGetLastError());
-    const uint32_t ovf = (uint32_t)c->h_pinned[8];
     if (ovf) return set_err(GGCAT_B200_ERR_CAPACITY, "merge output overflow (code %u)", ovf);
     c->last_entries = c->h_pinned[0];
     c->fin = FinalTable();
@@ -720,9 +758,10 @@ int32_t merge_range_device_wide(ggcat_b200_ctx *c, uint32_t first_bucket, uint32
     }
     const uint64_t cap = std::max<uint64_t>(tot_kmers, 1);
     CU(c->out_keys.reserve(cap * 8)); CU(c->out_hi.reserve(cap * 8)); CU(c->out_cf.reserve(cap * 4));
+    const uint64_t rec_total = std::max(cap, pb.cap_total);
     if (pb.ub == 0) {
-        const uint64_t fc = std::max(cap, pb.cap_total);
-        CU(c->out_keys2.reserve(fc * 8)); CU(c->out_hi2.reserve(fc * 8)); CU(c->out_cf2.reserve(fc * 4));
+        // coloured builds fold in one piece and need every (k-mer, colour) entry; the others grow with the survivors
+        TRY(final_reserve(c, c->wide_mode == MODE_COLOR ? rec_total : final_estimate(c, rec_total), 0, true));
         CU(c->unit_final_off.reserve(((size_t)c->P.n_units + 2) * 8));
     }
     CU(c->cursor.reserve(64)); CU(c->overflow.reserve(16));
@@ -744,18 +783,28 @@ int32_t merge_range_device_wide(ggcat_b200_ctx *c, uint32_t first_bucket, uint32
     uint32_t end_bit = 128;
     if (c->wide_mode == MODE_SEQ128) end_bit = std::min(128u, (2 * P.k + 7) & ~7u);
     else if (c->wide_mode == MODE_COLOR) end_bit = std::min(128u, (32 + 2 * P.k + 7) & ~7u);
-    {
-        LaunchTimer t(c, F_SORT128, 2);
-        k_scan_counts_u64<<<1, 1024, 0, st>>>(c->unit_out_cnt.as<uint32_t>(), c->unit_final_off.as<uint64_t>() + pb.ub, nu, pb.eb);
-        auto kern = k_sort_units128<W_SORT_THREADS, W_SORT_CAP>;
-        const size_t smem = sort_units128_smem_bytes<W_SORT_THREADS, W_SORT_CAP>();
-        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<(unsigned)std::min<uint32_t>(nu, (uint32_t)c->sm_count * 2 * 8), W_SORT_THREADS, smem, st>>>(
-            c->out_keys.as<uint64_t>(), c->out_hi.as<uint64_t>(), c->out_cf.as<uint32_t>(), c->unit_out_off.as<uint64_t>(),
-            c->unit_out_cnt.as<uint32_t>(), c->unit_final_off.as<uint64_t>() + pb.ub, c->out_keys2.as<uint64_t>(),
-            c->out_hi2.as<uint64_t>(), c->out_cf2.as<uint32_t>(), nu, 0u, end_bit);
+    for (int attempt = 0;; attempt++) {
+        {
+            LaunchTimer t(c, F_SORT128, 2);
+            k_scan_counts_u64<<<1, 1024, 0, st>>>(c->unit_out_cnt.as<uint32_t>(), c->unit_final_off.as<uint64_t>() + pb.ub, nu, pb.eb);
+            auto kern = k_sort_units128<W_SORT_THREADS, W_SORT_CAP>;
+            const size_t smem = sort_units128_smem_bytes<W_SORT_THREADS, W_SORT_CAP>();
+            CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<(unsigned)std::min<uint32_t>(nu, (uint32_t)c->sm_count * 2 * 8), W_SORT_THREADS, smem, st>>>(
+                c->out_keys.as<uint64_t>(), c->out_hi.as<uint64_t>(), c->out_cf.as<uint32_t>(), c->unit_out_off.as<uint64_t>(),
+                c->unit_out_cnt.as<uint32_t>(), c->unit_final_off.as<uint64_t>() + pb.ub, c->out_keys2.as<uint64_t>(),
+                c->out_hi2.as<uint64_t>(), c->out_cf2.as<uint32_t>(), nu, 0u, end_bit, c->fin_cap, c->overflow.as<uint32_t>());
+        }
+        CU(cudaGetLastError());
+        if (c->wide_mode == MODE_COLOR || attempt > 0) break;   // sized for every record / already regrown
+        CU(cudaMemcpyAsync(c->h_pinned, c->cursor.p, 24, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(c->h_pinned + 8, c->overflow.p, 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        if ((uint32_t)c->h_pinned[8] != 4u) break;
+        const uint64_t need = pb.eb + c->h_pinned[0];
+        TRY(final_reserve(c, std::max(need, std::min(rec_total, need + need / 2)), pb.eb, true));
+        CU(cudaMemsetAsync(c->overflow.p, 0, 16, st));
     }
-    CU(cudaGetLastError());
     c->fin = FinalTable();
     if (c->wide_mode == MODE_COLOR) {
         // fold the (k-mer, colour) entries of every k-mer; the unsorted buffers are free again and take the result
@@ -891,6 +940,7 @@ int32_t ggcat_b200_create(const ggcat_b200_params *params, ggcat_b200_ctx **out)
     if (cudaGetDeviceProperties(&prop, p.device) == cudaSuccess) c->sm_count = prop.multiProcessorCount;
     if (const char *hb = getenv("GGCAT_B200_HOST_BATCH")) { uint64_t v = strtoull(hb, nullptr, 10); if (v >= 1024) c->host_batch = std::min<uint64_t>(v, c->max_batch); }
     if (const char *pk = getenv("GGCAT_B200_PART_KMERS")) { uint64_t v = strtoull(pk, nullptr, 10); if (v >= 1024) c->part_kmers = v; }
+    if (const char *pk = getenv("GGCAT_B200_PART_KMERS_DEV")) { uint64_t v = strtoull(pk, nullptr, 10); if (v >= 1024) c->part_kmers_dev = v; }
     c->host_batch = std::min(c->host_batch, c->max_batch);
     bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) == cudaSuccess &&
@@ -1117,7 +1167,46 @@ int32_t ggcat_b200_dump_superkmers(ggcat_b200_ctx *c, uint32_t bucket, ggcat_b20
 int32_t ggcat_b200_merge_bucket_range_device(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_buckets, uint64_t *n_entries,
                                              uint64_t *unique_kmers, uint64_t *total_kmers) {
     TRY(check_ctx(c));
-    return merge_range_device(c, first_bucket, n_buckets, n_entries, unique_kmers, total_kmers);
+    if (!c->finished) return set_err(GGCAT_B200_ERR_STATE, "merge before finish_bucketing");
+    const DevParams &P = c->P;
+    const uint32_t nb_total = (1u << P.b1) + 1;
+    if (n_buckets == 0 || first_bucket >= nb_total || first_bucket + n_buckets > nb_total)
+        return set_err(GGCAT_B200_ERR_INVALID, "bucket range [%u,+%u) outside 0..%u", first_bucket, n_buckets, nb_total);
+    // parts of ~part_kmers_dev records (whole buckets) bound the per-part scratch; every part appends to one final
+    // table that stays in HBM.  Coloured builds fold in one piece.
+    std::vector<uint64_t> bk(n_buckets, 0);
+    uint64_t tot = 0;
+    for (uint32_t b = 0; b < n_buckets; b++) {
+        const uint32_t ua = (first_bucket + b) << P.b2, ub2 = (first_bucket + b + 1) << P.b2;
+        for (Chunk *ch : c->chunks) {
+            const uint32_t lo = std::max(ua, ch->first_unit), hi = std::min(ub2, ch->first_unit + ch->n_units);
+            for (uint32_t u = lo; u < hi; u++) bk[b] += ch->h_kmers[u - ch->first_unit];
+        }
+        tot += bk[b];
+    }
+    std::vector<std::pair<uint32_t, uint32_t>> parts;
+    if (c->wide_mode == MODE_COLOR || tot <= c->part_kmers_dev + c->part_kmers_dev / 2) parts.push_back({first_bucket, n_buckets});
+    else {
+        uint32_t b0 = 0; uint64_t acc = 0;
+        for (uint32_t b = 0; b < n_buckets; b++) {
+            acc += bk[b];
+            if (acc >= c->part_kmers_dev || b + 1 == n_buckets) { parts.push_back({first_bucket + b0, b + 1 - b0}); b0 = b + 1; acc = 0; }
+        }
+    }
+    uint64_t eb = 0, uq = 0, tk = 0;
+    uint32_t ub = 0;
+    for (auto &pr : parts) {
+        PartBase pb; pb.eb = eb; pb.ub = ub; pb.cap_total = std::max<uint64_t>(tot, 1);
+        uint64_t ne = 0, u1 = 0, t1 = 0;
+        TRY(merge_range_device(c, pr.first, pr.second, &ne, &u1, &t1, pb));
+        eb += ne; uq += u1; tk += t1;
+        ub += pr.second << P.b2;
+    }
+    c->final_hint = eb;
+    if (n_entries) *n_entries = eb;
+    if (unique_kmers) *unique_kmers = uq;
+    if (total_kmers) *total_kmers = tk;
+    return 0;
 }
 
 // Host-table growth for the part-wise D2H: keeps what was already copied.
@@ -1231,6 +1320,7 @@ int32_t ggcat_b200_merge_bucket_range(ggcat_b200_ctx *c, uint32_t first_bucket, 
     out->first_unit = first_bucket << P.b2; out->n_units = nu; out->unit_offsets = t->unit_offsets;
     out->color_offsets = colored ? t->color_offsets : nullptr; out->colors = colored ? t->colors : nullptr;
     out->total_kmers = tk; out->unique_kmers = uq; out->opaque = t;
+    if (!colored) c->final_hint = ne;
     return 0;
 }
 

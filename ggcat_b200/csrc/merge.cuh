@@ -321,71 +321,97 @@ __device__ __forceinline__ void hash_insert(uint64_t *K, uint32_t *C, uint32_t T
 __device__ __forceinline__ uint32_t slot_count(uint32_t cc) { return (cc & 0x3FFFFFFFu) + 1u; }   // occurrences of an occupied slot
 
 // ---- load-balanced expansion of a unit ---------------------------------------------------------------------------
-// Warp-parallel, barrier-free: a warp takes 32 consecutive descriptors (one per lane, one coalesced 512-byte load),
-// numbers their k-mer records 0..T with a warp scan and then walks the records 32 at a time, ONE RECORD PER LANE:
-//   owner super-k-mer of record r  = number of super-k-mers starting at or before r  (warp-wide OR of the start bits
-//                                    that fall in the current window of 32 records + popc), fetched by shuffle;
+// The k-mer records of a unit are numbered 0..tot over all its super-k-mers (all chunks, THREADS descriptors per
+// round: one block scan of the k-mer counts).  Every WARP takes an equal, 32-aligned range of records and walks it 32
+// records at a time, ONE RECORD PER LANE:
+//   owner super-k-mer of record r  = (super-k-mer that contains the window's first record) + number of super-k-mers
+//                                    starting inside the window at or before r  (warp-wide OR of start bits + popc);
 //   k-mer at offset i of the owner = 64 bits extracted at bit 2i of its payload (three cached word loads), canonical
 //                                    form by one bit-reversal (cn_seqhash_base.rs:27-69 evaluated directly, no rolling).
-// Every lane does the same work whatever the super-k-mer lengths are: no divergence, no binary search, no block
-// barrier between the table clear and the table scan.
+// Every lane does the same work whatever the super-k-mer lengths are (no divergence), and all warps of the CTA finish
+// within one window of each other (the unit is small: ~130 windows for 16 warps on the C2 shape).
+constexpr int UNIT_MAXC = 32;   // chunks gathered per round
+
+template <int THREADS>
+struct UnitStage {                       // lives in the kernel's scratch area while records are inserted
+    const uint32_t *c_pl[UNIT_MAXC];     // payload base of the chunk, word bias already subtracted
+    uint32_t c_d0[UNIT_MAXC], c_cnt[UNIT_MAXC];
+    uint32_t start[THREADS + 1];         // first record number of the staged super-k-mer (exclusive prefix of k-mer counts)
+    uint32_t woff[THREADS];              // payload word offset inside its chunk
+    uint32_t lf[THREADS];                // len | flags << 30
+    uint8_t ci[THREADS];                 // chunk (relative to the round's first)
+};
+
 template <int THREADS, typename Emit>
 __device__ __forceinline__ void unit_for_each_kmer64(const ChunkView *__restrict__ chunks, uint32_t n_chunks, uint32_t unit,
-                                                     uint32_t k, uint32_t forward_only, Emit emit) {
+                                                     uint32_t k, uint32_t forward_only, UnitStage<THREADS> *S, uint32_t *s_scan,
+                                                     Emit emit) {
     constexpr uint32_t WARPS = THREADS / 32;
-    const uint32_t lane = lane_id(), warp = warp_id();
+    const uint32_t tid = threadIdx.x, lane = lane_id(), warp = warp_id();
     const uint64_t mask = (1ull << (2 * k)) - 1ull;
     const uint32_t le_mask = 0xFFFFFFFFu >> (31u - lane);
-    uint32_t gbase = 0;   // descriptor groups handed out so far: groups go to warps round-robin ACROSS chunks
-    for (uint32_t c = 0; c < n_chunks; c++) {
-        const ChunkView &cv = chunks[c];
-        const uint32_t fu = cv.first_unit;
-        if (unit < fu || unit >= fu + cv.n_units) continue;
-        const uint32_t d0 = cv.unit_off[unit - fu], d1 = cv.unit_off[unit - fu + 1];
-        const uint4 *__restrict__ desc = cv.desc;
-        const uint32_t *__restrict__ payload = cv.payload;
-        const uint32_t bias = cv.word_bias;
-        const uint32_t first = (warp + WARPS - gbase % WARPS) % WARPS;
-        gbase += (d1 - d0 + 31u) >> 5;
-        for (uint32_t g = d0 + first * 32u; g < d1; g += WARPS * 32u) {
-            const uint32_t di = g + lane;
-            const bool valid = di < d1;
-            uint32_t woff = 0, lf = 0, cnt = 0;
-            if (valid) {
-                const uint4 d = desc[di];
-                woff = d.x - bias;
-                lf = d.y | (((d.z >> 16) & 3u) << 30);
+    for (uint32_t c0 = 0; c0 < n_chunks; c0 += UNIT_MAXC) {
+        const uint32_t nc = min((uint32_t)UNIT_MAXC, n_chunks - c0);
+        if (tid < nc) {
+            const ChunkView &cv = chunks[c0 + tid];
+            uint32_t d0 = 0, d1 = 0;
+            if (unit >= cv.first_unit && unit < cv.first_unit + cv.n_units) {
+                d0 = cv.unit_off[unit - cv.first_unit]; d1 = cv.unit_off[unit - cv.first_unit + 1];
+            }
+            S->c_d0[tid] = d0; S->c_cnt[tid] = d1 - d0;
+            S->c_pl[tid] = cv.payload - cv.word_bias;
+        }
+        __syncthreads();
+        uint32_t dtot = 0;
+        for (uint32_t c = 0; c < nc; c++) dtot += S->c_cnt[c];
+        for (uint32_t g0 = 0; g0 < dtot; g0 += THREADS) {
+            const uint32_t dr = min((uint32_t)THREADS, dtot - g0);
+            uint32_t cnt = 0;
+            if (tid < dr) {
+                uint32_t g = g0 + tid, c = 0;
+                while (g >= S->c_cnt[c]) { g -= S->c_cnt[c]; ++c; }
+                const uint4 d = chunks[c0 + c].desc[S->c_d0[c] + g];
+                S->woff[tid] = d.x;
+                S->lf[tid] = d.y | (((d.z >> 16) & 3u) << 30);
+                S->ci[tid] = (uint8_t)c;
                 cnt = d.y - k + 1;
             }
-            uint32_t incl = cnt;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= (uint32_t)o) incl += y;
-            }
-            const uint32_t excl = incl - cnt;
-            const uint32_t T = __shfl_sync(0xffffffffu, incl, 31);
-            uint32_t jbase = 0;
-            for (uint32_t w0 = 0; w0 < T; w0 += 32u) {
-                const uint32_t rel = excl - w0;                                  // wraps to a huge value when excl < w0
-                const uint32_t smask = __reduce_or_sync(0xffffffffu, (valid && rel < 32u) ? (1u << rel) : 0u);
-                const uint32_t j = (jbase + (uint32_t)__popc(smask & le_mask) - 1u) & 31u;
-                jbase += (uint32_t)__popc(smask);
-                const uint32_t sj = __shfl_sync(0xffffffffu, excl, j);
-                const uint32_t wj = __shfl_sync(0xffffffffu, woff, j);
-                const uint32_t lj = __shfl_sync(0xffffffffu, lf, j);
-                const uint32_t r = w0 + lane;
-                if (r < T) {
-                    const uint32_t i = r - sj, last = (lj & 0x3FFFFFFFu) - k, flags = lj >> 30;
-                    const uint64_t fw = extract64(payload + wj, 2ull * i) & mask;
-                    const uint64_t rc = revcomp64(fw) >> (64 - 2 * k);
-                    const bool isf = forward_only ? true : (fw < rc);
-                    const uint64_t key = isf ? fw : rc;
-                    const uint32_t bi = (!(flags & READ_FLAG_INCL_BEGIN) && i == 0) ? 1u : 0u;
-                    const uint32_t ei = (!(flags & READ_FLAG_INCL_END) && i == last) ? 1u : 0u;
-                    emit(key, (bi << (isf ? 0 : 1)) | (ei << (isf ? 1 : 0)));  // hashmap.rs:385-399
+            uint32_t tot;
+            const uint32_t p = block_exclusive_scan<THREADS>(cnt, s_scan, &tot);
+            if (tid < dr) S->start[tid] = p;
+            if (tid == 0) S->start[dr] = tot;
+            __syncthreads();
+            const uint32_t per = ((tot + WARPS * 32u - 1u) / (WARPS * 32u)) * 32u;   // records per warp, 32-aligned
+            const uint32_t r_beg = warp * per, r_end = min(tot, r_beg + per);
+            if (r_beg < r_end) {
+                uint32_t lo = 0, hi = dr - 1;                                          // last j with start[j] <= r_beg
+                while (lo < hi) {
+                    const uint32_t mid = (lo + hi + 1) >> 1;
+                    if (S->start[mid] <= r_beg) lo = mid; else hi = mid - 1;
+                }
+                uint32_t j = lo;                                                       // invariant: start[j] <= r0 < start[j+1]
+                for (uint32_t r0 = r_beg; r0 < r_end; r0 += 32u) {
+                    const uint32_t cand = j + 1u + lane;
+                    const uint32_t rel = (cand < dr ? S->start[cand] : 0xFFFFFFFFu) - r0;  // > 0 by the invariant
+                    const uint32_t smask = __reduce_or_sync(0xffffffffu, rel < 32u ? (1u << rel) : 0u);
+                    const uint32_t owner = j + (uint32_t)__popc(smask & le_mask);
+                    const uint32_t r = r0 + lane;
+                    if (r < r_end) {
+                        const uint32_t lj = S->lf[owner];
+                        const uint32_t i = r - S->start[owner], last = (lj & 0x3FFFFFFFu) - k, flags = lj >> 30;
+                        const uint64_t fw = extract64(S->c_pl[S->ci[owner]] + S->woff[owner], 2ull * i) & mask;
+                        const uint64_t rc = revcomp64(fw) >> (64 - 2 * k);
+                        const bool isf = forward_only ? true : (fw < rc);
+                        const uint64_t key = isf ? fw : rc;
+                        const uint32_t bi = (!(flags & READ_FLAG_INCL_BEGIN) && i == 0) ? 1u : 0u;
+                        const uint32_t ei = (!(flags & READ_FLAG_INCL_END) && i == last) ? 1u : 0u;
+                        emit(key, (bi << (isf ? 0 : 1)) | (ei << (isf ? 1 : 0)));  // hashmap.rs:385-399
+                    }
+                    j += (uint32_t)__popc(smask);
+                    if (j + 1u < dr && S->start[j + 1u] == r0 + 32u) ++j;              // next window starts a new super-k-mer
                 }
             }
+            __syncthreads();  // staging is rewritten by the next round
         }
     }
 }
@@ -418,11 +444,13 @@ k_merge_hash(const ChunkView *__restrict__ chunks, uint32_t n_chunks, const uint
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int WARPS = THREADS / 32;
     constexpr uint32_t SCR_BYTES = WARPS * 256 * 4;  // scratch area: descriptor staging / survivor staging + bins / radix histograms
+    static_assert(sizeof(UnitStage<THREADS>) <= SCR_BYTES, "descriptor staging must fit the scratch area");
     uint64_t *K = reinterpret_cast<uint64_t *>(smem_raw);                      // TS keys
     uint32_t *C = reinterpret_cast<uint32_t *>(K + TS_STATIC);                 // TS counters|flags
     uint32_t *hist = C + TS_STATIC;                                            // scratch area (SCR_BYTES)
     uint32_t *s_scan = hist + WARPS * 256;                                     // 40
     unsigned long long *s_base = reinterpret_cast<unsigned long long *>(s_scan + 40);
+    UnitStage<THREADS> *stage = reinterpret_cast<UnitStage<THREADS> *>(hist);
     const uint32_t tid = threadIdx.x;
     if (n_work_dev) n_work = min(n_work, *n_work_dev);  // device-side list (big units whose partitions overflowed)
     for (uint32_t wi = blockIdx.x; wi < n_work; wi += gridDim.x) {
@@ -468,7 +496,7 @@ k_merge_hash(const ChunkView *__restrict__ chunks, uint32_t n_chunks, const uint
                 hash_insert(K, C, TS, r >> 2, (uint32_t)r & 3u);
             }
         } else {
-            unit_for_each_kmer64<THREADS>(chunks, n_chunks, unit, P.k, P.forward_only,
+            unit_for_each_kmer64<THREADS>(chunks, n_chunks, unit, P.k, P.forward_only, stage, s_scan,
                                           [&](uint64_t key, uint32_t fb) { hash_insert(K, C, TS, key, fb); });
         }
         __syncthreads();
@@ -650,7 +678,11 @@ k_partition_units(const ChunkView *__restrict__ chunks, uint32_t n_chunks, const
                   uint64_t *__restrict__ recs, uint32_t *__restrict__ pcount, uint32_t pcap, uint32_t *__restrict__ big_ovf,
                   uint32_t *__restrict__ retry, uint32_t *__restrict__ retry_count) {
     __shared__ uint32_t s_cur[PART_MAXP];
+    static_assert(THREADS == 1024, "launched with 1024 threads");
+    __shared__ __align__(16) unsigned char s_stage_raw[sizeof(UnitStage<1024>)];
+    __shared__ uint32_t s_scan[40];
     __shared__ uint32_t s_ovf;
+    UnitStage<1024> *stage = reinterpret_cast<UnitStage<1024> *>(s_stage_raw);
     const uint32_t tid = threadIdx.x;
     for (uint32_t bi = blockIdx.x; bi < n_big; bi += gridDim.x) {
         const uint32_t unit = big_unit[bi], np = 1u << big_logp[bi], pbase = big_pbase[bi];
@@ -658,7 +690,7 @@ k_partition_units(const ChunkView *__restrict__ chunks, uint32_t n_chunks, const
         if (tid == 0) s_ovf = 0;
         __syncthreads();
         uint64_t *dst = recs + (uint64_t)pbase * pcap;
-        unit_for_each_kmer64<THREADS>(chunks, n_chunks, unit, P.k, P.forward_only, [&](uint64_t key, uint32_t fb) {
+        unit_for_each_kmer64<1024>(chunks, n_chunks, unit, P.k, P.forward_only, stage, s_scan, [&](uint64_t key, uint32_t fb) {
             const uint32_t p = part_hash(key) & (np - 1);
             const uint32_t pos = atomicAdd(&s_cur[p], 1u);
             if (pos < pcap) dst[(uint64_t)p * pcap + pos] = (key << 2) | fb;
@@ -683,8 +715,16 @@ __global__ void __launch_bounds__(THREADS)
 k_finish_units(const uint64_t *__restrict__ src_keys, const uint32_t *__restrict__ src_cf, const uint64_t *__restrict__ slot_off,
                const uint32_t *__restrict__ slot_cnt, const uint32_t *__restrict__ slot_of_unit /* n_units + 1, or NULL */,
                const uint64_t *__restrict__ dst_off, uint64_t *__restrict__ dst_keys, uint32_t *__restrict__ dst_cf,
-               uint64_t *__restrict__ tmp_keys, uint32_t *__restrict__ tmp_cf, uint32_t n_units, uint32_t end_bit) {
+               uint64_t *__restrict__ tmp_keys, uint32_t *__restrict__ tmp_cf, uint32_t n_units, uint32_t end_bit,
+               uint64_t capacity, uint32_t *__restrict__ overflow) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    // the final table grows with the survivors actually seen: when this part does not fit, nothing is written and the
+    // host enlarges the table and launches the gather again (overflow bit 2)
+    if (dst_off[n_units] > capacity) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(overflow, 4u);
+        return;
+    }
+    const uint64_t tmp_base = dst_off[0];   // tmp_* hold this part only
     constexpr int WARPS = THREADS / 32;
     uint64_t *sA = reinterpret_cast<uint64_t *>(smem_raw), *sB = sA + SCAP;
     uint32_t *sAv = reinterpret_cast<uint32_t *>(sB + SCAP), *sBv = sAv + SCAP;
@@ -712,8 +752,8 @@ k_finish_units(const uint64_t *__restrict__ src_keys, const uint32_t *__restrict
             run += c;
         }
         __syncthreads();
-        uint64_t *B = in_smem ? sB : tmp_keys + d;
-        uint32_t *Bv = in_smem ? sBv : tmp_cf + d;
+        uint64_t *B = in_smem ? sB : tmp_keys + (d - tmp_base);
+        uint32_t *Bv = in_smem ? sBv : tmp_cf + (d - tmp_base);
         uint32_t *Vs = nullptr;
         uint64_t *Ss = block_radix_sort64<THREADS, true>(A, B, n, 0, end_bit, hist, s_scan, Av, Bv, &Vs);
         if (Ss != dst_keys + d)

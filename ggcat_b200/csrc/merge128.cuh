@@ -328,8 +328,13 @@ __global__ void __launch_bounds__(THREADS)
 k_sort_units128(uint64_t *__restrict__ src_lo, uint64_t *__restrict__ src_hi, uint32_t *__restrict__ src_cf,
                 const uint64_t *__restrict__ unit_out_off, const uint32_t *__restrict__ unit_out_cnt,
                 const uint64_t *__restrict__ unit_final_off, uint64_t *__restrict__ dst_lo, uint64_t *__restrict__ dst_hi,
-                uint32_t *__restrict__ dst_cf, uint32_t n_units, uint32_t first_bit, uint32_t end_bit) {
+                uint32_t *__restrict__ dst_cf, uint32_t n_units, uint32_t first_bit, uint32_t end_bit, uint64_t capacity,
+                uint32_t *__restrict__ overflow) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    if (unit_final_off[n_units] > capacity) {   // the host enlarges the final table and launches the sort again
+        if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(overflow, 4u);
+        return;
+    }
     constexpr int WARPS = THREADS / 32;
     uint64_t *sAlo = reinterpret_cast<uint64_t *>(smem_raw);
     uint64_t *sAhi = sAlo + CAP, *sBlo = sAhi + CAP, *sBhi = sBlo + CAP;

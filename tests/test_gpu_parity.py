@@ -216,6 +216,32 @@ def test_pipelined_host_path_small_batches(k, ht, monkeypatch):
         ctx.close()
 
 
+@pytest.mark.parametrize("k,ht,s", [(31, O.HASH_SEQ, 1), (31, O.HASH_SEQ, 2), (63, O.HASH_RK128, 1), (41, O.HASH_SEQ, 2)])
+def test_final_table_growth_and_device_parts(k, ht, s, monkeypatch):
+    """The final table is sized from an estimate of the survivors and grows when a part does not fit; the
+    device-resident merge appends bounded parts.  Force a tiny estimate and tiny parts: identical tables (host path,
+    which shares the growth code) and identical counters from merge_bucket_range_device."""
+    G = _gpu()
+    monkeypatch.setenv("GGCAT_B200_FINAL_EST", "7")
+    monkeypatch.setenv("GGCAT_B200_PART_KMERS", "3000")
+    monkeypatch.setenv("GGCAT_B200_PART_KMERS_DEV", "3000")
+    rng = np.random.default_rng(900 + k + s)
+    m, b1, b2 = (12 if k == 31 else 14), 3, 2
+    seqs = _mixed_reads(rng, k, n=400) + [util.rand_seq(rng, 40000)]
+    reads = O.Reads.from_list(seqs)
+    sk, _ = O.bucketing(reads, k, m, b1, b2)
+    ctx, st = G.minimizer_bucketing([(reads.data, reads.offsets)], b1, b2, k, m, min_multiplicity=s, hash_type=ht)
+    try:
+        n_checked = _check_tables(G, ctx, reads, sk, k, s, b1, b2, hash_type=ht)
+        ne, uq, tk = ctx.merge_bucket_range_device(0, (1 << b1) + 1)
+        assert ne == n_checked and tk == st.n_kmers
+        ne2, _, _ = ctx.merge_bucket_range_device(2, 4)      # a sub-range after a full one: the table restarts at entry 0
+        tab = ctx.merge_bucket_range(2, 4)
+        assert ne2 == tab.n_entries
+    finally:
+        ctx.close()
+
+
 def test_several_large_units_in_one_range():
     """More than one unit above the shared-memory capacity in the same merge call (global-scratch tables, work list
     of large units sorted by size)."""
