@@ -172,9 +172,36 @@ def run_ours(args):
     import ggcat_b200 as G
     from ggcat_b200 import dist as gdist
 
-    n_reads = args.reads_per_gpu
-    data, offsets = make_reads(rank, world, n_reads)
-    n_bases = int(data.size)
+    wl = args.workload
+    n_reads = args.reads_per_gpu if args.reads_per_gpu else (READS_PER_GPU if wl == "c2" else 20_000_000)
+    dev = torch.device("cuda", local_rank)
+    if wl == "c2":
+        data, offsets = make_reads(rank, world, n_reads)
+        n_bases = int(data.size)
+        h_data = torch.from_numpy(data).pin_memory()
+        h_off = torch.from_numpy(offsets.view(np.int64)).pin_memory()
+        d_data = h_data.cuda(non_blocking=True)
+        d_off = h_off.cuda(non_blocking=True)
+        genome_len, err, seed_note = GENOME_PER_GPU * world, ERR, "1% errors"
+        reads_per_push = n_reads
+    else:
+        # C4 shape (BASELINE configs[3]): error-free 150 bp reads at 30x of one genome shared by all ranks, generated
+        # on the device; rank r holds reads [r*R, (r+1)*R).  Full C4 is 77.5 M reads per GPU at N=8.
+        from ggcat_b200 import synth
+        genome_len, err, seed_note = 5 * n_reads * world, 0.0, "error-free"
+        genome = synth.genome_codes_torch(0xC4, genome_len, dev)
+        d_data = synth.simulate_reads_torch(genome, n_reads, READ_LEN, 0.0, 0xC4 + 1, first_read=rank * n_reads)
+        del genome
+        torch.cuda.empty_cache()
+        n_bases = int(d_data.numel())
+        d_off = torch.arange(n_reads + 1, dtype=torch.int64, device=dev) * READ_LEN
+        h_data = h_off = None
+        if not args.no_e2e:
+            h_data = torch.empty(n_bases, dtype=torch.uint8).pin_memory()
+            h_data.copy_(d_data)
+            h_off = torch.empty(n_reads + 1, dtype=torch.int64).pin_memory()
+            h_off.copy_(d_off)
+        reads_per_push = 4_000_000          # device pushes of 600 Mbases (one bucket chunk each)
     # bucket counts as the reference derives them from the size of the WHOLE input (all ranks' FASTA bytes,
     # crates/io/src/lib.rs:67-140)
     b1, b2 = G.bucket_counts(int(n_reads * world * (READ_LEN + 15)))
@@ -183,12 +210,13 @@ def run_ours(args):
     nb = (1 << b1) + 1
     ctx = G.GGCATB200(G.Params(k=K, m=M, min_multiplicity=S, buckets_count_log=b1, second_buckets_count_log=b2,
                                device=local_rank))
-    ext = torch.cuda.ExternalStream(ctx.stream_ptr, device=torch.device("cuda", local_rank))
-    # inputs: pinned host copies (e2e) and device-resident copies (value)
-    h_data = torch.from_numpy(data).pin_memory()
-    h_off = torch.from_numpy(offsets.view(np.int64)).pin_memory()
-    d_data = h_data.cuda(non_blocking=True)
-    d_off = h_off.cuda(non_blocking=True)
+    ext = torch.cuda.ExternalStream(ctx.stream_ptr, device=dev)
+    # per-push device views (offsets rebased to the push)
+    pushes = []
+    for r0 in range(0, n_reads, reads_per_push):
+        r1 = min(n_reads, r0 + reads_per_push)
+        off = (d_off[r0:r1 + 1] - r0 * READ_LEN).contiguous() if r0 else d_off[:r1 + 1]
+        pushes.append((d_data.data_ptr() + r0 * READ_LEN, off, r1 - r0, (r1 - r0) * READ_LEN))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
     torch.cuda.synchronize()
     owner = gdist.OwnerMap(b1, b2, world)
@@ -196,14 +224,16 @@ def run_ours(args):
     if world > 1:
         transport = os.environ.get("GGCAT_B200_EXCHANGE", "peer")
         if transport == "peer":
-            # receive arena: descriptors (16 B / super-k-mer) + payload ~ 2.4 B per input base, 2.5x headroom
-            gdist.peer_setup(ctx, rank, world, arena_bytes=max(6 * n_bases, 64 << 20))
+            # receive arena: descriptors (16 B / super-k-mer) + payload ~ 2.4 B per input base; 2.5x headroom on small
+            # inputs, 1.5x on large ones (the arena is HBM that the merge cannot use)
+            gdist.peer_setup(ctx, rank, world, arena_bytes=max(int((6 if n_bases < (1 << 31) else 3.6) * n_bases), 64 << 20))
 
     last_stats = [None]
 
     def step_device():
         ctx.reset()
-        ctx.push_reads_device(d_data.data_ptr(), d_off.data_ptr(), n_reads, n_bases)
+        for ptr, off, nr, nbytes in pushes:
+            ctx.push_reads_device(ptr, off.data_ptr(), nr, nbytes)
         last_stats[0] = ctx.finish_bucketing()   # this rank's own super-k-mers (before the exchange adds imported chunks)
         if world > 1:
             gdist.exchange_and_import(ctx, owner, rank, world, ext)
@@ -212,7 +242,7 @@ def run_ours(args):
 
     def step_host():
         ctx.reset()
-        ctx.push_reads_ptr(h_data.data_ptr(), h_off.data_ptr(), n_reads)
+        ctx.push_reads_ptr(h_data.data_ptr(), h_off.data_ptr(), n_reads)   # the library splits it into double-buffered H2D batches
         ctx.finish_bucketing()
         if world > 1:
             gdist.exchange_and_import(ctx, owner, rank, world, ext)
@@ -281,26 +311,28 @@ def run_ours(args):
                     "frac_of_770_GBps": sent_max / (ex_ms * 1e-3) / 1e9 / 770.0 if ex_ms > 0 else None}
 
     # ---- e2e through the C ABI with host buffers
-    for _ in range(2):
-        step_host().release()
-    e2e_times = []
-    d2h = 0
-    for _ in range(args.steps):
-        l2_flush()
-        barrier()
-        t0 = time.perf_counter()
-        tab = step_host()
-        torch.cuda.synchronize()
-        e2e_times.append(time.perf_counter() - t0)
-        d2h = int(tab.keys_lo.nbytes + tab.count_flags.nbytes + tab.unit_offsets.nbytes)
-        tab.release()
-    e2e_ms = float(np.mean(e2e_times)) * 1e3
-    t = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_ms = float(t.item())
-    e2e_val = (n_bases * world) / (e2e_ms * 1e-3) / 1e9
-    h2d = int(data.nbytes + offsets.nbytes)
+    e2e = None
+    if h_data is not None:
+        for _ in range(2):
+            step_host().release()
+        e2e_times = []
+        d2h = 0
+        for _ in range(args.steps):
+            l2_flush()
+            barrier()
+            t0 = time.perf_counter()
+            tab = step_host()
+            torch.cuda.synchronize()
+            e2e_times.append(time.perf_counter() - t0)
+            d2h = int(tab.keys_lo.nbytes + tab.count_flags.nbytes + tab.unit_offsets.nbytes)
+            tab.release()
+        e2e_ms = float(np.mean(e2e_times)) * 1e3
+        t = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+        e2e = {"value": (n_bases * world) / (e2e_ms * 1e-3) / 1e9, "unit": "Gbases/s",
+               "h2d_bytes_per_step": int(h_data.numel() + h_off.numel() * 8), "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms}
 
     # ---- roofline of the dominant kernel (largest device time in the per-kernel pass)
     peak, peak_kind = measured_peak()
@@ -338,14 +370,13 @@ def run_ours(args):
         "metric": "build Gbases/s (bucketing+k-mer merge)", "value": value, "unit": "Gbases/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": f"C2 per GPU: {n_reads} x {READ_LEN} bp reads (30x of {GENOME_PER_GPU * world} bp genome, 1% errors), "
+        "config": {"workload": f"{wl.upper()} per GPU: {n_reads} x {READ_LEN} bp reads (30x of {genome_len} bp genome, {seed_note}), "
                                f"k={K} m={M} -s {S} seq-hash, buckets {1 << b1}(+1) x {1 << b2}",
                    "l2": "flushed (256 MB write) between timed steps", "reads_per_gpu": n_reads,
                    "parallelism": f"bucket-owner x{world}" if world > 1 else "single GPU",
                    "exchange": {"peer": "k_peer_push over NVLink peer memory (CUDA IPC)", "nccl": "NCCL all_to_all_single",
                                 "none": "none"}[transport]},
-        "e2e": {"value": e2e_val, "unit": "Gbases/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": e2e_ms},
+        "e2e": e2e,
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,
@@ -354,7 +385,7 @@ def run_ours(args):
         "counts": {"bases_per_gpu": n_bases, "superkmers": int(st.n_superkmers), "kmer_records": int(st.n_kmers),
                    "unique": int(unique), "kept": int(n_entries)},
     }
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and wl == "c2" and not args.no_cpu_baseline:
         from oracle import oracle as O
 
         sr = args.sample_reads
@@ -383,7 +414,10 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--reads-per-gpu", type=int, default=READS_PER_GPU)
+    ap.add_argument("--reads-per-gpu", type=int, default=0, help="default: 1 M (c2) / 20 M (c4)")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c4"],
+                    help="c2 = BASELINE configs[1] (the bench line); c4 = a slice of configs[3] (human-scale shape, big merge units)")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer pass (large c4 slices)")
     ap.add_argument("--sample-reads", type=int, default=READS_PER_GPU, help="reads per CPU pass (default: the whole C2 batch)")
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="CPU baseline: repeat passes until this much CPU wall time")
     ap.add_argument("--no-cpu-baseline", action="store_true")

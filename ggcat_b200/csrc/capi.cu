@@ -148,6 +148,7 @@ struct ggcat_b200_ctx {
     std::vector<Chunk *> chunks;
     std::vector<Chunk *> chunk_pool;  // recycled local chunks (device buffers kept)
     // phase-2 workspace
+    DevBuf d_unit_n, d_static_off, d_unit_fill;
     DevBuf d_views, d_work[3], d_scratch, out_keys, out_cf, out_keys2, out_cf2, cursor, unit_out_off,
         unit_out_cnt, unit_final_off, overflow, d_retry, d_partmeta, d_recs, fin_tmp_keys, fin_tmp_cf, out_hi, out_hi2, unit_keys, unit_cols, col_off, out_coloff, out_colors;
     unsigned long long *h_pinned = nullptr;  // small pinned staging (16 u64)
@@ -402,7 +403,7 @@ int32_t merge_range_device_wide(ggcat_b200_ctx *c, uint32_t first_bucket, uint32
 
 constexpr uint32_t PART_CAP = 6144;       // records a key partition may hold (= capacity of the 8192-slot shared table)
 constexpr uint32_t PART_TARGET = 4096;    // partitions per big unit = pow2 >= records / PART_TARGET
-constexpr int FIN_THREADS = 512, FIN_SCAP = 3072;
+constexpr int FIN_THREADS = 512, FIN_BCAP = 6144;
 
 int32_t merge_range_device(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_buckets, uint64_t *n_entries,
                            uint64_t *unique, uint64_t *total, PartBase pb = PartBase()) {
@@ -515,15 +516,11 @@ int32_t merge_range_device(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_
     const uint64_t cap = std::max<uint64_t>(tot_kmers, 1);
     CU(c->out_keys.reserve(cap * 8)); CU(c->out_cf.reserve(cap * 4));
     CU(c->cursor.reserve(64)); CU(c->overflow.reserve(16));
-    CU(c->d_retry.reserve(((size_t)nu + 2) * 4 * 3));  // three lists: [0] = count, [1..] = unit ids
-    uint32_t *retry_cnt = c->d_retry.as<uint32_t>(), *retry = retry_cnt + 1;
-    uint32_t *retry2_cnt = retry_cnt + nu + 2, *retry2 = retry2_cnt + 1;
-    uint32_t *retry3_cnt = retry2_cnt + nu + 2, *retry3 = retry3_cnt + 1;   // big units with an overflowed partition
+    CU(c->d_retry.reserve(((size_t)nu + 2) * 4));  // [0] = count, [1..] = unit ids
+    uint32_t *retry3_cnt = c->d_retry.as<uint32_t>(), *retry3 = retry3_cnt + 1;   // big units with an overflowed partition
     if (!big.empty()) tiers.push_back(make_tier(retry3, big.size(), retry3_cnt, big[0].first));
     for (const Tier &tr : tiers) scratch_u64 = std::max(scratch_u64, tr.per_cta * tr.grid);
     CU(c->d_scratch.reserve(scratch_u64 * 8));
-    CU(cudaMemsetAsync(retry_cnt, 0, 4, st));
-    CU(cudaMemsetAsync(retry2_cnt, 0, 4, st));
     CU(cudaMemsetAsync(retry3_cnt, 0, 4, st));
     CU(c->unit_out_off.reserve(((size_t)n_slots + 1) * 8)); CU(c->unit_out_cnt.reserve(((size_t)n_slots + 1) * 4));
     if (pb.ub == 0) CU(c->unit_final_off.reserve(((size_t)c->P.n_units + 2) * 8));
@@ -531,10 +528,24 @@ int32_t merge_range_device(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_
     CU(cudaMemsetAsync(c->overflow.p, 0, 16, st));
     CU(cudaMemsetAsync(c->unit_out_off.p, 0, ((size_t)n_slots + 1) * 8, st));
     CU(cudaMemsetAsync(c->unit_out_cnt.p, 0, ((size_t)n_slots + 1) * 4, st));
+    // every unit owns the region [static_off[u], static_off[u] + records(u)) of the part's output buffers
+    {
+        std::vector<uint32_t> un(nu);
+        std::vector<uint64_t> so((size_t)nu + 1);
+        uint64_t acc = 0;
+        for (uint32_t i = 0; i < nu; i++) { un[i] = (uint32_t)unit_n[i]; so[i] = acc; acc += unit_n[i]; }
+        so[nu] = acc;
+        CU(c->d_unit_n.reserve((size_t)nu * 4)); CU(c->d_static_off.reserve(((size_t)nu + 1) * 8)); CU(c->d_unit_fill.reserve((size_t)nu * 4));
+        CU(cudaMemcpyAsync(c->d_unit_n.p, un.data(), (size_t)nu * 4, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(c->d_static_off.p, so.data(), ((size_t)nu + 1) * 8, cudaMemcpyHostToDevice, st));
+        CU(cudaMemsetAsync(c->d_unit_fill.p, 0, (size_t)nu * 4, st));
+    }
+    const uint32_t *d_unit_n = c->d_unit_n.as<uint32_t>();
     MergeOut out;
     out.keys = c->out_keys.as<uint64_t>(); out.count_flags = c->out_cf.as<uint32_t>();
     out.cursor = c->cursor.as<unsigned long long>(); out.unit_out_off = c->unit_out_off.as<uint64_t>();
-    out.unit_out_cnt = c->unit_out_cnt.as<uint32_t>(); out.capacity = cap; out.overflow = c->overflow.as<uint32_t>();
+    out.unit_out_cnt = c->unit_out_cnt.as<uint32_t>(); out.overflow = c->overflow.as<uint32_t>();
+    out.static_off = c->d_static_off.as<uint64_t>(); out.unit_fill = c->d_unit_fill.as<uint32_t>();
     out.slot_of_unit = d_slot_of_unit;
     const ChunkView *dv = c->d_views.as<ChunkView>();
     const uint32_t nch = (uint32_t)views.size();
@@ -547,7 +558,7 @@ int32_t merge_range_device(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_
             CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             const unsigned grid = (unsigned)std::min<size_t>(work[0].size(), (size_t)c->sm_count * 2 * 8);
             kern<<<grid, SM_THREADS_S, smem, st>>>(dv, nch, c->d_work[0].as<uint32_t>(), (uint32_t)work[0].size(), u0, P, ms, out,
-                                                   retry, retry_cnt, nullptr, 0, PartSrc(), nullptr);
+                                                   d_unit_n, nullptr, 0, PartSrc(), nullptr);
         }
         if (!work[1].empty()) {
             LaunchTimer t(c, F_MERGE_HASH);
@@ -556,15 +567,7 @@ int32_t merge_range_device(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_
             CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             const unsigned grid = (unsigned)std::min<size_t>(work[1].size(), (size_t)c->sm_count * 8);
             kern<<<grid, SM_THREADS_L, smem, st>>>(dv, nch, c->d_work[1].as<uint32_t>(), (uint32_t)work[1].size(), u0, P, ms, out,
-                                                   retry, retry_cnt, nullptr, 0, PartSrc(), nullptr);
-        }
-        if (!work[0].empty() || !work[1].empty()) {
-            // units whose survivors did not leave room for the in-table sort: redo with the sort kernel
-            LaunchTimer t(c, F_MERGE_SMEM);
-            auto kern = k_merge_units<SM_THREADS_L, SM_CAP_L, false>;
-            const size_t smem = merge_smem_bytes<SM_THREADS_L, SM_CAP_L>(false);
-            CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            kern<<<(unsigned)c->sm_count, SM_THREADS_L, smem, st>>>(dv, nch, retry, 0u, u0, P, ms, out, nullptr, 0, retry_cnt);
+                                                   d_unit_n, nullptr, 0, PartSrc(), nullptr);
         }
         if (!big.empty()) {
             {
@@ -577,12 +580,12 @@ int32_t merge_range_device(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_
                 LaunchTimer t(c, F_MERGE_HASH_PART);
                 PartSrc ps;
                 ps.recs = c->d_recs.as<uint64_t>(); ps.pcount = d_pcount; ps.part_slot = d_part_slot; ps.part_big = d_part_big;
-                ps.big_ovf = d_big_ovf; ps.pcap = PART_CAP; ps.pad = 0;
+                ps.big_ovf = d_big_ovf; ps.big_unit = d_big_unit; ps.pcap = PART_CAP; ps.pad = 0;
                 auto kern = k_merge_hash<SM_THREADS_S, HASH_TS_S, SRC_RECORDS>;
                 const size_t smem = merge_hash_smem_bytes<SM_THREADS_S, HASH_TS_S>();
                 CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 const unsigned grid = (unsigned)std::min<size_t>(n_parts, (size_t)c->sm_count * 2 * 8);
-                kern<<<grid, SM_THREADS_S, smem, st>>>(dv, nch, nullptr, n_parts, u0, P, ms, out, nullptr, nullptr, nullptr, 0, ps, nullptr);
+                kern<<<grid, SM_THREADS_S, smem, st>>>(dv, nch, nullptr, n_parts, u0, P, ms, out, d_unit_n, nullptr, 0, ps, nullptr);
             }
         }
         work[0].clear(); work[1].clear();
@@ -607,19 +610,11 @@ int32_t merge_range_device(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_
         auto sortk = k_merge_units<GL_THREADS, 0, true>;
         const size_t smem_sort = merge_smem_bytes<GL_THREADS, 0>(true);
         if (hash_mode) {
-            {
-                LaunchTimer t(c, F_MERGE_HASH_GLOBAL);
-                auto kern = k_merge_hash<GL_THREADS, 0>;
-                kern<<<tr.grid, GL_THREADS, merge_hash_smem_bytes<GL_THREADS, 0>(), st>>>(
-                    dv, nch, tr.wl, (uint32_t)tr.count, u0, P, ms, out, retry2, retry2_cnt, c->d_scratch.as<uint64_t>(), tr.per_cta,
-                    PartSrc(), tr.count_dev);
-            }
-            {   // survivors > half the table: redo those units with the global-scratch sort
-                LaunchTimer t(c, F_MERGE_GLOBAL);
-                sortk<<<tr.grid, GL_THREADS, smem_sort, st>>>(dv, nch, retry2, 0u, u0, P, ms, out, c->d_scratch.as<uint64_t>(),
-                                                             tr.per_cta, retry2_cnt);
-            }
-            CU(cudaMemsetAsync(retry2_cnt, 0, 4, st));
+            LaunchTimer t(c, F_MERGE_HASH_GLOBAL);
+            auto kern = k_merge_hash<GL_THREADS, 0>;
+            kern<<<tr.grid, GL_THREADS, merge_hash_smem_bytes<GL_THREADS, 0>(), st>>>(
+                dv, nch, tr.wl, (uint32_t)tr.count, u0, P, ms, out, d_unit_n, c->d_scratch.as<uint64_t>(), tr.per_cta,
+                PartSrc(), tr.count_dev);
         } else {
             LaunchTimer t(c, F_MERGE_GLOBAL);
             sortk<<<tr.grid, GL_THREADS, smem_sort, st>>>(dv, nch, tr.wl, (uint32_t)tr.count, u0, P, ms, out, c->d_scratch.as<uint64_t>(),
@@ -630,21 +625,25 @@ int32_t merge_range_device(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_
     // ---- unit-ordered final layout (parts append at entry pb.eb / unit pb.ub)
     const uint64_t rec_total = std::max(cap, pb.cap_total);
     if (pb.ub == 0) TRY(final_reserve(c, final_estimate(c, rec_total), 0, false));
-    if (!big.empty()) { CU(c->fin_tmp_keys.reserve(cap * 8)); CU(c->fin_tmp_cf.reserve(cap * 4)); }
+    CU(c->fin_tmp_keys.reserve(cap * 8)); CU(c->fin_tmp_cf.reserve(cap * 4));   // units sorted in global memory (> FIN_BCAP survivors)
     uint32_t ovf = 0;
     for (int attempt = 0;; attempt++) {
         {
-            LaunchTimer t(c, F_GATHER, 2);
+            LaunchTimer t(c, F_GATHER, 3);
             uint64_t *foff = c->unit_final_off.as<uint64_t>() + pb.ub;
             k_scan_unit_slots<<<1, 1024, 0, st>>>(c->unit_out_cnt.as<uint32_t>(), d_slot_of_unit, foff, nu, pb.eb);
-            auto kern = k_finish_units<FIN_THREADS, FIN_SCAP>;
-            const size_t smem = finish_units_smem_bytes<FIN_THREADS, FIN_SCAP>();
+            FinishArgs fa;
+            fa.src_keys = c->out_keys.as<uint64_t>(); fa.src_cf = c->out_cf.as<uint32_t>();
+            fa.slot_off = c->unit_out_off.as<uint64_t>(); fa.slot_cnt = c->unit_out_cnt.as<uint32_t>();
+            fa.slot_of_unit = d_slot_of_unit; fa.dst_off = foff;
+            fa.dst_keys = c->out_keys2.as<uint64_t>(); fa.dst_cf = c->out_cf2.as<uint32_t>();
+            fa.tmp_keys = c->fin_tmp_keys.as<uint64_t>(); fa.tmp_cf = c->fin_tmp_cf.as<uint32_t>();
+            fa.n_units = nu; fa.kbits = 2 * P.k; fa.capacity = c->fin_cap; fa.overflow = c->overflow.as<uint32_t>();
+            k_finish_small<<<(unsigned)std::min<uint32_t>((nu + FIN_WARPS - 1) / FIN_WARPS, (uint32_t)c->sm_count * 16), FIN_WARPS * 32, 0, st>>>(fa);
+            auto kern = k_finish_units<FIN_THREADS, FIN_BCAP>;
+            const size_t smem = finish_units_smem_bytes<FIN_THREADS, FIN_BCAP>();
             CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            const uint32_t end_bit = std::min(64u, (2 * P.k + 7) & ~7u);
-            kern<<<(unsigned)std::min<uint32_t>(nu, (uint32_t)c->sm_count * 2 * 8), FIN_THREADS, smem, st>>>(
-                c->out_keys.as<uint64_t>(), c->out_cf.as<uint32_t>(), c->unit_out_off.as<uint64_t>(), c->unit_out_cnt.as<uint32_t>(),
-                d_slot_of_unit, foff, c->out_keys2.as<uint64_t>(), c->out_cf2.as<uint32_t>(), c->fin_tmp_keys.as<uint64_t>(),
-                c->fin_tmp_cf.as<uint32_t>(), nu, end_bit, c->fin_cap, c->overflow.as<uint32_t>());
+            kern<<<(unsigned)std::min<uint32_t>(nu, (uint32_t)c->sm_count * 2 * 4), FIN_THREADS, smem, st>>>(fa);
         }
         CU(cudaMemcpyAsync(c->h_pinned, c->cursor.p, 24, cudaMemcpyDeviceToHost, st));
         CU(cudaMemcpyAsync(c->h_pinned + 8, c->overflow.p, 4, cudaMemcpyDeviceToHost, st));
@@ -979,7 +978,7 @@ void ggcat_b200_destroy(ggcat_b200_ctx *c) {
     for (DevBuf *b : {&c->d_ascii, &c->d_offsets, &c->d_colors, &c->pk, &c->bad, &c->brk, &c->ent, &c->tile_cnt, &c->tile_sbase,
                       &c->tmp, &c->tmp_color, &c->cur_cnt, &c->cur_words, &c->totals, &c->d_views, &c->d_work[0], &c->d_work[1],
                       &c->d_work[2], &c->d_scratch, &c->out_keys, &c->out_cf, &c->out_keys2, &c->out_cf2,
-                      &c->cursor, &c->unit_out_off, &c->unit_out_cnt, &c->unit_final_off, &c->overflow, &c->d_retry,
+                      &c->d_unit_n, &c->d_static_off, &c->d_unit_fill, &c->cursor, &c->unit_out_off, &c->unit_out_cnt, &c->unit_final_off, &c->overflow, &c->d_retry,
                       &c->d_partmeta, &c->d_recs, &c->fin_tmp_keys, &c->fin_tmp_cf,
                       &c->out_hi, &c->out_hi2, &c->unit_keys, &c->unit_cols, &c->col_off, &c->out_coloff, &c->out_colors})
         b->release();
@@ -1511,6 +1510,7 @@ int32_t ggcat_b200_peer_exchange(ggcat_b200_ctx *c) {
     for (uint32_t d = 0; d < W; d++) {
         if (d == me) continue;
         const uint32_t fu = first_unit_of(d), nu = first_unit_of(d + 1) - fu;
+        const uint32_t slot = (d + W - me - 1) % W;   // 0 .. W-2: the grid of k_peer_push is split over the destinations
         const uint64_t s_meta = align16(3ull * nu * 4), s_uoff = align16(((uint64_t)nu + 2) * 4);
         uint8_t *hs = ps.h_stage + (size_t)d * tbl;
         memset(hs, 0, tbl);
@@ -1532,16 +1532,16 @@ int32_t ggcat_b200_peer_exchange(ggcat_b200_ctx *c) {
             for (uint32_t j = 0; j < nsl; j++) {
                 const Chunk *ch = local[j];
                 uint8_t *meta = dst + PEER_META_OFF + (uint64_t)j * s_meta;
-                jobs[n_jobs++] = {reinterpret_cast<const uint8_t *>(ch->d_unit_cnt + fu), meta, (uint64_t)nu * 4};
-                jobs[n_jobs++] = {reinterpret_cast<const uint8_t *>(ch->d_unit_words + fu), meta + (uint64_t)nu * 4, (uint64_t)nu * 4};
-                jobs[n_jobs++] = {reinterpret_cast<const uint8_t *>(ch->d_unit_kmers + fu), meta + (uint64_t)nu * 8, (uint64_t)nu * 4};
+                jobs[n_jobs++] = {reinterpret_cast<const uint8_t *>(ch->d_unit_cnt + fu), meta, (uint64_t)nu * 4, slot, 0u};
+                jobs[n_jobs++] = {reinterpret_cast<const uint8_t *>(ch->d_unit_words + fu), meta + (uint64_t)nu * 4, (uint64_t)nu * 4, slot, 0u};
+                jobs[n_jobs++] = {reinterpret_cast<const uint8_t *>(ch->d_unit_kmers + fu), meta + (uint64_t)nu * 8, (uint64_t)nu * 4, slot, 0u};
                 if (tb[j].n_sk) {
-                    jobs[n_jobs++] = {reinterpret_cast<const uint8_t *>(ch->d_desc + ch->h_off[fu]), dst + tb[j].desc_off, tb[j].n_sk * 16};
-                    jobs[n_jobs++] = {reinterpret_cast<const uint8_t *>(ch->d_payload + ch->h_woff[fu]), dst + tb[j].pay_off, tb[j].n_words * 4};
+                    jobs[n_jobs++] = {reinterpret_cast<const uint8_t *>(ch->d_desc + ch->h_off[fu]), dst + tb[j].desc_off, tb[j].n_sk * 16, slot, 0u};
+                    jobs[n_jobs++] = {reinterpret_cast<const uint8_t *>(ch->d_payload + ch->h_woff[fu]), dst + tb[j].pay_off, tb[j].n_words * 4, slot, 0u};
                 }
             }
         }
-        jobs[n_jobs++] = {ps.d_stage.as<uint8_t>() + (size_t)d * tbl, dst, (uint64_t)(PEER_TABLE_OFF + (uint64_t)nsl * 64)};
+        jobs[n_jobs++] = {ps.d_stage.as<uint8_t>() + (size_t)d * tbl, dst, (uint64_t)(PEER_TABLE_OFF + (uint64_t)nsl * 64), slot, 0u};
     }
     for (uint32_t j = 0; j < n_jobs; j++) ps.last_sent += jobs[j].bytes;
     CU(cudaMemcpyAsync(ps.d_stage.p, ps.h_stage, (size_t)W * tbl, cudaMemcpyHostToDevice, st));
@@ -1554,7 +1554,7 @@ int32_t ggcat_b200_peer_exchange(ggcat_b200_ctx *c) {
         LaunchTimer t(c, F_PEER, 3);
         // every peer has finished merging what we sent last time -> push -> tell the owners, wait for our sources
         k_peer_sync<<<1, PEER_MAX_WORLD, 0, st>>>(hp, me, W, 0u, epoch - 1, ps.d_err.as<uint32_t>(), timeout_ns);
-        k_peer_push<<<(unsigned)c->sm_count * 4, 256, 0, st>>>(ps.d_jobs.as<PeerJob>(), n_jobs);
+        k_peer_push<<<(unsigned)c->sm_count * 4, 256, 0, st>>>(ps.d_jobs.as<PeerJob>(), n_jobs, W - 1);
         k_peer_sync<<<1, PEER_MAX_WORLD, 0, st>>>(hp, me, W, 1u, epoch, ps.d_err.as<uint32_t>(), timeout_ns);
     }
     // ---- receive: headers, slice tables and per-unit counts of every source, one read-back in the common case

@@ -28,17 +28,28 @@ struct ChunkView {
     uint32_t pad;
 };
 
+// Output of the merge kernels, before the unit-ordered final layout.  Every unit owns the region
+// [static_off[u], static_off[u] + records(u)) of keys/count_flags (survivors <= distinct <= records), so no kernel
+// waits for a global allocation: a CTA that owns a whole unit writes at the region's start, the key partitions of a
+// big unit share the region through the unit's fill counter.  cursor[] are statistics only (fire-and-forget atomics).
+constexpr uint32_t SLOT_SORTED = 0x80000000u;   // flag in unit_out_cnt: the slot's entries are already ordered by key
 struct MergeOut {
     uint64_t *keys;                     // survivors: canonical k-mer (2k bits)
     uint32_t *count_flags;              // multiplicity (30 bits, saturating) | flags << 30
     unsigned long long *cursor;         // [0] entries written, [1] distinct keys, [2] k-mer occurrences
-    uint64_t *unit_out_off;             // per unit (relative to first unit of the launch): offset
-    uint32_t *unit_out_cnt;             //                                                   count
-    uint64_t capacity;                  // entries available in keys/count_flags
-    uint32_t *overflow;                 // set to 1 if capacity was exceeded
+    uint64_t *unit_out_off;             // per output slot: offset
+    uint32_t *unit_out_cnt;             //                  count | SLOT_SORTED
+    const uint64_t *static_off;         // per unit (relative to the first unit of the launch): start of its region
+    uint32_t *unit_fill;                // per unit: entries handed out inside the region (key partitions)
+    uint32_t *overflow;                 // set to 2 if a unit was routed to a kernel that cannot hold it
     const uint32_t *slot_of_unit;       // output slot of a unit (big units own several slots, one per key partition);
                                         // NULL: slot = unit index relative to the first unit of the launch
     __device__ __forceinline__ uint32_t slot(uint32_t unit_rel) const { return slot_of_unit ? slot_of_unit[unit_rel] : unit_rel; }
+    __device__ __forceinline__ void stats(uint32_t survivors, uint32_t distinct, uint32_t records) const {
+        atomicAdd(&cursor[0], (unsigned long long)survivors);
+        atomicAdd(&cursor[1], (unsigned long long)distinct);
+        atomicAdd(&cursor[2], (unsigned long long)records);
+    }
 };
 
 // Key partitions of big units (units that do not fit a shared-memory table): k_partition_units expands the unit once
@@ -50,6 +61,7 @@ struct PartSrc {
     const uint32_t *pcount;      // [n_parts_total] records per partition
     const uint32_t *part_slot;   // work item -> output slot
     const uint32_t *part_big;    // work item -> index of its big unit
+    const uint32_t *big_unit;    // [n_big] unit id
     const uint32_t *big_ovf;     // [n_big] 1 = a partition overflowed, the unit is redone by the global-table kernel
     uint32_t pcap;
     uint32_t pad;
@@ -160,7 +172,7 @@ __device__ uint64_t *block_radix_sort64(uint64_t *A, uint64_t *B, uint32_t n, ui
 // not alias S).  Survivors go to out.keys/out.count_flags at an atomically reserved range.
 template <int THREADS>
 __device__ void block_reduce_filter(const uint64_t *S, uint32_t *aux, uint32_t n, uint32_t min_mult, const MergeOut &out,
-                                    uint32_t unit_rel, uint32_t *s_scan, unsigned long long *s_base) {
+                                    uint32_t unit_rel, uint32_t *s_scan) {
     const uint32_t tid = threadIdx.x;
     uint32_t my_keep = 0, my_heads = 0;
     for (uint32_t i = tid; i < n; i += THREADS) {
@@ -189,18 +201,13 @@ __device__ void block_reduce_filter(const uint64_t *S, uint32_t *aux, uint32_t n
     block_exclusive_scan<THREADS>(my_keep, s_scan, &tot);  // tot = survivors
     uint32_t tot_heads;
     block_exclusive_scan<THREADS>(my_heads, s_scan, &tot_heads);
+    const unsigned long long gbase = out.static_off[unit_rel];
     if (tid == 0) {
-        unsigned long long b = atomicAdd(&out.cursor[0], (unsigned long long)tot);
-        atomicAdd(&out.cursor[1], (unsigned long long)tot_heads);
-        atomicAdd(&out.cursor[2], (unsigned long long)n);
-        *s_base = b;
-        out.unit_out_off[unit_rel] = b;
-        out.unit_out_cnt[unit_rel] = tot;
-        if (b + tot > out.capacity) *out.overflow = 1u;
+        out.stats(tot, tot_heads, n);
+        const uint32_t sl = out.slot(unit_rel);
+        out.unit_out_off[sl] = gbase;
+        out.unit_out_cnt[sl] = tot | SLOT_SORTED;
     }
-    __syncthreads();
-    const unsigned long long gbase = *s_base;
-    if (gbase + tot > out.capacity) return;  // overflow reported; nothing written
     uint32_t running = 0;
     for (uint32_t base = 0; base < n; base += THREADS) {
         const uint32_t i = base + tid;
@@ -229,8 +236,7 @@ k_merge_units(const ChunkView *__restrict__ chunks, uint32_t n_chunks, const uin
     constexpr int WARPS = THREADS / 32;
     uint32_t *hist = reinterpret_cast<uint32_t *>(smem_raw);                 // WARPS*256 u32
     uint32_t *s_scan = hist + WARPS * 256;                                    // 40 u32
-    unsigned long long *s_base = reinterpret_cast<unsigned long long *>(s_scan + 40);
-    uint64_t *sA = reinterpret_cast<uint64_t *>(s_base + 2);
+    uint64_t *sA = reinterpret_cast<uint64_t *>(s_scan + 44);
     uint64_t *sB = sA + (GLOBAL_SCRATCH ? 0 : CAP);
 
     const uint32_t tid = threadIdx.x;
@@ -277,8 +283,7 @@ k_merge_units(const ChunkView *__restrict__ chunks, uint32_t n_chunks, const uin
         uint64_t *S = block_radix_sort64<THREADS>(A, B, n, 0, end_bit, hist, s_scan);
         uint64_t *other = (S == A) ? B : A;
         // ---- reduce + filter
-        block_reduce_filter<THREADS>(S, reinterpret_cast<uint32_t *>(other), n, min_mult, out, out.slot(unit - first_unit), s_scan,
-                                     s_base);
+        block_reduce_filter<THREADS>(S, reinterpret_cast<uint32_t *>(other), n, min_mult, out, unit - first_unit, s_scan);
         __syncthreads();
     }
 }
@@ -429,65 +434,52 @@ __host__ __device__ __forceinline__ uint32_t hash_table_slots_pow2(uint32_t n) {
     return t;
 }
 
-constexpr uint32_t SORT_BINS = 512;  // bin-rank sort: bins on the top 9 key bits
 
-// TS_STATIC > 0: table of up to TS_STATIC slots in shared memory (sized per unit: hash_table_slots(n)); survivors
-// ordered by a bin-rank sort.  TS_STATIC == 0: table in this CTA's slice of a global scratch buffer (L2-resident
-// for typical units); survivors ordered by the LSD radix sort.  Units whose survivors leave no room for the sort's
-// second buffer are appended to `retry` and re-done by the sort-based kernel.
+// TS_STATIC > 0: table of up to TS_STATIC slots in shared memory (sized per unit: hash_table_slots(n)).
+// TS_STATIC == 0: table in this CTA's slice of a global scratch buffer (L2-resident for typical units).
+// After the inserts the table is scanned once (MapEntry -> multiplicity, -s filter) and the survivors are written
+// straight into the unit's output region in table order; ordering by key (part of the output contract) is the job of
+// k_finish_small / k_finish_units, which touch only the survivors.  Per unit the CTA passes 7 barriers.
 template <int THREADS, int TS_STATIC, int SRC = SRC_SUPERKMERS>
 __global__ void __launch_bounds__(THREADS)
 k_merge_hash(const ChunkView *__restrict__ chunks, uint32_t n_chunks, const uint32_t *__restrict__ work, uint32_t n_work,
-             uint32_t first_unit, DevParams P, uint32_t min_mult, MergeOut out, uint32_t *__restrict__ retry,
-             uint32_t *__restrict__ retry_count, uint64_t *__restrict__ scratch, uint64_t per_cta_u64, PartSrc ps,
-             const uint32_t *__restrict__ n_work_dev) {
+             uint32_t first_unit, DevParams P, uint32_t min_mult, MergeOut out, const uint32_t *__restrict__ unit_n,
+             uint64_t *__restrict__ scratch, uint64_t per_cta_u64, PartSrc ps, const uint32_t *__restrict__ n_work_dev) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int WARPS = THREADS / 32;
-    constexpr uint32_t SCR_BYTES = WARPS * 256 * 4;  // scratch area: descriptor staging / survivor staging + bins / radix histograms
+    constexpr uint32_t SCR_BYTES = WARPS * 256 * 4;  // scratch area: descriptor staging
     static_assert(sizeof(UnitStage<THREADS>) <= SCR_BYTES, "descriptor staging must fit the scratch area");
     uint64_t *K = reinterpret_cast<uint64_t *>(smem_raw);                      // TS keys
     uint32_t *C = reinterpret_cast<uint32_t *>(K + TS_STATIC);                 // TS counters|flags
     uint32_t *hist = C + TS_STATIC;                                            // scratch area (SCR_BYTES)
     uint32_t *s_scan = hist + WARPS * 256;                                     // 40
-    unsigned long long *s_base = reinterpret_cast<unsigned long long *>(s_scan + 40);
     UnitStage<THREADS> *stage = reinterpret_cast<UnitStage<THREADS> *>(hist);
     const uint32_t tid = threadIdx.x;
     if (n_work_dev) n_work = min(n_work, *n_work_dev);  // device-side list (big units whose partitions overflowed)
     for (uint32_t wi = blockIdx.x; wi < n_work; wi += gridDim.x) {
-        uint32_t *s_cnt = s_scan + 36;  // [0] survivors, [1] occupied slots, [2] records of the unit
-        uint32_t unit = 0, oslot, n;
+        uint32_t *s_cnt = s_scan + 36;  // [0] survivors written, [1] occupied slots, [2] region base inside the unit (partitions)
+        uint32_t unit_rel, oslot, n;
         if (SRC == SRC_RECORDS) {
             if (ps.big_ovf[ps.part_big[wi]]) continue;   // the whole unit is redone from its super-k-mers
+            unit_rel = ps.big_unit[ps.part_big[wi]] - first_unit;
             oslot = ps.part_slot[wi];
             n = min(ps.pcount[wi], ps.pcap);
             if (n == 0) continue;
         } else {
-            unit = work[wi];
-            oslot = out.slot(unit - first_unit);
-            if (tid == 0) s_cnt[2] = 0;
-            __syncthreads();
-            for (uint32_t c = tid; c < n_chunks; c += THREADS) {  // one round of load latency whatever the chunk count
-                const ChunkView &cv = chunks[c];
-                if (unit >= cv.first_unit && unit < cv.first_unit + cv.n_units) {
-                    const uint32_t v = cv.unit_kmers[unit - cv.first_unit];
-                    if (v) atomicAdd(&s_cnt[2], v);
-                }
-            }
-            __syncthreads();
-            n = s_cnt[2];
+            unit_rel = work[wi] - first_unit;
+            oslot = out.slot(unit_rel);
+            n = unit_n[unit_rel];
         }
         uint32_t TS = hash_table_slots(n);
         if (TS_STATIC == 0) {
             K = scratch + (uint64_t)blockIdx.x * per_cta_u64;
             C = reinterpret_cast<uint32_t *>(K + TS);
-        } else {
-            if (TS > (uint32_t)TS_STATIC) {  // host routes such units elsewhere
-                if (tid == 0) *out.overflow = 2u;
-                continue;
-            }
-            TS = min(TS, (uint32_t)TS_STATIC);
+        } else if (TS > (uint32_t)TS_STATIC) {  // host routes such units elsewhere
+            if (tid == 0) *out.overflow = 2u;
+            continue;
         }
-                for (uint32_t i = tid; i < TS; i += THREADS) { K[i] = HASH_EMPTY; C[i] = 0u; }
+        for (uint32_t i = tid; i < TS; i += THREADS) { K[i] = HASH_EMPTY; C[i] = 0u; }
+        if (tid < 2) s_cnt[tid] = 0;
         __syncthreads();
         if (SRC == SRC_RECORDS) {
             const uint64_t *recs = ps.recs + (uint64_t)wi * ps.pcap;
@@ -496,174 +488,79 @@ k_merge_hash(const ChunkView *__restrict__ chunks, uint32_t n_chunks, const uint
                 hash_insert(K, C, TS, r >> 2, (uint32_t)r & 3u);
             }
         } else {
-            unit_for_each_kmer64<THREADS>(chunks, n_chunks, unit, P.k, P.forward_only, stage, s_scan,
+            unit_for_each_kmer64<THREADS>(chunks, n_chunks, work[wi], P.k, P.forward_only, stage, s_scan,
                                           [&](uint64_t key, uint32_t fb) { hash_insert(K, C, TS, key, fb); });
         }
         __syncthreads();
-        // ---- scan the table once: MapEntry -> multiplicity, filter; survivors are appended to a small
-        //      staging area (in the scratch area) in arbitrary order
-        constexpr uint32_t STAGE_CAP = TS_STATIC ? (SCR_BYTES - SORT_BINS * 8) / 12 : SCR_BYTES / 12;
-        constexpr uint32_t RANK_MAX = 512;                                  // rank-sort threshold (global-table variant)
-        uint64_t *stage_k = reinterpret_cast<uint64_t *>(hist);
-        uint32_t *stage_c = reinterpret_cast<uint32_t *>(stage_k + STAGE_CAP);
-        uint32_t *bin_start = stage_c + STAGE_CAP;                          // [SORT_BINS]   (shared-table variant)
-        uint32_t *bin_cur = bin_start + SORT_BINS;                          // [SORT_BINS]
-        if (tid < 2) s_cnt[tid] = 0;
-        __syncthreads();
-        {
-            uint32_t my_occ = 0;
+        // ---- scan the table once: MapEntry -> multiplicity, filter, survivors appended to the unit's region
+        unsigned long long gbase = out.static_off[unit_rel];
+        if (SRC == SRC_RECORDS) {
+            // a key partition shares the unit's region: count first, reserve inside the region, then write
+            uint32_t my_keep = 0, my_occ = 0;
             for (uint32_t i = tid; i < TS; i += THREADS) {
                 const uint64_t kk = K[i];
                 if (kk == HASH_EMPTY) continue;
                 ++my_occ;
                 const uint32_t cc = C[i];
                 const uint32_t cnt = slot_count(cc), fl = cc >> 30;
-                const uint32_t mult = cnt >> ((fl == (READ_FLAG_INCL_BEGIN | READ_FLAG_INCL_END)) ? 1 : 0);  // map_entry.rs:79-84
-                if (mult >= min_mult) {
-                    const uint32_t idx = atomicAdd(&s_cnt[0], 1u);
-                    if (idx < STAGE_CAP) { stage_k[idx] = (kk << 2) | fl; stage_c[idx] = mult | (fl << 30); }
-                }
+                if ((cnt >> ((fl == 3u) ? 1 : 0)) >= min_mult) ++my_keep;
             }
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) my_occ += __shfl_xor_sync(0xffffffffu, my_occ, o);
-            if (lane_id() == 0 && my_occ) atomicAdd(&s_cnt[1], my_occ);
-        }
-        __syncthreads();
-        const uint32_t S = s_cnt[0], n_occ = s_cnt[1];
-        const uint32_t end_bit = min(64u, (2 * P.k + 2 + 7) & ~7u);
-        if (SRC != SRC_RECORDS && S > STAGE_CAP && S > TS / 2) {  // no room for the sort's second buffer: hand the unit to the sort-based kernel
-            if (tid == 0) retry[atomicAdd(retry_count, 1u)] = unit;
+            for (int o = 16; o > 0; o >>= 1) { my_keep += __shfl_xor_sync(0xffffffffu, my_keep, o); my_occ += __shfl_xor_sync(0xffffffffu, my_occ, o); }
+            if (lane_id() == 0) { if (my_keep) atomicAdd(&s_cnt[0], my_keep); if (my_occ) atomicAdd(&s_cnt[1], my_occ); }
             __syncthreads();
-            continue;
+            if (tid == 0) {
+                const uint32_t S = s_cnt[0];
+                s_cnt[2] = atomicAdd(&out.unit_fill[unit_rel], S);
+                out.stats(S, s_cnt[1], n);
+                out.unit_out_off[oslot] = gbase + s_cnt[2];
+                out.unit_out_cnt[oslot] = S;
+                s_cnt[0] = 0;
+            }
+            __syncthreads();
+            gbase += s_cnt[2];
         }
-        if (tid == 0) {
-            const unsigned long long b = atomicAdd(&out.cursor[0], (unsigned long long)S);
-            atomicAdd(&out.cursor[1], (unsigned long long)n_occ);
-            atomicAdd(&out.cursor[2], (unsigned long long)n);
-            *s_base = b;
-            out.unit_out_off[oslot] = b;
-            out.unit_out_cnt[oslot] = S;
-            if (b + S > out.capacity) *out.overflow = 1u;
-        }
-        __syncthreads();
-        const unsigned long long gbase = *s_base;
-        const bool room = gbase + S <= out.capacity;
-        if (SRC == SRC_RECORDS) {
-            // a key partition: survivors leave in any order, k_finish_units sorts the whole unit
-            if (room) {
-                if (S <= STAGE_CAP) {
-                    for (uint32_t i = tid; i < S; i += THREADS) { out.keys[gbase + i] = stage_k[i] >> 2; out.count_flags[gbase + i] = stage_c[i]; }
-                } else {
-                    if (tid == 0) s_cnt[0] = 0;
-                    __syncthreads();
-                    for (uint32_t base = 0; base < TS; base += THREADS) {
-                        const uint32_t i = base + tid;
-                        const uint64_t kk = K[i];
-                        uint32_t cf = 0;
-                        if (kk != HASH_EMPTY) {
-                            const uint32_t cc = C[i];
-                            const uint32_t cnt = slot_count(cc), fl = cc >> 30;
-                            const uint32_t mult = cnt >> ((fl == 3u) ? 1 : 0);
-                            if (mult >= min_mult) cf = mult | (fl << 30);
-                        }
-                        const uint32_t bal = __ballot_sync(0xffffffffu, cf != 0);
-                        uint32_t wb = 0;
-                        if (lane_id() == 0 && bal) wb = atomicAdd(&s_cnt[0], (uint32_t)__popc(bal));
-                        wb = __shfl_sync(0xffffffffu, wb, 0);
-                        if (cf) {
-                            const unsigned long long o = gbase + wb + __popc(bal & ((1u << lane_id()) - 1u));
-                            out.keys[o] = kk; out.count_flags[o] = cf;
-                        }
+        {
+            uint32_t my_occ = 0;
+            for (uint32_t base = 0; base < TS; base += THREADS) {
+                const uint32_t i = base + tid;
+                uint64_t kk = HASH_EMPTY;
+                uint32_t cf = 0;
+                if (i < TS) {
+                    kk = K[i];
+                    if (kk != HASH_EMPTY) {
+                        ++my_occ;
+                        const uint32_t cc = C[i];
+                        const uint32_t cnt = slot_count(cc), fl = cc >> 30;
+                        const uint32_t mult = cnt >> ((fl == (READ_FLAG_INCL_BEGIN | READ_FLAG_INCL_END)) ? 1 : 0);  // map_entry.rs:79-84
+                        if (mult >= min_mult) cf = (mult > 0x3FFFFFFFu ? 0x3FFFFFFFu : mult) | (fl << 30);
+                    }
+                }
+                const uint32_t bal = __ballot_sync(0xffffffffu, cf != 0);
+                if (bal) {
+                    uint32_t wb = 0;
+                    if (lane_id() == 0) wb = atomicAdd(&s_cnt[0], (uint32_t)__popc(bal));
+                    wb = __shfl_sync(0xffffffffu, wb, 0);
+                    if (cf) {
+                        const unsigned long long o = gbase + wb + __popc(bal & ((1u << lane_id()) - 1u));
+                        out.keys[o] = kk; out.count_flags[o] = cf;
                     }
                 }
             }
-            __syncthreads();
-            continue;
-        }
-        // many survivors: in-place block-scan compaction of the table itself -> K[0..S), C[0..S)
-        auto compact_table = [&]() {
-            uint32_t running = 0;
-            for (uint32_t base = 0; base < TS; base += THREADS) {
-                const uint32_t i = base + tid;
-                const uint64_t kk = K[i];
-                const uint32_t cc = C[i];
-                uint32_t cf = 0, fl = 0;
-                if (kk != HASH_EMPTY) {
-                    const uint32_t cnt = slot_count(cc);
-                    fl = cc >> 30;
-                    const uint32_t mult = cnt >> ((fl == (READ_FLAG_INCL_BEGIN | READ_FLAG_INCL_END)) ? 1 : 0);
-                    if (mult >= min_mult) cf = mult | (fl << 30);
-                }
-                uint32_t tot;
-                const uint32_t p = block_exclusive_scan<THREADS>(cf ? 1u : 0u, s_scan, &tot);  // all reads precede writes
-                if (cf) { K[running + p] = (kk << 2) | fl; C[running + p] = cf; }
-                running += tot;
-            }
-            __syncthreads();
-        };
-        if (TS_STATIC != 0) {
-            // ---- bin-rank sort: scatter the survivors into SORT_BINS bins on their top key bits (counting sort),
-            //      then every survivor's position = bin start + number of smaller keys inside its bin.
-            const uint64_t *src_k; const uint32_t *src_c;
-            uint64_t *dst_k; uint32_t *dst_c;
-            if (S <= STAGE_CAP) { src_k = stage_k; src_c = stage_c; dst_k = K; dst_c = C; }
-            else { compact_table(); src_k = K; src_c = C; dst_k = K + TS / 2; dst_c = C + TS / 2; }
-            const uint32_t bshift = 2 * P.k + 2 > 9 ? 2 * P.k + 2 - 9 : 0;  // staged keys carry 2 flag bits
-            for (uint32_t i = tid; i < SORT_BINS; i += THREADS) bin_cur[i] = 0;
-            __syncthreads();
-            for (uint32_t i = tid; i < S; i += THREADS) atomicAdd(&bin_cur[(uint32_t)(src_k[i] >> bshift) & (SORT_BINS - 1)], 1u);
-            __syncthreads();
-            {
-                uint32_t v = 0;
-                if (tid < SORT_BINS) v = bin_cur[tid];
-                uint32_t tot;
-                const uint32_t p = block_exclusive_scan<THREADS>(v, s_scan, &tot);
-                if (tid < SORT_BINS) { bin_start[tid] = p; bin_cur[tid] = p; }
-            }
-            __syncthreads();
-            for (uint32_t i = tid; i < S; i += THREADS) {
-                const uint64_t r = src_k[i];
-                const uint32_t pos = atomicAdd(&bin_cur[(uint32_t)(r >> bshift) & (SORT_BINS - 1)], 1u);
-                dst_k[pos] = r; dst_c[pos] = src_c[i];
-            }
-            __syncthreads();
-            if (room) {
-                for (uint32_t i = tid; i < S; i += THREADS) {
-                    const uint64_t r = dst_k[i];
-                    const uint32_t b = (uint32_t)(r >> bshift) & (SORT_BINS - 1);
-                    const uint32_t lo = bin_start[b], hi = bin_cur[b];   // bin_cur == end of the bin after the scatter
-                    uint32_t rank = lo;
-                    for (uint32_t j = lo; j < hi; j++) rank += dst_k[j] < r ? 1u : 0u;
-                    out.keys[gbase + rank] = r >> 2;
-                    out.count_flags[gbase + rank] = dst_c[i];
-                }
-            }
-        } else if (S <= RANK_MAX) {
-            // rank sort: keys are distinct, so rank = number of smaller keys is the sorted position
-            if (room) {
-                for (uint32_t i = tid; i < S; i += THREADS) {
-                    const uint64_t r = stage_k[i];
-                    uint32_t rank = 0;
-                    for (uint32_t j = 0; j < S; j++) rank += stage_k[j] < r ? 1u : 0u;
-                    out.keys[gbase + rank] = r >> 2;
-                    out.count_flags[gbase + rank] = stage_c[i];
-                }
-            }
-        } else {
-            if (S <= STAGE_CAP) {  // staging -> table memory (the table is dead now), then key-value radix sort
-                for (uint32_t i = tid; i < S; i += THREADS) { K[i] = stage_k[i]; C[i] = stage_c[i]; }
-                __syncthreads();
-            } else compact_table();
-            uint32_t *Vs = nullptr;
-            uint64_t *Ss = block_radix_sort64<THREADS, true>(K, K + TS / 2, S, 0, end_bit, hist, s_scan, C, C + TS / 2, &Vs);
-            if (room) {
-                for (uint32_t i = tid; i < S; i += THREADS) {
-                    out.keys[gbase + i] = Ss[i] >> 2;
-                    out.count_flags[gbase + i] = Vs[i];
-                }
+            if (SRC != SRC_RECORDS) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) my_occ += __shfl_xor_sync(0xffffffffu, my_occ, o);
+                if (lane_id() == 0 && my_occ) atomicAdd(&s_cnt[1], my_occ);
             }
         }
         __syncthreads();
+        if (SRC != SRC_RECORDS && tid == 0) {
+            const uint32_t S = s_cnt[0];
+            out.stats(S, s_cnt[1], n);
+            out.unit_out_off[oslot] = gbase;
+            out.unit_out_cnt[oslot] = S;
+        }
+        __syncthreads();   // s_cnt / table are rewritten by the next unit
     }
 }
 
@@ -704,60 +601,234 @@ k_partition_units(const ChunkView *__restrict__ chunks, uint32_t n_chunks, const
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_finish_units: survivors of every unit -> unit-ordered final table.  A unit with one output slot is already
-// sorted (copy); a big unit's slots (one per key partition, unsorted) are concatenated and radix-sorted by key,
-// in shared memory when they fit, else between the final buffer and a global scratch of the same layout.
-template <int THREADS, int SCAP>
-constexpr size_t finish_units_smem_bytes() { return (size_t)(THREADS / 32) * 256 * 4 + 48 * 4 + (size_t)SCAP * 24; }
+// Unit-ordered final table.  The merge kernels leave every unit's survivors in one or several output slots, in table
+// order; the final table wants them contiguous per unit and ascending by key.  Keys inside a unit are spread over the
+// whole 2k-bit range, so a BIN-RANK sort does it in one pass over the data: histogram on the top key bits, exclusive
+// scan, scatter into the bins, then rank = bin start + number of smaller keys inside the (tiny) bin.
+//   k_finish_small   one WARP per unit with <= FIN_WCAP survivors (no block barrier at all; 128 bins)
+//   k_finish_units   one CTA per larger unit: bin-rank in shared memory up to BCAP survivors (2048 bins), LSD radix
+//                    sort between the final buffer and a scratch of the part's size beyond that
+// Slots flagged SLOT_SORTED (sort-based merge kernels) of single-slot units are copied.
+constexpr uint32_t FIN_WCAP = 512, FIN_WBINS = 128, FIN_WARPS = 4;
 
-template <int THREADS, int SCAP>
-__global__ void __launch_bounds__(THREADS)
-k_finish_units(const uint64_t *__restrict__ src_keys, const uint32_t *__restrict__ src_cf, const uint64_t *__restrict__ slot_off,
-               const uint32_t *__restrict__ slot_cnt, const uint32_t *__restrict__ slot_of_unit /* n_units + 1, or NULL */,
-               const uint64_t *__restrict__ dst_off, uint64_t *__restrict__ dst_keys, uint32_t *__restrict__ dst_cf,
-               uint64_t *__restrict__ tmp_keys, uint32_t *__restrict__ tmp_cf, uint32_t n_units, uint32_t end_bit,
-               uint64_t capacity, uint32_t *__restrict__ overflow) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    // the final table grows with the survivors actually seen: when this part does not fit, nothing is written and the
+__device__ __forceinline__ uint32_t key_bin(uint64_t key, uint32_t kbits, uint32_t log_bins) {
+    return kbits > log_bins ? (uint32_t)(key >> (kbits - log_bins)) : (uint32_t)key;
+}
+
+struct FinishArgs {
+    const uint64_t *src_keys; const uint32_t *src_cf;
+    const uint64_t *slot_off; const uint32_t *slot_cnt;
+    const uint32_t *slot_of_unit;      // n_units + 1, or NULL (slot == unit)
+    const uint64_t *dst_off;           // n_units + 1 final offsets
+    uint64_t *dst_keys; uint32_t *dst_cf;
+    uint64_t *tmp_keys; uint32_t *tmp_cf;   // scratch of the part's size (units sorted in global memory)
+    uint32_t n_units, kbits;           // kbits = 2k: keys are < 2^kbits
+    uint64_t capacity; uint32_t *overflow;
+};
+
+__global__ void __launch_bounds__(FIN_WARPS * 32) k_finish_small(FinishArgs a) {
+    __shared__ uint64_t s_k[FIN_WARPS][FIN_WCAP];
+    __shared__ uint32_t s_v[FIN_WARPS][FIN_WCAP];
+    __shared__ uint32_t s_bin[FIN_WARPS][FIN_WBINS + 1], s_cur[FIN_WARPS][FIN_WBINS];
+    // the final table grows with the survivors actually seen: when this part does not fit nothing is written and the
     // host enlarges the table and launches the gather again (overflow bit 2)
-    if (dst_off[n_units] > capacity) {
-        if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(overflow, 4u);
+    if (a.dst_off[a.n_units] > a.capacity) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(a.overflow, 4u);
         return;
     }
-    const uint64_t tmp_base = dst_off[0];   // tmp_* hold this part only
-    constexpr int WARPS = THREADS / 32;
-    uint64_t *sA = reinterpret_cast<uint64_t *>(smem_raw), *sB = sA + SCAP;
-    uint32_t *sAv = reinterpret_cast<uint32_t *>(sB + SCAP), *sBv = sAv + SCAP;
-    uint32_t *hist = sBv + SCAP;
-    uint32_t *s_scan = hist + WARPS * 256;
-    const uint32_t tid = threadIdx.x;
-    for (uint32_t u = blockIdx.x; u < n_units; u += gridDim.x) {
-        const uint32_t s0 = slot_of_unit ? slot_of_unit[u] : u, s1 = slot_of_unit ? slot_of_unit[u + 1] : u + 1;
-        const uint64_t d = dst_off[u];
-        const uint32_t n = (uint32_t)(dst_off[u + 1] - d);
-        if (n == 0) continue;
-        if (s1 - s0 == 1) {
-            const uint64_t so = slot_off[s0];
-            for (uint32_t i = tid; i < n; i += THREADS) { dst_keys[d + i] = src_keys[so + i]; dst_cf[d + i] = src_cf[so + i]; }
+    const uint32_t lane = lane_id(), w = warp_id();
+    uint64_t *sk = s_k[w]; uint32_t *sv = s_v[w], *bin = s_bin[w], *cur = s_cur[w];
+    for (uint32_t u = blockIdx.x * FIN_WARPS + w; u < a.n_units; u += gridDim.x * FIN_WARPS) {
+        const uint64_t d = a.dst_off[u];
+        const uint32_t n = (uint32_t)(a.dst_off[u + 1] - d);
+        if (n == 0 || n > FIN_WCAP) continue;
+        const uint32_t s0 = a.slot_of_unit ? a.slot_of_unit[u] : u, s1 = a.slot_of_unit ? a.slot_of_unit[u + 1] : u + 1;
+        if (s1 - s0 == 1 && (a.slot_cnt[s0] & SLOT_SORTED)) {
+            const uint64_t so = a.slot_off[s0];
+            for (uint32_t i = lane; i < n; i += 32) { a.dst_keys[d + i] = a.src_keys[so + i]; a.dst_cf[d + i] = a.src_cf[so + i]; }
             continue;
         }
-        const bool in_smem = n <= (uint32_t)SCAP;
-        uint64_t *A = in_smem ? sA : dst_keys + d;
-        uint32_t *Av = in_smem ? sAv : dst_cf + d;
+        for (uint32_t i = lane; i < FIN_WBINS; i += 32) bin[i] = 0;
+        __syncwarp();
+        for (uint32_t sl = s0; sl < s1; sl++) {
+            const uint32_t c = a.slot_cnt[sl] & ~SLOT_SORTED;
+            const uint64_t so = a.slot_off[sl];
+            for (uint32_t i = lane; i < c; i += 32) atomicAdd(&bin[key_bin(a.src_keys[so + i], a.kbits, 7)], 1u);
+        }
+        __syncwarp();
+        {   // exclusive scan of the 128 bin counts: 4 per lane
+            uint32_t v[4], sum = 0;
+#pragma unroll
+            for (int q = 0; q < 4; q++) { v[q] = bin[lane * 4 + q]; sum += v[q]; }
+            uint32_t x = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= (uint32_t)o) x += y; }
+            uint32_t p = x - sum;
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < 4; q++) { bin[lane * 4 + q] = p; cur[lane * 4 + q] = p; p += v[q]; }
+            if (lane == 31) bin[FIN_WBINS] = p;
+        }
+        __syncwarp();
+        for (uint32_t sl = s0; sl < s1; sl++) {
+            const uint32_t c = a.slot_cnt[sl] & ~SLOT_SORTED;
+            const uint64_t so = a.slot_off[sl];
+            for (uint32_t i = lane; i < c; i += 32) {
+                const uint64_t key = a.src_keys[so + i];
+                const uint32_t pos = atomicAdd(&cur[key_bin(key, a.kbits, 7)], 1u);
+                sk[pos] = key; sv[pos] = a.src_cf[so + i];
+            }
+        }
+        __syncwarp();
+        for (uint32_t i = lane; i < n; i += 32) {
+            const uint64_t key = sk[i];
+            const uint32_t b = key_bin(key, a.kbits, 7);
+            const uint32_t lo = bin[b], hi = bin[b + 1];
+            uint32_t rank = lo;
+            for (uint32_t j = lo; j < hi; j++) rank += sk[j] < key ? 1u : 0u;
+            a.dst_keys[d + rank] = key; a.dst_cf[d + rank] = sv[i];
+        }
+        __syncwarp();
+    }
+}
+
+template <int THREADS, int BCAP>
+constexpr size_t finish_units_smem_bytes() { return (size_t)(THREADS / 32) * 256 * 4 + 48 * 4 + (size_t)BCAP * 12 + (2048 * 2 + 1) * 4; }
+
+template <int THREADS, int BCAP>
+__global__ void __launch_bounds__(THREADS) k_finish_units(FinishArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int WARPS = THREADS / 32;
+    constexpr uint32_t NB = 2048;
+    uint64_t *sk = reinterpret_cast<uint64_t *>(smem_raw);
+    uint32_t *sv = reinterpret_cast<uint32_t *>(sk + BCAP);
+    uint32_t *bin = sv + BCAP, *cur = bin + NB + 1;
+    uint32_t *hist = cur + NB;                       // radix histograms (global path)
+    uint32_t *s_scan = hist + WARPS * 256;
+    if (a.dst_off[a.n_units] > a.capacity) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(a.overflow, 4u);
+        return;
+    }
+    const uint64_t tmp_base = a.dst_off[0];          // tmp_* hold this part only
+    const uint32_t tid = threadIdx.x;
+    for (uint32_t u = blockIdx.x; u < a.n_units; u += gridDim.x) {
+        const uint64_t d = a.dst_off[u];
+        const uint32_t n = (uint32_t)(a.dst_off[u + 1] - d);
+        if (n <= FIN_WCAP) continue;                 // k_finish_small
+        const uint32_t s0 = a.slot_of_unit ? a.slot_of_unit[u] : u, s1 = a.slot_of_unit ? a.slot_of_unit[u + 1] : u + 1;
+        if (s1 - s0 == 1 && (a.slot_cnt[s0] & SLOT_SORTED)) {
+            const uint64_t so = a.slot_off[s0];
+            for (uint32_t i = tid; i < n; i += THREADS) { a.dst_keys[d + i] = a.src_keys[so + i]; a.dst_cf[d + i] = a.src_cf[so + i]; }
+            continue;
+        }
+        if (n <= (uint32_t)BCAP) {
+            for (uint32_t i = tid; i < NB; i += THREADS) bin[i] = 0;
+            __syncthreads();
+            for (uint32_t sl = s0; sl < s1; sl++) {
+                const uint32_t c = a.slot_cnt[sl] & ~SLOT_SORTED;
+                const uint64_t so = a.slot_off[sl];
+                for (uint32_t i = tid; i < c; i += THREADS) atomicAdd(&bin[key_bin(a.src_keys[so + i], a.kbits, 11)], 1u);
+            }
+            __syncthreads();
+            {
+                constexpr uint32_t PER = NB / THREADS;
+                uint32_t v[PER], sum = 0;
+#pragma unroll
+                for (uint32_t q = 0; q < PER; q++) { v[q] = bin[tid * PER + q]; sum += v[q]; }
+                uint32_t tot;
+                uint32_t p = block_exclusive_scan<THREADS>(sum, s_scan, &tot);
+#pragma unroll
+                for (uint32_t q = 0; q < PER; q++) { bin[tid * PER + q] = p; cur[tid * PER + q] = p; p += v[q]; }
+                if (tid == THREADS - 1) bin[NB] = p;
+            }
+            __syncthreads();
+            for (uint32_t sl = s0; sl < s1; sl++) {
+                const uint32_t c = a.slot_cnt[sl] & ~SLOT_SORTED;
+                const uint64_t so = a.slot_off[sl];
+                for (uint32_t i = tid; i < c; i += THREADS) {
+                    const uint64_t key = a.src_keys[so + i];
+                    const uint32_t pos = atomicAdd(&cur[key_bin(key, a.kbits, 11)], 1u);
+                    sk[pos] = key; sv[pos] = a.src_cf[so + i];
+                }
+            }
+            __syncthreads();
+            for (uint32_t i = tid; i < n; i += THREADS) {
+                const uint64_t key = sk[i];
+                const uint32_t b = key_bin(key, a.kbits, 11);
+                const uint32_t lo = bin[b], hi = bin[b + 1];
+                uint32_t rank = lo;
+                for (uint32_t j = lo; j < hi; j++) rank += sk[j] < key ? 1u : 0u;
+                a.dst_keys[d + rank] = key; a.dst_cf[d + rank] = sv[i];
+            }
+            __syncthreads();
+            continue;
+        }
+        // larger than the shared buffers: the same bin-rank sort with the entries in the scratch buffer (the unit's
+        // slice of it is L2-resident) and 8192 bins in the shared memory the staging would have used
+        constexpr uint32_t NBG = 8192, GSKEW = 1024;
+        static_assert((size_t)BCAP * 12 >= (size_t)(2 * NBG + 1) * 4, "global-path bins reuse the staging area");
+        uint32_t *gbin = reinterpret_cast<uint32_t *>(smem_raw), *gcur = gbin + NBG + 1;
+        uint64_t *B = a.tmp_keys + (d - tmp_base);
+        uint32_t *Bv = a.tmp_cf + (d - tmp_base);
+        for (uint32_t i = tid; i < NBG; i += THREADS) gbin[i] = 0;
+        __syncthreads();
+        for (uint32_t sl = s0; sl < s1; sl++) {
+            const uint32_t c = a.slot_cnt[sl] & ~SLOT_SORTED;
+            const uint64_t so = a.slot_off[sl];
+            for (uint32_t i = tid; i < c; i += THREADS) atomicAdd(&gbin[key_bin(a.src_keys[so + i], a.kbits, 13)], 1u);
+        }
+        __syncthreads();
+        uint32_t maxbin = 0;
+        {
+            constexpr uint32_t PER = NBG / THREADS;
+            uint32_t v[PER], sum = 0;
+#pragma unroll
+            for (uint32_t q = 0; q < PER; q++) { v[q] = gbin[tid * PER + q]; sum += v[q]; maxbin = max(maxbin, v[q]); }
+            uint32_t tot;
+            uint32_t p = block_exclusive_scan<THREADS>(sum, s_scan, &tot);
+#pragma unroll
+            for (uint32_t q = 0; q < PER; q++) { gbin[tid * PER + q] = p; gcur[tid * PER + q] = p; p += v[q]; }
+            if (tid == THREADS - 1) gbin[NBG] = p;
+        }
+        maxbin = __syncthreads_or(maxbin > GSKEW ? 1 : 0);
+        if (!maxbin) {
+            for (uint32_t sl = s0; sl < s1; sl++) {
+                const uint32_t c = a.slot_cnt[sl] & ~SLOT_SORTED;
+                const uint64_t so = a.slot_off[sl];
+                for (uint32_t i = tid; i < c; i += THREADS) {
+                    const uint64_t key = a.src_keys[so + i];
+                    const uint32_t pos = atomicAdd(&gcur[key_bin(key, a.kbits, 13)], 1u);
+                    B[pos] = key; Bv[pos] = a.src_cf[so + i];
+                }
+            }
+            __syncthreads();
+            for (uint32_t i = tid; i < n; i += THREADS) {
+                const uint64_t key = B[i];
+                const uint32_t b = key_bin(key, a.kbits, 13);
+                const uint32_t lo = gbin[b], hi = gbin[b + 1];
+                uint32_t rank = lo;
+                for (uint32_t j = lo; j < hi; j++) rank += B[j] < key ? 1u : 0u;
+                a.dst_keys[d + rank] = key; a.dst_cf[d + rank] = Bv[i];
+            }
+            __syncthreads();
+            continue;
+        }
+        // heavily skewed keys (a bin of > GSKEW entries): concatenate into the final buffer, LSD radix sort against the scratch
+        uint64_t *A = a.dst_keys + d;
+        uint32_t *Av = a.dst_cf + d;
         uint32_t run = 0;
-        for (uint32_t sl = s0; sl < s1; sl++) {   // concatenate the partitions
-            const uint32_t c = slot_cnt[sl];
-            const uint64_t so = slot_off[sl];
-            for (uint32_t i = tid; i < c; i += THREADS) { A[run + i] = src_keys[so + i]; Av[run + i] = src_cf[so + i]; }
+        for (uint32_t sl = s0; sl < s1; sl++) {
+            const uint32_t c = a.slot_cnt[sl] & ~SLOT_SORTED;
+            const uint64_t so = a.slot_off[sl];
+            for (uint32_t i = tid; i < c; i += THREADS) { A[run + i] = a.src_keys[so + i]; Av[run + i] = a.src_cf[so + i]; }
             run += c;
         }
         __syncthreads();
-        uint64_t *B = in_smem ? sB : tmp_keys + (d - tmp_base);
-        uint32_t *Bv = in_smem ? sBv : tmp_cf + (d - tmp_base);
         uint32_t *Vs = nullptr;
+        const uint32_t end_bit = min(64u, (a.kbits + 7u) & ~7u);
         uint64_t *Ss = block_radix_sort64<THREADS, true>(A, B, n, 0, end_bit, hist, s_scan, Av, Bv, &Vs);
-        if (Ss != dst_keys + d)
-            for (uint32_t i = tid; i < n; i += THREADS) { dst_keys[d + i] = Ss[i]; dst_cf[d + i] = Vs[i]; }
+        if (Ss != A)
+            for (uint32_t i = tid; i < n; i += THREADS) { A[i] = Ss[i]; Av[i] = Vs[i]; }
         __syncthreads();
     }
 }
@@ -771,8 +842,8 @@ __global__ void __launch_bounds__(1024) k_scan_unit_slots(const uint32_t *__rest
         const uint32_t i = b0 + threadIdx.x;
         uint32_t v = 0;
         if (i < n) {
-            if (slot_of_unit) { for (uint32_t s = slot_of_unit[i]; s < slot_of_unit[i + 1]; s++) v += slot_cnt[s]; }
-            else v = slot_cnt[i];
+            if (slot_of_unit) { for (uint32_t s = slot_of_unit[i]; s < slot_of_unit[i + 1]; s++) v += slot_cnt[s] & ~SLOT_SORTED; }
+            else v = slot_cnt[i] & ~SLOT_SORTED;
         }
         uint32_t tot;
         const uint32_t p = block_exclusive_scan<1024>(v, s_scan, &tot);

@@ -44,7 +44,8 @@ struct PeerSlice {           // 64 bytes: one local chunk's slice for this desti
     uint64_t pad[3];
 };
 
-struct PeerJob { const uint8_t *src; uint8_t *dst; uint64_t bytes; };   // 4-byte aligned, bytes % 4 == 0
+struct PeerJob { const uint8_t *src; uint8_t *dst; uint64_t bytes; uint32_t slot, pad; };   // 4-byte aligned, bytes % 4 == 0;
+                                                                                          // slot = destination index among the peers
 
 struct PeerHdrPtrs { PeerHdr *h[PEER_MAX_WORLD]; };
 
@@ -62,14 +63,19 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
     return t;
 }
 
-// k_peer_push: bulk copies into peer memory.  Jobs whose source and destination agree modulo 16 move as uint4
+// k_peer_push: bulk copies into peer memory.  The grid is split evenly over the destinations (CTA b serves destination
+// slot b % n_slots), so every owner receives from all its sources at 1/(W-1) of their rate all the time: no rank is
+// the target of everybody at once (the incast that a destination-after-destination order produces: measured 194 GB/s
+// per GPU at N=8 against 530 GB/s at N=2).  Jobs whose source and destination agree modulo 16 move as uint4
 // (4 independent 16-byte loads in flight per thread, 512 contiguous bytes per warp store); the rest as u32.
-__global__ void __launch_bounds__(256) k_peer_push(const PeerJob *__restrict__ jobs, uint32_t n_jobs) {
-    const uint64_t gtid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const uint64_t gsz = (uint64_t)gridDim.x * blockDim.x;
+__global__ void __launch_bounds__(256) k_peer_push(const PeerJob *__restrict__ jobs, uint32_t n_jobs, uint32_t n_slots) {
+    const uint32_t my_slot = blockIdx.x % n_slots, my_idx = blockIdx.x / n_slots;
+    const uint32_t ctas = (gridDim.x - my_slot + n_slots - 1) / n_slots;     // CTAs serving this slot
+    const uint64_t gtid = (uint64_t)my_idx * blockDim.x + threadIdx.x;
+    const uint64_t gsz = (uint64_t)ctas * blockDim.x;
     for (uint32_t j = 0; j < n_jobs; j++) {
         const PeerJob job = jobs[j];
-        if (job.bytes == 0) continue;
+        if (job.slot != my_slot || job.bytes == 0) continue;
         const uintptr_t sa = (uintptr_t)job.src, da = (uintptr_t)job.dst;
         if (((sa ^ da) & 15u) == 0) {
             uint64_t head = (16u - (sa & 15u)) & 15u;
@@ -84,7 +90,7 @@ __global__ void __launch_bounds__(256) k_peer_push(const PeerJob *__restrict__ j
                 d4[i] = a; d4[i + gsz] = b; d4[i + 2 * gsz] = c; d4[i + 3 * gsz] = d;
             }
             for (; i < nvec; i += gsz) d4[i] = __ldcs(s4 + i);
-            if (blockIdx.x == 0) {
+            if (my_idx == 0) {
                 const uint32_t *s1 = reinterpret_cast<const uint32_t *>(job.src);
                 uint32_t *d1 = reinterpret_cast<uint32_t *>(job.dst);
                 for (uint64_t q = threadIdx.x; q < (head >> 2); q += blockDim.x) d1[q] = s1[q];
