@@ -67,12 +67,16 @@ struct Chunk {
     uint64_t n_sk = 0, n_words = 0, n_kmers = 0, n_bases = 0;
     std::vector<uint32_t> h_cnt, h_off, h_words, h_woff, h_kmers;  // host mirrors (after finish / import)
     uint32_t *h_pin = nullptr; size_t h_pin_cap = 0;   // pinned landing area of the per-unit counts (cnt | words | kmers),
-    bool mirror_queued = false;                        // filled by copies queued right behind k_scatter
+    bool mirror_queued = false;                        // filled by copies queued right behind k_emit on the copy stream
+    cudaEvent_t ev_emit = nullptr, ev_mirror = nullptr;   // histograms complete / mirror landed
     void release() {
         desc.release(); payload.release(); unit_cnt.release(); unit_off.release(); unit_words.release();
         unit_woff.release(); unit_kmers.release();
         if (h_pin) cudaFreeHost(h_pin);
         h_pin = nullptr; h_pin_cap = 0;
+        if (ev_emit) cudaEventDestroy(ev_emit);
+        if (ev_mirror) cudaEventDestroy(ev_mirror);
+        ev_emit = ev_mirror = nullptr;
     }
 };
 
@@ -149,6 +153,8 @@ struct ggcat_b200_ctx {
     std::vector<Chunk *> chunk_pool;  // recycled local chunks (device buffers kept)
     // phase-2 workspace
     DevBuf d_unit_n, d_static_off, d_unit_fill;
+    DevBuf d_mstage;                       // merge uploads (views, work lists, unit_n, static_off) in one copy
+    uint8_t *h_mstage = nullptr; size_t h_mstage_cap = 0;
     DevBuf d_views, d_work[3], d_scratch, out_keys, out_cf, out_keys2, out_cf2, cursor, unit_out_off,
         unit_out_cnt, unit_final_off, overflow, d_retry, d_partmeta, d_recs, fin_tmp_keys, fin_tmp_cf, out_hi, out_hi2, unit_keys, unit_cols, col_off, out_coloff, out_colors;
     unsigned long long *h_pinned = nullptr;  // small pinned staging (16 u64)
@@ -277,6 +283,26 @@ int32_t bucket_batch_device(ggcat_b200_ctx *c, const uint8_t *d_data, const uint
                                         d_colors, ch->unit_cnt.as<uint32_t>(), ch->unit_words.as<uint32_t>(),
                                         ch->unit_kmers.as<uint32_t>());
     }
+    // host mirror of the per-unit counts: they are final after k_emit, so they travel on the copy stream while
+    // k_scatter runs; finish_bucketing waits for this event only, and the host side of the merge (unit classification,
+    // uploads) overlaps the tail of phase 1
+    if (c->copy_stream) {
+        const size_t nu = P.n_units;
+        if (ch->h_pin_cap < 3 * nu) {
+            if (ch->h_pin) cudaFreeHost(ch->h_pin);
+            ch->h_pin = nullptr; ch->h_pin_cap = 0;
+            CU(cudaHostAlloc(reinterpret_cast<void **>(&ch->h_pin), 3 * nu * 4, cudaHostAllocDefault));
+            ch->h_pin_cap = 3 * nu;
+        }
+        if (!ch->ev_emit) { CU(cudaEventCreateWithFlags(&ch->ev_emit, cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&ch->ev_mirror, cudaEventDisableTiming)); }
+        CU(cudaEventRecord(ch->ev_emit, st));
+        CU(cudaStreamWaitEvent(c->copy_stream, ch->ev_emit, 0));
+        CU(cudaMemcpyAsync(ch->h_pin, ch->unit_cnt.p, nu * 4, cudaMemcpyDeviceToHost, c->copy_stream));
+        CU(cudaMemcpyAsync(ch->h_pin + nu, ch->unit_words.p, nu * 4, cudaMemcpyDeviceToHost, c->copy_stream));
+        CU(cudaMemcpyAsync(ch->h_pin + 2 * nu, ch->unit_kmers.p, nu * 4, cudaMemcpyDeviceToHost, c->copy_stream));
+        CU(cudaEventRecord(ch->ev_mirror, c->copy_stream));
+        ch->mirror_queued = true;
+    }
     {
         LaunchTimer t(c, F_SCAN, 2);
         k_exclusive_scan_u32<<<1, 1024, 0, st>>>(ch->unit_cnt.as<uint32_t>(), ch->unit_off.as<uint32_t>(), P.n_units,
@@ -303,20 +329,6 @@ int32_t bucket_batch_device(ggcat_b200_ctx *c, const uint8_t *d_data, const uint
     ch->d_unit_cnt = ch->unit_cnt.as<uint32_t>(); ch->d_unit_off = ch->unit_off.as<uint32_t>();
     ch->d_unit_words = ch->unit_words.as<uint32_t>(); ch->d_unit_woff = ch->unit_woff.as<uint32_t>();
     ch->d_unit_kmers = ch->unit_kmers.as<uint32_t>();
-    // host mirror of the per-unit counts: queued here so that finish_bucketing only has to wait for the stream
-    {
-        const size_t nu = P.n_units;
-        if (ch->h_pin_cap < 3 * nu) {
-            if (ch->h_pin) cudaFreeHost(ch->h_pin);
-            ch->h_pin = nullptr; ch->h_pin_cap = 0;
-            CU(cudaHostAlloc(reinterpret_cast<void **>(&ch->h_pin), 3 * nu * 4, cudaHostAllocDefault));
-            ch->h_pin_cap = 3 * nu;
-        }
-        CU(cudaMemcpyAsync(ch->h_pin, ch->d_unit_cnt, nu * 4, cudaMemcpyDeviceToHost, st));
-        CU(cudaMemcpyAsync(ch->h_pin + nu, ch->d_unit_words, nu * 4, cudaMemcpyDeviceToHost, st));
-        CU(cudaMemcpyAsync(ch->h_pin + 2 * nu, ch->d_unit_kmers, nu * 4, cudaMemcpyDeviceToHost, st));
-        ch->mirror_queued = true;
-    }
     CU(cudaGetLastError());
     return 0;
 }
@@ -327,7 +339,7 @@ int32_t mirror_chunk(ggcat_b200_ctx *c, Chunk *ch) {
     ch->h_cnt.resize(nu + 1); ch->h_off.resize(nu + 1); ch->h_words.resize(nu + 1); ch->h_woff.resize(nu + 1);
     ch->h_kmers.resize(nu + 1);
     if (ch->mirror_queued && ch->h_pin && !ch->imported) {
-        CU(cudaStreamSynchronize(c->stream));   // no-op after finish_bucketing's own synchronisation
+        CU(cudaEventSynchronize(ch->ev_mirror));
         memcpy(ch->h_cnt.data(), ch->h_pin, nu * 4);
         memcpy(ch->h_words.data(), ch->h_pin + nu, nu * 4);
         memcpy(ch->h_kmers.data(), ch->h_pin + 2 * nu, nu * 4);
@@ -365,11 +377,23 @@ __global__ void __launch_bounds__(1024) k_scan_counts_u64(const uint32_t *cnt, u
 constexpr int SM_THREADS_S = 512, SM_CAP_S = 6144;     // 2 CTAs / SM
 constexpr int SM_THREADS_L = 1024, SM_CAP_L = 12288;   // 1 CTA / SM
 constexpr int GL_THREADS = 1024;
-constexpr int HASH_TS_S = 8192, HASH_TS_L = 16384;       // hash-table slots: unit records <= 3/4 of the slots
+constexpr int HASH_TS_S = 8192, HASH_TS_L = 16384;       // hash-table slots (table = 1.25 n + 64 slots, 12 bytes each)
+constexpr int HASH_TS_T = 5120, SM_CAP_T = 4044;         // small units: 69 KB per CTA, 3 CTAs / SM
 
 // A bucket range may be merged in several parts that append to one final table (merge_range_parts): `eb` = entries
 // already in the table, `ub` = units already in unit_final_off, `cap_total` = final-buffer capacity for the whole range.
 struct PartBase { uint64_t eb = 0; uint32_t ub = 0; uint64_t cap_total = 0; };
+int32_t pinned_reserve(uint8_t **p, size_t *cap, size_t need);
+
+int32_t pinned_reserve(uint8_t **p, size_t *cap, size_t need) {
+    if (need <= *cap) return 0;
+    if (*p) cudaFreeHost(*p);
+    *p = nullptr; *cap = 0;
+    const size_t want = need + need / 4 + 4096;
+    if (cudaMallocHost((void **)p, want) != cudaSuccess) return set_err(GGCAT_B200_ERR_CUDA, "cudaMallocHost(%zu) failed", want);
+    *cap = want;
+    return 0;
+}
 
 // The final table is sized by the survivors actually seen, not by the k-mer occurrences (which are 10-25x more at
 // 30x coverage): it starts from an estimate and grows (keeping the first `keep` entries) when a part does not fit.
@@ -420,7 +444,7 @@ int32_t merge_range_device(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_
     //   work[0]  <= 6144 records : 512-thread CTA, shared table          work[1]  <= 12288 : 1024-thread CTA
     //   big      <= PART_MAXP * PART_TARGET : key partitions in HBM, one shared-table CTA per partition
     //   work[2]  giant units (and every large unit in sort mode) : table / sort buffers in a global scratch slice
-    std::vector<uint32_t> work[3];
+    std::vector<uint32_t> work[3], work_t;
     std::vector<std::pair<uint64_t, uint32_t>> large, big;  // (records, unit)
     std::vector<uint64_t> unit_n(nu, 0);
     uint64_t tot_kmers = 0;
@@ -432,7 +456,8 @@ int32_t merge_range_device(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_
         if (n == 0) continue;
         if (n >= (1ull << 31)) return set_err(GGCAT_B200_ERR_INVALID, "unit %u holds %llu k-mers (> 2^31)", u, (unsigned long long)n);
         tot_kmers += n;
-        if (n <= SM_CAP_S) work[0].push_back(u);
+        if (hash_mode && n <= SM_CAP_T) work_t.push_back(u);
+        else if (n <= SM_CAP_S) work[0].push_back(u);
         else if (n <= SM_CAP_L) work[1].push_back(u);
         else if (hash_mode && n <= (uint64_t)PART_MAXP * PART_TARGET && !c->no_partition) big.push_back({n, u});
         else large.push_back({n, u});
@@ -473,7 +498,8 @@ int32_t merge_range_device(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_
         const uint64_t g = std::min<uint64_t>(std::min<uint64_t>(count, (uint64_t)c->sm_count * 2), std::max<uint64_t>(1, budget / (per_cta * 8)));
         return Tier{wl, count, count_dev, per_cta, (unsigned)g};
     };
-    // ---- uploads
+    // ---- uploads: chunk views, work lists, per-unit record counts and output regions travel in ONE copy from a pinned
+    //      staging buffer (every merge call ends with a stream synchronisation, so the buffer is free again)
     std::vector<ChunkView> views;
     for (Chunk *ch : c->chunks) {
         ChunkView v;
@@ -481,14 +507,30 @@ int32_t merge_range_device(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_
         v.first_unit = ch->first_unit; v.n_units = ch->n_units; v.word_bias = ch->word_bias; v.pad = 0;
         views.push_back(v);
     }
-    CU(c->d_views.reserve(std::max<size_t>(1, views.size()) * sizeof(ChunkView)));
-    if (!views.empty())
-        CU(cudaMemcpyAsync(c->d_views.p, views.data(), views.size() * sizeof(ChunkView), cudaMemcpyHostToDevice, st));
-    for (int q = 0; q < 3; q++) {
-        CU(c->d_work[q].reserve(std::max<size_t>(1, work[q].size()) * 4));
-        if (!work[q].empty())
-            CU(cudaMemcpyAsync(c->d_work[q].p, work[q].data(), work[q].size() * 4, cudaMemcpyHostToDevice, st));
+    auto al16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
+    const size_t off_views = 0, off_wt = al16(off_views + std::max<size_t>(1, views.size()) * sizeof(ChunkView));
+    const size_t off_w0 = al16(off_wt + work_t.size() * 4), off_w1 = al16(off_w0 + work[0].size() * 4);
+    const size_t off_w2 = al16(off_w1 + work[1].size() * 4), off_un = al16(off_w2 + work[2].size() * 4);
+    const size_t off_so = al16(off_un + (size_t)nu * 4), stage_bytes = al16(off_so + ((size_t)nu + 1) * 8);
+    TRY(pinned_reserve(&c->h_mstage, &c->h_mstage_cap, stage_bytes));
+    CU(c->d_mstage.reserve(stage_bytes));
+    {
+        uint8_t *h = c->h_mstage;
+        if (!views.empty()) memcpy(h + off_views, views.data(), views.size() * sizeof(ChunkView));
+        if (!work_t.empty()) memcpy(h + off_wt, work_t.data(), work_t.size() * 4);
+        for (int q = 0; q < 3; q++)
+            if (!work[q].empty()) memcpy(h + (q == 0 ? off_w0 : q == 1 ? off_w1 : off_w2), work[q].data(), work[q].size() * 4);
+        uint32_t *un = reinterpret_cast<uint32_t *>(h + off_un);
+        uint64_t *so = reinterpret_cast<uint64_t *>(h + off_so);
+        uint64_t acc = 0;   // every unit owns the region [static_off[u], static_off[u] + records(u)) of the part's output buffers
+        for (uint32_t i = 0; i < nu; i++) { un[i] = (uint32_t)unit_n[i]; so[i] = acc; acc += unit_n[i]; }
+        so[nu] = acc;
+        CU(cudaMemcpyAsync(c->d_mstage.p, h, stage_bytes, cudaMemcpyHostToDevice, st));
     }
+    uint8_t *dm = c->d_mstage.as<uint8_t>();
+    const uint32_t *d_work_t = reinterpret_cast<const uint32_t *>(dm + off_wt);
+    const uint32_t *d_w[3] = {reinterpret_cast<const uint32_t *>(dm + off_w0), reinterpret_cast<const uint32_t *>(dm + off_w1),
+                              reinterpret_cast<const uint32_t *>(dm + off_w2)};
     uint32_t *d_big_unit = nullptr, *d_big_logp = nullptr, *d_big_pbase = nullptr, *d_big_ovf = nullptr, *d_part_slot = nullptr,
              *d_part_big = nullptr, *d_pcount = nullptr, *d_slot_of_unit = nullptr;
     if (!big.empty()) {
@@ -511,8 +553,8 @@ int32_t merge_range_device(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_
     }
     std::vector<Tier> tiers;
     uint64_t scratch_u64 = 1;
-    if (n_giant) tiers.push_back(make_tier(c->d_work[2].as<uint32_t>(), n_giant, nullptr, large[0].first));
-    if (large.size() > n_giant) tiers.push_back(make_tier(c->d_work[2].as<uint32_t>() + n_giant, large.size() - n_giant, nullptr, large[n_giant].first));
+    if (n_giant) tiers.push_back(make_tier(d_w[2], n_giant, nullptr, large[0].first));
+    if (large.size() > n_giant) tiers.push_back(make_tier(d_w[2] + n_giant, large.size() - n_giant, nullptr, large[n_giant].first));
     const uint64_t cap = std::max<uint64_t>(tot_kmers, 1);
     CU(c->out_keys.reserve(cap * 8)); CU(c->out_cf.reserve(cap * 4));
     CU(c->cursor.reserve(64)); CU(c->overflow.reserve(16));
@@ -528,36 +570,35 @@ int32_t merge_range_device(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_
     CU(cudaMemsetAsync(c->overflow.p, 0, 16, st));
     CU(cudaMemsetAsync(c->unit_out_off.p, 0, ((size_t)n_slots + 1) * 8, st));
     CU(cudaMemsetAsync(c->unit_out_cnt.p, 0, ((size_t)n_slots + 1) * 4, st));
-    // every unit owns the region [static_off[u], static_off[u] + records(u)) of the part's output buffers
-    {
-        std::vector<uint32_t> un(nu);
-        std::vector<uint64_t> so((size_t)nu + 1);
-        uint64_t acc = 0;
-        for (uint32_t i = 0; i < nu; i++) { un[i] = (uint32_t)unit_n[i]; so[i] = acc; acc += unit_n[i]; }
-        so[nu] = acc;
-        CU(c->d_unit_n.reserve((size_t)nu * 4)); CU(c->d_static_off.reserve(((size_t)nu + 1) * 8)); CU(c->d_unit_fill.reserve((size_t)nu * 4));
-        CU(cudaMemcpyAsync(c->d_unit_n.p, un.data(), (size_t)nu * 4, cudaMemcpyHostToDevice, st));
-        CU(cudaMemcpyAsync(c->d_static_off.p, so.data(), ((size_t)nu + 1) * 8, cudaMemcpyHostToDevice, st));
-        CU(cudaMemsetAsync(c->d_unit_fill.p, 0, (size_t)nu * 4, st));
-    }
-    const uint32_t *d_unit_n = c->d_unit_n.as<uint32_t>();
+    CU(c->d_unit_fill.reserve((size_t)nu * 4));
+    CU(cudaMemsetAsync(c->d_unit_fill.p, 0, (size_t)nu * 4, st));
+    const uint32_t *d_unit_n = reinterpret_cast<const uint32_t *>(dm + off_un);
     MergeOut out;
     out.keys = c->out_keys.as<uint64_t>(); out.count_flags = c->out_cf.as<uint32_t>();
     out.cursor = c->cursor.as<unsigned long long>(); out.unit_out_off = c->unit_out_off.as<uint64_t>();
     out.unit_out_cnt = c->unit_out_cnt.as<uint32_t>(); out.overflow = c->overflow.as<uint32_t>();
-    out.static_off = c->d_static_off.as<uint64_t>(); out.unit_fill = c->d_unit_fill.as<uint32_t>();
+    out.static_off = reinterpret_cast<const uint64_t *>(dm + off_so); out.unit_fill = c->d_unit_fill.as<uint32_t>();
     out.slot_of_unit = d_slot_of_unit;
-    const ChunkView *dv = c->d_views.as<ChunkView>();
+    const ChunkView *dv = reinterpret_cast<const ChunkView *>(dm + off_views);
     const uint32_t nch = (uint32_t)views.size();
     const uint32_t ms = c->params.min_multiplicity;
     if (hash_mode) {
+        if (!work_t.empty()) {
+            LaunchTimer t(c, F_MERGE_HASH);
+            auto kern = k_merge_hash<SM_THREADS_S, HASH_TS_T>;
+            const size_t smem = merge_hash_smem_bytes<SM_THREADS_S, HASH_TS_T>();
+            CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            const unsigned grid = (unsigned)std::min<size_t>(work_t.size(), (size_t)c->sm_count * 3 * 8);
+            kern<<<grid, SM_THREADS_S, smem, st>>>(dv, nch, d_work_t, (uint32_t)work_t.size(), u0, P, ms, out,
+                                                   d_unit_n, nullptr, 0, PartSrc(), nullptr);
+        }
         if (!work[0].empty()) {
             LaunchTimer t(c, F_MERGE_HASH);
             auto kern = k_merge_hash<SM_THREADS_S, HASH_TS_S>;
             const size_t smem = merge_hash_smem_bytes<SM_THREADS_S, HASH_TS_S>();
             CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             const unsigned grid = (unsigned)std::min<size_t>(work[0].size(), (size_t)c->sm_count * 2 * 8);
-            kern<<<grid, SM_THREADS_S, smem, st>>>(dv, nch, c->d_work[0].as<uint32_t>(), (uint32_t)work[0].size(), u0, P, ms, out,
+            kern<<<grid, SM_THREADS_S, smem, st>>>(dv, nch, d_w[0], (uint32_t)work[0].size(), u0, P, ms, out,
                                                    d_unit_n, nullptr, 0, PartSrc(), nullptr);
         }
         if (!work[1].empty()) {
@@ -566,7 +607,7 @@ int32_t merge_range_device(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_
             const size_t smem = merge_hash_smem_bytes<SM_THREADS_L, HASH_TS_L>();
             CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             const unsigned grid = (unsigned)std::min<size_t>(work[1].size(), (size_t)c->sm_count * 8);
-            kern<<<grid, SM_THREADS_L, smem, st>>>(dv, nch, c->d_work[1].as<uint32_t>(), (uint32_t)work[1].size(), u0, P, ms, out,
+            kern<<<grid, SM_THREADS_L, smem, st>>>(dv, nch, d_w[1], (uint32_t)work[1].size(), u0, P, ms, out,
                                                    d_unit_n, nullptr, 0, PartSrc(), nullptr);
         }
         if (!big.empty()) {
@@ -596,7 +637,7 @@ int32_t merge_range_device(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_
         const size_t smem = merge_smem_bytes<SM_THREADS_S, SM_CAP_S>(false);
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const unsigned grid = (unsigned)std::min<size_t>(work[0].size(), (size_t)c->sm_count * 2 * 8);
-        kern<<<grid, SM_THREADS_S, smem, st>>>(dv, nch, c->d_work[0].as<uint32_t>(), (uint32_t)work[0].size(), u0, P, ms, out, nullptr, 0, nullptr);
+        kern<<<grid, SM_THREADS_S, smem, st>>>(dv, nch, d_w[0], (uint32_t)work[0].size(), u0, P, ms, out, nullptr, 0, nullptr);
     }
     if (!work[1].empty()) {
         LaunchTimer t(c, F_MERGE_SMEM);
@@ -604,7 +645,7 @@ int32_t merge_range_device(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_
         const size_t smem = merge_smem_bytes<SM_THREADS_L, SM_CAP_L>(false);
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const unsigned grid = (unsigned)std::min<size_t>(work[1].size(), (size_t)c->sm_count * 8);
-        kern<<<grid, SM_THREADS_L, smem, st>>>(dv, nch, c->d_work[1].as<uint32_t>(), (uint32_t)work[1].size(), u0, P, ms, out, nullptr, 0, nullptr);
+        kern<<<grid, SM_THREADS_L, smem, st>>>(dv, nch, d_w[1], (uint32_t)work[1].size(), u0, P, ms, out, nullptr, 0, nullptr);
     }
     for (const Tier &tr : tiers) {
         auto sortk = k_merge_units<GL_THREADS, 0, true>;
@@ -978,7 +1019,7 @@ void ggcat_b200_destroy(ggcat_b200_ctx *c) {
     for (DevBuf *b : {&c->d_ascii, &c->d_offsets, &c->d_colors, &c->pk, &c->bad, &c->brk, &c->ent, &c->tile_cnt, &c->tile_sbase,
                       &c->tmp, &c->tmp_color, &c->cur_cnt, &c->cur_words, &c->totals, &c->d_views, &c->d_work[0], &c->d_work[1],
                       &c->d_work[2], &c->d_scratch, &c->out_keys, &c->out_cf, &c->out_keys2, &c->out_cf2,
-                      &c->d_unit_n, &c->d_static_off, &c->d_unit_fill, &c->cursor, &c->unit_out_off, &c->unit_out_cnt, &c->unit_final_off, &c->overflow, &c->d_retry,
+                      &c->d_mstage, &c->d_unit_n, &c->d_static_off, &c->d_unit_fill, &c->cursor, &c->unit_out_off, &c->unit_out_cnt, &c->unit_final_off, &c->overflow, &c->d_retry,
                       &c->d_partmeta, &c->d_recs, &c->fin_tmp_keys, &c->fin_tmp_cf,
                       &c->out_hi, &c->out_hi2, &c->unit_keys, &c->unit_cols, &c->col_off, &c->out_coloff, &c->out_colors})
         b->release();
@@ -1000,6 +1041,7 @@ void ggcat_b200_destroy(ggcat_b200_ctx *c) {
         if (ps.h_stage) cudaFreeHost(ps.h_stage);
         if (ps.h_recv) cudaFreeHost(ps.h_recv);
     }
+    if (c->h_mstage) cudaFreeHost(c->h_mstage);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -1084,8 +1126,9 @@ int32_t ggcat_b200_push_reads_device(ggcat_b200_ctx *c, const uint8_t *d_data, c
 
 int32_t ggcat_b200_finish_bucketing(ggcat_b200_ctx *c, ggcat_b200_bucket_stats *stats) {
     TRY(check_ctx(c));
-    CU(cudaStreamSynchronize(c->stream));
-    CU(cudaGetLastError());
+    // no stream synchronisation here: the per-unit counts of every chunk arrive on the copy stream right after its
+    // k_emit, so this returns while the last k_scatter is still running; everything that follows is stream-ordered
+    // (ggcat_b200_synchronize() is there for callers that touch chunk buffers from another stream)
     uint64_t sk = 0, km = 0, words = 0;
     for (Chunk *ch : c->chunks) {
         TRY(mirror_chunk(c, ch));
@@ -1340,6 +1383,7 @@ int32_t ggcat_b200_export_chunk_slice(ggcat_b200_ctx *c, uint32_t chunk, uint32_
     Chunk *ch = c->chunks[chunk];
     if (ch->imported) return set_err(GGCAT_B200_ERR_INVALID, "cannot export an imported chunk");
     if (first_unit + n_units > ch->n_units) return set_err(GGCAT_B200_ERR_INVALID, "unit range outside chunk");
+    CU(cudaStreamSynchronize(c->stream));   // the pointers handed out are read from other streams: phase 1 must be complete
     const uint32_t d0 = ch->h_off[first_unit], d1 = ch->h_off[first_unit + n_units];
     const uint32_t w0 = ch->h_woff[first_unit], w1 = ch->h_woff[first_unit + n_units];
     out->n_superkmers = d1 - d0; out->n_words = w1 - w0; out->word_bias = w0;
@@ -1466,15 +1510,6 @@ int32_t ggcat_b200_peer_connect(ggcat_b200_ctx *c, const ggcat_b200_peer_handle 
     return 0;
 }
 
-static int32_t pinned_reserve(uint8_t **p, size_t *cap, size_t need) {
-    if (need <= *cap) return 0;
-    if (*p) cudaFreeHost(*p);
-    *p = nullptr; *cap = 0;
-    const size_t want = need + need / 4 + 4096;
-    if (cudaMallocHost((void **)p, want) != cudaSuccess) return set_err(GGCAT_B200_ERR_CUDA, "cudaMallocHost(%zu) failed", want);
-    *cap = want;
-    return 0;
-}
 
 int32_t ggcat_b200_peer_exchange(ggcat_b200_ctx *c) {
     TRY(check_ctx(c));

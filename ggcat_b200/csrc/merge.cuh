@@ -347,6 +347,9 @@ struct UnitStage {                       // lives in the kernel's scratch area w
     uint8_t ci[THREADS];                 // chunk (relative to the round's first)
 };
 
+template <int THREADS>
+__host__ __device__ constexpr size_t merge_hash_stage_bytes() { return (sizeof(UnitStage<THREADS>) + 15) & ~(size_t)15; }
+
 template <int THREADS, typename Emit>
 __device__ __forceinline__ void unit_for_each_kmer64(const ChunkView *__restrict__ chunks, uint32_t n_chunks, uint32_t unit,
                                                      uint32_t k, uint32_t forward_only, UnitStage<THREADS> *S, uint32_t *s_scan,
@@ -446,14 +449,10 @@ k_merge_hash(const ChunkView *__restrict__ chunks, uint32_t n_chunks, const uint
              uint32_t first_unit, DevParams P, uint32_t min_mult, MergeOut out, const uint32_t *__restrict__ unit_n,
              uint64_t *__restrict__ scratch, uint64_t per_cta_u64, PartSrc ps, const uint32_t *__restrict__ n_work_dev) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int WARPS = THREADS / 32;
-    constexpr uint32_t SCR_BYTES = WARPS * 256 * 4;  // scratch area: descriptor staging
-    static_assert(sizeof(UnitStage<THREADS>) <= SCR_BYTES, "descriptor staging must fit the scratch area");
     uint64_t *K = reinterpret_cast<uint64_t *>(smem_raw);                      // TS keys
     uint32_t *C = reinterpret_cast<uint32_t *>(K + TS_STATIC);                 // TS counters|flags
-    uint32_t *hist = C + TS_STATIC;                                            // scratch area (SCR_BYTES)
-    uint32_t *s_scan = hist + WARPS * 256;                                     // 40
-    UnitStage<THREADS> *stage = reinterpret_cast<UnitStage<THREADS> *>(hist);
+    UnitStage<THREADS> *stage = reinterpret_cast<UnitStage<THREADS> *>(C + TS_STATIC);   // descriptor staging
+    uint32_t *s_scan = reinterpret_cast<uint32_t *>(smem_raw + (size_t)TS_STATIC * 12 + merge_hash_stage_bytes<THREADS>());  // 40
     const uint32_t tid = threadIdx.x;
     if (n_work_dev) n_work = min(n_work, *n_work_dev);  // device-side list (big units whose partitions overflowed)
     for (uint32_t wi = blockIdx.x; wi < n_work; wi += gridDim.x) {
@@ -855,7 +854,7 @@ __global__ void __launch_bounds__(1024) k_scan_unit_slots(const uint32_t *__rest
 
 template <int THREADS, int TS_STATIC>
 constexpr size_t merge_hash_smem_bytes() {
-    return (size_t)TS_STATIC * 12 + (size_t)(THREADS / 32) * 256 * 4 + 40 * 4 + 16;
+    return (size_t)TS_STATIC * 12 + merge_hash_stage_bytes<THREADS>() + 40 * 4 + 16;
 }
 
 template <int THREADS, int CAP>

@@ -126,6 +126,9 @@ int32_t ggcat_b200_push_reads(ggcat_b200_ctx *ctx, const uint8_t *data, const ui
 /* Same, with data/offsets/colors already resident in device memory of ctx's device. */
 int32_t ggcat_b200_push_reads_device(ggcat_b200_ctx *ctx, const uint8_t *d_data, const uint64_t *d_offsets,
                                      uint64_t n_reads, uint64_t n_bytes, const uint32_t *d_colors);
+/* Returns as soon as the per-unit counts of every chunk are on the host (they are final before the last scatter
+ * kernel ends); later calls are ordered on the context stream.  Callers that read chunk buffers from another stream
+ * go through export_chunk_slice (which synchronises) or call ggcat_b200_synchronize(). */
 int32_t ggcat_b200_finish_bucketing(ggcat_b200_ctx *ctx, ggcat_b200_bucket_stats *stats);
 
 /* Per-unit sizes after finish_bucketing: arrays of stats.n_units entries (either may be NULL). */
