@@ -161,6 +161,14 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device -- the ggcat_b200 path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        try:   # pin this rank to the CPUs / NUMA node of its GPU before any pinned host memory is allocated (e2e copies
+               # of 8 ranks share the host's memory system); N=1 keeps every core for the CPU baseline
+            import pynvml
+            pynvml.nvmlInit()
+            pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local_rank))
+        except Exception:
+            pass
+    if world > 1:
         # the exchange is one large point-to-point all-to-all: let NCCL spread it over more channels
         os.environ.setdefault("NCCL_MIN_P2P_NCHANNELS", "16")
         os.environ.setdefault("NCCL_MAX_P2P_NCHANNELS", "32")

@@ -1060,8 +1060,13 @@ int32_t ggcat_b200_push_reads(ggcat_b200_ctx *c, const uint8_t *data, const uint
         if (offsets[r0 + 1] - offsets[r0] > c->max_batch)
             return set_err(GGCAT_B200_ERR_INVALID, "record %llu is longer than the batch limit %llu; split it with k-1 overlap "
                            "(crates/io/src/sequences_reader.rs:162-173)", (unsigned long long)r0, (unsigned long long)c->max_batch);
-        // the first batch is a third of the others: its copy is the only one no kernel overlaps
-        const uint64_t limit = batches.empty() ? std::max<uint64_t>(c->host_batch / 3, 1024) : c->host_batch;
+        // the first batch is a third of the others (its copy is the only one no kernel overlaps) and the last ones
+        // shrink (the kernels of the final batch are the only ones no copy overlaps)
+        const uint64_t left = offsets[n_reads] - offsets[r0];
+        uint64_t limit = c->host_batch;
+        if (batches.empty()) limit = std::max<uint64_t>(c->host_batch / 3, 1024);
+        else if (left <= c->host_batch / 2) limit = left;
+        else if (left <= c->host_batch + c->host_batch / 2) limit = left * 2 / 3;
         uint64_t lo = r0 + 1, hi = n_reads;
         while (lo < hi) {  // last record that still fits
             const uint64_t mid = (lo + hi + 1) >> 1;
@@ -1292,10 +1297,18 @@ int32_t ggcat_b200_merge_bucket_range(ggcat_b200_ctx *c, uint32_t first_bucket, 
     std::vector<std::pair<uint32_t, uint32_t>> parts;  // (first bucket, count)
     if (colored || tot <= c->part_kmers + c->part_kmers / 2) parts.push_back({first_bucket, n_buckets});
     else {
-        uint32_t b0 = 0; uint64_t acc = 0;
+        // shrinking parts: every part costs a fixed host round trip and only the LAST part's D2H is exposed, so the
+        // first part takes half of what is left (bounded by the device part size), the last ones ~part_kmers
+        uint32_t b0 = 0; uint64_t acc = 0, left = tot;
+        uint64_t target = std::min<uint64_t>(c->part_kmers_dev, std::max<uint64_t>(c->part_kmers, left / 2));
         for (uint32_t b = 0; b < n_buckets; b++) {
             acc += bk[b];
-            if (acc >= c->part_kmers || b + 1 == n_buckets) { parts.push_back({first_bucket + b0, b + 1 - b0}); b0 = b + 1; acc = 0; }
+            if (acc >= target || b + 1 == n_buckets) {
+                parts.push_back({first_bucket + b0, b + 1 - b0}); b0 = b + 1;
+                left -= std::min(left, acc); acc = 0;
+                target = std::min<uint64_t>(c->part_kmers_dev, std::max<uint64_t>(c->part_kmers, left / 2));
+                if (left < c->part_kmers + c->part_kmers / 2) target = left + 1;   // the rest in one piece
+            }
         }
     }
     HostTable *t = nullptr;
