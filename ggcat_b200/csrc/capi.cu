@@ -153,6 +153,7 @@ struct ggcat_b200_ctx {
     std::vector<Chunk *> chunk_pool;  // recycled local chunks (device buffers kept)
     // phase-2 workspace
     DevBuf d_unit_n, d_static_off, d_unit_fill;
+    DevBuf d_recfl;                        // flag bits of the wide path's partition records
     DevBuf d_mstage;                       // merge uploads (views, work lists, unit_n, static_off) in one copy
     uint8_t *h_mstage = nullptr; size_t h_mstage_cap = 0;
     DevBuf d_views, d_work[3], d_scratch, out_keys, out_cf, out_keys2, out_cf2, cursor, unit_out_off,
@@ -727,7 +728,7 @@ int32_t launch_hash128(ggcat_b200_ctx *c, const ChunkView *dv, uint32_t nch, std
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const unsigned grid = (unsigned)std::min<size_t>(work[0].size(), (size_t)c->sm_count * 2 * 8);
         kern<<<grid, W_THREADS_S, smem, st>>>(dv, nch, c->d_work[0].as<uint32_t>(), (uint32_t)work[0].size(), u0, P, c->rk,
-                                               c->params.min_multiplicity, out, nullptr, 0);
+                                               c->params.min_multiplicity, out, nullptr, 0, PartSrc128(), nullptr);
     }
     if (!work[1].empty()) {
         LaunchTimer t(c, F_MERGE_HASH128);
@@ -736,7 +737,7 @@ int32_t launch_hash128(ggcat_b200_ctx *c, const ChunkView *dv, uint32_t nch, std
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const unsigned grid = (unsigned)std::min<size_t>(work[1].size(), (size_t)c->sm_count * 8);
         kern<<<grid, W_THREADS_L, smem, st>>>(dv, nch, c->d_work[1].as<uint32_t>(), (uint32_t)work[1].size(), u0, P, c->rk,
-                                               c->params.min_multiplicity, out, nullptr, 0);
+                                               c->params.min_multiplicity, out, nullptr, 0, PartSrc128(), nullptr);
     }
     // large units: table in a per-CTA slice of global scratch, biggest first, two tiers (see merge_range_device)
     const uint64_t TIER = 1ull << 20;
@@ -754,7 +755,77 @@ int32_t launch_hash128(ggcat_b200_ctx *c, const ChunkView *dv, uint32_t nch, std
         auto kern = k_merge_hash128<W_THREADS_L, 0, MODE>;
         kern<<<(unsigned)g, W_THREADS_L, merge_hash128_smem_bytes<W_THREADS_L, 0>(), st>>>(
             dv, nch, c->d_work[2].as<uint32_t>() + first, (uint32_t)count, u0, P, c->rk, c->params.min_multiplicity, out,
-            c->d_scratch.as<uint64_t>(), per_cta);
+            c->d_scratch.as<uint64_t>(), per_cta, PartSrc128(), nullptr);
+    }
+    CU(cudaGetLastError());
+    return 0;
+}
+
+// Big units of the wide path: key partitions in HBM (k_partition_units128), one shared-table CTA per partition, and the
+// global-table kernel for units whose partitions overflowed.
+struct BigPlan128 {
+    std::vector<uint32_t> unit, logp, pbase, part_big;
+    std::vector<uint64_t> off;     // static output region of every big unit
+    uint32_t n_parts = 0;
+    uint64_t nmax = 0;
+};
+constexpr uint32_t W_PART_CAP = 3072, W_PART_TARGET = 2048;   // a partition fits the 4096-slot shared table
+
+template <int MODE>
+int32_t launch_partitions128(ggcat_b200_ctx *c, const ChunkView *dv, uint32_t nch, uint32_t u0, const MergeOut128 &out,
+                             const BigPlan128 &bp) {
+    const DevParams &P = c->P;
+    cudaStream_t st = c->stream;
+    const size_t nbig = bp.unit.size();
+    if (!nbig) return 0;
+    // metadata: big_unit | big_logp | big_pbase | big_ovf | big_fill | part_big | pcount   (u32), big_off (u64)
+    const size_t words = 5 * nbig + 2 * (size_t)bp.n_parts;
+    CU(c->d_partmeta.reserve(words * 4));
+    CU(c->d_static_off.reserve(nbig * 8));
+    uint32_t *base = c->d_partmeta.as<uint32_t>();
+    uint32_t *d_unit = base, *d_logp = base + nbig, *d_pbase = base + 2 * nbig, *d_ovf = base + 3 * nbig, *d_fill = base + 4 * nbig;
+    uint32_t *d_part_big = base + 5 * nbig, *d_pcount = d_part_big + bp.n_parts;
+    CU(cudaMemcpyAsync(d_unit, bp.unit.data(), nbig * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_logp, bp.logp.data(), nbig * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_pbase, bp.pbase.data(), nbig * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(d_ovf, 0, 2 * nbig * 4, st));   // big_ovf and big_fill
+    CU(cudaMemcpyAsync(d_part_big, bp.part_big.data(), (size_t)bp.n_parts * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(c->d_static_off.p, bp.off.data(), nbig * 8, cudaMemcpyHostToDevice, st));
+    const size_t nrec = (size_t)bp.n_parts * W_PART_CAP;
+    CU(c->d_recs.reserve(nrec * 16));
+    CU(c->d_recfl.reserve(nrec));
+    CU(c->d_retry.reserve((nbig + 2) * 4));
+    uint32_t *retry_cnt = c->d_retry.as<uint32_t>(), *retry = retry_cnt + 1;
+    CU(cudaMemsetAsync(retry_cnt, 0, 4, st));
+    uint64_t *rec_lo = c->d_recs.as<uint64_t>(), *rec_hi = rec_lo + nrec;
+    {
+        LaunchTimer t(c, F_PARTITION);
+        const unsigned grid = (unsigned)std::min<size_t>(nbig, (size_t)c->sm_count * 2);
+        k_partition_units128<1024, MODE><<<grid, 1024, 0, st>>>(dv, nch, d_unit, d_logp, d_pbase, (uint32_t)nbig, P, c->rk, rec_lo, rec_hi,
+                                                                c->d_recfl.as<uint8_t>(), d_pcount, W_PART_CAP, d_ovf, retry, retry_cnt);
+    }
+    {
+        LaunchTimer t(c, F_MERGE_HASH_PART);
+        PartSrc128 ps;
+        ps.rec_lo = rec_lo; ps.rec_hi = rec_hi; ps.rec_fl = c->d_recfl.as<uint8_t>(); ps.pcount = d_pcount; ps.part_big = d_part_big;
+        ps.big_unit = d_unit; ps.big_ovf = d_ovf; ps.big_off = c->d_static_off.as<uint64_t>(); ps.big_fill = d_fill;
+        ps.pcap = W_PART_CAP; ps.pad = 0;
+        auto kern = k_merge_hash128<W_THREADS_S, W_TS_S, MODE, SRC_RECORDS>;
+        const size_t smem = merge_hash128_smem_bytes<W_THREADS_S, W_TS_S>();
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const unsigned grid = (unsigned)std::min<size_t>(bp.n_parts, (size_t)c->sm_count * 2 * 8);
+        kern<<<grid, W_THREADS_S, smem, st>>>(dv, nch, nullptr, bp.n_parts, u0, P, c->rk, c->params.min_multiplicity, out, nullptr, 0, ps, nullptr);
+    }
+    {   // units with an overflowed partition: global-table kernel over the device-side retry list
+        uint64_t per_cta = ((uint64_t)hash_table_slots_pow2((uint32_t)bp.nmax) * 20 + 15) / 16 * 2 + 2;
+        const uint64_t budget = 12ull << 30;
+        const uint64_t g = std::min<uint64_t>(std::min<uint64_t>(nbig, (uint64_t)c->sm_count * 2), std::max<uint64_t>(1, budget / (per_cta * 8)));
+        CU(c->d_scratch.reserve(per_cta * g * 8));
+        LaunchTimer t(c, F_MERGE_HASH128);
+        auto kern = k_merge_hash128<W_THREADS_L, 0, MODE>;
+        kern<<<(unsigned)g, W_THREADS_L, merge_hash128_smem_bytes<W_THREADS_L, 0>(), st>>>(
+            dv, nch, retry, (uint32_t)nbig, u0, P, c->rk, c->params.min_multiplicity, out, c->d_scratch.as<uint64_t>(), per_cta,
+            PartSrc128(), retry_cnt);
     }
     CU(cudaGetLastError());
     return 0;
@@ -766,7 +837,7 @@ int32_t merge_range_device_wide(ggcat_b200_ctx *c, uint32_t first_bucket, uint32
     cudaStream_t st = c->stream;
     const uint32_t u0 = first_bucket << P.b2, nu = n_buckets << P.b2;
     std::vector<uint32_t> work[3];
-    std::vector<std::pair<uint64_t, uint32_t>> large;
+    std::vector<std::pair<uint64_t, uint32_t>> large, big;
     uint64_t tot_kmers = 0;
     for (uint32_t u = u0; u < u0 + nu; u++) {
         uint64_t n = 0;
@@ -777,10 +848,23 @@ int32_t merge_range_device_wide(ggcat_b200_ctx *c, uint32_t first_bucket, uint32
         tot_kmers += n;
         if (n <= W_TS_S * 3 / 4) work[0].push_back(u);
         else if (n <= W_TS_L * 3 / 4) work[1].push_back(u);
+        else if (n <= (uint64_t)PART_MAXP * W_PART_TARGET && !c->no_partition) big.push_back({n, u});
         else large.push_back({n, u});
     }
     std::sort(large.begin(), large.end(), [](const auto &a, const auto &b) { return a.first > b.first; });
     for (auto &pr : large) work[2].push_back(pr.second);
+    std::sort(big.begin(), big.end(), [](const auto &a, const auto &b) { return a.first > b.first; });
+    BigPlan128 bp;
+    uint64_t big_records = 0;
+    for (auto &pr : big) {
+        uint32_t lp = 2;
+        while (((uint64_t)W_PART_TARGET << lp) < pr.first) lp++;
+        bp.unit.push_back(pr.second); bp.logp.push_back(lp); bp.pbase.push_back(bp.n_parts);
+        for (uint32_t q = 0; q < (1u << lp); q++) bp.part_big.push_back((uint32_t)bp.unit.size() - 1);
+        bp.n_parts += 1u << lp;
+        big_records += pr.first;
+        bp.nmax = std::max(bp.nmax, pr.first);
+    }
     std::vector<ChunkView> views;
     for (Chunk *ch : c->chunks) {
         ChunkView v;
@@ -797,7 +881,13 @@ int32_t merge_range_device_wide(ggcat_b200_ctx *c, uint32_t first_bucket, uint32
             CU(cudaMemcpyAsync(c->d_work[q].p, work[q].data(), work[q].size() * 4, cudaMemcpyHostToDevice, st));
     }
     const uint64_t cap = std::max<uint64_t>(tot_kmers, 1);
-    CU(c->out_keys.reserve(cap * 8)); CU(c->out_hi.reserve(cap * 8)); CU(c->out_cf.reserve(cap * 4));
+    // dynamic region [0, cap) (cursor allocation), then the static regions of the partitioned units
+    {
+        uint64_t acc = cap;
+        for (auto &pr : big) { bp.off.push_back(acc); acc += pr.first; }
+    }
+    const uint64_t cap_all = cap + big_records;
+    CU(c->out_keys.reserve(cap_all * 8)); CU(c->out_hi.reserve(cap_all * 8)); CU(c->out_cf.reserve(cap_all * 4));
     const uint64_t rec_total = std::max(cap, pb.cap_total);
     if (pb.ub == 0) {
         // coloured builds fold in one piece and need every (k-mer, colour) entry; the others grow with the survivors
@@ -816,9 +906,9 @@ int32_t merge_range_device_wide(ggcat_b200_ctx *c, uint32_t first_bucket, uint32
     out.unit_out_cnt = c->unit_out_cnt.as<uint32_t>(); out.capacity = cap; out.overflow = c->overflow.as<uint32_t>();
     const ChunkView *dv = c->d_views.as<ChunkView>();
     const uint32_t nch = (uint32_t)views.size();
-    if (c->wide_mode == MODE_SEQ128) TRY(launch_hash128<MODE_SEQ128>(c, dv, nch, work, u0, out, large));
-    else if (c->wide_mode == MODE_RK128) TRY(launch_hash128<MODE_RK128>(c, dv, nch, work, u0, out, large));
-    else TRY(launch_hash128<MODE_COLOR>(c, dv, nch, work, u0, out, large));
+    if (c->wide_mode == MODE_SEQ128) { TRY(launch_hash128<MODE_SEQ128>(c, dv, nch, work, u0, out, large)); TRY(launch_partitions128<MODE_SEQ128>(c, dv, nch, u0, out, bp)); }
+    else if (c->wide_mode == MODE_RK128) { TRY(launch_hash128<MODE_RK128>(c, dv, nch, work, u0, out, large)); TRY(launch_partitions128<MODE_RK128>(c, dv, nch, u0, out, bp)); }
+    else { TRY(launch_hash128<MODE_COLOR>(c, dv, nch, work, u0, out, large)); TRY(launch_partitions128<MODE_COLOR>(c, dv, nch, u0, out, bp)); }
     // ---- order every unit's entries by key into the unit-ordered layout
     uint32_t end_bit = 128;
     if (c->wide_mode == MODE_SEQ128) end_bit = std::min(128u, (2 * P.k + 7) & ~7u);
@@ -837,11 +927,11 @@ int32_t merge_range_device_wide(ggcat_b200_ctx *c, uint32_t first_bucket, uint32
         }
         CU(cudaGetLastError());
         if (c->wide_mode == MODE_COLOR || attempt > 0) break;   // sized for every record / already regrown
-        CU(cudaMemcpyAsync(c->h_pinned, c->cursor.p, 24, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(c->h_pinned, c->cursor.p, 32, cudaMemcpyDeviceToHost, st));
         CU(cudaMemcpyAsync(c->h_pinned + 8, c->overflow.p, 4, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
         if ((uint32_t)c->h_pinned[8] != 4u) break;
-        const uint64_t need = pb.eb + c->h_pinned[0];
+        const uint64_t need = pb.eb + c->h_pinned[0] + c->h_pinned[3];
         TRY(final_reserve(c, std::max(need, std::min(rec_total, need + need / 2)), pb.eb, true));
         CU(cudaMemsetAsync(c->overflow.p, 0, 16, st));
     }
@@ -874,12 +964,13 @@ int32_t merge_range_device_wide(ggcat_b200_ctx *c, uint32_t first_bucket, uint32
         c->fin.keys_lo = c->out_keys2.as<uint64_t>(); c->fin.keys_hi = c->out_hi2.as<uint64_t>(); c->fin.cf = c->out_cf2.as<uint32_t>();
         c->fin.unit_off = c->unit_final_off.as<uint64_t>();
     }
-    CU(cudaMemcpyAsync(c->h_pinned, c->cursor.p, 24, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(c->h_pinned, c->cursor.p, 32, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(c->h_pinned + 8, c->overflow.p, 4, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     CU(cudaGetLastError());
     const uint32_t ovf = (uint32_t)c->h_pinned[8];
     if (ovf) return set_err(GGCAT_B200_ERR_CAPACITY, "merge output overflow (code %u)", ovf);
+    c->h_pinned[0] += c->h_pinned[3];   // entries of the dynamic region + entries of the partitioned units' regions
     uint64_t uq = c->h_pinned[1];
     if (c->wide_mode == MODE_COLOR) {
         c->fin.n_entries = c->h_pinned[4]; c->fin.n_colors = c->h_pinned[5];
@@ -1019,7 +1110,7 @@ void ggcat_b200_destroy(ggcat_b200_ctx *c) {
     for (DevBuf *b : {&c->d_ascii, &c->d_offsets, &c->d_colors, &c->pk, &c->bad, &c->brk, &c->ent, &c->tile_cnt, &c->tile_sbase,
                       &c->tmp, &c->tmp_color, &c->cur_cnt, &c->cur_words, &c->totals, &c->d_views, &c->d_work[0], &c->d_work[1],
                       &c->d_work[2], &c->d_scratch, &c->out_keys, &c->out_cf, &c->out_keys2, &c->out_cf2,
-                      &c->d_mstage, &c->d_unit_n, &c->d_static_off, &c->d_unit_fill, &c->cursor, &c->unit_out_off, &c->unit_out_cnt, &c->unit_final_off, &c->overflow, &c->d_retry,
+                      &c->d_recfl, &c->d_mstage, &c->d_unit_n, &c->d_static_off, &c->d_unit_fill, &c->cursor, &c->unit_out_off, &c->unit_out_cnt, &c->unit_final_off, &c->overflow, &c->d_retry,
                       &c->d_partmeta, &c->d_recs, &c->fin_tmp_keys, &c->fin_tmp_cf,
                       &c->out_hi, &c->out_hi2, &c->unit_keys, &c->unit_cols, &c->col_off, &c->out_coloff, &c->out_colors})
         b->release();

@@ -46,11 +46,27 @@ __host__ __device__ __forceinline__ K128 to_k128(u128 v) { return K128{(unsigned
 struct MergeOut128 {
     uint64_t *keys_lo, *keys_hi;
     uint32_t *count_flags;
-    unsigned long long *cursor;   // [0] entries written, [1] distinct slot keys, [2] k-mer occurrences
+    unsigned long long *cursor;   // [0] entries written (allocation cursor of the dynamic region), [1] distinct slot keys,
+                                  // [2] k-mer occurrences, [3] entries written into the static regions of big units
     uint64_t *unit_out_off;
     uint32_t *unit_out_cnt;
-    uint64_t capacity;
+    uint64_t capacity;            // dynamic region [0, capacity); the static regions of partitioned units follow it
     uint32_t *overflow;
+};
+
+// Key partitions of big units (same scheme as merge.cuh, 128-bit keys): k_partition_units128 expands a unit once and
+// routes every record by a hash of its key into partitions of <= pcap records in HBM; k_merge_hash128<.., SRC_RECORDS>
+// counts one partition per CTA in shared memory and appends its survivors to the unit's static output region.
+struct PartSrc128 {
+    const uint64_t *rec_lo, *rec_hi;   // [n_parts_total][pcap]
+    const uint8_t *rec_fl;             // flag bits of the record
+    const uint32_t *pcount;            // [n_parts_total]
+    const uint32_t *part_big;          // work item -> index of its big unit
+    const uint32_t *big_unit;          // [n_big] unit id
+    const uint32_t *big_ovf;           // [n_big] 1 = a partition overflowed: the unit is redone by the global-table kernel
+    const uint64_t *big_off;           // [n_big] start of the unit's static output region
+    uint32_t *big_fill;                // [n_big] entries handed out inside the region
+    uint32_t pcap, pad;
 };
 
 constexpr unsigned long long EMPTY64 = ~0ull;
@@ -133,23 +149,31 @@ constexpr size_t merge_hash128_smem_bytes() {
 
 // TS_STATIC > 0: table in shared memory (units with <= 3/4 TS_STATIC records).  TS_STATIC == 0: table in this CTA's
 // slice of `scratch` (hash_table_slots_pow2(n) slots of 20 bytes).
-template <int THREADS, int TS_STATIC, int MODE>
+template <int THREADS, int TS_STATIC, int MODE, int SRC = SRC_SUPERKMERS>
 __global__ void __launch_bounds__(THREADS)
 k_merge_hash128(const ChunkView *__restrict__ chunks, uint32_t n_chunks, const uint32_t *__restrict__ work, uint32_t n_work,
                 uint32_t first_unit, DevParams P, RkTables T, uint32_t min_mult, MergeOut128 out,
-                uint64_t *__restrict__ scratch, uint64_t per_cta_u64) {
+                uint64_t *__restrict__ scratch, uint64_t per_cta_u64, PartSrc128 ps, const uint32_t *__restrict__ n_work_dev) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     K128 *K = reinterpret_cast<K128 *>(smem_raw);
     uint32_t *C = reinterpret_cast<uint32_t *>(K + TS_STATIC);
     __shared__ uint32_t s_cnt[2];
     __shared__ unsigned long long s_base;
     const uint32_t tid = threadIdx.x;
+    if (n_work_dev) n_work = min(n_work, *n_work_dev);   // device-side list (big units whose partitions overflowed)
     for (uint32_t wi = blockIdx.x; wi < n_work; wi += gridDim.x) {
-        const uint32_t unit = work[wi];
-        uint32_t n = 0;
-        for (uint32_t c = 0; c < n_chunks; c++) {
-            const ChunkView &cv = chunks[c];
-            if (unit >= cv.first_unit && unit < cv.first_unit + cv.n_units) n += cv.unit_kmers[unit - cv.first_unit];
+        uint32_t unit = 0, n = 0;
+        if (SRC == SRC_RECORDS) {
+            if (ps.big_ovf[ps.part_big[wi]]) continue;   // the whole unit is redone from its super-k-mers
+            unit = ps.big_unit[ps.part_big[wi]];
+            n = min(ps.pcount[wi], ps.pcap);
+            if (n == 0) continue;
+        } else {
+            unit = work[wi];
+            for (uint32_t c = 0; c < n_chunks; c++) {
+                const ChunkView &cv = chunks[c];
+                if (unit >= cv.first_unit && unit < cv.first_unit + cv.n_units) n += cv.unit_kmers[unit - cv.first_unit];
+            }
         }
         uint32_t TS = TS_STATIC;
         if (TS_STATIC == 0) {
@@ -161,18 +185,24 @@ k_merge_hash128(const ChunkView *__restrict__ chunks, uint32_t n_chunks, const u
         for (uint32_t i = tid; i < TS; i += THREADS) { K[i] = K128{EMPTY64, EMPTY64}; C[i] = 0u; }
         if (tid < 2) s_cnt[tid] = 0;
         __syncthreads();
-        for (uint32_t c = 0; c < n_chunks; c++) {
-            const ChunkView cv = chunks[c];
-            if (unit < cv.first_unit || unit >= cv.first_unit + cv.n_units) continue;
-            const uint32_t d0 = cv.unit_off[unit - cv.first_unit], d1 = cv.unit_off[unit - cv.first_unit + 1];
-            for (uint32_t di = d0 + tid; di < d1; di += THREADS) {
-                const uint4 d = cv.desc[di];
-                const uint32_t color = d.w;
-                for_each_kmer128<MODE>(cv.payload + (d.x - cv.word_bias), d.y, (d.z >> 16) & 3u, P.k, P.forward_only, T,
-                                       [&](u128 key, uint32_t fb) {
-                                           if (MODE == MODE_COLOR) key = (key << 32) | (u128)color;
-                                           hash_insert128(K, C, tmask, key, fb);
-                                       });
+        if (SRC == SRC_RECORDS) {
+            const uint64_t ro = (uint64_t)wi * ps.pcap;
+            for (uint32_t i = tid; i < n; i += THREADS)
+                hash_insert128(K, C, tmask, ((u128)ps.rec_hi[ro + i] << 64) | (u128)ps.rec_lo[ro + i], ps.rec_fl[ro + i]);
+        } else {
+            for (uint32_t c = 0; c < n_chunks; c++) {
+                const ChunkView cv = chunks[c];
+                if (unit < cv.first_unit || unit >= cv.first_unit + cv.n_units) continue;
+                const uint32_t d0 = cv.unit_off[unit - cv.first_unit], d1 = cv.unit_off[unit - cv.first_unit + 1];
+                for (uint32_t di = d0 + tid; di < d1; di += THREADS) {
+                    const uint4 d = cv.desc[di];
+                    const uint32_t color = d.w;
+                    for_each_kmer128<MODE>(cv.payload + (d.x - cv.word_bias), d.y, (d.z >> 16) & 3u, P.k, P.forward_only, T,
+                                           [&](u128 key, uint32_t fb) {
+                                               if (MODE == MODE_COLOR) key = (key << 32) | (u128)color;
+                                               hash_insert128(K, C, tmask, key, fb);
+                                           });
+                }
             }
         }
         __syncthreads();
@@ -200,20 +230,30 @@ k_merge_hash128(const ChunkView *__restrict__ chunks, uint32_t n_chunks, const u
         __syncthreads();
         const uint32_t S = s_cnt[0];
         if (tid == 0) {
-            const unsigned long long b = atomicAdd(&out.cursor[0], (unsigned long long)S);
+            unsigned long long b;
+            if (SRC == SRC_RECORDS) {
+                // the partitions of a unit share its static region: survivors of all partitions end up contiguous
+                const uint32_t bi = ps.part_big[wi];
+                b = ps.big_off[bi] + atomicAdd(&ps.big_fill[bi], S);
+                atomicAdd(&out.cursor[3], (unsigned long long)S);
+                out.unit_out_off[unit - first_unit] = ps.big_off[bi];
+                atomicAdd(&out.unit_out_cnt[unit - first_unit], S);
+            } else {
+                b = atomicAdd(&out.cursor[0], (unsigned long long)S);
+                out.unit_out_off[unit - first_unit] = b;
+                out.unit_out_cnt[unit - first_unit] = S;
+                if (b + S > out.capacity) *out.overflow = 1u;
+            }
             atomicAdd(&out.cursor[1], (unsigned long long)s_cnt[1]);
             atomicAdd(&out.cursor[2], (unsigned long long)n);
             s_base = b;
-            out.unit_out_off[unit - first_unit] = b;
-            out.unit_out_cnt[unit - first_unit] = S;
-            if (b + S > out.capacity) *out.overflow = 1u;
         }
         __syncthreads();
         const unsigned long long gbase = s_base;
         if (tid == 0) s_cnt[0] = 0;
         __syncthreads();
         // ---- pass 2: append survivors (arbitrary order inside the unit's range; k_sort_units128 orders them)
-        if (gbase + S <= out.capacity) {
+        if (SRC == SRC_RECORDS || gbase + S <= out.capacity) {
             for (uint32_t base = 0; base < TS; base += THREADS) {
                 const uint32_t i = base + tid;
                 bool keep = false;
@@ -241,6 +281,58 @@ k_merge_hash128(const ChunkView *__restrict__ chunks, uint32_t n_chunks, const u
                 }
             }
         }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_partition_units128: one CTA per big unit.  Expands the unit once (one super-k-mer per thread, rolling hashes) and
+// appends every record to partition part_hash128(key) & (np - 1); the CTA owns all partitions of its unit, so the
+// cursors live in shared memory.  An overflowing partition flags the unit for the global-table kernel.
+__device__ __forceinline__ uint32_t part_hash128(u128 key) {   // independent of the in-table slot hash (mix128)
+    const unsigned long long lo = (unsigned long long)key, hi = (unsigned long long)(key >> 64);
+    return (uint32_t)(((lo * 0xD6E8FEB86659FD93ull) ^ (hi * 0x9E3779B97F4A7C15ull) ^ (hi >> 29)) >> 40);
+}
+
+template <int THREADS, int MODE>
+__global__ void __launch_bounds__(THREADS)
+k_partition_units128(const ChunkView *__restrict__ chunks, uint32_t n_chunks, const uint32_t *__restrict__ big_unit,
+                     const uint32_t *__restrict__ big_logp, const uint32_t *__restrict__ big_pbase, uint32_t n_big, DevParams P,
+                     RkTables T, uint64_t *__restrict__ rec_lo, uint64_t *__restrict__ rec_hi, uint8_t *__restrict__ rec_fl,
+                     uint32_t *__restrict__ pcount, uint32_t pcap, uint32_t *__restrict__ big_ovf, uint32_t *__restrict__ retry,
+                     uint32_t *__restrict__ retry_count) {
+    __shared__ uint32_t s_cur[PART_MAXP];
+    __shared__ uint32_t s_ovf;
+    const uint32_t tid = threadIdx.x;
+    for (uint32_t bi = blockIdx.x; bi < n_big; bi += gridDim.x) {
+        const uint32_t unit = big_unit[bi], np = 1u << big_logp[bi], pbase = big_pbase[bi];
+        for (uint32_t i = tid; i < np; i += THREADS) s_cur[i] = 0;
+        if (tid == 0) s_ovf = 0;
+        __syncthreads();
+        const uint64_t base = (uint64_t)pbase * pcap;
+        for (uint32_t c = 0; c < n_chunks; c++) {
+            const ChunkView cv = chunks[c];
+            if (unit < cv.first_unit || unit >= cv.first_unit + cv.n_units) continue;
+            const uint32_t d0 = cv.unit_off[unit - cv.first_unit], d1 = cv.unit_off[unit - cv.first_unit + 1];
+            for (uint32_t di = d0 + tid; di < d1; di += THREADS) {
+                const uint4 d = cv.desc[di];
+                const uint32_t color = d.w;
+                for_each_kmer128<MODE>(cv.payload + (d.x - cv.word_bias), d.y, (d.z >> 16) & 3u, P.k, P.forward_only, T,
+                                       [&](u128 key, uint32_t fb) {
+                                           // coloured builds: all colours of a k-mer must meet in one partition
+                                           const uint32_t p = part_hash128(key) & (np - 1);
+                                           if (MODE == MODE_COLOR) key = (key << 32) | (u128)color;
+                                           const uint32_t pos = atomicAdd(&s_cur[p], 1u);
+                                           if (pos < pcap) {
+                                               const uint64_t o = base + (uint64_t)p * pcap + pos;
+                                               rec_lo[o] = (uint64_t)key; rec_hi[o] = (uint64_t)(key >> 64); rec_fl[o] = (uint8_t)fb;
+                                           } else s_ovf = 1u;
+                                       });
+            }
+        }
+        __syncthreads();
+        for (uint32_t i = tid; i < np; i += THREADS) pcount[pbase + i] = min(s_cur[i], pcap);
+        if (tid == 0 && s_ovf) { big_ovf[bi] = 1u; retry[atomicAdd(retry_count, 1u)] = unit; }
         __syncthreads();
     }
 }

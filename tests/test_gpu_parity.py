@@ -462,6 +462,51 @@ def test_wide_unit_size_paths(n_bases, ht):
             ctx.close()
 
 
+@pytest.mark.parametrize("k,ht,s", [(63, O.HASH_RK128, 1), (63, O.HASH_RK128, 2), (41, O.HASH_SEQ, 2), (64, O.HASH_SEQ, 40)])
+def test_wide_key_partitions_and_overflow_fallback(k, ht, s):
+    """Wide path, units above the shared-table capacity: key partitions in HBM (k_partition_units128 ->
+    k_merge_hash128<SRC_RECORDS>, survivors of all partitions contiguous in the unit's static region).  A tandem
+    repeat makes some partitions overflow: that unit is redone by the global-table kernel.  Identical tables."""
+    G = _gpu()
+    rng = np.random.default_rng(177 + k)
+    m, b1, b2 = 14, 1, 0
+    motif = util.rand_seq(rng, 211)
+    seqs = [motif * 400, util.rand_seq(rng, 70000), util.revcomp(motif * 150), util.rand_seq(rng, 40000)]
+    reads = O.Reads.from_list(seqs)
+    sk, _ = O.bucketing(reads, k, m, b1, b2)
+    ctx, st = G.minimizer_bucketing([(reads.data, reads.offsets)], b1, b2, k, m, min_multiplicity=s, hash_type=ht)
+    try:
+        _, km = ctx.unit_sizes()
+        assert (km > 6144).sum() >= 2
+        _check_tables(G, ctx, reads, sk, k, s, b1, b2, hash_type=ht)
+    finally:
+        ctx.close()
+
+
+def test_colored_big_units():
+    """-c with units above the shared-table capacity (partition path of the wide kernels in MODE_COLOR)."""
+    G = _gpu()
+    rng = np.random.default_rng(4711)
+    k, m, b1, b2, s = 31, 12, 1, 0, 1
+    anc = util.rand_seq(rng, 30000)
+    seqs, cols = [], []
+    for c in range(4):
+        g = bytearray(anc)
+        for _ in range(40):
+            g[int(rng.integers(0, len(g)))] = ord("ACGT"[int(rng.integers(0, 4))])
+        seqs.append(bytes(g)); cols.append(c)
+    reads = O.Reads.from_list(seqs, colors=cols)
+    sk, _ = O.bucketing(reads, k, m, b1, b2)
+    ctx, st = G.minimizer_bucketing([(reads.data, reads.offsets, reads.colors)], b1, b2, k, m, min_multiplicity=s, colors=True)
+    try:
+        _, km = ctx.unit_sizes()
+        assert (km > 6144).sum() >= 2
+        n = _check_tables(G, ctx, reads, sk, k, s, b1, b2, colors=True)
+        assert n > 0
+    finally:
+        ctx.close()
+
+
 @pytest.mark.parametrize("k,m,b1,b2,s,fo", [(31, 12, 2, 2, 1, False), (31, 12, 1, 1, 2, False), (21, 10, 2, 1, 1, True),
                                              (41, 13, 1, 1, 1, False)])
 def test_colored_build(k, m, b1, b2, s, fo):
