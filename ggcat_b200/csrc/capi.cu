@@ -153,6 +153,7 @@ struct ggcat_b200_ctx {
     std::vector<Chunk *> chunk_pool;  // recycled local chunks (device buffers kept)
     // phase-2 workspace
     DevBuf d_unit_n, d_static_off, d_unit_fill;
+    DevBuf d_rkpos;                        // rabin-karp per-position tables
     DevBuf d_recfl;                        // flag bits of the wide path's partition records
     DevBuf d_mstage;                       // merge uploads (views, work lists, unit_n, static_off) in one copy
     uint8_t *h_mstage = nullptr; size_t h_mstage_cap = 0;
@@ -1063,6 +1064,19 @@ int32_t ggcat_b200_create(const ggcat_b200_params *params, ggcat_b200_ctx **out)
             c->rk.fwd[b] = to_k128(L[b]); c->rk.bkw[b] = to_k128(L[b ^ 2]);
             c->rk.fwd_mk[b] = to_k128(L[b] * mk1 * M); c->rk.bkw_mk1[b] = to_k128(L[b ^ 2] * mk1);
         }
+        // per-position terms L[b] M^j, j < 64
+        std::vector<K128> pos(2 * 64 * 4);
+        u128 mj = 1;
+        for (int j = 0; j < 64; j++) {
+            for (int b = 0; b < 4; b++) { pos[j * 4 + b] = to_k128(L[b] * mj); pos[256 + j * 4 + b] = to_k128(L[b ^ 2] * mj); }
+            mj *= M;
+        }
+        if (c->d_rkpos.reserve(pos.size() * sizeof(K128)) != cudaSuccess ||
+            cudaMemcpy(c->d_rkpos.p, pos.data(), pos.size() * sizeof(K128), cudaMemcpyHostToDevice) != cudaSuccess) {
+            delete c;
+            return set_err(GGCAT_B200_ERR_CUDA, "rabin-karp table upload failed");
+        }
+        c->rk.pos_fwd = c->d_rkpos.as<K128>(); c->rk.pos_bkw = c->d_rkpos.as<K128>() + 256;
     }
     if (const char *np = getenv("GGCAT_B200_NO_PARTITION")) c->no_partition = atoi(np) != 0;
     if (const char *mm = getenv("GGCAT_B200_MERGE")) c->merge_mode = (strcmp(mm, "sort") == 0) ? 0 : 1;
@@ -1110,7 +1124,7 @@ void ggcat_b200_destroy(ggcat_b200_ctx *c) {
     for (DevBuf *b : {&c->d_ascii, &c->d_offsets, &c->d_colors, &c->pk, &c->bad, &c->brk, &c->ent, &c->tile_cnt, &c->tile_sbase,
                       &c->tmp, &c->tmp_color, &c->cur_cnt, &c->cur_words, &c->totals, &c->d_views, &c->d_work[0], &c->d_work[1],
                       &c->d_work[2], &c->d_scratch, &c->out_keys, &c->out_cf, &c->out_keys2, &c->out_cf2,
-                      &c->d_recfl, &c->d_mstage, &c->d_unit_n, &c->d_static_off, &c->d_unit_fill, &c->cursor, &c->unit_out_off, &c->unit_out_cnt, &c->unit_final_off, &c->overflow, &c->d_retry,
+                      &c->d_rkpos, &c->d_recfl, &c->d_mstage, &c->d_unit_n, &c->d_static_off, &c->d_unit_fill, &c->cursor, &c->unit_out_off, &c->unit_out_cnt, &c->unit_final_off, &c->overflow, &c->d_retry,
                       &c->d_partmeta, &c->d_recs, &c->fin_tmp_keys, &c->fin_tmp_cf,
                       &c->out_hi, &c->out_hi2, &c->unit_keys, &c->unit_cols, &c->col_off, &c->out_coloff, &c->out_colors})
         b->release();

@@ -38,6 +38,8 @@ struct RkTables {
     K128 bkw[4];        // L[c ^ 2]
     K128 fwd_mk[4];     // L[c] * M^k        (leaving base, forward hash)
     K128 bkw_mk1[4];    // L[c ^ 2] * M^(k-1) (entering base, reverse hash)
+    const K128 *pos_fwd;  // device [64][4]: L[c] * M^j       -- the first k-mer of a super-k-mer is a sum of table terms
+    const K128 *pos_bkw;  // device [64][4]: L[c ^ 2] * M^j      (k 128-bit adds instead of k 128-bit multiplies)
 };
 
 __host__ __device__ __forceinline__ u128 to_u128(K128 v) { return ((u128)v.hi << 64) | (u128)v.lo; }
@@ -127,9 +129,17 @@ __device__ __forceinline__ void for_each_kmer128(const uint32_t *__restrict__ pl
         }
     } else {
         const u128 M = to_u128(T.mult), MI = to_u128(T.mult_inv);
+        // fw = sum L[b_i] M^(k-1-i), rc = sum L[b_i ^ 2] M^i  (cn_rkhash_base.rs:66-108), from the per-position tables
         u128 fw = 0, rc = 0;
-        for (uint32_t i = 0; i < k; i++) fw = fw * M + to_u128(T.fwd[packed_base(pl, i)]);
-        for (uint32_t i = k; i-- > 0;) rc = rc * M + to_u128(T.bkw[packed_base(pl, i)]);
+        uint32_t cw0 = 0;
+        for (uint32_t i = 0; i < k; i++) {
+            if ((i & 15u) == 0) cw0 = pl[i >> 4];
+            const uint32_t b = (cw0 >> (2u * (i & 15u))) & 3u;
+            const ulonglong2 f = __ldg(reinterpret_cast<const ulonglong2 *>(T.pos_fwd + (k - 1 - i) * 4 + b));
+            const ulonglong2 r = __ldg(reinterpret_cast<const ulonglong2 *>(T.pos_bkw + i * 4 + b));
+            fw += ((u128)f.y << 64) | (u128)f.x;
+            rc += ((u128)r.y << 64) | (u128)r.x;
+        }
         for (uint32_t i = 0;; ++i) {
             const bool isf = forward_only ? true : (fw < rc);
             const u128 key = forward_only ? fw : (fw < rc ? fw : rc);
