@@ -209,7 +209,7 @@ def run_ours(args):
             h_data.copy_(d_data)
             h_off = torch.empty(n_reads + 1, dtype=torch.int64).pin_memory()
             h_off.copy_(d_off)
-        reads_per_push = 4_000_000          # device pushes of 600 Mbases (one bucket chunk each)
+        reads_per_push = args.reads_per_push          # device pushes of 600 Mbases (one bucket chunk each)
     # bucket counts as the reference derives them from the size of the WHOLE input (all ranks' FASTA bytes,
     # crates/io/src/lib.rs:67-140)
     b1, b2 = G.bucket_counts(int(n_reads * world * (READ_LEN + 15)))
@@ -426,6 +426,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=["c2", "c4"],
                     help="c2 = BASELINE configs[1] (the bench line); c4 = a slice of configs[3] (human-scale shape, big merge units)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer pass (large c4 slices)")
+    ap.add_argument("--reads-per-push", type=int, default=4_000_000, help="c4: reads per device push (one bucket chunk each)")
     ap.add_argument("--sample-reads", type=int, default=READS_PER_GPU, help="reads per CPU pass (default: the whole C2 batch)")
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="CPU baseline: repeat passes until this much CPU wall time")
     ap.add_argument("--no-cpu-baseline", action="store_true")

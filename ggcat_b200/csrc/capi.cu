@@ -134,6 +134,7 @@ struct ggcat_b200_ctx {
     uint64_t host_batch = 48ull << 20;   // push_reads(host): H2D of batch i+1 overlaps the kernels of batch i
     uint64_t part_kmers = 36ull << 20;   // merge_bucket_range(host): D2H of part j overlaps the merge of part j+1
     uint64_t part_kmers_dev = 192ull << 20;  // merge_bucket_range_device: bounds the per-part scratch (12 B / record + key partitions)
+    bool part_dev_fixed = false;         // GGCAT_B200_PART_KMERS_DEV given: no grid-filling enlargement (tests)
     uint64_t fin_cap = 0;                // entries the final table (out_keys2 / out_cf2 / out_hi2) can hold
     uint64_t final_hint = 0;             // survivors of the previous build of this context (sizes the next final table)
     cudaStream_t copy_stream = nullptr;
@@ -1085,7 +1086,7 @@ int32_t ggcat_b200_create(const ggcat_b200_params *params, ggcat_b200_ctx **out)
     if (cudaGetDeviceProperties(&prop, p.device) == cudaSuccess) c->sm_count = prop.multiProcessorCount;
     if (const char *hb = getenv("GGCAT_B200_HOST_BATCH")) { uint64_t v = strtoull(hb, nullptr, 10); if (v >= 1024) c->host_batch = std::min<uint64_t>(v, c->max_batch); }
     if (const char *pk = getenv("GGCAT_B200_PART_KMERS")) { uint64_t v = strtoull(pk, nullptr, 10); if (v >= 1024) c->part_kmers = v; }
-    if (const char *pk = getenv("GGCAT_B200_PART_KMERS_DEV")) { uint64_t v = strtoull(pk, nullptr, 10); if (v >= 1024) c->part_kmers_dev = v; }
+    if (const char *pk = getenv("GGCAT_B200_PART_KMERS_DEV")) { uint64_t v = strtoull(pk, nullptr, 10); if (v >= 1024) { c->part_kmers_dev = v; c->part_dev_fixed = true; } }
     c->host_batch = std::min(c->host_batch, c->max_batch);
     bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) == cudaSuccess &&
@@ -1327,22 +1328,28 @@ int32_t ggcat_b200_merge_bucket_range_device(ggcat_b200_ctx *c, uint32_t first_b
     // parts of ~part_kmers_dev records (whole buckets) bound the per-part scratch; every part appends to one final
     // table that stays in HBM.  Coloured builds fold in one piece.
     std::vector<uint64_t> bk(n_buckets, 0);
-    uint64_t tot = 0;
-    for (uint32_t b = 0; b < n_buckets; b++) {
-        const uint32_t ua = (first_bucket + b) << P.b2, ub2 = (first_bucket + b + 1) << P.b2;
+    uint64_t tot = 0, unit_max = 0;
+    {
+        std::vector<uint64_t> un((size_t)n_buckets << P.b2, 0);
+        const uint32_t ua = first_bucket << P.b2, ub2 = (first_bucket + n_buckets) << P.b2;
         for (Chunk *ch : c->chunks) {
             const uint32_t lo = std::max(ua, ch->first_unit), hi = std::min(ub2, ch->first_unit + ch->n_units);
-            for (uint32_t u = lo; u < hi; u++) bk[b] += ch->h_kmers[u - ch->first_unit];
+            for (uint32_t u = lo; u < hi; u++) un[u - ua] += ch->h_kmers[u - ch->first_unit];
         }
-        tot += bk[b];
+        for (size_t i = 0; i < un.size(); i++) { bk[i >> P.b2] += un[i]; unit_max = std::max(unit_max, un[i]); }
+        for (uint32_t b = 0; b < n_buckets; b++) tot += bk[b];
     }
+    // a part must hold enough big units to fill the grid of the one-CTA-per-unit kernels (k_partition_units,
+    // k_finish_units): at human-scale inputs a unit has > 1 M records and 192 M records are only ~150 units
+    const uint64_t part_target = c->part_dev_fixed ? c->part_kmers_dev
+        : std::min<uint64_t>(std::max<uint64_t>(c->part_kmers_dev, 2ull * c->sm_count * unit_max), 640ull << 20);
     std::vector<std::pair<uint32_t, uint32_t>> parts;
-    if (c->wide_mode == MODE_COLOR || tot <= c->part_kmers_dev + c->part_kmers_dev / 2) parts.push_back({first_bucket, n_buckets});
+    if (c->wide_mode == MODE_COLOR || tot <= part_target + part_target / 2) parts.push_back({first_bucket, n_buckets});
     else {
         uint32_t b0 = 0; uint64_t acc = 0;
         for (uint32_t b = 0; b < n_buckets; b++) {
             acc += bk[b];
-            if (acc >= c->part_kmers_dev || b + 1 == n_buckets) { parts.push_back({first_bucket + b0, b + 1 - b0}); b0 = b + 1; acc = 0; }
+            if (acc >= part_target || b + 1 == n_buckets) { parts.push_back({first_bucket + b0, b + 1 - b0}); b0 = b + 1; acc = 0; }
         }
     }
     uint64_t eb = 0, uq = 0, tk = 0;
