@@ -134,6 +134,8 @@ struct ggcat_b200_ctx {
     uint64_t host_batch = 48ull << 20;   // push_reads(host): H2D of batch i+1 overlaps the kernels of batch i
     uint64_t part_kmers = 36ull << 20;   // merge_bucket_range(host): D2H of part j overlaps the merge of part j+1
     uint64_t part_kmers_dev = 192ull << 20;  // merge_bucket_range_device: bounds the per-part scratch (12 B / record + key partitions)
+    double distinct_ratio = 1.0;         // distinct keys / records of the parts merged so far (sizes the key partitions)
+    bool part_fixed = false;             // GGCAT_B200_PART_TARGET=fixed: 4096-record partitions whatever the ratio (tests)
     bool part_dev_fixed = false;         // GGCAT_B200_PART_KMERS_DEV given: no grid-filling enlargement (tests)
     uint64_t fin_cap = 0;                // entries the final table (out_keys2 / out_cf2 / out_hi2) can hold
     uint64_t final_hint = 0;             // survivors of the previous build of this context (sizes the next final table)
@@ -450,6 +452,15 @@ int32_t merge_range_device(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_
     std::vector<uint32_t> work[3], work_t;
     std::vector<std::pair<uint64_t, uint32_t>> large, big;  // (records, unit)
     std::vector<uint64_t> unit_n(nu, 0);
+    // key partitions are sized by the distinct keys they should hold (~2048 = a quarter of the 8192-slot table), from the
+    // distinct/records ratio of the parts merged so far with a 2x margin; k_merge_parts splits a partition that
+    // turns out fuller than that.  Unknown ratio (first part of a context): 4096 records, the table's guaranteed capacity.
+    uint32_t part_target = PART_TARGET;
+    if (!c->part_fixed) {
+        const double r = std::min(1.0, 2.0 * c->distinct_ratio);
+        part_target = (uint32_t)std::min<double>(65536.0, std::max<double>(PART_TARGET, 2048.0 / std::max(r, 1e-3)));
+    }
+    const uint32_t part_cap = part_target + part_target / 2;
     uint64_t tot_kmers = 0;
     for (uint32_t u = u0; u < u0 + nu; u++) {
         uint64_t n = 0;
@@ -462,7 +473,7 @@ int32_t merge_range_device(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_
         if (hash_mode && n <= SM_CAP_T) work_t.push_back(u);
         else if (n <= SM_CAP_S) work[0].push_back(u);
         else if (n <= SM_CAP_L) work[1].push_back(u);
-        else if (hash_mode && n <= (uint64_t)PART_MAXP * PART_TARGET && !c->no_partition) big.push_back({n, u});
+        else if (hash_mode && n <= (uint64_t)PART_MAXP * part_target && !c->no_partition) big.push_back({n, u});
         else large.push_back({n, u});
     }
     // ---- key partitions of big units and the output-slot map
@@ -470,20 +481,12 @@ int32_t merge_range_device(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_
     std::vector<uint32_t> big_unit, big_logp, big_pbase, part_slot, part_big, slot_of_unit;
     uint32_t n_parts = 0, n_slots = nu;
     if (!big.empty()) {
-        std::vector<uint32_t> logp_of(nu, 0);
+        // every unit keeps ONE output slot: the partitions of a big unit append into its region (unit_out_cnt is the fill counter)
         for (auto &pr : big) {
-            uint32_t lp = 2;
-            while (((uint64_t)PART_TARGET << lp) < pr.first) lp++;
-            logp_of[pr.second - u0] = lp;
-        }
-        slot_of_unit.resize(nu + 1);
-        uint32_t sl = 0;
-        for (uint32_t i = 0; i < nu; i++) { slot_of_unit[i] = sl; sl += 1u << logp_of[i]; }
-        slot_of_unit[nu] = sl; n_slots = sl;
-        for (auto &pr : big) {
-            const uint32_t lp = logp_of[pr.second - u0];
+            uint32_t lp = 1;
+            while (((uint64_t)part_target << lp) < pr.first) lp++;
             big_unit.push_back(pr.second); big_logp.push_back(lp); big_pbase.push_back(n_parts);
-            for (uint32_t q = 0; q < (1u << lp); q++) { part_slot.push_back(slot_of_unit[pr.second - u0] + q); part_big.push_back((uint32_t)big_unit.size() - 1); }
+            for (uint32_t q = 0; q < (1u << lp); q++) { part_slot.push_back(pr.second - u0); part_big.push_back((uint32_t)big_unit.size() - 1); }
             n_parts += 1u << lp;
         }
     }
@@ -551,8 +554,8 @@ int32_t merge_range_device(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_
         CU(cudaMemsetAsync(d_big_ovf, 0, nbig * 4, st));
         CU(cudaMemcpyAsync(d_part_slot, part_slot.data(), (size_t)n_parts * 4, cudaMemcpyHostToDevice, st));
         CU(cudaMemcpyAsync(d_part_big, part_big.data(), (size_t)n_parts * 4, cudaMemcpyHostToDevice, st));
-        CU(cudaMemcpyAsync(d_slot_of_unit, slot_of_unit.data(), ((size_t)nu + 1) * 4, cudaMemcpyHostToDevice, st));
-        CU(c->d_recs.reserve((size_t)n_parts * PART_CAP * 8));
+        d_slot_of_unit = nullptr;   // one slot per unit
+        CU(c->d_recs.reserve((size_t)n_parts * part_cap * 8));
     }
     std::vector<Tier> tiers;
     uint64_t scratch_u64 = 1;
@@ -618,18 +621,18 @@ int32_t merge_range_device(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_
                 LaunchTimer t(c, F_PARTITION);
                 const unsigned grid = (unsigned)std::min<size_t>(big.size(), (size_t)c->sm_count * 2);
                 k_partition_units<1024><<<grid, 1024, 0, st>>>(dv, nch, d_big_unit, d_big_logp, d_big_pbase, (uint32_t)big.size(), P,
-                                                               c->d_recs.as<uint64_t>(), d_pcount, PART_CAP, d_big_ovf, retry3, retry3_cnt);
+                                                               c->d_recs.as<uint64_t>(), d_pcount, part_cap, d_big_ovf, retry3, retry3_cnt);
             }
             {
                 LaunchTimer t(c, F_MERGE_HASH_PART);
                 PartSrc ps;
                 ps.recs = c->d_recs.as<uint64_t>(); ps.pcount = d_pcount; ps.part_slot = d_part_slot; ps.part_big = d_part_big;
-                ps.big_ovf = d_big_ovf; ps.big_unit = d_big_unit; ps.pcap = PART_CAP; ps.pad = 0;
-                auto kern = k_merge_hash<SM_THREADS_S, HASH_TS_S, SRC_RECORDS>;
-                const size_t smem = merge_hash_smem_bytes<SM_THREADS_S, HASH_TS_S>();
+                ps.big_ovf = d_big_ovf; ps.big_unit = d_big_unit; ps.pcap = part_cap; ps.pad = 0;
+                auto kern = k_merge_parts<SM_THREADS_S, HASH_TS_S>;
+                const size_t smem = merge_parts_smem_bytes<SM_THREADS_S, HASH_TS_S>();
                 CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 const unsigned grid = (unsigned)std::min<size_t>(n_parts, (size_t)c->sm_count * 2 * 8);
-                kern<<<grid, SM_THREADS_S, smem, st>>>(dv, nch, nullptr, n_parts, u0, P, ms, out, d_unit_n, nullptr, 0, ps, nullptr);
+                kern<<<grid, SM_THREADS_S, smem, st>>>(n_parts, u0, ms, out, ps);
             }
         }
         work[0].clear(); work[1].clear();
@@ -707,6 +710,7 @@ int32_t merge_range_device(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_
     c->fin = FinalTable();
     c->fin.keys_lo = c->out_keys2.as<uint64_t>(); c->fin.cf = c->out_cf2.as<uint32_t>();
     c->fin.unit_off = c->unit_final_off.as<uint64_t>(); c->fin.n_entries = pb.eb + c->h_pinned[0];
+    if (c->h_pinned[2] >= (1ull << 20)) c->distinct_ratio = (double)c->h_pinned[1] / (double)c->h_pinned[2];
     if (n_entries) *n_entries = c->h_pinned[0];
     if (unique) *unique = c->h_pinned[1];
     if (total) *total = c->h_pinned[2];
@@ -1080,6 +1084,8 @@ int32_t ggcat_b200_create(const ggcat_b200_params *params, ggcat_b200_ctx **out)
         c->rk.pos_fwd = c->d_rkpos.as<K128>(); c->rk.pos_bkw = c->d_rkpos.as<K128>() + 256;
     }
     if (const char *np = getenv("GGCAT_B200_NO_PARTITION")) c->no_partition = atoi(np) != 0;
+    if (const char *pt = getenv("GGCAT_B200_PART_TARGET")) c->part_fixed = strcmp(pt, "fixed") == 0;
+    if (const char *dr = getenv("GGCAT_B200_DISTINCT_RATIO")) { const double v = atof(dr); if (v > 0) c->distinct_ratio = v; }  // tests: pretend a ratio
     if (const char *mm = getenv("GGCAT_B200_MERGE")) c->merge_mode = (strcmp(mm, "sort") == 0) ? 0 : 1;
     if (const char *mb = getenv("GGCAT_B200_MAX_BATCH")) { uint64_t v = strtoull(mb, nullptr, 10); if (v >= 1024) c->max_batch = std::min<uint64_t>(v, 1ull << 30); }
     cudaDeviceProp prop;

@@ -564,6 +564,149 @@ k_merge_hash(const ChunkView *__restrict__ chunks, uint32_t n_chunks, const uint
 }
 
 // ------------------------------------------------------------------------------------------------
+// k_merge_parts: one CTA per key partition of a big unit (records written by k_partition_units).
+// Partitions are sized by the DISTINCT keys they are expected to hold, not by their records (at 30x coverage a
+// partition of 60 k records has ~2.5 k distinct k-mers): fewer, larger partitions mean a smaller scatter fan-out in
+// k_partition_units and fewer table clears / scans per record here.  The expectation comes from the parts already
+// merged, so it can be wrong: inserts probe a bounded number of slots, and when the table turns out to be full the CTA
+// splits the partition's KEY SPACE four ways by an independent hash and counts each quarter on its own (work stack in
+// shared memory, records re-read from HBM/L2).  Survivors of every successful pass are appended to the unit's output
+// region (unit_out_cnt is the fill counter), in table order; k_finish_* orders the unit.
+__device__ __forceinline__ bool hash_insert_bounded(uint64_t *K, uint32_t *C, uint32_t TS, uint64_t key, uint32_t fb, uint32_t limit) {
+    uint32_t slot = hash_slot(key, TS);
+    bool claimed = false;
+    for (uint32_t probes = 0;; ++probes) {
+        if (probes >= limit) return false;
+        const uint64_t cur = *reinterpret_cast<volatile uint64_t *>(&K[slot]);
+        if (cur == key) break;
+        if (cur == HASH_EMPTY) {
+            const unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long *>(&K[slot]), HASH_EMPTY, key);
+            if (old == HASH_EMPTY) { claimed = true; break; }
+            if (old == key) break;
+        }
+        slot = slot + 1 == TS ? 0u : slot + 1;
+    }
+    if (!claimed) atomicAdd(&C[slot], 1u);
+    if (fb && ((*reinterpret_cast<volatile uint32_t *>(&C[slot]) >> 30) & fb) != fb) atomicOr(&C[slot], fb << 30);
+    return true;
+}
+__device__ __forceinline__ uint32_t sub_hash(uint64_t key) {   // independent of part_hash and hash_slot
+    return (uint32_t)((key * 0xA24BAED4963EE407ull) >> 33);
+}
+
+template <int THREADS, int TS_STATIC>
+constexpr size_t merge_parts_smem_bytes() { return (size_t)TS_STATIC * 12; }
+
+template <int THREADS, int TS_STATIC>
+__global__ void __launch_bounds__(THREADS)
+k_merge_parts(uint32_t n_parts, uint32_t first_unit, uint32_t min_mult, MergeOut out, PartSrc ps) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t *K = reinterpret_cast<uint64_t *>(smem_raw);
+    uint32_t *C = reinterpret_cast<uint32_t *>(K + TS_STATIC);
+    __shared__ uint32_t s_cnt[6];          // [0] survivors, [1] occupied, [2] records of the pass, [3] table full, [4] write cursor, [5] region base (low)
+    __shared__ unsigned long long s_base;
+    __shared__ uint32_t s_sj[64], s_sq[64], s_sp;
+    const uint32_t tid = threadIdx.x;
+    constexpr uint32_t PROBE_LIMIT = 192;
+    for (uint32_t wi = blockIdx.x; wi < n_parts; wi += gridDim.x) {
+        if (ps.big_ovf[ps.part_big[wi]]) continue;   // a partition overflowed its record buffer: the unit is redone elsewhere
+        const uint32_t n = min(ps.pcount[wi], ps.pcap);
+        if (n == 0) continue;
+        const uint32_t unit_rel = ps.big_unit[ps.part_big[wi]] - first_unit;
+        const uint64_t *__restrict__ recs = ps.recs + (uint64_t)wi * ps.pcap;
+        if (tid == 0) { s_sp = 1; s_sj[0] = 0; s_sq[0] = 0; }
+        __syncthreads();
+        while (true) {
+            const uint32_t sp = s_sp;
+            if (sp == 0) break;
+            const uint32_t j = s_sj[sp - 1], q = s_sq[sp - 1];
+            __syncthreads();
+            const uint32_t TS = j == 0 ? min((uint32_t)TS_STATIC, hash_table_slots(n)) : (uint32_t)TS_STATIC;
+            for (uint32_t i = tid; i < TS; i += THREADS) { K[i] = HASH_EMPTY; C[i] = 0u; }
+            if (tid < 5) s_cnt[tid] = 0;
+            if (tid == 0) s_sp = sp - 1;
+            __syncthreads();
+            const uint32_t jmask = (1u << j) - 1u;
+            uint32_t my_n = 0;
+            for (uint32_t i = tid; i < n; i += THREADS) {
+                const uint64_t r = recs[i];
+                const uint64_t key = r >> 2;
+                if (j && (sub_hash(key) & jmask) != q) continue;
+                ++my_n;
+                if (*reinterpret_cast<volatile uint32_t *>(&s_cnt[3])) break;      // somebody found the table full
+                if (!hash_insert_bounded(K, C, TS, key, (uint32_t)r & 3u, PROBE_LIMIT)) { s_cnt[3] = 1u; break; }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) my_n += __shfl_xor_sync(0xffffffffu, my_n, o);
+            if (lane_id() == 0 && my_n) atomicAdd(&s_cnt[2], my_n);
+            __syncthreads();
+            if (s_cnt[3]) {
+                // split this key subset four ways (j <= 28 keeps the stack within bounds: 3 net entries per level)
+                if (tid == 0) {
+                    uint32_t p2 = s_sp;
+                    if (j <= 28 && p2 + 4 <= 64) {
+                        for (uint32_t c = 0; c < 4; c++) { s_sj[p2] = j + 2; s_sq[p2] = q | (c << j); ++p2; }
+                        s_sp = p2;
+                    } else *out.overflow = 2u;   // cannot happen with < 2^31 records; reported rather than looping
+                }
+                __syncthreads();
+                continue;
+            }
+            // ---- count survivors, reserve inside the unit's region, write
+            {
+                uint32_t my_keep = 0, my_occ = 0;
+                for (uint32_t i = tid; i < TS; i += THREADS) {
+                    const uint64_t kk = K[i];
+                    if (kk == HASH_EMPTY) continue;
+                    ++my_occ;
+                    const uint32_t cc = C[i];
+                    const uint32_t cnt = slot_count(cc), fl = cc >> 30;
+                    if ((cnt >> ((fl == 3u) ? 1 : 0)) >= min_mult) ++my_keep;
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) { my_keep += __shfl_xor_sync(0xffffffffu, my_keep, o); my_occ += __shfl_xor_sync(0xffffffffu, my_occ, o); }
+                if (lane_id() == 0) { if (my_keep) atomicAdd(&s_cnt[0], my_keep); if (my_occ) atomicAdd(&s_cnt[1], my_occ); }
+            }
+            __syncthreads();
+            if (tid == 0) {
+                const uint32_t S = s_cnt[0];
+                s_base = out.static_off[unit_rel] + atomicAdd(&out.unit_out_cnt[unit_rel], S);
+                out.unit_out_off[unit_rel] = out.static_off[unit_rel];
+                out.stats(S, s_cnt[1], s_cnt[2]);
+            }
+            __syncthreads();
+            const unsigned long long gbase = s_base;
+            for (uint32_t base = 0; base < TS; base += THREADS) {
+                const uint32_t i = base + tid;
+                uint64_t kk = HASH_EMPTY;
+                uint32_t cf = 0;
+                if (i < TS) {
+                    kk = K[i];
+                    if (kk != HASH_EMPTY) {
+                        const uint32_t cc = C[i];
+                        const uint32_t cnt = slot_count(cc), fl = cc >> 30;
+                        const uint32_t mult = cnt >> ((fl == 3u) ? 1 : 0);                   // map_entry.rs:79-84
+                        if (mult >= min_mult) cf = (mult > 0x3FFFFFFFu ? 0x3FFFFFFFu : mult) | (fl << 30);
+                    }
+                }
+                const uint32_t bal = __ballot_sync(0xffffffffu, cf != 0);
+                if (bal) {
+                    uint32_t wb = 0;
+                    if (lane_id() == 0) wb = atomicAdd(&s_cnt[4], (uint32_t)__popc(bal));
+                    wb = __shfl_sync(0xffffffffu, wb, 0);
+                    if (cf) {
+                        const unsigned long long o = gbase + wb + __popc(bal & ((1u << lane_id()) - 1u));
+                        out.keys[o] = kk; out.count_flags[o] = cf;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // k_partition_units: one CTA per big unit.  Expands the unit (load-balanced, as k_merge_hash) and appends every record
 // to partition part_hash(key) & (P-1); the CTA owns all partitions of its unit, so the cursors live in shared memory.
 constexpr int PART_MAXP = 4096;

@@ -281,6 +281,29 @@ def test_key_partition_overflow_falls_back(s):
         ctx.close()
 
 
+@pytest.mark.parametrize("s,ratio", [(1, "0.01"), (2, "0.01"), (1, "0.1")])
+def test_key_partitions_sized_by_distinct_keys_split_when_wrong(s, ratio, monkeypatch):
+    """Key partitions are sized from the distinct/records ratio of earlier parts.  Pretend a ratio of 1 % on data whose
+    k-mers are almost all distinct: partitions of tens of thousands of records overflow the 8192-slot table and
+    k_merge_parts must split their key space (twice) -- identical tables and counters."""
+    G = _gpu()
+    monkeypatch.setenv("GGCAT_B200_DISTINCT_RATIO", ratio)
+    rng = np.random.default_rng(99 + s)
+    k, m, b1, b2 = 31, 12, 1, 0
+    g = util.rand_seq(rng, 90000)
+    seqs = [g, util.rand_seq(rng, 60000), util.revcomp(g[10000:40000])]
+    reads = O.Reads.from_list(seqs)
+    sk, _ = O.bucketing(reads, k, m, b1, b2)
+    ctx, st = G.minimizer_bucketing([(reads.data, reads.offsets)], b1, b2, k, m, min_multiplicity=s)
+    try:
+        _, km = ctx.unit_sizes()
+        assert (km > 30000).sum() >= 2
+        _check_tables(G, ctx, reads, sk, k, s, b1, b2)
+        _check_tables(G, ctx, reads, sk, k, s, b1, b2)   # second merge: the ratio now comes from the first one
+    finally:
+        ctx.close()
+
+
 @pytest.mark.parametrize("k,ht", [(31, O.HASH_SEQ), (63, O.HASH_RK128)])
 def test_owner_side_import_on_one_gpu(k, ht):
     """The multi-GPU owner path on one device: context A buckets two pushes, its per-owner chunk slices are copied
