@@ -430,8 +430,7 @@ uint64_t final_estimate(const ggcat_b200_ctx *c, uint64_t records) {
 int32_t merge_range_device_wide(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_buckets, uint64_t *n_entries,
                                 uint64_t *unique, uint64_t *total, PartBase pb);
 
-constexpr uint32_t PART_CAP = 6144;       // records a key partition may hold (= capacity of the 8192-slot shared table)
-constexpr uint32_t PART_TARGET = 4096;    // partitions per big unit = pow2 >= records / PART_TARGET
+constexpr uint32_t PART_TARGET = 4096;    // smallest partition target (records): fits the 8192-slot shared table whatever the data
 constexpr int FIN_THREADS = 512, FIN_BCAP = 6144;
 
 int32_t merge_range_device(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_buckets, uint64_t *n_entries,
@@ -596,7 +595,7 @@ int32_t merge_range_device(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_
             CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             const unsigned grid = (unsigned)std::min<size_t>(work_t.size(), (size_t)c->sm_count * 3 * 8);
             kern<<<grid, SM_THREADS_S, smem, st>>>(dv, nch, d_work_t, (uint32_t)work_t.size(), u0, P, ms, out,
-                                                   d_unit_n, nullptr, 0, PartSrc(), nullptr);
+                                                   d_unit_n, nullptr, 0, nullptr);
         }
         if (!work[0].empty()) {
             LaunchTimer t(c, F_MERGE_HASH);
@@ -605,7 +604,7 @@ int32_t merge_range_device(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_
             CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             const unsigned grid = (unsigned)std::min<size_t>(work[0].size(), (size_t)c->sm_count * 2 * 8);
             kern<<<grid, SM_THREADS_S, smem, st>>>(dv, nch, d_w[0], (uint32_t)work[0].size(), u0, P, ms, out,
-                                                   d_unit_n, nullptr, 0, PartSrc(), nullptr);
+                                                   d_unit_n, nullptr, 0, nullptr);
         }
         if (!work[1].empty()) {
             LaunchTimer t(c, F_MERGE_HASH);
@@ -614,7 +613,7 @@ int32_t merge_range_device(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_
             CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             const unsigned grid = (unsigned)std::min<size_t>(work[1].size(), (size_t)c->sm_count * 8);
             kern<<<grid, SM_THREADS_L, smem, st>>>(dv, nch, d_w[1], (uint32_t)work[1].size(), u0, P, ms, out,
-                                                   d_unit_n, nullptr, 0, PartSrc(), nullptr);
+                                                   d_unit_n, nullptr, 0, nullptr);
         }
         if (!big.empty()) {
             {
@@ -660,8 +659,7 @@ int32_t merge_range_device(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_
             LaunchTimer t(c, F_MERGE_HASH_GLOBAL);
             auto kern = k_merge_hash<GL_THREADS, 0>;
             kern<<<tr.grid, GL_THREADS, merge_hash_smem_bytes<GL_THREADS, 0>(), st>>>(
-                dv, nch, tr.wl, (uint32_t)tr.count, u0, P, ms, out, d_unit_n, c->d_scratch.as<uint64_t>(), tr.per_cta,
-                PartSrc(), tr.count_dev);
+                dv, nch, tr.wl, (uint32_t)tr.count, u0, P, ms, out, d_unit_n, c->d_scratch.as<uint64_t>(), tr.per_cta, tr.count_dev);
         } else {
             LaunchTimer t(c, F_MERGE_GLOBAL);
             sortk<<<tr.grid, GL_THREADS, smem_sort, st>>>(dv, nch, tr.wl, (uint32_t)tr.count, u0, P, ms, out, c->d_scratch.as<uint64_t>(),

@@ -54,7 +54,7 @@ struct MergeOut {
 
 // Key partitions of big units (units that do not fit a shared-memory table): k_partition_units expands the unit once
 // and routes every k-mer record by a hash of its key into one of P partitions in HBM (all occurrences of a k-mer
-// land in the same partition, so partitions are counted independently, no fold); k_merge_hash<.., SRC_RECORDS>
+// land in the same partition, so partitions are counted independently, no fold); k_merge_parts
 // counts one partition per CTA in shared memory; k_finish_units orders the unit's survivors.
 struct PartSrc {
     const uint64_t *recs;        // [n_parts_total][pcap] records (key << 2 | flag bits)
@@ -443,11 +443,12 @@ __host__ __device__ __forceinline__ uint32_t hash_table_slots_pow2(uint32_t n) {
 // After the inserts the table is scanned once (MapEntry -> multiplicity, -s filter) and the survivors are written
 // straight into the unit's output region in table order; ordering by key (part of the output contract) is the job of
 // k_finish_small / k_finish_units, which touch only the survivors.  Per unit the CTA passes 7 barriers.
-template <int THREADS, int TS_STATIC, int SRC = SRC_SUPERKMERS>
+// (Key partitions of big units are counted by k_merge_parts below.)
+template <int THREADS, int TS_STATIC>
 __global__ void __launch_bounds__(THREADS)
 k_merge_hash(const ChunkView *__restrict__ chunks, uint32_t n_chunks, const uint32_t *__restrict__ work, uint32_t n_work,
              uint32_t first_unit, DevParams P, uint32_t min_mult, MergeOut out, const uint32_t *__restrict__ unit_n,
-             uint64_t *__restrict__ scratch, uint64_t per_cta_u64, PartSrc ps, const uint32_t *__restrict__ n_work_dev) {
+             uint64_t *__restrict__ scratch, uint64_t per_cta_u64, const uint32_t *__restrict__ n_work_dev) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t *K = reinterpret_cast<uint64_t *>(smem_raw);                      // TS keys
     uint32_t *C = reinterpret_cast<uint32_t *>(K + TS_STATIC);                 // TS counters|flags
@@ -456,19 +457,10 @@ k_merge_hash(const ChunkView *__restrict__ chunks, uint32_t n_chunks, const uint
     const uint32_t tid = threadIdx.x;
     if (n_work_dev) n_work = min(n_work, *n_work_dev);  // device-side list (big units whose partitions overflowed)
     for (uint32_t wi = blockIdx.x; wi < n_work; wi += gridDim.x) {
-        uint32_t *s_cnt = s_scan + 36;  // [0] survivors written, [1] occupied slots, [2] region base inside the unit (partitions)
-        uint32_t unit_rel, oslot, n;
-        if (SRC == SRC_RECORDS) {
-            if (ps.big_ovf[ps.part_big[wi]]) continue;   // the whole unit is redone from its super-k-mers
-            unit_rel = ps.big_unit[ps.part_big[wi]] - first_unit;
-            oslot = ps.part_slot[wi];
-            n = min(ps.pcount[wi], ps.pcap);
-            if (n == 0) continue;
-        } else {
-            unit_rel = work[wi] - first_unit;
-            oslot = out.slot(unit_rel);
-            n = unit_n[unit_rel];
-        }
+        uint32_t *s_cnt = s_scan + 36;  // [0] survivors written, [1] occupied slots
+        const uint32_t unit_rel = work[wi] - first_unit;
+        const uint32_t oslot = out.slot(unit_rel);
+        const uint32_t n = unit_n[unit_rel];
         uint32_t TS = hash_table_slots(n);
         if (TS_STATIC == 0) {
             K = scratch + (uint64_t)blockIdx.x * per_cta_u64;
@@ -480,45 +472,11 @@ k_merge_hash(const ChunkView *__restrict__ chunks, uint32_t n_chunks, const uint
         for (uint32_t i = tid; i < TS; i += THREADS) { K[i] = HASH_EMPTY; C[i] = 0u; }
         if (tid < 2) s_cnt[tid] = 0;
         __syncthreads();
-        if (SRC == SRC_RECORDS) {
-            const uint64_t *recs = ps.recs + (uint64_t)wi * ps.pcap;
-            for (uint32_t i = tid; i < n; i += THREADS) {
-                const uint64_t r = recs[i];
-                hash_insert(K, C, TS, r >> 2, (uint32_t)r & 3u);
-            }
-        } else {
-            unit_for_each_kmer64<THREADS>(chunks, n_chunks, work[wi], P.k, P.forward_only, stage, s_scan,
-                                          [&](uint64_t key, uint32_t fb) { hash_insert(K, C, TS, key, fb); });
-        }
+        unit_for_each_kmer64<THREADS>(chunks, n_chunks, work[wi], P.k, P.forward_only, stage, s_scan,
+                                      [&](uint64_t key, uint32_t fb) { hash_insert(K, C, TS, key, fb); });
         __syncthreads();
         // ---- scan the table once: MapEntry -> multiplicity, filter, survivors appended to the unit's region
-        unsigned long long gbase = out.static_off[unit_rel];
-        if (SRC == SRC_RECORDS) {
-            // a key partition shares the unit's region: count first, reserve inside the region, then write
-            uint32_t my_keep = 0, my_occ = 0;
-            for (uint32_t i = tid; i < TS; i += THREADS) {
-                const uint64_t kk = K[i];
-                if (kk == HASH_EMPTY) continue;
-                ++my_occ;
-                const uint32_t cc = C[i];
-                const uint32_t cnt = slot_count(cc), fl = cc >> 30;
-                if ((cnt >> ((fl == 3u) ? 1 : 0)) >= min_mult) ++my_keep;
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) { my_keep += __shfl_xor_sync(0xffffffffu, my_keep, o); my_occ += __shfl_xor_sync(0xffffffffu, my_occ, o); }
-            if (lane_id() == 0) { if (my_keep) atomicAdd(&s_cnt[0], my_keep); if (my_occ) atomicAdd(&s_cnt[1], my_occ); }
-            __syncthreads();
-            if (tid == 0) {
-                const uint32_t S = s_cnt[0];
-                s_cnt[2] = atomicAdd(&out.unit_fill[unit_rel], S);
-                out.stats(S, s_cnt[1], n);
-                out.unit_out_off[oslot] = gbase + s_cnt[2];
-                out.unit_out_cnt[oslot] = S;
-                s_cnt[0] = 0;
-            }
-            __syncthreads();
-            gbase += s_cnt[2];
-        }
+        const unsigned long long gbase = out.static_off[unit_rel];
         {
             uint32_t my_occ = 0;
             for (uint32_t base = 0; base < TS; base += THREADS) {
@@ -546,14 +504,12 @@ k_merge_hash(const ChunkView *__restrict__ chunks, uint32_t n_chunks, const uint
                     }
                 }
             }
-            if (SRC != SRC_RECORDS) {
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) my_occ += __shfl_xor_sync(0xffffffffu, my_occ, o);
-                if (lane_id() == 0 && my_occ) atomicAdd(&s_cnt[1], my_occ);
-            }
+            for (int o = 16; o > 0; o >>= 1) my_occ += __shfl_xor_sync(0xffffffffu, my_occ, o);
+            if (lane_id() == 0 && my_occ) atomicAdd(&s_cnt[1], my_occ);
         }
         __syncthreads();
-        if (SRC != SRC_RECORDS && tid == 0) {
+        if (tid == 0) {
             const uint32_t S = s_cnt[0];
             out.stats(S, s_cnt[1], n);
             out.unit_out_off[oslot] = gbase;
