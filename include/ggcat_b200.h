@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define GGCAT_B200_ABI_VERSION 3
+#define GGCAT_B200_ABI_VERSION 4
 
 typedef enum {
     GGCAT_B200_OK = 0,
