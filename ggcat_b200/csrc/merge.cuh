@@ -584,13 +584,22 @@ k_merge_parts(uint32_t n_parts, uint32_t first_unit, uint32_t min_mult, MergeOut
             __syncthreads();
             const uint32_t jmask = (1u << j) - 1u;
             uint32_t my_n = 0;
-            for (uint32_t i = tid; i < n; i += THREADS) {
-                const uint64_t r = recs[i];
-                const uint64_t key = r >> 2;
-                if (j && (sub_hash(key) & jmask) != q) continue;
-                ++my_n;
-                if (*reinterpret_cast<volatile uint32_t *>(&s_cnt[3])) break;      // somebody found the table full
-                if (!hash_insert_bounded(K, C, TS, key, (uint32_t)r & 3u, PROBE_LIMIT)) { s_cnt[3] = 1u; break; }
+            bool stop = false;
+            for (uint32_t i0 = tid; i0 < n && !stop; i0 += 4 * THREADS) {
+                // four independent record loads in flight per thread (the records come from HBM / L2, one pass)
+                uint64_t rr[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) { const uint32_t i = i0 + u * THREADS; rr[u] = i < n ? __ldcs(recs + i) : 0ull; }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const uint64_t r = rr[u];
+                    if (i0 + u * THREADS >= n || stop) continue;
+                    const uint64_t key = r >> 2;
+                    if (j && (sub_hash(key) & jmask) != q) continue;
+                    ++my_n;
+                    if (*reinterpret_cast<volatile uint32_t *>(&s_cnt[3])) { stop = true; continue; }   // somebody found the table full
+                    if (!hash_insert_bounded(K, C, TS, key, (uint32_t)r & 3u, PROBE_LIMIT)) { s_cnt[3] = 1u; stop = true; }
+                }
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) my_n += __shfl_xor_sync(0xffffffffu, my_n, o);
