@@ -155,7 +155,7 @@ struct ggcat_b200_ctx {
     std::vector<Chunk *> chunks;
     std::vector<Chunk *> chunk_pool;  // recycled local chunks (device buffers kept)
     // phase-2 workspace
-    DevBuf d_unit_n, d_static_off, d_unit_fill;
+    DevBuf d_static_off;                   // wide path: static output regions of partitioned units
     DevBuf d_rkpos;                        // rabin-karp per-position tables
     DevBuf d_recfl;                        // flag bits of the wide path's partition records
     DevBuf d_mstage;                       // merge uploads (views, work lists, unit_n, static_off) in one copy
@@ -477,15 +477,16 @@ int32_t merge_range_device(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_
     }
     // ---- key partitions of big units and the output-slot map
     std::sort(big.begin(), big.end(), [](const auto &a, const auto &b) { return a.first > b.first; });
-    std::vector<uint32_t> big_unit, big_logp, big_pbase, part_slot, part_big, slot_of_unit;
-    uint32_t n_parts = 0, n_slots = nu;
+    std::vector<uint32_t> big_unit, big_logp, big_pbase, part_big;
+    uint32_t n_parts = 0;
+    const uint32_t n_slots = nu;   // one output slot per unit
     if (!big.empty()) {
         // every unit keeps ONE output slot: the partitions of a big unit append into its region (unit_out_cnt is the fill counter)
         for (auto &pr : big) {
             uint32_t lp = 1;
             while (((uint64_t)part_target << lp) < pr.first) lp++;
             big_unit.push_back(pr.second); big_logp.push_back(lp); big_pbase.push_back(n_parts);
-            for (uint32_t q = 0; q < (1u << lp); q++) { part_slot.push_back(pr.second - u0); part_big.push_back((uint32_t)big_unit.size() - 1); }
+            for (uint32_t q = 0; q < (1u << lp); q++) part_big.push_back((uint32_t)big_unit.size() - 1);
             n_parts += 1u << lp;
         }
     }
@@ -536,24 +537,22 @@ int32_t merge_range_device(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_
     const uint32_t *d_work_t = reinterpret_cast<const uint32_t *>(dm + off_wt);
     const uint32_t *d_w[3] = {reinterpret_cast<const uint32_t *>(dm + off_w0), reinterpret_cast<const uint32_t *>(dm + off_w1),
                               reinterpret_cast<const uint32_t *>(dm + off_w2)};
-    uint32_t *d_big_unit = nullptr, *d_big_logp = nullptr, *d_big_pbase = nullptr, *d_big_ovf = nullptr, *d_part_slot = nullptr,
-             *d_part_big = nullptr, *d_pcount = nullptr, *d_slot_of_unit = nullptr;
+    uint32_t *d_big_unit = nullptr, *d_big_logp = nullptr, *d_big_pbase = nullptr, *d_big_ovf = nullptr, *d_part_big = nullptr,
+             *d_pcount = nullptr;
+    const uint32_t *d_slot_of_unit = nullptr;   // every unit has one output slot (the finish kernels also accept a slot map)
     if (!big.empty()) {
         const size_t nbig = big.size();
-        // one metadata buffer: big_unit | big_logp | big_pbase | big_ovf | part_slot | part_big | pcount | slot_of_unit
-        const size_t words = 4 * nbig + 3 * (size_t)n_parts + nu + 1;
+        // one metadata buffer: big_unit | big_logp | big_pbase | big_ovf | part_big | pcount
+        const size_t words = 4 * nbig + 2 * (size_t)n_parts;
         CU(c->d_partmeta.reserve(words * 4));
         uint32_t *base = c->d_partmeta.as<uint32_t>();
         d_big_unit = base; d_big_logp = base + nbig; d_big_pbase = base + 2 * nbig; d_big_ovf = base + 3 * nbig;
-        d_part_slot = base + 4 * nbig; d_part_big = d_part_slot + n_parts; d_pcount = d_part_big + n_parts;
-        d_slot_of_unit = d_pcount + n_parts;
+        d_part_big = base + 4 * nbig; d_pcount = d_part_big + n_parts;
         CU(cudaMemcpyAsync(d_big_unit, big_unit.data(), nbig * 4, cudaMemcpyHostToDevice, st));
         CU(cudaMemcpyAsync(d_big_logp, big_logp.data(), nbig * 4, cudaMemcpyHostToDevice, st));
         CU(cudaMemcpyAsync(d_big_pbase, big_pbase.data(), nbig * 4, cudaMemcpyHostToDevice, st));
         CU(cudaMemsetAsync(d_big_ovf, 0, nbig * 4, st));
-        CU(cudaMemcpyAsync(d_part_slot, part_slot.data(), (size_t)n_parts * 4, cudaMemcpyHostToDevice, st));
         CU(cudaMemcpyAsync(d_part_big, part_big.data(), (size_t)n_parts * 4, cudaMemcpyHostToDevice, st));
-        d_slot_of_unit = nullptr;   // one slot per unit
         CU(c->d_recs.reserve((size_t)n_parts * part_cap * 8));
     }
     std::vector<Tier> tiers;
@@ -575,14 +574,12 @@ int32_t merge_range_device(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_
     CU(cudaMemsetAsync(c->overflow.p, 0, 16, st));
     CU(cudaMemsetAsync(c->unit_out_off.p, 0, ((size_t)n_slots + 1) * 8, st));
     CU(cudaMemsetAsync(c->unit_out_cnt.p, 0, ((size_t)n_slots + 1) * 4, st));
-    CU(c->d_unit_fill.reserve((size_t)nu * 4));
-    CU(cudaMemsetAsync(c->d_unit_fill.p, 0, (size_t)nu * 4, st));
     const uint32_t *d_unit_n = reinterpret_cast<const uint32_t *>(dm + off_un);
     MergeOut out;
     out.keys = c->out_keys.as<uint64_t>(); out.count_flags = c->out_cf.as<uint32_t>();
     out.cursor = c->cursor.as<unsigned long long>(); out.unit_out_off = c->unit_out_off.as<uint64_t>();
     out.unit_out_cnt = c->unit_out_cnt.as<uint32_t>(); out.overflow = c->overflow.as<uint32_t>();
-    out.static_off = reinterpret_cast<const uint64_t *>(dm + off_so); out.unit_fill = c->d_unit_fill.as<uint32_t>();
+    out.static_off = reinterpret_cast<const uint64_t *>(dm + off_so);
     out.slot_of_unit = d_slot_of_unit;
     const ChunkView *dv = reinterpret_cast<const ChunkView *>(dm + off_views);
     const uint32_t nch = (uint32_t)views.size();
@@ -625,7 +622,7 @@ int32_t merge_range_device(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_
             {
                 LaunchTimer t(c, F_MERGE_HASH_PART);
                 PartSrc ps;
-                ps.recs = c->d_recs.as<uint64_t>(); ps.pcount = d_pcount; ps.part_slot = d_part_slot; ps.part_big = d_part_big;
+                ps.recs = c->d_recs.as<uint64_t>(); ps.pcount = d_pcount; ps.part_big = d_part_big;
                 ps.big_ovf = d_big_ovf; ps.big_unit = d_big_unit; ps.pcap = part_cap; ps.pad = 0;
                 auto kern = k_merge_parts<SM_THREADS_S, HASH_TS_S>;
                 const size_t smem = merge_parts_smem_bytes<SM_THREADS_S, HASH_TS_S>();
@@ -1129,7 +1126,7 @@ void ggcat_b200_destroy(ggcat_b200_ctx *c) {
     for (DevBuf *b : {&c->d_ascii, &c->d_offsets, &c->d_colors, &c->pk, &c->bad, &c->brk, &c->ent, &c->tile_cnt, &c->tile_sbase,
                       &c->tmp, &c->tmp_color, &c->cur_cnt, &c->cur_words, &c->totals, &c->d_views, &c->d_work[0], &c->d_work[1],
                       &c->d_work[2], &c->d_scratch, &c->out_keys, &c->out_cf, &c->out_keys2, &c->out_cf2,
-                      &c->d_rkpos, &c->d_recfl, &c->d_mstage, &c->d_unit_n, &c->d_static_off, &c->d_unit_fill, &c->cursor, &c->unit_out_off, &c->unit_out_cnt, &c->unit_final_off, &c->overflow, &c->d_retry,
+                      &c->d_rkpos, &c->d_recfl, &c->d_mstage, &c->d_static_off, &c->cursor, &c->unit_out_off, &c->unit_out_cnt, &c->unit_final_off, &c->overflow, &c->d_retry,
                       &c->d_partmeta, &c->d_recs, &c->fin_tmp_keys, &c->fin_tmp_cf,
                       &c->out_hi, &c->out_hi2, &c->unit_keys, &c->unit_cols, &c->col_off, &c->out_coloff, &c->out_colors})
         b->release();

@@ -31,7 +31,8 @@ struct ChunkView {
 // Output of the merge kernels, before the unit-ordered final layout.  Every unit owns the region
 // [static_off[u], static_off[u] + records(u)) of keys/count_flags (survivors <= distinct <= records), so no kernel
 // waits for a global allocation: a CTA that owns a whole unit writes at the region's start, the key partitions of a
-// big unit share the region through the unit's fill counter.  cursor[] are statistics only (fire-and-forget atomics).
+// big unit append to the region with unit_out_cnt as the fill counter.  cursor[] are statistics only (fire-and-forget
+// atomics).
 constexpr uint32_t SLOT_SORTED = 0x80000000u;   // flag in unit_out_cnt: the slot's entries are already ordered by key
 struct MergeOut {
     uint64_t *keys;                     // survivors: canonical k-mer (2k bits)
@@ -40,7 +41,6 @@ struct MergeOut {
     uint64_t *unit_out_off;             // per output slot: offset
     uint32_t *unit_out_cnt;             //                  count | SLOT_SORTED
     const uint64_t *static_off;         // per unit (relative to the first unit of the launch): start of its region
-    uint32_t *unit_fill;                // per unit: entries handed out inside the region (key partitions)
     uint32_t *overflow;                 // set to 2 if a unit was routed to a kernel that cannot hold it
     const uint32_t *slot_of_unit;       // output slot of a unit (big units own several slots, one per key partition);
                                         // NULL: slot = unit index relative to the first unit of the launch
@@ -59,7 +59,6 @@ struct MergeOut {
 struct PartSrc {
     const uint64_t *recs;        // [n_parts_total][pcap] records (key << 2 | flag bits)
     const uint32_t *pcount;      // [n_parts_total] records per partition
-    const uint32_t *part_slot;   // work item -> output slot
     const uint32_t *part_big;    // work item -> index of its big unit
     const uint32_t *big_unit;    // [n_big] unit id
     const uint32_t *big_ovf;     // [n_big] 1 = a partition overflowed, the unit is redone by the global-table kernel
