@@ -13,7 +13,13 @@ contiguous ranges, super-k-mers are routed with one all-to-all (NCCL) and each o
 Printed JSON line (rank 0): see DESIGN.md "Measurement".
   value    device-timed (CUDA events on the library's stream), inputs resident in HBM
   e2e      same metric through the C ABI with HOST buffers (H2D of reads, D2H of the table inside the timed region)
-  roofline dominant kernel (k_merge_units<smem>) against the measured HBM peak
+  roofline dominant kernel family (k_merge_hash<smem> on C2) against the measured HBM peak; `achieved` uses the
+           algorithmic-bytes model of SURVEY 8(d), `compulsory_bytes_per_launch` what the kernel really has to move
+  exchange N > 1: bytes pushed over NVLink per GPU, time of the push + flag kernels, fraction of 770 GB/s
+  cpu_baseline  N = 1: the oracle's OpenMP port, repeated passes over the whole batch for >= 10 s (kind "port")
+
+--workload c4 benches a slice of BASELINE configs[3] (error-free reads generated on the device, 1024 x 64 buckets, big
+merge units; --reads-per-gpu 77500000 at --gpus 8 is the full 93 Gbases set).  The bench line stays C2.
 """
 from __future__ import annotations
 
