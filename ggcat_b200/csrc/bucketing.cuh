@@ -442,20 +442,28 @@ k_emit(const uint64_t *__restrict__ ent, const uint32_t *__restrict__ tile_cnt, 
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_scatter: one thread per super-k-mer.  Reserves a slot in its unit (atomic cursor), writes the
-// final descriptor {payload word offset, len, meta, colour} and the payload in stored orientation
+// k_scatter: one thread per super-k-mer.  Reserves a descriptor slot AND its payload words in its unit with ONE 64-bit
+// atomic (cursor = slot << 32 | word), so descriptors and payload of a unit appear in the same order: any contiguous
+// descriptor range of a unit owns a contiguous payload range.  Writes the final descriptor {payload word offset, len,
+// meta, colour} and the payload in stored orientation
 // (crates/io/src/concurrent/temp_reads/creads_utils.rs:389-406: rc => reverse-complement packing).
+__global__ void k_init_cursors(const uint32_t *__restrict__ unit_off, const uint32_t *__restrict__ unit_woff, uint32_t n_units,
+                               unsigned long long *__restrict__ cur) {
+    const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u < n_units) cur[u] = ((unsigned long long)unit_off[u] << 32) | (unsigned long long)unit_woff[u];
+}
+
 __global__ void __launch_bounds__(256)
 k_scatter(const uint4 *__restrict__ tmp, const uint32_t *__restrict__ tmp_color, uint32_t n_sk,
-          const uint32_t *__restrict__ pk, uint32_t *__restrict__ cur_cnt, uint32_t *__restrict__ cur_words,
+          const uint32_t *__restrict__ pk, unsigned long long *__restrict__ cur,
           uint4 *__restrict__ desc, uint32_t *__restrict__ payload, uint32_t with_color) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_sk) return;
     const uint4 t = tmp[i];
     const uint32_t start = t.x, len = t.y, meta = t.z, unit = t.w;
     const uint32_t nw = (len + 15u) >> 4;
-    const uint32_t slot = atomicAdd(&cur_cnt[unit], 1u);
-    const uint32_t woff = atomicAdd(&cur_words[unit], nw);
+    const unsigned long long cw = atomicAdd(&cur[unit], (1ull << 32) | (unsigned long long)nw);
+    const uint32_t slot = (uint32_t)(cw >> 32), woff = (uint32_t)cw;
     desc[slot] = make_uint4(woff, len, meta, with_color ? tmp_color[i] : 0u);
     const bool rc = (meta >> 18) & 1u;
     uint32_t *dst = payload + woff;

@@ -146,12 +146,14 @@ struct ggcat_b200_ctx {
     bool timing = false;
     int merge_mode = 1;  // 1 = shared-memory hash table (default), 0 = LSD radix sort (GGCAT_B200_MERGE=sort)
     bool no_partition = false;  // GGCAT_B200_NO_PARTITION=1: big units use the global-scratch table (A/B switch)
+    bool no_tiers = false;      // GGCAT_B200_NO_TIERS=1: every unit takes the key-partition / global-table path (tests)
+    int tier_a_threads = 512;   // GGCAT_B200_TIER_A_THREADS=256: A/B switch of the small-unit tier's CTA size
     int wide_mode = -1;  // -1: 64-bit key path (merge.cuh); else MODE_SEQ128 / MODE_RK128 / MODE_COLOR (merge128.cuh)
     RkTables rk;
     FinalTable fin;
     ggcat_b200_bucket_stats stats;
     // phase-1 workspace
-    DevBuf d_ascii, d_offsets, d_colors, pk, bad, brk, ent, tile_cnt, tile_sbase, tmp, tmp_color, cur_cnt, cur_words, totals;
+    DevBuf d_ascii, d_offsets, d_colors, pk, bad, brk, ent, tile_cnt, tile_sbase, tmp, tmp_color, cur_cnt, totals;
     std::vector<Chunk *> chunks;
     std::vector<Chunk *> chunk_pool;  // recycled local chunks (device buffers kept)
     // phase-2 workspace
@@ -266,10 +268,16 @@ int32_t bucket_batch_device(ggcat_b200_ctx *c, const uint8_t *d_data, const uint
     if (n_sk == 0) return 0;
     if (n_sk >= (1ull << 32)) return set_err(GGCAT_B200_ERR_INVALID, "too many super-k-mers in one batch");
 
+    // the chunk is registered with the context only after the last operation that can fail; until then an error return
+    // puts it back into the pool (a half-initialised chunk must never reach finish_bucketing / the merge)
+    struct ChunkGuard {
+        ggcat_b200_ctx *c; Chunk *ch;
+        ~ChunkGuard() { if (ch) c->chunk_pool.push_back(ch); }
+    } guard{c, nullptr};
     Chunk *ch;
     if (!c->chunk_pool.empty()) { ch = c->chunk_pool.back(); c->chunk_pool.pop_back(); }
     else ch = new Chunk();
-    c->chunks.push_back(ch);
+    guard.ch = ch;
     ch->imported = false; ch->word_bias = 0; ch->mirror_queued = false;
     ch->h_cnt.clear(); ch->h_off.clear(); ch->h_words.clear(); ch->h_woff.clear(); ch->h_kmers.clear();
     ch->first_unit = 0; ch->n_units = P.n_units; ch->n_sk = n_sk; ch->n_bases = n;
@@ -320,21 +328,22 @@ int32_t bucket_batch_device(ggcat_b200_ctx *c, const uint8_t *d_data, const uint
     if (words_bound >= (1ull << 32)) return set_err(GGCAT_B200_ERR_INVALID, "payload of one batch exceeds 2^32 words");
     CU(ch->desc.reserve(n_sk * 16));
     CU(ch->payload.reserve(words_bound * 4));
-    CU(c->cur_cnt.reserve(ub)); CU(c->cur_words.reserve(ub));
-    CU(cudaMemcpyAsync(c->cur_cnt.p, ch->unit_off.p, ub, cudaMemcpyDeviceToDevice, st));
-    CU(cudaMemcpyAsync(c->cur_words.p, ch->unit_woff.p, ub, cudaMemcpyDeviceToDevice, st));
+    CU(c->cur_cnt.reserve(((size_t)P.n_units + 2) * 8));
     {
-        LaunchTimer t(c, F_SCATTER);
+        LaunchTimer t(c, F_SCATTER, 2);
+        k_init_cursors<<<(P.n_units + 255) / 256, 256, 0, st>>>(ch->unit_off.as<uint32_t>(), ch->unit_woff.as<uint32_t>(), P.n_units,
+                                                              c->cur_cnt.as<unsigned long long>());
         k_scatter<<<(unsigned)((n_sk + 255) / 256), 256, 0, st>>>(c->tmp.as<uint4>(), c->tmp_color.as<uint32_t>(), (uint32_t)n_sk,
-                                                                  c->pk.as<uint32_t>(), c->cur_cnt.as<uint32_t>(),
-                                                                  c->cur_words.as<uint32_t>(), ch->desc.as<uint4>(),
-                                                                  ch->payload.as<uint32_t>(), P.colors);
+                                                                  c->pk.as<uint32_t>(), c->cur_cnt.as<unsigned long long>(),
+                                                                  ch->desc.as<uint4>(), ch->payload.as<uint32_t>(), P.colors);
     }
     ch->d_desc = ch->desc.as<uint4>(); ch->d_payload = ch->payload.as<uint32_t>();
     ch->d_unit_cnt = ch->unit_cnt.as<uint32_t>(); ch->d_unit_off = ch->unit_off.as<uint32_t>();
     ch->d_unit_words = ch->unit_words.as<uint32_t>(); ch->d_unit_woff = ch->unit_woff.as<uint32_t>();
     ch->d_unit_kmers = ch->unit_kmers.as<uint32_t>();
     CU(cudaGetLastError());
+    guard.ch = nullptr;
+    c->chunks.push_back(ch);
     return 0;
 }
 
@@ -379,11 +388,20 @@ __global__ void __launch_bounds__(1024) k_scan_counts_u64(const uint32_t *cnt, u
     if (threadIdx.x == 0) off[n] = running;
 }
 
-constexpr int SM_THREADS_S = 512, SM_CAP_S = 6144;     // 2 CTAs / SM
+constexpr int SM_THREADS_S = 512, SM_CAP_S = 6144;     // sort-mode (GGCAT_B200_MERGE=sort) capacities, 2 CTAs / SM
 constexpr int SM_THREADS_L = 1024, SM_CAP_L = 12288;   // 1 CTA / SM
 constexpr int GL_THREADS = 1024;
-constexpr int HASH_TS_S = 8192, HASH_TS_L = 16384;       // hash-table slots (table = 1.25 n + 64 slots, 12 bytes each)
-constexpr int HASH_TS_T = 5120, SM_CAP_T = 4044;         // small units: 69 KB per CTA, 3 CTAs / SM
+// k_merge_tier instantiations (merge.cuh): {threads, table slots, super-k-mers, payload words, landing buffers}
+//   A  ~73 KB  3 CTAs / SM   typical units of a bacterial-size build (C2: ~4 k records, ~400 super-k-mers, ~1.2 k keys)
+//   B  ~112 KB 2 CTAs / SM
+//   C  ~221 KB 1 CTA  / SM   units of up to ~25 k records at 30x coverage (C2-sized slices on 8 GPUs: 16 k records)
+constexpr int HASH_TS_S = 8192;                       // k_merge_parts: table slots of one key partition
+#define TIER_A 512, 3072, 512, 2048, 2
+#define TIER_A256 256, 3072, 512, 2048, 2
+#define TIER_B 512, 5632, 1408, 4608, 1
+#define TIER_C 1024, 11776, 2560, 8192, 1
+struct TierCap { uint32_t ts, skcap, pwcap; };
+constexpr TierCap kTierCaps[3] = {{3072, 512, 2048}, {5632, 1408, 4608}, {11776, 2560, 8192}};
 
 // A bucket range may be merged in several parts that append to one final table (merge_range_parts): `eb` = entries
 // already in the table, `ub` = units already in unit_final_off, `cap_total` = final-buffer capacity for the whole range.
@@ -444,13 +462,15 @@ int32_t merge_range_device(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_
     if (c->wide_mode >= 0) return merge_range_device_wide(c, first_bucket, n_buckets, n_entries, unique, total, pb);
     const uint32_t u0 = first_bucket << P.b2, nu = n_buckets << P.b2;
     const bool hash_mode = c->merge_mode == 1;
-    // ---- classify units by record count
-    //   work[0]  <= 6144 records : 512-thread CTA, shared table          work[1]  <= 12288 : 1024-thread CTA
-    //   big      <= PART_MAXP * PART_TARGET : key partitions in HBM, one shared-table CTA per partition
-    //   work[2]  giant units (and every large unit in sort mode) : table / sort buffers in a global scratch slice
-    std::vector<uint32_t> work[3], work_t;
+    // ---- classify units
+    //   tier[0..2]  units that fit one staging round of k_merge_tier (super-k-mers, payload words, expected distinct keys)
+    //   big         <= PART_MAXP * part_target records: key partitions in HBM, one shared-table CTA per partition
+    //   work[2]     giant units (and every large unit in sort mode): table / sort buffers in a global scratch slice
+    //   sort mode (GGCAT_B200_MERGE=sort): work[0] <= 6144 records, work[1] <= 12288
+    std::vector<uint32_t> work[3], tier[3];
     std::vector<std::pair<uint64_t, uint32_t>> large, big;  // (records, unit)
     std::vector<uint64_t> unit_n(nu, 0);
+    std::vector<uint32_t> unit_sk(nu, 0), unit_w(nu, 0), unit_sl(nu, 0);
     // key partitions are sized by the distinct keys they should hold (~2048 = a quarter of the 8192-slot table), from the
     // distinct/records ratio of the parts merged so far with a 2x margin; k_merge_parts splits a partition that
     // turns out fuller than that.  Unknown ratio (first part of a context): 4096 records, the table's guaranteed capacity.
@@ -460,18 +480,33 @@ int32_t merge_range_device(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_
         part_target = (uint32_t)std::min<double>(65536.0, std::max<double>(PART_TARGET, 2048.0 / std::max(r, 1e-3)));
     }
     const uint32_t part_cap = part_target + part_target / 2;
-    uint64_t tot_kmers = 0;
+    // table slots per k-mer record of the tier kernel: expected distinct keys (15 % margin) at a load of 0.75
+    const double slots_per_rec = std::min(1.0, 1.15 * c->distinct_ratio) / 0.75;
+    const uint32_t slots_q16 = (uint32_t)(slots_per_rec * 65536.0 + 1.0);
+    for (Chunk *ch : c->chunks) {
+        const uint32_t lo = std::max(u0, ch->first_unit), hi = std::min(u0 + nu, ch->first_unit + ch->n_units);
+        for (uint32_t u = lo; u < hi; u++) {
+            const uint32_t q = u - ch->first_unit, sk = ch->h_cnt[q];
+            if (!sk) continue;
+            unit_n[u - u0] += ch->h_kmers[q]; unit_sk[u - u0] += sk; unit_w[u - u0] += ch->h_words[q]; unit_sl[u - u0] += 1;
+        }
+    }
+    const bool tiers_ok = hash_mode && c->chunks.size() <= (size_t)TIER_MAXSL && !c->no_tiers;
+    uint64_t tot_kmers = 0, tier_nmax = 0;
     for (uint32_t u = u0; u < u0 + nu; u++) {
-        uint64_t n = 0;
-        for (Chunk *ch : c->chunks)
-            if (u >= ch->first_unit && u < ch->first_unit + ch->n_units) n += ch->h_kmers[u - ch->first_unit];
-        unit_n[u - u0] = n;
+        const uint64_t n = unit_n[u - u0];
         if (n == 0) continue;
         if (n >= (1ull << 31)) return set_err(GGCAT_B200_ERR_INVALID, "unit %u holds %llu k-mers (> 2^31)", u, (unsigned long long)n);
         tot_kmers += n;
-        if (hash_mode && n <= SM_CAP_T) work_t.push_back(u);
-        else if (n <= SM_CAP_S) work[0].push_back(u);
-        else if (n <= SM_CAP_L) work[1].push_back(u);
+        int t = -1;
+        if (tiers_ok && n < (1u << 24)) {
+            const uint64_t need_ts = ((n * slots_q16) >> 16) + 32, need_w = (uint64_t)unit_w[u - u0] + 6ull * unit_sl[u - u0];
+            for (int q = 0; q < 3 && t < 0; q++)
+                if (unit_sk[u - u0] <= kTierCaps[q].skcap && need_w <= kTierCaps[q].pwcap && need_ts <= kTierCaps[q].ts) t = q;
+        }
+        if (t >= 0) { tier[t].push_back(u); tier_nmax = std::max(tier_nmax, n); }
+        else if (!hash_mode && n <= SM_CAP_S) work[0].push_back(u);
+        else if (!hash_mode && n <= SM_CAP_L) work[1].push_back(u);
         else if (hash_mode && n <= (uint64_t)PART_MAXP * part_target && !c->no_partition) big.push_back({n, u});
         else large.push_back({n, u});
     }
@@ -509,13 +544,14 @@ int32_t merge_range_device(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_
     std::vector<ChunkView> views;
     for (Chunk *ch : c->chunks) {
         ChunkView v;
-        v.desc = ch->d_desc; v.payload = ch->d_payload; v.unit_off = ch->d_unit_off; v.unit_kmers = ch->d_unit_kmers;
+        v.desc = ch->d_desc; v.payload = ch->d_payload; v.unit_off = ch->d_unit_off; v.unit_woff = ch->d_unit_woff; v.unit_kmers = ch->d_unit_kmers;
         v.first_unit = ch->first_unit; v.n_units = ch->n_units; v.word_bias = ch->word_bias; v.pad = 0;
         views.push_back(v);
     }
     auto al16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
-    const size_t off_views = 0, off_wt = al16(off_views + std::max<size_t>(1, views.size()) * sizeof(ChunkView));
-    const size_t off_w0 = al16(off_wt + work_t.size() * 4), off_w1 = al16(off_w0 + work[0].size() * 4);
+    const size_t off_views = 0, off_t0 = al16(off_views + std::max<size_t>(1, views.size()) * sizeof(ChunkView));
+    const size_t off_t1 = al16(off_t0 + tier[0].size() * 4), off_t2 = al16(off_t1 + tier[1].size() * 4);
+    const size_t off_w0 = al16(off_t2 + tier[2].size() * 4), off_w1 = al16(off_w0 + work[0].size() * 4);
     const size_t off_w2 = al16(off_w1 + work[1].size() * 4), off_un = al16(off_w2 + work[2].size() * 4);
     const size_t off_so = al16(off_un + (size_t)nu * 4), stage_bytes = al16(off_so + ((size_t)nu + 1) * 8);
     TRY(pinned_reserve(&c->h_mstage, &c->h_mstage_cap, stage_bytes));
@@ -523,7 +559,8 @@ int32_t merge_range_device(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_
     {
         uint8_t *h = c->h_mstage;
         if (!views.empty()) memcpy(h + off_views, views.data(), views.size() * sizeof(ChunkView));
-        if (!work_t.empty()) memcpy(h + off_wt, work_t.data(), work_t.size() * 4);
+        for (int q = 0; q < 3; q++)
+            if (!tier[q].empty()) memcpy(h + (q == 0 ? off_t0 : q == 1 ? off_t1 : off_t2), tier[q].data(), tier[q].size() * 4);
         for (int q = 0; q < 3; q++)
             if (!work[q].empty()) memcpy(h + (q == 0 ? off_w0 : q == 1 ? off_w1 : off_w2), work[q].data(), work[q].size() * 4);
         uint32_t *un = reinterpret_cast<uint32_t *>(h + off_un);
@@ -534,7 +571,8 @@ int32_t merge_range_device(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_
         CU(cudaMemcpyAsync(c->d_mstage.p, h, stage_bytes, cudaMemcpyHostToDevice, st));
     }
     uint8_t *dm = c->d_mstage.as<uint8_t>();
-    const uint32_t *d_work_t = reinterpret_cast<const uint32_t *>(dm + off_wt);
+    const uint32_t *d_tier[3] = {reinterpret_cast<const uint32_t *>(dm + off_t0), reinterpret_cast<const uint32_t *>(dm + off_t1),
+                                 reinterpret_cast<const uint32_t *>(dm + off_t2)};
     const uint32_t *d_w[3] = {reinterpret_cast<const uint32_t *>(dm + off_w0), reinterpret_cast<const uint32_t *>(dm + off_w1),
                               reinterpret_cast<const uint32_t *>(dm + off_w2)};
     uint32_t *d_big_unit = nullptr, *d_big_logp = nullptr, *d_big_pbase = nullptr, *d_big_ovf = nullptr, *d_part_big = nullptr,
@@ -564,7 +602,10 @@ int32_t merge_range_device(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_
     CU(c->cursor.reserve(64)); CU(c->overflow.reserve(16));
     CU(c->d_retry.reserve(((size_t)nu + 2) * 4));  // [0] = count, [1..] = unit ids
     uint32_t *retry3_cnt = c->d_retry.as<uint32_t>(), *retry3 = retry3_cnt + 1;   // big units with an overflowed partition
-    if (!big.empty()) tiers.push_back(make_tier(retry3, big.size(), retry3_cnt, big[0].first));
+    // units that come back: big units with an overflowed partition, tier units whose table filled up
+    const size_t n_tier_units = tier[0].size() + tier[1].size() + tier[2].size();
+    if (!big.empty() || n_tier_units)
+        tiers.push_back(make_tier(retry3, big.size() + n_tier_units, retry3_cnt, std::max<uint64_t>(big.empty() ? 0 : big[0].first, tier_nmax)));
     for (const Tier &tr : tiers) scratch_u64 = std::max(scratch_u64, tr.per_cta * tr.grid);
     CU(c->d_scratch.reserve(scratch_u64 * 8));
     CU(cudaMemsetAsync(retry3_cnt, 0, 4, st));
@@ -585,33 +626,21 @@ int32_t merge_range_device(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_
     const uint32_t nch = (uint32_t)views.size();
     const uint32_t ms = c->params.min_multiplicity;
     if (hash_mode) {
-        if (!work_t.empty()) {
+        // work counters of the three tier launches live behind the statistics in `cursor` (zeroed above)
+        uint32_t *wc = reinterpret_cast<uint32_t *>(c->cursor.as<unsigned long long>() + 4);
+        auto launch_tier = [&](auto kern, size_t smem, int threads, int ctas_per_sm, int q) -> int32_t {
+            if (tier[q].empty()) return 0;
             LaunchTimer t(c, F_MERGE_HASH);
-            auto kern = k_merge_hash<SM_THREADS_S, HASH_TS_T>;
-            const size_t smem = merge_hash_smem_bytes<SM_THREADS_S, HASH_TS_T>();
             CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            const unsigned grid = (unsigned)std::min<size_t>(work_t.size(), (size_t)c->sm_count * 3 * 8);
-            kern<<<grid, SM_THREADS_S, smem, st>>>(dv, nch, d_work_t, (uint32_t)work_t.size(), u0, P, ms, out,
-                                                   d_unit_n, nullptr, 0, nullptr);
-        }
-        if (!work[0].empty()) {
-            LaunchTimer t(c, F_MERGE_HASH);
-            auto kern = k_merge_hash<SM_THREADS_S, HASH_TS_S>;
-            const size_t smem = merge_hash_smem_bytes<SM_THREADS_S, HASH_TS_S>();
-            CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            const unsigned grid = (unsigned)std::min<size_t>(work[0].size(), (size_t)c->sm_count * 2 * 8);
-            kern<<<grid, SM_THREADS_S, smem, st>>>(dv, nch, d_w[0], (uint32_t)work[0].size(), u0, P, ms, out,
-                                                   d_unit_n, nullptr, 0, nullptr);
-        }
-        if (!work[1].empty()) {
-            LaunchTimer t(c, F_MERGE_HASH);
-            auto kern = k_merge_hash<SM_THREADS_L, HASH_TS_L>;
-            const size_t smem = merge_hash_smem_bytes<SM_THREADS_L, HASH_TS_L>();
-            CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            const unsigned grid = (unsigned)std::min<size_t>(work[1].size(), (size_t)c->sm_count * 8);
-            kern<<<grid, SM_THREADS_L, smem, st>>>(dv, nch, d_w[1], (uint32_t)work[1].size(), u0, P, ms, out,
-                                                   d_unit_n, nullptr, 0, nullptr);
-        }
+            const unsigned grid = (unsigned)std::min<size_t>(tier[q].size(), (size_t)c->sm_count * ctas_per_sm);
+            kern<<<grid, threads, smem, st>>>(dv, nch, d_tier[q], (uint32_t)tier[q].size(), u0, P, ms, out, d_unit_n, slots_q16,
+                                              wc + q, retry3, retry3_cnt);
+            return 0;
+        };
+        if (c->tier_a_threads == 256) TRY(launch_tier(k_merge_tier<TIER_A256>, TierSmem<TIER_A256>::bytes, 256, 3, 0));
+        else TRY(launch_tier(k_merge_tier<TIER_A>, TierSmem<TIER_A>::bytes, 512, 3, 0));
+        TRY(launch_tier(k_merge_tier<TIER_B>, TierSmem<TIER_B>::bytes, 512, 2, 1));
+        TRY(launch_tier(k_merge_tier<TIER_C>, TierSmem<TIER_C>::bytes, 1024, 1, 2));
         if (!big.empty()) {
             {
                 LaunchTimer t(c, F_PARTITION);
@@ -631,7 +660,6 @@ int32_t merge_range_device(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_
                 kern<<<grid, SM_THREADS_S, smem, st>>>(n_parts, u0, ms, out, ps);
             }
         }
-        work[0].clear(); work[1].clear();
     }
     if (!work[0].empty()) {
         LaunchTimer t(c, F_MERGE_SMEM);
@@ -869,7 +897,7 @@ int32_t merge_range_device_wide(ggcat_b200_ctx *c, uint32_t first_bucket, uint32
     std::vector<ChunkView> views;
     for (Chunk *ch : c->chunks) {
         ChunkView v;
-        v.desc = ch->d_desc; v.payload = ch->d_payload; v.unit_off = ch->d_unit_off; v.unit_kmers = ch->d_unit_kmers;
+        v.desc = ch->d_desc; v.payload = ch->d_payload; v.unit_off = ch->d_unit_off; v.unit_woff = ch->d_unit_woff; v.unit_kmers = ch->d_unit_kmers;
         v.first_unit = ch->first_unit; v.n_units = ch->n_units; v.word_bias = ch->word_bias; v.pad = 0;
         views.push_back(v);
     }
@@ -1079,6 +1107,8 @@ int32_t ggcat_b200_create(const ggcat_b200_params *params, ggcat_b200_ctx **out)
         c->rk.pos_fwd = c->d_rkpos.as<K128>(); c->rk.pos_bkw = c->d_rkpos.as<K128>() + 256;
     }
     if (const char *np = getenv("GGCAT_B200_NO_PARTITION")) c->no_partition = atoi(np) != 0;
+    if (const char *nt = getenv("GGCAT_B200_NO_TIERS")) c->no_tiers = atoi(nt) != 0;
+    if (const char *ta = getenv("GGCAT_B200_TIER_A_THREADS")) c->tier_a_threads = atoi(ta) == 256 ? 256 : 512;
     if (const char *pt = getenv("GGCAT_B200_PART_TARGET")) c->part_fixed = strcmp(pt, "fixed") == 0;
     if (const char *dr = getenv("GGCAT_B200_DISTINCT_RATIO")) { const double v = atof(dr); if (v > 0) c->distinct_ratio = v; }  // tests: pretend a ratio
     if (const char *mm = getenv("GGCAT_B200_MERGE")) c->merge_mode = (strcmp(mm, "sort") == 0) ? 0 : 1;
@@ -1108,7 +1138,7 @@ int32_t ggcat_b200_reset(ggcat_b200_ctx *c) {
     cudaStreamSynchronize(c->stream);
     for (Chunk *ch : c->chunks) {
         if (!ch->imported) c->chunk_pool.push_back(ch);  // keep the device buffers for the next build
-        else { ch->unit_off.release(); delete ch; }
+        else { ch->release(); delete ch; }
     }
     c->chunks.clear();
     c->finished = false;
@@ -1124,7 +1154,7 @@ void ggcat_b200_destroy(ggcat_b200_ctx *c) {
     c->chunk_pool.clear();
     collect_timings(c);
     for (DevBuf *b : {&c->d_ascii, &c->d_offsets, &c->d_colors, &c->pk, &c->bad, &c->brk, &c->ent, &c->tile_cnt, &c->tile_sbase,
-                      &c->tmp, &c->tmp_color, &c->cur_cnt, &c->cur_words, &c->totals, &c->d_views, &c->d_work[0], &c->d_work[1],
+                      &c->tmp, &c->tmp_color, &c->cur_cnt, &c->totals, &c->d_views, &c->d_work[0], &c->d_work[1],
                       &c->d_work[2], &c->d_scratch, &c->out_keys, &c->out_cf, &c->out_keys2, &c->out_cf2,
                       &c->d_rkpos, &c->d_recfl, &c->d_mstage, &c->d_static_off, &c->cursor, &c->unit_out_off, &c->unit_out_cnt, &c->unit_final_off, &c->overflow, &c->d_retry,
                       &c->d_partmeta, &c->d_recs, &c->fin_tmp_keys, &c->fin_tmp_cf,
@@ -1531,12 +1561,15 @@ int32_t ggcat_b200_import_chunk_slice(ggcat_b200_ctx *c, uint32_t first_unit, ui
     ch->d_desc = reinterpret_cast<const uint4 *>(s->d_descriptors); ch->d_payload = s->d_payload;
     ch->d_unit_cnt = s->d_unit_counts; ch->d_unit_words = s->d_unit_words; ch->d_unit_kmers = s->d_unit_kmers;
     cudaError_t e = ch->unit_off.reserve(((size_t)n_units + 2) * 4);
-    if (e != cudaSuccess) { delete ch; return set_err(GGCAT_B200_ERR_CUDA, "cudaMalloc: %s", cudaGetErrorString(e)); }
-    CU(c->totals.reserve(8 * 8));
+    if (e == cudaSuccess) e = ch->unit_woff.reserve(((size_t)n_units + 2) * 4);
+    if (e == cudaSuccess) e = c->totals.reserve(8 * 8);
+    if (e != cudaSuccess) { ch->release(); delete ch; return set_err(GGCAT_B200_ERR_CUDA, "cudaMalloc: %s", cudaGetErrorString(e)); }
     k_exclusive_scan_u32<<<1, 1024, 0, c->stream>>>(s->d_unit_counts, ch->unit_off.as<uint32_t>(), n_units,
                                                      c->totals.as<unsigned long long>() + 3);
+    k_exclusive_scan_u32<<<1, 1024, 0, c->stream>>>(s->d_unit_words, ch->unit_woff.as<uint32_t>(), n_units,
+                                                     c->totals.as<unsigned long long>() + 4);
     ch->d_unit_off = ch->unit_off.as<uint32_t>();
-    c->chunks.push_back(ch);
+    ch->d_unit_woff = ch->unit_woff.as<uint32_t>();   // relative to the slice's payload pointer
     if (s->h_unit_counts && s->h_unit_words && s->h_unit_kmers) {
         // host copies supplied by the transport: no device read-back, no synchronisation
         const size_t nu = n_units;
@@ -1551,10 +1584,16 @@ int32_t ggcat_b200_import_chunk_slice(ggcat_b200_ctx *c, uint32_t first_unit, ui
         }
         ch->h_off[nu] = (uint32_t)a; ch->h_woff[nu] = (uint32_t)b;
         ch->n_sk = a; ch->n_words = b; ch->n_kmers = km;
-        if (a != s->n_superkmers) return set_err(GGCAT_B200_ERR_INVALID, "import: unit counts sum to %llu, slice holds %llu super-k-mers", (unsigned long long)a, (unsigned long long)s->n_superkmers);
+        if (a != s->n_superkmers) {
+            ch->release(); delete ch;
+            return set_err(GGCAT_B200_ERR_INVALID, "import: unit counts sum to %llu, slice holds %llu super-k-mers", (unsigned long long)a, (unsigned long long)s->n_superkmers);
+        }
+        c->chunks.push_back(ch);
         return 0;
     }
-    TRY(mirror_chunk(c, ch));
+    const int32_t rc = mirror_chunk(c, ch);
+    if (rc) { ch->release(); delete ch; return rc; }
+    c->chunks.push_back(ch);   // registered only once nothing can fail any more
     // imported payload pointer already addresses the slice: word offsets inside it are (woff - word_bias)
     return 0;
 }
@@ -1672,7 +1711,7 @@ int32_t ggcat_b200_peer_exchange(ggcat_b200_ctx *c) {
         if (d == me) continue;
         const uint32_t fu = first_unit_of(d), nu = first_unit_of(d + 1) - fu;
         const uint32_t slot = (d + W - me - 1) % W;   // 0 .. W-2: the grid of k_peer_push is split over the destinations
-        const uint64_t s_meta = align16(3ull * nu * 4), s_uoff = align16(((uint64_t)nu + 2) * 4);
+        const uint64_t s_meta = align16(3ull * nu * 4), s_uoff = 2 * align16(((uint64_t)nu + 2) * 4);   // descriptor + word offsets
         uint8_t *hs = ps.h_stage + (size_t)d * tbl;
         memset(hs, 0, tbl);
         RegionHdr *rh = reinterpret_cast<RegionHdr *>(hs);
@@ -1720,7 +1759,7 @@ int32_t ggcat_b200_peer_exchange(ggcat_b200_ctx *c) {
     }
     // ---- receive: headers, slice tables and per-unit counts of every source, one read-back in the common case
     const uint32_t my_fu = first_unit_of(me), my_nu = first_unit_of(me + 1) - my_fu;
-    const uint64_t s_meta = align16(3ull * my_nu * 4), s_uoff = align16(((uint64_t)my_nu + 2) * 4);
+    const uint64_t s_meta = align16(3ull * my_nu * 4), s_uoff = 2 * align16(((uint64_t)my_nu + 2) * 4);
     uint32_t guess = std::max<uint32_t>(nsl, 1);
     for (int attempt = 0; attempt < 2; attempt++) {
         const size_t stride = (size_t)(PEER_META_OFF + (uint64_t)guess * s_meta);
@@ -1769,8 +1808,10 @@ int32_t ggcat_b200_peer_exchange(ggcat_b200_ctx *c) {
             const uint32_t *dm = reinterpret_cast<const uint32_t *>(reg + PEER_META_OFF + (uint64_t)j * s_meta);
             ch->d_unit_cnt = dm; ch->d_unit_words = dm + my_nu; ch->d_unit_kmers = dm + 2 * (size_t)my_nu;
             uint32_t *uoff = reinterpret_cast<uint32_t *>(reg + PEER_META_OFF + (uint64_t)rh->n_slices * s_meta + (uint64_t)j * s_uoff);
+            uint32_t *uwoff = uoff + (s_uoff / 8);
             k_exclusive_scan_u32<<<1, 1024, 0, st>>>(dm, uoff, my_nu, c->totals.as<unsigned long long>() + 3);
-            ch->d_unit_off = uoff;
+            k_exclusive_scan_u32<<<1, 1024, 0, st>>>(dm + my_nu, uwoff, my_nu, c->totals.as<unsigned long long>() + 4);
+            ch->d_unit_off = uoff; ch->d_unit_woff = uwoff;
             const uint32_t *hm = reinterpret_cast<const uint32_t *>(hr + PEER_META_OFF + (uint64_t)j * s_meta);
             const size_t nu = my_nu;
             ch->h_cnt.assign(hm, hm + nu); ch->h_cnt.push_back(0);
@@ -1785,10 +1826,12 @@ int32_t ggcat_b200_peer_exchange(ggcat_b200_ctx *c) {
             ch->h_off[nu] = (uint32_t)a; ch->h_woff[nu] = (uint32_t)b;
             ch->n_sk = a; ch->n_words = b; ch->n_kmers = km;
             ps.last_received += a * 16 + b * 4 + 3ull * nu * 4;
-            c->chunks.push_back(ch);
-            if (a != tb[j].n_sk || b != tb[j].n_words)
+            if (a != tb[j].n_sk || b != tb[j].n_words) {
+                delete ch;
                 return set_err(GGCAT_B200_ERR_INVALID, "peer_exchange: slice %u of rank %u: unit counts sum to %llu super-k-mers / %llu words, header says %llu / %llu",
                                j, s, (unsigned long long)a, (unsigned long long)b, (unsigned long long)tb[j].n_sk, (unsigned long long)tb[j].n_words);
+            }
+            c->chunks.push_back(ch);
         }
     }
     CU(cudaGetLastError());

@@ -5,6 +5,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <cstdio>
 
 namespace ggb {
 
@@ -81,13 +82,28 @@ __device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gmem_src
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_addr(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
 }
+// Orders earlier generic-proxy accesses of shared memory (plain ld/st by the CTA's threads, made visible to the issuing
+// thread by a barrier) before later async-proxy writes (a bulk copy that reuses the same buffer).
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase) {
     const uint32_t addr = smem_addr(bar);
     uint32_t done;
-    do {
+    unsigned long long t0 = 0;
+    for (uint32_t spins = 0;; ++spins) {
         asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
                      : "=r"(done) : "r"(addr), "r"(phase) : "memory");
-    } while (!done);
+        if (done) break;
+        // a bulk copy that never lands (bad descriptor, wrong byte count) must not hang the device: trap after ~5 s
+        if ((spins & 0xFFFu) == 0xFFFu) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            if (t0 == 0) t0 = t;
+            else if (t - t0 > 5000000000ull) {
+                printf("ggcat_b200: mbarrier wait timed out (block %u thread %u parity %u)\n", blockIdx.x, threadIdx.x, phase);
+                __trap();
+            }
+        }
+    }
 }
 
 // ---- block-wide helpers -------------------------------------------------------------------------

@@ -21,6 +21,7 @@ struct ChunkView {
     const uint4 *desc;           // descriptors, unit-sorted
     const uint32_t *payload;     // packed bases
     const uint32_t *unit_off;    // [n_units + 1] descriptor offsets, relative to `desc`
+    const uint32_t *unit_woff;   // [n_units + 1] payload word offsets, relative to `payload` (a unit's words are contiguous)
     const uint32_t *unit_kmers;  // [n_units]
     uint32_t first_unit;         // units [first_unit, first_unit + n_units) are present
     uint32_t n_units;
@@ -319,7 +320,19 @@ __device__ __forceinline__ void hash_insert(uint64_t *K, uint32_t *C, uint32_t T
         }
         slot = slot + 1 == TS ? 0u : slot + 1;
     }
-    if (!claimed) atomicAdd(&C[slot], 1u);
+    if (!claimed) {
+        // The counter SATURATES at 2^30 - 1 occurrences (the reference's counter is 61-bit, map_entry.rs:5-10; -s only
+        // needs "at least"): far below the limit a plain atomicAdd (at most ~10^5 threads race, the margin is 2^20);
+        // close to it a CAS loop that never carries into the flag bits.  Only giant units get here.
+        uint32_t cur = *reinterpret_cast<volatile uint32_t *>(&C[slot]);
+        if ((cur & 0x3FFFFFFFu) < 0x3FF00000u) atomicAdd(&C[slot], 1u);
+        else
+            while ((cur & 0x3FFFFFFFu) < 0x3FFFFFFEu) {
+                const uint32_t old = atomicCAS(&C[slot], cur, cur + 1u);
+                if (old == cur) break;
+                cur = old;
+            }
+    }
     if (fb && ((*reinterpret_cast<volatile uint32_t *>(&C[slot]) >> 30) & fb) != fb) atomicOr(&C[slot], fb << 30);
 }
 __device__ __forceinline__ uint32_t slot_count(uint32_t cc) { return (cc & 0x3FFFFFFFu) + 1u; }   // occurrences of an occupied slot
@@ -519,14 +532,8 @@ k_merge_hash(const ChunkView *__restrict__ chunks, uint32_t n_chunks, const uint
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_merge_parts: one CTA per key partition of a big unit (records written by k_partition_units).
-// Partitions are sized by the DISTINCT keys they are expected to hold, not by their records (at 30x coverage a
-// partition of 60 k records has ~2.5 k distinct k-mers): fewer, larger partitions mean a smaller scatter fan-out in
-// k_partition_units and fewer table clears / scans per record here.  The expectation comes from the parts already
-// merged, so it can be wrong: inserts probe a bounded number of slots, and when the table turns out to be full the CTA
-// splits the partition's KEY SPACE four ways by an independent hash and counts each quarter on its own (work stack in
-// shared memory, records re-read from HBM/L2).  Survivors of every successful pass are appended to the unit's output
-// region (unit_out_cnt is the fill counter), in table order; k_finish_* orders the unit.
+// hash_insert_bounded: hash_insert that gives up after `limit` probes (table sized from an ESTIMATE of the distinct
+// keys: the caller re-routes the unit / splits the key space when the estimate was too low).
 __device__ __forceinline__ bool hash_insert_bounded(uint64_t *K, uint32_t *C, uint32_t TS, uint64_t key, uint32_t fb, uint32_t limit) {
     uint32_t slot = hash_slot(key, TS);
     bool claimed = false;
@@ -545,6 +552,287 @@ __device__ __forceinline__ bool hash_insert_bounded(uint64_t *K, uint32_t *C, ui
     if (fb && ((*reinterpret_cast<volatile uint32_t *>(&C[slot]) >> 30) & fb) != fb) atomicOr(&C[slot], fb << 30);
     return true;
 }
+
+// ------------------------------------------------------------------------------------------------
+// k_merge_tier: the shared-table merge of every unit that fits one staging round -- the kernel that counts almost all
+// k-mers of a build (C2: all units; human-scale inputs: whatever is not a "big" unit).
+//
+//   * PERSISTENT CTAs pull units from a device-side work counter (dynamic balance, no tail of idle CTAs).
+//   * A unit-sorted chunk keeps a unit's descriptors AND its payload words contiguous, so staging a unit is two 1-D bulk
+//     copies per chunk slice (cp.async.bulk -> UBLKCP, completion on an mbarrier).  Warp 0 arms the copies of the NEXT
+//     unit before the CTA touches the current one (NBUF = 2: second landing buffer; NBUF = 1: issued when the inserts of
+//     the current unit are done, so they overlap the table scan), which hides the descriptor / payload latency that the
+//     first version of this kernel paid at the start of every unit (ncu: 12.6 % of its stall samples on that load).
+//   * All bit extraction reads shared memory: descriptors are rewritten in place to {first record, payload word, len|flags}.
+//   * The table is sized from the DISTINCT keys the unit is expected to hold (slots_q16 = slots per k-mer record, from the
+//     distinct/records ratio of what this context merged before), not from its records: at 30x coverage a unit of 16 k
+//     records holds ~5 k keys.  Inserts probe a bounded number of slots; a unit whose table fills goes to the retry list
+//     (global-table kernel).  Scanning the table resets it for the next unit (no separate clear pass).
+//   * Barriers per unit: 1 (prefix scan of the k-mer counts) + 3, against 7 + 3 per staging round before.
+// Semantics per record: hashmap.rs:385-399 / map_entry.rs:33-84, as k_merge_hash.
+constexpr int TIER_MAXSL = 32;             // chunk slices of one unit (one lane of warp 0 each)
+constexpr uint32_t TIER_PROBE_LIMIT = 128;
+constexpr uint32_t TIER_DONE = 0xFFFFFFFFu;
+
+template <int THREADS, int TS, int SKCAP, int PWCAP, int NBUF>
+struct TierSmem {
+    static constexpr size_t k_off = 0;
+    static constexpr size_t c_off = k_off + (size_t)TS * 8;
+    static constexpr size_t sk_off = c_off + (size_t)TS * 4;                              // NBUF x SKCAP uint4 (TMA landing, then staged records)
+    static constexpr size_t pay_off = sk_off + (size_t)NBUF * SKCAP * 16;                 // NBUF x (PWCAP + 8) u32 (TMA landing)
+    static constexpr size_t start_off = pay_off + (size_t)NBUF * (PWCAP + 8) * 4;         // NBUF x SKCAP u32: first record of a super-k-mer
+    static constexpr size_t bar_off = start_off + (size_t)NBUF * SKCAP * 4;               // NBUF mbarriers
+    static constexpr size_t meta_off = bar_off + (size_t)NBUF * 8;                        // NBUF x {unit, n_sk, -, -}
+    static constexpr size_t dstart_off = meta_off + (size_t)NBUF * 16;                    // NBUF x (MAXSL + 1): first staged descriptor of a slice
+    static constexpr size_t delta_off = dstart_off + (size_t)NBUF * (TIER_MAXSL + 1) * 4; // NBUF x MAXSL: staged payload word = descriptor word + delta
+    static constexpr size_t scan_off = delta_off + (size_t)NBUF * TIER_MAXSL * 4;         // 34 u32
+    static constexpr size_t cnt_off = scan_off + 34 * 4;                                  // 4 u32
+    static constexpr size_t bytes = ((cnt_off + 4 * 4 + 15) / 16) * 16;
+    static_assert((size_t)TS % 4 == 0 && PWCAP % 4 == 0 && SKCAP % 4 == 0, "bulk-copy destinations must be 16-byte aligned");
+};
+
+// Exclusive block scan with ONE barrier: every warp re-scans the WARPS partial sums itself.
+template <int THREADS>
+__device__ __forceinline__ uint32_t block_scan1(uint32_t v, uint32_t *s_w, uint32_t *total) {
+    constexpr int WARPS = THREADS / 32;
+    const uint32_t lane = lane_id(), warp = warp_id();
+    uint32_t x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= (uint32_t)o) x += y; }
+    if (lane == 31) s_w[warp] = x;
+    __syncthreads();
+    const uint32_t w = lane < (uint32_t)WARPS ? s_w[lane] : 0u;
+    uint32_t s = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, s, o); if (lane >= (uint32_t)o) s += y; }
+    const uint32_t base = __shfl_sync(0xffffffffu, s - w, warp);
+    *total = __shfl_sync(0xffffffffu, s, WARPS - 1);
+    return base + x - v;
+}
+
+// Warp 0: take the next unit from the work counter and arm the bulk copies of its slices into one landing buffer.
+__device__ __forceinline__ void tier_prefetch(const ChunkView *__restrict__ chunks, uint32_t n_chunks, const uint32_t *__restrict__ work,
+                                              uint32_t n_work, uint32_t *__restrict__ work_counter, uint4 *sk, uint32_t *pay,
+                                              uint64_t *bar, uint32_t *meta, uint32_t *sl_dstart, uint32_t *sl_delta) {
+    const uint32_t lane = lane_id();
+    uint32_t wi = 0;
+    if (lane == 0) wi = atomicAdd(work_counter, 1u);
+    wi = __shfl_sync(0xffffffffu, wi, 0);
+    if (wi >= n_work) { if (lane == 0) meta[0] = TIER_DONE; return; }
+    const uint32_t unit = work[wi];
+    uint32_t cnt = 0, nw = 0, lead = 0, w0 = 0, d0 = 0, bias = 0;
+    const uint4 *desc = nullptr;
+    const uint32_t *src = nullptr;
+    if (lane < n_chunks) {
+        const ChunkView &cv = chunks[lane];
+        if (unit >= cv.first_unit && unit < cv.first_unit + cv.n_units) {
+            const uint32_t u = unit - cv.first_unit;
+            d0 = cv.unit_off[u]; cnt = cv.unit_off[u + 1] - d0;
+            w0 = cv.unit_woff[u]; nw = cv.unit_woff[u + 1] - w0;
+            src = cv.payload + w0;
+            lead = (uint32_t)(((uintptr_t)src >> 2) & 3u);      // the bulk copy starts at the 16-byte boundary below
+            bias = cv.word_bias; desc = cv.desc;
+        }
+    }
+    const uint32_t cw = cnt ? ((lead + nw + 3u) & ~3u) : 0u;
+    uint32_t dx = cnt, px = cw;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t a = __shfl_up_sync(0xffffffffu, dx, o), b = __shfl_up_sync(0xffffffffu, px, o);
+        if (lane >= (uint32_t)o) { dx += a; px += b; }
+    }
+    const uint32_t dtot = __shfl_sync(0xffffffffu, dx, 31), ptot = __shfl_sync(0xffffffffu, px, 31);
+    const uint32_t dpos = dx - cnt, ppos = px - cw;
+    sl_dstart[lane] = dpos;
+    sl_delta[lane] = ppos + lead - w0 - bias;   // descriptor word (relative to its source chunk) -> staged word
+    if (lane == 31) sl_dstart[32] = dtot;
+    fence_proxy_async_smem();                   // the landing buffers were read / rewritten by plain loads and stores
+    if (lane == 0) {
+        meta[0] = unit; meta[1] = dtot;
+        mbar_expect_tx(bar, dtot * 16u + ptot * 4u);
+    }
+    __syncwarp();
+    if (cnt) {
+        tma_load_1d(sk + dpos, desc + d0, cnt * 16u, bar);
+        tma_load_1d(pay + ppos, src - lead, cw * 4u, bar);
+    }
+}
+
+template <int THREADS, int TS, int SKCAP, int PWCAP, int NBUF>
+__global__ void __launch_bounds__(THREADS)
+k_merge_tier(const ChunkView *__restrict__ chunks, uint32_t n_chunks, const uint32_t *__restrict__ work, uint32_t n_work,
+             uint32_t first_unit, DevParams P, uint32_t min_mult, MergeOut out, const uint32_t *__restrict__ unit_n,
+             uint32_t slots_q16, uint32_t *__restrict__ work_counter, uint32_t *__restrict__ retry, uint32_t *__restrict__ retry_count) {
+    using L = TierSmem<THREADS, TS, SKCAP, PWCAP, NBUF>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr uint32_t WARPS = THREADS / 32;
+    constexpr int ITEMS = (SKCAP + THREADS - 1) / THREADS;
+    uint64_t *K = reinterpret_cast<uint64_t *>(smem_raw + L::k_off);
+    uint32_t *C = reinterpret_cast<uint32_t *>(smem_raw + L::c_off);
+    uint4 *skb = reinterpret_cast<uint4 *>(smem_raw + L::sk_off);
+    uint32_t *payb = reinterpret_cast<uint32_t *>(smem_raw + L::pay_off);
+    uint32_t *startb = reinterpret_cast<uint32_t *>(smem_raw + L::start_off);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + L::bar_off);
+    uint32_t *metab = reinterpret_cast<uint32_t *>(smem_raw + L::meta_off);
+    uint32_t *dstartb = reinterpret_cast<uint32_t *>(smem_raw + L::dstart_off);
+    uint32_t *deltab = reinterpret_cast<uint32_t *>(smem_raw + L::delta_off);
+    uint32_t *s_scan = reinterpret_cast<uint32_t *>(smem_raw + L::scan_off);
+    uint32_t *s_cnt = reinterpret_cast<uint32_t *>(smem_raw + L::cnt_off);   // [0] survivors written, [1] occupied slots, [3] table full
+
+    const uint32_t tid = threadIdx.x, lane = lane_id(), warp = warp_id();
+    const uint32_t k = P.k, forward_only = P.forward_only;
+    const uint64_t kmask = (1ull << (2 * k)) - 1ull;
+    const uint32_t le_mask = 0xFFFFFFFFu >> (31u - lane);
+    auto prefetch = [&](uint32_t b) {
+        tier_prefetch(chunks, n_chunks, work, n_work, work_counter, skb + (size_t)b * SKCAP, payb + (size_t)b * (PWCAP + 8), bars + b,
+                      metab + 4 * b, dstartb + (TIER_MAXSL + 1) * b, deltab + TIER_MAXSL * b);
+    };
+    for (uint32_t i = tid; i < (uint32_t)TS; i += THREADS) { K[i] = HASH_EMPTY; C[i] = 0u; }
+    if (tid == 0) {
+        for (int b = 0; b < NBUF; b++) mbar_init(bars + b, 1);
+        s_cnt[0] = s_cnt[1] = s_cnt[2] = s_cnt[3] = 0;
+    }
+    __syncthreads();
+    if (warp == 0) prefetch(0);
+    __syncthreads();
+    for (uint32_t it = 0;; ++it) {
+        const uint32_t b = NBUF == 2 ? (it & 1u) : 0u;
+        const uint32_t unit = metab[4 * b], nsk = metab[4 * b + 1];
+        if (unit == TIER_DONE) break;
+        if (NBUF == 2 && warp == 0) prefetch(b ^ 1u);     // the other landing buffer: its unit finished before the last barrier
+        mbar_wait(bars + b, NBUF == 2 ? ((it >> 1) & 1u) : (it & 1u));
+        const uint32_t unit_rel = unit - first_unit;
+        const uint32_t n = unit_n[unit_rel];
+        uint32_t ts = (uint32_t)((((uint64_t)n * slots_q16) >> 16) + 31u) & ~31u;
+        ts = ts < 512u ? 512u : (ts > (uint32_t)TS ? (uint32_t)TS : ts);
+        uint4 *sk = skb + (size_t)b * SKCAP;
+        uint32_t *start = startb + (size_t)b * SKCAP;
+        const uint32_t *pay = payb + (size_t)b * (PWCAP + 8);
+        const uint32_t *sl_dstart = dstartb + (TIER_MAXSL + 1) * b, *sl_delta = deltab + TIER_MAXSL * b;
+        // ---- stage: raw descriptor {word, len, meta, colour} -> {first record, staged payload word, len | flags << 30}
+        uint32_t tot;
+        {
+            uint32_t pwv[ITEMS], lfv[ITEMS], cntv[ITEMS], sum = 0;
+#pragma unroll
+            for (int t = 0; t < ITEMS; t++) {
+                const uint32_t j = tid * ITEMS + t;
+                pwv[t] = lfv[t] = cntv[t] = 0;
+                if (j < nsk) {
+                    const uint4 d = sk[j];
+                    uint32_t q = 0;
+                    while (j >= sl_dstart[q + 1]) ++q;
+                    pwv[t] = d.x + sl_delta[q];
+                    lfv[t] = d.y | (((d.z >> 16) & 3u) << 30);
+                    cntv[t] = d.y - k + 1u;
+                }
+                sum += cntv[t];
+            }
+            uint32_t pre = block_scan1<THREADS>(sum, s_scan, &tot);
+#pragma unroll
+            for (int t = 0; t < ITEMS; t++) {
+                const uint32_t j = tid * ITEMS + t;
+                if (j < nsk) { sk[j] = make_uint4(pre, pwv[t], lfv[t], 0u); start[j] = pre; }
+                pre += cntv[t];
+            }
+        }
+        __syncthreads();
+        // ---- insert: every warp walks an equal, 32-aligned range of the unit's records, one record per lane
+        {
+            const uint32_t per = ((tot + WARPS * 32u - 1u) / (WARPS * 32u)) * 32u;
+            const uint32_t r_beg = warp * per, r_end = min(tot, r_beg + per);
+            if (r_beg < r_end) {
+                uint32_t lo = 0, hi = nsk - 1;                                          // last j with start[j] <= r_beg
+                while (lo < hi) {
+                    const uint32_t mid = (lo + hi + 1) >> 1;
+                    if (start[mid] <= r_beg) lo = mid; else hi = mid - 1;
+                }
+                uint32_t j = lo;                                                       // invariant: start[j] <= r0 < start[j+1]
+                for (uint32_t r0 = r_beg; r0 < r_end; r0 += 32u) {
+                    if (*reinterpret_cast<volatile uint32_t *>(&s_cnt[3])) break;      // somebody found the table full
+                    const uint32_t cand = j + 1u + lane;
+                    const uint32_t rel = (cand < nsk ? start[cand] : 0xFFFFFFFFu) - r0;  // > 0 by the invariant
+                    const uint32_t smask = __reduce_or_sync(0xffffffffu, rel < 32u ? (1u << rel) : 0u);
+                    const uint32_t owner = j + (uint32_t)__popc(smask & le_mask);
+                    const uint32_t r = r0 + lane;
+                    if (r < r_end) {
+                        const uint4 s = sk[owner];
+                        const uint32_t i = r - s.x, last = (s.z & 0x3FFFFFFFu) - k, flags = s.z >> 30;
+                        const uint64_t fw = extract64(pay + s.y, 2ull * i) & kmask;
+                        const uint64_t rc = revcomp64(fw) >> (64 - 2 * k);
+                        const bool isf = forward_only ? true : (fw < rc);
+                        const uint64_t key = isf ? fw : rc;
+                        const uint32_t bi = (!(flags & READ_FLAG_INCL_BEGIN) && i == 0) ? 1u : 0u;
+                        const uint32_t ei = (!(flags & READ_FLAG_INCL_END) && i == last) ? 1u : 0u;
+                        const uint32_t fb = (bi << (isf ? 0 : 1)) | (ei << (isf ? 1 : 0));     // hashmap.rs:385-399
+                        if (!hash_insert_bounded(K, C, ts, key, fb, TIER_PROBE_LIMIT)) s_cnt[3] = 1u;
+                    }
+                    j += (uint32_t)__popc(smask);
+                    if (j + 1u < nsk && start[j + 1u] == r0 + 32u) ++j;                // next window starts a new super-k-mer
+                }
+            }
+        }
+        __syncthreads();
+        const uint32_t full = s_cnt[3];
+        if (NBUF == 1 && warp == 0) prefetch(0);          // the landing buffer is free: the copies overlap the table scan
+        const unsigned long long gbase = out.static_off[unit_rel];
+        if (full) {
+            for (uint32_t i = tid; i < ts; i += THREADS) { K[i] = HASH_EMPTY; C[i] = 0u; }
+            if (tid == 0) retry[atomicAdd(retry_count, 1u)] = unit;
+        } else {
+            // ---- scan the table once: MapEntry -> multiplicity, -s filter, survivors to the unit's region; reset the slots
+            uint32_t my_occ = 0;
+            for (uint32_t base = 0; base < ts; base += THREADS) {
+                const uint32_t i = base + tid;
+                uint64_t kk = HASH_EMPTY;
+                uint32_t cf = 0;
+                if (i < ts) {
+                    kk = K[i];
+                    if (kk != HASH_EMPTY) {
+                        const uint32_t cc = C[i];
+                        K[i] = HASH_EMPTY; C[i] = 0u;
+                        ++my_occ;
+                        const uint32_t cnt = slot_count(cc), fl = cc >> 30;
+                        const uint32_t mult = cnt >> ((fl == (READ_FLAG_INCL_BEGIN | READ_FLAG_INCL_END)) ? 1 : 0);  // map_entry.rs:79-84
+                        if (mult >= min_mult) cf = mult | (fl << 30);
+                    }
+                }
+                const uint32_t bal = __ballot_sync(0xffffffffu, cf != 0);
+                if (bal) {
+                    uint32_t wb = 0;
+                    if (lane == 0) wb = atomicAdd(&s_cnt[0], (uint32_t)__popc(bal));
+                    wb = __shfl_sync(0xffffffffu, wb, 0);
+                    if (cf) {
+                        const unsigned long long o = gbase + wb + __popc(bal & ((1u << lane) - 1u));
+                        out.keys[o] = kk; out.count_flags[o] = cf;
+                    }
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) my_occ += __shfl_xor_sync(0xffffffffu, my_occ, o);
+            if (lane == 0 && my_occ) atomicAdd(&s_cnt[1], my_occ);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            if (!full) {
+                const uint32_t S = s_cnt[0], oslot = out.slot(unit_rel);
+                out.stats(S, s_cnt[1], tot);
+                out.unit_out_off[oslot] = gbase;
+                out.unit_out_cnt[oslot] = S;
+            }
+            s_cnt[0] = s_cnt[1] = s_cnt[3] = 0;   // next written after the next unit's staging barrier
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_merge_parts: one CTA per key partition of a big unit (records written by k_partition_units).
+// Partitions are sized by the DISTINCT keys they are expected to hold, not by their records (at 30x coverage a
+// partition of 60 k records has ~2.5 k distinct k-mers): fewer, larger partitions mean a smaller scatter fan-out in
+// k_partition_units and fewer table clears / scans per record here.  The expectation comes from the parts already
+// merged, so it can be wrong: inserts probe a bounded number of slots, and when the table turns out to be full the CTA
+// splits the partition's KEY SPACE four ways by an independent hash and counts each quarter on its own (work stack in
+// shared memory, records re-read from HBM/L2).  Survivors of every successful pass are appended to the unit's output
+// region (unit_out_cnt is the fill counter), in table order; k_finish_* orders the unit.
 __device__ __forceinline__ uint32_t sub_hash(uint64_t key) {   // independent of part_hash and hash_slot
     return (uint32_t)((key * 0xA24BAED4963EE407ull) >> 33);
 }
