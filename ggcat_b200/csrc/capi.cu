@@ -147,7 +147,7 @@ struct ggcat_b200_ctx {
     int merge_mode = 1;  // 1 = shared-memory hash table (default), 0 = LSD radix sort (GGCAT_B200_MERGE=sort)
     bool no_partition = false;  // GGCAT_B200_NO_PARTITION=1: big units use the global-scratch table (A/B switch)
     bool no_tiers = false;      // GGCAT_B200_NO_TIERS=1: every unit takes the key-partition / global-table path (tests)
-    int tier_a_threads = 512;   // GGCAT_B200_TIER_A_THREADS=256: A/B switch of the small-unit tier's CTA size
+    int tier_a_variant = 0;     // GGCAT_B200_TIER_A=1|2: A/B switch of the small-unit tier (see TIER_A1 / TIER_A256)
     int wide_mode = -1;  // -1: 64-bit key path (merge.cuh); else MODE_SEQ128 / MODE_RK128 / MODE_COLOR (merge128.cuh)
     RkTables rk;
     FinalTable fin;
@@ -396,12 +396,14 @@ constexpr int GL_THREADS = 1024;
 //   B  ~112 KB 2 CTAs / SM
 //   C  ~221 KB 1 CTA  / SM   units of up to ~25 k records at 30x coverage (C2-sized slices on 8 GPUs: 16 k records)
 constexpr int HASH_TS_S = 8192;                       // k_merge_parts: table slots of one key partition
-#define TIER_A 512, 3072, 512, 2048, 2
-#define TIER_A256 256, 3072, 512, 2048, 2
-#define TIER_B 512, 5632, 1408, 4608, 1
-#define TIER_C 1024, 11776, 2560, 8192, 1
+#define TIER_A 512, 3072, 512, 2048, 2, 3
+#define TIER_A1 512, 4096, 512, 2048, 1, 3     // A/B variant: one landing buffer, sparser table
+#define TIER_A256 256, 3072, 512, 2048, 2, 3   // A/B variant: 8 warps per unit
+#define TIER_B 512, 5632, 1408, 4608, 1, 2
+#define TIER_C 1024, 11776, 2560, 8192, 1, 1
 struct TierCap { uint32_t ts, skcap, pwcap; };
 constexpr TierCap kTierCaps[3] = {{3072, 512, 2048}, {5632, 1408, 4608}, {11776, 2560, 8192}};
+constexpr double TIER_MAX_LOAD = 0.5;   // expected distinct keys / table slots a unit may have in its tier
 
 // A bucket range may be merged in several parts that append to one final table (merge_range_parts): `eb` = entries
 // already in the table, `ub` = units already in unit_final_off, `cap_total` = final-buffer capacity for the whole range.
@@ -480,9 +482,10 @@ int32_t merge_range_device(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_
         part_target = (uint32_t)std::min<double>(65536.0, std::max<double>(PART_TARGET, 2048.0 / std::max(r, 1e-3)));
     }
     const uint32_t part_cap = part_target + part_target / 2;
-    // table slots per k-mer record of the tier kernel: expected distinct keys (15 % margin) at a load of 0.75
-    const double slots_per_rec = std::min(1.0, 1.15 * c->distinct_ratio) / 0.75;
-    const uint32_t slots_q16 = (uint32_t)(slots_per_rec * 65536.0 + 1.0);
+    // expected distinct keys per k-mer record (15 % margin): routes a unit to the smallest tier whose table stays sparse
+    const double keys_per_rec = std::min(1.0, 1.15 * c->distinct_ratio);
+    TierCap caps[3] = {kTierCaps[0], kTierCaps[1], kTierCaps[2]};
+    if (c->tier_a_variant == 1) caps[0].ts = 4096;
     for (Chunk *ch : c->chunks) {
         const uint32_t lo = std::max(u0, ch->first_unit), hi = std::min(u0 + nu, ch->first_unit + ch->n_units);
         for (uint32_t u = lo; u < hi; u++) {
@@ -500,9 +503,10 @@ int32_t merge_range_device(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_
         tot_kmers += n;
         int t = -1;
         if (tiers_ok && n < (1u << 24)) {
-            const uint64_t need_ts = ((n * slots_q16) >> 16) + 32, need_w = (uint64_t)unit_w[u - u0] + 6ull * unit_sl[u - u0];
+            const double need_keys = (double)n * keys_per_rec;
+            const uint64_t need_w = (uint64_t)unit_w[u - u0] + 6ull * unit_sl[u - u0];
             for (int q = 0; q < 3 && t < 0; q++)
-                if (unit_sk[u - u0] <= kTierCaps[q].skcap && need_w <= kTierCaps[q].pwcap && need_ts <= kTierCaps[q].ts) t = q;
+                if (unit_sk[u - u0] <= caps[q].skcap && need_w <= caps[q].pwcap && need_keys <= TIER_MAX_LOAD * caps[q].ts) t = q;
         }
         if (t >= 0) { tier[t].push_back(u); tier_nmax = std::max(tier_nmax, n); }
         else if (!hash_mode && n <= SM_CAP_S) work[0].push_back(u);
@@ -633,14 +637,14 @@ int32_t merge_range_device(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_
             LaunchTimer t(c, F_MERGE_HASH);
             CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             const unsigned grid = (unsigned)std::min<size_t>(tier[q].size(), (size_t)c->sm_count * ctas_per_sm);
-            kern<<<grid, threads, smem, st>>>(dv, nch, d_tier[q], (uint32_t)tier[q].size(), u0, P, ms, out, d_unit_n, slots_q16,
-                                              wc + q, retry3, retry3_cnt);
+            kern<<<grid, threads, smem, st>>>(dv, nch, d_tier[q], (uint32_t)tier[q].size(), u0, P, ms, out, wc + q, retry3, retry3_cnt);
             return 0;
         };
-        if (c->tier_a_threads == 256) TRY(launch_tier(k_merge_tier<TIER_A256>, TierSmem<TIER_A256>::bytes, 256, 3, 0));
-        else TRY(launch_tier(k_merge_tier<TIER_A>, TierSmem<TIER_A>::bytes, 512, 3, 0));
-        TRY(launch_tier(k_merge_tier<TIER_B>, TierSmem<TIER_B>::bytes, 512, 2, 1));
-        TRY(launch_tier(k_merge_tier<TIER_C>, TierSmem<TIER_C>::bytes, 1024, 1, 2));
+        if (c->tier_a_variant == 2) TRY(launch_tier(k_merge_tier<TIER_A256>, TierSmem<256, 3072, 512, 2048, 2>::bytes, 256, 3, 0));
+        else if (c->tier_a_variant == 1) TRY(launch_tier(k_merge_tier<TIER_A1>, TierSmem<512, 4096, 512, 2048, 1>::bytes, 512, 3, 0));
+        else TRY(launch_tier(k_merge_tier<TIER_A>, TierSmem<512, 3072, 512, 2048, 2>::bytes, 512, 3, 0));
+        TRY(launch_tier(k_merge_tier<TIER_B>, TierSmem<512, 5632, 1408, 4608, 1>::bytes, 512, 2, 1));
+        TRY(launch_tier(k_merge_tier<TIER_C>, TierSmem<1024, 11776, 2560, 8192, 1>::bytes, 1024, 1, 2));
         if (!big.empty()) {
             {
                 LaunchTimer t(c, F_PARTITION);
@@ -1108,7 +1112,7 @@ int32_t ggcat_b200_create(const ggcat_b200_params *params, ggcat_b200_ctx **out)
     }
     if (const char *np = getenv("GGCAT_B200_NO_PARTITION")) c->no_partition = atoi(np) != 0;
     if (const char *nt = getenv("GGCAT_B200_NO_TIERS")) c->no_tiers = atoi(nt) != 0;
-    if (const char *ta = getenv("GGCAT_B200_TIER_A_THREADS")) c->tier_a_threads = atoi(ta) == 256 ? 256 : 512;
+    if (const char *ta = getenv("GGCAT_B200_TIER_A")) c->tier_a_variant = std::max(0, std::min(2, atoi(ta)));
     if (const char *pt = getenv("GGCAT_B200_PART_TARGET")) c->part_fixed = strcmp(pt, "fixed") == 0;
     if (const char *dr = getenv("GGCAT_B200_DISTINCT_RATIO")) { const double v = atof(dr); if (v > 0) c->distinct_ratio = v; }  // tests: pretend a ratio
     if (const char *mm = getenv("GGCAT_B200_MERGE")) c->merge_mode = (strcmp(mm, "sort") == 0) ? 0 : 1;

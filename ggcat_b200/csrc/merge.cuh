@@ -564,9 +564,10 @@ __device__ __forceinline__ bool hash_insert_bounded(uint64_t *K, uint32_t *C, ui
 //     the current unit are done, so they overlap the table scan), which hides the descriptor / payload latency that the
 //     first version of this kernel paid at the start of every unit (ncu: 12.6 % of its stall samples on that load).
 //   * All bit extraction reads shared memory: descriptors are rewritten in place to {first record, payload word, len|flags}.
-//   * The table is sized from the DISTINCT keys the unit is expected to hold (slots_q16 = slots per k-mer record, from the
-//     distinct/records ratio of what this context merged before), not from its records: at 30x coverage a unit of 16 k
-//     records holds ~5 k keys.  Inserts probe a bounded number of slots; a unit whose table fills goes to the retry list
+//   * A unit is routed to a tier by the DISTINCT keys it is expected to hold (host: distinct/records ratio of what this
+//     context merged before, target load <= 0.5), not by its records: at 30x coverage a unit of 16 k records holds ~5 k
+//     keys.  Divergence in the probe loop is what costs issue slots (every extra probe of one lane stalls 31 others), so
+//     the table is kept sparse.  Inserts probe a bounded number of slots; a unit whose table fills goes to the retry list
 //     (global-table kernel).  Scanning the table resets it for the next unit (no separate clear pass).
 //   * Barriers per unit: 1 (prefix scan of the k-mer counts) + 3, against 7 + 3 per staging round before.
 // Semantics per record: hashmap.rs:385-399 / map_entry.rs:33-84, as k_merge_hash.
@@ -611,8 +612,10 @@ __device__ __forceinline__ uint32_t block_scan1(uint32_t v, uint32_t *s_w, uint3
 }
 
 // Warp 0: take the next unit from the work counter and arm the bulk copies of its slices into one landing buffer.
+// meta = {unit, n_sk, start of the unit's output region (lo, hi)}: loaded here, a whole unit ahead of their use.
 __device__ __forceinline__ void tier_prefetch(const ChunkView *__restrict__ chunks, uint32_t n_chunks, const uint32_t *__restrict__ work,
-                                              uint32_t n_work, uint32_t *__restrict__ work_counter, uint4 *sk, uint32_t *pay,
+                                              uint32_t n_work, uint32_t *__restrict__ work_counter, uint32_t first_unit,
+                                              const uint64_t *__restrict__ static_off, uint4 *sk, uint32_t *pay,
                                               uint64_t *bar, uint32_t *meta, uint32_t *sl_dstart, uint32_t *sl_delta) {
     const uint32_t lane = lane_id();
     uint32_t wi = 0;
@@ -634,6 +637,8 @@ __device__ __forceinline__ void tier_prefetch(const ChunkView *__restrict__ chun
             bias = cv.word_bias; desc = cv.desc;
         }
     }
+    unsigned long long gbase = 0;
+    if (lane == 0) gbase = static_off[unit - first_unit];
     const uint32_t cw = cnt ? ((lead + nw + 3u) & ~3u) : 0u;
     uint32_t dx = cnt, px = cw;
 #pragma unroll
@@ -648,7 +653,7 @@ __device__ __forceinline__ void tier_prefetch(const ChunkView *__restrict__ chun
     if (lane == 31) sl_dstart[32] = dtot;
     fence_proxy_async_smem();                   // the landing buffers were read / rewritten by plain loads and stores
     if (lane == 0) {
-        meta[0] = unit; meta[1] = dtot;
+        meta[0] = unit; meta[1] = dtot; meta[2] = (uint32_t)gbase; meta[3] = (uint32_t)(gbase >> 32);
         mbar_expect_tx(bar, dtot * 16u + ptot * 4u);
     }
     __syncwarp();
@@ -658,11 +663,11 @@ __device__ __forceinline__ void tier_prefetch(const ChunkView *__restrict__ chun
     }
 }
 
-template <int THREADS, int TS, int SKCAP, int PWCAP, int NBUF>
-__global__ void __launch_bounds__(THREADS)
+template <int THREADS, int TS, int SKCAP, int PWCAP, int NBUF, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
 k_merge_tier(const ChunkView *__restrict__ chunks, uint32_t n_chunks, const uint32_t *__restrict__ work, uint32_t n_work,
-             uint32_t first_unit, DevParams P, uint32_t min_mult, MergeOut out, const uint32_t *__restrict__ unit_n,
-             uint32_t slots_q16, uint32_t *__restrict__ work_counter, uint32_t *__restrict__ retry, uint32_t *__restrict__ retry_count) {
+             uint32_t first_unit, DevParams P, uint32_t min_mult, MergeOut out,
+             uint32_t *__restrict__ work_counter, uint32_t *__restrict__ retry, uint32_t *__restrict__ retry_count) {
     using L = TierSmem<THREADS, TS, SKCAP, PWCAP, NBUF>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr uint32_t WARPS = THREADS / 32;
@@ -681,11 +686,12 @@ k_merge_tier(const ChunkView *__restrict__ chunks, uint32_t n_chunks, const uint
 
     const uint32_t tid = threadIdx.x, lane = lane_id(), warp = warp_id();
     const uint32_t k = P.k, forward_only = P.forward_only;
-    const uint64_t kmask = (1ull << (2 * k)) - 1ull;
+    const uint32_t kmask_lo = (uint32_t)((1ull << (2 * k)) - 1ull), kmask_hi = (uint32_t)(((1ull << (2 * k)) - 1ull) >> 32), rc_shift = 64u - 2u * k;
     const uint32_t le_mask = 0xFFFFFFFFu >> (31u - lane);
+    const uint32_t aK = smem_addr(K), aC = smem_addr(C), aFull = smem_addr(s_cnt + 3);
     auto prefetch = [&](uint32_t b) {
-        tier_prefetch(chunks, n_chunks, work, n_work, work_counter, skb + (size_t)b * SKCAP, payb + (size_t)b * (PWCAP + 8), bars + b,
-                      metab + 4 * b, dstartb + (TIER_MAXSL + 1) * b, deltab + TIER_MAXSL * b);
+        tier_prefetch(chunks, n_chunks, work, n_work, work_counter, first_unit, out.static_off, skb + (size_t)b * SKCAP,
+                      payb + (size_t)b * (PWCAP + 8), bars + b, metab + 4 * b, dstartb + (TIER_MAXSL + 1) * b, deltab + TIER_MAXSL * b);
     };
     for (uint32_t i = tid; i < (uint32_t)TS; i += THREADS) { K[i] = HASH_EMPTY; C[i] = 0u; }
     if (tid == 0) {
@@ -699,15 +705,12 @@ k_merge_tier(const ChunkView *__restrict__ chunks, uint32_t n_chunks, const uint
         const uint32_t b = NBUF == 2 ? (it & 1u) : 0u;
         const uint32_t unit = metab[4 * b], nsk = metab[4 * b + 1];
         if (unit == TIER_DONE) break;
+        const unsigned long long gbase = ((unsigned long long)metab[4 * b + 3] << 32) | metab[4 * b + 2];
         if (NBUF == 2 && warp == 0) prefetch(b ^ 1u);     // the other landing buffer: its unit finished before the last barrier
         mbar_wait(bars + b, NBUF == 2 ? ((it >> 1) & 1u) : (it & 1u));
         const uint32_t unit_rel = unit - first_unit;
-        const uint32_t n = unit_n[unit_rel];
-        uint32_t ts = (uint32_t)((((uint64_t)n * slots_q16) >> 16) + 31u) & ~31u;
-        ts = ts < 512u ? 512u : (ts > (uint32_t)TS ? (uint32_t)TS : ts);
         uint4 *sk = skb + (size_t)b * SKCAP;
         uint32_t *start = startb + (size_t)b * SKCAP;
-        const uint32_t *pay = payb + (size_t)b * (PWCAP + 8);
         const uint32_t *sl_dstart = dstartb + (TIER_MAXSL + 1) * b, *sl_delta = deltab + TIER_MAXSL * b;
         // ---- stage: raw descriptor {word, len, meta, colour} -> {first record, staged payload word, len | flags << 30}
         uint32_t tot;
@@ -736,56 +739,83 @@ k_merge_tier(const ChunkView *__restrict__ chunks, uint32_t n_chunks, const uint
             }
         }
         __syncthreads();
-        // ---- insert: every warp walks an equal, 32-aligned range of the unit's records, one record per lane
+        // ---- insert: every warp walks an equal, 32-aligned range of the unit's records, one record per lane.
+        //      Shared memory is addressed by 32-bit shared-window addresses; the probe loop only FINDS (or claims) the
+        //      slot, the lanes reconverge, then one counter update / flag update for the whole warp.
         {
+            const uint32_t aSk = smem_addr(sk), aStart = smem_addr(start), aPay = smem_addr(payb + (size_t)b * (PWCAP + 8));
             const uint32_t per = ((tot + WARPS * 32u - 1u) / (WARPS * 32u)) * 32u;
             const uint32_t r_beg = warp * per, r_end = min(tot, r_beg + per);
             if (r_beg < r_end) {
                 uint32_t lo = 0, hi = nsk - 1;                                          // last j with start[j] <= r_beg
                 while (lo < hi) {
                     const uint32_t mid = (lo + hi + 1) >> 1;
-                    if (start[mid] <= r_beg) lo = mid; else hi = mid - 1;
+                    if (lds_u32(aStart + 4u * mid) <= r_beg) lo = mid; else hi = mid - 1;
                 }
                 uint32_t j = lo;                                                       // invariant: start[j] <= r0 < start[j+1]
                 for (uint32_t r0 = r_beg; r0 < r_end; r0 += 32u) {
-                    if (*reinterpret_cast<volatile uint32_t *>(&s_cnt[3])) break;      // somebody found the table full
+                    if (lds_u32(aFull)) break;                                         // somebody found the table full
                     const uint32_t cand = j + 1u + lane;
-                    const uint32_t rel = (cand < nsk ? start[cand] : 0xFFFFFFFFu) - r0;  // > 0 by the invariant
+                    const uint32_t rel = (cand < nsk ? lds_u32(aStart + 4u * cand) : 0xFFFFFFFFu) - r0;  // > 0 by the invariant
                     const uint32_t smask = __reduce_or_sync(0xffffffffu, rel < 32u ? (1u << rel) : 0u);
                     const uint32_t owner = j + (uint32_t)__popc(smask & le_mask);
                     const uint32_t r = r0 + lane;
-                    if (r < r_end) {
-                        const uint4 s = sk[owner];
+                    const bool active = r < r_end;
+                    uint32_t slot = 0, fb = 0;
+                    bool claimed = true;                                               // inactive lanes touch nothing below
+                    if (active) {
+                        const uint4 s = lds_u128(aSk + 16u * owner);
                         const uint32_t i = r - s.x, last = (s.z & 0x3FFFFFFFu) - k, flags = s.z >> 30;
-                        const uint64_t fw = extract64(pay + s.y, 2ull * i) & kmask;
-                        const uint64_t rc = revcomp64(fw) >> (64 - 2 * k);
-                        const bool isf = forward_only ? true : (fw < rc);
-                        const uint64_t key = isf ? fw : rc;
+                        const uint32_t wa = aPay + 4u * (s.y + (i >> 4)), sh = (i & 15u) * 2u;
+                        const uint32_t w0 = lds_u32(wa), w1 = lds_u32(wa + 4u), w2 = lds_u32(wa + 8u);
+                        const uint32_t flo = __funnelshift_r(w0, w1, sh) & kmask_lo, fhi = __funnelshift_r(w1, w2, sh) & kmask_hi;
+                        // reverse complement of the 2k-bit k-mer (cn_seqhash_base.rs:27-69 evaluated directly)
+                        const unsigned long long fw = ((unsigned long long)fhi << 32) | flo;
+                        const unsigned long long rcx = (((unsigned long long)revcomp32(flo) << 32) | revcomp32(fhi)) >> rc_shift;
+                        const bool isf = forward_only ? true : (fw < rcx);
+                        const unsigned long long key = isf ? fw : rcx;
                         const uint32_t bi = (!(flags & READ_FLAG_INCL_BEGIN) && i == 0) ? 1u : 0u;
                         const uint32_t ei = (!(flags & READ_FLAG_INCL_END) && i == last) ? 1u : 0u;
-                        const uint32_t fb = (bi << (isf ? 0 : 1)) | (ei << (isf ? 1 : 0));     // hashmap.rs:385-399
-                        if (!hash_insert_bounded(K, C, ts, key, fb, TIER_PROBE_LIMIT)) s_cnt[3] = 1u;
+                        fb = (bi << (isf ? 0 : 1)) | (ei << (isf ? 1 : 0));           // hashmap.rs:385-399
+                        const uint32_t klo = (uint32_t)key, khi = (uint32_t)(key >> 32);
+                        slot = hash_slot(key, (uint32_t)TS);
+                        claimed = false;
+                        uint32_t probes = 0;
+                        while (true) {
+                            const uint2 cur = lds_u64x(aK + 8u * slot);
+                            if (cur.x == klo && cur.y == khi) break;
+                            if (cur.y == 0xFFFFFFFFu) {                                // empty: keys are < 2^62
+                                const unsigned long long old = atoms_cas64(aK + 8u * slot, HASH_EMPTY, key);
+                                if (old == HASH_EMPTY) { claimed = true; break; }
+                                if (old == key) break;
+                            }
+                            slot = slot + 1u == (uint32_t)TS ? 0u : slot + 1u;
+                            if (++probes >= TIER_PROBE_LIMIT) { s_cnt[3] = 1u; claimed = true; fb = 0; break; }
+                        }
                     }
+                    __syncwarp();
+                    if (!claimed) atoms_inc32(aC + 4u * slot);
+                    if (fb && ((lds_u32(aC + 4u * slot) >> 30) & fb) != fb) atoms_or32(aC + 4u * slot, fb << 30);
                     j += (uint32_t)__popc(smask);
-                    if (j + 1u < nsk && start[j + 1u] == r0 + 32u) ++j;                // next window starts a new super-k-mer
+                    if (j + 1u < nsk && lds_u32(aStart + 4u * (j + 1u)) == r0 + 32u) ++j;   // next window starts a new super-k-mer
                 }
             }
         }
         __syncthreads();
         const uint32_t full = s_cnt[3];
         if (NBUF == 1 && warp == 0) prefetch(0);          // the landing buffer is free: the copies overlap the table scan
-        const unsigned long long gbase = out.static_off[unit_rel];
         if (full) {
-            for (uint32_t i = tid; i < ts; i += THREADS) { K[i] = HASH_EMPTY; C[i] = 0u; }
+            for (uint32_t i = tid; i < (uint32_t)TS; i += THREADS) { K[i] = HASH_EMPTY; C[i] = 0u; }
             if (tid == 0) retry[atomicAdd(retry_count, 1u)] = unit;
         } else {
             // ---- scan the table once: MapEntry -> multiplicity, -s filter, survivors to the unit's region; reset the slots
             uint32_t my_occ = 0;
-            for (uint32_t base = 0; base < ts; base += THREADS) {
+#pragma unroll 2
+            for (uint32_t base = 0; base < (uint32_t)TS; base += THREADS) {
                 const uint32_t i = base + tid;
                 uint64_t kk = HASH_EMPTY;
                 uint32_t cf = 0;
-                if (i < ts) {
+                if (i < (uint32_t)TS) {
                     kk = K[i];
                     if (kk != HASH_EMPTY) {
                         const uint32_t cc = C[i];
