@@ -396,13 +396,13 @@ constexpr int GL_THREADS = 1024;
 //   B  ~112 KB 2 CTAs / SM
 //   C  ~221 KB 1 CTA  / SM   units of up to ~25 k records at 30x coverage (C2-sized slices on 8 GPUs: 16 k records)
 constexpr int HASH_TS_S = 8192;                       // k_merge_parts: table slots of one key partition
-#define TIER_A 512, 3072, 512, 2048, 2, 3
-#define TIER_A1 512, 4096, 512, 2048, 1, 3     // A/B variant: one landing buffer, sparser table
+#define TIER_A 512, 4096, 512, 2048, 1, 3      // one landing buffer + a sparser table measured faster than two buffers + 3072 slots (1.35 vs 1.43 ms on C2)
+#define TIER_A1 512, 3072, 512, 2048, 2, 3     // A/B variant: two landing buffers, 3072 slots
 #define TIER_A256 256, 3072, 512, 2048, 2, 3   // A/B variant: 8 warps per unit
 #define TIER_B 512, 5632, 1408, 4608, 1, 2
 #define TIER_C 1024, 11776, 2560, 8192, 1, 1
 struct TierCap { uint32_t ts, skcap, pwcap; };
-constexpr TierCap kTierCaps[3] = {{3072, 512, 2048}, {5632, 1408, 4608}, {11776, 2560, 8192}};
+constexpr TierCap kTierCaps[3] = {{4096, 512, 2048}, {5632, 1408, 4608}, {11776, 2560, 8192}};
 constexpr double TIER_MAX_LOAD = 0.5;   // expected distinct keys / table slots a unit may have in its tier
 
 // A bucket range may be merged in several parts that append to one final table (merge_range_parts): `eb` = entries
@@ -485,7 +485,7 @@ int32_t merge_range_device(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_
     // expected distinct keys per k-mer record (15 % margin): routes a unit to the smallest tier whose table stays sparse
     const double keys_per_rec = std::min(1.0, 1.15 * c->distinct_ratio);
     TierCap caps[3] = {kTierCaps[0], kTierCaps[1], kTierCaps[2]};
-    if (c->tier_a_variant == 1) caps[0].ts = 4096;
+    if (c->tier_a_variant != 0) caps[0].ts = 3072;
     for (Chunk *ch : c->chunks) {
         const uint32_t lo = std::max(u0, ch->first_unit), hi = std::min(u0 + nu, ch->first_unit + ch->n_units);
         for (uint32_t u = lo; u < hi; u++) {
@@ -641,8 +641,8 @@ int32_t merge_range_device(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_
             return 0;
         };
         if (c->tier_a_variant == 2) TRY(launch_tier(k_merge_tier<TIER_A256>, TierSmem<256, 3072, 512, 2048, 2>::bytes, 256, 3, 0));
-        else if (c->tier_a_variant == 1) TRY(launch_tier(k_merge_tier<TIER_A1>, TierSmem<512, 4096, 512, 2048, 1>::bytes, 512, 3, 0));
-        else TRY(launch_tier(k_merge_tier<TIER_A>, TierSmem<512, 3072, 512, 2048, 2>::bytes, 512, 3, 0));
+        else if (c->tier_a_variant == 1) TRY(launch_tier(k_merge_tier<TIER_A1>, TierSmem<512, 3072, 512, 2048, 2>::bytes, 512, 3, 0));
+        else TRY(launch_tier(k_merge_tier<TIER_A>, TierSmem<512, 4096, 512, 2048, 1>::bytes, 512, 3, 0));
         TRY(launch_tier(k_merge_tier<TIER_B>, TierSmem<512, 5632, 1408, 4608, 1>::bytes, 512, 2, 1));
         TRY(launch_tier(k_merge_tier<TIER_C>, TierSmem<1024, 11776, 2560, 8192, 1>::bytes, 1024, 1, 2));
         if (!big.empty()) {

@@ -808,38 +808,45 @@ k_merge_tier(const ChunkView *__restrict__ chunks, uint32_t n_chunks, const uint
             for (uint32_t i = tid; i < (uint32_t)TS; i += THREADS) { K[i] = HASH_EMPTY; C[i] = 0u; }
             if (tid == 0) retry[atomicAdd(retry_count, 1u)] = unit;
         } else {
-            // ---- scan the table once: MapEntry -> multiplicity, -s filter, survivors to the unit's region; reset the slots
-            uint32_t my_occ = 0;
-#pragma unroll 2
-            for (uint32_t base = 0; base < (uint32_t)TS; base += THREADS) {
-                const uint32_t i = base + tid;
-                uint64_t kk = HASH_EMPTY;
+            // ---- table -> survivors, two passes over the thread's own slots (no block barrier in between):
+            //   1  MapEntry -> multiplicity (map_entry.rs:79-84), -s filter; the slot's counter word is overwritten with
+            //      the entry's final count|flags (0 = dropped)
+            //   2  one warp scan + ONE shared atomic per warp reserve the output range; survivors are written to the
+            //      unit's region, every slot is reset for the next unit
+            uint32_t my_occ = 0, my_keep = 0;
+            for (uint32_t i = tid; i < (uint32_t)TS; i += THREADS) {
+                const uint2 kk = lds_u64x(aK + 8u * i);
                 uint32_t cf = 0;
-                if (i < (uint32_t)TS) {
-                    kk = K[i];
-                    if (kk != HASH_EMPTY) {
-                        const uint32_t cc = C[i];
-                        K[i] = HASH_EMPTY; C[i] = 0u;
-                        ++my_occ;
-                        const uint32_t cnt = slot_count(cc), fl = cc >> 30;
-                        const uint32_t mult = cnt >> ((fl == (READ_FLAG_INCL_BEGIN | READ_FLAG_INCL_END)) ? 1 : 0);  // map_entry.rs:79-84
-                        if (mult >= min_mult) cf = mult | (fl << 30);
-                    }
-                }
-                const uint32_t bal = __ballot_sync(0xffffffffu, cf != 0);
-                if (bal) {
-                    uint32_t wb = 0;
-                    if (lane == 0) wb = atomicAdd(&s_cnt[0], (uint32_t)__popc(bal));
-                    wb = __shfl_sync(0xffffffffu, wb, 0);
-                    if (cf) {
-                        const unsigned long long o = gbase + wb + __popc(bal & ((1u << lane) - 1u));
-                        out.keys[o] = kk; out.count_flags[o] = cf;
-                    }
+                if (kk.y != 0xFFFFFFFFu) {
+                    const uint32_t cc = C[i];
+                    ++my_occ;
+                    const uint32_t cnt = slot_count(cc), fl = cc >> 30;
+                    const uint32_t mult = cnt >> ((fl == (READ_FLAG_INCL_BEGIN | READ_FLAG_INCL_END)) ? 1 : 0);
+                    if (mult >= min_mult) { cf = mult | (fl << 30); ++my_keep; }
+                    C[i] = cf;
                 }
             }
+            uint32_t incl = my_keep;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (uint32_t)o) incl += y; }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) my_occ += __shfl_xor_sync(0xffffffffu, my_occ, o);
-            if (lane == 0 && my_occ) atomicAdd(&s_cnt[1], my_occ);
+            uint32_t wbase = 0;
+            if (lane == 31) {
+                if (incl) wbase = atomicAdd(&s_cnt[0], incl);
+                if (my_occ) atomicAdd(&s_cnt[1], my_occ);
+            }
+            wbase = __shfl_sync(0xffffffffu, wbase, 31);
+            unsigned long long o = gbase + wbase + (incl - my_keep);
+            for (uint32_t i = tid; i < (uint32_t)TS; i += THREADS) {
+                const uint32_t cf = C[i];
+                if (cf) {
+                    out.keys[o] = K[i]; out.count_flags[o] = cf;
+                    ++o;
+                    C[i] = 0u;
+                }
+                K[i] = HASH_EMPTY;
+            }
         }
         __syncthreads();
         if (tid == 0) {
