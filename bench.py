@@ -13,8 +13,12 @@ contiguous ranges, super-k-mers are routed with one all-to-all (NCCL) and each o
 Printed JSON line (rank 0): see DESIGN.md "Measurement".
   value    device-timed (CUDA events on the library's stream), inputs resident in HBM
   e2e      same metric through the C ABI with HOST buffers (H2D of reads, D2H of the table inside the timed region)
-  roofline dominant kernel family (k_merge_hash<smem> on C2) against the measured HBM peak; `achieved` uses the
-           algorithmic-bytes model of SURVEY 8(d), `compulsory_bytes_per_launch` what the kernel really has to move
+  roofline dominant kernel family against the measured HBM peak: `achieved` = the bytes the kernel has to move (inputs once,
+           outputs once) / its CUDA-event time, `traffic` = dram__bytes_read+write measured by an ncu pass of this run
+           (fallback: profiles/r02_traffic.json, labelled), `frac` = achieved / peak; `limiter` says what really bounds it
+           (issue slots), `step` / `per_kernel` give the same for the whole step and every family;
+           `survey_model_equiv_frac` is the SURVEY 8(d) DRAM-LSD pipeline (195 B/base, W+P = 12) at this step time
+  parity   N > 1: sampled owned units of every rank (device path and host path) against the oracle on the union of all reads
   exchange N > 1: bytes pushed over NVLink per GPU, time of the push + flag kernels, fraction of 770 GB/s
   cpu_baseline  N = 1: the oracle's OpenMP port, repeated passes over the whole batch for >= 10 s (kind "port")
 
@@ -103,6 +107,62 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def workload_string(wl: str, n_reads: int, world: int, b1: int, b2: int) -> str:
+    """config.workload, shared by both arms (the driver compares the two strings)."""
+    if wl == "c2":
+        return (f"C2 per GPU: {n_reads} x {READ_LEN} bp reads (30x of {GENOME_PER_GPU * world} bp genome, 1% errors), "
+                f"k={K} m={M} -s {S} seq-hash, buckets {1 << b1}(+1) x {1 << b2}")
+    return (f"C4 per GPU: {n_reads} x {READ_LEN} bp reads (30x of {5 * n_reads * world} bp genome, error-free), "
+            f"k={K} m={M} -s {S} seq-hash, buckets {1 << b1}(+1) x {1 << b2}")
+
+
+FAMILY_OF = [  # kernel-name regex -> family name of ggcat_b200_kernel_times
+    (r"k_pack|k_mark", "k_pack+k_mark"), (r"k_windows", "k_windows"), (r"k_emit", "k_emit"),
+    (r"k_scatter|k_init_cursors", "k_scatter"), (r"k_exclusive_scan_u32", "k_exclusive_scan_u32"),
+    (r"k_merge_tier", "k_merge_hash<smem>"), (r"k_merge_hash<", "k_merge_hash<global>"),
+    (r"k_scan_unit_slots|k_finish_small|k_finish_units", "k_gather_units"), (r"k_partition_units", "k_partition_units"),
+    (r"k_merge_parts", "k_merge_hash<partitions>"),
+]
+
+
+def traffic_pass(timeout_s: float = 150.0):
+    """DRAM traffic per kernel family of ONE warm C2 step, measured now: ncu (dram__bytes_read/write.sum) over
+    profiles/prof_driver.py, which brackets its last step with cudaProfilerStart/Stop.  Returns (dict, source)."""
+    import csv
+    import re
+    import shutil
+
+    ncu = shutil.which("ncu") or "/usr/local/cuda/bin/ncu"
+    try:
+        out = subprocess.run([ncu, "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none",
+                              "--profile-from-start", "off", "--csv", sys.executable, str(ROOT / "profiles" / "prof_driver.py"), "3"],
+                             capture_output=True, text=True, timeout=timeout_s, cwd=str(ROOT))
+        rows = list(csv.reader([l for l in out.stdout.splitlines() if l.startswith('"')]))
+        hdr = rows[0]
+        ik, im, iu, iv = hdr.index("Kernel Name"), hdr.index("Metric Name"), hdr.index("Metric Unit"), hdr.index("Metric Value")
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        fam = {}
+        for r in rows[1:]:
+            if not r[im].startswith("dram__bytes"):
+                continue
+            name = next((f for pat, f in FAMILY_OF if re.search(pat, r[ik])), None)
+            if name is None:
+                continue
+            fam[name] = fam.get(name, 0.0) + float(r[iv].replace(",", "")) * scale.get(r[iu], 1.0)
+        if fam:
+            return {k: int(v) for k, v in fam.items()}, "ncu pass in this run (dram__bytes_read.sum + dram__bytes_write.sum, one warm step)"
+    except Exception:
+        pass
+    tr = ROOT / "profiles" / "r02_traffic.json"
+    if tr.exists():
+        try:
+            d = json.loads(tr.read_text())
+            return {k: v for k, v in d.items() if not k.startswith("_")}, "profiles/r02_traffic.json (committed ncu pass of the same command; ncu unavailable in this run)"
+        except Exception:
+            pass
+    return {}, "unavailable"
+
+
 def make_reads(rank: int, world: int, n_reads: int):
     from ggcat_b200 import synth
 
@@ -123,10 +183,20 @@ def run_reference(args):
     import ggcat_b200  # noqa: F401  (only for bucket_counts parity with our arm; no GPU work)
     from ggcat_b200 import synth
 
-    sample_reads = args.sample_reads   # default: the whole per-GPU C2 batch, ~1 s of CPU work per step on 16 cores
+    world = max(args.gpus, 1)
+    per_gpu = args.reads_per_gpu if args.reads_per_gpu else READS_PER_GPU
+    # the same N-GPU workload as our arm: the slices of all N ranks, one pass over all of them per step (about 1 s of
+    # CPU work per GPU slice on 16 cores); --sample-reads bounds it (tests)
+    if args.sample_reads:
+        parts = [make_reads(0, world, args.sample_reads)]
+        sample_note = f"{args.sample_reads} reads of rank 0's slice"
+    else:
+        parts = [make_reads(r, world, per_gpu) for r in range(world)]
+        sample_note = f"all {world} x {per_gpu} reads of the workload"
     cores = os.cpu_count() or 1
-    data, offsets = make_reads(0, max(args.gpus, 1), sample_reads)
-    b1, b2 = O.bucket_counts(int(READS_PER_GPU * max(args.gpus, 1) * (READ_LEN + 15)))  # same bucket counts as the full workload
+    data = np.concatenate([d for d, _ in parts])
+    offsets = np.arange(data.size // READ_LEN + 1, dtype=np.uint64) * np.uint64(READ_LEN)
+    b1, b2 = O.bucket_counts(int(per_gpu * world * (READ_LEN + 15)))  # same bucket counts as the full workload
     reads = O.Reads(data, offsets)
     times = []
     st = None
@@ -143,14 +213,60 @@ def run_reference(args):
         "impl": "reference", "metric": "build Gbases/s (bucketing+k-mer merge)", "value": val, "unit": "Gbases/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": f"C2: {sample_reads} x {READ_LEN} bp reads of the 5 Mbp/30x/1% set per step, k={K} m={M} -s {S}, "
-                               f"buckets {1 << b1}(+1) x {1 << b2}"},
+        "config": {"workload": workload_string("c2", per_gpu, world, b1, b2)},
         "cpu_baseline": {"value": val, "unit": "Gbases/s", "cores": int(st.threads), "kind": "port",
-                         "sample": f"{sample_reads} reads ({bases} bases); phase1 {st.t_bucketing:.3f}s phase2 {st.t_merge:.3f}s"},
+                         "sample": f"{sample_note} ({bases} bases per step); phase1 {st.t_bucketing:.3f}s phase2 {st.t_merge:.3f}s"},
         "e2e": {"value": val, "unit": "Gbases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def multi_gpu_parity(args, ctx, owner, rank, world, b1, b2, n_reads, step_device, step_host):
+    """Every rank hands `parity_units` sampled units of its owner range (tables of the device path and of the host
+    path) to rank 0, which runs the oracle on the UNION of all ranks' reads and compares bit for bit."""
+    import torch.distributed as dist
+
+    fb, cnt = owner.bucket_range(rank)
+    u_lo, u_hi = fb << b2, (fb + cnt) << b2
+    rng = np.random.default_rng(1234 + rank)
+    units = np.sort(rng.choice(np.arange(u_lo, u_hi), size=min(args.parity_units, u_hi - u_lo), replace=False))
+    payload = {"rank": rank, "units": units.tolist(), "tables": {}}
+    step_device()
+    tab = ctx.read_device_table([int(u) for u in units])      # only the sampled units leave the GPU
+    payload["tables"]["device"] = [(np.array(tab.keys_lo[tab.unit_slice_at(i)]), np.array(tab.count_flags[tab.unit_slice_at(i)]))
+                                   for i in range(len(units))]
+    if step_host is not None:
+        tab = step_host()
+        payload["tables"]["host"] = [(np.array(tab.keys_lo[tab.unit_slice(int(u))]), np.array(tab.count_flags[tab.unit_slice(int(u))]))
+                                     for u in units]
+        tab.release()
+    gathered = [None] * world if rank == 0 else None
+    dist.gather_object(payload, gathered, dst=0)
+    if rank != 0:
+        return None
+    from oracle import oracle as O
+
+    parts = [make_reads(r, world, n_reads) for r in range(world)]
+    data = np.concatenate([d for d, _ in parts])
+    offsets = np.arange(data.size // READ_LEN + 1, dtype=np.uint64) * np.uint64(READ_LEN)
+    reads = O.Reads(data, offsets)
+    sk, _ = O.bucketing(reads, K, M, b1, b2)
+    checked, entries, bad = 0, 0, []
+    for pl in gathered:
+        for i, u in enumerate(pl["units"]):
+            ref, _, _ = O.merge_unit(reads, sk, int(u) >> b2, int(u) & ((1 << b2) - 1), K, S)
+            ref = ref[ref["kept"] == 1]
+            rcf = (ref["multiplicity"].astype(np.uint32) & np.uint32(0x3FFFFFFF)) | (ref["flags"].astype(np.uint32) << np.uint32(30))
+            for path, rows in pl["tables"].items():
+                keys, cf = rows[i]
+                ok = np.array_equal(keys, ref["key_lo"]) and np.array_equal(cf, rcf)
+                checked += 1
+                entries += len(ref)
+                if not ok:
+                    bad.append({"rank": pl["rank"], "unit": int(u), "path": path})
+    return {"ok": not bad, "units_checked": checked, "entries_checked": entries, "paths": sorted(gathered[0]["tables"].keys()),
+            "oracle": "oracle/ggcat_oracle.c on the union of all ranks' reads", "mismatches": bad[:8]}
 
 
 # ------------------------------------------------------------------------------------------- our arm
@@ -348,7 +464,7 @@ def run_ours(args):
         e2e = {"value": (n_bases * world) / (e2e_ms * 1e-3) / 1e9, "unit": "Gbases/s",
                "h2d_bytes_per_step": int(h_data.numel() + h_off.numel() * 8), "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms}
 
-    # ---- roofline of the dominant kernel (largest device time in the per-kernel pass)
+    # ---- roofline: measured DRAM traffic and the bytes each family has to move, against the measured HBM peak
     peak, peak_kind = measured_peak()
     total_kernel_ms = max(sum(v[0] for v in kt.values()), 1e-9)
     dom = max(kt, key=lambda name: kt[name][0])
@@ -357,35 +473,73 @@ def run_ours(args):
     launches_per_step = max(dom_launches / n_prof, 1)
     B_s = st.payload_words * 4 + st.n_superkmers * 16       # super-k-mer payload + descriptors
     N_k = st.n_kmers
-    if dom.startswith("k_merge"):
-        # SURVEY 8(d) merge model with this build's record size W+P = 8 B and R = 8 LSD passes:
-        #   B_s + N_k*8*(1 expand write + 2R sort + 1 reduce read) + S*12
-        model_bytes = B_s + N_k * 8 * (1 + 2 * 8 + 1) + n_entries * 12
-        compulsory = B_s + n_entries * 12                   # what the kernel must move: super-k-mers in, table out
-        model = "SURVEY 8(d) DRAM-LSD-equivalent bytes (W+P=8, R=8); the kernel counts in shared memory"
-    else:
-        # bucketing kernels: packed bases + 2 bitmaps in, entries out (SURVEY 8(d) bucketing model share)
-        model_bytes = compulsory = n_bases // 4 + 2 * (n_bases // 8) + st.n_superkmers * 8
-        model = "compulsory bytes: packed bases + bad/brk bitmaps in, split entries out"
-    achieved = model_bytes / launches_per_step / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_kind": peak_kind, "model": model,
-                "algorithmic_bytes_per_launch": model_bytes / launches_per_step,
-                "compulsory_bytes_per_launch": compulsory / launches_per_step, "ms_per_launch": per_launch_ms,
-                "kernel_share_of_step": dom_ms / total_kernel_ms}
-    tr = ROOT / "profiles" / "traffic.json"
-    if tr.exists():
+    n_ent_est = st.n_superkmers * 1.1                       # split entries (super-k-mer starts + segment ends)
+    # algorithmic bytes per step of every family: inputs read once + outputs written once
+    algo = {
+        "k_pack+k_mark": n_bases + n_bases // 4 + n_bases // 8 + n_reads * 8,
+        "k_windows": n_bases // 4 + 2 * (n_bases // 8) + n_ent_est * 8,
+        "k_emit": n_ent_est * 8 + st.n_superkmers * 16,
+        "k_scatter": st.n_superkmers * 16 + n_bases // 4 + B_s,
+        "k_merge_hash<smem>": B_s + n_entries * 12,
+        "k_gather_units": 2 * n_entries * 12,
+        "k_partition_units": B_s + N_k * 8, "k_merge_hash<partitions>": N_k * 8 + n_entries * 12,
+    }
+    traffic, traffic_src = ({}, "skipped")
+    if rank == 0 and world == 1 and wl == "c2" and not args.no_traffic_pass:
+        ctx.synchronize()
+        traffic, traffic_src = traffic_pass()
+    per_kernel = {}
+    for name, (ms_f, ln) in kt.items():
+        if ln == 0:
+            continue
+        ms1 = ms_f / n_prof
+        ent = {"ms": round(ms1, 4)}
+        if name in algo and ms1 > 0:
+            ent["algorithmic_bytes"] = int(algo[name])
+            ent["achieved_GBps"] = round(algo[name] / (ms1 * 1e-3) / 1e9, 1)
+            ent["frac"] = round(algo[name] / (ms1 * 1e-3) / 1e9 / peak, 4)
+        if name in traffic and ms1 > 0:
+            ent["traffic_bytes"] = int(traffic[name])
+            ent["traffic_GBps"] = round(traffic[name] / (ms1 * 1e-3) / 1e9, 1)
+        per_kernel[name] = ent
+    dom_algo = algo.get(dom, 0) / launches_per_step
+    achieved = dom_algo / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms > 0 else 0.0
+    step_algo = sum(algo[name] for name in per_kernel if name in algo)
+    step_traffic = sum(traffic.values()) if traffic else None
+    limiter = None
+    lim = ROOT / "profiles" / "r02_limiters.json"
+    if lim.exists():
         try:
-            roofline["traffic"] = json.loads(tr.read_text()).get(dom)
+            limiter = json.loads(lim.read_text()).get(dom)
         except Exception:
-            pass
+            limiter = None
+    # the DRAM-LSD pipeline moves ~195 B/base at k=31 (W+P = 12, R = 8); its HBM-bound time is what this
+    # figure compares the measured step with (> 1 = faster than that pipeline could run at HBM peak, NOT a bandwidth)
+    survey_bytes = 4.1 * n_bases + B_s + N_k * 12 * (1 + 2 * 8 + 1) + n_entries * 12
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": (traffic.get(dom) / launches_per_step) if dom in traffic else None,
+                "traffic_source": traffic_src, "peak_kind": peak_kind,
+                "algorithmic_bytes_per_launch": dom_algo, "ms_per_launch": per_launch_ms,
+                "kernel_share_of_step": dom_ms / total_kernel_ms,
+                "limiter": limiter or {"kind": "issue", "note": "see profiles/ (ncu --set full): the path is issue/latency-bound, DRAM < 5 % of peak"},
+                "step": {"algorithmic_bytes": int(step_algo), "traffic_bytes": int(step_traffic) if step_traffic else None,
+                         "ms": ms_per_step, "achieved": step_algo / (ms_per_step * 1e-3) / 1e9,
+                         "frac": step_algo / (ms_per_step * 1e-3) / 1e9 / peak,
+                         "traffic_frac": (step_traffic / (ms_per_step * 1e-3) / 1e9 / peak) if step_traffic else None},
+                "per_kernel": per_kernel,
+                "survey_model_equiv_frac": survey_bytes / (ms_per_step * 1e-3) / 1e9 / peak,
+                "survey_model": "SURVEY 8(d) DRAM-LSD pipeline bytes (W+P=12, R=8) / measured step time / peak; not a bandwidth"}
+
+    # ---- N > 1: parity of sampled owned units (device path and host path) against the oracle on the union of all reads
+    parity = None
+    if world > 1 and wl == "c2" and args.parity_units > 0:
+        parity = multi_gpu_parity(args, ctx, owner, rank, world, b1, b2, n_reads, step_device, step_host if h_data is not None else None)
 
     line = {
         "metric": "build Gbases/s (bucketing+k-mer merge)", "value": value, "unit": "Gbases/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": f"{wl.upper()} per GPU: {n_reads} x {READ_LEN} bp reads (30x of {genome_len} bp genome, {seed_note}), "
-                               f"k={K} m={M} -s {S} seq-hash, buckets {1 << b1}(+1) x {1 << b2}",
+        "config": {"workload": workload_string(wl, n_reads, world, b1, b2),
                    "l2": "flushed (256 MB write) between timed steps", "reads_per_gpu": n_reads,
                    "parallelism": f"bucket-owner x{world}" if world > 1 else "single GPU",
                    "exchange": {"peer": "k_peer_push over NVLink peer memory (CUDA IPC)", "nccl": "NCCL all_to_all_single",
@@ -396,13 +550,14 @@ def run_ours(args):
         "roofline": roofline,
         "kernels_ms_per_step": {k: round(v[0] / n_prof, 4) for k, v in kt.items()},
         "exchange": exchange,
+        "parity": parity,
         "counts": {"bases_per_gpu": n_bases, "superkmers": int(st.n_superkmers), "kmer_records": int(st.n_kmers),
                    "unique": int(unique), "kept": int(n_entries)},
     }
     if rank == 0 and world == 1 and wl == "c2" and not args.no_cpu_baseline:
         from oracle import oracle as O
 
-        sr = args.sample_reads
+        sr = args.sample_reads or READS_PER_GPU
         cdata, coff = make_reads(0, 1, sr)
         creads = O.Reads(cdata, coff)
         O.pipeline(creads, K, M, b1, b2, S, n_threads=os.cpu_count() or 1)   # warm-up (page faults, thread pool)
@@ -433,7 +588,9 @@ def main():
                     help="c2 = BASELINE configs[1] (the bench line); c4 = a slice of configs[3] (human-scale shape, big merge units)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer pass (large c4 slices)")
     ap.add_argument("--reads-per-push", type=int, default=4_000_000, help="c4: reads per device push (one bucket chunk each)")
-    ap.add_argument("--sample-reads", type=int, default=READS_PER_GPU, help="reads per CPU pass (default: the whole C2 batch)")
+    ap.add_argument("--sample-reads", type=int, default=0, help="reads per CPU pass (default: the whole workload / the whole C2 batch)")
+    ap.add_argument("--no-traffic-pass", action="store_true", help="skip the ncu DRAM-traffic pass (roofline.traffic from profiles/)")
+    ap.add_argument("--parity-units", type=int, default=16, help="N > 1: sampled owned units per rank checked against the oracle")
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="CPU baseline: repeat passes until this much CPU wall time")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--b1", type=int, default=None, help="experiment: override buckets_count_log")

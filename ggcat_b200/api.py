@@ -120,6 +120,10 @@ class KmerTable:
         u = unit - self.first_unit
         return slice(int(self.unit_offsets[u]), int(self.unit_offsets[u + 1]))
 
+    def unit_slice_at(self, i: int) -> slice:
+        """Slice of the i-th unit of a table read with read_device_table(units=[...])."""
+        return slice(int(self.unit_offsets[i]), int(self.unit_offsets[i + 1]))
+
 
 class GGCATB200:
     """One context = one build on one GPU (the reference's per-run global state)."""
@@ -243,6 +247,53 @@ class GGCATB200:
         _check(self._lib.ggcat_b200_merge_bucket_range_device(self._h, first_bucket, n_buckets, C.byref(a), C.byref(b),
                                                               C.byref(c)))
         return a.value, b.value, c.value
+
+    def device_table(self) -> "_lib.TableC":
+        """The table left in HBM by the last merge_bucket_range_device (every pointer is device memory)."""
+        t = _lib.TableC()
+        _check(self._lib.ggcat_b200_device_table(self._h, C.byref(t)))
+        return t
+
+    def _dev_bytes(self, addr: int, nbytes: int) -> np.ndarray:
+        """Host copy of `nbytes` of device memory at `addr` (verification helpers only)."""
+        import torch
+
+        if not nbytes or not addr:
+            return np.zeros(0, np.uint8)
+
+        class _V:
+            __cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (addr, False), "version": 2}
+
+        return torch.as_tensor(_V(), device=torch.device("cuda", self.params.device)).cpu().numpy()
+
+    def read_device_table(self, units: Optional[Sequence[int]] = None) -> KmerTable:
+        """Host copy of device_table() -- the whole table, or only the slices of the given (absolute) unit ids, laid out
+        back to back in the order given (unit_offsets then has len(units)+1 entries; use .unit_slice_at(i)).
+        Verification / tests; a device-side consumer reads the pointers of device_table() directly."""
+        t = self.device_table()
+        ptr = lambda p: C.cast(p, C.c_void_p).value or 0
+        nu = int(t.n_units)
+        uo = self._dev_bytes(ptr(t.unit_offsets), (nu + 1) * 8).view(np.uint64)
+        wide = bool(t.keys_hi)
+        if units is None:
+            ne = int(t.n_entries)
+            keys = self._dev_bytes(ptr(t.keys_lo), ne * 8).view(np.uint64)
+            hi = self._dev_bytes(ptr(t.keys_hi), ne * 8).view(np.uint64) if wide else None
+            cf = self._dev_bytes(ptr(t.count_flags), ne * 4).view(np.uint32)
+            return KmerTable(keys, hi, cf, int(t.first_unit), uo, int(t.total_kmers), int(t.unique_kmers))
+        ks, hs, cs, offs = [], [], [], [0]
+        for u in units:
+            a, b = int(uo[u - int(t.first_unit)]), int(uo[u - int(t.first_unit) + 1])
+            ks.append(self._dev_bytes(ptr(t.keys_lo) + a * 8, (b - a) * 8).view(np.uint64))
+            if wide:
+                hs.append(self._dev_bytes(ptr(t.keys_hi) + a * 8, (b - a) * 8).view(np.uint64))
+            cs.append(self._dev_bytes(ptr(t.count_flags) + a * 4, (b - a) * 4).view(np.uint32))
+            offs.append(offs[-1] + (b - a))
+        cat = lambda xs, dt: np.concatenate(xs) if xs else np.zeros(0, dt)
+        tab = KmerTable(cat(ks, np.uint64), cat(hs, np.uint64) if wide else None, cat(cs, np.uint32), 0,
+                        np.array(offs, np.uint64), int(t.total_kmers), int(t.unique_kmers))
+        tab.n_entries_total = int(t.n_entries)
+        return tab
 
     # -- multi-GPU plumbing
     def n_chunks(self) -> int:

@@ -107,6 +107,8 @@ struct FinalTable {
     const uint64_t *color_off = nullptr;     // n_entries (+1 implied = n_colors)
     const uint32_t *colors = nullptr;
     uint64_t n_entries = 0, n_colors = 0;
+    uint32_t first_unit = 0, n_units = 0;    // unit range of the merge that produced it
+    uint64_t total_kmers = 0, unique_kmers = 0;
 };
 
 // NVLink peer exchange (peer.cuh): this rank's receive arena, the peers' arenas mapped through CUDA IPC, staging.
@@ -1145,6 +1147,7 @@ int32_t ggcat_b200_reset(ggcat_b200_ctx *c) {
         else { ch->release(); delete ch; }
     }
     c->chunks.clear();
+    c->fin = FinalTable();
     c->finished = false;
     memset(&c->stats, 0, sizeof(c->stats));
     return 0;
@@ -1397,9 +1400,24 @@ int32_t ggcat_b200_merge_bucket_range_device(ggcat_b200_ctx *c, uint32_t first_b
         ub += pr.second << P.b2;
     }
     c->final_hint = eb;
+    c->fin.first_unit = first_bucket << P.b2; c->fin.n_units = n_buckets << P.b2;
+    c->fin.total_kmers = tk; c->fin.unique_kmers = uq;
     if (n_entries) *n_entries = eb;
     if (unique_kmers) *unique_kmers = uq;
     if (total_kmers) *total_kmers = tk;
+    return 0;
+}
+
+int32_t ggcat_b200_device_table(ggcat_b200_ctx *c, ggcat_b200_table *out) {
+    TRY(check_ctx(c));
+    if (!out) return set_err(GGCAT_B200_ERR_INVALID, "null table");
+    memset(out, 0, sizeof(*out));
+    const FinalTable &f = c->fin;
+    if (!f.unit_off || f.n_units == 0) return set_err(GGCAT_B200_ERR_STATE, "device_table before merge_bucket_range_device");
+    out->n_entries = f.n_entries; out->keys_lo = f.keys_lo; out->keys_hi = f.keys_hi; out->count_flags = f.cf;
+    out->first_unit = f.first_unit; out->n_units = f.n_units; out->unit_offsets = f.unit_off;
+    out->color_offsets = f.color_off; out->colors = f.colors;   // color_offsets has n_entries entries on the device (the end is n_colors)
+    out->total_kmers = f.total_kmers; out->unique_kmers = f.unique_kmers;
     return 0;
 }
 

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define GGCAT_B200_ABI_VERSION 4
+#define GGCAT_B200_ABI_VERSION 5
 
 typedef enum {
     GGCAT_B200_OK = 0,
@@ -149,6 +149,11 @@ int32_t ggcat_b200_release_table(ggcat_b200_ctx *ctx, ggcat_b200_table *table);
  * Returns entry count and distinct/total k-mer counters. */
 int32_t ggcat_b200_merge_bucket_range_device(ggcat_b200_ctx *ctx, uint32_t first_bucket, uint32_t n_buckets,
                                              uint64_t *n_entries, uint64_t *unique_kmers, uint64_t *total_kmers);
+
+/* The table left in HBM by the last merge_bucket_range_device, in the layout of ggcat_b200_table: every pointer is
+ * DEVICE memory owned by the context, valid until the next merge / reset (opaque is NULL; nothing to release).  This is
+ * what a device-side consumer (partial-unitig construction) or a verifier reads without a host copy. */
+int32_t ggcat_b200_device_table(ggcat_b200_ctx *ctx, ggcat_b200_table *out);
 
 /* Drops all bucket chunks so the context can be reused for another build. */
 int32_t ggcat_b200_reset(ggcat_b200_ctx *ctx);

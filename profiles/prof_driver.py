@@ -1,5 +1,7 @@
 """Minimal driver for ncu captures: a few C2 steps (phase 1 + phase 2) with inputs resident in HBM.
-Usage (under gpurun):  ncu ... python profiles/prof_driver.py [steps] [reads]"""
+Usage (under gpurun):  ncu ... python profiles/prof_driver.py [steps] [reads]
+The last step is bracketed by cudaProfilerStart/Stop, so `ncu --profile-from-start off` captures exactly one warm step
+(bench.py's traffic pass does that)."""
 import sys
 from pathlib import Path
 
@@ -20,9 +22,13 @@ d_data = torch.from_numpy(data).cuda()
 d_off = torch.from_numpy(offsets.view(np.int64)).cuda()
 torch.cuda.synchronize()
 for i in range(steps):
+    if i == steps - 1:
+        torch.cuda.profiler.start()   # ncu --profile-from-start off: only the last (warm) step is captured
     ctx.reset()
     ctx.push_reads_device(d_data.data_ptr(), d_off.data_ptr(), n_reads, int(data.size))
     st = ctx.finish_bucketing()
     res = ctx.merge_bucket_range_device(0, (1 << b1) + 1)
+torch.cuda.synchronize()
+torch.cuda.profiler.stop()
 print("steps", steps, "superkmers", st.n_superkmers, "kmers", st.n_kmers, "kept/unique/total", res)
 ctx.close()

@@ -29,7 +29,7 @@ def test_header_symbols_exported(lib):
     assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/ggcat_b200.h but not exported"
-    assert lib.ggcat_b200_abi_version() == 4
+    assert lib.ggcat_b200_abi_version() == int(re.search(r"#define GGCAT_B200_ABI_VERSION (\d+)", header).group(1))
 
 
 def test_struct_layouts():
