@@ -317,3 +317,114 @@ def test_unitigs_per_unit_join_equals_global(k, m, b1, b2, s, fo):
     assert np.array_equal(A["lengths"], B["lengths"])
     assert np.array_equal(A["kmers_lo"], nv["key_lo"]) and np.array_equal(A["kmers_hi"], nv["key_hi"])
     assert np.array_equal(B["kmers_lo"], nv["key_lo"])
+
+
+# ------------------------------------------------------------------ the reference's own test harnesses, re-run on the oracle
+class Pcg32:
+    """PCG XSH-RR 64/32 with a selectable stream (O'Neill 2014), seeded the way rand_core 0.6.4 `seed_from_u64` fills a
+    16-byte seed (Cargo.lock:2373-2376) and the PCG reference implementation consumes it (state, sequence).
+    The reference's harness uses `pcg_rand::Pcg32::seed_from_u64(773 + k)` (crates/hashes/src/lib.rs:206-210,269);
+    pcg_rand 0.13.0 (Cargo.lock:2126-2129) is not vendored under /root/reference, so its exact seed layout cannot be
+    confirmed here -- every check below is a PROPERTY that holds for any base sequence, the stream only picks the sample."""
+    MUL = 6364136223846793005
+    M64 = (1 << 64) - 1
+
+    def __init__(self, seed_u64: int):
+        st = seed_u64 & self.M64
+        words = []
+        for _ in range(4):   # rand_core::SeedableRng::seed_from_u64: PCG32 outputs fill the seed, 4 bytes at a time
+            st = (st * self.MUL + 11634580027462260723) & self.M64
+            x = (((st >> 18) ^ st) >> 27) & 0xFFFFFFFF
+            rot = st >> 59
+            words.append(((x >> rot) | (x << ((32 - rot) & 31))) & 0xFFFFFFFF)
+        initstate = words[0] | (words[1] << 32)
+        initseq = words[2] | (words[3] << 32)
+        self.inc = ((initseq << 1) | 1) & self.M64
+        self.state = 0
+        self.next_u32()
+        self.state = (self.state + initstate) & self.M64
+        self.next_u32()
+
+    def next_u32(self) -> int:
+        old = self.state
+        self.state = (old * self.MUL + self.inc) & self.M64
+        x = (((old >> 18) ^ old) >> 27) & 0xFFFFFFFF
+        rot = old >> 59
+        return ((x >> rot) | (x << ((32 - rot) & 31))) & 0xFFFFFFFF
+
+
+def _harness_bases(k: int) -> bytes:
+    """generate_bases(k * 10, 773 + k) of crates/hashes/src/lib.rs:238-247 (decompress_base: 0123 -> ACTG)."""
+    rng = Pcg32(773 + k)
+    return bytes(b"ACTG"[rng.next_u32() % 4] for _ in range(k * 10))
+
+
+def _check_hash_properties(hashes_of, k: int, canonical: bool, wide_enough: bool):
+    """The stream-independent checks of test_hash_function (crates/hashes/src/lib.rs:265-349): no collisions between
+    different k-mers (>= 64-bit hashes), hash(x || x) repeats with period |x|, canonical symmetry."""
+    s = _harness_bases(k)
+    h = hashes_of(s)
+    n = len(s) - k + 1
+    assert len(h) == n
+    if wide_enough:
+        seen = {}
+        for i, v in enumerate(h):
+            km = s[i:i + k]
+            c = min(km, revcomp(km)) if canonical else km
+            assert seen.setdefault(v, c) == c, f"collision at k={k}"
+    d = hashes_of(s + s)
+    assert d[:n] == d[n + k - 1:], f"double-hash test failed at k={k}"
+    if canonical:
+        assert h == hashes_of(revcomp(s))[::-1], f"canonical test failed at k={k}"
+
+
+@pytest.mark.parametrize("m", [32, 33, 47, 64, 100, 255, 511])      # cn_nthash.rs:245-248 runs 32..512
+def test_reference_hash_harness_nthash(m):
+    def hashes_of(s):
+        fw, rc = O.nthash(s, m)
+        return [int(x) for x in np.minimum(fw, rc)]      # to_unextendable (cn_nthash.rs:96-99, before the << 1)
+
+    _check_hash_properties(hashes_of, m, canonical=True, wide_enough=True)
+
+
+@pytest.mark.parametrize("k,ht,fo", [(k, O.HASH_SEQ, False) for k in (2, 3, 15, 16, 31, 32, 33, 47, 63)]      # cn_seqhash_base.rs:246-252
+                         + [(k, O.HASH_SEQ, True) for k in (2, 31, 32, 63)]                                    # fw_seqhash_base.rs:224-230
+                         + [(k, O.HASH_RK128, False) for k in (2, 17, 31, 63, 64, 65, 255, 1000, 4095)]        # cn_rkhash_base.rs:303-306
+                         + [(k, O.HASH_RK128, True) for k in (2, 63, 300)])                                    # fw_rkhash_base.rs:250-253
+def test_reference_hash_harness_kmer_hashes(k, ht, fo):
+    def hashes_of(s):
+        lo, hi, _ = O.kmer_hashes(s, k, ht, forward_only=fo)
+        return [(int(a), int(b)) for a, b in zip(lo, hi)]
+
+    # seq-hash of tiny k is narrower than 64 bits in the reference too (u16 / u32): collisions impossible anyway (invertible)
+    _check_hash_properties(hashes_of, k, canonical=not fo, wide_enough=True)
+
+
+@pytest.mark.parametrize("inject_duplicates", [False, True])
+def test_reference_minqueue_invariant_10m(inject_duplicates):
+    """crates/hashes/src/rolling/minqueue_testing.rs:261-365 (minqueue_test; stale against today's callback arity, so it
+    is restated here): 10 M random u64 with bit 0 set, window 13 -- for every window the reported minimum equals the true
+    window minimum (unique-flag masked) and the unique flag is cleared iff the minimum occurs more than once.
+    The second variant adds the duplicates the reference test has commented out (`117 << 32 | 1` pushed with p = 0.5), so
+    that the cleared-flag branch is exercised too.  (numpy's PCG64 stream, seed 2: the reference's pcg_rand::Pcg64 is
+    not vendored; the invariant does not depend on the stream.)"""
+    SIZE, W = 10_000_000, 13
+    rng = np.random.Generator(np.random.PCG64(2))
+    items = rng.integers(0, 1 << 64, SIZE, dtype=np.uint64) | np.uint64(1)
+    if inject_duplicates:
+        dup = rng.random(SIZE) < 0.5
+        items = np.where(dup, np.uint64((117 << 32) | 1), items)
+    items = items[::-1].copy()
+    ov, _ = O.window_minima(items, W)
+    n = SIZE - W + 1
+    assert len(ov) == n
+    mask = ~np.uint64(1)
+    step = 1 << 20
+    for a in range(0, n, step):
+        b = min(n, a + step)
+        win = np.lib.stride_tricks.sliding_window_view(items[a:b + W - 1], W)
+        true_min = win.min(axis=1)
+        got = ov[a:b]
+        assert np.array_equal(got & mask, true_min & mask)
+        count = ((win & mask) == (got & mask)[:, None]).sum(axis=1)
+        assert np.array_equal(count > 1, (got & np.uint64(1)) == 0)
