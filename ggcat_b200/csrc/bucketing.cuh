@@ -389,15 +389,18 @@ __global__ void __launch_bounds__(256)
 k_emit(const uint64_t *__restrict__ ent, const uint32_t *__restrict__ tile_cnt, const uint32_t *__restrict__ tile_sbase,
        uint32_t n_tiles, DevParams P, uint4 *__restrict__ tmp, uint32_t *__restrict__ tmp_color,
        const uint64_t *__restrict__ offsets, uint64_t n_reads, uint64_t off0, const uint32_t *__restrict__ colors,
-       uint32_t *__restrict__ unit_cnt, uint32_t *__restrict__ unit_words, uint32_t *__restrict__ unit_kmers) {
+       uint32_t *__restrict__ unit_cnt, uint32_t *__restrict__ unit_words, uint32_t *__restrict__ unit_kmers,
+       uint32_t *__restrict__ seg_count) {
     const uint32_t tile = blockIdx.x;
     const uint32_t cnt = tile_cnt[tile];
     const uint32_t posmask = (1u << ENT_POS_BITS) - 1;
+    uint32_t my_first = 0;   // N-free segments of length >= k that start in this tile (SequencesSplitter::valid_bases bookkeeping)
     for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) {
         const uint64_t e = ent[(uint64_t)tile * WIN_T + i];
         if (!(e & ENT_S)) continue;
         const uint32_t pos = tile * WIN_T + (uint32_t)(e & posmask);
         const bool first = e & ENT_FIRST;
+        my_first += first ? 1u : 0u;
         uint32_t end;
         bool last;
         if (e & ENT_E) {
@@ -439,6 +442,10 @@ k_emit(const uint64_t *__restrict__ ent, const uint32_t *__restrict__ tile_cnt, 
         atomicAdd(&unit_words[unit], (len + 15u) >> 4);
         atomicAdd(&unit_kmers[unit], len - P.k + 1u);
     }
+    __syncwarp();
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) my_first += __shfl_xor_sync(0xffffffffu, my_first, o);
+    if ((threadIdx.x & 31u) == 0 && my_first) atomicAdd(seg_count, my_first);
 }
 
 // ------------------------------------------------------------------------------------------------

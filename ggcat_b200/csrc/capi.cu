@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -64,7 +65,7 @@ struct Chunk {
     const uint32_t *d_unit_cnt = nullptr, *d_unit_off = nullptr, *d_unit_words = nullptr, *d_unit_woff = nullptr,
                    *d_unit_kmers = nullptr;
     uint32_t first_unit = 0, n_units = 0, word_bias = 0;
-    uint64_t n_sk = 0, n_words = 0, n_kmers = 0, n_bases = 0;
+    uint64_t n_sk = 0, n_words = 0, n_kmers = 0, n_bases = 0, n_segments = 0;
     std::vector<uint32_t> h_cnt, h_off, h_words, h_woff, h_kmers;  // host mirrors (after finish / import)
     uint32_t *h_pin = nullptr; size_t h_pin_cap = 0;   // pinned landing area of the per-unit counts (cnt | words | kmers),
     bool mirror_queued = false;                        // filled by copies queued right behind k_emit on the copy stream
@@ -127,6 +128,7 @@ struct PeerState {
 }  // namespace
 
 struct ggcat_b200_ctx {
+    std::mutex mu;   // serialises the entry points that change the context (push_reads may be called from many host threads)
     ggcat_b200_params params;
     DevParams P;
     int device = 0;
@@ -296,18 +298,18 @@ int32_t bucket_batch_device(ggcat_b200_ctx *c, const uint8_t *d_data, const uint
         k_emit<<<n_tiles, 256, 0, st>>>(c->ent.as<uint64_t>(), c->tile_cnt.as<uint32_t>(), c->tile_sbase.as<uint32_t>(),
                                         n_tiles, P, c->tmp.as<uint4>(), c->tmp_color.as<uint32_t>(), d_offsets, n_reads, off0,
                                         d_colors, ch->unit_cnt.as<uint32_t>(), ch->unit_words.as<uint32_t>(),
-                                        ch->unit_kmers.as<uint32_t>());
+                                        ch->unit_kmers.as<uint32_t>(), ch->unit_cnt.as<uint32_t>() + P.n_units /* spare slot: segments */);
     }
     // host mirror of the per-unit counts: they are final after k_emit, so they travel on the copy stream while
     // k_scatter runs; finish_bucketing waits for this event only, and the host side of the merge (unit classification,
     // uploads) overlaps the tail of phase 1
     if (c->copy_stream) {
         const size_t nu = P.n_units;
-        if (ch->h_pin_cap < 3 * nu) {
+        if (ch->h_pin_cap < 3 * nu + 1) {
             if (ch->h_pin) cudaFreeHost(ch->h_pin);
             ch->h_pin = nullptr; ch->h_pin_cap = 0;
-            CU(cudaHostAlloc(reinterpret_cast<void **>(&ch->h_pin), 3 * nu * 4, cudaHostAllocDefault));
-            ch->h_pin_cap = 3 * nu;
+            CU(cudaHostAlloc(reinterpret_cast<void **>(&ch->h_pin), (3 * nu + 1) * 4, cudaHostAllocDefault));
+            ch->h_pin_cap = 3 * nu + 1;
         }
         if (!ch->ev_emit) { CU(cudaEventCreateWithFlags(&ch->ev_emit, cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&ch->ev_mirror, cudaEventDisableTiming)); }
         CU(cudaEventRecord(ch->ev_emit, st));
@@ -315,6 +317,7 @@ int32_t bucket_batch_device(ggcat_b200_ctx *c, const uint8_t *d_data, const uint
         CU(cudaMemcpyAsync(ch->h_pin, ch->unit_cnt.p, nu * 4, cudaMemcpyDeviceToHost, c->copy_stream));
         CU(cudaMemcpyAsync(ch->h_pin + nu, ch->unit_words.p, nu * 4, cudaMemcpyDeviceToHost, c->copy_stream));
         CU(cudaMemcpyAsync(ch->h_pin + 2 * nu, ch->unit_kmers.p, nu * 4, cudaMemcpyDeviceToHost, c->copy_stream));
+        CU(cudaMemcpyAsync(ch->h_pin + 3 * nu, ch->unit_cnt.as<uint32_t>() + nu, 4, cudaMemcpyDeviceToHost, c->copy_stream));   // segments
         CU(cudaEventRecord(ch->ev_mirror, c->copy_stream));
         ch->mirror_queued = true;
     }
@@ -359,11 +362,15 @@ int32_t mirror_chunk(ggcat_b200_ctx *c, Chunk *ch) {
         memcpy(ch->h_cnt.data(), ch->h_pin, nu * 4);
         memcpy(ch->h_words.data(), ch->h_pin + nu, nu * 4);
         memcpy(ch->h_kmers.data(), ch->h_pin + 2 * nu, nu * 4);
+        ch->n_segments = ch->h_pin[3 * nu];
     } else {
         CU(cudaMemcpyAsync(ch->h_cnt.data(), ch->d_unit_cnt, nu * 4, cudaMemcpyDeviceToHost, c->stream));
         CU(cudaMemcpyAsync(ch->h_words.data(), ch->d_unit_words, nu * 4, cudaMemcpyDeviceToHost, c->stream));
         CU(cudaMemcpyAsync(ch->h_kmers.data(), ch->d_unit_kmers, nu * 4, cudaMemcpyDeviceToHost, c->stream));
+        uint32_t nseg = 0;
+        if (!ch->imported) CU(cudaMemcpyAsync(&nseg, ch->d_unit_cnt + nu, 4, cudaMemcpyDeviceToHost, c->stream));
         CU(cudaStreamSynchronize(c->stream));
+        ch->n_segments = nseg;
     }
     uint64_t a = 0, b = 0, km = 0;
     for (size_t u = 0; u < nu; u++) {
@@ -1141,6 +1148,7 @@ int32_t ggcat_b200_create(const ggcat_b200_params *params, ggcat_b200_ctx **out)
 
 int32_t ggcat_b200_reset(ggcat_b200_ctx *c) {
     TRY(check_ctx(c));
+    std::lock_guard<std::mutex> lock__(c->mu);
     cudaStreamSynchronize(c->stream);
     for (Chunk *ch : c->chunks) {
         if (!ch->imported) c->chunk_pool.push_back(ch);  // keep the device buffers for the next build
@@ -1194,6 +1202,7 @@ void ggcat_b200_destroy(ggcat_b200_ctx *c) {
 int32_t ggcat_b200_push_reads(ggcat_b200_ctx *c, const uint8_t *data, const uint64_t *offsets, uint64_t n_reads,
                               const uint32_t *colors) {
     TRY(check_ctx(c));
+    std::lock_guard<std::mutex> lock__(c->mu);
     if (c->finished) return set_err(GGCAT_B200_ERR_STATE, "push_reads after finish_bucketing");
     if (n_reads == 0) return 0;
     if (!data || !offsets) return set_err(GGCAT_B200_ERR_INVALID, "null input");
@@ -1266,6 +1275,7 @@ int32_t ggcat_b200_push_reads(ggcat_b200_ctx *c, const uint8_t *data, const uint
 int32_t ggcat_b200_push_reads_device(ggcat_b200_ctx *c, const uint8_t *d_data, const uint64_t *d_offsets, uint64_t n_reads,
                                      uint64_t n_bytes, const uint32_t *d_colors) {
     TRY(check_ctx(c));
+    std::lock_guard<std::mutex> lock__(c->mu);
     if (c->finished) return set_err(GGCAT_B200_ERR_STATE, "push_reads after finish_bucketing");
     if (n_reads == 0) return 0;
     if (!d_data || !d_offsets) return set_err(GGCAT_B200_ERR_INVALID, "null input");
@@ -1275,18 +1285,21 @@ int32_t ggcat_b200_push_reads_device(ggcat_b200_ctx *c, const uint8_t *d_data, c
 
 int32_t ggcat_b200_finish_bucketing(ggcat_b200_ctx *c, ggcat_b200_bucket_stats *stats) {
     TRY(check_ctx(c));
+    std::lock_guard<std::mutex> lock__(c->mu);
     // no stream synchronisation here: the per-unit counts of every chunk arrive on the copy stream right after its
     // k_emit, so this returns while the last k_scatter is still running; everything that follows is stream-ordered
     // (ggcat_b200_synchronize() is there for callers that touch chunk buffers from another stream)
-    uint64_t sk = 0, km = 0, words = 0;
+    uint64_t sk = 0, km = 0, words = 0, segs = 0;
     for (Chunk *ch : c->chunks) {
         TRY(mirror_chunk(c, ch));
-        sk += ch->n_sk; km += ch->n_kmers; words += ch->n_words;
+        sk += ch->n_sk; km += ch->n_kmers; words += ch->n_words; segs += ch->n_segments;
     }
     c->stats.n_superkmers = sk; c->stats.n_kmers = km; c->stats.payload_words = words;
     c->stats.n_buckets = (1u << c->P.b1) + 1; c->stats.n_units = c->P.n_units;
-    // every k-mer occurrence is stored once, boundary k-mers once per side: valid bases follow
-    c->stats.valid_bases = 0;  // filled by callers that need it from per-chunk data (not tracked on device)
+    // SequencesSplitter::valid_bases (crates/minimizer_bucketing/src/sequences_splitter.rs:15-40): bases of the N-free
+    // segments of length >= k.  A segment of L bases split into n super-k-mers (consecutive ones overlap by k bases)
+    // stores (L - k + 1) + (n - 1) k-mers, so  sum L = k-mers - super-k-mers + segments * k.
+    c->stats.valid_bases = km - sk + segs * (uint64_t)c->P.k;
     c->finished = true;
     if (stats) *stats = c->stats;
     return 0;
@@ -1294,6 +1307,7 @@ int32_t ggcat_b200_finish_bucketing(ggcat_b200_ctx *c, ggcat_b200_bucket_stats *
 
 int32_t ggcat_b200_unit_sizes(ggcat_b200_ctx *c, uint64_t *n_superkmers, uint64_t *n_kmers) {
     TRY(check_ctx(c));
+    std::lock_guard<std::mutex> lock__(c->mu);
     if (!c->finished) return set_err(GGCAT_B200_ERR_STATE, "unit_sizes before finish_bucketing");
     for (uint32_t u = 0; u < c->P.n_units; u++) {
         uint64_t a = 0, b = 0;
@@ -1308,6 +1322,7 @@ int32_t ggcat_b200_unit_sizes(ggcat_b200_ctx *c, uint64_t *n_superkmers, uint64_
 int32_t ggcat_b200_dump_superkmers(ggcat_b200_ctx *c, uint32_t bucket, ggcat_b200_superkmer *out, uint64_t cap, uint8_t *payload,
                                    uint64_t payload_cap, uint64_t *n_out, uint64_t *payload_bytes) {
     TRY(check_ctx(c));
+    std::lock_guard<std::mutex> lock__(c->mu);
     if (!c->finished) return set_err(GGCAT_B200_ERR_STATE, "dump before finish_bucketing");
     const DevParams &P = c->P;
     if (bucket > (1u << P.b1)) return set_err(GGCAT_B200_ERR_INVALID, "bucket %u out of range", bucket);
@@ -1358,6 +1373,7 @@ int32_t ggcat_b200_dump_superkmers(ggcat_b200_ctx *c, uint32_t bucket, ggcat_b20
 int32_t ggcat_b200_merge_bucket_range_device(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_buckets, uint64_t *n_entries,
                                              uint64_t *unique_kmers, uint64_t *total_kmers) {
     TRY(check_ctx(c));
+    std::lock_guard<std::mutex> lock__(c->mu);
     if (!c->finished) return set_err(GGCAT_B200_ERR_STATE, "merge before finish_bucketing");
     const DevParams &P = c->P;
     const uint32_t nb_total = (1u << P.b1) + 1;
@@ -1410,6 +1426,7 @@ int32_t ggcat_b200_merge_bucket_range_device(ggcat_b200_ctx *c, uint32_t first_b
 
 int32_t ggcat_b200_device_table(ggcat_b200_ctx *c, ggcat_b200_table *out) {
     TRY(check_ctx(c));
+    std::lock_guard<std::mutex> lock__(c->mu);
     if (!out) return set_err(GGCAT_B200_ERR_INVALID, "null table");
     memset(out, 0, sizeof(*out));
     const FinalTable &f = c->fin;
@@ -1441,6 +1458,7 @@ static int32_t host_table_reserve(ggcat_b200_ctx *c, HostTable *t, uint64_t need
 
 int32_t ggcat_b200_merge_bucket_range(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_buckets, ggcat_b200_table *out) {
     TRY(check_ctx(c));
+    std::lock_guard<std::mutex> lock__(c->mu);
     if (!out) return set_err(GGCAT_B200_ERR_INVALID, "null table");
     memset(out, 0, sizeof(*out));
     if (!c->finished) return set_err(GGCAT_B200_ERR_STATE, "merge before finish_bucketing");
@@ -1500,9 +1518,10 @@ int32_t ggcat_b200_merge_bucket_range(ggcat_b200_ctx *c, uint32_t first_bucket, 
             if (rc) return fail(rc);
             if (ne) {  // the part is complete on the compute stream (synchronised): copy it out while the next part merges
                 const FinalTable &f = c->fin;
-                CU(cudaMemcpyAsync(t->keys + eb, f.keys_lo + eb, ne * 8, cudaMemcpyDeviceToHost, c->copy_stream));
-                CU(cudaMemcpyAsync(t->cf + eb, f.cf + eb, ne * 4, cudaMemcpyDeviceToHost, c->copy_stream));
-                if (wide) CU(cudaMemcpyAsync(t->keys_hi + eb, f.keys_hi + eb, ne * 8, cudaMemcpyDeviceToHost, c->copy_stream));
+                cudaError_t e1 = cudaMemcpyAsync(t->keys + eb, f.keys_lo + eb, ne * 8, cudaMemcpyDeviceToHost, c->copy_stream);
+                if (e1 == cudaSuccess) e1 = cudaMemcpyAsync(t->cf + eb, f.cf + eb, ne * 4, cudaMemcpyDeviceToHost, c->copy_stream);
+                if (e1 == cudaSuccess && wide) e1 = cudaMemcpyAsync(t->keys_hi + eb, f.keys_hi + eb, ne * 8, cudaMemcpyDeviceToHost, c->copy_stream);
+                if (e1 != cudaSuccess) return fail(set_err(GGCAT_B200_ERR_CUDA, "table copy failed: %s", cudaGetErrorString(e1)));
             }
             eb += ne;
         } else eb = ne;
@@ -1546,6 +1565,7 @@ int32_t ggcat_b200_merge_bucket_range(ggcat_b200_ctx *c, uint32_t first_bucket, 
 
 int32_t ggcat_b200_release_table(ggcat_b200_ctx *c, ggcat_b200_table *table) {
     if (!c || !table) return set_err(GGCAT_B200_ERR_INVALID, "null argument");
+    std::lock_guard<std::mutex> lock__(c->mu);
     if (table->opaque) c->free_tables.push_back(reinterpret_cast<HostTable *>(table->opaque));
     memset(table, 0, sizeof(*table));
     return 0;
@@ -1556,6 +1576,7 @@ uint32_t ggcat_b200_n_chunks(ggcat_b200_ctx *c) { return c ? (uint32_t)c->chunks
 int32_t ggcat_b200_export_chunk_slice(ggcat_b200_ctx *c, uint32_t chunk, uint32_t first_unit, uint32_t n_units,
                                       ggcat_b200_chunk_slice *out) {
     TRY(check_ctx(c));
+    std::lock_guard<std::mutex> lock__(c->mu);
     if (!c->finished) return set_err(GGCAT_B200_ERR_STATE, "export before finish_bucketing");
     if (!out || chunk >= c->chunks.size()) return set_err(GGCAT_B200_ERR_INVALID, "bad chunk index");
     Chunk *ch = c->chunks[chunk];
@@ -1575,6 +1596,7 @@ int32_t ggcat_b200_export_chunk_slice(ggcat_b200_ctx *c, uint32_t chunk, uint32_
 
 int32_t ggcat_b200_import_chunk_slice(ggcat_b200_ctx *c, uint32_t first_unit, uint32_t n_units, const ggcat_b200_chunk_slice *s) {
     TRY(check_ctx(c));
+    std::lock_guard<std::mutex> lock__(c->mu);
     if (!s) return set_err(GGCAT_B200_ERR_INVALID, "null slice");
     if (first_unit + n_units > c->P.n_units) return set_err(GGCAT_B200_ERR_INVALID, "unit range outside 0..%u", c->P.n_units);
     if (s->n_superkmers == 0) return 0;
@@ -1622,6 +1644,7 @@ int32_t ggcat_b200_import_chunk_slice(ggcat_b200_ctx *c, uint32_t first_unit, ui
 
 int32_t ggcat_b200_drop_local_chunks(ggcat_b200_ctx *c) {
     TRY(check_ctx(c));
+    std::lock_guard<std::mutex> lock__(c->mu);
     cudaStreamSynchronize(c->stream);
     std::vector<Chunk *> keep;
     for (Chunk *ch : c->chunks) {
@@ -1651,6 +1674,7 @@ int32_t ggcat_b200_owner_range(uint32_t buckets_count_log, uint32_t rank, uint32
 
 int32_t ggcat_b200_peer_init(ggcat_b200_ctx *c, uint32_t rank, uint32_t world, uint64_t arena_bytes, ggcat_b200_peer_handle *out) {
     TRY(check_ctx(c));
+    std::lock_guard<std::mutex> lock__(c->mu);
     PeerState &ps = c->peer;
     if (ps.inited) return set_err(GGCAT_B200_ERR_STATE, "peer_init called twice");
     if (world == 0 || world > (uint32_t)PEER_MAX_WORLD || rank >= world || world > (1u << c->P.b1))
@@ -1678,6 +1702,7 @@ int32_t ggcat_b200_peer_init(ggcat_b200_ctx *c, uint32_t rank, uint32_t world, u
 
 int32_t ggcat_b200_peer_connect(ggcat_b200_ctx *c, const ggcat_b200_peer_handle *handles) {
     TRY(check_ctx(c));
+    std::lock_guard<std::mutex> lock__(c->mu);
     PeerState &ps = c->peer;
     if (!ps.inited) return set_err(GGCAT_B200_ERR_STATE, "peer_connect before peer_init");
     if (ps.connected) return set_err(GGCAT_B200_ERR_STATE, "peer_connect called twice");
@@ -1700,6 +1725,7 @@ int32_t ggcat_b200_peer_connect(ggcat_b200_ctx *c, const ggcat_b200_peer_handle 
 
 int32_t ggcat_b200_peer_exchange(ggcat_b200_ctx *c) {
     TRY(check_ctx(c));
+    std::lock_guard<std::mutex> lock__(c->mu);
     PeerState &ps = c->peer;
     if (!ps.connected) return set_err(GGCAT_B200_ERR_STATE, "peer_exchange before peer_connect");
     if (!c->finished) return set_err(GGCAT_B200_ERR_STATE, "peer_exchange before finish_bucketing");
@@ -1875,12 +1901,14 @@ int32_t ggcat_b200_synchronize(ggcat_b200_ctx *c) {
 }
 int32_t ggcat_b200_set_timing(ggcat_b200_ctx *c, int32_t enabled) {
     TRY(check_ctx(c));
+    std::lock_guard<std::mutex> lock__(c->mu);
     collect_timings(c);
     c->timing = enabled != 0;
     return 0;
 }
 int32_t ggcat_b200_kernel_times(ggcat_b200_ctx *c, const char **names, float *ms, uint32_t *launches, uint32_t cap, int32_t reset) {
     TRY(check_ctx(c));
+    std::lock_guard<std::mutex> lock__(c->mu);
     collect_timings(c);
     for (uint32_t i = 0; i < (uint32_t)F_COUNT && i < cap; i++) {
         if (names) names[i] = kFamilyNames[i];

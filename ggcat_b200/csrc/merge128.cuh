@@ -80,9 +80,17 @@ __device__ __forceinline__ uint32_t mix128(unsigned long long lo, unsigned long 
 
 // Insert one k-mer occurrence: claim / find the slot with a 128-bit CAS (ATOMS.CAS.128 / ATOMG.CAS.128),
 // then MapEntry::incr_by_and_check + update_flags on the slot word.
-__device__ __forceinline__ void hash_insert128(K128 *K, uint32_t *C, uint32_t mask, u128 key, uint32_t fb) {
+// The all-ones key doubles as the empty-slot sentinel, but it IS a legal key when the key uses all 128 bits (forward-only
+// seq-hash of k = 64: poly-G; colours with k = 48; any rk128 hash): such occurrences are counted in `special`, a
+// MapEntry word beside the table that the scan treats as one more slot.
+__device__ __forceinline__ void hash_insert128(K128 *K, uint32_t *C, uint32_t mask, u128 key, uint32_t fb, uint32_t *special) {
     const K128 want = to_k128(key);
     const K128 empty = K128{EMPTY64, EMPTY64};
+    if (want.lo == EMPTY64 && want.hi == EMPTY64) {
+        atomicAdd(special, 1u);
+        if (fb) atomicOr(special, fb << 30);
+        return;
+    }
     uint32_t slot = mix128(want.lo, want.hi) & mask;
     while (true) {
         const K128 old = atomicCAS(&K[slot], empty, want);
@@ -168,6 +176,7 @@ k_merge_hash128(const ChunkView *__restrict__ chunks, uint32_t n_chunks, const u
     K128 *K = reinterpret_cast<K128 *>(smem_raw);
     uint32_t *C = reinterpret_cast<uint32_t *>(K + TS_STATIC);
     __shared__ uint32_t s_cnt[2];
+    __shared__ uint32_t s_special;         // MapEntry word of the all-ones key (see hash_insert128)
     __shared__ unsigned long long s_base;
     const uint32_t tid = threadIdx.x;
     if (n_work_dev) n_work = min(n_work, *n_work_dev);   // device-side list (big units whose partitions overflowed)
@@ -194,11 +203,12 @@ k_merge_hash128(const ChunkView *__restrict__ chunks, uint32_t n_chunks, const u
         const uint32_t tmask = TS - 1;
         for (uint32_t i = tid; i < TS; i += THREADS) { K[i] = K128{EMPTY64, EMPTY64}; C[i] = 0u; }
         if (tid < 2) s_cnt[tid] = 0;
+        if (tid == 0) s_special = 0;
         __syncthreads();
         if (SRC == SRC_RECORDS) {
             const uint64_t ro = (uint64_t)wi * ps.pcap;
             for (uint32_t i = tid; i < n; i += THREADS)
-                hash_insert128(K, C, tmask, ((u128)ps.rec_hi[ro + i] << 64) | (u128)ps.rec_lo[ro + i], ps.rec_fl[ro + i]);
+                hash_insert128(K, C, tmask, ((u128)ps.rec_hi[ro + i] << 64) | (u128)ps.rec_lo[ro + i], ps.rec_fl[ro + i], &s_special);
         } else {
             for (uint32_t c = 0; c < n_chunks; c++) {
                 const ChunkView cv = chunks[c];
@@ -210,7 +220,7 @@ k_merge_hash128(const ChunkView *__restrict__ chunks, uint32_t n_chunks, const u
                     for_each_kmer128<MODE>(cv.payload + (d.x - cv.word_bias), d.y, (d.z >> 16) & 3u, P.k, P.forward_only, T,
                                            [&](u128 key, uint32_t fb) {
                                                if (MODE == MODE_COLOR) key = (key << 32) | (u128)color;
-                                               hash_insert128(K, C, tmask, key, fb);
+                                               hash_insert128(K, C, tmask, key, fb, &s_special);
                                            });
                 }
             }
@@ -220,6 +230,11 @@ k_merge_hash128(const ChunkView *__restrict__ chunks, uint32_t n_chunks, const u
         //      per-k-mer fold, done after the sort)
         {
             uint32_t my_keep = 0, my_occ = 0;
+            if (tid == 0 && (s_special & 0x3FFFFFFFu)) {   // the all-ones key: one more occupied "slot"
+                const uint32_t cc = s_special, cnt = cc & 0x3FFFFFFFu, fl = cc >> 30;
+                ++my_occ;
+                if (MODE == MODE_COLOR || (cnt >> ((fl == 3u) ? 1 : 0)) >= min_mult) ++my_keep;
+            }
             for (uint32_t i = tid; i < TS; i += THREADS) {
                 const K128 kk = K[i];
                 if (kk.lo == EMPTY64 && kk.hi == EMPTY64) continue;
@@ -260,7 +275,19 @@ k_merge_hash128(const ChunkView *__restrict__ chunks, uint32_t n_chunks, const u
         }
         __syncthreads();
         const unsigned long long gbase = s_base;
-        if (tid == 0) s_cnt[0] = 0;
+        if (tid == 0) {
+            uint32_t first = 0;
+            if ((s_special & 0x3FFFFFFFu) && (SRC == SRC_RECORDS || gbase + S <= out.capacity)) {
+                const uint32_t cc = s_special, cnt = cc & 0x3FFFFFFFu, fl = cc >> 30;
+                const uint32_t mult = cnt >> ((fl == 3u) ? 1 : 0);
+                if (MODE == MODE_COLOR || mult >= min_mult) {
+                    out.keys_lo[gbase] = EMPTY64; out.keys_hi[gbase] = EMPTY64;
+                    out.count_flags[gbase] = MODE == MODE_COLOR ? cc : (mult | (fl << 30));
+                    first = 1;
+                }
+            }
+            s_cnt[0] = first;   // the slots' survivors follow
+        }
         __syncthreads();
         // ---- pass 2: append survivors (arbitrary order inside the unit's range; k_sort_units128 orders them)
         if (SRC == SRC_RECORDS || gbase + S <= out.capacity) {

@@ -85,7 +85,8 @@ typedef struct {
 /* k-mer table of a range of buckets: what HashMapUnitigsExtender holds after add_sequence().
  * Entries are grouped by merge unit (bucket, second_bucket) and sorted ascending by key inside a
  * unit.  Only entries with multiplicity >= min_multiplicity are present.
- *   count_flags = multiplicity (low 30 bits, saturating) | MapEntry flags << 30.
+ *   count_flags = multiplicity (low 30 bits, saturating at 2^30 - 1: the reference's counter is 61-bit,
+ *   crates/structs/src/map_entry.rs:5-10, but -s only needs "at least") | MapEntry flags << 30.
  * All pointers are library-owned pinned host memory, valid until ggcat_b200_release_table(). */
 typedef struct {
     uint64_t n_entries;
@@ -120,7 +121,8 @@ void ggcat_b200_host_free(void *p);
  * offsets[r+1])), as produced by the reference's reader before normalisation
  * (crates/io/src/sequences_reader.rs:106-179).  colors: one id per record or NULL.
  * The batch is normalised, N-split, hashed, split into super-k-mers and scattered into
- * device-resident buckets.  May be called repeatedly; each call appends one bucket chunk. */
+ * device-resident buckets.  May be called repeatedly and from several host threads (calls are serialised on the
+ * context); every call appends bucket chunks (one per internal H2D batch of <= 48 MB, GGCAT_B200_HOST_BATCH). */
 int32_t ggcat_b200_push_reads(ggcat_b200_ctx *ctx, const uint8_t *data, const uint64_t *offsets, uint64_t n_reads,
                               const uint32_t *colors);
 /* Same, with data/offsets/colors already resident in device memory of ctx's device. */

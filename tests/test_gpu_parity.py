@@ -720,3 +720,84 @@ def test_error_behaviour():
     with pytest.raises(G.GgcatB200Error):
         ctx.merge_bucket_range(4, 2)
     ctx.close()
+
+
+def test_valid_bases_matches_sequences_splitter():
+    """stats.valid_bases = bases of the N-free segments of length >= k (SequencesSplitter::valid_bases), over several
+    pushes, with N runs, short reads and lower-case / non-ACGT bytes."""
+    G = _gpu()
+    rng = np.random.default_rng(2024)
+    k, m, b1, b2 = 31, 12, 3, 2
+    seqs = _mixed_reads(rng, k, n=500)
+    reads = O.Reads.from_list(seqs)
+    sk, vb = O.bucketing(reads, k, m, b1, b2)
+    third = len(seqs) // 3
+    blocks = [O.Reads.from_list(seqs[:third]), O.Reads.from_list(seqs[third:2 * third]), O.Reads.from_list(seqs[2 * third:])]
+    ctx, st = G.minimizer_bucketing([(r.data, r.offsets) for r in blocks], b1, b2, k, m)
+    try:
+        assert st.n_superkmers == len(sk)
+        assert st.valid_bases == vb
+        assert st.total_bases == sum(len(s) for s in seqs)
+    finally:
+        ctx.close()
+
+
+@pytest.mark.parametrize("k,colors,s", [(64, False, 1), (64, False, 2), (48, True, 1)])
+def test_all_ones_key_forward_only_poly_g(k, colors, s):
+    """Forward-only seq-hash of k = 64 uses all 128 key bits: the poly-G k-mer IS the all-ones value that marks an empty
+    table slot (with colours: k = 48 and colour 0xFFFFFFFF).  It must be counted like any other key, in the shared-table,
+    the key-partition and the global-table paths (the slot stayed 'empty' and its count leaked)."""
+    G = _gpu()
+    rng = np.random.default_rng(64 + k)
+    m, b1, b2 = 14, 2, 1
+    g = util.rand_seq(rng, 3000)
+    seqs = [b"G" * 300, g[:500] + b"G" * 150 + g[500:900], b"G" * 90, g, b"C" * 200, util.rand_seq(rng, 40000), b"G" * 4000]
+    cols = np.array([0xFFFFFFFF, 1, 0xFFFFFFFF, 2, 3, 0xFFFFFFFF, 0xFFFFFFFF], np.uint32) if colors else None
+    reads = O.Reads.from_list(seqs, colors=cols) if colors else O.Reads.from_list(seqs)
+    sk, _ = O.bucketing(reads, k, m, b1, b2, forward_only=True)
+    blk = (reads.data, reads.offsets, cols) if colors else (reads.data, reads.offsets)
+    ctx, st = G.minimizer_bucketing([blk], b1, b2, k, m, forward_only=True, min_multiplicity=s, colors=colors)
+    try:
+        assert st.n_superkmers == len(sk)
+        n = _check_tables(G, ctx, reads, sk, k, s, b1, b2, forward_only=True, colors=colors)
+        tab = ctx.merge_bucket_range(0, (1 << b1) + 1)
+        allones = (tab.keys_lo == np.uint64(0xFFFFFFFFFFFFFFFF)) & (tab.keys_hi == np.uint64((1 << (2 * k - 64)) - 1))
+        assert allones.any(), "the poly-G k-mer must be in the table"
+        assert n > 0
+    finally:
+        ctx.close()
+
+
+def test_push_reads_from_several_threads():
+    """push_reads is callable from many host threads (calls are serialised on the context): four threads push
+    interleaved shares; the tables equal the oracle's on all reads (bucket contents are order-independent)."""
+    G = _gpu()
+    import threading
+
+    rng = np.random.default_rng(8)
+    k, m, b1, b2, s = 31, 12, 3, 2, 2
+    seqs = _mixed_reads(rng, k, n=800)
+    reads = O.Reads.from_list(seqs)
+    sk, _ = O.bucketing(reads, k, m, b1, b2)
+    ctx = G.GGCATB200(G.Params(k=k, m=m, min_multiplicity=s, buckets_count_log=b1, second_buckets_count_log=b2))
+    try:
+        shares = [O.Reads.from_list(seqs[i::4]) for i in range(4)]
+        errs = []
+
+        def work(r):
+            try:
+                for a in range(0, r.n, 50):
+                    b = min(r.n, a + 50)
+                    ctx.push_reads(r.data[int(r.offsets[a]):int(r.offsets[b])], r.offsets[a:b + 1] - r.offsets[a])
+            except Exception as e:  # noqa: BLE001
+                errs.append(e)
+
+        ts = [threading.Thread(target=work, args=(r,)) for r in shares]
+        [t.start() for t in ts]
+        [t.join() for t in ts]
+        assert not errs, errs
+        st = ctx.finish_bucketing()
+        assert st.n_superkmers == len(sk)
+        _check_tables(G, ctx, reads, sk, k, s, b1, b2)
+    finally:
+        ctx.close()
