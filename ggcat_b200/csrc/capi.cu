@@ -82,11 +82,11 @@ struct Chunk {
 };
 
 enum Family { F_PACK = 0, F_WINDOWS, F_EMIT, F_SCATTER, F_SCAN, F_MERGE_HASH, F_MERGE_HASH_GLOBAL, F_MERGE_SMEM, F_MERGE_GLOBAL,
-              F_GATHER, F_MERGE_HASH128, F_SORT128, F_COLOR_FOLD, F_PARTITION, F_MERGE_HASH_PART, F_PEER, F_COUNT };
+              F_GATHER, F_MERGE_HASH128, F_SORT128, F_COLOR_FOLD, F_PARTITION, F_MERGE_HASH_PART, F_PEER, F_PEER_PUSH, F_COUNT };
 static const char *kFamilyNames[F_COUNT] = {"k_pack+k_mark", "k_windows", "k_emit", "k_scatter", "k_exclusive_scan_u32",
                                             "k_merge_hash<smem>", "k_merge_hash<global>", "k_merge_units<smem>",
                                             "k_merge_units<global>", "k_gather_units", "k_merge_hash128", "k_sort_units128",
-                                            "k_color_fold", "k_partition_units", "k_merge_hash<partitions>", "k_peer_push+k_peer_sync"};
+                                            "k_color_fold", "k_partition_units", "k_merge_hash<partitions>", "k_peer_sync<exposed>", "k_peer_push<side streams>"};
 
 struct TimedLaunch { int fam; cudaEvent_t a, b; };
 
@@ -119,8 +119,15 @@ struct PeerState {
     uint8_t *arena = nullptr;
     uint64_t arena_bytes = 0, region_bytes = 0;
     uint8_t *peer_arena[PEER_MAX_WORLD] = {};
-    DevBuf d_jobs, d_stage, d_err;
-    uint8_t *h_stage = nullptr; size_t h_stage_cap = 0;   // pinned: region headers + slice tables being sent, then the jobs
+    uint32_t meta_slots = 64;                 // S: bucket chunks one build may route (GGCAT_B200_PEER_SLICES, <= PEER_MAX_SLICES)
+    cudaStream_t meta_stream = nullptr, data_stream = nullptr;   // per-unit counts + slice entries / bulk slices
+    cudaEvent_t ev_scatter = nullptr, ev_data = nullptr, ev_meta = nullptr;
+    bool build_started = false;
+    uint32_t n_pushed = 0;                    // local chunks already pushed in this build
+    uint64_t cursor[PEER_MAX_WORLD] = {};     // next free byte of this rank's region on destination d
+    bool overflow[PEER_MAX_WORLD] = {};
+    DevBuf d_stage, d_err;                    // d_stage: ring of per-chunk blocks (copy jobs + the slice entries / headers being sent)
+    uint8_t *h_stage = nullptr; size_t h_stage_cap = 0;   // pinned mirror of d_stage
     uint8_t *h_recv = nullptr; size_t h_recv_cap = 0;     // pinned: received headers, tables and per-unit counts
     uint64_t last_sent = 0, last_received = 0;            // payload + descriptor + metadata bytes of the last exchange
 };
@@ -181,17 +188,17 @@ struct ggcat_b200_ctx {
 namespace {
 
 struct LaunchTimer {
-    ggcat_b200_ctx *c; int fam; cudaEvent_t a = nullptr, b = nullptr;
-    LaunchTimer(ggcat_b200_ctx *ctx, int f, uint32_t n_kernels = 1) : c(ctx), fam(f) {
+    ggcat_b200_ctx *c; int fam; cudaStream_t st; cudaEvent_t a = nullptr, b = nullptr;
+    LaunchTimer(ggcat_b200_ctx *ctx, int f, uint32_t n_kernels = 1, cudaStream_t stream = nullptr) : c(ctx), fam(f), st(stream ? stream : ctx->stream) {
         c->fam_launches[fam] += n_kernels;
         if (!c->timing) return;
         auto get = [&]() { cudaEvent_t e; if (!c->event_pool.empty()) { e = c->event_pool.back(); c->event_pool.pop_back(); } else cudaEventCreate(&e); return e; };
         a = get(); b = get();
-        cudaEventRecord(a, c->stream);
+        cudaEventRecord(a, st);
     }
     ~LaunchTimer() {
         if (!c->timing) return;
-        cudaEventRecord(b, c->stream);
+        cudaEventRecord(b, st);
         c->launches.push_back({fam, a, b});
     }
 };
@@ -199,6 +206,7 @@ struct LaunchTimer {
 void collect_timings(ggcat_b200_ctx *c) {
     if (c->launches.empty()) return;
     cudaStreamSynchronize(c->stream);
+    if (c->peer.data_stream) { cudaStreamSynchronize(c->peer.data_stream); cudaStreamSynchronize(c->peer.meta_stream); }
     for (auto &l : c->launches) {
         float ms = 0;
         cudaEventElapsedTime(&ms, l.a, l.b);
@@ -226,6 +234,11 @@ int32_t check_ctx(ggcat_b200_ctx *c) {
     if (e != cudaSuccess) return set_err(GGCAT_B200_ERR_CUDA, "cudaSetDevice(%d): %s", c->device, cudaGetErrorString(e));
     return 0;
 }
+
+int32_t mirror_chunk(ggcat_b200_ctx *c, Chunk *ch);
+int32_t peer_begin_build(ggcat_b200_ctx *c);
+int32_t peer_push_chunk(ggcat_b200_ctx *c, Chunk *ch);
+int32_t pinned_reserve(uint8_t **p, size_t *cap, size_t need);
 
 // One batch of <= max_batch bases, inputs already on the device.
 int32_t bucket_batch_device(ggcat_b200_ctx *c, const uint8_t *d_data, const uint64_t *d_offsets, uint64_t n_reads,
@@ -349,6 +362,13 @@ int32_t bucket_batch_device(ggcat_b200_ctx *c, const uint8_t *d_data, const uint
     CU(cudaGetLastError());
     guard.ch = nullptr;
     c->chunks.push_back(ch);
+    // sharded build over NVLink peer memory: the slices of this chunk leave for their owners now, on side streams, while
+    // the next batch is bucketed
+    if (c->peer.connected && c->peer.world > 1) {
+        if (!c->peer.build_started) TRY(peer_begin_build(c));
+        CU(cudaEventRecord(c->peer.ev_scatter, st));
+        TRY(peer_push_chunk(c, ch));
+    }
     return 0;
 }
 
@@ -382,6 +402,106 @@ int32_t mirror_chunk(ggcat_b200_ctx *c, Chunk *ch) {
     return 0;
 }
 
+
+// ---- NVLink peer exchange, sender side (peer.cuh) ------------------------------------------------------------------
+static uint32_t owner_first_bucket(uint32_t b1, uint32_t r, uint32_t world) {
+    const uint64_t nb = 1ull << b1;
+    if (r >= world) return (uint32_t)nb + 1;                      // the last rank also owns the duplicates bucket
+    return (uint32_t)(((uint64_t)r * nb + world - 1) / world);    // owner(b) = b * world >> b1
+}
+static inline uint64_t peer_align16(uint64_t x) { return (x + 15) & ~15ull; }
+static inline uint64_t peer_s_meta(uint32_t nu) { return peer_align16(3ull * nu * 4); }             // cnt | words | kmers of one slice
+static inline uint64_t peer_s_uoff(uint32_t nu) { return 2 * peer_align16(((uint64_t)nu + 2) * 4); }  // receiver's two offset scans
+static inline uint64_t peer_data_off(uint32_t S, uint32_t nu) { return (PEER_META_OFF + (uint64_t)S * (peer_s_meta(nu) + peer_s_uoff(nu)) + 255) & ~255ull; }
+// staging block of one chunk: [meta jobs: 4 per rank][data jobs: 2 per rank][slice entries / headers: 64 B per rank]
+static inline size_t peer_block_data_jobs_off(uint32_t W) { return (size_t)W * 4 * sizeof(PeerJob); }
+static inline size_t peer_block_entries_off(uint32_t W) { return (size_t)W * 6 * sizeof(PeerJob); }
+static inline size_t peer_block_bytes(uint32_t W) { return (size_t)W * (6 * sizeof(PeerJob) + 64); }
+
+// First chunk of a build: new epoch; tell every peer that this rank is done with what it received in the last build
+// (stream-ordered behind the last merge), and make both side streams wait until every destination has said the same.
+int32_t peer_begin_build(ggcat_b200_ctx *c) {
+    PeerState &ps = c->peer;
+    const uint32_t W = ps.world, me = ps.rank;
+    ps.epoch++; ps.build_started = true; ps.n_pushed = 0; ps.last_sent = ps.last_received = 0;
+    for (uint32_t d = 0; d < W; d++) {
+        const uint32_t nu = (owner_first_bucket(c->P.b1, d + 1, W) - owner_first_bucket(c->P.b1, d, W)) << c->P.b2;
+        ps.cursor[d] = peer_data_off(ps.meta_slots, nu); ps.overflow[d] = false;
+    }
+    PeerHdrPtrs hp;
+    memset(&hp, 0, sizeof(hp));
+    for (uint32_t r = 0; r < W; r++) hp.h[r] = reinterpret_cast<PeerHdr *>(ps.peer_arena[r]);
+    const unsigned long long timeout_ns = 20ull * 1000000000ull;
+    c->fam_launches[F_PEER] += 3;
+    k_peer_sync<<<1, PEER_MAX_WORLD, 0, c->stream>>>(hp, me, W, PEER_FLAG_RELEASED, ps.epoch - 1, 1u, 0u, ps.d_err.as<uint32_t>(), timeout_ns);
+    k_peer_sync<<<1, PEER_MAX_WORLD, 0, ps.meta_stream>>>(hp, me, W, PEER_FLAG_RELEASED, ps.epoch - 1, 0u, 1u, ps.d_err.as<uint32_t>(), timeout_ns);
+    k_peer_sync<<<1, PEER_MAX_WORLD, 0, ps.data_stream>>>(hp, me, W, PEER_FLAG_RELEASED, ps.epoch - 1, 0u, 1u, ps.d_err.as<uint32_t>(), timeout_ns);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+// Push the slices of one local chunk to their owners.  The caller has recorded ps.ev_scatter on the compute stream behind
+// the chunk's k_scatter.  Counts + slice entry go out on the meta stream at once (they are final after k_emit, which the
+// host mirror of the counts has already waited for); descriptors + payload follow on the data stream behind ev_scatter.
+int32_t peer_push_chunk(ggcat_b200_ctx *c, Chunk *ch) {
+    PeerState &ps = c->peer;
+    const uint32_t W = ps.world, me = ps.rank, j = ps.n_pushed;
+    const DevParams &P = c->P;
+    if (j >= ps.meta_slots)
+        return set_err(GGCAT_B200_ERR_CAPACITY, "the NVLink exchange routes at most %u bucket chunks per build (GGCAT_B200_PEER_SLICES, max %d): "
+                       "push larger batches", ps.meta_slots, PEER_MAX_SLICES);
+    TRY(mirror_chunk(c, ch));
+    const size_t bb = peer_block_bytes(W);
+    uint8_t *hb = ps.h_stage + (size_t)j * bb, *db = ps.d_stage.as<uint8_t>() + (size_t)j * bb;
+    PeerJob *mjobs = reinterpret_cast<PeerJob *>(hb), *djobs = reinterpret_cast<PeerJob *>(hb + peer_block_data_jobs_off(W));
+    PeerSlice *ent = reinterpret_cast<PeerSlice *>(hb + peer_block_entries_off(W));
+    uint32_t nm = 0, nd = 0;
+    for (uint32_t d = 0; d < W; d++) {
+        if (d == me) continue;
+        const uint32_t fu = owner_first_bucket(P.b1, d, W) << P.b2, nu = (owner_first_bucket(P.b1, d + 1, W) << P.b2) - fu;
+        const uint32_t slot = (d + W - me - 1) % W;   // 0 .. W-2: the grid of k_peer_push is split over the destinations
+        const uint64_t d0 = ch->h_off[fu], d1 = ch->h_off[fu + nu], w0 = ch->h_woff[fu], w1 = ch->h_woff[fu + nu];
+        PeerSlice &e = ent[d];
+        memset(&e, 0, sizeof(e));
+        uint8_t *dst = ps.peer_arena[d] + PEER_HDR_BYTES + (uint64_t)me * ps.region_bytes;
+        if (!ps.overflow[d]) {
+            const uint64_t desc_off = peer_align16(ps.cursor[d]);
+            const uint64_t pay_off = peer_align16(desc_off + (d1 - d0) * 16) + ((w0 * 4) & 15u);
+            const uint64_t end = pay_off + (w1 - w0 + 8) * 4;
+            if (end > ps.region_bytes) ps.overflow[d] = true;
+            else {
+                e.n_sk = d1 - d0; e.n_words = w1 - w0; e.word_bias = w0; e.desc_off = desc_off; e.pay_off = pay_off;
+                ps.cursor[d] = end;
+                if (e.n_sk) {
+                    djobs[nd++] = {reinterpret_cast<const uint8_t *>(ch->d_desc + d0), dst + desc_off, e.n_sk * 16, slot, 0u};
+                    djobs[nd++] = {reinterpret_cast<const uint8_t *>(ch->d_payload + w0), dst + pay_off, e.n_words * 4, slot, 0u};
+                }
+            }
+        }
+        uint8_t *meta = dst + PEER_META_OFF + (uint64_t)j * peer_s_meta(nu);
+        mjobs[nm++] = {reinterpret_cast<const uint8_t *>(ch->d_unit_cnt + fu), meta, (uint64_t)nu * 4, slot, 0u};
+        mjobs[nm++] = {reinterpret_cast<const uint8_t *>(ch->d_unit_words + fu), meta + (uint64_t)nu * 4, (uint64_t)nu * 4, slot, 0u};
+        mjobs[nm++] = {reinterpret_cast<const uint8_t *>(ch->d_unit_kmers + fu), meta + (uint64_t)nu * 8, (uint64_t)nu * 4, slot, 0u};
+        mjobs[nm++] = {db + peer_block_entries_off(W) + (size_t)d * 64, dst + PEER_TABLE_OFF + (uint64_t)j * 64, 64ull, slot, 0u};
+    }
+    for (uint32_t q = 0; q < nm; q++) ps.last_sent += mjobs[q].bytes;
+    for (uint32_t q = 0; q < nd; q++) ps.last_sent += djobs[q].bytes;
+    // the whole block travels on the meta stream; the data stream waits for it through ev_meta
+    CU(cudaMemcpyAsync(db, hb, bb, cudaMemcpyHostToDevice, ps.meta_stream));
+    CU(cudaEventRecord(ps.ev_meta, ps.meta_stream));
+    k_peer_push<<<(W - 1) * 4, 256, 0, ps.meta_stream>>>(reinterpret_cast<const PeerJob *>(db), nm, W - 1);
+    c->fam_launches[F_PEER_PUSH] += 1;
+    CU(cudaStreamWaitEvent(ps.data_stream, ps.ev_meta, 0));
+    CU(cudaStreamWaitEvent(ps.data_stream, ps.ev_scatter, 0));
+    if (nd) {
+        LaunchTimer t(c, F_PEER_PUSH, 1, ps.data_stream);   // device time of the bulk push (overlaps the bucketing of the next batch)
+        k_peer_push<<<(unsigned)c->sm_count * 2, 256, 0, ps.data_stream>>>(reinterpret_cast<const PeerJob *>(db + peer_block_data_jobs_off(W)), nd, W - 1);
+    }
+    CU(cudaGetLastError());
+    ps.n_pushed++;
+    return 0;
+}
+
 // exclusive scan u32 counts -> u64 offsets (n_units small: single CTA, sequential per thread chunks)
 __global__ void __launch_bounds__(1024) k_scan_counts_u64(const uint32_t *cnt, uint64_t *off, uint32_t n, uint64_t base = 0) {
     __shared__ uint32_t s_scan[1024 / 32 + 2];
@@ -412,7 +532,8 @@ constexpr int HASH_TS_S = 8192;                       // k_merge_parts: table sl
 #define TIER_C 1024, 11776, 2560, 8192, 1, 1
 struct TierCap { uint32_t ts, skcap, pwcap; };
 constexpr TierCap kTierCaps[3] = {{4096, 512, 2048}, {5632, 1408, 4608}, {11776, 2560, 8192}};
-constexpr double TIER_MAX_LOAD = 0.5;   // expected distinct keys / table slots a unit may have in its tier
+constexpr double kTierMaxLoad[3] = {0.5, 0.5, 0.72};   // expected distinct keys / table slots a unit may have in its tier (the last tier
+                                                       // takes denser tables rather than sending the unit to the key-partition path)
 
 // A bucket range may be merged in several parts that append to one final table (merge_range_parts): `eb` = entries
 // already in the table, `ub` = units already in unit_final_off, `cap_total` = final-buffer capacity for the whole range.
@@ -515,7 +636,7 @@ int32_t merge_range_device(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_
             const double need_keys = (double)n * keys_per_rec;
             const uint64_t need_w = (uint64_t)unit_w[u - u0] + 6ull * unit_sl[u - u0];
             for (int q = 0; q < 3 && t < 0; q++)
-                if (unit_sk[u - u0] <= caps[q].skcap && need_w <= caps[q].pwcap && need_keys <= TIER_MAX_LOAD * caps[q].ts) t = q;
+                if (unit_sk[u - u0] <= caps[q].skcap && need_w <= caps[q].pwcap && need_keys <= kTierMaxLoad[q] * caps[q].ts) t = q;
         }
         if (t >= 0) { tier[t].push_back(u); tier_nmax = std::max(tier_nmax, n); }
         else if (!hash_mode && n <= SM_CAP_S) work[0].push_back(u);
@@ -730,8 +851,14 @@ int32_t merge_range_device(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_
         }
         CU(cudaMemcpyAsync(c->h_pinned, c->cursor.p, 24, cudaMemcpyDeviceToHost, st));
         CU(cudaMemcpyAsync(c->h_pinned + 8, c->overflow.p, 4, cudaMemcpyDeviceToHost, st));
+        c->h_pinned[9] = 0;
+        if (c->peer.connected && c->peer.world > 1) CU(cudaMemcpyAsync(c->h_pinned + 9, c->peer.d_err.p, 4, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
         CU(cudaGetLastError());
+        if ((uint32_t)c->h_pinned[9]) {   // a peer never signalled that its bulk push was complete: what was merged is incomplete
+            cudaMemset(c->peer.d_err.p, 0, 16);
+            return set_err(GGCAT_B200_ERR_STATE, "NVLink exchange: rank %u did not complete its push within 20 s", (uint32_t)c->h_pinned[9] - 1);
+        }
         ovf = (uint32_t)c->h_pinned[8];
         if (ovf == 4u && attempt == 0) {   // the part's survivors do not fit the final table: grow it, gather again
             const uint64_t need = pb.eb + c->h_pinned[0];
@@ -1157,6 +1284,7 @@ int32_t ggcat_b200_reset(ggcat_b200_ctx *c) {
     c->chunks.clear();
     c->fin = FinalTable();
     c->finished = false;
+    c->peer.build_started = false;
     memset(&c->stats, 0, sizeof(c->stats));
     return 0;
 }
@@ -1189,7 +1317,10 @@ void ggcat_b200_destroy(ggcat_b200_ctx *c) {
         for (uint32_t r = 0; r < ps.world; r++)
             if (ps.connected && r != ps.rank && ps.peer_arena[r]) cudaIpcCloseMemHandle(ps.peer_arena[r]);
         if (ps.arena) cudaFree(ps.arena);
-        ps.d_jobs.release(); ps.d_stage.release(); ps.d_err.release();
+        ps.d_stage.release(); ps.d_err.release();
+        if (ps.meta_stream) cudaStreamDestroy(ps.meta_stream);
+        if (ps.data_stream) cudaStreamDestroy(ps.data_stream);
+        for (cudaEvent_t e : {ps.ev_scatter, ps.ev_data, ps.ev_meta}) if (e) cudaEventDestroy(e);
         if (ps.h_stage) cudaFreeHost(ps.h_stage);
         if (ps.h_recv) cudaFreeHost(ps.h_recv);
     }
@@ -1657,11 +1788,6 @@ int32_t ggcat_b200_drop_local_chunks(ggcat_b200_ctx *c) {
 
 
 // ---- NVLink peer exchange (peer.cuh) -----------------------------------------------------------------------------
-static uint32_t owner_first_bucket(uint32_t b1, uint32_t r, uint32_t world) {
-    const uint64_t nb = 1ull << b1;
-    if (r >= world) return (uint32_t)nb + 1;                      // the last rank also owns the duplicates bucket
-    return (uint32_t)(((uint64_t)r * nb + world - 1) / world);    // owner(b) = b * world >> b1
-}
 
 int32_t ggcat_b200_owner_range(uint32_t buckets_count_log, uint32_t rank, uint32_t world, uint32_t *first_bucket, uint32_t *n_buckets) {
     if (world == 0 || rank >= world || buckets_count_log > 13 || world > (1u << buckets_count_log))
@@ -1683,8 +1809,13 @@ int32_t ggcat_b200_peer_init(ggcat_b200_ctx *c, uint32_t rank, uint32_t world, u
     static_assert(sizeof(cudaIpcMemHandle_t) <= sizeof(ggcat_b200_peer_handle), "IPC handle must fit the ABI struct");
     memset(out, 0, sizeof(*out));
     ps.rank = rank; ps.world = world;
+    if (const char *e = getenv("GGCAT_B200_PEER_SLICES")) ps.meta_slots = (uint32_t)std::max(1, std::min(PEER_MAX_SLICES, atoi(e)));
     if (world > 1) {
-        const uint64_t min_region = PEER_META_OFF + (1ull << 20);
+        // every region starts with the slice table and S meta + scratch slots sized by the LARGEST owner range
+        uint32_t nu_max = 0;
+        for (uint32_t r = 0; r < world; r++)
+            nu_max = std::max(nu_max, (owner_first_bucket(c->P.b1, r + 1, world) - owner_first_bucket(c->P.b1, r, world)) << c->P.b2);
+        const uint64_t min_region = peer_data_off(ps.meta_slots, nu_max) + (1ull << 20);
         ps.region_bytes = std::max<uint64_t>(arena_bytes / world, min_region) & ~255ull;
         ps.arena_bytes = PEER_HDR_BYTES + ps.region_bytes * world;
         CU(cudaMalloc((void **)&ps.arena, ps.arena_bytes));
@@ -1695,6 +1826,14 @@ int32_t ggcat_b200_peer_init(ggcat_b200_ctx *c, uint32_t rank, uint32_t world, u
         memcpy(out->bytes, &h, sizeof(h));
         CU(ps.d_err.reserve(16));
         CU(cudaMemset(ps.d_err.p, 0, 16));
+        CU(cudaStreamCreateWithFlags(&ps.meta_stream, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&ps.data_stream, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&ps.ev_scatter, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&ps.ev_data, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&ps.ev_meta, cudaEventDisableTiming));
+        const size_t stage_bytes = (size_t)(ps.meta_slots + 1) * peer_block_bytes(world);
+        CU(ps.d_stage.reserve(stage_bytes));
+        TRY(pinned_reserve(&ps.h_stage, &ps.h_stage_cap, stage_bytes));
     }
     ps.inited = true;
     return 0;
@@ -1722,7 +1861,6 @@ int32_t ggcat_b200_peer_connect(ggcat_b200_ctx *c, const ggcat_b200_peer_handle 
     return 0;
 }
 
-
 int32_t ggcat_b200_peer_exchange(ggcat_b200_ctx *c) {
     TRY(check_ctx(c));
     std::lock_guard<std::mutex> lock__(c->mu);
@@ -1736,117 +1874,93 @@ int32_t ggcat_b200_peer_exchange(ggcat_b200_ctx *c) {
     std::vector<Chunk *> local;
     for (Chunk *ch : c->chunks) {
         if (ch->imported) return set_err(GGCAT_B200_ERR_STATE, "peer_exchange: chunks were already exchanged");
-        TRY(mirror_chunk(c, ch));
         local.push_back(ch);
     }
-    const uint32_t nsl = (uint32_t)local.size();
-    if (nsl > (uint32_t)PEER_MAX_SLICES)
-        return set_err(GGCAT_B200_ERR_INVALID, "peer_exchange routes at most %d bucket chunks (pushes) per build, got %u", PEER_MAX_SLICES, nsl);
-    const uint32_t epoch = ++ps.epoch;
-    auto first_unit_of = [&](uint32_t r) { return owner_first_bucket(P.b1, r, W) << P.b2; };
-    auto align16 = [](uint64_t x) { return (x + 15) & ~15ull; };
-    // ---- plan: region header + slice table per destination, copy jobs
-    const size_t tbl = (size_t)PEER_META_OFF;
-    const size_t max_jobs = (size_t)W * (1 + 5 * (size_t)std::max<uint32_t>(nsl, 1));
-    TRY(pinned_reserve(&ps.h_stage, &ps.h_stage_cap, (size_t)W * tbl + max_jobs * sizeof(PeerJob)));
-    CU(ps.d_stage.reserve((size_t)W * tbl));
-    CU(ps.d_jobs.reserve(max_jobs * sizeof(PeerJob)));
-    PeerJob *jobs = reinterpret_cast<PeerJob *>(ps.h_stage + (size_t)W * tbl);
-    uint32_t n_jobs = 0;
-    bool sent_overflow = false;
-    ps.last_sent = ps.last_received = 0;
-    for (uint32_t d = 0; d < W; d++) {
-        if (d == me) continue;
-        const uint32_t fu = first_unit_of(d), nu = first_unit_of(d + 1) - fu;
-        const uint32_t slot = (d + W - me - 1) % W;   // 0 .. W-2: the grid of k_peer_push is split over the destinations
-        const uint64_t s_meta = align16(3ull * nu * 4), s_uoff = 2 * align16(((uint64_t)nu + 2) * 4);   // descriptor + word offsets
-        uint8_t *hs = ps.h_stage + (size_t)d * tbl;
-        memset(hs, 0, tbl);
-        RegionHdr *rh = reinterpret_cast<RegionHdr *>(hs);
-        PeerSlice *tb = reinterpret_cast<PeerSlice *>(hs + PEER_TABLE_OFF);
-        uint8_t *dst = ps.peer_arena[d] + PEER_HDR_BYTES + (uint64_t)me * ps.region_bytes;
-        uint64_t cursor = PEER_META_OFF + (uint64_t)nsl * (s_meta + s_uoff);
-        for (uint32_t j = 0; j < nsl; j++) {
-            const Chunk *ch = local[j];
-            const uint64_t d0 = ch->h_off[fu], d1 = ch->h_off[fu + nu], w0 = ch->h_woff[fu], w1 = ch->h_woff[fu + nu];
-            tb[j].n_sk = d1 - d0; tb[j].n_words = w1 - w0; tb[j].word_bias = w0;
-            tb[j].desc_off = align16(cursor); cursor = tb[j].desc_off + (d1 - d0) * 16;
-            tb[j].pay_off = align16(cursor) + ((w0 * 4) & 15u); cursor = tb[j].pay_off + (w1 - w0 + 8) * 4;
-        }
-        rh->n_units = nu; rh->epoch = epoch;
-        if (cursor > ps.region_bytes) { rh->overflow = 1; rh->n_slices = 0; sent_overflow = true; }
-        else {
-            rh->n_slices = nsl;
-            for (uint32_t j = 0; j < nsl; j++) {
-                const Chunk *ch = local[j];
-                uint8_t *meta = dst + PEER_META_OFF + (uint64_t)j * s_meta;
-                jobs[n_jobs++] = {reinterpret_cast<const uint8_t *>(ch->d_unit_cnt + fu), meta, (uint64_t)nu * 4, slot, 0u};
-                jobs[n_jobs++] = {reinterpret_cast<const uint8_t *>(ch->d_unit_words + fu), meta + (uint64_t)nu * 4, (uint64_t)nu * 4, slot, 0u};
-                jobs[n_jobs++] = {reinterpret_cast<const uint8_t *>(ch->d_unit_kmers + fu), meta + (uint64_t)nu * 8, (uint64_t)nu * 4, slot, 0u};
-                if (tb[j].n_sk) {
-                    jobs[n_jobs++] = {reinterpret_cast<const uint8_t *>(ch->d_desc + ch->h_off[fu]), dst + tb[j].desc_off, tb[j].n_sk * 16, slot, 0u};
-                    jobs[n_jobs++] = {reinterpret_cast<const uint8_t *>(ch->d_payload + ch->h_woff[fu]), dst + tb[j].pay_off, tb[j].n_words * 4, slot, 0u};
-                }
-            }
-        }
-        jobs[n_jobs++] = {ps.d_stage.as<uint8_t>() + (size_t)d * tbl, dst, (uint64_t)(PEER_TABLE_OFF + (uint64_t)nsl * 64), slot, 0u};
+    if (!ps.build_started) TRY(peer_begin_build(c));
+    // chunks that were not pushed eagerly (peer arena connected in the middle of a build)
+    for (size_t j = ps.n_pushed; j < local.size(); j++) {
+        CU(cudaEventRecord(ps.ev_scatter, st));
+        TRY(peer_push_chunk(c, local[j]));
     }
-    for (uint32_t j = 0; j < n_jobs; j++) ps.last_sent += jobs[j].bytes;
-    CU(cudaMemcpyAsync(ps.d_stage.p, ps.h_stage, (size_t)W * tbl, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(ps.d_jobs.p, jobs, (size_t)n_jobs * sizeof(PeerJob), cudaMemcpyHostToDevice, st));
+    const uint32_t epoch = ps.epoch, S = ps.meta_slots;
+    auto first_unit_of = [&](uint32_t r) { return owner_first_bucket(P.b1, r, W) << P.b2; };
     PeerHdrPtrs hp;
     memset(&hp, 0, sizeof(hp));
     for (uint32_t r = 0; r < W; r++) hp.h[r] = reinterpret_cast<PeerHdr *>(ps.peer_arena[r]);
     const unsigned long long timeout_ns = 20ull * 1000000000ull;
+    // ---- region headers (slice count of this build) -> every owner; then "my counts are complete" / wait for everybody's
     {
-        LaunchTimer t(c, F_PEER, 3);
-        // every peer has finished merging what we sent last time -> push -> tell the owners, wait for our sources
-        k_peer_sync<<<1, PEER_MAX_WORLD, 0, st>>>(hp, me, W, 0u, epoch - 1, ps.d_err.as<uint32_t>(), timeout_ns);
-        k_peer_push<<<(unsigned)c->sm_count * 4, 256, 0, st>>>(ps.d_jobs.as<PeerJob>(), n_jobs, W - 1);
-        k_peer_sync<<<1, PEER_MAX_WORLD, 0, st>>>(hp, me, W, 1u, epoch, ps.d_err.as<uint32_t>(), timeout_ns);
+        const size_t bb = peer_block_bytes(W);
+        uint8_t *hb = ps.h_stage + (size_t)S * bb, *db = ps.d_stage.as<uint8_t>() + (size_t)S * bb;
+        PeerJob *jobs = reinterpret_cast<PeerJob *>(hb);
+        RegionHdr *hdrs = reinterpret_cast<RegionHdr *>(hb + peer_block_entries_off(W));
+        uint32_t nj = 0;
+        for (uint32_t d = 0; d < W; d++) {
+            if (d == me) continue;
+            RegionHdr &rh = hdrs[d];
+            memset(&rh, 0, sizeof(rh));
+            rh.n_slices = ps.n_pushed; rh.overflow = ps.overflow[d] ? 1u : 0u; rh.n_units = first_unit_of(d + 1) - first_unit_of(d); rh.epoch = epoch;
+            uint8_t *dst = ps.peer_arena[d] + PEER_HDR_BYTES + (uint64_t)me * ps.region_bytes;
+            jobs[nj++] = {db + peer_block_entries_off(W) + (size_t)d * 64, dst, 64ull, (d + W - me - 1) % W, 0u};
+        }
+        CU(cudaMemcpyAsync(db, hb, bb, cudaMemcpyHostToDevice, ps.meta_stream));
+        c->fam_launches[F_PEER_PUSH] += 2;
+        k_peer_push<<<W - 1, 64, 0, ps.meta_stream>>>(reinterpret_cast<const PeerJob *>(db), nj, W - 1);
+        k_peer_sync<<<1, PEER_MAX_WORLD, 0, ps.meta_stream>>>(hp, me, W, PEER_FLAG_META, epoch, 1u, 1u, ps.d_err.as<uint32_t>(), timeout_ns);
     }
-    // ---- receive: headers, slice tables and per-unit counts of every source, one read-back in the common case
+    // ---- receive: headers, slice tables and per-unit counts of every source (the bulk data may still be in flight)
     const uint32_t my_fu = first_unit_of(me), my_nu = first_unit_of(me + 1) - my_fu;
-    const uint64_t s_meta = align16(3ull * my_nu * 4), s_uoff = 2 * align16(((uint64_t)my_nu + 2) * 4);
-    uint32_t guess = std::max<uint32_t>(nsl, 1);
+    const uint64_t s_meta = peer_s_meta(my_nu), s_uoff = peer_s_uoff(my_nu);
+    uint32_t guess = std::max<uint32_t>(ps.n_pushed, 1);
     for (int attempt = 0; attempt < 2; attempt++) {
         const size_t stride = (size_t)(PEER_META_OFF + (uint64_t)guess * s_meta);
         TRY(pinned_reserve(&ps.h_recv, &ps.h_recv_cap, (size_t)W * stride));
-        for (uint32_t s = 0; s < W; s++) {
-            if (s == me) continue;
-            const uint8_t *reg = ps.arena + PEER_HDR_BYTES + (uint64_t)s * ps.region_bytes;
-            CU(cudaMemcpyAsync(ps.h_recv + (size_t)s * stride, reg, std::min<uint64_t>(stride, ps.region_bytes), cudaMemcpyDeviceToHost, st));
+        for (uint32_t s2 = 0; s2 < W; s2++) {
+            if (s2 == me) continue;
+            const uint8_t *reg = ps.arena + PEER_HDR_BYTES + (uint64_t)s2 * ps.region_bytes;
+            CU(cudaMemcpyAsync(ps.h_recv + (size_t)s2 * stride, reg, std::min<uint64_t>(stride, ps.region_bytes), cudaMemcpyDeviceToHost, ps.meta_stream));
         }
-        CU(cudaMemcpyAsync(c->h_pinned + 9, ps.d_err.p, 4, cudaMemcpyDeviceToHost, st));
-        CU(cudaStreamSynchronize(st));
+        CU(cudaMemcpyAsync(c->h_pinned + 9, ps.d_err.p, 4, cudaMemcpyDeviceToHost, ps.meta_stream));
+        CU(cudaEventRecord(ps.ev_meta, ps.meta_stream));
+        CU(cudaEventSynchronize(ps.ev_meta));
         CU(cudaGetLastError());
         if ((uint32_t)c->h_pinned[9]) {
             CU(cudaMemset(ps.d_err.p, 0, 16));
             return set_err(GGCAT_B200_ERR_STATE, "peer_exchange: rank %u did not answer within 20 s", (uint32_t)c->h_pinned[9] - 1);
         }
         uint32_t need = 0;
-        for (uint32_t s = 0; s < W; s++) {
-            if (s == me) continue;
-            const RegionHdr *rh = reinterpret_cast<const RegionHdr *>(ps.h_recv + (size_t)s * stride);
-            if (rh->epoch != epoch) return set_err(GGCAT_B200_ERR_STATE, "peer_exchange: rank %u delivered epoch %u, expected %u", s, rh->epoch, epoch);
+        for (uint32_t s2 = 0; s2 < W; s2++) {
+            if (s2 == me) continue;
+            const RegionHdr *rh = reinterpret_cast<const RegionHdr *>(ps.h_recv + (size_t)s2 * stride);
+            if (rh->epoch != epoch) return set_err(GGCAT_B200_ERR_STATE, "peer_exchange: rank %u delivered epoch %u, expected %u", s2, rh->epoch, epoch);
             if (rh->overflow) return set_err(GGCAT_B200_ERR_CAPACITY, "peer_exchange: the slices of rank %u do not fit a %llu-byte arena region; "
-                                             "give peer_init a larger arena", s, (unsigned long long)ps.region_bytes);
-            if (rh->n_units != my_nu) return set_err(GGCAT_B200_ERR_INVALID, "peer_exchange: rank %u assumes %u units for this owner, expected %u", s, rh->n_units, my_nu);
+                                             "give peer_init a larger arena", s2, (unsigned long long)ps.region_bytes);
+            if (rh->n_units != my_nu) return set_err(GGCAT_B200_ERR_INVALID, "peer_exchange: rank %u assumes %u units for this owner, expected %u", s2, rh->n_units, my_nu);
             need = std::max(need, rh->n_slices);
         }
         if (need <= guess) break;
         guess = need;
     }
-    if (sent_overflow) return set_err(GGCAT_B200_ERR_CAPACITY, "peer_exchange: local slices do not fit a %llu-byte arena region; give peer_init a larger arena",
-                                      (unsigned long long)ps.region_bytes);
+    for (uint32_t d = 0; d < W; d++)
+        if (d != me && ps.overflow[d])
+            return set_err(GGCAT_B200_ERR_CAPACITY, "peer_exchange: local slices do not fit a %llu-byte arena region; give peer_init a larger arena",
+                           (unsigned long long)ps.region_bytes);
+    // ---- compute stream: my bulk pushes are complete -> tell the owners, wait for my sources; everything that follows
+    //      (offset scans of the received slices, the merge) is stream-ordered behind it -- no host synchronisation here
+    CU(cudaEventRecord(ps.ev_data, ps.data_stream));
+    CU(cudaStreamWaitEvent(st, ps.ev_data, 0));
+    {
+        LaunchTimer t(c, F_PEER, 1);
+        k_peer_sync<<<1, PEER_MAX_WORLD, 0, st>>>(hp, me, W, PEER_FLAG_READY, epoch, 1u, 1u, ps.d_err.as<uint32_t>(), timeout_ns);
+    }
     const size_t stride = (size_t)(PEER_META_OFF + (uint64_t)guess * s_meta);
     CU(c->totals.reserve(8 * 8));
-    for (uint32_t s = 0; s < W; s++) {
-        if (s == me) continue;
-        const uint8_t *hr = ps.h_recv + (size_t)s * stride;
+    for (uint32_t s2 = 0; s2 < W; s2++) {
+        if (s2 == me) continue;
+        const uint8_t *hr = ps.h_recv + (size_t)s2 * stride;
         const RegionHdr *rh = reinterpret_cast<const RegionHdr *>(hr);
         const PeerSlice *tb = reinterpret_cast<const PeerSlice *>(hr + PEER_TABLE_OFF);
-        uint8_t *reg = ps.arena + PEER_HDR_BYTES + (uint64_t)s * ps.region_bytes;
+        uint8_t *reg = ps.arena + PEER_HDR_BYTES + (uint64_t)s2 * ps.region_bytes;
         for (uint32_t j = 0; j < rh->n_slices; j++) {
             if (tb[j].n_sk == 0) continue;
             Chunk *ch = new Chunk();
@@ -1855,7 +1969,7 @@ int32_t ggcat_b200_peer_exchange(ggcat_b200_ctx *c) {
             ch->d_payload = reinterpret_cast<const uint32_t *>(reg + tb[j].pay_off);
             const uint32_t *dm = reinterpret_cast<const uint32_t *>(reg + PEER_META_OFF + (uint64_t)j * s_meta);
             ch->d_unit_cnt = dm; ch->d_unit_words = dm + my_nu; ch->d_unit_kmers = dm + 2 * (size_t)my_nu;
-            uint32_t *uoff = reinterpret_cast<uint32_t *>(reg + PEER_META_OFF + (uint64_t)rh->n_slices * s_meta + (uint64_t)j * s_uoff);
+            uint32_t *uoff = reinterpret_cast<uint32_t *>(reg + PEER_META_OFF + (uint64_t)S * s_meta + (uint64_t)j * s_uoff);
             uint32_t *uwoff = uoff + (s_uoff / 8);
             k_exclusive_scan_u32<<<1, 1024, 0, st>>>(dm, uoff, my_nu, c->totals.as<unsigned long long>() + 3);
             k_exclusive_scan_u32<<<1, 1024, 0, st>>>(dm + my_nu, uwoff, my_nu, c->totals.as<unsigned long long>() + 4);
@@ -1877,7 +1991,7 @@ int32_t ggcat_b200_peer_exchange(ggcat_b200_ctx *c) {
             if (a != tb[j].n_sk || b != tb[j].n_words) {
                 delete ch;
                 return set_err(GGCAT_B200_ERR_INVALID, "peer_exchange: slice %u of rank %u: unit counts sum to %llu super-k-mers / %llu words, header says %llu / %llu",
-                               j, s, (unsigned long long)a, (unsigned long long)b, (unsigned long long)tb[j].n_sk, (unsigned long long)tb[j].n_words);
+                               j, s2, (unsigned long long)a, (unsigned long long)b, (unsigned long long)tb[j].n_sk, (unsigned long long)tb[j].n_words);
             }
             c->chunks.push_back(ch);
         }

@@ -10,17 +10,24 @@
 // hold contiguous unit ranges, so a slice is a plain sub-array), no host round trip on the sender.
 //
 // Arena of rank X:   [PeerHdr 4 KiB] [region 0] ... [region world-1]      (region s is written by rank s only)
-// Region:            [RegionHdr 64 B] [PeerSlice table] [meta slots] [unit-offset slots] [descriptors / payload ...]
-// Flow control, all stream-ordered device code (k_peer_sync):
-//   released[d] on rank X = last epoch whose data rank d has finished merging  -> X may overwrite its region on d
-//   ready[s]    on rank X = last epoch whose push from rank s is complete      -> X may merge
+// Region:            [RegionHdr 64 B] [PeerSlice table, PEER_MAX_SLICES entries] [S meta slots: per-unit cnt | words | kmers]
+//                    [S scratch slots: the receiver's descriptor / word offset scans] [descriptors / payload of the slices ...]
+//                    (S = slices a build may route, fixed at peer_init; slot sizes follow from the owner's unit count)
+// A rank pushes EAGERLY: the slices of a bucket chunk leave for their owners as soon as the chunk's k_scatter is done, on a
+// side stream, while the next batch is bucketed; the small per-unit counts (meta) and the slice-table entry of a chunk
+// travel on a second side stream right after its k_emit, so that every owner's HOST knows the sizes of what it will merge
+// (unit classification, work lists) before the bulk data has arrived.  Flow control, all stream-ordered device code
+// (k_peer_sync), epochs count builds:
+//   released[d] on rank X = last epoch whose data rank d has finished merging     -> X may overwrite its region on d
+//   meta[s]     on rank X = last epoch whose headers / counts from rank s are complete -> X's host may plan its merge
+//   ready[s]    on rank X = last epoch whose bulk push from rank s is complete        -> X may merge
 #pragma once
 #include "device_utils.cuh"
 
 namespace ggb {
 
 constexpr int PEER_MAX_WORLD = 64;
-constexpr int PEER_MAX_SLICES = 64;                 // local chunks (pushes) one exchange can route
+constexpr int PEER_MAX_SLICES = 256;                // local chunks one build can route (64 B of slice table each)
 constexpr uint64_t PEER_HDR_BYTES = 4096;
 constexpr uint64_t PEER_TABLE_OFF = 64;
 constexpr uint64_t PEER_META_OFF = PEER_TABLE_OFF + (uint64_t)PEER_MAX_SLICES * 64;
@@ -28,7 +35,9 @@ constexpr uint64_t PEER_META_OFF = PEER_TABLE_OFF + (uint64_t)PEER_MAX_SLICES * 
 struct PeerHdr {
     uint32_t ready[PEER_MAX_WORLD];
     uint32_t released[PEER_MAX_WORLD];
+    uint32_t meta[PEER_MAX_WORLD];
 };
+enum { PEER_FLAG_RELEASED = 0, PEER_FLAG_READY = 1, PEER_FLAG_META = 2 };
 
 struct RegionHdr {           // 64 bytes, written by the sender
     uint32_t n_slices;
@@ -105,21 +114,27 @@ __global__ void __launch_bounds__(256) k_peer_push(const PeerJob *__restrict__ j
     __threadfence_system();
 }
 
-// k_peer_sync: thread t talks to rank t.  Stores `value` into this rank's slot of rank t's flag array (ready or
-// released), then waits until rank t's slot of the LOCAL flag array reaches `value`.  Bounded spin: on timeout
-// *err is set and the host reports GGCAT_B200_ERR_STATE instead of hanging.
-__global__ void k_peer_sync(PeerHdrPtrs peers, uint32_t me, uint32_t world, uint32_t which, uint32_t value, uint32_t *err,
-                            unsigned long long timeout_ns) {
+// k_peer_sync: thread t talks to rank t.  signal: stores `value` into this rank's slot of rank t's flag array `which`;
+// wait: spins until rank t's slot of the LOCAL flag array reaches `value`.  Bounded spin: on timeout *err is set and the
+// host reports GGCAT_B200_ERR_STATE instead of hanging.
+__global__ void k_peer_sync(PeerHdrPtrs peers, uint32_t me, uint32_t world, uint32_t which, uint32_t value, uint32_t do_signal,
+                            uint32_t do_wait, uint32_t *err, unsigned long long timeout_ns) {
     const uint32_t t = threadIdx.x;
     if (t >= world || t == me) return;
     __threadfence_system();
-    uint32_t *theirs = which ? &peers.h[t]->ready[me] : &peers.h[t]->released[me];
-    st_release_sys(theirs, value);
-    const uint32_t *mine = which ? &peers.h[me]->ready[t] : &peers.h[me]->released[t];
-    const unsigned long long t0 = global_timer_ns();
-    while ((int32_t)(ld_acquire_sys(mine) - value) < 0) {
-        __nanosleep(200);
-        if (global_timer_ns() - t0 > timeout_ns) { atomicExch(err, 1u + t); return; }
+    if (do_signal) {
+        PeerHdr *h = peers.h[t];
+        uint32_t *theirs = which == PEER_FLAG_READY ? &h->ready[me] : which == PEER_FLAG_RELEASED ? &h->released[me] : &h->meta[me];
+        st_release_sys(theirs, value);
+    }
+    if (do_wait) {
+        const PeerHdr *h = peers.h[me];
+        const uint32_t *mine = which == PEER_FLAG_READY ? &h->ready[t] : which == PEER_FLAG_RELEASED ? &h->released[t] : &h->meta[t];
+        const unsigned long long t0 = global_timer_ns();
+        while ((int32_t)(ld_acquire_sys(mine) - value) < 0) {
+            __nanosleep(200);
+            if (global_timer_ns() - t0 > timeout_ns) { atomicExch(err, 1u + t); return; }
+        }
     }
 }
 
