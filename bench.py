@@ -313,8 +313,9 @@ def run_ours(args):
         d_data = h_data.cuda(non_blocking=True)
         d_off = h_off.cuda(non_blocking=True)
         genome_len, err, seed_note = GENOME_PER_GPU * world, ERR, "1% errors"
-        # sharded build: two pushes per rank, so that the NVLink push of the first bucket chunk overlaps the bucketing of the second
-        reads_per_push = n_reads if world == 1 else (n_reads + 1) // 2
+        # one push per rank (--reads-per-push splits it: the NVLink push of a bucket chunk then overlaps the bucketing of the
+        # next one; at C2's size the per-batch fixed costs outweigh that, measured 6.6 vs 5.x ms per step at N=8)
+        reads_per_push = args.reads_per_push if args.reads_per_push_given else n_reads
     else:
         # C4 shape (BASELINE configs[3]): error-free 150 bp reads at 30x of one genome shared by all ranks, generated
         # on the device; rank r holds reads [r*R, (r+1)*R).  Full C4 is 77.5 M reads per GPU at N=8.
@@ -360,6 +361,9 @@ def run_ours(args):
             gdist.peer_setup(ctx, rank, world, arena_bytes=max(int((6 if n_bases < (1 << 31) else 3.6) * n_bases), 64 << 20))
 
     last_stats = [None]
+    my_fb, my_cnt = owner.bucket_range(rank)
+    # the one exchange step: ggcat_b200_peer_exchange (NVLink peer memory) or the NCCL all-to-all of ggcat_b200.dist
+    exchange = ctx.peer_exchange if transport == "peer" else (lambda: gdist.exchange_and_import(ctx, owner, rank, world, ext))
 
     def step_device():
         ctx.reset()
@@ -367,18 +371,16 @@ def run_ours(args):
             ctx.push_reads_device(ptr, off.data_ptr(), nr, nbytes)
         last_stats[0] = ctx.finish_bucketing()   # this rank's own super-k-mers (before the exchange adds imported chunks)
         if world > 1:
-            gdist.exchange_and_import(ctx, owner, rank, world, ext)
-        fb, cnt = owner.bucket_range(rank)
-        return ctx.merge_bucket_range_device(fb, cnt)
+            exchange()
+        return ctx.merge_bucket_range_device(my_fb, my_cnt)
 
     def step_host():
         ctx.reset()
         ctx.push_reads_ptr(h_data.data_ptr(), h_off.data_ptr(), n_reads)   # the library splits it into double-buffered H2D batches
         ctx.finish_bucketing()
         if world > 1:
-            gdist.exchange_and_import(ctx, owner, rank, world, ext)
-        fb, cnt = owner.bucket_range(rank)
-        return ctx.merge_bucket_range(fb, cnt, copy=False)  # what the C ABI hands a host: pinned table, no extra copy
+            exchange()
+        return ctx.merge_bucket_range(my_fb, my_cnt, copy=False)  # what the C ABI hands a host: pinned table, no extra copy
 
     def l2_flush():
         with torch.cuda.stream(ext):
@@ -599,6 +601,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--b1", type=int, default=None, help="experiment: override buckets_count_log")
     args = ap.parse_args()
+    args.reads_per_push_given = "--reads-per-push" in sys.argv
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -6,6 +6,7 @@
 #include "peer.cuh"
 
 #include <algorithm>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -25,6 +26,13 @@ static int32_t set_err(int32_t code, const char *fmt, ...) {
     va_end(ap);
     g_err = buf;
     return code;
+}
+// GGCAT_B200_TRACE=host: wall-clock marks of the host side of every entry point (us since the first mark), on stderr.
+static void trace_host(const char *label) {
+    const char *e = getenv("GGCAT_B200_TRACE");
+    if (!e || strcmp(e, "host") != 0) return;
+    static const auto t0 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[ggcat_b200 host] %9.1f us  %s\n", std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count(), label);
 }
 #define CU(call)                                                                                              \
     do {                                                                                                      \
@@ -167,6 +175,8 @@ struct ggcat_b200_ctx {
     DevBuf d_ascii, d_offsets, d_colors, pk, bad, brk, ent, tile_cnt, tile_sbase, tmp, tmp_color, cur_cnt, totals;
     std::vector<Chunk *> chunks;
     std::vector<Chunk *> chunk_pool;  // recycled local chunks (device buffers kept)
+    struct UnitTot { uint64_t n; uint32_t sk, w, sl, pad; };
+    std::vector<UnitTot> unit_tot;    // merge: per-unit totals over all chunks (kept allocated between merges)
     // phase-2 workspace
     DevBuf d_static_off;                   // wide path: static output regions of partitioned units
     DevBuf d_rkpos;                        // rabin-karp per-position tables
@@ -207,10 +217,17 @@ void collect_timings(ggcat_b200_ctx *c) {
     if (c->launches.empty()) return;
     cudaStreamSynchronize(c->stream);
     if (c->peer.data_stream) { cudaStreamSynchronize(c->peer.data_stream); cudaStreamSynchronize(c->peer.meta_stream); }
+    const bool trace = getenv("GGCAT_B200_TRACE") != nullptr;   // timeline of every timed launch, ms since the first one
     for (auto &l : c->launches) {
         float ms = 0;
         cudaEventElapsedTime(&ms, l.a, l.b);
         c->fam_ms[l.fam] += ms;
+        if (trace) {
+            float t0 = 0, t1 = 0;
+            cudaEventElapsedTime(&t0, c->launches.front().a, l.a);
+            cudaEventElapsedTime(&t1, c->launches.front().a, l.b);
+            fprintf(stderr, "[ggcat_b200 trace] %-28s %8.3f -> %8.3f ms\n", kFamilyNames[l.fam], t0, t1);
+        }
         c->event_pool.push_back(l.a);
         c->event_pool.push_back(l.b);
     }
@@ -247,6 +264,9 @@ int32_t bucket_batch_device(ggcat_b200_ctx *c, const uint8_t *d_data, const uint
     cudaStream_t st = c->stream;
     if (n >= (1ull << 31)) return set_err(GGCAT_B200_ERR_INVALID, "batch of %llu bases exceeds 2^31", (unsigned long long)n);
     c->stats.total_bases += n;
+    // sharded build: the "I am done with what I received in the last build" flag goes out BEFORE this build's kernels are
+    // queued (behind the last merge in stream order) -- the peers' pushes into this rank's arena wait for it
+    if (c->peer.connected && c->peer.world > 1 && !c->peer.build_started) TRY(peer_begin_build(c));
     if (n < P.k) return 0;
     const uint32_t n_tiles = (uint32_t)((n + WIN_T - 1) / WIN_T);
     const uint64_t padded = (uint64_t)n_tiles * WIN_T + 4 * WIN_WMAX + 256;
@@ -282,6 +302,7 @@ int32_t bucket_batch_device(ggcat_b200_ctx *c, const uint8_t *d_data, const uint
     CU(cudaMemcpyAsync(c->h_pinned, c->totals.p, 8, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     const uint64_t n_sk = c->h_pinned[0];
+    trace_host("bucket_batch: super-k-mer count on the host");
     if (n_sk == 0) return 0;
     if (n_sk >= (1ull << 32)) return set_err(GGCAT_B200_ERR_INVALID, "too many super-k-mers in one batch");
 
@@ -362,10 +383,10 @@ int32_t bucket_batch_device(ggcat_b200_ctx *c, const uint8_t *d_data, const uint
     CU(cudaGetLastError());
     guard.ch = nullptr;
     c->chunks.push_back(ch);
+    trace_host("bucket_batch: kernels queued");
     // sharded build over NVLink peer memory: the slices of this chunk leave for their owners now, on side streams, while
     // the next batch is bucketed
     if (c->peer.connected && c->peer.world > 1) {
-        if (!c->peer.build_started) TRY(peer_begin_build(c));
         CU(cudaEventRecord(c->peer.ev_scatter, st));
         TRY(peer_push_chunk(c, ch));
     }
@@ -451,6 +472,7 @@ int32_t peer_push_chunk(ggcat_b200_ctx *c, Chunk *ch) {
         return set_err(GGCAT_B200_ERR_CAPACITY, "the NVLink exchange routes at most %u bucket chunks per build (GGCAT_B200_PEER_SLICES, max %d): "
                        "push larger batches", ps.meta_slots, PEER_MAX_SLICES);
     TRY(mirror_chunk(c, ch));
+    trace_host("peer_push_chunk: counts of the chunk on the host");
     const size_t bb = peer_block_bytes(W);
     uint8_t *hb = ps.h_stage + (size_t)j * bb, *db = ps.d_stage.as<uint8_t>() + (size_t)j * bb;
     PeerJob *mjobs = reinterpret_cast<PeerJob *>(hb), *djobs = reinterpret_cast<PeerJob *>(hb + peer_block_data_jobs_off(W));
@@ -499,6 +521,7 @@ int32_t peer_push_chunk(ggcat_b200_ctx *c, Chunk *ch) {
     }
     CU(cudaGetLastError());
     ps.n_pushed++;
+    trace_host("peer_push_chunk: queued");
     return 0;
 }
 
@@ -592,6 +615,7 @@ int32_t merge_range_device(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_
     if (n_buckets == 0 || first_bucket >= nb_total || first_bucket + n_buckets > nb_total)
         return set_err(GGCAT_B200_ERR_INVALID, "bucket range [%u,+%u) outside 0..%u", first_bucket, n_buckets, nb_total);
     if (c->wide_mode >= 0) return merge_range_device_wide(c, first_bucket, n_buckets, n_entries, unique, total, pb);
+    trace_host("merge_range_device: enter");
     const uint32_t u0 = first_bucket << P.b2, nu = n_buckets << P.b2;
     const bool hash_mode = c->merge_mode == 1;
     // ---- classify units
@@ -601,8 +625,9 @@ int32_t merge_range_device(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_
     //   sort mode (GGCAT_B200_MERGE=sort): work[0] <= 6144 records, work[1] <= 12288
     std::vector<uint32_t> work[3], tier[3];
     std::vector<std::pair<uint64_t, uint32_t>> large, big;  // (records, unit)
-    std::vector<uint64_t> unit_n(nu, 0);
-    std::vector<uint32_t> unit_sk(nu, 0), unit_w(nu, 0), unit_sl(nu, 0);
+    if (c->unit_tot.size() < nu) c->unit_tot.resize(nu);
+    ggcat_b200_ctx::UnitTot *ut = c->unit_tot.data();
+    memset(ut, 0, (size_t)nu * sizeof(*ut));
     // key partitions are sized by the distinct keys they should hold (~2048 = a quarter of the 8192-slot table), from the
     // distinct/records ratio of the parts merged so far with a 2x margin; k_merge_parts splits a partition that
     // turns out fuller than that.  Unknown ratio (first part of a context): 4096 records, the table's guaranteed capacity.
@@ -618,25 +643,29 @@ int32_t merge_range_device(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_
     if (c->tier_a_variant != 0) caps[0].ts = 3072;
     for (Chunk *ch : c->chunks) {
         const uint32_t lo = std::max(u0, ch->first_unit), hi = std::min(u0 + nu, ch->first_unit + ch->n_units);
-        for (uint32_t u = lo; u < hi; u++) {
-            const uint32_t q = u - ch->first_unit, sk = ch->h_cnt[q];
-            if (!sk) continue;
-            unit_n[u - u0] += ch->h_kmers[q]; unit_sk[u - u0] += sk; unit_w[u - u0] += ch->h_words[q]; unit_sl[u - u0] += 1;
+        if (lo >= hi) continue;
+        const uint32_t *hc = ch->h_cnt.data() + (lo - ch->first_unit), *hk = ch->h_kmers.data() + (lo - ch->first_unit),
+                       *hw = ch->h_words.data() + (lo - ch->first_unit);
+        ggcat_b200_ctx::UnitTot *t = ut + (lo - u0);
+        for (uint32_t i = 0, e = hi - lo; i < e; i++) {
+            const uint32_t sk = hc[i];
+            t[i].n += hk[i]; t[i].sk += sk; t[i].w += hw[i]; t[i].sl += sk ? 1u : 0u;   // a slice without super-k-mers adds zeros
         }
     }
+    for (int q = 0; q < 3; q++) tier[q].reserve(nu);
     const bool tiers_ok = hash_mode && c->chunks.size() <= (size_t)TIER_MAXSL && !c->no_tiers;
     uint64_t tot_kmers = 0, tier_nmax = 0;
     for (uint32_t u = u0; u < u0 + nu; u++) {
-        const uint64_t n = unit_n[u - u0];
+        const uint64_t n = ut[u - u0].n;
         if (n == 0) continue;
         if (n >= (1ull << 31)) return set_err(GGCAT_B200_ERR_INVALID, "unit %u holds %llu k-mers (> 2^31)", u, (unsigned long long)n);
         tot_kmers += n;
         int t = -1;
         if (tiers_ok && n < (1u << 24)) {
             const double need_keys = (double)n * keys_per_rec;
-            const uint64_t need_w = (uint64_t)unit_w[u - u0] + 6ull * unit_sl[u - u0];
+            const uint64_t need_w = (uint64_t)ut[u - u0].w + 6ull * ut[u - u0].sl;
             for (int q = 0; q < 3 && t < 0; q++)
-                if (unit_sk[u - u0] <= caps[q].skcap && need_w <= caps[q].pwcap && need_keys <= kTierMaxLoad[q] * caps[q].ts) t = q;
+                if (ut[u - u0].sk <= caps[q].skcap && need_w <= caps[q].pwcap && need_keys <= kTierMaxLoad[q] * caps[q].ts) t = q;
         }
         if (t >= 0) { tier[t].push_back(u); tier_nmax = std::max(tier_nmax, n); }
         else if (!hash_mode && n <= SM_CAP_S) work[0].push_back(u);
@@ -644,6 +673,7 @@ int32_t merge_range_device(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_
         else if (hash_mode && n <= (uint64_t)PART_MAXP * part_target && !c->no_partition) big.push_back({n, u});
         else large.push_back({n, u});
     }
+    trace_host("merge_range_device: units classified");
     // ---- key partitions of big units and the output-slot map
     std::sort(big.begin(), big.end(), [](const auto &a, const auto &b) { return a.first > b.first; });
     std::vector<uint32_t> big_unit, big_logp, big_pbase, part_big;
@@ -700,7 +730,7 @@ int32_t merge_range_device(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_
         uint32_t *un = reinterpret_cast<uint32_t *>(h + off_un);
         uint64_t *so = reinterpret_cast<uint64_t *>(h + off_so);
         uint64_t acc = 0;   // every unit owns the region [static_off[u], static_off[u] + records(u)) of the part's output buffers
-        for (uint32_t i = 0; i < nu; i++) { un[i] = (uint32_t)unit_n[i]; so[i] = acc; acc += unit_n[i]; }
+        for (uint32_t i = 0; i < nu; i++) { un[i] = (uint32_t)ut[i].n; so[i] = acc; acc += ut[i].n; }
         so[nu] = acc;
         CU(cudaMemcpyAsync(c->d_mstage.p, h, stage_bytes, cudaMemcpyHostToDevice, st));
     }
@@ -749,6 +779,7 @@ int32_t merge_range_device(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_
     CU(cudaMemsetAsync(c->overflow.p, 0, 16, st));
     CU(cudaMemsetAsync(c->unit_out_off.p, 0, ((size_t)n_slots + 1) * 8, st));
     CU(cudaMemsetAsync(c->unit_out_cnt.p, 0, ((size_t)n_slots + 1) * 4, st));
+    trace_host("merge_range_device: uploads queued");
     const uint32_t *d_unit_n = reinterpret_cast<const uint32_t *>(dm + off_un);
     MergeOut out;
     out.keys = c->out_keys.as<uint64_t>(); out.count_flags = c->out_cf.as<uint32_t>();
@@ -826,6 +857,7 @@ int32_t merge_range_device(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_
         }
     }
     CU(cudaGetLastError());
+    trace_host("merge_range_device: merge kernels launched");
     // ---- unit-ordered final layout (parts append at entry pb.eb / unit pb.ub)
     const uint64_t rec_total = std::max(cap, pb.cap_total);
     if (pb.ub == 0) TRY(final_reserve(c, final_estimate(c, rec_total), 0, false));
@@ -1433,6 +1465,7 @@ int32_t ggcat_b200_finish_bucketing(ggcat_b200_ctx *c, ggcat_b200_bucket_stats *
     c->stats.valid_bases = km - sk + segs * (uint64_t)c->P.k;
     c->finished = true;
     if (stats) *stats = c->stats;
+    trace_host("finish_bucketing: return");
     return 0;
 }
 
@@ -1826,7 +1859,12 @@ int32_t ggcat_b200_peer_init(ggcat_b200_ctx *c, uint32_t rank, uint32_t world, u
         memcpy(out->bytes, &h, sizeof(h));
         CU(ps.d_err.reserve(16));
         CU(cudaMemset(ps.d_err.p, 0, 16));
-        CU(cudaStreamCreateWithFlags(&ps.meta_stream, cudaStreamNonBlocking));
+        {   // the count / header pushes are a few CTAs that must not queue behind the thousands of pending CTAs of k_scatter:
+            // highest stream priority (their blocks are dispatched first as soon as any SM frees a slot)
+            int lo_prio = 0, hi_prio = 0;
+            CU(cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio));
+            CU(cudaStreamCreateWithPriority(&ps.meta_stream, cudaStreamNonBlocking, hi_prio));
+        }
         CU(cudaStreamCreateWithFlags(&ps.data_stream, cudaStreamNonBlocking));
         CU(cudaEventCreateWithFlags(&ps.ev_scatter, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&ps.ev_data, cudaEventDisableTiming));
@@ -1876,6 +1914,7 @@ int32_t ggcat_b200_peer_exchange(ggcat_b200_ctx *c) {
         if (ch->imported) return set_err(GGCAT_B200_ERR_STATE, "peer_exchange: chunks were already exchanged");
         local.push_back(ch);
     }
+    trace_host("peer_exchange: enter");
     if (!ps.build_started) TRY(peer_begin_build(c));
     // chunks that were not pushed eagerly (peer arena connected in the middle of a build)
     for (size_t j = ps.n_pushed; j < local.size(); j++) {
@@ -1923,6 +1962,7 @@ int32_t ggcat_b200_peer_exchange(ggcat_b200_ctx *c) {
         CU(cudaMemcpyAsync(c->h_pinned + 9, ps.d_err.p, 4, cudaMemcpyDeviceToHost, ps.meta_stream));
         CU(cudaEventRecord(ps.ev_meta, ps.meta_stream));
         CU(cudaEventSynchronize(ps.ev_meta));
+        trace_host("peer_exchange: counts of all sources on the host");
         CU(cudaGetLastError());
         if ((uint32_t)c->h_pinned[9]) {
             CU(cudaMemset(ps.d_err.p, 0, 16));
@@ -1997,6 +2037,7 @@ int32_t ggcat_b200_peer_exchange(ggcat_b200_ctx *c) {
         }
     }
     CU(cudaGetLastError());
+    trace_host("peer_exchange: return");
     return 0;
 }
 

@@ -26,14 +26,14 @@ for r0 in range(0, n_reads, per):
     r1 = min(n_reads, r0 + per)
     off = (d_off[r0:r1 + 1] - r0 * 150).contiguous()
     pushes.append((d_data.data_ptr() + r0 * 150, off, r1 - r0, (r1 - r0) * 150))
+fb, cnt = owner.bucket_range(rank)
 def step():
     ctx.reset()
     for ptr, off, nr, nb in pushes:
         ctx.push_reads_device(ptr, off.data_ptr(), nr, nb)
     ctx.finish_bucketing()
     if world > 1:
-        gdist.exchange_and_import(ctx, owner, rank, world)
-    fb, cnt = owner.bucket_range(rank)
+        ctx.peer_exchange()
     return ctx.merge_bucket_range_device(fb, cnt)
 for _ in range(4):
     step()
