@@ -363,7 +363,7 @@ def run_ours(args):
     last_stats = [None]
     my_fb, my_cnt = owner.bucket_range(rank)
     # the one exchange step: ggcat_b200_peer_exchange (NVLink peer memory) or the NCCL all-to-all of ggcat_b200.dist
-    exchange = ctx.peer_exchange if transport == "peer" else (lambda: gdist.exchange_and_import(ctx, owner, rank, world, ext))
+    do_exchange = ctx.peer_exchange if transport == "peer" else (lambda: gdist.exchange_and_import(ctx, owner, rank, world, ext))
 
     def step_device():
         ctx.reset()
@@ -371,7 +371,7 @@ def run_ours(args):
             ctx.push_reads_device(ptr, off.data_ptr(), nr, nbytes)
         last_stats[0] = ctx.finish_bucketing()   # this rank's own super-k-mers (before the exchange adds imported chunks)
         if world > 1:
-            exchange()
+            do_exchange()
         return ctx.merge_bucket_range_device(my_fb, my_cnt)
 
     def step_host():
@@ -379,7 +379,7 @@ def run_ours(args):
         ctx.push_reads_ptr(h_data.data_ptr(), h_off.data_ptr(), n_reads)   # the library splits it into double-buffered H2D batches
         ctx.finish_bucketing()
         if world > 1:
-            exchange()
+            do_exchange()
         return ctx.merge_bucket_range(my_fb, my_cnt, copy=False)  # what the C ABI hands a host: pinned table, no extra copy
 
     def l2_flush():
