@@ -384,10 +384,11 @@ __global__ void __launch_bounds__(1024) k_exclusive_scan_u32(const uint32_t *in,
 
 // ------------------------------------------------------------------------------------------------
 // k_emit: entry -> super-k-mer descriptor in position order + per-unit histogram.
-// tmp descriptor: {start, len, meta, unit}.
+// tmp descriptor: {start (position in the chunk's packed bases), len, meta, unit}.
 __global__ void __launch_bounds__(256)
 k_emit(const uint64_t *__restrict__ ent, const uint32_t *__restrict__ tile_cnt, const uint32_t *__restrict__ tile_sbase,
        uint32_t n_tiles, DevParams P, uint4 *__restrict__ tmp, uint32_t *__restrict__ tmp_color,
+       uint32_t base /* position of the batch's first base inside the chunk's packed bases */,
        const uint64_t *__restrict__ offsets, uint64_t n_reads, uint64_t off0, const uint32_t *__restrict__ colors,
        uint32_t *__restrict__ unit_cnt, uint32_t *__restrict__ unit_words, uint32_t *__restrict__ unit_kmers,
        uint32_t *__restrict__ seg_count) {
@@ -428,7 +429,7 @@ k_emit(const uint64_t *__restrict__ ent, const uint32_t *__restrict__ tile_cnt, 
         const uint32_t bucket = (uint32_t)(e >> ENT_BUCKET_SHIFT) & 0x3FFFu;
         const uint32_t unit = (bucket << P.b2) | second;
         const uint32_t idx = tile_sbase[tile] + (uint32_t)((e >> ENT_SRANK_SHIFT) & 0xFFFFu);
-        tmp[idx] = make_uint4(start, len, make_meta(mpos, flags, rc, second), unit);
+        tmp[idx] = make_uint4(base + start, len, make_meta(mpos, flags, rc, second), unit);
         if (P.colors) {
             // record index = last r with offsets[r] <= start
             uint64_t lo = 0, hi = n_reads;

@@ -175,6 +175,8 @@ struct ggcat_b200_ctx {
     DevBuf d_ascii, d_offsets, d_colors, pk, bad, brk, ent, tile_cnt, tile_sbase, tmp, tmp_color, cur_cnt, totals;
     std::vector<Chunk *> chunks;
     std::vector<Chunk *> chunk_pool;  // recycled local chunks (device buffers kept)
+    Chunk *open_chunk = nullptr;      // chunk the batches of the current push accumulate into (closed by flush_open_chunk)
+    uint64_t open_bases = 0, open_sk = 0;   // positions used in pk / descriptors held in tmp
     struct UnitTot { uint64_t n; uint32_t sk, w, sl, pad; };
     std::vector<UnitTot> unit_tot;    // merge: per-unit totals over all chunks (kept allocated between merges)
     // phase-2 workspace
@@ -257,9 +259,30 @@ int32_t peer_begin_build(ggcat_b200_ctx *c);
 int32_t peer_push_chunk(ggcat_b200_ctx *c, Chunk *ch);
 int32_t pinned_reserve(uint8_t **p, size_t *cap, size_t need);
 
-// One batch of <= max_batch bases, inputs already on the device.
+// Grow a device buffer keeping its first `keep` bytes (the chunk being accumulated lives in pk / tmp / tmp_color).
+int32_t reserve_keep(ggcat_b200_ctx *c, DevBuf &b, size_t bytes, size_t keep) {
+    if (bytes <= b.cap) return 0;
+    DevBuf nb;
+    CU(nb.reserve(bytes + bytes / 4));
+    if (keep && b.p) CU(cudaMemcpyAsync(nb.p, b.p, keep, cudaMemcpyDeviceToDevice, c->stream));
+    if (b.p) { CU(cudaStreamSynchronize(c->stream)); b.release(); }
+    b = nb;
+    return 0;
+}
+
+int32_t flush_open_chunk(ggcat_b200_ctx *c);
+void abort_open_chunk(ggcat_b200_ctx *c) {   // an error in the middle of a push: what was accumulated is dropped
+    if (c->open_chunk) c->chunk_pool.push_back(c->open_chunk);
+    c->open_chunk = nullptr; c->open_sk = 0; c->open_bases = 0;
+}
+
+// One batch of <= max_batch bases, inputs already on the device: pack, window minima, super-k-mer descriptors and the
+// per-unit histograms.  Batches ACCUMULATE into the open chunk (packed bases, descriptors and unit counts of every batch of
+// one push call); flush_open_chunk() scatters them into ONE unit-sorted bucket chunk, so a push of any size makes one
+// chunk -- one slice per unit and source in the merge and in the exchange -- while the H2D copy of the next batch still
+// overlaps everything but that final scatter.  `reserve_bases`: bases the whole push will bring (sizes the buffers once).
 int32_t bucket_batch_device(ggcat_b200_ctx *c, const uint8_t *d_data, const uint64_t *d_offsets, uint64_t n_reads,
-                            uint64_t off0, uint64_t n, const uint32_t *d_colors) {
+                            uint64_t off0, uint64_t n, const uint32_t *d_colors, uint64_t reserve_bases) {
     const DevParams &P = c->P;
     cudaStream_t st = c->stream;
     if (n >= (1ull << 31)) return set_err(GGCAT_B200_ERR_INVALID, "batch of %llu bases exceeds 2^31", (unsigned long long)n);
@@ -269,19 +292,46 @@ int32_t bucket_batch_device(ggcat_b200_ctx *c, const uint8_t *d_data, const uint
     if (c->peer.connected && c->peer.world > 1 && !c->peer.build_started) TRY(peer_begin_build(c));
     if (n < P.k) return 0;
     const uint32_t n_tiles = (uint32_t)((n + WIN_T - 1) / WIN_T);
-    const uint64_t padded = (uint64_t)n_tiles * WIN_T + 4 * WIN_WMAX + 256;
-    const uint64_t n_groups = (padded + 31) / 32;  // 32-base groups incl. padding
-    CU(c->pk.reserve((2 * n_groups + 8) * 4));
+    const uint64_t padded = ((uint64_t)n_tiles * WIN_T + 4 * WIN_WMAX + 256 + 1023) & ~1023ull;   // positions this batch occupies in pk
+    const uint64_t n_groups = padded / 32;  // 32-base groups incl. padding
+    // positions inside a chunk are 32-bit: a chunk that would outgrow them is closed first
+    if (c->open_chunk && c->open_bases + padded >= (1ull << 32) - (1ull << 20)) TRY(flush_open_chunk(c));
+    if (!c->open_chunk) {
+        Chunk *ch;
+        if (!c->chunk_pool.empty()) { ch = c->chunk_pool.back(); c->chunk_pool.pop_back(); }
+        else ch = new Chunk();
+        ch->imported = false; ch->word_bias = 0; ch->mirror_queued = false;
+        ch->h_cnt.clear(); ch->h_off.clear(); ch->h_words.clear(); ch->h_woff.clear(); ch->h_kmers.clear();
+        ch->first_unit = 0; ch->n_units = P.n_units; ch->n_sk = 0; ch->n_bases = 0;
+        c->open_chunk = ch; c->open_bases = 0; c->open_sk = 0;
+        const size_t ub = ((size_t)P.n_units + 2) * 4;
+        cudaError_t e = ch->unit_cnt.reserve(ub);
+        if (e == cudaSuccess) e = ch->unit_off.reserve(ub);
+        if (e == cudaSuccess) e = ch->unit_words.reserve(ub);
+        if (e == cudaSuccess) e = ch->unit_woff.reserve(ub);
+        if (e == cudaSuccess) e = ch->unit_kmers.reserve(ub);
+        if (e == cudaSuccess) e = cudaMemsetAsync(ch->unit_cnt.p, 0, ub, st);
+        if (e == cudaSuccess) e = cudaMemsetAsync(ch->unit_words.p, 0, ub, st);
+        if (e == cudaSuccess) e = cudaMemsetAsync(ch->unit_kmers.p, 0, ub, st);
+        if (e != cudaSuccess) {
+            c->chunk_pool.push_back(ch); c->open_chunk = nullptr;
+            return set_err(GGCAT_B200_ERR_CUDA, "bucket chunk allocation failed: %s", cudaGetErrorString(e));
+        }
+    }
+    Chunk *ch = c->open_chunk;
+    const uint64_t base = c->open_bases;                      // first position of this batch inside the chunk's packed bases
+    const uint64_t want_bases = std::max<uint64_t>(base + padded, std::min<uint64_t>(reserve_bases + (reserve_bases >> 4) + 8 * padded, (1ull << 32)));
+    TRY(reserve_keep(c, c->pk, (want_bases / 16 + 16) * 4, (size_t)(base / 16) * 4));
     CU(c->bad.reserve((n_groups + 8) * 4));
     CU(c->brk.reserve((n_groups + 8) * 4));
+    uint32_t *pkb = c->pk.as<uint32_t>() + base / 16;         // this batch's packed bases (16-byte aligned: base % 1024 == 0)
     CU(cudaMemsetAsync(c->brk.p, 0, (n_groups + 8) * 4, st));
-    CU(cudaMemsetAsync(c->pk.as<uint32_t>() + 2 * n_groups, 0, 8 * 4, st));
+    CU(cudaMemsetAsync(pkb + 2 * n_groups, 0, 8 * 4, st));
     CU(cudaMemsetAsync(c->bad.as<uint32_t>() + n_groups, 0xFF, 8 * 4, st));
     {
         LaunchTimer t(c, F_PACK, 2);
         const int aligned = ((uintptr_t)d_data & 15) == 0;
-        k_pack<<<(unsigned)((n_groups + 255) / 256), 256, 0, st>>>(d_data, n, c->pk.as<uint32_t>(), c->bad.as<uint32_t>(),
-                                                                   n_groups, aligned);
+        k_pack<<<(unsigned)((n_groups + 255) / 256), 256, 0, st>>>(d_data, n, pkb, c->bad.as<uint32_t>(), n_groups, aligned);
         k_mark<<<(unsigned)((n_reads + 255) / 256), 256, 0, st>>>(d_offsets, n_reads, off0, n, c->brk.as<uint32_t>());
     }
     CU(c->ent.reserve((uint64_t)n_tiles * WIN_T * 8));
@@ -289,7 +339,7 @@ int32_t bucket_batch_device(ggcat_b200_ctx *c, const uint8_t *d_data, const uint
     CU(c->tile_sbase.reserve(((uint64_t)n_tiles + 2) * 4));
     {
         LaunchTimer t(c, F_WINDOWS);
-        k_windows<<<n_tiles, WIN_THREADS, 0, st>>>(c->pk.as<uint32_t>(), c->bad.as<uint32_t>(), c->brk.as<uint32_t>(),
+        k_windows<<<n_tiles, WIN_THREADS, 0, st>>>(pkb, c->bad.as<uint32_t>(), c->brk.as<uint32_t>(),
                                                    (uint32_t)n, P, c->ent.as<uint64_t>(), c->tile_cnt.as<uint32_t>(),
                                                    c->tile_sbase.as<uint32_t>());
     }
@@ -304,37 +354,39 @@ int32_t bucket_batch_device(ggcat_b200_ctx *c, const uint8_t *d_data, const uint
     const uint64_t n_sk = c->h_pinned[0];
     trace_host("bucket_batch: super-k-mer count on the host");
     if (n_sk == 0) return 0;
-    if (n_sk >= (1ull << 32)) return set_err(GGCAT_B200_ERR_INVALID, "too many super-k-mers in one batch");
-
-    // the chunk is registered with the context only after the last operation that can fail; until then an error return
-    // puts it back into the pool (a half-initialised chunk must never reach finish_bucketing / the merge)
-    struct ChunkGuard {
-        ggcat_b200_ctx *c; Chunk *ch;
-        ~ChunkGuard() { if (ch) c->chunk_pool.push_back(ch); }
-    } guard{c, nullptr};
-    Chunk *ch;
-    if (!c->chunk_pool.empty()) { ch = c->chunk_pool.back(); c->chunk_pool.pop_back(); }
-    else ch = new Chunk();
-    guard.ch = ch;
-    ch->imported = false; ch->word_bias = 0; ch->mirror_queued = false;
-    ch->h_cnt.clear(); ch->h_off.clear(); ch->h_words.clear(); ch->h_woff.clear(); ch->h_kmers.clear();
-    ch->first_unit = 0; ch->n_units = P.n_units; ch->n_sk = n_sk; ch->n_bases = n;
-    const size_t ub = ((size_t)P.n_units + 2) * 4;
-    CU(ch->unit_cnt.reserve(ub)); CU(ch->unit_off.reserve(ub)); CU(ch->unit_words.reserve(ub));
-    CU(ch->unit_woff.reserve(ub)); CU(ch->unit_kmers.reserve(ub));
-    CU(cudaMemsetAsync(ch->unit_cnt.p, 0, ub, st));
-    CU(cudaMemsetAsync(ch->unit_words.p, 0, ub, st));
-    CU(cudaMemsetAsync(ch->unit_kmers.p, 0, ub, st));
-    CU(c->tmp.reserve(n_sk * 16));
-    if (P.colors) CU(c->tmp_color.reserve(n_sk * 4));
+    if (c->open_sk + n_sk >= (1ull << 32)) return set_err(GGCAT_B200_ERR_INVALID, "too many super-k-mers in one push");
+    TRY(reserve_keep(c, c->tmp, (c->open_sk + n_sk) * 16, (size_t)c->open_sk * 16));
+    if (P.colors) TRY(reserve_keep(c, c->tmp_color, (c->open_sk + n_sk) * 4, (size_t)c->open_sk * 4));
     {
         LaunchTimer t(c, F_EMIT);
         k_emit<<<n_tiles, 256, 0, st>>>(c->ent.as<uint64_t>(), c->tile_cnt.as<uint32_t>(), c->tile_sbase.as<uint32_t>(),
-                                        n_tiles, P, c->tmp.as<uint4>(), c->tmp_color.as<uint32_t>(), d_offsets, n_reads, off0,
-                                        d_colors, ch->unit_cnt.as<uint32_t>(), ch->unit_words.as<uint32_t>(),
+                                        n_tiles, P, c->tmp.as<uint4>() + c->open_sk, c->tmp_color.as<uint32_t>() + c->open_sk, (uint32_t)base,
+                                        d_offsets, n_reads, off0, d_colors, ch->unit_cnt.as<uint32_t>(), ch->unit_words.as<uint32_t>(),
                                         ch->unit_kmers.as<uint32_t>(), ch->unit_cnt.as<uint32_t>() + P.n_units /* spare slot: segments */);
     }
-    // host mirror of the per-unit counts: they are final after k_emit, so they travel on the copy stream while
+    CU(cudaGetLastError());
+    c->open_sk += n_sk; c->open_bases += padded; ch->n_bases += n;
+    trace_host("bucket_batch: kernels queued");
+    return 0;
+}
+
+// Close the open chunk: per-unit counts to the host (copy stream), offset scans, one scatter of every descriptor /
+// payload of the push into the unit-sorted layout; the chunk is registered (and, in a sharded build, pushed to the
+// owners) only after the last operation that can fail.
+int32_t flush_open_chunk(ggcat_b200_ctx *c) {
+    Chunk *ch = c->open_chunk;
+    if (!ch) return 0;
+    const DevParams &P = c->P;
+    cudaStream_t st = c->stream;
+    struct ChunkGuard {
+        ggcat_b200_ctx *c; Chunk *ch;
+        ~ChunkGuard() { if (ch) c->chunk_pool.push_back(ch); c->open_chunk = nullptr; c->open_sk = 0; c->open_bases = 0; }
+    } guard{c, ch};
+    const uint64_t n_sk = c->open_sk;
+    if (n_sk == 0) return 0;      // nothing but reads shorter than k: the chunk goes back to the pool
+    ch->n_sk = n_sk;
+    const size_t ub = ((size_t)P.n_units + 2) * 4;
+    // host mirror of the per-unit counts: they are final after the last k_emit, so they travel on the copy stream while
     // k_scatter runs; finish_bucketing waits for this event only, and the host side of the merge (unit classification,
     // uploads) overlaps the tail of phase 1
     if (c->copy_stream) {
@@ -363,8 +415,8 @@ int32_t bucket_batch_device(ggcat_b200_ctx *c, const uint8_t *d_data, const uint
                                                  c->totals.as<unsigned long long>() + 2);
     }
     // payload bound: sum ceil(len/16) <= (bases covered)/16 + n_sk, bases covered <= n + n_sk*(k-1)
-    const uint64_t words_bound = (n + n_sk * (uint64_t)(P.k - 1)) / 16 + n_sk + 8;
-    if (words_bound >= (1ull << 32)) return set_err(GGCAT_B200_ERR_INVALID, "payload of one batch exceeds 2^32 words");
+    const uint64_t words_bound = (ch->n_bases + n_sk * (uint64_t)(P.k - 1)) / 16 + n_sk + 8;
+    if (words_bound >= (1ull << 32)) return set_err(GGCAT_B200_ERR_INVALID, "payload of one push exceeds 2^32 words: push smaller batches");
     CU(ch->desc.reserve(n_sk * 16));
     CU(ch->payload.reserve(words_bound * 4));
     CU(c->cur_cnt.reserve(((size_t)P.n_units + 2) * 8));
@@ -383,9 +435,9 @@ int32_t bucket_batch_device(ggcat_b200_ctx *c, const uint8_t *d_data, const uint
     CU(cudaGetLastError());
     guard.ch = nullptr;
     c->chunks.push_back(ch);
-    trace_host("bucket_batch: kernels queued");
+    trace_host("flush_open_chunk: scatter queued");
     // sharded build over NVLink peer memory: the slices of this chunk leave for their owners now, on side streams, while
-    // the next batch is bucketed
+    // the next push is bucketed
     if (c->peer.connected && c->peer.world > 1) {
         CU(cudaEventRecord(c->peer.ev_scatter, st));
         TRY(peer_push_chunk(c, ch));
@@ -1309,6 +1361,7 @@ int32_t ggcat_b200_reset(ggcat_b200_ctx *c) {
     TRY(check_ctx(c));
     std::lock_guard<std::mutex> lock__(c->mu);
     cudaStreamSynchronize(c->stream);
+    abort_open_chunk(c);
     for (Chunk *ch : c->chunks) {
         if (!ch->imported) c->chunk_pool.push_back(ch);  // keep the device buffers for the next build
         else { ch->release(); delete ch; }
@@ -1420,11 +1473,14 @@ int32_t ggcat_b200_push_reads(ggcat_b200_ctx *c, const uint8_t *data, const uint
         const uint64_t r0 = batches[bi].first, r1 = batches[bi].second;
         CU(cudaStreamWaitEvent(c->stream, c->ev_h2d[sl], 0));
         tmark(c->stream);
-        TRY(bucket_batch_device(c, c->st_ascii[sl].as<uint8_t>(), c->st_off[sl].as<uint64_t>(), r1 - r0, offsets[r0],
-                                offsets[r1] - offsets[r0], colors ? c->st_col[sl].as<uint32_t>() : nullptr));
+        int32_t rc = bucket_batch_device(c, c->st_ascii[sl].as<uint8_t>(), c->st_off[sl].as<uint64_t>(), r1 - r0, offsets[r0],
+                                         offsets[r1] - offsets[r0], colors ? c->st_col[sl].as<uint32_t>() : nullptr,
+                                         offsets[n_reads] - offsets[0]);
+        if (rc) { abort_open_chunk(c); return rc; }
         CU(cudaEventRecord(c->ev_free[sl], c->stream));
         tmark(c->stream);
     }
+    TRY(flush_open_chunk(c));    // one bucket chunk per push call
     if (trace) {
         cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->copy_stream);
         fprintf(stderr, "[ggcat_b200 trace] push_reads: %zu batches; ms since first copy was queued:", batches.size());
@@ -1443,7 +1499,9 @@ int32_t ggcat_b200_push_reads_device(ggcat_b200_ctx *c, const uint8_t *d_data, c
     if (n_reads == 0) return 0;
     if (!d_data || !d_offsets) return set_err(GGCAT_B200_ERR_INVALID, "null input");
     if (n_bytes > c->max_batch) return set_err(GGCAT_B200_ERR_INVALID, "device batch of %llu bases exceeds limit %llu", (unsigned long long)n_bytes, (unsigned long long)c->max_batch);
-    return bucket_batch_device(c, d_data, d_offsets, n_reads, 0, n_bytes, c->P.colors ? d_colors : nullptr);
+    int32_t rc = bucket_batch_device(c, d_data, d_offsets, n_reads, 0, n_bytes, c->P.colors ? d_colors : nullptr, n_bytes);
+    if (rc) { abort_open_chunk(c); return rc; }
+    return flush_open_chunk(c);
 }
 
 int32_t ggcat_b200_finish_bucketing(ggcat_b200_ctx *c, ggcat_b200_bucket_stats *stats) {
@@ -1452,6 +1510,7 @@ int32_t ggcat_b200_finish_bucketing(ggcat_b200_ctx *c, ggcat_b200_bucket_stats *
     // no stream synchronisation here: the per-unit counts of every chunk arrive on the copy stream right after its
     // k_emit, so this returns while the last k_scatter is still running; everything that follows is stream-ordered
     // (ggcat_b200_synchronize() is there for callers that touch chunk buffers from another stream)
+    TRY(flush_open_chunk(c));
     uint64_t sk = 0, km = 0, words = 0, segs = 0;
     for (Chunk *ch : c->chunks) {
         TRY(mirror_chunk(c, ch));

@@ -122,7 +122,8 @@ void ggcat_b200_host_free(void *p);
  * (crates/io/src/sequences_reader.rs:106-179).  colors: one id per record or NULL.
  * The batch is normalised, N-split, hashed, split into super-k-mers and scattered into
  * device-resident buckets.  May be called repeatedly and from several host threads (calls are serialised on the
- * context); every call appends bucket chunks (one per internal H2D batch of <= 48 MB, GGCAT_B200_HOST_BATCH). */
+ * context); each call appends ONE bucket chunk: the host input travels in double-buffered H2D batches of <= 48 MB
+ * (GGCAT_B200_HOST_BATCH) whose kernels overlap the next copy, and the batches of a call are scattered together. */
 int32_t ggcat_b200_push_reads(ggcat_b200_ctx *ctx, const uint8_t *data, const uint64_t *offsets, uint64_t n_reads,
                               const uint32_t *colors);
 /* Same, with data/offsets/colors already resident in device memory of ctx's device. */
