@@ -184,6 +184,26 @@ class GGCATB200:
                           d_colors_ptr: Optional[int] = None):
         _check(self._lib.ggcat_b200_push_reads_device(self._h, d_data_ptr, d_offsets_ptr, n_reads, n_bytes, d_colors_ptr))
 
+    def push_text(self, text, fmt: int = 0, color: int = 0) -> int:
+        """Raw FASTA (fmt=0) / FASTQ (fmt=1) text (bytes or uint8 array, whole records): tokenised on the device
+        (ggcat_b200_push_text).  Returns the number of records found."""
+        a = np.frombuffer(text, np.uint8) if isinstance(text, (bytes, bytearray, memoryview)) else np.ascontiguousarray(text, np.uint8)
+        n = C.c_uint64(0)
+        _check(self._lib.ggcat_b200_push_text(self._h, a.ctypes.data if a.size else None, a.size, fmt, color, C.byref(n)))
+        return int(n.value)
+
+    def tokenize(self, text, fmt: int = 0):
+        """Test hook: (sequence bytes, offsets) the device tokenizer makes of raw FASTA / FASTQ text."""
+        import torch
+
+        a = np.frombuffer(text, np.uint8) if isinstance(text, (bytes, bytearray, memoryview)) else np.ascontiguousarray(text, np.uint8)
+        d = torch.from_numpy(a.copy()).cuda(self.params.device)
+        ps, po, nr, ns = C.c_void_p(0), C.c_void_p(0), C.c_uint64(0), C.c_uint64(0)
+        _check(self._lib.ggcat_b200_tokenize_device(self._h, d.data_ptr() if a.size else None, a.size, fmt, C.byref(ps), C.byref(po), C.byref(nr), C.byref(ns)))
+        seq = self._dev_bytes(ps.value or 0, int(ns.value))
+        off = self._dev_bytes(po.value or 0, (int(nr.value) + 1) * 8).view(np.uint64) if po.value else np.zeros(1, np.uint64)
+        return seq, off
+
     def finish_bucketing(self) -> BucketStats:
         st = _lib.BucketStatsC()
         _check(self._lib.ggcat_b200_finish_bucketing(self._h, C.byref(st)))

@@ -4,6 +4,7 @@
 #include "../../include/ggcat_b200.h"
 #include "merge128.cuh"
 #include "peer.cuh"
+#include "tokenize.cuh"
 
 #include <algorithm>
 #include <chrono>
@@ -90,11 +91,11 @@ struct Chunk {
 };
 
 enum Family { F_PACK = 0, F_WINDOWS, F_EMIT, F_SCATTER, F_SCAN, F_MERGE_HASH, F_MERGE_HASH_GLOBAL, F_MERGE_SMEM, F_MERGE_GLOBAL,
-              F_GATHER, F_MERGE_HASH128, F_SORT128, F_COLOR_FOLD, F_PARTITION, F_MERGE_HASH_PART, F_PEER, F_PEER_PUSH, F_COUNT };
+              F_GATHER, F_MERGE_HASH128, F_SORT128, F_COLOR_FOLD, F_PARTITION, F_MERGE_HASH_PART, F_PEER, F_PEER_PUSH, F_TOKENIZE, F_COUNT };
 static const char *kFamilyNames[F_COUNT] = {"k_pack+k_mark", "k_windows", "k_emit", "k_scatter", "k_exclusive_scan_u32",
                                             "k_merge_hash<smem>", "k_merge_hash<global>", "k_merge_units<smem>",
                                             "k_merge_units<global>", "k_gather_units", "k_merge_hash128", "k_sort_units128",
-                                            "k_color_fold", "k_partition_units", "k_merge_hash<partitions>", "k_peer_sync<exposed>", "k_peer_push<side streams>"};
+                                            "k_color_fold", "k_partition_units", "k_merge_hash<partitions>", "k_peer_sync<exposed>", "k_peer_push<side streams>", "k_tok_*"};
 
 struct TimedLaunch { int fam; cudaEvent_t a, b; };
 
@@ -180,6 +181,7 @@ struct ggcat_b200_ctx {
     struct UnitTot { uint64_t n; uint32_t sk, w, sl, pad; };
     std::vector<UnitTot> unit_tot;    // merge: per-unit totals over all chunks (kept allocated between merges)
     // phase-2 workspace
+    DevBuf tok_agg, tok_keep, tok_base, tok_marks, tok_tmarks, tok_seq, tok_offsets, tok_text, tok_colors;   // FASTA / FASTQ tokenizer (tokenize.cuh)
     DevBuf d_static_off;                   // wide path: static output regions of partitioned units
     DevBuf d_rkpos;                        // rabin-karp per-position tables
     DevBuf d_recfl;                        // flag bits of the wide path's partition records
@@ -1385,7 +1387,8 @@ void ggcat_b200_destroy(ggcat_b200_ctx *c) {
                       &c->tmp, &c->tmp_color, &c->cur_cnt, &c->totals, &c->d_views, &c->d_work[0], &c->d_work[1],
                       &c->d_work[2], &c->d_scratch, &c->out_keys, &c->out_cf, &c->out_keys2, &c->out_cf2,
                       &c->d_rkpos, &c->d_recfl, &c->d_mstage, &c->d_static_off, &c->cursor, &c->unit_out_off, &c->unit_out_cnt, &c->unit_final_off, &c->overflow, &c->d_retry,
-                      &c->d_partmeta, &c->d_recs, &c->fin_tmp_keys, &c->fin_tmp_cf,
+                      &c->d_partmeta, &c->d_recs, &c->fin_tmp_keys, &c->fin_tmp_cf, &c->tok_agg, &c->tok_keep, &c->tok_base, &c->tok_marks,
+                      &c->tok_tmarks, &c->tok_seq, &c->tok_offsets, &c->tok_text, &c->tok_colors,
                       &c->out_hi, &c->out_hi2, &c->unit_keys, &c->unit_cols, &c->col_off, &c->out_coloff, &c->out_colors})
         b->release();
     for (cudaEvent_t e : c->event_pool) cudaEventDestroy(e);
@@ -1502,6 +1505,113 @@ int32_t ggcat_b200_push_reads_device(ggcat_b200_ctx *c, const uint8_t *d_data, c
     int32_t rc = bucket_batch_device(c, d_data, d_offsets, n_reads, 0, n_bytes, c->P.colors ? d_colors : nullptr, n_bytes);
     if (rc) { abort_open_chunk(c); return rc; }
     return flush_open_chunk(c);
+}
+
+
+// ---- FASTA / FASTQ text on the device (tokenize.cuh) ----------------------------------------------
+extern "C++" {
+template <int FORMAT>
+static int32_t tokenize_device_impl(ggcat_b200_ctx *c, const uint8_t *d_text, uint64_t n, uint64_t *n_records, uint64_t *n_seq) {
+    cudaStream_t st = c->stream;
+    const uint32_t n_tiles = (uint32_t)((n + TOK_TILE - 1) / TOK_TILE);
+    CU(c->tok_agg.reserve(((size_t)n_tiles + 2) * 8)); CU(c->tok_keep.reserve(((size_t)n_tiles + 2) * 4)); CU(c->tok_base.reserve(((size_t)n_tiles + 2) * 4));
+    CU(c->tok_marks.reserve((n / 32 + 4) * 4)); CU(c->tok_seq.reserve(n + 64)); CU(c->totals.reserve(8 * 8));
+    CU(cudaMemsetAsync(c->tok_marks.p, 0, (n / 32 + 4) * 4, st));
+    {
+        LaunchTimer t(c, F_TOKENIZE, 5);
+        k_tok_tile_lines<FORMAT><<<n_tiles, TOK_THREADS, 0, st>>>(d_text, n, c->tok_agg.as<unsigned long long>());
+        k_tok_scan_tiles<FORMAT><<<1, 1024, 0, st>>>(c->tok_agg.as<unsigned long long>(), n_tiles);
+        k_tok_compact<FORMAT, false><<<n_tiles, TOK_THREADS, 0, st>>>(d_text, n, c->tok_agg.as<unsigned long long>(), c->tok_keep.as<uint32_t>(), nullptr, nullptr, nullptr);
+        k_exclusive_scan_u32<<<1, 1024, 0, st>>>(c->tok_keep.as<uint32_t>(), c->tok_base.as<uint32_t>(), n_tiles, c->totals.as<unsigned long long>() + 5);
+        k_tok_compact<FORMAT, true><<<n_tiles, TOK_THREADS, 0, st>>>(d_text, n, c->tok_agg.as<unsigned long long>(), nullptr, c->tok_base.as<uint32_t>(),
+                                                                    c->tok_seq.as<uint8_t>(), c->tok_marks.as<uint32_t>());
+    }
+    CU(cudaMemcpyAsync(c->h_pinned + 10, c->totals.as<unsigned long long>() + 5, 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    const uint64_t total = c->h_pinned[10];
+    uint64_t nrec = 0;
+    CU(c->tok_offsets.reserve(16));
+    if (total) {
+        const uint64_t n_words = total / 32 + 1;
+        const uint32_t mt = (uint32_t)((n_words + 255) / 256);
+        CU(c->tok_tmarks.reserve(((size_t)mt + 2) * 4 * 2));
+        uint32_t *tm = c->tok_tmarks.as<uint32_t>(), *tr = tm + mt + 2;
+        LaunchTimer t(c, F_TOKENIZE, 3);
+        k_tok_count_marks<<<mt, 256, 0, st>>>(c->tok_marks.as<uint32_t>(), n_words, total, tm);
+        k_exclusive_scan_u32<<<1, 1024, 0, st>>>(tm, tr, mt, c->totals.as<unsigned long long>() + 6);
+        CU(cudaMemcpyAsync(c->h_pinned + 11, c->totals.as<unsigned long long>() + 6, 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        nrec = c->h_pinned[11];
+        CU(c->tok_offsets.reserve((nrec + 2) * 8));
+        k_tok_write_offsets<<<mt, 256, 0, st>>>(c->tok_marks.as<uint32_t>(), n_words, tr, c->tok_offsets.as<uint64_t>());
+    }
+    c->h_pinned[12] = total;
+    CU(cudaMemcpyAsync(c->tok_offsets.as<uint64_t>() + nrec, c->h_pinned + 12, 8, cudaMemcpyHostToDevice, st));
+    CU(cudaGetLastError());
+    *n_records = nrec; *n_seq = total;
+    return 0;
+}
+
+static int32_t tokenize_device(ggcat_b200_ctx *c, const uint8_t *d_text, uint64_t n, int32_t format, uint64_t *n_records, uint64_t *n_seq) {
+    if (format != TOK_FASTA && format != TOK_FASTQ) return set_err(GGCAT_B200_ERR_INVALID, "text format %d unsupported (0 = FASTA, 1 = FASTQ)", format);
+    if (n == 0) { *n_records = *n_seq = 0; return 0; }
+    if (n > c->max_batch) return set_err(GGCAT_B200_ERR_INVALID, "text block of %llu bytes exceeds the batch limit %llu", (unsigned long long)n, (unsigned long long)c->max_batch);
+    return format == TOK_FASTA ? tokenize_device_impl<TOK_FASTA>(c, d_text, n, n_records, n_seq) : tokenize_device_impl<TOK_FASTQ>(c, d_text, n, n_records, n_seq);
+}
+__global__ void k_fill_u32(uint32_t *p, uint64_t n, uint32_t v) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+}  // extern "C++"
+
+int32_t ggcat_b200_tokenize_device(ggcat_b200_ctx *c, const uint8_t *d_text, uint64_t n_bytes, int32_t format, const uint8_t **d_seq,
+                                   const uint64_t **d_offsets, uint64_t *n_records, uint64_t *n_seq_bytes) {
+    TRY(check_ctx(c));
+    std::lock_guard<std::mutex> lock__(c->mu);
+    if (!d_text && n_bytes) return set_err(GGCAT_B200_ERR_INVALID, "null input");
+    uint64_t nr = 0, ns = 0;
+    TRY(tokenize_device(c, d_text, n_bytes, format, &nr, &ns));
+    CU(cudaStreamSynchronize(c->stream));
+    if (d_seq) *d_seq = c->tok_seq.as<uint8_t>();
+    if (d_offsets) *d_offsets = c->tok_offsets.as<uint64_t>();
+    if (n_records) *n_records = nr;
+    if (n_seq_bytes) *n_seq_bytes = ns;
+    return 0;
+}
+
+static int32_t push_text_device_locked(ggcat_b200_ctx *c, const uint8_t *d_text, uint64_t n_bytes, int32_t format, uint32_t color, uint64_t *n_records) {
+    if (c->finished) return set_err(GGCAT_B200_ERR_STATE, "push_text after finish_bucketing");
+    if (!d_text && n_bytes) return set_err(GGCAT_B200_ERR_INVALID, "null input");
+    uint64_t nr = 0, ns = 0;
+    TRY(tokenize_device(c, d_text, n_bytes, format, &nr, &ns));
+    if (n_records) *n_records = nr;
+    if (nr == 0) return 0;
+    const uint32_t *d_colors = nullptr;
+    if (c->P.colors) {
+        CU(c->tok_colors.reserve(nr * 4));
+        k_fill_u32<<<(unsigned)((nr + 255) / 256), 256, 0, c->stream>>>(c->tok_colors.as<uint32_t>(), nr, color);
+        d_colors = c->tok_colors.as<uint32_t>();
+    }
+    int32_t rc = bucket_batch_device(c, c->tok_seq.as<uint8_t>(), c->tok_offsets.as<uint64_t>(), nr, 0, ns, d_colors, ns);
+    if (rc) { abort_open_chunk(c); return rc; }
+    return flush_open_chunk(c);
+}
+
+int32_t ggcat_b200_push_text(ggcat_b200_ctx *c, const uint8_t *text, uint64_t n_bytes, int32_t format, uint32_t color, uint64_t *n_records) {
+    TRY(check_ctx(c));
+    if (!text && n_bytes) return set_err(GGCAT_B200_ERR_INVALID, "null input");
+    if (n_bytes > c->max_batch) return set_err(GGCAT_B200_ERR_INVALID, "text block of %llu bytes exceeds the batch limit %llu: push whole records in smaller blocks",
+                                               (unsigned long long)n_bytes, (unsigned long long)c->max_batch);
+    std::lock_guard<std::mutex> lock__(c->mu);
+    CU(c->tok_text.reserve(n_bytes + 64));
+    CU(cudaMemcpyAsync(c->tok_text.p, text, n_bytes, cudaMemcpyHostToDevice, c->stream));
+    return push_text_device_locked(c, c->tok_text.as<uint8_t>(), n_bytes, format, color, n_records);
+}
+
+int32_t ggcat_b200_push_text_device(ggcat_b200_ctx *c, const uint8_t *d_text, uint64_t n_bytes, int32_t format, uint32_t color, uint64_t *n_records) {
+    TRY(check_ctx(c));
+    std::lock_guard<std::mutex> lock__(c->mu);
+    return push_text_device_locked(c, d_text, n_bytes, format, color, n_records);
 }
 
 int32_t ggcat_b200_finish_bucketing(ggcat_b200_ctx *c, ggcat_b200_bucket_stats *stats) {

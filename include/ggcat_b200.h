@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define GGCAT_B200_ABI_VERSION 5
+#define GGCAT_B200_ABI_VERSION 6
 
 typedef enum {
     GGCAT_B200_OK = 0,
@@ -129,6 +129,25 @@ int32_t ggcat_b200_push_reads(ggcat_b200_ctx *ctx, const uint8_t *data, const ui
 /* Same, with data/offsets/colors already resident in device memory of ctx's device. */
 int32_t ggcat_b200_push_reads_device(ggcat_b200_ctx *ctx, const uint8_t *d_data, const uint64_t *d_offsets,
                                      uint64_t n_reads, uint64_t n_bytes, const uint32_t *d_colors);
+/* Input side on the device: raw FASTA / FASTQ TEXT instead of tokenised records.  Replaces the
+ * reference's line reader and record state machines (crates/io/src/lines_reader.rs:140-175,
+ * crates/io/src/sequences_reader.rs:106-179 process_fasta, :181-241 process_fastq): '>' lines start a record, ';' lines
+ * are comments, every other line is appended to the record's bases ('\n' and a '\r' right before it dropped); FASTQ is
+ * strict 4-line records; records without bases are not emitted.  The block must hold whole records (a record may not
+ * continue in the next call) and at most 2^30 bytes; decompression (.gz) stays on the host.  Every record gets `color`.
+ * Records longer than the reference's 4 MiB split (sequences_reader.rs:119-122) are processed in one piece here -- same
+ * k-mers, no k-1 overlap copies needed. */
+typedef enum { GGCAT_B200_TEXT_FASTA = 0, GGCAT_B200_TEXT_FASTQ = 1 } ggcat_b200_text_format;
+int32_t ggcat_b200_push_text(ggcat_b200_ctx *ctx, const uint8_t *text, uint64_t n_bytes, int32_t format, uint32_t color,
+                             uint64_t *n_records);
+int32_t ggcat_b200_push_text_device(ggcat_b200_ctx *ctx, const uint8_t *d_text, uint64_t n_bytes, int32_t format,
+                                    uint32_t color, uint64_t *n_records);
+/* The tokenizer alone: d_seq / d_offsets (n_records + 1 entries) are device buffers owned by the context, valid until
+ * the next tokenize / push_text call. */
+int32_t ggcat_b200_tokenize_device(ggcat_b200_ctx *ctx, const uint8_t *d_text, uint64_t n_bytes, int32_t format,
+                                   const uint8_t **d_seq, const uint64_t **d_offsets, uint64_t *n_records,
+                                   uint64_t *n_seq_bytes);
+
 /* Returns as soon as the per-unit counts of every chunk are on the host (they are final before the last scatter
  * kernel ends); later calls are ordered on the context stream.  Callers that read chunk buffers from another stream
  * go through export_chunk_slice (which synchronises) or call ggcat_b200_synchronize(). */

@@ -802,3 +802,116 @@ def test_push_reads_from_several_threads():
         _check_tables(G, ctx, reads, sk, k, s, b1, b2)
     finally:
         ctx.close()
+
+
+# ------------------------------------------------------------------ FASTA / FASTQ text on the device
+def _parse_fasta_ref(text: bytes):
+    """The reference's process_fasta (crates/io/src/sequences_reader.rs:106-179) restated line by line."""
+    recs, cur = [], bytearray()
+    for raw in text.split(b"\n"):
+        line = raw[:-1] if raw.endswith(b"\r") else raw
+        if line[:1] == b">":
+            if cur:
+                recs.append(bytes(cur))
+            cur = bytearray()
+        elif line[:1] == b";":
+            continue
+        else:
+            cur += line
+    if cur:
+        recs.append(bytes(cur))
+    return recs
+
+
+def _parse_fastq_ref(text: bytes):
+    """process_fastq (sequences_reader.rs:181-241): strict 4-line records."""
+    lines = text.split(b"\n")
+    if lines and lines[-1] == b"":
+        lines = lines[:-1]
+    recs = []
+    for i in range(1, len(lines), 4):
+        ln = lines[i][:-1] if lines[i].endswith(b"\r") else lines[i]
+        if ln:
+            recs.append(bytes(ln))
+    return recs
+
+
+def _fasta_text(rng, n_rec, crlf=False):
+    eol = b"\r\n" if crlf else b"\n"
+    out = bytearray()
+    if rng.random() < 0.5:
+        out += util.rand_seq(rng, 37) + eol            # bases before the first ident line form a record too
+    for r in range(n_rec):
+        out += b">rec%d some description" % r + eol
+        if rng.random() < 0.1:
+            out += b";a comment line" + eol
+        L = int(rng.integers(0, 700))
+        s = util.rand_seq(rng, L, b"ACGTNacgt")
+        w = int(rng.integers(20, 90))
+        for a in range(0, L, w):
+            out += s[a:a + w] + eol
+        if rng.random() < 0.1:
+            out += eol                                     # empty line inside / after a record
+    if rng.random() < 0.5:
+        out = out[:-len(eol)]                              # file without a trailing newline
+    return bytes(out)
+
+
+@pytest.mark.parametrize("seed,crlf", [(1, False), (2, True), (3, False)])
+def test_device_tokenizer_fasta_matches_reader_semantics(seed, crlf):
+    G = _gpu()
+    rng = np.random.default_rng(seed)
+    text = _fasta_text(rng, 400 if seed < 3 else 5000, crlf)
+    want = _parse_fasta_ref(text)
+    ctx = G.GGCATB200(G.Params(k=31, buckets_count_log=2, second_buckets_count_log=1))
+    try:
+        seq, off = ctx.tokenize(text, 0)
+        got = [seq[int(off[i]):int(off[i + 1])].tobytes() for i in range(off.size - 1)]
+        assert got == want
+    finally:
+        ctx.close()
+
+
+def test_device_tokenizer_fastq_and_edge_cases():
+    G = _gpu()
+    rng = np.random.default_rng(9)
+    recs = [util.rand_seq(rng, int(rng.integers(1, 300)), b"ACGTN") for _ in range(3000)]
+    fq = b"".join(b"@r%d\n" % i + r + b"\n+\n" + b"I" * len(r) + b"\n" for i, r in enumerate(recs))
+    ctx = G.GGCATB200(G.Params(k=31, buckets_count_log=2, second_buckets_count_log=1))
+    try:
+        for text in (fq, fq[:-1], fq.replace(b"\n", b"\r\n")):
+            seq, off = ctx.tokenize(text, 1)
+            got = [seq[int(off[i]):int(off[i + 1])].tobytes() for i in range(off.size - 1)]
+            assert got == _parse_fastq_ref(text)
+        for text in (b"", b">only a header\n", b">h1\n>h2\nACGT\n>h3\n", b"ACGT", b"\n\n>x\n\nAC\n\nGT\n"):
+            seq, off = ctx.tokenize(text, 0)
+            got = [seq[int(off[i]):int(off[i + 1])].tobytes() for i in range(off.size - 1)]
+            assert got == _parse_fasta_ref(text), text
+    finally:
+        ctx.close()
+
+
+def test_push_text_c1_files_equal_tokenised_push(golden_dir):
+    """BASELINE configs[0] from the FASTA text itself: the three example files (multi-line FASTA, gunzipped on the host)
+    pushed as raw text give the same super-k-mer counts and the same table digests as the tokenised records."""
+    import gzip
+
+    G = _gpu()
+    k, m, b1, b2, s = 31, 12, 2, 6, 1
+    recs = util.c1_records()
+    reads = O.Reads.from_list(recs)
+    ctx_a, st_a = G.minimizer_bucketing([(reads.data, reads.offsets)], b1, b2, k, m, min_multiplicity=s)
+    ctx_b = G.GGCATB200(G.Params(k=k, m=m, min_multiplicity=s, buckets_count_log=b1, second_buckets_count_log=b2))
+    try:
+        n = 0
+        for f in ("sal1.fa.gz", "sal2.fa.gz", "sal3.fa.gz"):
+            n += ctx_b.push_text(gzip.open(golden_dir / f, "rb").read(), 0)
+        assert n == len(recs)
+        st_b = ctx_b.finish_bucketing()
+        assert (st_b.n_superkmers, st_b.n_kmers, st_b.valid_bases) == (st_a.n_superkmers, st_a.n_kmers, st_a.valid_bases)
+        nb = (1 << b1) + 1
+        ta, tb = ctx_a.merge_bucket_range(0, nb), ctx_b.merge_bucket_range(0, nb)
+        assert np.array_equal(ta.keys_lo, tb.keys_lo) and np.array_equal(ta.count_flags, tb.count_flags)
+        assert np.array_equal(ta.unit_offsets, tb.unit_offsets)
+    finally:
+        ctx_a.close(); ctx_b.close()
