@@ -66,6 +66,8 @@ SYMBOLS = {
     "ggcat_b200_push_text": (_i32, [_vp, _vp, _u64, _i32, _u32, C.POINTER(_u64)]),
     "ggcat_b200_push_text_device": (_i32, [_vp, _vp, _u64, _i32, _u32, C.POINTER(_u64)]),
     "ggcat_b200_tokenize_device": (_i32, [_vp, _vp, _u64, _i32, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_u64), C.POINTER(_u64)]),
+    "ggcat_b200_write_bucket_file": (_i32, [_vp, _u32, C.c_char_p, C.POINTER(_u64)]),
+    "ggcat_b200_import_bucket_file": (_i32, [_vp, _u32, C.c_char_p, C.POINTER(_u64)]),
     "ggcat_b200_finish_bucketing": (_i32, [_vp, C.POINTER(BucketStatsC)]),
     "ggcat_b200_unit_sizes": (_i32, [_vp, _vp, _vp]),
     "ggcat_b200_dump_superkmers": (_i32, [_vp, _u32, _vp, _u64, _vp, _u64, C.POINTER(_u64), C.POINTER(_u64)]),

@@ -204,6 +204,18 @@ class GGCATB200:
         off = self._dev_bytes(po.value or 0, (int(nr.value) + 1) * 8).view(np.uint64) if po.value else np.zeros(1, np.uint64)
         return seq, off
 
+    def write_bucket_file(self, bucket: int, path) -> int:
+        """One first-level bucket as a reference-format bucket file (ggcat_b200_write_bucket_file); returns its records."""
+        n = C.c_uint64(0)
+        _check(self._lib.ggcat_b200_write_bucket_file(self._h, bucket, str(path).encode(), C.byref(n)))
+        return int(n.value)
+
+    def import_bucket_file(self, bucket: int, path) -> int:
+        """Registers the super-k-mers of a reference-format bucket file as a bucket chunk (before finish_bucketing)."""
+        n = C.c_uint64(0)
+        _check(self._lib.ggcat_b200_import_bucket_file(self._h, bucket, str(path).encode(), C.byref(n)))
+        return int(n.value)
+
     def finish_bucketing(self) -> BucketStats:
         st = _lib.BucketStatsC()
         _check(self._lib.ggcat_b200_finish_bucketing(self._h, C.byref(st)))

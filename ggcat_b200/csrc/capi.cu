@@ -5,6 +5,7 @@
 #include "merge128.cuh"
 #include "peer.cuh"
 #include "tokenize.cuh"
+#include "wire.hpp"
 
 #include <algorithm>
 #include <chrono>
@@ -1614,6 +1615,118 @@ int32_t ggcat_b200_push_text_device(ggcat_b200_ctx *c, const uint8_t *d_text, ui
     return push_text_device_locked(c, d_text, n_bytes, format, color, n_records);
 }
 
+
+// ---- the reference's bucket file format (wire.hpp) --------------------------------------------------
+static int32_t dump_superkmers_impl(ggcat_b200_ctx *c, uint32_t bucket, ggcat_b200_superkmer *out, uint64_t cap, uint8_t *payload,
+                                    uint64_t payload_cap, uint64_t *n_out, uint64_t *payload_bytes);
+int32_t ggcat_b200_write_bucket_file(ggcat_b200_ctx *c, uint32_t bucket, const char *path, uint64_t *n_records) {
+    TRY(check_ctx(c));
+    std::lock_guard<std::mutex> lock__(c->mu);
+    if (!path) return set_err(GGCAT_B200_ERR_INVALID, "null path");
+    if (c->P.colors) return set_err(GGCAT_B200_ERR_INVALID, "bucket files of coloured builds are not written (the colour varint depends on the reference writer's buffer state)");
+    uint64_t n = 0, pb = 0;
+    TRY(dump_superkmers_impl(c, bucket, nullptr, 0, nullptr, 0, &n, &pb));
+    std::vector<ggcat_b200_superkmer> sk(n);
+    std::vector<uint8_t> payload(pb + 16);
+    if (n) TRY(dump_superkmers_impl(c, bucket, sk.data(), n, payload.data(), pb, &n, &pb));
+    // group by sub-bucket, keeping the order inside each group
+    const uint32_t nsub = 1u << c->P.b2;
+    std::vector<uint64_t> cnt(nsub + 1, 0);
+    for (auto &r : sk) cnt[r.second_bucket + 1]++;
+    for (uint32_t q = 0; q < nsub; q++) cnt[q + 1] += cnt[q];
+    std::vector<uint32_t> order(n);
+    {
+        std::vector<uint64_t> cur(cnt.begin(), cnt.end() - 1);
+        for (uint64_t i = 0; i < n; i++) order[cur[sk[i].second_bucket]++] = (uint32_t)i;
+    }
+    ggb_wire::Writer w(c->P.k);
+    for (uint32_t q = 0; q < nsub; q++) {
+        if (cnt[q + 1] == cnt[q]) continue;
+        w.begin_sub_bucket(q, cnt[q + 1] - cnt[q]);
+        for (uint64_t i = cnt[q]; i < cnt[q + 1]; i++) {
+            const ggcat_b200_superkmer &r = sk[order[i]];
+            w.record(r.len, r.minimizer_pos, r.flags, payload.data() + r.payload_offset);
+        }
+    }
+    w.finish();
+    FILE *f = fopen(path, "wb");
+    if (!f) return set_err(GGCAT_B200_ERR_INVALID, "cannot create %s", path);
+    const bool ok = fwrite(w.out.data(), 1, w.out.size(), f) == w.out.size();
+    if (fclose(f) != 0 || !ok) return set_err(GGCAT_B200_ERR_INVALID, "short write to %s", path);
+    if (n_records) *n_records = n;
+    return 0;
+}
+
+int32_t ggcat_b200_import_bucket_file(ggcat_b200_ctx *c, uint32_t bucket, const char *path, uint64_t *n_records) {
+    TRY(check_ctx(c));
+    std::lock_guard<std::mutex> lock__(c->mu);
+    const DevParams &P = c->P;
+    if (!path) return set_err(GGCAT_B200_ERR_INVALID, "null path");
+    if (c->finished) return set_err(GGCAT_B200_ERR_STATE, "import_bucket_file after finish_bucketing");
+    if (P.colors) return set_err(GGCAT_B200_ERR_INVALID, "bucket files of coloured builds are not read");
+    if (bucket > (1u << P.b1)) return set_err(GGCAT_B200_ERR_INVALID, "bucket %u out of range", bucket);
+    std::vector<uint8_t> file;
+    {
+        FILE *f = fopen(path, "rb");
+        if (!f) return set_err(GGCAT_B200_ERR_INVALID, "cannot open %s", path);
+        fseek(f, 0, SEEK_END);
+        const long sz = ftell(f);
+        fseek(f, 0, SEEK_SET);
+        file.resize(sz > 0 ? (size_t)sz : 0);
+        const bool ok = file.empty() || fread(file.data(), 1, file.size(), f) == file.size();
+        fclose(f);
+        if (!ok) return set_err(GGCAT_B200_ERR_INVALID, "short read from %s", path);
+    }
+    std::vector<ggb_wire::Record> recs;
+    const std::string err = ggb_wire::parse(file, P.k, recs);
+    if (!err.empty()) return set_err(GGCAT_B200_ERR_INVALID, "%s: %s", path, err.c_str());
+    if (n_records) *n_records = recs.size();
+    if (recs.empty()) return 0;
+    const uint32_t nsub = 1u << P.b2;
+    std::vector<uint32_t> h_cnt(nsub + 1, 0), h_words(nsub + 1, 0), h_kmers(nsub + 1, 0), h_off(nsub + 1, 0), h_woff(nsub + 1, 0);
+    for (auto &r : recs) {
+        if (r.sub_bucket >= nsub) return set_err(GGCAT_B200_ERR_INVALID, "%s: sub-bucket %u >= %u", path, r.sub_bucket, nsub);
+        if (r.len < P.k) return set_err(GGCAT_B200_ERR_INVALID, "%s: record shorter than k", path);
+        h_cnt[r.sub_bucket]++; h_words[r.sub_bucket] += (r.len + 15) / 16; h_kmers[r.sub_bucket] += r.len - P.k + 1;
+    }
+    uint64_t a = 0, b = 0, km = 0;
+    for (uint32_t q = 0; q < nsub; q++) { h_off[q] = (uint32_t)a; h_woff[q] = (uint32_t)b; a += h_cnt[q]; b += h_words[q]; km += h_kmers[q]; }
+    h_off[nsub] = (uint32_t)a; h_woff[nsub] = (uint32_t)b;
+    if (b >= (1ull << 32)) return set_err(GGCAT_B200_ERR_INVALID, "%s: payload exceeds 2^32 words", path);
+    std::vector<uint4> desc(a);
+    std::vector<uint32_t> payload(b + 8, 0);
+    {
+        std::vector<uint32_t> cd(h_off.begin(), h_off.end()), cw(h_woff.begin(), h_woff.end());
+        for (auto &r : recs) {
+            const uint32_t slot = cd[r.sub_bucket]++, woff = cw[r.sub_bucket];
+            cw[r.sub_bucket] += (r.len + 15) / 16;
+            desc[slot] = make_uint4(woff, r.len, make_meta(r.minimizer_pos, r.flags, 0u, r.sub_bucket), 0u);
+            memcpy(reinterpret_cast<uint8_t *>(payload.data() + woff), file.data() + r.byte_off, (r.len + 3) / 4);
+        }
+    }
+    Chunk *ch = new Chunk();
+    ch->imported = true; ch->first_unit = bucket << P.b2; ch->n_units = nsub; ch->word_bias = 0;
+    cudaError_t e = ch->desc.reserve(a * 16);
+    if (e == cudaSuccess) e = ch->payload.reserve((b + 8) * 4);
+    for (DevBuf *d : {&ch->unit_cnt, &ch->unit_off, &ch->unit_words, &ch->unit_woff, &ch->unit_kmers})
+        if (e == cudaSuccess) e = d->reserve(((size_t)nsub + 2) * 4);
+    auto up = [&](DevBuf &d, const void *src, size_t bytes) { if (e == cudaSuccess) e = cudaMemcpyAsync(d.p, src, bytes, cudaMemcpyHostToDevice, c->stream); };
+    up(ch->desc, desc.data(), a * 16); up(ch->payload, payload.data(), (b + 8) * 4);
+    up(ch->unit_cnt, h_cnt.data(), (nsub + 1) * 4); up(ch->unit_off, h_off.data(), (nsub + 1) * 4);
+    up(ch->unit_words, h_words.data(), (nsub + 1) * 4); up(ch->unit_woff, h_woff.data(), (nsub + 1) * 4);
+    up(ch->unit_kmers, h_kmers.data(), (nsub + 1) * 4);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);      // the host vectors go out of scope
+    if (e != cudaSuccess) { ch->release(); delete ch; return set_err(GGCAT_B200_ERR_CUDA, "bucket file upload failed: %s", cudaGetErrorString(e)); }
+    ch->d_desc = ch->desc.as<uint4>(); ch->d_payload = ch->payload.as<uint32_t>();
+    ch->d_unit_cnt = ch->unit_cnt.as<uint32_t>(); ch->d_unit_off = ch->unit_off.as<uint32_t>();
+    ch->d_unit_words = ch->unit_words.as<uint32_t>(); ch->d_unit_woff = ch->unit_woff.as<uint32_t>();
+    ch->d_unit_kmers = ch->unit_kmers.as<uint32_t>();
+    ch->h_cnt = h_cnt; ch->h_words = h_words; ch->h_kmers = h_kmers; ch->h_off = h_off; ch->h_woff = h_woff;
+    ch->n_sk = a; ch->n_words = b; ch->n_kmers = km;
+    c->chunks.push_back(ch);
+    return 0;
+}
+
 int32_t ggcat_b200_finish_bucketing(ggcat_b200_ctx *c, ggcat_b200_bucket_stats *stats) {
     TRY(check_ctx(c));
     std::lock_guard<std::mutex> lock__(c->mu);
@@ -1656,6 +1769,10 @@ int32_t ggcat_b200_dump_superkmers(ggcat_b200_ctx *c, uint32_t bucket, ggcat_b20
                                    uint64_t payload_cap, uint64_t *n_out, uint64_t *payload_bytes) {
     TRY(check_ctx(c));
     std::lock_guard<std::mutex> lock__(c->mu);
+    return dump_superkmers_impl(c, bucket, out, cap, payload, payload_cap, n_out, payload_bytes);
+}
+static int32_t dump_superkmers_impl(ggcat_b200_ctx *c, uint32_t bucket, ggcat_b200_superkmer *out, uint64_t cap, uint8_t *payload,
+                                    uint64_t payload_cap, uint64_t *n_out, uint64_t *payload_bytes) {
     if (!c->finished) return set_err(GGCAT_B200_ERR_STATE, "dump before finish_bucketing");
     const DevParams &P = c->P;
     if (bucket > (1u << P.b1)) return set_err(GGCAT_B200_ERR_INVALID, "bucket %u out of range", bucket);

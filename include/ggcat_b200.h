@@ -153,6 +153,18 @@ int32_t ggcat_b200_tokenize_device(ggcat_b200_ctx *ctx, const uint8_t *d_text, u
  * go through export_chunk_slice (which synchronises) or call ggcat_b200_synchronize(). */
 int32_t ggcat_b200_finish_bucketing(ggcat_b200_ctx *ctx, ggcat_b200_bucket_stats *stats);
 
+/* The reference's bucket FILE format, so that a GPU phase 1 can feed an unmodified CPU phase 2 and a
+ * CPU phase 1 can feed this phase 2: one PLAIN_INTR_BKT_M bucket file per first-level bucket, chunks grouped by
+ * sub-bucket with ReadsCheckpointData checkpoints, MinimizerBucketMode::SingleGrouped records -- what the reference's
+ * compactor leaves behind (crates/minimizer_bucketing/src/compactor.rs:370-420) and SplittedBucket::generate /
+ * decode_sequences read (split_buckets.rs:46-131, decode_helper.rs:14-63); container:
+ * libs-crates/parallel-processor-rs/src/buckets/writers/{mod.rs:15-70,lock_free_binary_writer.rs},
+ * readers/binary_reader.rs:120-190; record: crates/io/src/concurrent/temp_reads/creads_utils.rs:374-434.
+ * write: after finish_bucketing.  import: before finish_bucketing, instead of (or beside) push_reads; lz4
+ * (CPLZ4_INTR_BKT_M) files and Compacted / coloured records are rejected.  Uncoloured builds only. */
+int32_t ggcat_b200_write_bucket_file(ggcat_b200_ctx *ctx, uint32_t bucket, const char *path, uint64_t *n_records);
+int32_t ggcat_b200_import_bucket_file(ggcat_b200_ctx *ctx, uint32_t bucket, const char *path, uint64_t *n_records);
+
 /* Per-unit sizes after finish_bucketing: arrays of stats.n_units entries (either may be NULL). */
 int32_t ggcat_b200_unit_sizes(ggcat_b200_ctx *ctx, uint64_t *n_superkmers, uint64_t *n_kmers);
 

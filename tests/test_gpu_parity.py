@@ -915,3 +915,98 @@ def test_push_text_c1_files_equal_tokenised_push(golden_dir):
         assert np.array_equal(ta.unit_offsets, tb.unit_offsets)
     finally:
         ctx_a.close(); ctx_b.close()
+
+
+# ------------------------------------------------------------------ the reference's bucket file format
+def _bincode_varint(buf, p):
+    b = buf[p]
+    if b < 251:
+        return b, p + 1
+    n = {251: 2, 252: 4, 253: 8}[b]
+    return int.from_bytes(buf[p + 1:p + 1 + n], "little"), p + 1 + n
+
+
+def _parse_bucket_file(buf: bytes, k: int):
+    """Independent reader of a PLAIN SingleGrouped bucket file, following
+    parallel-processor-rs/src/buckets/readers/binary_reader.rs:120-190 and crates/io/src/varint.rs:58-84:
+    -> {sub_bucket: [record bytes incl. the varint_flags header]} in file order."""
+    assert buf[:16] == b"PLAIN_INTR_BKT_M"
+    index_offset = int.from_bytes(buf[16:24], "little")
+    fmt = buf[24:56]
+    assert fmt[0] == 1 and not any(fmt[1:]), "data_format_info = bincode(MinimizerBucketMode::SingleGrouped)"
+    n, p = _bincode_varint(buf, index_offset)
+    cps = []
+    for _ in range(n):
+        off, p = _bincode_varint(buf, p)
+        opt = buf[p]; p += 1
+        data = None
+        if opt == 1:
+            ln, p = _bincode_varint(buf, p)
+            sub, q = _bincode_varint(buf, p)
+            cnt, q = _bincode_varint(buf, q)
+            assert q == p + ln
+            data = (sub, cnt); p += ln
+        cps.append((off, data))
+    assert p == len(buf), "the checkpoint index is the last thing in the file"
+    assert cps[0] == (56, None), "first checkpoint: right behind the header, no data"
+    assert [c[0] for c in cps] == sorted(c[0] for c in cps)
+    klog = (k - 1).bit_length()
+    out = {}
+    for i, (off, data) in enumerate(cps):
+        if data is None:
+            continue
+        end = cps[i + 1][0] if i + 1 < len(cps) else index_offset
+        recs, q = [], off
+        while q < end:
+            start = q
+            f = buf[q]; q += 1
+            v, sh, nxt = f & 31, 5, bool(f & 32)
+            while nxt:
+                b = buf[q]; q += 1
+                nxt = bool(b & 128); v |= (b & 127) << sh; sh += 7
+            ln = (v >> klog) + k
+            q += (ln + 3) // 4
+            recs.append(bytes(buf[start:q]))
+        assert q == end and len(recs) == data[1]
+        assert data[0] not in out, "one chunk per sub-bucket"
+        out[data[0]] = recs
+    return out
+
+
+@pytest.mark.parametrize("k,m", [(31, 12), (21, 10)])
+def test_bucket_files_reference_format_roundtrip(k, m, tmp_path):
+    """GPU phase 1 -> the reference's bucket files (what its phase 2 reads) -> records byte-equal to the oracle's
+    serialisation (creads_utils.rs:374-434 restated in oracle/ggcat_oracle.c); then the files are imported into a fresh
+    context (a CPU phase 1 feeding the GPU phase 2) and the merged tables are identical."""
+    G = _gpu()
+    rng = np.random.default_rng(31 + k)
+    b1, b2, s = 2, 3, 2
+    seqs = _mixed_reads(rng, k, n=500) + [util.rand_seq(rng, 30000)]
+    reads = O.Reads.from_list(seqs)
+    sk, _ = O.bucketing(reads, k, m, b1, b2)
+    ctx, st = G.minimizer_bucketing([(reads.data, reads.offsets)], b1, b2, k, m, min_multiplicity=s)
+    nb = (1 << b1) + 1
+    ctx2 = G.GGCATB200(G.Params(k=k, m=m, min_multiplicity=s, buckets_count_log=b1, second_buckets_count_log=b2))
+    try:
+        total = 0
+        for b in range(nb):
+            path = tmp_path / f"bucket.{b}"
+            n = ctx.write_bucket_file(b, path)
+            total += n
+            got = _parse_bucket_file(path.read_bytes(), k)
+            want = {}
+            for row in sk[sk["bucket"] == b]:
+                want.setdefault(int(row["second_bucket"]), []).append(O.superkmer_record(reads, row, k)[1:])   # without the leading second-bucket byte
+            assert set(got) == set(want)
+            for sub in want:
+                assert sorted(got[sub]) == sorted(want[sub]), f"bucket {b} sub-bucket {sub}"
+            assert ctx2.import_bucket_file(b, path) == n
+        assert total == st.n_superkmers
+        st2 = ctx2.finish_bucketing()
+        assert (st2.n_superkmers, st2.n_kmers) == (st.n_superkmers, st.n_kmers)
+        ta, tb = ctx.merge_bucket_range(0, nb), ctx2.merge_bucket_range(0, nb)
+        assert np.array_equal(ta.keys_lo, tb.keys_lo) and np.array_equal(ta.count_flags, tb.count_flags)
+        assert np.array_equal(ta.unit_offsets, tb.unit_offsets)
+        _check_tables(G, ctx2, reads, sk, k, s, b1, b2)
+    finally:
+        ctx.close(); ctx2.close()
