@@ -41,6 +41,16 @@ class TableC(C.Structure):
     ]
 
 
+class UnitigC(C.Structure):
+    _fields_ = [("word_offset", C.c_uint64), ("len", C.c_uint32), ("unit", C.c_uint32), ("bucket", C.c_uint16),
+                ("flags", C.c_uint8), ("last_align", C.c_uint8), ("n_kmers", C.c_uint32)]
+
+
+class UnitigsC(C.Structure):
+    _fields_ = [("n_unitigs", C.c_uint64), ("n_words", C.c_uint64), ("n_kmers", C.c_uint64), ("unitigs", C.POINTER(UnitigC)),
+                ("bases", C.POINTER(C.c_uint32)), ("d_unitigs", C.c_void_p), ("d_bases", C.c_void_p)]
+
+
 class ChunkSliceC(C.Structure):
     _fields_ = [
         ("n_superkmers", C.c_uint64), ("n_words", C.c_uint64), ("word_bias", C.c_uint64),
@@ -75,6 +85,7 @@ SYMBOLS = {
     "ggcat_b200_release_table": (_i32, [_vp, C.POINTER(TableC)]),
     "ggcat_b200_merge_bucket_range_device": (_i32, [_vp, _u32, _u32, C.POINTER(_u64), C.POINTER(_u64), C.POINTER(_u64)]),
     "ggcat_b200_device_table": (_i32, [_vp, C.POINTER(TableC)]),
+    "ggcat_b200_partial_unitigs": (_i32, [_vp, _u32, C.POINTER(UnitigsC)]),
     "ggcat_b200_reset": (_i32, [_vp]),
     "ggcat_b200_n_chunks": (_u32, [_vp]),
     "ggcat_b200_export_chunk_slice": (_i32, [_vp, _u32, _u32, _u32, C.POINTER(ChunkSliceC)]),

@@ -327,6 +327,19 @@ class GGCATB200:
         tab.n_entries_total = int(t.n_entries)
         return tab
 
+    UNITIG_DTYPE = np.dtype([("word_offset", "<u8"), ("len", "<u4"), ("unit", "<u4"), ("bucket", "<u2"), ("flags", "u1"),
+                             ("last_align", "u1"), ("n_kmers", "<u4")])
+
+    def partial_unitigs(self, result_buckets_log: int = 3):
+        """Partial unitigs of the table left by the last merge_bucket_range_device, built on the device
+        (ggcat_b200_partial_unitigs).  Returns (records: structured array, bases: uint32 words, total k-mers)."""
+        u = _lib.UnitigsC()
+        _check(self._lib.ggcat_b200_partial_unitigs(self._h, result_buckets_log, C.byref(u)))
+        n, nw = int(u.n_unitigs), int(u.n_words)
+        recs = np.ctypeslib.as_array(C.cast(u.unitigs, C.POINTER(C.c_uint8)), shape=(n * 24,)).copy().view(self.UNITIG_DTYPE) if n else np.zeros(0, self.UNITIG_DTYPE)
+        bases = np.ctypeslib.as_array(u.bases, shape=(nw,)).copy() if nw else np.zeros(0, np.uint32)
+        return recs, bases, int(u.n_kmers)
+
     # -- multi-GPU plumbing
     def n_chunks(self) -> int:
         return int(self._lib.ggcat_b200_n_chunks(self._h))

@@ -6,6 +6,7 @@
 #include "peer.cuh"
 #include "tokenize.cuh"
 #include "wire.hpp"
+#include "unitigs.cuh"
 
 #include <algorithm>
 #include <chrono>
@@ -92,11 +93,11 @@ struct Chunk {
 };
 
 enum Family { F_PACK = 0, F_WINDOWS, F_EMIT, F_SCATTER, F_SCAN, F_MERGE_HASH, F_MERGE_HASH_GLOBAL, F_MERGE_SMEM, F_MERGE_GLOBAL,
-              F_GATHER, F_MERGE_HASH128, F_SORT128, F_COLOR_FOLD, F_PARTITION, F_MERGE_HASH_PART, F_PEER, F_PEER_PUSH, F_TOKENIZE, F_COUNT };
+              F_GATHER, F_MERGE_HASH128, F_SORT128, F_COLOR_FOLD, F_PARTITION, F_MERGE_HASH_PART, F_PEER, F_PEER_PUSH, F_TOKENIZE, F_UNITIGS, F_COUNT };
 static const char *kFamilyNames[F_COUNT] = {"k_pack+k_mark", "k_windows", "k_emit", "k_scatter", "k_exclusive_scan_u32",
                                             "k_merge_hash<smem>", "k_merge_hash<global>", "k_merge_units<smem>",
                                             "k_merge_units<global>", "k_gather_units", "k_merge_hash128", "k_sort_units128",
-                                            "k_color_fold", "k_partition_units", "k_merge_hash<partitions>", "k_peer_sync<exposed>", "k_peer_push<side streams>", "k_tok_*"};
+                                            "k_color_fold", "k_partition_units", "k_merge_hash<partitions>", "k_peer_sync<exposed>", "k_peer_push<side streams>", "k_tok_*", "k_unitig_*"};
 
 struct TimedLaunch { int fam; cudaEvent_t a, b; };
 
@@ -182,6 +183,8 @@ struct ggcat_b200_ctx {
     struct UnitTot { uint64_t n; uint32_t sk, w, sl, pad; };
     std::vector<UnitTot> unit_tot;    // merge: per-unit totals over all chunks (kept allocated between merges)
     // phase-2 workspace
+    DevBuf ut_links, ut_visited, ut_recs, ut_bases, ut_counters;   // partial unitigs (unitigs.cuh)
+    uint8_t *h_unitigs = nullptr; size_t h_unitigs_cap = 0;        // pinned: records, then packed bases
     DevBuf tok_agg, tok_keep, tok_base, tok_marks, tok_tmarks, tok_seq, tok_offsets, tok_text, tok_colors;   // FASTA / FASTQ tokenizer (tokenize.cuh)
     DevBuf d_static_off;                   // wide path: static output regions of partitioned units
     DevBuf d_rkpos;                        // rabin-karp per-position tables
@@ -1389,7 +1392,8 @@ void ggcat_b200_destroy(ggcat_b200_ctx *c) {
                       &c->d_work[2], &c->d_scratch, &c->out_keys, &c->out_cf, &c->out_keys2, &c->out_cf2,
                       &c->d_rkpos, &c->d_recfl, &c->d_mstage, &c->d_static_off, &c->cursor, &c->unit_out_off, &c->unit_out_cnt, &c->unit_final_off, &c->overflow, &c->d_retry,
                       &c->d_partmeta, &c->d_recs, &c->fin_tmp_keys, &c->fin_tmp_cf, &c->tok_agg, &c->tok_keep, &c->tok_base, &c->tok_marks,
-                      &c->tok_tmarks, &c->tok_seq, &c->tok_offsets, &c->tok_text, &c->tok_colors,
+                      &c->tok_tmarks, &c->tok_seq, &c->tok_offsets, &c->tok_text, &c->tok_colors, &c->ut_links, &c->ut_visited, &c->ut_recs,
+                      &c->ut_bases, &c->ut_counters,
                       &c->out_hi, &c->out_hi2, &c->unit_keys, &c->unit_cols, &c->col_off, &c->out_coloff, &c->out_colors})
         b->release();
     for (cudaEvent_t e : c->event_pool) cudaEventDestroy(e);
@@ -1414,6 +1418,7 @@ void ggcat_b200_destroy(ggcat_b200_ctx *c) {
         if (ps.h_recv) cudaFreeHost(ps.h_recv);
     }
     if (c->h_mstage) cudaFreeHost(c->h_mstage);
+    if (c->h_unitigs) cudaFreeHost(c->h_unitigs);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -1724,6 +1729,56 @@ int32_t ggcat_b200_import_bucket_file(ggcat_b200_ctx *c, uint32_t bucket, const 
     ch->h_cnt = h_cnt; ch->h_words = h_words; ch->h_kmers = h_kmers; ch->h_off = h_off; ch->h_woff = h_woff;
     ch->n_sk = a; ch->n_words = b; ch->n_kmers = km;
     c->chunks.push_back(ch);
+    return 0;
+}
+
+
+// ---- partial unitigs on the device (unitigs.cuh) -------------------------------------------
+int32_t ggcat_b200_partial_unitigs(ggcat_b200_ctx *c, uint32_t result_buckets_log, ggcat_b200_unitigs *out) {
+    TRY(check_ctx(c));
+    std::lock_guard<std::mutex> lock__(c->mu);
+    if (!out) return set_err(GGCAT_B200_ERR_INVALID, "null output");
+    memset(out, 0, sizeof(*out));
+    const FinalTable &f = c->fin;
+    if (!f.unit_off || f.n_units == 0) return set_err(GGCAT_B200_ERR_STATE, "partial_unitigs before merge_bucket_range_device");
+    if (c->wide_mode >= 0) return set_err(GGCAT_B200_ERR_INVALID, "partial unitigs are built on the 64-bit key path (seq-hash, k <= 31, no colours)");
+    if ((c->P.k & 1u) == 0) return set_err(GGCAT_B200_ERR_INVALID, "partial unitigs need odd k (self-complementary k-mers of even k, final_executor.rs:249-264, are not handled)");
+    if (result_buckets_log > 15) return set_err(GGCAT_B200_ERR_INVALID, "result_buckets_log > 15");
+    static_assert(sizeof(UnitigRec) == sizeof(ggcat_b200_unitig), "device record == ABI record");
+    cudaStream_t st = c->stream;
+    const uint64_t ne = f.n_entries;
+    if (ne >= (1ull << 31)) return set_err(GGCAT_B200_ERR_INVALID, "table of %llu entries exceeds 2^31: build partial unitigs per bucket range", (unsigned long long)ne);
+    if (ne == 0) return 0;
+    const uint64_t word_cap = ne * ((c->P.k + 14) / 16 + 2) + 16;
+    CU(c->ut_links.reserve(ne * 8)); CU(c->ut_visited.reserve(ne)); CU(c->ut_recs.reserve(ne * sizeof(UnitigRec)));
+    CU(c->ut_bases.reserve(word_cap * 4)); CU(c->ut_counters.reserve(64));
+    CU(cudaMemsetAsync(c->ut_counters.p, 0, 64, st));
+    UnitigTable T;
+    T.keys = f.keys_lo; T.cf = f.cf; T.unit_off = f.unit_off; T.n_units = f.n_units; T.first_unit = f.first_unit; T.k = c->P.k; T.n_entries = ne;
+    UnitigOut O;
+    O.recs = c->ut_recs.as<UnitigRec>(); O.bases = c->ut_bases.as<uint32_t>(); O.counters = c->ut_counters.as<unsigned long long>();
+    O.rec_cap = ne; O.word_cap = word_cap; O.overflow = reinterpret_cast<uint32_t *>(c->ut_counters.as<unsigned long long>() + 4);
+    O.result_bits = result_buckets_log;
+    {
+        LaunchTimer t(c, F_UNITIGS, 3);
+        k_unitig_links<<<(unsigned)((ne + 255) / 256), 256, 0, st>>>(T, c->ut_links.as<uint32_t>(), c->ut_visited.as<uint8_t>());
+        k_unitig_paths<<<(unsigned)((2 * ne + 255) / 256), 256, 0, st>>>(T, c->ut_links.as<uint32_t>(), c->ut_visited.as<uint8_t>(), O);
+        k_unitig_cycles<<<(unsigned)((ne + 255) / 256), 256, 0, st>>>(T, c->ut_links.as<uint32_t>(), c->ut_visited.as<uint8_t>(), O);
+    }
+    CU(cudaMemcpyAsync(c->h_pinned, c->ut_counters.p, 40, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    CU(cudaGetLastError());
+    if ((uint32_t)c->h_pinned[4]) return set_err(GGCAT_B200_ERR_CAPACITY, "partial unitig output overflow (code %u)", (uint32_t)c->h_pinned[4]);
+    const uint64_t nu = c->h_pinned[0], nw = c->h_pinned[1];
+    const size_t rec_bytes = (nu * sizeof(UnitigRec) + 15) & ~(size_t)15;
+    TRY(pinned_reserve(&c->h_unitigs, &c->h_unitigs_cap, rec_bytes + nw * 4 + 16));
+    if (nu) CU(cudaMemcpyAsync(c->h_unitigs, c->ut_recs.p, nu * sizeof(UnitigRec), cudaMemcpyDeviceToHost, st));
+    if (nw) CU(cudaMemcpyAsync(c->h_unitigs + rec_bytes, c->ut_bases.p, nw * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    out->n_unitigs = nu; out->n_words = nw; out->n_kmers = c->h_pinned[2];
+    out->unitigs = reinterpret_cast<const ggcat_b200_unitig *>(c->h_unitigs);
+    out->bases = reinterpret_cast<const uint32_t *>(c->h_unitigs + rec_bytes);
+    out->d_unitigs = c->ut_recs.p; out->d_bases = c->ut_bases.as<uint32_t>();
     return 0;
 }
 

@@ -189,6 +189,37 @@ int32_t ggcat_b200_merge_bucket_range_device(ggcat_b200_ctx *ctx, uint32_t first
  * what a device-side consumer (partial-unitig construction) or a verifier reads without a host copy. */
 int32_t ggcat_b200_device_table(ggcat_b200_ctx *ctx, ggcat_b200_table *out);
 
+/* Partial unitigs of the table left by the last merge_bucket_range_device, built on the device (SURVEY 8(f)-1 + rows
+ * a12 / a13): what HashMapUnitigsExtender::compute_unitigs + try_extend_function
+ * (crates/assembler_kmers_merge/src/unitigs_extender/hashmap.rs:162-297,442-601) produce per merge unit, with the routing
+ * ParallelKmersMergeFinalExecutor::output_sequence (final_executor.rs:103-245) would apply for
+ * 1 << result_buckets_log "result" buckets (crates/assembler_kmers_merge/src/lib.rs:206-212).
+ * flags: 1 open at the beginning (backward hash is Some: the unitig continues in another unit), 2 open at the end,
+ *        4 circular (hashmap.rs:556-577), 8 should_rc, 16 HASH_ENDING_FLAG, 32 OTHER_END_FLAG
+ *        (crates/io/src/partial_unitigs_extra_data.rs:16-18) -- the last three as output_sequence stores them.
+ * bucket: result bucket of an open unitig; 0xFFFF for unitigs closed at both ends (written straight to the final file).
+ * The bases are stored in walk orientation (base i at bits 2(i%16) of word word_offset + i/16); a consumer that writes the
+ * reference's "result" buckets applies should_rc itself.  Host pointers are pinned memory owned by the context, valid until
+ * the next call; d_* are the same arrays in HBM for a device-side consumer (extend_unitigs).
+ * 64-bit key path only (seq-hash, odd k <= 31, uncoloured). */
+typedef struct {
+    uint64_t word_offset;
+    uint32_t len;            /* bases */
+    uint32_t unit;           /* merge unit (bucket << second_buckets_count_log | second_bucket) it was built in */
+    uint16_t bucket;
+    uint8_t flags;
+    uint8_t last_align;      /* output_sequence's minimizer_pos field: (len - k) % 4 or 0 */
+    uint32_t n_kmers;        /* len - k + 1 */
+} ggcat_b200_unitig;
+typedef struct {
+    uint64_t n_unitigs, n_words, n_kmers;
+    const ggcat_b200_unitig *unitigs;
+    const uint32_t *bases;
+    const void *d_unitigs;
+    const uint32_t *d_bases;
+} ggcat_b200_unitigs;
+int32_t ggcat_b200_partial_unitigs(ggcat_b200_ctx *ctx, uint32_t result_buckets_log, ggcat_b200_unitigs *out);
+
 /* Drops all bucket chunks so the context can be reused for another build. */
 int32_t ggcat_b200_reset(ggcat_b200_ctx *ctx);
 

@@ -267,3 +267,99 @@ int orc_unitigs_from_tables(const uint64_t *keys_lo, const uint64_t *keys_hi, co
     free(L.v); free(ends); free(partner); free(allk); free(seen);
     return rc;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Partial unitigs of every unit + their routing, for the parity tests of the device builder
+ * (ggcat_b200/csrc/unitigs.cuh).  compute_unitigs is ut_compute_unit above; the routing restates
+ *   assembler_kmers_merge/src/final_executor.rs:103-245  output_sequence
+ *   hashes/src/base/cn_seqhash_base.rs:140-150           get_bucket, constants hashes/src/cn_seqhash.rs:1-27 in the
+ *                                                        integer width api/src/utils.rs:27-45 selects for k
+ *   unitigs_extender/hashmap.rs:556-577                  is_circular (equal canonical (k-1)-mers at both closed ends)
+ * Output per partial unitig (in emission order): unit, len, flags (1 open begin = bw_hash Some, 2 open end, 4 circular,
+ * 8 should_rc, 16 HASH_ENDING, 32 OTHER_END), bucket (0xFFFF = lonely), last_align, byte offset of its bases (one 2-bit code
+ * per byte) in `bases`.  Returns the number of partial unitigs (> cap_u / > cap_b total bases: nothing beyond the caps is
+ * written, call again with larger buffers).
+ * ---------------------------------------------------------------------------------------------- */
+static uint32_t ut_get_bucket(u128 canon, unsigned bits, unsigned k) {
+    if (k <= 8) {
+        uint16_t x = (uint16_t)((uint16_t)canon * (uint16_t)0x0193 + (uint16_t)0x9dc5);
+        x = (uint16_t)((x >> 3) | (x << 13));
+        return (uint32_t)(x % (1u << bits));
+    }
+    if (k <= 16) {
+        uint32_t x = (uint32_t)canon * 0x01000193u + 0x811c9dc5u;
+        x = (x >> 3) | (x << 29);
+        return (uint32_t)(x % (1u << bits));
+    }
+    if (k <= 32) {
+        uint64_t x = (uint64_t)canon * 0x00000100000001b3ULL + 0xcbf29ce484222325ULL;
+        x = (x >> 3) | (x << 61);
+        return (uint32_t)(x % (1ULL << bits));
+    }
+    {
+        const u128 mul = ((u128)0x0000000001000000ULL << 64) | 0x000000000000013bULL;
+        const u128 bas = ((u128)0x6c62272e07bb0142ULL << 64) | 0x62b821756295c58dULL;
+        u128 x = canon * mul + bas;
+        x = (x >> 3) | (x << 125);
+        return (uint32_t)(x % ((u128)1 << bits));
+    }
+}
+
+size_t orc_partial_unitigs(const uint64_t *keys_lo, const uint64_t *keys_hi, const uint32_t *count_flags, const uint64_t *unit_off,
+                           size_t n_units, unsigned first_unit, unsigned k, int forward_only, unsigned result_bits,
+                           uint32_t *o_unit, uint32_t *o_len, uint8_t *o_flags, uint16_t *o_bucket, uint8_t *o_align,
+                           uint64_t *o_off, size_t cap_u, uint8_t *bases, size_t cap_b, uint64_t *total_bases) {
+    const u128 mask = (k >= 64) ? ~(u128)0 : ((((u128)1) << (2 * k)) - 1);
+    size_t nu = 0, nb = 0;
+    ut_table TC = {NULL, NULL, 0, k, forward_only, mask};
+    for (size_t u = 0; u < n_units; u++) {
+        const size_t a = unit_off[u], e = unit_off[u + 1];
+        if (a == e) continue;
+        ut_node *nodes = (ut_node *)malloc(sizeof(ut_node) * (e - a));
+        for (size_t i = a; i < e; i++) {
+            nodes[i - a].key = ((u128)(keys_hi ? keys_hi[i] : 0) << 64) | keys_lo[i];
+            nodes[i - a].flags = (uint8_t)(count_flags[i] >> 30);
+            nodes[i - a].used = 0;
+        }
+        ut_table T = {nodes, nodes, (long)(e - a), k, forward_only, mask};
+        ut_plist L = {0};
+        ut_compute_unit(&T, &L);
+        for (size_t i = 0; i < L.n; i++) {
+            const ut_partial *p = &L.v[i];
+            uint32_t fl = (p->open_bw ? 1u : 0u) | (p->open_fw ? 2u : 0u);
+            uint32_t bucket = 0xFFFFu, align = 0;
+            const u128 first = ut_kmer_at(p->bases, 0, k), last = ut_kmer_at(p->bases, p->len - k, k);
+            if (!p->open_bw && !p->open_fw) {
+                const u128 m1 = (((u128)1) << (2 * (k - 1))) - 1;
+                ut_table T1 = {NULL, NULL, 0, k - 1, 0, m1};
+                if (ut_canon(&T1, first & m1) == ut_canon(&T1, last >> 2)) fl |= 4u;
+            } else {
+                const u128 fr = ut_rc(first, k), lr = ut_rc(last, k);
+                const int first_fw = first < fr, last_fw = last < lr;   /* ExtendableHashTraitType::is_forward */
+                const uint32_t lb = p->open_bw ? ut_get_bucket(first_fw ? first : fr, result_bits, k) : 0xFFFFu;
+                const uint32_t rb = p->open_fw ? ut_get_bucket(last_fw ? last : lr, result_bits, k) : 0xFFFFu;
+                const int lrc = p->open_bw ? !first_fw : 0, rrc = p->open_fw ? !last_fw : 1;
+                const int hash_beginning = lb <= rb;
+                const int should_rc = hash_beginning ? lrc : rrc;
+                bucket = hash_beginning ? lb : rb;
+                align = (hash_beginning ^ should_rc) ? 0u : (uint32_t)((p->len - k) % 4);
+                if (should_rc) fl |= 8u;
+                if ((!hash_beginning) ^ should_rc) fl |= 16u;
+                if (p->open_bw && p->open_fw) fl |= 32u;
+            }
+            if (nu < cap_u) {
+                o_unit[nu] = first_unit + (uint32_t)u; o_len[nu] = (uint32_t)p->len; o_flags[nu] = (uint8_t)fl;
+                o_bucket[nu] = (uint16_t)bucket; o_align[nu] = (uint8_t)align; o_off[nu] = nb;
+                if (nb + p->len <= cap_b) memcpy(bases + nb, p->bases, p->len);
+            }
+            nb += p->len;
+            nu++;
+            free(p->bases);
+        }
+        free(L.v);
+        free(nodes);
+    }
+    (void)TC;
+    *total_bases = nb;
+    return nu;
+}

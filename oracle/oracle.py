@@ -354,3 +354,32 @@ def table_checksum(keys_lo, mult, flags) -> int:
         k = np.asarray(keys_lo, np.uint64) * np.uint64(0x9E3779B97F4A7C15)
         v = k + np.asarray(mult, np.uint64) + (np.asarray(flags, np.uint64) << np.uint64(40))
         return int(v.sum(dtype=np.uint64))
+
+
+def partial_unitigs(keys_lo, keys_hi, count_flags, unit_offsets, first_unit: int, k: int, result_bits: int = 3,
+                    forward_only: bool = False):
+    """Partial unitigs of every unit of a table + their routing (oracle/ggcat_unitigs.c orc_partial_unitigs: compute_unitigs
+    hashmap.rs:442-601, output_sequence final_executor.rs:103-245).  Returns a list of
+    (unit, sequence as ASCII bytes, flags, bucket, last_align) in the reference's emission order."""
+    L = lib()
+    keys_lo = np.ascontiguousarray(keys_lo, np.uint64)
+    kh = None if keys_hi is None else np.ascontiguousarray(keys_hi, np.uint64)
+    cf = np.ascontiguousarray(count_flags, np.uint32)
+    uo = np.ascontiguousarray(unit_offsets, np.uint64)
+    n = keys_lo.size
+    cap_u, cap_b = n + 1, n * (k + 1) + k + 16
+    o_unit = np.zeros(cap_u, np.uint32); o_len = np.zeros(cap_u, np.uint32); o_fl = np.zeros(cap_u, np.uint8)
+    o_bk = np.zeros(cap_u, np.uint16); o_al = np.zeros(cap_u, np.uint8); o_off = np.zeros(cap_u, np.uint64)
+    bases = np.zeros(cap_b, np.uint8)
+    tot = C.c_uint64(0)
+    L.orc_partial_unitigs.restype = C.c_size_t
+    nu = L.orc_partial_unitigs(_p(keys_lo), _p(kh) if kh is not None else None, _p(cf), _p(uo), C.c_size_t(uo.size - 1),
+                               C.c_uint(first_unit), C.c_uint(k), C.c_int(forward_only), C.c_uint(result_bits), _p(o_unit), _p(o_len),
+                               _p(o_fl), _p(o_bk), _p(o_al), _p(o_off), C.c_size_t(cap_u), _p(bases), C.c_size_t(cap_b), C.byref(tot))
+    assert nu <= cap_u and tot.value <= cap_b
+    letters = np.frombuffer(b"ACTG", np.uint8)
+    out = []
+    for i in range(nu):
+        a = int(o_off[i])
+        out.append((int(o_unit[i]), letters[bases[a:a + int(o_len[i])]].tobytes(), int(o_fl[i]), int(o_bk[i]), int(o_al[i])))
+    return out

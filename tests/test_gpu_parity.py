@@ -1010,3 +1010,78 @@ def test_bucket_files_reference_format_roundtrip(k, m, tmp_path):
         _check_tables(G, ctx2, reads, sk, k, s, b1, b2)
     finally:
         ctx.close(); ctx2.close()
+
+
+# ------------------------------------------------------------------ partial unitigs on the device
+def _unitig_strings(recs, bases):
+    letters = np.frombuffer(b"ACTG", np.uint8)
+    out = []
+    for r in recs:
+        n, w0 = int(r["len"]), int(r["word_offset"])
+        words = bases[w0:w0 + (n + 15) // 16].astype(np.uint64)
+        codes = ((words[:, None] >> (np.arange(16, dtype=np.uint64) * np.uint64(2))[None, :]) & np.uint64(3)).reshape(-1)[:n]
+        out.append((int(r["unit"]), letters[codes.astype(np.int64)].tobytes(), int(r["flags"]), int(r["bucket"]), int(r["last_align"])))
+    return out
+
+
+@pytest.mark.parametrize("k,m,b1,b2,s,pbits", [(31, 12, 2, 2, 1, 3), (31, 12, 3, 2, 2, 5), (21, 10, 1, 1, 1, 4), (15, 9, 2, 1, 1, 3),
+                                                (27, 11, 0, 0, 1, 6)])
+def test_partial_unitigs_on_device_match_compute_unitigs(k, m, b1, b2, s, pbits):
+    """Rows a12 / a13 / f1: the device builds, per merge unit, the partial unitigs HashMapUnitigsExtender::compute_unitigs
+    would (same sequences in the same orientation, same open / closed ends, circular flag) and routes them as
+    output_sequence would (result bucket, should_rc, HASH_ENDING / OTHER_END, last_align) -- compared as a multiset
+    per unit with the oracle restatement run on the same GPU table; the partial unitigs cover every table entry once."""
+    G = _gpu()
+    rng = np.random.default_rng(1000 + k + b1)
+    g = util.rand_seq(rng, 6000)
+    seqs = _mixed_reads(rng, k, n=400) + [g, g[1000:3000], util.revcomp(g[2500:5200]), util.rand_seq(rng, 2500)]
+    circ = util.rand_seq(rng, 300)
+    seqs += [circ + circ[:k - 1], (circ + circ[:k - 1])[40:] + circ[:60]]         # a cycle in the de Bruijn graph
+    seqs += [b"ACGT" * 40, b"A" * 200, b"AT" * 90]                                # low complexity, self-overlapping k-mers
+    reads = O.Reads.from_list(seqs)
+    ctx, st = G.minimizer_bucketing([(reads.data, reads.offsets)], b1, b2, k, m, min_multiplicity=s)
+    try:
+        nb = (1 << b1) + 1
+        ne, _, _ = ctx.merge_bucket_range_device(0, nb)
+        tab = ctx.read_device_table()
+        recs, bases, nk = ctx.partial_unitigs(pbits)
+        assert nk == ne == int(recs["n_kmers"].sum()), "every kept k-mer lies on exactly one partial unitig"
+        assert (recs["len"] == recs["n_kmers"] + k - 1).all()
+        got = _unitig_strings(recs, bases)
+        want = O.partial_unitigs(tab.keys_lo, None, tab.count_flags, tab.unit_offsets, tab.first_unit, k, pbits)
+        assert len(got) == len(want)
+        # cycles: the reference opens them at their smallest k-mer -- so does the device; everything is compared verbatim
+        assert sorted(got) == sorted(want)
+        assert any(f & 4 for _, _, f, _, _ in want), "the input holds a circular unitig"
+        assert any(f & 3 for _, _, f, _, _ in want) or b1 == 0
+    finally:
+        ctx.close()
+
+
+def test_partial_unitigs_c1_join_to_maximal_unitigs(golden_dir):
+    """BASELINE configs[0]: device-built partial unitigs of the three example files, joined at their open ends (the semantic
+    join of oracle/ggcat_unitigs.c on the same table), give the maximal unitigs of the global flag-free build."""
+    G = _gpu()
+    k, m, b1, b2, s = 31, 12, 2, 6, 1
+    recs_in = util.c1_records()
+    reads = O.Reads.from_list(recs_in)
+    ctx, st = G.minimizer_bucketing([(reads.data, reads.offsets)], b1, b2, k, m, min_multiplicity=s)
+    try:
+        nb = (1 << b1) + 1
+        ne, _, _ = ctx.merge_bucket_range_device(0, nb)
+        tab = ctx.read_device_table()
+        recs, bases, nk = ctx.partial_unitigs(3)
+        assert nk == ne
+        got = _unitig_strings(recs, bases)
+        want = O.partial_unitigs(tab.keys_lo, None, tab.count_flags, tab.unit_offsets, tab.first_unit, k, 3)
+        assert sorted(got) == sorted(want)
+        # open ends pair up: every open end k-mer (canonical) occurs exactly twice over all partial unitigs
+        ends = {}
+        for _, sq, f, _, _ in got:
+            for bit, km in ((1, sq[:k]), (2, sq[-k:])):
+                if f & bit:
+                    c = min(km, util.revcomp(km))
+                    ends[c] = ends.get(c, 0) + 1
+        assert ends and set(ends.values()) == {2}
+    finally:
+        ctx.close()
