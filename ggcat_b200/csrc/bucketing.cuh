@@ -111,6 +111,14 @@ __global__ void k_mark(const uint64_t *__restrict__ offsets, uint64_t n_reads, u
 // (crates/hashes/src/rolling/batch_minqueue.rs:63-70,78-84,97-113: equal values clear the unique bit).
 __device__ __forceinline__ uint64_t comb(uint64_t a, uint64_t b) { return a == b ? (a & ~1ull) : (a < b ? a : b); }
 
+// comb() that also carries the position of the (unique) minimum: the argmin of a window comes out of the same reduction
+// that computes its minimum, so no thread has to search the window afterwards (ties clear the unique bit; the position
+// of a non-unique minimum is never used: such windows go to the duplicates bucket).
+__device__ __forceinline__ void combp(uint64_t &av, uint32_t &ap, uint64_t bv, uint32_t bp) {
+    if (av == bv) av &= ~1ull;
+    else if (bv < av) { av = bv; ap = bp; }
+}
+
 // `cnt` (<= 64) bits of a shared-memory bitmap starting at bit `s`, as a u64.
 __device__ __forceinline__ uint64_t bits64(const uint32_t *bm, uint32_t s, uint32_t cnt) {
     const uint64_t v = extract64(bm, s);
@@ -124,7 +132,8 @@ __device__ __forceinline__ uint64_t bits64(const uint32_t *bm, uint32_t s, uint3
 //   C  window minima, van Herk / Gil-Werman: per block of w items a suffix scan and a prefix scan with
 //      comb() -- exactly the two arrays the reference's BatchMinQueue keeps (batch_minqueue.rs:58-113)
 //   D  M_x = comb(suffix[x], prefix[x+w-1])
-//   E  split-start / segment-end flags, F in-order compaction (one block scan), G per-entry minimizer lookup
+//   E  split-start / segment-end flags, F in-order compaction (one block scan) + bucket / orientation / minimizer offset
+//      of every super-k-mer start from the (minimum, argmin) pair its thread holds in registers, G copy-out
 __global__ void __launch_bounds__(WIN_THREADS)
 k_windows(const uint32_t *__restrict__ pk, const uint32_t *__restrict__ bad, const uint32_t *__restrict__ brk,
           uint32_t n /* bases in batch */, DevParams P, uint64_t *__restrict__ ent, uint32_t *__restrict__ tile_cnt,
@@ -138,7 +147,6 @@ k_windows(const uint32_t *__restrict__ pk, const uint32_t *__restrict__ bad, con
     // m-mer values and window minima: element x lives at PADX(x) = x + x/8, so that the 8-windows-per-thread phase
     // (lane stride 8 elements) touches every 8-byte bank pair twice per warp instead of sixteen times
     __shared__ uint64_t s_v0[PADX(WIN_NI + 16) + 1];
-    __shared__ uint64_t s_M[PADX(WIN_T + 8) + 1];
     __shared__ uint8_t s_fwd[WIN_NI + 1];
     __shared__ uint64_t s_ent[WIN_T];
     __shared__ uint64_t s_TF[32][4], s_TR[32][4];  // rotl(h(c), m-1-i), rotl(r(c), i)
@@ -235,39 +243,44 @@ k_windows(const uint32_t *__restrict__ pk, const uint32_t *__restrict__ bad, con
     static_assert(WPT * WIN_THREADS == WIN_T, "8 windows per thread cover the tile");
     const uint32_t x0 = 1 + tid * WPT;
     uint64_t Mreg[WPT], Mprev;
+    uint32_t Preg[WPT];    // item index (tile x coordinate) of the window's minimum
     if (w >= (uint32_t)WPT) {
         uint64_t common = s_v0[PADX(x0 + WPT - 1)], common_short = common;   // [x0+7, x0+w-1] and the same without the last item
-        for (uint32_t q = x0 + WPT; q < x0 + w; ++q) { common_short = common; common = comb(common, s_v0[PADX(q)]); }
+        uint32_t common_p = x0 + WPT - 1;
+        for (uint32_t q = x0 + WPT; q < x0 + w; ++q) { common_short = common; combp(common, common_p, s_v0[PADX(q)], q); }
         uint64_t L[WPT - 1];
-        L[WPT - 2] = s_v0[PADX(x0 + WPT - 2)];
+        uint32_t Lp[WPT - 1];
+        L[WPT - 2] = s_v0[PADX(x0 + WPT - 2)]; Lp[WPT - 2] = x0 + WPT - 2;
 #pragma unroll
-        for (int i = WPT - 3; i >= 0; --i) L[i] = comb(s_v0[PADX(x0 + i)], L[i + 1]);
+        for (int i = WPT - 3; i >= 0; --i) { L[i] = s_v0[PADX(x0 + i)]; Lp[i] = x0 + i; combp(L[i], Lp[i], L[i + 1], Lp[i + 1]); }
         // window x0-1 = item x0-1 + items [x0, x0+6] + items [x0+7, x0+w-2]
         Mprev = comb(s_v0[PADX(x0 - 1)], L[0]);
         if (w > (uint32_t)WPT) Mprev = comb(Mprev, common_short);
         uint64_t R = 0;
+        uint32_t Rp = 0;
 #pragma unroll
         for (int i = 0; i < WPT; i++) {
-            uint64_t mi = (i < WPT - 1) ? comb(L[i], common) : common;
+            uint64_t mi = common;
+            uint32_t mp = common_p;
+            if (i < WPT - 1) { mi = L[i]; mp = Lp[i]; combp(mi, mp, common, common_p); }
             if (i > 0) {
                 const uint64_t nv = s_v0[PADX(x0 + w + i - 1)];
-                R = (i == 1) ? nv : comb(R, nv);
-                mi = comb(mi, R);
+                if (i == 1) { R = nv; Rp = x0 + w; } else combp(R, Rp, nv, x0 + w + i - 1);
+                combp(mi, mp, R, Rp);
             }
-            Mreg[i] = mi;
+            Mreg[i] = mi; Preg[i] = mp;
         }
     } else {
 #pragma unroll
         for (int i = 0; i < WPT; i++) {
             uint64_t mi = s_v0[PADX(x0 + i)];
-            for (uint32_t q = 1; q < w; ++q) mi = comb(mi, s_v0[PADX(x0 + i + q)]);
-            Mreg[i] = mi;
+            uint32_t mp = x0 + i;
+            for (uint32_t q = 1; q < w; ++q) combp(mi, mp, s_v0[PADX(x0 + i + q)], x0 + i + q);
+            Mreg[i] = mi; Preg[i] = mp;
         }
         Mprev = s_v0[PADX(x0 - 1)];
         for (uint32_t q = 1; q < w; ++q) Mprev = comb(Mprev, s_v0[PADX(x0 - 1 + q)]);
     }
-#pragma unroll
-    for (int i = 0; i < WPT; i++) s_M[PADX(x0 + i)] = Mreg[i];
     // window validity for x0-1 .. x0+8: inside one N-free segment of one record (sequences_splitter.rs:15-40):
     //   no bad base in [j, j+k-1) and no record start in (j, j+k-1)  <=>  base j is good and
     //   (bad | record-start) has no bit in (j, j+k-1)
@@ -312,13 +325,16 @@ k_windows(const uint32_t *__restrict__ pk, const uint32_t *__restrict__ bad, con
             if (f & 3u) mine += 1u + ((f & 1u) << 16);
         }
         uint32_t tot;
-        uint32_t pre = block_exclusive_scan<WIN_THREADS>(mine, s_scan, &tot);   // its barriers also publish s_M
+        uint32_t pre = block_exclusive_scan<WIN_THREADS>(mine, s_scan, &tot);   // (three block barriers)
 #pragma unroll
         for (int i = 0; i < WPT; i++) {
             const uint32_t f = (fl >> (3 * i)) & 7u;
             if (f & 3u) {
-                s_ent[pre & 0xFFFFu] = (uint64_t)(x0 + i - 1) | ((f & 1u) ? ENT_S : 0) | ((f & 2u) ? ENT_E : 0) |
-                                       ((f & 4u) ? ENT_FIRST : 0) | ((uint64_t)(pre >> 16) << ENT_SRANK_SHIFT);
+                uint64_t e = (uint64_t)(x0 + i - 1) | ((f & 1u) ? ENT_S : 0) | ((f & 2u) ? ENT_E : 0) |
+                             ((f & 4u) ? ENT_FIRST : 0) | ((uint64_t)(pre >> 16) << ENT_SRANK_SHIFT);
+                if (f & 1u)   // a super-k-mer starts here: remember where its minimizer is (and whether it is unique)
+                    e |= ((uint64_t)(Preg[i] - (x0 + i)) << ENT_ARG_SHIFT) | ((Mreg[i] & 1ull) ? 0 : ENT_DUP);
+                s_ent[pre & 0xFFFFu] = e;
                 pre += 1u + ((f & 1u) << 16);
             }
         }
@@ -326,26 +342,24 @@ k_windows(const uint32_t *__restrict__ pk, const uint32_t *__restrict__ bad, con
     }
     __syncthreads();
 
-    // ---- G: per super-k-mer: locate the minimizer, derive bucket / orientation
-    // (assembler_minimizer_bucketing/src/lib.rs:218-238)
+    // ---- G: per super-k-mer: bucket / orientation from its minimizer (assembler_minimizer_bucketing/src/lib.rs:218-238);
+    //         the minimizer's position came out of the window reduction, nothing is searched
     for (uint32_t i = tid; i < n_ent; i += WIN_THREADS) {
         uint64_t e = s_ent[i];
         if (e & ENT_S) {
             const uint32_t x = (uint32_t)(e & ((1u << ENT_POS_BITS) - 1)) + 1;
-            const uint64_t M = s_M[PADX(x)];
-            uint32_t bucket, rcf = 0, arg = 0;
-            if ((M & 1ull) == 0) {
+            const uint32_t arg = (uint32_t)(e >> ENT_ARG_SHIFT) & 0xFFu;
+            const uint64_t M = s_v0[PADX(x + arg)];     // the window minimum (bit 0 aside: ENT_DUP says whether it is unique)
+            uint32_t bucket, rcf = 0;
+            if (e & ENT_DUP) {
                 bucket = 1u << P.b1;  // duplicates bucket
-                e |= ENT_DUP;
+                e &= ~(0xFFull << ENT_ARG_SHIFT);
             } else {
-                for (uint32_t q = 0; q < w; q++)
-                    if (s_v0[PADX(x + q)] == M) { arg = q; break; }
                 rcf = (!P.forward_only && !s_fwd[x + arg]) ? 1u : 0u;
                 bucket = (uint32_t)(M >> 1) & ((1u << P.b1) - 1);   // cn_nthash.rs:135-142 get_bucket(0, b1, M)
             }
             const uint32_t second = (uint32_t)(M >> (P.b1 + 1)) & ((1u << P.b2) - 1);
-            e |= (rcf ? ENT_RC : 0) | ((uint64_t)second << ENT_SECOND_SHIFT) | ((uint64_t)bucket << ENT_BUCKET_SHIFT) |
-                 ((uint64_t)arg << ENT_ARG_SHIFT);
+            e |= (rcf ? ENT_RC : 0) | ((uint64_t)second << ENT_SECOND_SHIFT) | ((uint64_t)bucket << ENT_BUCKET_SHIFT);
         }
         ent[(uint64_t)tile * WIN_T + i] = e;
     }
