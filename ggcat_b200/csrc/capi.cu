@@ -609,10 +609,10 @@ constexpr int HASH_TS_S = 8192;                       // k_merge_parts: table sl
 #define TIER_A 512, 4096, 512, 2048, 1, 3      // one landing buffer + a sparser table measured faster than two buffers + 3072 slots (1.35 vs 1.43 ms on C2)
 #define TIER_A1 512, 3072, 512, 2048, 2, 3     // A/B variant: two landing buffers, 3072 slots
 #define TIER_A256 256, 3072, 512, 2048, 2, 3   // A/B variant: 8 warps per unit
-#define TIER_B 512, 5632, 1408, 4608, 1, 2
-#define TIER_C 1024, 11776, 2560, 8192, 1, 1
+#define TIER_B 512, 4608, 1408, 4608, 1, 2
+#define TIER_C 1024, 10240, 2560, 8192, 1, 1
 struct TierCap { uint32_t ts, skcap, pwcap; };
-constexpr TierCap kTierCaps[3] = {{4096, 512, 2048}, {5632, 1408, 4608}, {11776, 2560, 8192}};
+constexpr TierCap kTierCaps[3] = {{4096, 512, 2048}, {4608, 1408, 4608}, {10240, 2560, 8192}};
 constexpr double kTierMaxLoad[3] = {0.5, 0.5, 0.72};   // expected distinct keys / table slots a unit may have in its tier (the last tier
                                                        // takes denser tables rather than sending the unit to the key-partition path)
 
@@ -719,7 +719,7 @@ int32_t merge_range_device(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_
         if (n >= (1ull << 31)) return set_err(GGCAT_B200_ERR_INVALID, "unit %u holds %llu k-mers (> 2^31)", u, (unsigned long long)n);
         tot_kmers += n;
         int t = -1;
-        if (tiers_ok && n < (1u << 24)) {
+        if (tiers_ok && n < (1u << 20)) {
             const double need_keys = (double)n * keys_per_rec;
             const uint64_t need_w = (uint64_t)ut[u - u0].w + 6ull * ut[u - u0].sl;
             for (int q = 0; q < 3 && t < 0; q++)
@@ -856,14 +856,14 @@ int32_t merge_range_device(ggcat_b200_ctx *c, uint32_t first_bucket, uint32_t n_
             LaunchTimer t(c, F_MERGE_HASH);
             CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             const unsigned grid = (unsigned)std::min<size_t>(tier[q].size(), (size_t)c->sm_count * ctas_per_sm);
-            kern<<<grid, threads, smem, st>>>(dv, nch, d_tier[q], (uint32_t)tier[q].size(), u0, P, ms, out, wc + q, retry3, retry3_cnt);
+            kern<<<grid, threads, smem, st>>>(dv, nch, d_tier[q], (uint32_t)tier[q].size(), u0, P, ms, out, d_unit_n, wc + q, retry3, retry3_cnt);
             return 0;
         };
         if (c->tier_a_variant == 2) TRY(launch_tier(k_merge_tier<TIER_A256>, TierSmem<256, 3072, 512, 2048, 2>::bytes, 256, 3, 0));
         else if (c->tier_a_variant == 1) TRY(launch_tier(k_merge_tier<TIER_A1>, TierSmem<512, 3072, 512, 2048, 2>::bytes, 512, 3, 0));
         else TRY(launch_tier(k_merge_tier<TIER_A>, TierSmem<512, 4096, 512, 2048, 1>::bytes, 512, 3, 0));
-        TRY(launch_tier(k_merge_tier<TIER_B>, TierSmem<512, 5632, 1408, 4608, 1>::bytes, 512, 2, 1));
-        TRY(launch_tier(k_merge_tier<TIER_C>, TierSmem<1024, 11776, 2560, 8192, 1>::bytes, 1024, 1, 2));
+        TRY(launch_tier(k_merge_tier<TIER_B>, TierSmem<512, 4608, 1408, 4608, 1>::bytes, 512, 2, 1));
+        TRY(launch_tier(k_merge_tier<TIER_C>, TierSmem<1024, 10240, 2560, 8192, 1>::bytes, 1024, 1, 2));
         if (!big.empty()) {
             {
                 LaunchTimer t(c, F_PARTITION);

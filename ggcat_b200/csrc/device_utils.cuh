@@ -121,6 +121,7 @@ __device__ __forceinline__ unsigned long long atoms_cas64(uint32_t a, unsigned l
     return old;
 }
 __device__ __forceinline__ void atoms_inc32(uint32_t a) { asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(a) : "memory"); }
+__device__ __forceinline__ void atoms_add32(uint32_t a, uint32_t v) { asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ void atoms_or32(uint32_t a, uint32_t v) { asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 
 // ---- block-wide helpers -------------------------------------------------------------------------

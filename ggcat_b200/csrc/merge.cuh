@@ -583,10 +583,11 @@ struct TierSmem {
     static constexpr size_t pay_off = sk_off + (size_t)NBUF * SKCAP * 16;                 // NBUF x (PWCAP + 8) u32 (TMA landing)
     static constexpr size_t start_off = pay_off + (size_t)NBUF * (PWCAP + 8) * 4;         // NBUF x SKCAP u32: first record of a super-k-mer
     static constexpr size_t bar_off = start_off + (size_t)NBUF * SKCAP * 4;               // NBUF mbarriers
-    static constexpr size_t meta_off = bar_off + (size_t)NBUF * 8;                        // NBUF x {unit, n_sk, -, -}
-    static constexpr size_t dstart_off = meta_off + (size_t)NBUF * 16;                    // NBUF x (MAXSL + 1): first staged descriptor of a slice
+    static constexpr size_t meta_off = bar_off + (size_t)NBUF * 8;                        // NBUF x {unit, n_sk, region start lo, hi}
+    static constexpr size_t dstart_off = meta_off + (size_t)NBUF * 32;                    // NBUF x (MAXSL + 1): first staged descriptor of a slice
     static constexpr size_t delta_off = dstart_off + (size_t)NBUF * (TIER_MAXSL + 1) * 4; // NBUF x MAXSL: staged payload word = descriptor word + delta
-    static constexpr size_t scan_off = delta_off + (size_t)NBUF * TIER_MAXSL * 4;         // 34 u32
+    static constexpr size_t dtab_off = delta_off + (size_t)NBUF * TIER_MAXSL * 4;         // 2 x SKCAP u32: super-k-mer dedup table
+    static constexpr size_t scan_off = dtab_off + (size_t)2 * SKCAP * 4;                  // 34 u32
     static constexpr size_t cnt_off = scan_off + 34 * 4;                                  // 4 u32
     static constexpr size_t bytes = ((cnt_off + 4 * 4 + 15) / 16) * 16;
     static_assert((size_t)TS % 4 == 0 && PWCAP % 4 == 0 && SKCAP % 4 == 0, "bulk-copy destinations must be 16-byte aligned");
@@ -615,7 +616,7 @@ __device__ __forceinline__ uint32_t block_scan1(uint32_t v, uint32_t *s_w, uint3
 // meta = {unit, n_sk, start of the unit's output region (lo, hi)}: loaded here, a whole unit ahead of their use.
 __device__ __forceinline__ void tier_prefetch(const ChunkView *__restrict__ chunks, uint32_t n_chunks, const uint32_t *__restrict__ work,
                                               uint32_t n_work, uint32_t *__restrict__ work_counter, uint32_t first_unit,
-                                              const uint64_t *__restrict__ static_off, uint4 *sk, uint32_t *pay,
+                                              const uint64_t *__restrict__ static_off, const uint32_t *__restrict__ unit_n, uint4 *sk, uint32_t *pay,
                                               uint64_t *bar, uint32_t *meta, uint32_t *sl_dstart, uint32_t *sl_delta) {
     const uint32_t lane = lane_id();
     uint32_t wi = 0;
@@ -638,7 +639,8 @@ __device__ __forceinline__ void tier_prefetch(const ChunkView *__restrict__ chun
         }
     }
     unsigned long long gbase = 0;
-    if (lane == 0) gbase = static_off[unit - first_unit];
+    uint32_t n_rec = 0;
+    if (lane == 0) { gbase = static_off[unit - first_unit]; n_rec = unit_n[unit - first_unit]; }
     const uint32_t cw = cnt ? ((lead + nw + 3u) & ~3u) : 0u;
     uint32_t dx = cnt, px = cw;
 #pragma unroll
@@ -653,7 +655,7 @@ __device__ __forceinline__ void tier_prefetch(const ChunkView *__restrict__ chun
     if (lane == 31) sl_dstart[32] = dtot;
     fence_proxy_async_smem();                   // the landing buffers were read / rewritten by plain loads and stores
     if (lane == 0) {
-        meta[0] = unit; meta[1] = dtot; meta[2] = (uint32_t)gbase; meta[3] = (uint32_t)(gbase >> 32);
+        meta[0] = unit; meta[1] = dtot; meta[2] = (uint32_t)gbase; meta[3] = (uint32_t)(gbase >> 32); meta[4] = n_rec;
         mbar_expect_tx(bar, dtot * 16u + ptot * 4u);
     }
     __syncwarp();
@@ -666,7 +668,7 @@ __device__ __forceinline__ void tier_prefetch(const ChunkView *__restrict__ chun
 template <int THREADS, int TS, int SKCAP, int PWCAP, int NBUF, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB)
 k_merge_tier(const ChunkView *__restrict__ chunks, uint32_t n_chunks, const uint32_t *__restrict__ work, uint32_t n_work,
-             uint32_t first_unit, DevParams P, uint32_t min_mult, MergeOut out,
+             uint32_t first_unit, DevParams P, uint32_t min_mult, MergeOut out, const uint32_t *__restrict__ unit_n,
              uint32_t *__restrict__ work_counter, uint32_t *__restrict__ retry, uint32_t *__restrict__ retry_count) {
     using L = TierSmem<THREADS, TS, SKCAP, PWCAP, NBUF>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -681,6 +683,7 @@ k_merge_tier(const ChunkView *__restrict__ chunks, uint32_t n_chunks, const uint
     uint32_t *metab = reinterpret_cast<uint32_t *>(smem_raw + L::meta_off);
     uint32_t *dstartb = reinterpret_cast<uint32_t *>(smem_raw + L::dstart_off);
     uint32_t *deltab = reinterpret_cast<uint32_t *>(smem_raw + L::delta_off);
+    uint32_t *dtab = reinterpret_cast<uint32_t *>(smem_raw + L::dtab_off);
     uint32_t *s_scan = reinterpret_cast<uint32_t *>(smem_raw + L::scan_off);
     uint32_t *s_cnt = reinterpret_cast<uint32_t *>(smem_raw + L::cnt_off);   // [0] survivors written, [1] occupied slots, [3] table full
 
@@ -690,10 +693,11 @@ k_merge_tier(const ChunkView *__restrict__ chunks, uint32_t n_chunks, const uint
     const uint32_t le_mask = 0xFFFFFFFFu >> (31u - lane);
     const uint32_t aK = smem_addr(K), aC = smem_addr(C), aFull = smem_addr(s_cnt + 3);
     auto prefetch = [&](uint32_t b) {
-        tier_prefetch(chunks, n_chunks, work, n_work, work_counter, first_unit, out.static_off, skb + (size_t)b * SKCAP,
-                      payb + (size_t)b * (PWCAP + 8), bars + b, metab + 4 * b, dstartb + (TIER_MAXSL + 1) * b, deltab + TIER_MAXSL * b);
+        tier_prefetch(chunks, n_chunks, work, n_work, work_counter, first_unit, out.static_off, unit_n, skb + (size_t)b * SKCAP,
+                      payb + (size_t)b * (PWCAP + 8), bars + b, metab + 8 * b, dstartb + (TIER_MAXSL + 1) * b, deltab + TIER_MAXSL * b);
     };
     for (uint32_t i = tid; i < (uint32_t)TS; i += THREADS) { K[i] = HASH_EMPTY; C[i] = 0u; }
+    for (uint32_t i = tid; i < 2u * SKCAP; i += THREADS) dtab[i] = 0xFFFFFFFFu;
     if (tid == 0) {
         for (int b = 0; b < NBUF; b++) mbar_init(bars + b, 1);
         s_cnt[0] = s_cnt[1] = s_cnt[2] = s_cnt[3] = 0;
@@ -703,39 +707,79 @@ k_merge_tier(const ChunkView *__restrict__ chunks, uint32_t n_chunks, const uint
     __syncthreads();
     for (uint32_t it = 0;; ++it) {
         const uint32_t b = NBUF == 2 ? (it & 1u) : 0u;
-        const uint32_t unit = metab[4 * b], nsk = metab[4 * b + 1];
+        const uint32_t unit = metab[8 * b], nsk = metab[8 * b + 1], n_records = metab[8 * b + 4];
         if (unit == TIER_DONE) break;
-        const unsigned long long gbase = ((unsigned long long)metab[4 * b + 3] << 32) | metab[4 * b + 2];
+        const unsigned long long gbase = ((unsigned long long)metab[8 * b + 3] << 32) | metab[8 * b + 2];
         if (NBUF == 2 && warp == 0) prefetch(b ^ 1u);     // the other landing buffer: its unit finished before the last barrier
         mbar_wait(bars + b, NBUF == 2 ? ((it >> 1) & 1u) : (it & 1u));
         const uint32_t unit_rel = unit - first_unit;
         uint4 *sk = skb + (size_t)b * SKCAP;
         uint32_t *start = startb + (size_t)b * SKCAP;
         const uint32_t *sl_dstart = dstartb + (TIER_MAXSL + 1) * b, *sl_delta = deltab + TIER_MAXSL * b;
-        // ---- stage: raw descriptor {word, len, meta, colour} -> {first record, staged payload word, len | flags << 30}
-        uint32_t tot;
-        {
-            uint32_t pwv[ITEMS], lfv[ITEMS], cntv[ITEMS], sum = 0;
+        // ---- stage 1: raw descriptor {word, len, meta, colour} -> {-, staged payload word, len | flags << 30, multiplicity 1}
+        const uint32_t *payw = payb + (size_t)b * (PWCAP + 8);
+        uint32_t pwv[ITEMS], lfv[ITEMS];
 #pragma unroll
-            for (int t = 0; t < ITEMS; t++) {
-                const uint32_t j = tid * ITEMS + t;
-                pwv[t] = lfv[t] = cntv[t] = 0;
-                if (j < nsk) {
-                    const uint4 d = sk[j];
-                    uint32_t q = 0;
-                    while (j >= sl_dstart[q + 1]) ++q;
-                    pwv[t] = d.x + sl_delta[q];
-                    lfv[t] = d.y | (((d.z >> 16) & 3u) << 30);
-                    cntv[t] = d.y - k + 1u;
-                }
-                sum += cntv[t];
+        for (int t = 0; t < ITEMS; t++) {
+            const uint32_t j = tid * ITEMS + t;
+            pwv[t] = lfv[t] = 0;
+            if (j < nsk) {
+                const uint4 d = sk[j];
+                uint32_t q = 0;
+                while (j >= sl_dstart[q + 1]) ++q;
+                pwv[t] = d.x + sl_delta[q];
+                lfv[t] = d.y | (((d.z >> 16) & 3u) << 30);
+                sk[j] = make_uint4(0u, pwv[t], lfv[t], 1u);
             }
-            uint32_t pre = block_scan1<THREADS>(sum, s_scan, &tot);
+        }
+        __syncthreads();
+        // ---- stage 2: super-k-mer compaction (the reference's BucketsCompactor, crates/minimizer_bucketing/src/compactor.rs:
+        //      128-196: identical (length, flags, packed bases) super-k-mers of a sub-bucket merge, multiplicities add up).
+        //      At 30x coverage about half of a unit's super-k-mers repeat one seen before, so half of the k-mer inserts
+        //      become "+ multiplicity" of one insert.  Open-addressing table of super-k-mer indices, CAS-claimed; a
+        //      duplicate adds 1 to its representative's multiplicity and contributes no records.
+        uint32_t tot, nrep;
+        {
+            constexpr uint32_t DCAP = 2u * SKCAP;
+            uint32_t myslot[ITEMS], packed[ITEMS], sum = 0;
 #pragma unroll
             for (int t = 0; t < ITEMS; t++) {
                 const uint32_t j = tid * ITEMS + t;
-                if (j < nsk) { sk[j] = make_uint4(pre, pwv[t], lfv[t], 0u); start[j] = pre; }
-                pre += cntv[t];
+                myslot[t] = 0xFFFFFFFFu; packed[t] = 0;
+                if (j < nsk) {
+                    const uint32_t len = lfv[t] & 0x3FFFFFFFu, nw = (len + 15u) >> 4;
+                    uint32_t h = lfv[t] * 0x9E3779B1u;
+                    for (uint32_t w = 0; w < nw; w++) h = (h ^ payw[pwv[t] + w]) * 0x85EBCA6Bu + 0x27D4EB2Fu;
+                    h ^= h >> 15;
+                    uint32_t slot = __umulhi(h * 0x2C1B3C6Du, DCAP);
+                    while (true) {
+                        const uint32_t old = atomicCAS(&dtab[slot], 0xFFFFFFFFu, j);
+                        if (old == 0xFFFFFFFFu) { myslot[t] = slot; packed[t] = (len - k + 1u) | (1u << 20); break; }
+                        const uint4 o = sk[old];
+                        bool same = o.z == lfv[t];
+                        for (uint32_t w = 0; same && w < nw; w++) same = payw[o.y + w] == payw[pwv[t] + w];
+                        if (same) { atomicAdd(&sk[old].w, 1u); break; }
+                        slot = slot + 1u == DCAP ? 0u : slot + 1u;
+                    }
+                }
+                sum += packed[t];
+            }
+            uint32_t total;
+            uint32_t pre = block_scan1<THREADS>(sum, s_scan, &total);     // records in the low 20 bits, representatives above
+            tot = total & 0xFFFFFu; nrep = total >> 20;
+            uint32_t mult[ITEMS];
+#pragma unroll
+            for (int t = 0; t < ITEMS; t++) mult[t] = packed[t] ? sk[tid * ITEMS + t].w : 0u;    // final: every duplicate has added itself
+            __syncthreads();
+#pragma unroll
+            for (int t = 0; t < ITEMS; t++) {
+                if (packed[t]) {
+                    const uint32_t rank = pre >> 20, rs = pre & 0xFFFFFu;
+                    sk[rank] = make_uint4(rs, pwv[t], lfv[t], mult[t]);          // compacted in place (rank <= own index)
+                    start[rank] = rs;
+                    dtab[myslot[t]] = 0xFFFFFFFFu;
+                }
+                pre += packed[t];
             }
         }
         __syncthreads();
@@ -747,7 +791,7 @@ k_merge_tier(const ChunkView *__restrict__ chunks, uint32_t n_chunks, const uint
             const uint32_t per = ((tot + WARPS * 32u - 1u) / (WARPS * 32u)) * 32u;
             const uint32_t r_beg = warp * per, r_end = min(tot, r_beg + per);
             if (r_beg < r_end) {
-                uint32_t lo = 0, hi = nsk - 1;                                          // last j with start[j] <= r_beg
+                uint32_t lo = 0, hi = nrep - 1;                                         // last j with start[j] <= r_beg
                 while (lo < hi) {
                     const uint32_t mid = (lo + hi + 1) >> 1;
                     if (lds_u32(aStart + 4u * mid) <= r_beg) lo = mid; else hi = mid - 1;
@@ -756,13 +800,13 @@ k_merge_tier(const ChunkView *__restrict__ chunks, uint32_t n_chunks, const uint
                 for (uint32_t r0 = r_beg; r0 < r_end; r0 += 32u) {
                     if (lds_u32(aFull)) break;                                         // somebody found the table full
                     const uint32_t cand = j + 1u + lane;
-                    const uint32_t rel = (cand < nsk ? lds_u32(aStart + 4u * cand) : 0xFFFFFFFFu) - r0;  // > 0 by the invariant
+                    const uint32_t rel = (cand < nrep ? lds_u32(aStart + 4u * cand) : 0xFFFFFFFFu) - r0;  // > 0 by the invariant
                     const uint32_t smask = __reduce_or_sync(0xffffffffu, rel < 32u ? (1u << rel) : 0u);
                     const uint32_t owner = j + (uint32_t)__popc(smask & le_mask);
                     const uint32_t r = r0 + lane;
                     const bool active = r < r_end;
-                    uint32_t slot = 0, fb = 0;
-                    bool claimed = true;                                               // inactive lanes touch nothing below
+                    uint32_t slot = 0, fb = 0, add = 0;                                // add: what this lane adds to the slot's counter
+                    bool claimed = false;                                              // (inactive lanes add nothing)
                     if (active) {
                         const uint4 s = lds_u128(aSk + 16u * owner);
                         const uint32_t i = r - s.x, last = (s.z & 0x3FFFFFFFu) - k, flags = s.z >> 30;
@@ -780,6 +824,7 @@ k_merge_tier(const ChunkView *__restrict__ chunks, uint32_t n_chunks, const uint
                         const uint32_t klo = (uint32_t)key, khi = (uint32_t)(key >> 32);
                         slot = hash_slot(key, (uint32_t)TS);
                         claimed = false;
+                        add = s.w;                                                     // the super-k-mer's multiplicity
                         uint32_t probes = 0;
                         while (true) {
                             const uint2 cur = lds_u64x(aK + 8u * slot);
@@ -790,14 +835,15 @@ k_merge_tier(const ChunkView *__restrict__ chunks, uint32_t n_chunks, const uint
                                 if (old == key) break;
                             }
                             slot = slot + 1u == (uint32_t)TS ? 0u : slot + 1u;
-                            if (++probes >= TIER_PROBE_LIMIT) { s_cnt[3] = 1u; claimed = true; fb = 0; break; }
+                            if (++probes >= TIER_PROBE_LIMIT) { s_cnt[3] = 1u; fb = 0; add = 0; break; }
                         }
                     }
                     __syncwarp();
-                    if (!claimed) atoms_inc32(aC + 4u * slot);
+                    if (claimed) --add;                    // the counter word holds occurrences - 1: the claim itself counts one
+                    if (add) atoms_add32(aC + 4u * slot, add);
                     if (fb && ((lds_u32(aC + 4u * slot) >> 30) & fb) != fb) atoms_or32(aC + 4u * slot, fb << 30);
                     j += (uint32_t)__popc(smask);
-                    if (j + 1u < nsk && lds_u32(aStart + 4u * (j + 1u)) == r0 + 32u) ++j;   // next window starts a new super-k-mer
+                    if (j + 1u < nrep && lds_u32(aStart + 4u * (j + 1u)) == r0 + 32u) ++j;  // next window starts a new super-k-mer
                 }
             }
         }
@@ -852,7 +898,7 @@ k_merge_tier(const ChunkView *__restrict__ chunks, uint32_t n_chunks, const uint
         if (tid == 0) {
             if (!full) {
                 const uint32_t S = s_cnt[0], oslot = out.slot(unit_rel);
-                out.stats(S, s_cnt[1], tot);
+                out.stats(S, s_cnt[1], n_records);
                 out.unit_out_off[oslot] = gbase;
                 out.unit_out_cnt[oslot] = S;
             }
