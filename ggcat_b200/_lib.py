@@ -86,6 +86,7 @@ SYMBOLS = {
     "ggcat_b200_merge_bucket_range_device": (_i32, [_vp, _u32, _u32, C.POINTER(_u64), C.POINTER(_u64), C.POINTER(_u64)]),
     "ggcat_b200_device_table": (_i32, [_vp, C.POINTER(TableC)]),
     "ggcat_b200_partial_unitigs": (_i32, [_vp, _u32, C.POINTER(UnitigsC)]),
+    "ggcat_b200_maximal_unitigs": (_i32, [_vp, C.POINTER(UnitigsC)]),
     "ggcat_b200_reset": (_i32, [_vp]),
     "ggcat_b200_n_chunks": (_u32, [_vp]),
     "ggcat_b200_export_chunk_slice": (_i32, [_vp, _u32, _u32, _u32, C.POINTER(ChunkSliceC)]),

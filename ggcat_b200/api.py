@@ -340,6 +340,16 @@ class GGCATB200:
         bases = np.ctypeslib.as_array(u.bases, shape=(nw,)).copy() if nw else np.zeros(0, np.uint32)
         return recs, bases, int(u.n_kmers)
 
+    def maximal_unitigs(self):
+        """Maximal unitigs: the partial unitigs of the last partial_unitigs() call joined on the device
+        (ggcat_b200_maximal_unitigs).  Same return shape as partial_unitigs()."""
+        u = _lib.UnitigsC()
+        _check(self._lib.ggcat_b200_maximal_unitigs(self._h, C.byref(u)))
+        n, nw = int(u.n_unitigs), int(u.n_words)
+        recs = np.ctypeslib.as_array(C.cast(u.unitigs, C.POINTER(C.c_uint8)), shape=(n * 24,)).copy().view(self.UNITIG_DTYPE) if n else np.zeros(0, self.UNITIG_DTYPE)
+        bases = np.ctypeslib.as_array(u.bases, shape=(nw,)).copy() if nw else np.zeros(0, np.uint32)
+        return recs, bases, int(u.n_kmers)
+
     # -- multi-GPU plumbing
     def n_chunks(self) -> int:
         return int(self._lib.ggcat_b200_n_chunks(self._h))

@@ -184,6 +184,8 @@ struct ggcat_b200_ctx {
     std::vector<UnitTot> unit_tot;    // merge: per-unit totals over all chunks (kept allocated between merges)
     // phase-2 workspace
     DevBuf ut_links, ut_visited, ut_recs, ut_bases, ut_counters;   // partial unitigs (unitigs.cuh)
+    DevBuf mu_recs, mu_bases, mu_ht, mu_first, mu_partner, mu_visited;   // maximal unitigs (join of the partial ones)
+    uint64_t ut_n = 0, ut_words = 0;                                 // partial unitigs / words of the last partial_unitigs call
     uint8_t *h_unitigs = nullptr; size_t h_unitigs_cap = 0;        // pinned: records, then packed bases
     DevBuf tok_agg, tok_keep, tok_base, tok_marks, tok_tmarks, tok_seq, tok_offsets, tok_text, tok_colors;   // FASTA / FASTQ tokenizer (tokenize.cuh)
     DevBuf d_static_off;                   // wide path: static output regions of partitioned units
@@ -1373,6 +1375,7 @@ int32_t ggcat_b200_reset(ggcat_b200_ctx *c) {
         else { ch->release(); delete ch; }
     }
     c->chunks.clear();
+    c->ut_n = c->ut_words = 0;
     c->fin = FinalTable();
     c->finished = false;
     c->peer.build_started = false;
@@ -1393,7 +1396,7 @@ void ggcat_b200_destroy(ggcat_b200_ctx *c) {
                       &c->d_rkpos, &c->d_recfl, &c->d_mstage, &c->d_static_off, &c->cursor, &c->unit_out_off, &c->unit_out_cnt, &c->unit_final_off, &c->overflow, &c->d_retry,
                       &c->d_partmeta, &c->d_recs, &c->fin_tmp_keys, &c->fin_tmp_cf, &c->tok_agg, &c->tok_keep, &c->tok_base, &c->tok_marks,
                       &c->tok_tmarks, &c->tok_seq, &c->tok_offsets, &c->tok_text, &c->tok_colors, &c->ut_links, &c->ut_visited, &c->ut_recs,
-                      &c->ut_bases, &c->ut_counters,
+                      &c->ut_bases, &c->ut_counters, &c->mu_recs, &c->mu_bases, &c->mu_ht, &c->mu_first, &c->mu_partner, &c->mu_visited,
                       &c->out_hi, &c->out_hi2, &c->unit_keys, &c->unit_cols, &c->col_off, &c->out_coloff, &c->out_colors})
         b->release();
     for (cudaEvent_t e : c->event_pool) cudaEventDestroy(e);
@@ -1742,6 +1745,7 @@ int32_t ggcat_b200_partial_unitigs(ggcat_b200_ctx *c, uint32_t result_buckets_lo
     const FinalTable &f = c->fin;
     if (!f.unit_off || f.n_units == 0) return set_err(GGCAT_B200_ERR_STATE, "partial_unitigs before merge_bucket_range_device");
     if (c->wide_mode >= 0) return set_err(GGCAT_B200_ERR_INVALID, "partial unitigs are built on the 64-bit key path (seq-hash, k <= 31, no colours)");
+    if (c->P.forward_only) return set_err(GGCAT_B200_ERR_INVALID, "partial unitigs of forward-only builds are not built on the device");
     if ((c->P.k & 1u) == 0) return set_err(GGCAT_B200_ERR_INVALID, "partial unitigs need odd k (self-complementary k-mers of even k, final_executor.rs:249-264, are not handled)");
     if (result_buckets_log > 15) return set_err(GGCAT_B200_ERR_INVALID, "result_buckets_log > 15");
     static_assert(sizeof(UnitigRec) == sizeof(ggcat_b200_unitig), "device record == ABI record");
@@ -1775,10 +1779,57 @@ int32_t ggcat_b200_partial_unitigs(ggcat_b200_ctx *c, uint32_t result_buckets_lo
     if (nu) CU(cudaMemcpyAsync(c->h_unitigs, c->ut_recs.p, nu * sizeof(UnitigRec), cudaMemcpyDeviceToHost, st));
     if (nw) CU(cudaMemcpyAsync(c->h_unitigs + rec_bytes, c->ut_bases.p, nw * 4, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    c->ut_n = nu; c->ut_words = nw;
     out->n_unitigs = nu; out->n_words = nw; out->n_kmers = c->h_pinned[2];
     out->unitigs = reinterpret_cast<const ggcat_b200_unitig *>(c->h_unitigs);
     out->bases = reinterpret_cast<const uint32_t *>(c->h_unitigs + rec_bytes);
     out->d_unitigs = c->ut_recs.p; out->d_bases = c->ut_bases.as<uint32_t>();
+    return 0;
+}
+
+
+int32_t ggcat_b200_maximal_unitigs(ggcat_b200_ctx *c, ggcat_b200_unitigs *out) {
+    TRY(check_ctx(c));
+    std::lock_guard<std::mutex> lock__(c->mu);
+    if (!out) return set_err(GGCAT_B200_ERR_INVALID, "null output");
+    memset(out, 0, sizeof(*out));
+    const uint64_t n = c->ut_n;
+    if (n == 0) return c->fin.unit_off ? 0 : set_err(GGCAT_B200_ERR_STATE, "maximal_unitigs before partial_unitigs");
+    if (n >= (1ull << 31)) return set_err(GGCAT_B200_ERR_INVALID, "too many partial unitigs for one join");
+    cudaStream_t st = c->stream;
+    const uint64_t slots = 4 * n + 1024, word_cap = c->ut_words + n + 16;
+    CU(c->mu_ht.reserve(slots * 8)); CU(c->mu_first.reserve(slots * 4)); CU(c->mu_partner.reserve(2 * n * 4)); CU(c->mu_visited.reserve(n));
+    CU(c->mu_recs.reserve(n * sizeof(UnitigRec))); CU(c->mu_bases.reserve(word_cap * 4));
+    CU(cudaMemsetAsync(c->ut_counters.p, 0, 64, st));
+    JoinTable J;
+    J.recs = c->ut_recs.as<UnitigRec>(); J.bases = c->ut_bases.as<uint32_t>(); J.n = n; J.k = c->P.k;
+    J.ht_keys = c->mu_ht.as<unsigned long long>(); J.ht_first = c->mu_first.as<uint32_t>(); J.ht_slots = slots;
+    J.partner = c->mu_partner.as<uint32_t>(); J.visited = c->mu_visited.as<uint8_t>();
+    UnitigOut O;
+    O.recs = c->mu_recs.as<UnitigRec>(); O.bases = c->mu_bases.as<uint32_t>(); O.counters = c->ut_counters.as<unsigned long long>();
+    O.rec_cap = n; O.word_cap = word_cap; O.overflow = reinterpret_cast<uint32_t *>(c->ut_counters.as<unsigned long long>() + 4); O.result_bits = 0;
+    {
+        LaunchTimer t(c, F_UNITIGS, 4);
+        k_join_init<<<(unsigned)((slots + 255) / 256), 256, 0, st>>>(J);
+        k_join_ends<<<(unsigned)((2 * n + 255) / 256), 256, 0, st>>>(J, O.overflow);
+        k_join_chains<<<(unsigned)((2 * n + 255) / 256), 256, 0, st>>>(J, O);
+        k_join_cycles<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(J, O);
+    }
+    CU(cudaMemcpyAsync(c->h_pinned, c->ut_counters.p, 40, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    CU(cudaGetLastError());
+    if ((uint32_t)c->h_pinned[4] & 4u) return set_err(GGCAT_B200_ERR_INVALID, "maximal_unitigs: more than two open ends share a k-mer (partial unitigs of an incomplete bucket range?)");
+    if ((uint32_t)c->h_pinned[4]) return set_err(GGCAT_B200_ERR_CAPACITY, "maximal unitig output overflow (code %u)", (uint32_t)c->h_pinned[4]);
+    const uint64_t nu = c->h_pinned[0], nw = c->h_pinned[1];
+    const size_t rec_bytes = (nu * sizeof(UnitigRec) + 15) & ~(size_t)15;
+    TRY(pinned_reserve(&c->h_unitigs, &c->h_unitigs_cap, rec_bytes + nw * 4 + 16));
+    if (nu) CU(cudaMemcpyAsync(c->h_unitigs, c->mu_recs.p, nu * sizeof(UnitigRec), cudaMemcpyDeviceToHost, st));
+    if (nw) CU(cudaMemcpyAsync(c->h_unitigs + rec_bytes, c->mu_bases.p, nw * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    out->n_unitigs = nu; out->n_words = nw; out->n_kmers = c->h_pinned[2];
+    out->unitigs = reinterpret_cast<const ggcat_b200_unitig *>(c->h_unitigs);
+    out->bases = reinterpret_cast<const uint32_t *>(c->h_unitigs + rec_bytes);
+    out->d_unitigs = c->mu_recs.p; out->d_bases = c->mu_bases.as<uint32_t>();
     return 0;
 }
 

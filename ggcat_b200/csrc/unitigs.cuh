@@ -237,4 +237,144 @@ __global__ void __launch_bounds__(256) k_unitig_cycles(UnitigTable T, const uint
     ut_emit(T, links, visited, O, (uint32_t)e, UT_BW, n, false, false, true);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Joining partial unitigs into maximal unitigs.
+//
+// Replaces crates/assembler_pipeline/src/extend_unitigs.rs:348- ("phase: unitigs joining"): the reference reads the
+// "result" buckets one after the other, keeps the partial unitigs of a bucket in a hash map keyed by the hash of their
+// open end, glues two partial unitigs that end in the same k-mer (stored once in each of the two units, with complementary
+// flags) and re-routes the glued piece by its other open end until nothing is open.  The fixed point of that is a graph
+// problem again: an open end has exactly one partner (the other partial unitig that ends in the same canonical k-mer), so
+// partial unitigs form chains and cycles, and every chain / cycle is one maximal unitig.
+//   k_join_ends    one thread per open end: canonical end k-mer -> CAS hash table; the second arrival pairs the two ends
+//   k_join_chains  one thread per chain end (closed end, or an open end nobody answered): walk through the partners; the
+//                  smaller end id emits -- first piece whole, every further piece without the k bases it shares
+//   k_join_cycles  pieces no chain visited: the smallest piece of a cycle emits it (k + L - 1 bases for L k-mers)
+// Orientation of a joined unitig is the walk's (the reference's depends on thread timing: SURVEY App. C); consumers
+// compare canonical k-mer sets.
+struct JoinTable {
+    const UnitigRec *recs; const uint32_t *bases;
+    uint64_t n;                       // partial unitigs
+    uint32_t k;
+    unsigned long long *ht_keys;      // open-addressing table of canonical end k-mers (EMPTY = ~0)
+    uint32_t *ht_first;               // first end that arrived at the slot
+    uint64_t ht_slots;
+    uint32_t *partner;                // [2n]: end id (unitig << 1 | end) of the partner end, UT_NONE = none
+    uint8_t *visited;                 // [n]
+};
+
+__device__ __forceinline__ uint64_t join_end_kmer(const JoinTable &J, uint64_t u, int end) {
+    const UnitigRec r = J.recs[u];
+    const uint32_t off = end ? r.len - J.k : 0u;
+    return extract64(J.bases + r.word_offset, 2ull * off) & ((1ull << (2 * J.k)) - 1ull);
+}
+
+__global__ void __launch_bounds__(256) k_join_init(JoinTable J) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < J.ht_slots) { J.ht_keys[i] = ~0ull; J.ht_first[i] = UT_NONE; }
+    if (i < 2 * J.n) J.partner[i] = UT_NONE;
+    if (i < J.n) J.visited[i] = 0;
+}
+
+__global__ void __launch_bounds__(256) k_join_ends(JoinTable J, uint32_t *__restrict__ overflow) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 2 * J.n) return;
+    const uint64_t u = t >> 1;
+    const int end = (int)(t & 1);
+    if (!(J.recs[u].flags & (end ? UTF_OPEN_END : UTF_OPEN_BEGIN))) return;
+    const uint64_t key = ut_canon(join_end_kmer(J, u, end), J.k);
+    uint64_t slot = ((key * 0x9E3779B97F4A7C15ull) >> 20) % J.ht_slots;
+    while (true) {
+        const unsigned long long old = atomicCAS(&J.ht_keys[slot], ~0ull, (unsigned long long)key);
+        if (old == ~0ull || old == key) break;
+        slot = slot + 1 == J.ht_slots ? 0 : slot + 1;
+    }
+    const uint32_t first = atomicCAS(&J.ht_first[slot], UT_NONE, (uint32_t)t);
+    if (first == UT_NONE) return;                                // the partner has not arrived yet
+    if (atomicCAS(&J.partner[first], UT_NONE, (uint32_t)t) != UT_NONE) { atomicOr(overflow, 4u); return; }   // a third end with this k-mer
+    J.partner[t] = first;
+}
+
+// Emits the chain / cycle that starts at piece u0, entered through end e0, n_pieces long.
+__device__ void join_emit(const JoinTable &J, const UnitigOut &O, uint64_t u0, int e0, uint32_t n_pieces, uint64_t total_len, bool cycle) {
+    const uint32_t k = J.k;
+    const uint64_t len = cycle ? total_len - 1 : total_len;
+    const uint64_t nw = (len + 15) >> 4;
+    const unsigned long long ri = atomicAdd(&O.counters[0], 1ull), w0 = atomicAdd(&O.counters[1], (unsigned long long)nw);
+    atomicAdd(&O.counters[2], (unsigned long long)(len - k + 1));
+    if (ri >= O.rec_cap || w0 + nw > O.word_cap || len >= (1ull << 32)) { atomicOr(O.overflow, 1u); return; }
+    uint32_t *dst = O.bases + w0;
+    uint32_t word = 0, nb = 0;
+    uint64_t wi = 0, written = 0, cur = u0;
+    int enter = e0;
+    for (uint32_t p = 0; p < n_pieces; p++) {
+        J.visited[cur] = 1;
+        const UnitigRec r = J.recs[cur];
+        const uint32_t *src = J.bases + r.word_offset;
+        for (uint32_t q = p ? k : 0u; q < r.len && written < len; q++) {
+            // entered at the beginning: stored orientation; entered at the end: reverse complement
+            const uint32_t pos = enter == 0 ? q : r.len - 1 - q;
+            uint32_t c = (src[pos >> 4] >> (2 * (pos & 15u))) & 3u;
+            if (enter) c ^= 2u;
+            word |= c << (2 * nb);
+            if (++nb == 16) { dst[wi++] = word; word = 0; nb = 0; }
+            ++written;
+        }
+        if (p + 1 < n_pieces) {
+            const uint32_t nx = J.partner[2 * cur + (uint64_t)(enter ^ 1)];
+            cur = nx >> 1; enter = (int)(nx & 1u);
+        }
+    }
+    if (nb) dst[wi++] = word;
+    UnitigRec o;
+    o.word_offset = w0; o.len = (uint32_t)len; o.unit = n_pieces; o.bucket = 0xFFFFu;
+    // a lonely partial unitig that was a cycle inside its unit keeps its circular flag (it already has k + L - 1 bases)
+    o.flags = (uint8_t)((cycle || (n_pieces == 1 && (J.recs[u0].flags & UTF_CIRCULAR))) ? UTF_CIRCULAR : 0);
+    o.last_align = 0; o.n_kmers = (uint32_t)(len - k + 1);
+    O.recs[ri] = o;
+}
+
+__global__ void __launch_bounds__(256) k_join_chains(JoinTable J, UnitigOut O) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 2 * J.n) return;
+    if (J.partner[t] != UT_NONE) return;                         // not a chain end
+    const uint64_t u0 = t >> 1;
+    const int e0 = (int)(t & 1);
+    uint64_t cur = u0, total = J.recs[u0].len;
+    int enter = e0;
+    uint32_t n = 1;
+    while (true) {
+        const uint32_t nx = J.partner[2 * cur + (uint64_t)(enter ^ 1)];
+        if (nx == UT_NONE) break;
+        cur = nx >> 1; enter = (int)(nx & 1u);
+        total += J.recs[cur].len - J.k;
+        if (++n > J.n) { atomicOr(O.overflow, 2u); return; }
+    }
+    const uint64_t other = 2 * cur + (uint64_t)(enter ^ 1);
+    if (other < t) return;                                        // the other end of the chain emits
+    join_emit(J, O, u0, e0, n, total, false);
+}
+
+__global__ void __launch_bounds__(256) k_join_cycles(JoinTable J, UnitigOut O) {
+    const uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= J.n) return;
+    if (J.visited[u] || J.partner[2 * u] == UT_NONE || J.partner[2 * u + 1] == UT_NONE) return;
+    uint64_t cur = u, total = J.recs[u].len;
+    int enter = 0;
+    uint32_t n = 1;
+    while (true) {
+        const uint32_t nx = J.partner[2 * cur + (uint64_t)(enter ^ 1)];
+        if (nx == UT_NONE) return;                               // a chain after all: unreachable
+        cur = nx >> 1; enter = (int)(nx & 1u);
+        if (cur == u) break;
+        if (cur < u) return;                                     // a smaller piece owns this cycle
+        total += J.recs[cur].len - J.k;
+        if (++n > J.n) { atomicOr(O.overflow, 2u); return; }
+    }
+    // closing the cycle: the last piece's last k-mer is the first piece's first k-mer.  total = sum(len) - k (n - 1) has
+    // L + 1 k-mers for the cycle's L; join_emit drops the last base
+    join_emit(J, O, u, 0, n, total, true);
+}
+
 }  // namespace ggb

@@ -219,6 +219,15 @@ typedef struct {
     const uint32_t *d_bases;
 } ggcat_b200_unitigs;
 int32_t ggcat_b200_partial_unitigs(ggcat_b200_ctx *ctx, uint32_t result_buckets_log, ggcat_b200_unitigs *out);
+/* Joins the partial unitigs of the last ggcat_b200_partial_unitigs call into MAXIMAL unitigs, on the device
+ * (SURVEY 8(f)-2): the fixed point of the reference's "phase: unitigs joining"
+ * (crates/assembler_pipeline/src/extend_unitigs.rs:348-): two partial unitigs that end in the same canonical k-mer are
+ * glued with that k-mer shared, chains and cycles of partial unitigs become one unitig each.  The partial unitigs must
+ * cover the whole build (merge_bucket_range_device over all buckets of one GPU); across GPUs the partial unitigs are
+ * first brought together by their result bucket (flags / bucket above).  Records: unit = number of partial unitigs glued,
+ * bucket = 0xFFFF, flags = 4 for circular unitigs (k + L - 1 bases for L k-mers).  Orientation is the walk's (the
+ * reference's depends on thread timing); compare canonical k-mer sets.  Invalidates the pointers of partial_unitigs. */
+int32_t ggcat_b200_maximal_unitigs(ggcat_b200_ctx *ctx, ggcat_b200_unitigs *out);
 
 /* Drops all bucket chunks so the context can be reused for another build. */
 int32_t ggcat_b200_reset(ggcat_b200_ctx *ctx);

@@ -1085,3 +1085,78 @@ def test_partial_unitigs_c1_join_to_maximal_unitigs(golden_dir):
         assert ends and set(ends.values()) == {2}
     finally:
         ctx.close()
+
+
+def _canon_kmers_of(strings, k):
+    """Sorted canonical k-mer keys (seq-hash u64: base i at bits 2i, A0 C1 T2 G3) of a list of sequences, with duplicates."""
+    code = np.zeros(256, np.uint64)
+    for ch, v in ((b"A", 0), (b"C", 1), (b"T", 2), (b"G", 3)):
+        code[ch[0]] = v
+    out = []
+    for sq in strings:
+        c = code[np.frombuffer(sq, np.uint8)]
+        n = len(sq) - k + 1
+        if n <= 0:
+            continue
+        win = np.lib.stride_tricks.sliding_window_view(c, k)
+        sh = (np.arange(k, dtype=np.uint64) * np.uint64(2))[None, :]
+        fw = (win << sh).sum(axis=1, dtype=np.uint64)
+        rc = ((win ^ np.uint64(2)) << sh[:, ::-1]).sum(axis=1, dtype=np.uint64)
+        out.append(np.minimum(fw, rc))
+    return np.sort(np.concatenate(out)) if out else np.zeros(0, np.uint64)
+
+
+@pytest.mark.parametrize("k,m,b1,b2,s", [(31, 12, 3, 2, 1), (31, 12, 2, 2, 2), (21, 10, 2, 2, 1), (27, 11, 4, 3, 1)])
+def test_maximal_unitigs_joined_on_device(k, m, b1, b2, s):
+    """SURVEY 8(f)-2 + north-star check 2 through the PRODUCT path: reads -> tables -> partial unitigs -> maximal unitigs,
+    all on the device; the result equals the unitigs of the independently counted global k-mer set (oracle join of the
+    flag-free global build): same unitig count, same length multiset, same canonical k-mer set, every k-mer once."""
+    G = _gpu()
+    rng = np.random.default_rng(k * 3 + s)
+    g = util.rand_seq(rng, 20000)
+    cyc = util.rand_seq(rng, 400)
+    seqs = [g, util.revcomp(g[3000:9000]), g[8000:15000], g[:700] + g[1500:3000], util.rand_seq(rng, 900),
+            g[15000:16000] + g[100:1100], cyc + cyc[:k], b"ACACACACAC" * 12, g[4000:4100] + b"N" + g[4101:4300]]
+    if s == 2:
+        seqs = seqs + seqs[:5]
+    reads = O.Reads.from_list(seqs)
+    ctx, st = G.minimizer_bucketing([(reads.data, reads.offsets)], b1, b2, k, m, min_multiplicity=s)
+    try:
+        ne, _, _ = ctx.merge_bucket_range_device(0, (1 << b1) + 1)
+        precs, _, pk = ctx.partial_unitigs(4)
+        assert pk == ne
+        recs, bases, nk = ctx.maximal_unitigs()
+    finally:
+        ctx.close()
+    nv, _ = O.naive_count(reads, k)
+    nv = nv[nv["count"] >= s]
+    B = O.unitigs_from_tables(nv["key_lo"], nv["key_hi"], nv["count"].astype(np.uint32), np.array([0, len(nv)], np.uint64), k)
+    assert len(recs) == B["n_unitigs"] and len(precs) > len(recs)
+    assert np.array_equal(np.sort(recs["len"].astype(np.uint64)), B["lengths"])
+    strings = [sq for _, sq, _, _, _ in _unitig_strings(recs, bases)]
+    km = _canon_kmers_of(strings, k)
+    assert nk == len(nv) == km.size
+    assert np.array_equal(km, nv["key_lo"]), "the maximal unitigs hold every kept k-mer exactly once"
+    assert (recs["flags"] & 4).any(), "the circular unitig is flagged"
+
+
+def test_c1_maximal_unitigs_on_device(golden_dir):
+    """BASELINE configs[0] end to end on the device: maximal unitigs of sal1+sal2+sal3 (k=31 -s 1) vs the golden unitig
+    count and the global k-mer set."""
+    G = _gpu()
+    k, m, b1, b2, s = 31, 12, 2, 6, 1
+    reads = O.Reads.from_list(util.c1_records())
+    ctx, st = G.minimizer_bucketing([(reads.data, reads.offsets)], b1, b2, k, m, min_multiplicity=s)
+    try:
+        ne, _, _ = ctx.merge_bucket_range_device(0, (1 << b1) + 1)
+        ctx.partial_unitigs(3)
+        recs, bases, nk = ctx.maximal_unitigs()
+    finally:
+        ctx.close()
+    gold = json.loads((golden_dir / "c1_golden.json").read_text())
+    nv, _ = O.naive_count(reads, k)
+    assert nk == len(nv)
+    if "n_unitigs" in gold:
+        assert len(recs) == gold["n_unitigs"]
+    km = _canon_kmers_of([sq for _, sq, _, _, _ in _unitig_strings(recs, bases)], k)
+    assert np.array_equal(km, nv["key_lo"])
