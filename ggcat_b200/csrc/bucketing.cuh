@@ -137,7 +137,7 @@ __device__ __forceinline__ uint64_t bits64(const uint32_t *bm, uint32_t s, uint3
 __global__ void __launch_bounds__(WIN_THREADS)
 k_windows(const uint32_t *__restrict__ pk, const uint32_t *__restrict__ bad, const uint32_t *__restrict__ brk,
           uint32_t n /* bases in batch */, DevParams P, uint64_t *__restrict__ ent, uint32_t *__restrict__ tile_cnt,
-          uint32_t *__restrict__ tile_scnt) {
+          uint32_t *__restrict__ tile_scnt, uint32_t *__restrict__ seg_count) {
     // TMA landing buffers (16-byte aligned; the tile's first word sits at offset (W0 & 3) / (BW0 & 3) because the
     // bulk copy starts at the 16-byte boundary below it)
     __shared__ __align__(16) uint32_t s_pk_raw[(WIN_T + 2 * WIN_WMAX + 64) / 16 + 12];
@@ -152,6 +152,7 @@ k_windows(const uint32_t *__restrict__ pk, const uint32_t *__restrict__ bad, con
     __shared__ uint64_t s_TF[32][4], s_TR[32][4];  // rotl(h(c), m-1-i), rotl(r(c), i)
     __shared__ uint64_t s_T1[16], s_T2[16];        // roll tables indexed by (leaving base << 2 | entering base)
     __shared__ uint32_t s_scan[WIN_THREADS / 32 + 2];
+    __shared__ uint32_t s_nfirst;                  // segments (N-free stretches of >= k bases) that start in this tile
 
     const uint32_t tid = threadIdx.x;
     const uint32_t tile = blockIdx.x;
@@ -172,6 +173,7 @@ k_windows(const uint32_t *__restrict__ pk, const uint32_t *__restrict__ bad, con
     uint32_t *s_pk = s_pk_raw + (W0 & 3u), *s_bad = s_bad_raw + (BW0 & 3u), *s_cmb = s_cmb_raw + (BW0 & 3u);
     const uint32_t pk_words = (n_pkw + (W0 & 3u) + 3u) & ~3u, bm_words = (n_bmw + (BW0 & 3u) + 3u) & ~3u;
     if (tid == 0) {
+        s_nfirst = 0;
         mbar_init(&s_bar, 1);
         mbar_expect_tx(&s_bar, (pk_words + 2 * bm_words) * 4);
         tma_load_1d(s_pk_raw, pk + (W0 & ~3u), pk_words * 4, &s_bar);
@@ -318,6 +320,7 @@ k_windows(const uint32_t *__restrict__ pk, const uint32_t *__restrict__ bad, con
                 fl |= ((S ? 1u : 0u) | (!okn ? 2u : 0u) | (first ? 4u : 0u)) << (3 * i);
             }
         }
+        if (fl & 0x924924u) atomicAdd(&s_nfirst, (uint32_t)__popc(fl & 0x924924u));   // bit 2 of every 3-bit group: segment starts (rare)
         uint32_t mine = 0;
 #pragma unroll
         for (int i = 0; i < WPT; i++) {
@@ -363,7 +366,10 @@ k_windows(const uint32_t *__restrict__ pk, const uint32_t *__restrict__ bad, con
         }
         ent[(uint64_t)tile * WIN_T + i] = e;
     }
-    if (tid == 0) { tile_cnt[tile] = n_ent; tile_scnt[tile] = n_s; }
+    if (tid == 0) {
+        tile_cnt[tile] = n_ent; tile_scnt[tile] = n_s;
+        if (s_nfirst) atomicAdd(seg_count, s_nfirst);     // SequencesSplitter::valid_bases bookkeeping (one atomic per tile)
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -404,18 +410,15 @@ k_emit(const uint64_t *__restrict__ ent, const uint32_t *__restrict__ tile_cnt, 
        uint32_t n_tiles, DevParams P, uint4 *__restrict__ tmp, uint32_t *__restrict__ tmp_color,
        uint32_t base /* position of the batch's first base inside the chunk's packed bases */,
        const uint64_t *__restrict__ offsets, uint64_t n_reads, uint64_t off0, const uint32_t *__restrict__ colors,
-       uint32_t *__restrict__ unit_cnt, uint32_t *__restrict__ unit_words, uint32_t *__restrict__ unit_kmers,
-       uint32_t *__restrict__ seg_count) {
+       uint32_t *__restrict__ unit_cnt, uint32_t *__restrict__ unit_words, uint32_t *__restrict__ unit_kmers) {
     const uint32_t tile = blockIdx.x;
     const uint32_t cnt = tile_cnt[tile];
     const uint32_t posmask = (1u << ENT_POS_BITS) - 1;
-    uint32_t my_first = 0;   // N-free segments of length >= k that start in this tile (SequencesSplitter::valid_bases bookkeeping)
     for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) {
         const uint64_t e = ent[(uint64_t)tile * WIN_T + i];
         if (!(e & ENT_S)) continue;
         const uint32_t pos = tile * WIN_T + (uint32_t)(e & posmask);
         const bool first = e & ENT_FIRST;
-        my_first += first ? 1u : 0u;
         uint32_t end;
         bool last;
         if (e & ENT_E) {
@@ -457,15 +460,6 @@ k_emit(const uint64_t *__restrict__ ent, const uint32_t *__restrict__ tile_cnt, 
         atomicAdd(&unit_words[unit], (len + 15u) >> 4);
         atomicAdd(&unit_kmers[unit], len - P.k + 1u);
     }
-    // one global atomic per tile (a per-warp atomic on this single counter cost 0.19 ms per 150 Mbases)
-    __shared__ uint32_t s_first;
-    if (threadIdx.x == 0) s_first = 0;
-    __syncthreads();
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) my_first += __shfl_xor_sync(0xffffffffu, my_first, o);
-    if ((threadIdx.x & 31u) == 0 && my_first) atomicAdd(&s_first, my_first);
-    __syncthreads();
-    if (threadIdx.x == 0 && s_first) atomicAdd(seg_count, s_first);
 }
 
 // ------------------------------------------------------------------------------------------------

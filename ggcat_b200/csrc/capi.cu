@@ -349,7 +349,7 @@ int32_t bucket_batch_device(ggcat_b200_ctx *c, const uint8_t *d_data, const uint
         LaunchTimer t(c, F_WINDOWS);
         k_windows<<<n_tiles, WIN_THREADS, 0, st>>>(pkb, c->bad.as<uint32_t>(), c->brk.as<uint32_t>(),
                                                    (uint32_t)n, P, c->ent.as<uint64_t>(), c->tile_cnt.as<uint32_t>(),
-                                                   c->tile_sbase.as<uint32_t>());
+                                                   c->tile_sbase.as<uint32_t>(), ch->unit_cnt.as<uint32_t>() + P.n_units /* spare slot: segments */);
     }
     CU(c->totals.reserve(8 * 8));
     {
@@ -370,7 +370,7 @@ int32_t bucket_batch_device(ggcat_b200_ctx *c, const uint8_t *d_data, const uint
         k_emit<<<n_tiles, 256, 0, st>>>(c->ent.as<uint64_t>(), c->tile_cnt.as<uint32_t>(), c->tile_sbase.as<uint32_t>(),
                                         n_tiles, P, c->tmp.as<uint4>() + c->open_sk, c->tmp_color.as<uint32_t>() + c->open_sk, (uint32_t)base,
                                         d_offsets, n_reads, off0, d_colors, ch->unit_cnt.as<uint32_t>(), ch->unit_words.as<uint32_t>(),
-                                        ch->unit_kmers.as<uint32_t>(), ch->unit_cnt.as<uint32_t>() + P.n_units /* spare slot: segments */);
+                                        ch->unit_kmers.as<uint32_t>());
     }
     CU(cudaGetLastError());
     c->open_sk += n_sk; c->open_bases += padded; ch->n_bases += n;
