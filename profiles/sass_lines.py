@@ -68,7 +68,7 @@ def main():
     for l, (s, n) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:topn]:
         text = ""
         if l:
-            f = next((p for p in (ROOT / "ggcat_b200" / "csrc").glob(l[0])), None)
+            f = next((p for p in (Path(os.environ.get("GGCAT_B200_PROF_SRC", str(ROOT / "ggcat_b200" / "csrc")))).glob(l[0])), None)
             if f:
                 src_cache.setdefault(f, f.read_text().splitlines())
                 if l[1] - 1 < len(src_cache[f]):
