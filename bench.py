@@ -42,6 +42,13 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 K, M, S = 31, 12, 2
+# parameters of the benchable BASELINE configs; wp = key + payload bytes, R = LSD passes of the SURVEY 8(d) byte model
+WORKLOADS = {
+    "c2": dict(k=31, m=12, s=2, hash_type=1, colors=False, wp=12, R=8),
+    "c4": dict(k=31, m=12, s=2, hash_type=1, colors=False, wp=12, R=8),
+    "c5": dict(k=63, m=14, s=2, hash_type=4, colors=False, wp=20, R=16),   # -w rabin-karp128
+    "c3": dict(k=31, m=12, s=1, hash_type=1, colors=True, wp=16, R=8),     # -c, colour = genome index
+}
 READ_LEN = 150
 READS_PER_GPU = 1_000_000
 GENOME_PER_GPU = 5_000_000
@@ -112,6 +119,12 @@ def workload_string(wl: str, n_reads: int, world: int, b1: int, b2: int) -> str:
     if wl == "c2":
         return (f"C2 per GPU: {n_reads} x {READ_LEN} bp reads (30x of {GENOME_PER_GPU * world} bp genome, 1% errors), "
                 f"k={K} m={M} -s {S} seq-hash, buckets {1 << b1}(+1) x {1 << b2}")
+    if wl == "c5":
+        return (f"C5 slice per GPU: {n_reads} x {READ_LEN} bp reads (30x of {5 * n_reads * world} bp genome, error-free), "
+                f"k=63 m=14 -s 2 rabin-karp128, buckets {1 << b1}(+1) x {1 << b2}")
+    if wl == "c3":
+        return (f"C3: {n_reads} genomes x 5000000 bp (20 shared 200 kbp segments mutated at 0.1%), colour = genome, "
+                f"k=31 m=12 -s 1 -c, buckets {1 << b1}(+1) x {1 << b2}")
     return (f"C4 per GPU: {n_reads} x {READ_LEN} bp reads (30x of {5 * n_reads * world} bp genome, error-free), "
             f"k={K} m={M} -s {S} seq-hash, buckets {1 << b1}(+1) x {1 << b2}")
 
@@ -303,9 +316,23 @@ def run_ours(args):
     from ggcat_b200 import dist as gdist
 
     wl = args.workload
-    n_reads = args.reads_per_gpu if args.reads_per_gpu else (READS_PER_GPU if wl == "c2" else 20_000_000)
+    cfg = WORKLOADS[wl]
+    if wl in ("c3", "c5") and world > 1:
+        raise SystemExit("bench.py: --workload c3 / c5 are single-GPU lines")
+    n_reads = args.reads_per_gpu if args.reads_per_gpu else {"c2": READS_PER_GPU, "c4": 20_000_000, "c5": 10_000_000, "c3": 100}[wl]
     dev = torch.device("cuda", local_rank)
-    if wl == "c2":
+    d_col = h_col = None
+    if wl == "c3":
+        # BASELINE configs[2]: n_reads genomes of 5 Mbp, one record and one colour each (host generation, ~0.5 GB)
+        from ggcat_b200 import synth
+        data, offsets, colors = synth.config_c3(n_genomes=n_reads)
+        n_bases = int(data.size)
+        h_data = torch.from_numpy(data).pin_memory()
+        h_off = torch.from_numpy(offsets.view(np.int64)).pin_memory()
+        h_col = torch.from_numpy(colors.view(np.int32)).pin_memory()
+        d_data, d_off, d_col = h_data.cuda(), h_off.cuda(), h_col.cuda()
+        reads_per_push = args.reads_per_push if args.reads_per_push_given else 20
+    elif wl == "c2":
         data, offsets = make_reads(rank, world, n_reads)
         n_bases = int(data.size)
         h_data = torch.from_numpy(data).pin_memory()
@@ -321,8 +348,9 @@ def run_ours(args):
         # on the device; rank r holds reads [r*R, (r+1)*R).  Full C4 is 77.5 M reads per GPU at N=8.
         from ggcat_b200 import synth
         genome_len, err, seed_note = 5 * n_reads * world, 0.0, "error-free"
-        genome = synth.genome_codes_torch(0xC4, genome_len, dev)
-        d_data = synth.simulate_reads_torch(genome, n_reads, READ_LEN, 0.0, 0xC4 + 1, first_read=rank * n_reads)
+        wseed = 0xC4 if wl == "c4" else 0xC5
+        genome = synth.genome_codes_torch(wseed, genome_len, dev)
+        d_data = synth.simulate_reads_torch(genome, n_reads, READ_LEN, 0.0, wseed + 1, first_read=rank * n_reads)
         del genome
         torch.cuda.empty_cache()
         n_bases = int(d_data.numel())
@@ -336,19 +364,21 @@ def run_ours(args):
         reads_per_push = args.reads_per_push          # device pushes of 600 Mbases (one bucket chunk each)
     # bucket counts as the reference derives them from the size of the WHOLE input (all ranks' FASTA bytes,
     # crates/io/src/lib.rs:67-140)
-    b1, b2 = G.bucket_counts(int(n_reads * world * (READ_LEN + 15)))
+    b1, b2 = G.bucket_counts(int(n_bases * 1.016) if wl == "c3" else int(n_reads * world * (READ_LEN + 15)))
     if args.b1 is not None:
         b1 = args.b1
     nb = (1 << b1) + 1
-    ctx = G.GGCATB200(G.Params(k=K, m=M, min_multiplicity=S, buckets_count_log=b1, second_buckets_count_log=b2,
-                               device=local_rank))
+    ctx = G.GGCATB200(G.Params(k=cfg["k"], m=cfg["m"], min_multiplicity=cfg["s"], buckets_count_log=b1, second_buckets_count_log=b2,
+                               hash_type=cfg["hash_type"], colors=cfg["colors"], device=local_rank))
     ext = torch.cuda.ExternalStream(ctx.stream_ptr, device=dev)
     # per-push device views (offsets rebased to the push)
     pushes = []
+    rec_len = n_bases // n_reads      # fixed-length records in every workload (150 bp reads / 5 Mbp genomes)
     for r0 in range(0, n_reads, reads_per_push):
         r1 = min(n_reads, r0 + reads_per_push)
-        off = (d_off[r0:r1 + 1] - r0 * READ_LEN).contiguous() if r0 else d_off[:r1 + 1]
-        pushes.append((d_data.data_ptr() + r0 * READ_LEN, off, r1 - r0, (r1 - r0) * READ_LEN))
+        off = (d_off[r0:r1 + 1] - r0 * rec_len).contiguous() if r0 else d_off[:r1 + 1]
+        pushes.append((d_data.data_ptr() + r0 * rec_len, off, r1 - r0, (r1 - r0) * rec_len,
+                       (d_col.data_ptr() + 4 * r0) if d_col is not None else None))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
     torch.cuda.synchronize()
     owner = gdist.OwnerMap(b1, b2, world)
@@ -367,8 +397,8 @@ def run_ours(args):
 
     def step_device():
         ctx.reset()
-        for ptr, off, nr, nbytes in pushes:
-            ctx.push_reads_device(ptr, off.data_ptr(), nr, nbytes)
+        for ptr, off, nr, nbytes, colp in pushes:
+            ctx.push_reads_device(ptr, off.data_ptr(), nr, nbytes, colp)
         last_stats[0] = ctx.finish_bucketing()   # this rank's own super-k-mers (before the exchange adds imported chunks)
         if world > 1:
             do_exchange()
@@ -376,7 +406,8 @@ def run_ours(args):
 
     def step_host():
         ctx.reset()
-        ctx.push_reads_ptr(h_data.data_ptr(), h_off.data_ptr(), n_reads)   # the library splits it into double-buffered H2D batches
+        # the library splits the push into double-buffered H2D batches
+        ctx.push_reads_ptr(h_data.data_ptr(), h_off.data_ptr(), n_reads, h_col.data_ptr() if h_col is not None else None)
         ctx.finish_bucketing()
         if world > 1:
             do_exchange()
@@ -460,7 +491,8 @@ def run_ours(args):
             tab = step_host()
             torch.cuda.synchronize()
             e2e_times.append(time.perf_counter() - t0)
-            d2h = int(tab.keys_lo.nbytes + tab.count_flags.nbytes + tab.unit_offsets.nbytes)
+            d2h = int(sum(a.nbytes for a in (tab.keys_lo, tab.keys_hi, tab.count_flags, tab.unit_offsets, tab.src_kmers,
+                                             tab.color_offsets, tab.colors) if a is not None))
             tab.release()
         e2e_ms = float(np.mean(e2e_times)) * 1e3
         t = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
@@ -468,7 +500,8 @@ def run_ours(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t.item())
         e2e = {"value": (n_bases * world) / (e2e_ms * 1e-3) / 1e9, "unit": "Gbases/s",
-               "h2d_bytes_per_step": int(h_data.numel() + h_off.numel() * 8), "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms}
+               "h2d_bytes_per_step": int(h_data.numel() + h_off.numel() * 8 + (h_col.numel() * 4 if h_col is not None else 0)),
+               "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms}
 
     # ---- roofline: measured DRAM traffic and the bytes each family has to move, against the measured HBM peak
     peak, peak_kind = measured_peak()
@@ -488,7 +521,10 @@ def run_ours(args):
         "k_scatter": st.n_superkmers * 16 + n_bases // 4 + B_s,
         "k_merge_hash<smem>": B_s + n_entries * 12,
         "k_gather_units": 2 * n_entries * 12,
-        "k_partition_units": B_s + N_k * 8, "k_merge_hash<partitions>": N_k * 8 + n_entries * 12,
+        "k_merge_hash128": B_s + N_k * 0 + n_entries * (36 if wl == "c5" else 20),
+        "k_sort_units128": 2 * n_entries * (36 if wl == "c5" else 20),
+        # k_partition_units / k_merge_hash<partitions> see only the records of the units above the shared-table tiers (a few
+        # units at C2 sizes): no byte model without that count, they are reported by time only
     }
     traffic, traffic_src = ({}, "skipped")
     if rank == 0 and world == 1 and wl == "c2" and not args.no_traffic_pass:
@@ -521,7 +557,7 @@ def run_ours(args):
             limiter = None
     # the DRAM-LSD pipeline moves ~195 B/base at k=31 (W+P = 12, R = 8); its HBM-bound time is what this
     # figure compares the measured step with (> 1 = faster than that pipeline could run at HBM peak, NOT a bandwidth)
-    survey_bytes = 4.1 * n_bases + B_s + N_k * 12 * (1 + 2 * 8 + 1) + n_entries * 12
+    survey_bytes = 4.1 * n_bases + B_s + N_k * cfg["wp"] * (1 + 2 * cfg["R"] + 1) + n_entries * cfg["wp"]
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": (traffic.get(dom) / launches_per_step) if dom in traffic else None,
                 "traffic_source": traffic_src, "peak_kind": peak_kind,
@@ -534,7 +570,7 @@ def run_ours(args):
                          "traffic_frac": (step_traffic / (ms_per_step * 1e-3) / 1e9 / peak) if step_traffic else None},
                 "per_kernel": per_kernel,
                 "survey_model_equiv_frac": survey_bytes / (ms_per_step * 1e-3) / 1e9 / peak,
-                "survey_model": "SURVEY 8(d) DRAM-LSD pipeline bytes (W+P=12, R=8) / measured step time / peak; not a bandwidth"}
+                "survey_model": f"SURVEY 8(d) DRAM-LSD pipeline bytes (W+P={cfg['wp']}, R={cfg['R']}) / measured step time / peak; not a bandwidth"}
 
     # ---- N > 1: parity of sampled owned units (device path and host path) against the oracle on the union of all reads
     parity = None
@@ -544,7 +580,7 @@ def run_ours(args):
     line = {
         "metric": "build Gbases/s (bucketing+k-mer merge)", "value": value, "unit": "Gbases/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "scaling": "weak", "vs_baseline": None, "dtype": "u64" if cfg["wp"] == 12 else "u128", "data": "synthetic",
         "config": {"workload": workload_string(wl, n_reads, world, b1, b2),
                    "l2": "flushed (256 MB write) between timed steps", "reads_per_gpu": n_reads,
                    "parallelism": f"bucket-owner x{world}" if world > 1 else "single GPU",
@@ -590,7 +626,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--reads-per-gpu", type=int, default=0, help="default: 1 M (c2) / 20 M (c4)")
-    ap.add_argument("--workload", default="c2", choices=["c2", "c4"],
+    ap.add_argument("--workload", default="c2", choices=["c2", "c4", "c5", "c3"],
                     help="c2 = BASELINE configs[1] (the bench line); c4 = a slice of configs[3] (human-scale shape, big merge units)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer pass (large c4 slices)")
     ap.add_argument("--reads-per-push", type=int, default=4_000_000, help="c4: reads per device push (one bucket chunk each)")

@@ -37,6 +37,7 @@ class TableC(C.Structure):
         ("count_flags", C.POINTER(C.c_uint32)), ("first_unit", C.c_uint32), ("n_units", C.c_uint32),
         ("unit_offsets", C.POINTER(C.c_uint64)), ("color_offsets", C.POINTER(C.c_uint64)),
         ("colors", C.POINTER(C.c_uint32)), ("total_kmers", C.c_uint64), ("unique_kmers", C.c_uint64),
+        ("src_kmers", C.POINTER(C.c_uint64)), ("src_kmer_words", C.c_uint32), ("reserved0", C.c_uint32),
         ("opaque", C.c_void_p),
     ]
 

@@ -81,7 +81,7 @@ class KmerTable:
     library-owned pinned buffers, so the object stays valid after release."""
 
     def __init__(self, keys_lo, keys_hi, count_flags, first_unit, unit_offsets, total_kmers, unique_kmers,
-                 color_offsets=None, colors=None):
+                 color_offsets=None, colors=None, src_kmers=None):
         self.keys_lo = keys_lo
         self.keys_hi = keys_hi
         self.count_flags = count_flags
@@ -91,6 +91,9 @@ class KmerTable:
         self.unique_kmers = unique_kmers
         self.color_offsets = color_offsets
         self.colors = colors
+        # rabin-karp128 only: (n_entries, words) uint64, the bases of one occurrence of every key (base j at bits 2(j % 32) of
+        # word j // 32), oriented so that their forward hash is the key -- the reference's saved_reads contract
+        self.src_kmers = src_kmers
         self._release = None
 
     def release(self):
@@ -98,7 +101,7 @@ class KmerTable:
         if self._release is not None:
             self._release()
             self._release = None
-            self.keys_lo = self.keys_hi = self.count_flags = self.unit_offsets = None
+            self.keys_lo = self.keys_hi = self.count_flags = self.unit_offsets = self.src_kmers = None
 
     @property
     def n_entries(self) -> int:
@@ -111,6 +114,11 @@ class KmerTable:
     @property
     def flags(self) -> np.ndarray:
         return (self.count_flags >> np.uint32(30)).astype(np.uint8)
+
+    def src_kmer(self, entry: int, k: int) -> bytes:
+        """ASCII bases of entry's source k-mer (non-invertible keys)."""
+        w = self.src_kmers[entry]
+        return bytes(b"ACTG"[(int(w[j >> 5]) >> (2 * (j & 31))) & 3] for j in range(k))
 
     def colors_of(self, entry: int) -> np.ndarray:
         """Sorted-unique colour ids of one entry (coloured builds)."""
@@ -263,7 +271,11 @@ class GGCATB200:
             if t.color_offsets:
                 co = arr(t.color_offsets, ne + 1, np.uint64)
                 cl = arr(t.colors, int(co[-1]), np.uint32)
-            tab = KmerTable(keys, hi, cf, int(t.first_unit), uo, int(t.total_kmers), int(t.unique_kmers), co, cl)
+            src = None
+            if t.src_kmers:
+                sw = int(t.src_kmer_words)
+                src = arr(t.src_kmers, ne * sw, np.uint64).reshape(ne, sw)
+            tab = KmerTable(keys, hi, cf, int(t.first_unit), uo, int(t.total_kmers), int(t.unique_kmers), co, cl, src)
         except Exception:
             self._lib.ggcat_b200_release_table(self._h, C.byref(t))
             raise
@@ -307,23 +319,28 @@ class GGCATB200:
         nu = int(t.n_units)
         uo = self._dev_bytes(ptr(t.unit_offsets), (nu + 1) * 8).view(np.uint64)
         wide = bool(t.keys_hi)
+        sw = int(t.src_kmer_words) if t.src_kmers else 0
         if units is None:
             ne = int(t.n_entries)
             keys = self._dev_bytes(ptr(t.keys_lo), ne * 8).view(np.uint64)
             hi = self._dev_bytes(ptr(t.keys_hi), ne * 8).view(np.uint64) if wide else None
             cf = self._dev_bytes(ptr(t.count_flags), ne * 4).view(np.uint32)
-            return KmerTable(keys, hi, cf, int(t.first_unit), uo, int(t.total_kmers), int(t.unique_kmers))
-        ks, hs, cs, offs = [], [], [], [0]
+            src = self._dev_bytes(ptr(t.src_kmers), ne * sw * 8).view(np.uint64).reshape(ne, sw) if sw else None
+            return KmerTable(keys, hi, cf, int(t.first_unit), uo, int(t.total_kmers), int(t.unique_kmers), src_kmers=src)
+        ks, hs, cs, ss, offs = [], [], [], [], [0]
         for u in units:
             a, b = int(uo[u - int(t.first_unit)]), int(uo[u - int(t.first_unit) + 1])
             ks.append(self._dev_bytes(ptr(t.keys_lo) + a * 8, (b - a) * 8).view(np.uint64))
             if wide:
                 hs.append(self._dev_bytes(ptr(t.keys_hi) + a * 8, (b - a) * 8).view(np.uint64))
             cs.append(self._dev_bytes(ptr(t.count_flags) + a * 4, (b - a) * 4).view(np.uint32))
+            if sw:
+                ss.append(self._dev_bytes(ptr(t.src_kmers) + a * sw * 8, (b - a) * sw * 8).view(np.uint64).reshape(b - a, sw))
             offs.append(offs[-1] + (b - a))
         cat = lambda xs, dt: np.concatenate(xs) if xs else np.zeros(0, dt)
         tab = KmerTable(cat(ks, np.uint64), cat(hs, np.uint64) if wide else None, cat(cs, np.uint32), 0,
-                        np.array(offs, np.uint64), int(t.total_kmers), int(t.unique_kmers))
+                        np.array(offs, np.uint64), int(t.total_kmers), int(t.unique_kmers),
+                        src_kmers=(np.concatenate(ss) if ss else np.zeros((0, sw), np.uint64)) if sw else None)
         tab.n_entries_total = int(t.n_entries)
         return tab
 

@@ -104,17 +104,19 @@ struct TimedLaunch { int fam; cudaEvent_t a, b; };
 struct HostTable {
     uint64_t *keys = nullptr, *keys_hi = nullptr; uint32_t *cf = nullptr; uint64_t *unit_offsets = nullptr;
     uint64_t *color_offsets = nullptr; uint32_t *colors = nullptr;
+    uint64_t *src = nullptr;   // rk128: 2 words of source bases per entry
     size_t cap_entries = 0, cap_units = 0, cap_colors = 0, cap_coloff = 0;
-    bool wide = false, colored = false;
+    bool wide = false, colored = false, with_src = false;
     void release() {
         cudaFreeHost(keys); cudaFreeHost(keys_hi); cudaFreeHost(cf); cudaFreeHost(unit_offsets); cudaFreeHost(color_offsets);
-        cudaFreeHost(colors);
+        cudaFreeHost(colors); cudaFreeHost(src);
     }
 };
 
 // where the finished table of the last merge lives on the device
 struct FinalTable {
     const uint64_t *keys_lo = nullptr, *keys_hi = nullptr; const uint32_t *cf = nullptr;
+    const uint64_t *src = nullptr;           // rk128: source bases, 2 words per entry
     const uint64_t *unit_off = nullptr;      // n_units + 1
     const uint64_t *color_off = nullptr;     // n_entries (+1 implied = n_colors)
     const uint32_t *colors = nullptr;
@@ -191,6 +193,7 @@ struct ggcat_b200_ctx {
     DevBuf d_static_off;                   // wide path: static output regions of partitioned units
     DevBuf d_rkpos;                        // rabin-karp per-position tables
     DevBuf d_recfl;                        // flag bits of the wide path's partition records
+    DevBuf d_recsrc, out_src, out_src2, sort_idx;   // rk128: source locators of partition records, source bases (unsorted / final), sort index ping-pong
     DevBuf d_mstage;                       // merge uploads (views, work lists, unit_n, static_off) in one copy
     uint8_t *h_mstage = nullptr; size_t h_mstage_cap = 0;
     DevBuf d_views, d_work[3], d_scratch, out_keys, out_cf, out_keys2, out_cf2, cursor, unit_out_off,
@@ -636,7 +639,8 @@ int32_t pinned_reserve(uint8_t **p, size_t *cap, size_t need) {
 // The final table is sized by the survivors actually seen, not by the k-mer occurrences (which are 10-25x more at
 // 30x coverage): it starts from an estimate and grows (keeping the first `keep` entries) when a part does not fit.
 int32_t final_reserve(ggcat_b200_ctx *c, uint64_t need, uint64_t keep, bool wide) {
-    if (need <= c->fin_cap && c->out_keys2.p && c->out_cf2.p && (!wide || c->out_hi2.p)) return 0;
+    const bool with_src = c->wide_mode == MODE_RK128;
+    if (need <= c->fin_cap && c->out_keys2.p && c->out_cf2.p && (!wide || c->out_hi2.p) && (!with_src || c->out_src2.p)) return 0;
     CU(cudaStreamSynchronize(c->stream));
     if (c->copy_stream) CU(cudaStreamSynchronize(c->copy_stream));   // copies of earlier parts read the old buffers
     auto grow = [&](DevBuf &b, size_t elem) -> cudaError_t {
@@ -651,6 +655,7 @@ int32_t final_reserve(ggcat_b200_ctx *c, uint64_t need, uint64_t keep, bool wide
     CU(grow(c->out_keys2, 8));
     CU(grow(c->out_cf2, 4));
     if (wide) CU(grow(c->out_hi2, 8));
+    if (with_src) CU(grow(c->out_src2, 16));
     c->fin_cap = need;
     return 0;
 }
@@ -985,7 +990,7 @@ int32_t launch_hash128(ggcat_b200_ctx *c, const ChunkView *dv, uint32_t nch, std
     if (!work[0].empty()) {
         LaunchTimer t(c, F_MERGE_HASH128);
         auto kern = k_merge_hash128<W_THREADS_S, W_TS_S, MODE>;
-        const size_t smem = merge_hash128_smem_bytes<W_THREADS_S, W_TS_S>();
+        const size_t smem = merge_hash128_smem_bytes<W_THREADS_S, W_TS_S, MODE>();
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const unsigned grid = (unsigned)std::min<size_t>(work[0].size(), (size_t)c->sm_count * 2 * 8);
         kern<<<grid, W_THREADS_S, smem, st>>>(dv, nch, c->d_work[0].as<uint32_t>(), (uint32_t)work[0].size(), u0, P, c->rk,
@@ -994,7 +999,7 @@ int32_t launch_hash128(ggcat_b200_ctx *c, const ChunkView *dv, uint32_t nch, std
     if (!work[1].empty()) {
         LaunchTimer t(c, F_MERGE_HASH128);
         auto kern = k_merge_hash128<W_THREADS_L, W_TS_L, MODE>;
-        const size_t smem = merge_hash128_smem_bytes<W_THREADS_L, W_TS_L>();
+        const size_t smem = merge_hash128_smem_bytes<W_THREADS_L, W_TS_L, MODE>();
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const unsigned grid = (unsigned)std::min<size_t>(work[1].size(), (size_t)c->sm_count * 8);
         kern<<<grid, W_THREADS_L, smem, st>>>(dv, nch, c->d_work[1].as<uint32_t>(), (uint32_t)work[1].size(), u0, P, c->rk,
@@ -1008,13 +1013,13 @@ int32_t launch_hash128(ggcat_b200_ctx *c, const ChunkView *dv, uint32_t nch, std
         const size_t first = tr == 0 ? 0 : n_giant, count = tr == 0 ? n_giant : large.size() - n_giant;
         if (!count) continue;
         const uint64_t nmax = large[first].first;
-        uint64_t per_cta = ((uint64_t)hash_table_slots_pow2((uint32_t)nmax) * 20 + 15) / 16 * 2 + 2;  // u64 words, 16-byte multiple
+        uint64_t per_cta = ((uint64_t)hash_table_slots_pow2((uint32_t)nmax) * slot_bytes128<MODE>() + 15) / 16 * 2 + 2;  // u64 words, 16-byte multiple
         const uint64_t budget = 12ull << 30;
         const uint64_t g = std::min<uint64_t>(std::min<uint64_t>(count, (uint64_t)c->sm_count * 2), std::max<uint64_t>(1, budget / (per_cta * 8)));
         CU(c->d_scratch.reserve(per_cta * g * 8));
         LaunchTimer t(c, F_MERGE_HASH128);
         auto kern = k_merge_hash128<W_THREADS_L, 0, MODE>;
-        kern<<<(unsigned)g, W_THREADS_L, merge_hash128_smem_bytes<W_THREADS_L, 0>(), st>>>(
+        kern<<<(unsigned)g, W_THREADS_L, merge_hash128_smem_bytes<W_THREADS_L, 0, MODE>(), st>>>(
             dv, nch, c->d_work[2].as<uint32_t>() + first, (uint32_t)count, u0, P, c->rk, c->params.min_multiplicity, out,
             c->d_scratch.as<uint64_t>(), per_cta, PartSrc128(), nullptr);
     }
@@ -1055,6 +1060,7 @@ int32_t launch_partitions128(ggcat_b200_ctx *c, const ChunkView *dv, uint32_t nc
     const size_t nrec = (size_t)bp.n_parts * W_PART_CAP;
     CU(c->d_recs.reserve(nrec * 16));
     CU(c->d_recfl.reserve(nrec));
+    if (MODE == MODE_RK128) CU(c->d_recsrc.reserve(nrec * 8));
     CU(c->d_retry.reserve((nbig + 2) * 4));
     uint32_t *retry_cnt = c->d_retry.as<uint32_t>(), *retry = retry_cnt + 1;
     CU(cudaMemsetAsync(retry_cnt, 0, 4, st));
@@ -1063,28 +1069,30 @@ int32_t launch_partitions128(ggcat_b200_ctx *c, const ChunkView *dv, uint32_t nc
         LaunchTimer t(c, F_PARTITION);
         const unsigned grid = (unsigned)std::min<size_t>(nbig, (size_t)c->sm_count * 2);
         k_partition_units128<1024, MODE><<<grid, 1024, 0, st>>>(dv, nch, d_unit, d_logp, d_pbase, (uint32_t)nbig, P, c->rk, rec_lo, rec_hi,
-                                                                c->d_recfl.as<uint8_t>(), d_pcount, W_PART_CAP, d_ovf, retry, retry_cnt);
+                                                                c->d_recfl.as<uint8_t>(), MODE == MODE_RK128 ? c->d_recsrc.as<uint64_t>() : nullptr,
+                                                                d_pcount, W_PART_CAP, d_ovf, retry, retry_cnt);
     }
     {
         LaunchTimer t(c, F_MERGE_HASH_PART);
         PartSrc128 ps;
         ps.rec_lo = rec_lo; ps.rec_hi = rec_hi; ps.rec_fl = c->d_recfl.as<uint8_t>(); ps.pcount = d_pcount; ps.part_big = d_part_big;
+        ps.rec_src = MODE == MODE_RK128 ? c->d_recsrc.as<uint64_t>() : nullptr;
         ps.big_unit = d_unit; ps.big_ovf = d_ovf; ps.big_off = c->d_static_off.as<uint64_t>(); ps.big_fill = d_fill;
         ps.pcap = W_PART_CAP; ps.pad = 0;
         auto kern = k_merge_hash128<W_THREADS_S, W_TS_S, MODE, SRC_RECORDS>;
-        const size_t smem = merge_hash128_smem_bytes<W_THREADS_S, W_TS_S>();
+        const size_t smem = merge_hash128_smem_bytes<W_THREADS_S, W_TS_S, MODE>();
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const unsigned grid = (unsigned)std::min<size_t>(bp.n_parts, (size_t)c->sm_count * 2 * 8);
         kern<<<grid, W_THREADS_S, smem, st>>>(dv, nch, nullptr, bp.n_parts, u0, P, c->rk, c->params.min_multiplicity, out, nullptr, 0, ps, nullptr);
     }
     {   // units with an overflowed partition: global-table kernel over the device-side retry list
-        uint64_t per_cta = ((uint64_t)hash_table_slots_pow2((uint32_t)bp.nmax) * 20 + 15) / 16 * 2 + 2;
+        uint64_t per_cta = ((uint64_t)hash_table_slots_pow2((uint32_t)bp.nmax) * slot_bytes128<MODE>() + 15) / 16 * 2 + 2;
         const uint64_t budget = 12ull << 30;
         const uint64_t g = std::min<uint64_t>(std::min<uint64_t>(nbig, (uint64_t)c->sm_count * 2), std::max<uint64_t>(1, budget / (per_cta * 8)));
         CU(c->d_scratch.reserve(per_cta * g * 8));
         LaunchTimer t(c, F_MERGE_HASH128);
         auto kern = k_merge_hash128<W_THREADS_L, 0, MODE>;
-        kern<<<(unsigned)g, W_THREADS_L, merge_hash128_smem_bytes<W_THREADS_L, 0>(), st>>>(
+        kern<<<(unsigned)g, W_THREADS_L, merge_hash128_smem_bytes<W_THREADS_L, 0, MODE>(), st>>>(
             dv, nch, retry, (uint32_t)nbig, u0, P, c->rk, c->params.min_multiplicity, out, c->d_scratch.as<uint64_t>(), per_cta,
             PartSrc128(), retry_cnt);
     }
@@ -1149,6 +1157,8 @@ int32_t merge_range_device_wide(ggcat_b200_ctx *c, uint32_t first_bucket, uint32
     }
     const uint64_t cap_all = cap + big_records;
     CU(c->out_keys.reserve(cap_all * 8)); CU(c->out_hi.reserve(cap_all * 8)); CU(c->out_cf.reserve(cap_all * 4));
+    const bool with_src = c->wide_mode == MODE_RK128;
+    if (with_src) { CU(c->out_src.reserve(cap_all * 16)); CU(c->sort_idx.reserve(cap_all * 8)); }
     const uint64_t rec_total = std::max(cap, pb.cap_total);
     if (pb.ub == 0) {
         // coloured builds fold in one piece and need every (k-mer, colour) entry; the others grow with the survivors
@@ -1165,6 +1175,7 @@ int32_t merge_range_device_wide(ggcat_b200_ctx *c, uint32_t first_bucket, uint32
     out.keys_lo = c->out_keys.as<uint64_t>(); out.keys_hi = c->out_hi.as<uint64_t>(); out.count_flags = c->out_cf.as<uint32_t>();
     out.cursor = c->cursor.as<unsigned long long>(); out.unit_out_off = c->unit_out_off.as<uint64_t>();
     out.unit_out_cnt = c->unit_out_cnt.as<uint32_t>(); out.capacity = cap; out.overflow = c->overflow.as<uint32_t>();
+    out.src = with_src ? c->out_src.as<uint64_t>() : nullptr;
     const ChunkView *dv = c->d_views.as<ChunkView>();
     const uint32_t nch = (uint32_t)views.size();
     if (c->wide_mode == MODE_SEQ128) { TRY(launch_hash128<MODE_SEQ128>(c, dv, nch, work, u0, out, large)); TRY(launch_partitions128<MODE_SEQ128>(c, dv, nch, u0, out, bp)); }
@@ -1178,13 +1189,15 @@ int32_t merge_range_device_wide(ggcat_b200_ctx *c, uint32_t first_bucket, uint32
         {
             LaunchTimer t(c, F_SORT128, 2);
             k_scan_counts_u64<<<1, 1024, 0, st>>>(c->unit_out_cnt.as<uint32_t>(), c->unit_final_off.as<uint64_t>() + pb.ub, nu, pb.eb);
-            auto kern = k_sort_units128<W_SORT_THREADS, W_SORT_CAP>;
+            auto kern = with_src ? k_sort_units128<W_SORT_THREADS, W_SORT_CAP, true> : k_sort_units128<W_SORT_THREADS, W_SORT_CAP, false>;
             const size_t smem = sort_units128_smem_bytes<W_SORT_THREADS, W_SORT_CAP>();
             CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             kern<<<(unsigned)std::min<uint32_t>(nu, (uint32_t)c->sm_count * 2 * 8), W_SORT_THREADS, smem, st>>>(
                 c->out_keys.as<uint64_t>(), c->out_hi.as<uint64_t>(), c->out_cf.as<uint32_t>(), c->unit_out_off.as<uint64_t>(),
                 c->unit_out_cnt.as<uint32_t>(), c->unit_final_off.as<uint64_t>() + pb.ub, c->out_keys2.as<uint64_t>(),
-                c->out_hi2.as<uint64_t>(), c->out_cf2.as<uint32_t>(), nu, 0u, end_bit, c->fin_cap, c->overflow.as<uint32_t>());
+                c->out_hi2.as<uint64_t>(), c->out_cf2.as<uint32_t>(), nu, 0u, end_bit, c->fin_cap, c->overflow.as<uint32_t>(),
+                with_src ? c->out_src.as<uint64_t>() : nullptr, with_src ? c->out_src2.as<uint64_t>() : nullptr,
+                with_src ? c->sort_idx.as<uint32_t>() : nullptr, with_src ? c->sort_idx.as<uint32_t>() + cap_all : nullptr);
         }
         CU(cudaGetLastError());
         if (c->wide_mode == MODE_COLOR || attempt > 0) break;   // sized for every record / already regrown
@@ -1224,6 +1237,7 @@ int32_t merge_range_device_wide(ggcat_b200_ctx *c, uint32_t first_bucket, uint32
     } else {
         c->fin.keys_lo = c->out_keys2.as<uint64_t>(); c->fin.keys_hi = c->out_hi2.as<uint64_t>(); c->fin.cf = c->out_cf2.as<uint32_t>();
         c->fin.unit_off = c->unit_final_off.as<uint64_t>();
+        c->fin.src = with_src ? c->out_src2.as<uint64_t>() : nullptr;
     }
     CU(cudaMemcpyAsync(c->h_pinned, c->cursor.p, 32, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(c->h_pinned + 8, c->overflow.p, 4, cudaMemcpyDeviceToHost, st));
@@ -1397,7 +1411,7 @@ void ggcat_b200_destroy(ggcat_b200_ctx *c) {
                       &c->d_partmeta, &c->d_recs, &c->fin_tmp_keys, &c->fin_tmp_cf, &c->tok_agg, &c->tok_keep, &c->tok_base, &c->tok_marks,
                       &c->tok_tmarks, &c->tok_seq, &c->tok_offsets, &c->tok_text, &c->tok_colors, &c->ut_links, &c->ut_visited, &c->ut_recs,
                       &c->ut_bases, &c->ut_counters, &c->mu_recs, &c->mu_bases, &c->mu_ht, &c->mu_first, &c->mu_partner, &c->mu_visited,
-                      &c->out_hi, &c->out_hi2, &c->unit_keys, &c->unit_cols, &c->col_off, &c->out_coloff, &c->out_colors})
+                      &c->out_hi, &c->out_hi2, &c->d_recsrc, &c->out_src, &c->out_src2, &c->sort_idx, &c->unit_keys, &c->unit_cols, &c->col_off, &c->out_coloff, &c->out_colors})
         b->release();
     for (cudaEvent_t e : c->event_pool) cudaEventDestroy(e);
     for (HostTable *t : c->free_tables) { t->release(); delete t; }
@@ -1988,6 +2002,7 @@ int32_t ggcat_b200_device_table(ggcat_b200_ctx *c, ggcat_b200_table *out) {
     const FinalTable &f = c->fin;
     if (!f.unit_off || f.n_units == 0) return set_err(GGCAT_B200_ERR_STATE, "device_table before merge_bucket_range_device");
     out->n_entries = f.n_entries; out->keys_lo = f.keys_lo; out->keys_hi = f.keys_hi; out->count_flags = f.cf;
+    out->src_kmers = f.src; out->src_kmer_words = f.src ? 2 : 0;
     out->first_unit = f.first_unit; out->n_units = f.n_units; out->unit_offsets = f.unit_off;
     out->color_offsets = f.color_off; out->colors = f.colors;   // color_offsets has n_entries entries on the device (the end is n_colors)
     out->total_kmers = f.total_kmers; out->unique_kmers = f.unique_kmers;
@@ -1999,16 +2014,18 @@ static int32_t host_table_reserve(ggcat_b200_ctx *c, HostTable *t, uint64_t need
     if (need_entries <= t->cap_entries) return 0;
     CU(cudaStreamSynchronize(c->copy_stream));
     const uint64_t cap = std::max<uint64_t>(need_entries + need_entries / 2, 1024);
-    uint64_t *nk = nullptr, *nh = nullptr; uint32_t *nc = nullptr;
+    uint64_t *nk = nullptr, *nh = nullptr, *ns = nullptr; uint32_t *nc = nullptr;
     bool ok = cudaMallocHost((void **)&nk, cap * 8) == cudaSuccess && cudaMallocHost((void **)&nc, cap * 4) == cudaSuccess;
     if (ok && wide) ok = cudaMallocHost((void **)&nh, cap * 8) == cudaSuccess;
-    if (!ok) { cudaFreeHost(nk); cudaFreeHost(nc); cudaFreeHost(nh); return set_err(GGCAT_B200_ERR_CUDA, "pinned table allocation failed"); }
+    if (ok && t->with_src) ok = cudaMallocHost((void **)&ns, cap * 16) == cudaSuccess;
+    if (!ok) { cudaFreeHost(nk); cudaFreeHost(nc); cudaFreeHost(nh); cudaFreeHost(ns); return set_err(GGCAT_B200_ERR_CUDA, "pinned table allocation failed"); }
     if (copied) {
         memcpy(nk, t->keys, copied * 8); memcpy(nc, t->cf, copied * 4);
         if (wide) memcpy(nh, t->keys_hi, copied * 8);
+        if (t->with_src) memcpy(ns, t->src, copied * 16);
     }
-    cudaFreeHost(t->keys); cudaFreeHost(t->cf); cudaFreeHost(t->keys_hi);
-    t->keys = nk; t->cf = nc; t->keys_hi = nh; t->cap_entries = cap;
+    cudaFreeHost(t->keys); cudaFreeHost(t->cf); cudaFreeHost(t->keys_hi); cudaFreeHost(t->src);
+    t->keys = nk; t->cf = nc; t->keys_hi = nh; t->src = ns; t->cap_entries = cap;
     return 0;
 }
 
@@ -2023,7 +2040,7 @@ int32_t ggcat_b200_merge_bucket_range(ggcat_b200_ctx *c, uint32_t first_bucket, 
     if (n_buckets == 0 || first_bucket >= nb_total || first_bucket + n_buckets > nb_total)
         return set_err(GGCAT_B200_ERR_INVALID, "bucket range [%u,+%u) outside 0..%u", first_bucket, n_buckets, nb_total);
     const uint32_t nu = n_buckets << P.b2;
-    const bool colored = c->wide_mode == MODE_COLOR, wide = c->wide_mode >= 0;
+    const bool colored = c->wide_mode == MODE_COLOR, wide = c->wide_mode >= 0, with_src = c->wide_mode == MODE_RK128;
     // split the range into parts of ~part_kmers records (whole buckets); coloured builds fold in one piece
     std::vector<uint64_t> bk(n_buckets, 0);
     uint64_t tot = 0;
@@ -2053,11 +2070,11 @@ int32_t ggcat_b200_merge_bucket_range(ggcat_b200_ctx *c, uint32_t first_bucket, 
     HostTable *t = nullptr;
     for (size_t i = 0; i < c->free_tables.size(); i++) {
         HostTable *q = c->free_tables[i];
-        if (q->cap_units >= nu + 1 && q->wide == wide && q->colored == colored) { t = q; c->free_tables.erase(c->free_tables.begin() + i); break; }
+        if (q->cap_units >= nu + 1 && q->wide == wide && q->colored == colored && q->with_src == with_src) { t = q; c->free_tables.erase(c->free_tables.begin() + i); break; }
     }
     if (!t) {
         t = new HostTable();
-        t->cap_units = nu + 1; t->wide = wide; t->colored = colored;
+        t->cap_units = nu + 1; t->wide = wide; t->colored = colored; t->with_src = with_src;
         if (cudaMallocHost((void **)&t->unit_offsets, t->cap_units * 8) != cudaSuccess) { delete t; return set_err(GGCAT_B200_ERR_CUDA, "pinned table allocation failed"); }
     }
     auto fail = [&](int32_t rc) { c->free_tables.push_back(t); return rc; };
@@ -2077,6 +2094,7 @@ int32_t ggcat_b200_merge_bucket_range(ggcat_b200_ctx *c, uint32_t first_bucket, 
                 cudaError_t e1 = cudaMemcpyAsync(t->keys + eb, f.keys_lo + eb, ne * 8, cudaMemcpyDeviceToHost, c->copy_stream);
                 if (e1 == cudaSuccess) e1 = cudaMemcpyAsync(t->cf + eb, f.cf + eb, ne * 4, cudaMemcpyDeviceToHost, c->copy_stream);
                 if (e1 == cudaSuccess && wide) e1 = cudaMemcpyAsync(t->keys_hi + eb, f.keys_hi + eb, ne * 8, cudaMemcpyDeviceToHost, c->copy_stream);
+                if (e1 == cudaSuccess && with_src) e1 = cudaMemcpyAsync(t->src + 2 * eb, f.src + 2 * eb, ne * 16, cudaMemcpyDeviceToHost, c->copy_stream);
                 if (e1 != cudaSuccess) return fail(set_err(GGCAT_B200_ERR_CUDA, "table copy failed: %s", cudaGetErrorString(e1)));
             }
             eb += ne;
@@ -2112,6 +2130,7 @@ int32_t ggcat_b200_merge_bucket_range(ggcat_b200_ctx *c, uint32_t first_bucket, 
     CU(cudaStreamSynchronize(c->copy_stream));
     if (colored) t->color_offsets[ne] = ncol;
     out->n_entries = ne; out->keys_lo = t->keys; out->keys_hi = wide ? t->keys_hi : nullptr; out->count_flags = t->cf;
+    out->src_kmers = with_src ? t->src : nullptr; out->src_kmer_words = with_src ? 2 : 0;
     out->first_unit = first_bucket << P.b2; out->n_units = nu; out->unit_offsets = t->unit_offsets;
     out->color_offsets = colored ? t->color_offsets : nullptr; out->colors = colored ? t->colors : nullptr;
     out->total_kmers = tk; out->unique_kmers = uq; out->opaque = t;

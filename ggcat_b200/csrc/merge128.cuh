@@ -54,6 +54,8 @@ struct MergeOut128 {
     uint32_t *unit_out_cnt;
     uint64_t capacity;            // dynamic region [0, capacity); the static regions of partitioned units follow it
     uint32_t *overflow;
+    uint64_t *src;                // MODE_RK128: packed bases of one occurrence of every surviving key, 2 words per entry
+                                  // (the hash is not invertible: the reference keeps `saved_reads` for this, hashmap.rs:32-33,96-149)
 };
 
 // Key partitions of big units (same scheme as merge.cuh, 128-bit keys): k_partition_units128 expands a unit once and
@@ -62,6 +64,7 @@ struct MergeOut128 {
 struct PartSrc128 {
     const uint64_t *rec_lo, *rec_hi;   // [n_parts_total][pcap]
     const uint8_t *rec_fl;             // flag bits of the record
+    const uint64_t *rec_src;           // MODE_RK128: source locator of the record (src_locator)
     const uint32_t *pcount;            // [n_parts_total]
     const uint32_t *part_big;          // work item -> index of its big unit
     const uint32_t *big_unit;          // [n_big] unit id
@@ -83,22 +86,34 @@ __device__ __forceinline__ uint32_t mix128(unsigned long long lo, unsigned long 
 // The all-ones key doubles as the empty-slot sentinel, but it IS a legal key when the key uses all 128 bits (forward-only
 // seq-hash of k = 64: poly-G; colours with k = 48; any rk128 hash): such occurrences are counted in `special`, a
 // MapEntry word beside the table that the scan treats as one more slot.
-__device__ __forceinline__ void hash_insert128(K128 *K, uint32_t *C, uint32_t mask, u128 key, uint32_t fb, uint32_t *special) {
+// Returns the slot (SLOT_SPECIAL for the all-ones key); *claimed = this call created the entry (it then records where
+// the k-mer's bases can be found when the hash is not invertible).
+constexpr uint32_t SLOT_SPECIAL = 0xFFFFFFFFu;
+__device__ __forceinline__ uint32_t hash_insert128(K128 *K, uint32_t *C, uint32_t mask, u128 key, uint32_t fb, uint32_t *special,
+                                                   bool *claimed) {
     const K128 want = to_k128(key);
     const K128 empty = K128{EMPTY64, EMPTY64};
     if (want.lo == EMPTY64 && want.hi == EMPTY64) {
-        atomicAdd(special, 1u);
+        *claimed = (atomicAdd(special, 1u) & 0x3FFFFFFFu) == 0u;
         if (fb) atomicOr(special, fb << 30);
-        return;
+        return SLOT_SPECIAL;
     }
     uint32_t slot = mix128(want.lo, want.hi) & mask;
     while (true) {
         const K128 old = atomicCAS(&K[slot], empty, want);
-        if ((old.lo == EMPTY64 && old.hi == EMPTY64) || (old.lo == want.lo && old.hi == want.hi)) break;
+        if (old.lo == EMPTY64 && old.hi == EMPTY64) { *claimed = true; break; }
+        if (old.lo == want.lo && old.hi == want.hi) { *claimed = false; break; }
         slot = (slot + 1) & mask;
     }
     atomicAdd(&C[slot], 1u);
     if (fb) atomicOr(&C[slot], fb << 30);
+    return slot;
+}
+
+// Where one k-mer occurrence lives: payload word of its super-k-mer inside chunk `c` (32 bits), k-mer index inside the
+// super-k-mer (16 bits), 1 = the key is the hash of the reverse complement, chunk index (15 bits).
+__device__ __forceinline__ uint64_t src_locator(uint32_t chunk, uint32_t word, uint32_t i, bool isf) {
+    return (uint64_t)word | ((uint64_t)(i & 0xFFFFu) << 32) | ((uint64_t)(isf ? 0u : 1u) << 48) | ((uint64_t)chunk << 49);
 }
 
 __device__ __forceinline__ u128 revcomp128(u128 x) {
@@ -127,7 +142,7 @@ __device__ __forceinline__ void for_each_kmer128(const uint32_t *__restrict__ pl
         for (uint32_t i = 0;; ++i) {
             const bool isf = forward_only ? true : (fw < rc);
             const u128 key = forward_only ? fw : (fw < rc ? fw : rc);
-            f(key, flag_bits(flags, i, last, isf));
+            f(key, flag_bits(flags, i, last, isf), i, isf);
             if (i == last) break;
             const uint32_t nb = i + k;
             if ((nb & 15u) == 0 || i == 0) cw = pl[nb >> 4];
@@ -151,7 +166,7 @@ __device__ __forceinline__ void for_each_kmer128(const uint32_t *__restrict__ pl
         for (uint32_t i = 0;; ++i) {
             const bool isf = forward_only ? true : (fw < rc);
             const u128 key = forward_only ? fw : (fw < rc ? fw : rc);
-            f(key, flag_bits(flags, i, last, isf));
+            f(key, flag_bits(flags, i, last, isf), i, isf);
             if (i == last) break;
             const uint32_t co = packed_base(pl, i), ci = packed_base(pl, i + k);
             fw = fw * M - to_u128(T.fwd_mk[co]) + to_u128(T.fwd[ci]);
@@ -160,9 +175,26 @@ __device__ __forceinline__ void for_each_kmer128(const uint32_t *__restrict__ pl
     }
 }
 
-template <int THREADS, int TS_STATIC>
+// bytes per table slot: 16 key + 4 MapEntry word (+ 8 source locator when the hash is not invertible)
+template <int MODE>
+constexpr uint32_t slot_bytes128() { return MODE == MODE_RK128 ? 28u : 20u; }
+
+template <int THREADS, int TS_STATIC, int MODE>
 constexpr size_t merge_hash128_smem_bytes() {
-    return (size_t)TS_STATIC * 20 + 64;
+    return (size_t)TS_STATIC * slot_bytes128<MODE>() + 64;
+}
+
+// 2k bits of a packed super-k-mer starting at base i (k <= 64), reverse-complemented when rc: the bases whose FORWARD
+// hash is the table key.
+__device__ __forceinline__ u128 kmer_bases128(const uint32_t *__restrict__ pl, uint32_t i, uint32_t k, bool rc) {
+    const uint32_t w0 = i >> 4, sh = 2u * (i & 15u), nw = (sh + 2u * k + 31u) >> 5;   // <= 5 words, all inside the super-k-mer
+    u128 x = 0;
+    for (uint32_t w = 0; w < nw && w < 4; w++) x |= (u128)pl[w0 + w] << (32u * w);
+    x >>= sh;
+    if (nw > 4 && sh) x |= (u128)pl[w0 + 4] << (128u - sh);
+    if (k < 64) x &= (((u128)1) << (2u * k)) - 1;
+    if (rc) x = revcomp128(x) >> (128u - 2u * k);
+    return x;
 }
 
 // TS_STATIC > 0: table in shared memory (units with <= 3/4 TS_STATIC records).  TS_STATIC == 0: table in this CTA's
@@ -173,10 +205,13 @@ k_merge_hash128(const ChunkView *__restrict__ chunks, uint32_t n_chunks, const u
                 uint32_t first_unit, DevParams P, RkTables T, uint32_t min_mult, MergeOut128 out,
                 uint64_t *__restrict__ scratch, uint64_t per_cta_u64, PartSrc128 ps, const uint32_t *__restrict__ n_work_dev) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr bool WITH_SRC = MODE == MODE_RK128;
     K128 *K = reinterpret_cast<K128 *>(smem_raw);
-    uint32_t *C = reinterpret_cast<uint32_t *>(K + TS_STATIC);
+    uint64_t *L = reinterpret_cast<uint64_t *>(K + TS_STATIC);                       // WITH_SRC: source locator per slot
+    uint32_t *C = reinterpret_cast<uint32_t *>(K + TS_STATIC) + (WITH_SRC ? 2 * TS_STATIC : 0);
     __shared__ uint32_t s_cnt[2];
     __shared__ uint32_t s_special;         // MapEntry word of the all-ones key (see hash_insert128)
+    __shared__ unsigned long long s_special_src;
     __shared__ unsigned long long s_base;
     const uint32_t tid = threadIdx.x;
     if (n_work_dev) n_work = min(n_work, *n_work_dev);   // device-side list (big units whose partitions overflowed)
@@ -198,7 +233,8 @@ k_merge_hash128(const ChunkView *__restrict__ chunks, uint32_t n_chunks, const u
         if (TS_STATIC == 0) {
             TS = hash_table_slots_pow2(n);
             K = reinterpret_cast<K128 *>(scratch + (uint64_t)blockIdx.x * per_cta_u64);
-            C = reinterpret_cast<uint32_t *>(K + TS);
+            L = reinterpret_cast<uint64_t *>(K + TS);
+            C = reinterpret_cast<uint32_t *>(K + TS) + (WITH_SRC ? 2 * (size_t)TS : 0);
         }
         const uint32_t tmask = TS - 1;
         for (uint32_t i = tid; i < TS; i += THREADS) { K[i] = K128{EMPTY64, EMPTY64}; C[i] = 0u; }
@@ -207,8 +243,12 @@ k_merge_hash128(const ChunkView *__restrict__ chunks, uint32_t n_chunks, const u
         __syncthreads();
         if (SRC == SRC_RECORDS) {
             const uint64_t ro = (uint64_t)wi * ps.pcap;
-            for (uint32_t i = tid; i < n; i += THREADS)
-                hash_insert128(K, C, tmask, ((u128)ps.rec_hi[ro + i] << 64) | (u128)ps.rec_lo[ro + i], ps.rec_fl[ro + i], &s_special);
+            for (uint32_t i = tid; i < n; i += THREADS) {
+                bool claimed;
+                const uint32_t slot = hash_insert128(K, C, tmask, ((u128)ps.rec_hi[ro + i] << 64) | (u128)ps.rec_lo[ro + i],
+                                                     ps.rec_fl[ro + i], &s_special, &claimed);
+                if (WITH_SRC && claimed) { if (slot == SLOT_SPECIAL) s_special_src = ps.rec_src[ro + i]; else L[slot] = ps.rec_src[ro + i]; }
+            }
         } else {
             for (uint32_t c = 0; c < n_chunks; c++) {
                 const ChunkView cv = chunks[c];
@@ -218,9 +258,14 @@ k_merge_hash128(const ChunkView *__restrict__ chunks, uint32_t n_chunks, const u
                     const uint4 d = cv.desc[di];
                     const uint32_t color = d.w;
                     for_each_kmer128<MODE>(cv.payload + (d.x - cv.word_bias), d.y, (d.z >> 16) & 3u, P.k, P.forward_only, T,
-                                           [&](u128 key, uint32_t fb) {
+                                           [&](u128 key, uint32_t fb, uint32_t ki, bool isf) {
                                                if (MODE == MODE_COLOR) key = (key << 32) | (u128)color;
-                                               hash_insert128(K, C, tmask, key, fb, &s_special);
+                                               bool claimed;
+                                               const uint32_t slot = hash_insert128(K, C, tmask, key, fb, &s_special, &claimed);
+                                               if (WITH_SRC && claimed) {
+                                                   const uint64_t loc = src_locator(c, d.x - cv.word_bias, ki, isf);
+                                                   if (slot == SLOT_SPECIAL) s_special_src = loc; else L[slot] = loc;
+                                               }
                                            });
                 }
             }
@@ -283,6 +328,11 @@ k_merge_hash128(const ChunkView *__restrict__ chunks, uint32_t n_chunks, const u
                 if (MODE == MODE_COLOR || mult >= min_mult) {
                     out.keys_lo[gbase] = EMPTY64; out.keys_hi[gbase] = EMPTY64;
                     out.count_flags[gbase] = MODE == MODE_COLOR ? cc : (mult | (fl << 30));
+                    if (WITH_SRC) {
+                        const unsigned long long loc = s_special_src;
+                        const u128 b = kmer_bases128(chunks[loc >> 49].payload + (uint32_t)loc, (uint32_t)(loc >> 32) & 0xFFFFu, P.k, (loc >> 48) & 1u);
+                        out.src[2 * gbase] = (uint64_t)b; out.src[2 * gbase + 1] = (uint64_t)(b >> 64);
+                    }
                     first = 1;
                 }
             }
@@ -315,6 +365,11 @@ k_merge_hash128(const ChunkView *__restrict__ chunks, uint32_t n_chunks, const u
                 if (keep) {
                     const unsigned long long o = gbase + wbase + __popc(bal & ((1u << lane_id()) - 1u));
                     out.keys_lo[o] = kk.lo; out.keys_hi[o] = kk.hi; out.count_flags[o] = cf;
+                    if (WITH_SRC) {
+                        const uint64_t loc = L[i];
+                        const u128 b = kmer_bases128(chunks[loc >> 49].payload + (uint32_t)loc, (uint32_t)(loc >> 32) & 0xFFFFu, P.k, (loc >> 48) & 1u);
+                        out.src[2 * o] = (uint64_t)b; out.src[2 * o + 1] = (uint64_t)(b >> 64);
+                    }
                 }
             }
         }
@@ -336,7 +391,7 @@ __global__ void __launch_bounds__(THREADS)
 k_partition_units128(const ChunkView *__restrict__ chunks, uint32_t n_chunks, const uint32_t *__restrict__ big_unit,
                      const uint32_t *__restrict__ big_logp, const uint32_t *__restrict__ big_pbase, uint32_t n_big, DevParams P,
                      RkTables T, uint64_t *__restrict__ rec_lo, uint64_t *__restrict__ rec_hi, uint8_t *__restrict__ rec_fl,
-                     uint32_t *__restrict__ pcount, uint32_t pcap, uint32_t *__restrict__ big_ovf, uint32_t *__restrict__ retry,
+                     uint64_t *__restrict__ rec_src /* MODE_RK128 only */, uint32_t *__restrict__ pcount, uint32_t pcap, uint32_t *__restrict__ big_ovf, uint32_t *__restrict__ retry,
                      uint32_t *__restrict__ retry_count) {
     __shared__ uint32_t s_cur[PART_MAXP];
     __shared__ uint32_t s_ovf;
@@ -355,7 +410,7 @@ k_partition_units128(const ChunkView *__restrict__ chunks, uint32_t n_chunks, co
                 const uint4 d = cv.desc[di];
                 const uint32_t color = d.w;
                 for_each_kmer128<MODE>(cv.payload + (d.x - cv.word_bias), d.y, (d.z >> 16) & 3u, P.k, P.forward_only, T,
-                                       [&](u128 key, uint32_t fb) {
+                                       [&](u128 key, uint32_t fb, uint32_t ki, bool isf) {
                                            // coloured builds: all colours of a k-mer must meet in one partition
                                            const uint32_t p = part_hash128(key) & (np - 1);
                                            if (MODE == MODE_COLOR) key = (key << 32) | (u128)color;
@@ -363,6 +418,7 @@ k_partition_units128(const ChunkView *__restrict__ chunks, uint32_t n_chunks, co
                                            if (pos < pcap) {
                                                const uint64_t o = base + (uint64_t)p * pcap + pos;
                                                rec_lo[o] = (uint64_t)key; rec_hi[o] = (uint64_t)(key >> 64); rec_fl[o] = (uint8_t)fb;
+                                               if (MODE == MODE_RK128) rec_src[o] = src_locator(c, d.x - cv.word_bias, ki, isf);
                                            } else s_ovf = 1u;
                                        });
             }
@@ -452,13 +508,17 @@ constexpr size_t sort_units128_smem_bytes() {
 
 // One CTA per unit: entries [unit_out_off, +cnt) of src -> sorted at [unit_final_off, +cnt) of dst.
 // The src range is scratch after this kernel (used as the ping-pong partner for big units).
-template <int THREADS, int CAP>
+// WITH_SRC (rk128): every entry also owns 2 words of source bases.  The sort then carries the entry's index inside the
+// unit instead of its MapEntry word (idx_a / idx_b: scratch, laid out like src), and the MapEntry words and the bases are
+// gathered through the sorted indices at the end (src_cf and src_bases are read-only here).
+template <int THREADS, int CAP, bool WITH_SRC>
 __global__ void __launch_bounds__(THREADS)
 k_sort_units128(uint64_t *__restrict__ src_lo, uint64_t *__restrict__ src_hi, uint32_t *__restrict__ src_cf,
                 const uint64_t *__restrict__ unit_out_off, const uint32_t *__restrict__ unit_out_cnt,
                 const uint64_t *__restrict__ unit_final_off, uint64_t *__restrict__ dst_lo, uint64_t *__restrict__ dst_hi,
                 uint32_t *__restrict__ dst_cf, uint32_t n_units, uint32_t first_bit, uint32_t end_bit, uint64_t capacity,
-                uint32_t *__restrict__ overflow) {
+                uint32_t *__restrict__ overflow, const uint64_t *__restrict__ src_bases, uint64_t *__restrict__ dst_bases,
+                uint32_t *__restrict__ idx_a, uint32_t *__restrict__ idx_b) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     if (unit_final_off[n_units] > capacity) {   // the host enlarges the final table and launches the sort again
         if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(overflow, 4u);
@@ -476,12 +536,31 @@ k_sort_units128(uint64_t *__restrict__ src_lo, uint64_t *__restrict__ src_hi, ui
         if (n == 0) continue;
         const uint64_t so = unit_out_off[u], fo = unit_final_off[u];
         if (n <= (uint32_t)CAP) {
-            for (uint32_t i = tid; i < n; i += THREADS) { sAlo[i] = src_lo[so + i]; sAhi[i] = src_hi[so + i]; sAv[i] = src_cf[so + i]; }
+            for (uint32_t i = tid; i < n; i += THREADS) { sAlo[i] = src_lo[so + i]; sAhi[i] = src_hi[so + i]; sAv[i] = WITH_SRC ? i : src_cf[so + i]; }
             __syncthreads();
             const int w = block_radix_sort128<THREADS>(sAlo, sAhi, sAv, sBlo, sBhi, sBv, n, first_bit, end_bit, hist, s_scan);
             const uint64_t *rl = w ? sBlo : sAlo, *rh = w ? sBhi : sAhi;
             const uint32_t *rv = w ? sBv : sAv;
-            for (uint32_t i = tid; i < n; i += THREADS) { dst_lo[fo + i] = rl[i]; dst_hi[fo + i] = rh[i]; dst_cf[fo + i] = rv[i]; }
+            for (uint32_t i = tid; i < n; i += THREADS) {
+                dst_lo[fo + i] = rl[i]; dst_hi[fo + i] = rh[i];
+                if (WITH_SRC) {
+                    const uint64_t j = so + rv[i];
+                    dst_cf[fo + i] = src_cf[j];
+                    dst_bases[2 * (fo + i)] = src_bases[2 * j]; dst_bases[2 * (fo + i) + 1] = src_bases[2 * j + 1];
+                } else dst_cf[fo + i] = rv[i];
+            }
+        } else if (WITH_SRC) {
+            for (uint32_t i = tid; i < n; i += THREADS) idx_a[so + i] = i;
+            __syncthreads();
+            const int w = block_radix_sort128<THREADS>(src_lo + so, src_hi + so, idx_a + so, dst_lo + fo, dst_hi + fo, idx_b + so,
+                                                       n, first_bit, end_bit, hist, s_scan);
+            const uint32_t *rv = (w ? idx_b : idx_a) + so;
+            for (uint32_t i = tid; i < n; i += THREADS) {
+                if (w == 0) { dst_lo[fo + i] = src_lo[so + i]; dst_hi[fo + i] = src_hi[so + i]; }
+                const uint64_t j = so + rv[i];
+                dst_cf[fo + i] = src_cf[j];
+                dst_bases[2 * (fo + i)] = src_bases[2 * j]; dst_bases[2 * (fo + i) + 1] = src_bases[2 * j + 1];
+            }
         } else {
             const int w = block_radix_sort128<THREADS>(src_lo + so, src_hi + so, src_cf + so, dst_lo + fo, dst_hi + fo, dst_cf + fo,
                                                        n, first_bit, end_bit, hist, s_scan);

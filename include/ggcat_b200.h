@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define GGCAT_B200_ABI_VERSION 6
+#define GGCAT_B200_ABI_VERSION 7
 
 typedef enum {
     GGCAT_B200_OK = 0,
@@ -100,6 +100,14 @@ typedef struct {
     const uint32_t *colors;         /* sorted-unique colour ids per entry */
     uint64_t total_kmers;           /* k-mer occurrences processed */
     uint64_t unique_kmers;          /* distinct keys before the multiplicity filter (0 = not tracked, coloured builds) */
+    /* Non-invertible keys (rabin-karp128): the bases of one occurrence of every entry, so that the consumer can rebuild
+     * sequence from a hash -- the role of the reference's `saved_reads` + `encoded_saved_reads_indexes`
+     * (crates/assembler_kmers_merge/src/unitigs_extender/hashmap.rs:32-33,96-149 get_kmers, :413-431 add_sequence).
+     * Entry e owns words [e * src_kmer_words, (e + 1) * src_kmer_words); base j of the k-mer sits at bits 2(j % 32) of word
+     * j / 32 (A0 C1 T2 G3), in the orientation whose FORWARD hash equals the key.  NULL / 0 for invertible keys (seq-hash). */
+    const uint64_t *src_kmers;
+    uint32_t src_kmer_words;
+    uint32_t reserved0;
     void *opaque;
 } ggcat_b200_table;
 

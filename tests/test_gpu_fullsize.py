@@ -43,6 +43,11 @@ def _check_units(tab_units, units, reads, sk, k, s, b2, hash_type=O.HASH_SEQ, wi
             assert np.array_equal(tab_units.keys_hi[sl], ref["key_hi"]), f"unit {u}: high key words differ"
         assert np.array_equal(tab_units.multiplicity[sl].astype(np.uint64), ref["multiplicity"]), f"unit {u}: counts"
         assert np.array_equal(tab_units.flags[sl], ref["flags"]), f"unit {u}: flags"
+        if hash_type == O.HASH_RK128:   # saved-reads contract: the source bases of a sample of entries re-hash to their keys
+            assert tab_units.src_kmers is not None
+            for e in list(range(sl.start, sl.stop))[:: max(1, (sl.stop - sl.start) // 16)]:
+                lo, hi, _ = O.kmer_hashes(tab_units.src_kmer(e, k), k, O.HASH_RK128, True)
+                assert (int(lo[0]), int(hi[0])) == (int(tab_units.keys_lo[e]), int(tab_units.keys_hi[e])), f"unit {u} entry {e}: source bases"
         n += len(ref)
     return n
 

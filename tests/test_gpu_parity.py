@@ -47,6 +47,24 @@ def _gpu_records(ctx, n_buckets):
     return sorted(out)
 
 
+def _check_src_kmers(tab, sl, k, hash_type, limit=64):
+    """Non-invertible keys (rk128) come with the bases of one occurrence (the reference's saved_reads contract,
+    hashmap.rs:96-149): re-hash them on the host -- their FORWARD hash must be the key."""
+    if hash_type != O.HASH_RK128:
+        assert tab.src_kmers is None
+        return
+    assert tab.src_kmers is not None and tab.src_kmers.shape == (tab.keys_lo.size, 2)
+    idx = list(range(sl.start, sl.stop))
+    if len(idx) > limit:
+        idx = idx[:: max(1, len(idx) // limit)]
+    for e in idx:
+        seq = tab.src_kmer(e, k)
+        lo, hi, _ = O.kmer_hashes(seq, k, O.HASH_RK128, True)
+        assert (int(lo[0]), int(hi[0])) == (int(tab.keys_lo[e]), int(tab.keys_hi[e])), f"entry {e}: source bases {seq} do not hash to the key"
+        w0, w1 = int(tab.src_kmers[e][0]), int(tab.src_kmers[e][1])
+        assert ((w1 << 64) | w0) >> (2 * k) == 0, "bits above the k-mer must be clear"
+
+
 def _check_tables(G, ctx, reads, sk, k, s, b1, b2, forward_only=False, ranges=None, hash_type=O.HASH_SEQ, colors=False):
     nb = (1 << b1) + 1
     ranges = ranges or [(0, nb)]
@@ -69,6 +87,7 @@ def _check_tables(G, ctx, reads, sk, k, s, b1, b2, forward_only=False, ranges=No
                 assert not ref["key_hi"].any()
             assert np.array_equal(tab.multiplicity[sl].astype(np.uint64), ref["multiplicity"]), f"unit {u}: counts"
             assert np.array_equal(tab.flags[sl], ref["flags"]), f"unit {u}: flags"
+            _check_src_kmers(tab, sl, k, hash_type)
             if colors:
                 for j, e in enumerate(range(sl.start, sl.stop)):
                     want = rcols[int(ref["color_off"][j]):int(ref["color_off"][j]) + int(ref["color_len"][j])]
