@@ -288,7 +288,16 @@ k_merge_hash128(const ChunkView *__restrict__ chunks, uint32_t n_chunks, const u
                 const uint32_t cc = C[i];
                 const uint32_t cnt = cc & 0x3FFFFFFFu, fl = cc >> 30;
                 const uint32_t mult = cnt >> ((fl == 3u) ? 1 : 0);  // map_entry.rs:79-84
-                if (mult >= min_mult) ++my_keep;
+                if (mult >= min_mult) {
+                    ++my_keep;
+                    if (WITH_SRC) {   // pass 2 reads the survivor's bases at a random payload address: start the fetch now
+                        const uint64_t loc = L[i];
+                        const uint32_t ki = (uint32_t)(loc >> 32) & 0xFFFFu;
+                        const uint32_t *pp = chunks[loc >> 49].payload + (uint32_t)loc + (ki >> 4);
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(pp));
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(pp + ((2u * (ki & 15u) + 2u * P.k - 1u) >> 5)));   // last word read
+                    }
+                }
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
