@@ -2,6 +2,7 @@
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 _HERE = Path(__file__).resolve().parent
@@ -117,7 +118,8 @@ def load() -> C.CDLL:
             f"{LIB_PATH} is missing: the CUDA extension has not been built "
             "(run `python -c 'import __graft_entry__ as g; g.build()'`). ggcat_b200 has no CPU fallback."
         )
-    lib = C.CDLL(str(LIB_PATH))
+    # GGCAT_B200_LIB: another build of the same sources (kernel A/B experiments: profiles/ab_variants.py)
+    lib = C.CDLL(os.environ.get("GGCAT_B200_LIB") or str(LIB_PATH))
     for name, (res, args) in SYMBOLS.items():
         fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
         fn.restype = res

@@ -32,17 +32,30 @@ struct DevParams {
     uint32_t hash_type;  // ggcat_b200_hash_type (k-mer identity hash of phase 2)
 };
 
-constexpr int WIN_T = 1024;       // windows per tile
-constexpr int WIN_THREADS = 128;   // 8 windows per thread
-constexpr int WIN_WMAX = 64;      // max supported k - m
+#ifndef GGB_WIN_T
+#define GGB_WIN_T 1024
+#endif
+#ifndef GGB_WIN_TPC
+#define GGB_WIN_TPC 1
+#endif
+constexpr int WIN_T = GGB_WIN_T;            // windows per tile (1024 or 2048)
+constexpr int WIN_THREADS = WIN_T / 8;      // 8 windows per thread
+constexpr int WIN_TPC = GGB_WIN_TPC;        // tiles per CTA: the bulk copies of tile t+1 are in flight while tile t is processed
+constexpr int WIN_NB = WIN_TPC > 1 ? 2 : 1; // landing buffers
+#ifndef GGB_WIN_MINB
+#define GGB_WIN_MINB 9
+#endif
+constexpr int WIN_MINB = GGB_WIN_MINB;      // resident CTAs per SM the register allocation must allow
+constexpr int WIN_WMAX = 128;     // max supported k - m (k <= 128)
 constexpr int WIN_NI = WIN_T + WIN_WMAX;  // m-mer items per tile (upper bound)
 #define PADX(x) ((x) + ((x) >> 3))
 
 // entry bit layout (u64)
-constexpr int ENT_POS_BITS = 11;  // position of the window inside its tile
-constexpr uint64_t ENT_S = 1ull << 11, ENT_E = 1ull << 12, ENT_FIRST = 1ull << 13, ENT_RC = 1ull << 14,
-                   ENT_DUP = 1ull << 15;
-constexpr int ENT_SECOND_SHIFT = 16, ENT_BUCKET_SHIFT = 24, ENT_ARG_SHIFT = 38, ENT_SRANK_SHIFT = 46;
+constexpr int ENT_POS_BITS = WIN_T <= 1024 ? 11 : 12;  // position of the window inside its tile (0 .. WIN_T)
+constexpr uint64_t ENT_S = 1ull << ENT_POS_BITS, ENT_E = ENT_S << 1, ENT_FIRST = ENT_S << 2, ENT_RC = ENT_S << 3,
+                   ENT_DUP = ENT_S << 4;
+constexpr int ENT_SECOND_SHIFT = ENT_POS_BITS + 5, ENT_BUCKET_SHIFT = ENT_SECOND_SHIFT + 8, ENT_ARG_SHIFT = ENT_BUCKET_SHIFT + 14,
+              ENT_SRANK_SHIFT = ENT_ARG_SHIFT + 8;   // then 12 bits of super-k-mer rank
 
 // descriptor meta word: minimizer_pos(16) | flags(2)<<16 | rc<<18 | second_bucket(8)<<19
 __host__ __device__ __forceinline__ uint32_t make_meta(uint32_t mpos, uint32_t flags, uint32_t rc, uint32_t second) {
@@ -134,16 +147,17 @@ __device__ __forceinline__ uint64_t bits64(const uint32_t *bm, uint32_t s, uint3
 //   D  M_x = comb(suffix[x], prefix[x+w-1])
 //   E  split-start / segment-end flags, F in-order compaction (one block scan) + bucket / orientation / minimizer offset
 //      of every super-k-mer start from the (minimum, argmin) pair its thread holds in registers, G copy-out
-__global__ void __launch_bounds__(WIN_THREADS)
+__global__ void __launch_bounds__(WIN_THREADS, WIN_MINB)
 k_windows(const uint32_t *__restrict__ pk, const uint32_t *__restrict__ bad, const uint32_t *__restrict__ brk,
           uint32_t n /* bases in batch */, DevParams P, uint64_t *__restrict__ ent, uint32_t *__restrict__ tile_cnt,
-          uint32_t *__restrict__ tile_scnt, uint32_t *__restrict__ seg_count) {
+          uint32_t *__restrict__ tile_scnt, uint32_t *__restrict__ seg_count, uint32_t n_tiles) {
     // TMA landing buffers (16-byte aligned; the tile's first word sits at offset (W0 & 3) / (BW0 & 3) because the
     // bulk copy starts at the 16-byte boundary below it)
-    __shared__ __align__(16) uint32_t s_pk_raw[(WIN_T + 2 * WIN_WMAX + 64) / 16 + 12];
-    __shared__ __align__(16) uint32_t s_bad_raw[(WIN_T + 2 * WIN_WMAX + 64) / 32 + 12];
-    __shared__ __align__(16) uint32_t s_cmb_raw[(WIN_T + 2 * WIN_WMAX + 64) / 32 + 12];   // record starts, then bad | record-start
-    __shared__ __align__(8) uint64_t s_bar;
+    constexpr int PKW = (((WIN_T + 2 * WIN_WMAX + 64) / 16 + 12) + 3) & ~3, BMW = (((WIN_T + 2 * WIN_WMAX + 64) / 32 + 12) + 3) & ~3;
+    __shared__ __align__(16) uint32_t s_pk_all[WIN_NB][PKW];
+    __shared__ __align__(16) uint32_t s_bad_all[WIN_NB][BMW];
+    __shared__ __align__(16) uint32_t s_cmb_all[WIN_NB][BMW];   // record starts, then bad | record-start
+    __shared__ __align__(8) uint64_t s_bar[WIN_NB];
     // m-mer values and window minima: element x lives at PADX(x) = x + x/8, so that the 8-windows-per-thread phase
     // (lane stride 8 elements) touches every 8-byte bank pair twice per warp instead of sixteen times
     __shared__ uint64_t s_v0[PADX(WIN_NI + 16) + 1];
@@ -152,33 +166,34 @@ k_windows(const uint32_t *__restrict__ pk, const uint32_t *__restrict__ bad, con
     __shared__ uint64_t s_TF[32][4], s_TR[32][4];  // rotl(h(c), m-1-i), rotl(r(c), i)
     __shared__ uint64_t s_T1[16], s_T2[16];        // roll tables indexed by (leaving base << 2 | entering base)
     __shared__ uint32_t s_scan[WIN_THREADS / 32 + 2];
-    __shared__ uint32_t s_nfirst;                  // segments (N-free stretches of >= k bases) that start in this tile
+    __shared__ uint32_t s_nfirst;                  // segments (N-free stretches of >= k bases) that start in this CTA's tiles
 
     const uint32_t tid = threadIdx.x;
-    const uint32_t tile = blockIdx.x;
-    const int64_t j0 = (int64_t)tile * WIN_T;  // first window of the tile (== its base index)
+    const uint32_t tile_first = blockIdx.x * WIN_TPC;
     const uint32_t k = P.k, m = P.m, w = P.w;
-    // x-coordinates: window / m-mer item x  <->  global position j0 - 1 + x
-    const int64_t gfirst = j0 - 1;
-    const int64_t bfirst = gfirst < 0 ? 0 : gfirst;       // first base the tile may touch
-    const uint32_t W0 = (uint32_t)(bfirst >> 4);          // first packed word
-    const uint32_t BW0 = (uint32_t)(bfirst >> 5);         // first bitmap word
     const uint32_t n_items = WIN_T + w;                   // m-mer items x in [0, n_items)
-    const uint32_t last_base = (uint32_t)(j0 + WIN_T + k + 1);  // exclusive upper bound of bases touched
-    const uint32_t n_pkw = ((last_base + 15) >> 4) - W0 + 2;
-    const uint32_t n_bmw = ((last_base + 31) >> 5) - BW0 + 3;
 
-    // ---- A: one elected thread issues three TMA bulk copies (packed bases, bad bitmap, record-start bitmap) that
-    //         land while the other threads build the hash tables
-    uint32_t *s_pk = s_pk_raw + (W0 & 3u), *s_bad = s_bad_raw + (BW0 & 3u), *s_cmb = s_cmb_raw + (BW0 & 3u);
-    const uint32_t pk_words = (n_pkw + (W0 & 3u) + 3u) & ~3u, bm_words = (n_bmw + (BW0 & 3u) + 3u) & ~3u;
+    // ---- A: one elected thread issues three TMA bulk copies per tile (packed bases, bad bitmap, record-start bitmap); the
+    //         copies of the first two tiles land while the other threads build the hash tables
+    auto issue = [&](uint32_t tl) {
+        const uint32_t tile = tile_first + tl;
+        if (tile >= n_tiles) return;
+        const int64_t bf = (int64_t)tile * WIN_T - 1 < 0 ? 0 : (int64_t)tile * WIN_T - 1;
+        const uint32_t W0 = (uint32_t)(bf >> 4), BW0 = (uint32_t)(bf >> 5);
+        const uint32_t lastb = (uint32_t)((int64_t)tile * WIN_T + WIN_T + k + 1);
+        const uint32_t n_pkw = ((lastb + 15) >> 4) - W0 + 2, n_bmw = ((lastb + 31) >> 5) - BW0 + 4;
+        const uint32_t pkw = (n_pkw + (W0 & 3u) + 3u) & ~3u, bmw = (n_bmw + (BW0 & 3u) + 3u) & ~3u;
+        const uint32_t b = tl & (WIN_NB - 1);
+        mbar_expect_tx(&s_bar[b], (pkw + 2 * bmw) * 4);
+        tma_load_1d(s_pk_all[b], pk + (W0 & ~3u), pkw * 4, &s_bar[b]);
+        tma_load_1d(s_bad_all[b], bad + (BW0 & ~3u), bmw * 4, &s_bar[b]);
+        tma_load_1d(s_cmb_all[b], brk + (BW0 & ~3u), bmw * 4, &s_bar[b]);
+    };
     if (tid == 0) {
         s_nfirst = 0;
-        mbar_init(&s_bar, 1);
-        mbar_expect_tx(&s_bar, (pk_words + 2 * bm_words) * 4);
-        tma_load_1d(s_pk_raw, pk + (W0 & ~3u), pk_words * 4, &s_bar);
-        tma_load_1d(s_bad_raw, bad + (BW0 & ~3u), bm_words * 4, &s_bar);
-        tma_load_1d(s_cmb_raw, brk + (BW0 & ~3u), bm_words * 4, &s_bar);
+        for (int b = 0; b < WIN_NB; b++) mbar_init(&s_bar[b], 1);
+        issue(0);
+        if (WIN_TPC > 1) issue(1);
     }
     if (tid < 16) {
         // cn_nthash.rs:43-57 roll_hash with both table terms folded:
@@ -192,8 +207,24 @@ k_windows(const uint32_t *__restrict__ pk, const uint32_t *__restrict__ bad, con
         s_TF[i][c] = rotl64(nt_h(c), m - 1 - i);
         s_TR[i][c] = rotl64(nt_r(c), i);
     }
-    __syncthreads();          // barrier initialised (and tables written) before anyone polls it
-    mbar_wait(&s_bar, 0);
+    __syncthreads();          // barriers initialised (and tables written) before anyone polls them
+#pragma unroll 1
+    for (uint32_t tl = 0; tl < (uint32_t)WIN_TPC; tl++) {
+    const uint32_t tile = tile_first + tl;
+    if (tile >= n_tiles) break;
+    const uint32_t lb_ = tl & (WIN_NB - 1);
+    const int64_t j0 = (int64_t)tile * WIN_T;  // first window of the tile (== its base index)
+    // x-coordinates: window / m-mer item x  <->  global position j0 - 1 + x
+    const int64_t gfirst = j0 - 1;
+    const int64_t bfirst = gfirst < 0 ? 0 : gfirst;       // first base the tile may touch
+    const uint32_t W0 = (uint32_t)(bfirst >> 4);          // first packed word
+    const uint32_t BW0 = (uint32_t)(bfirst >> 5);         // first bitmap word
+    const uint32_t last_base = (uint32_t)(j0 + WIN_T + k + 1);  // exclusive upper bound of bases touched
+    const uint32_t n_bmw = ((last_base + 31) >> 5) - BW0 + 4;
+    uint32_t *s_pk_raw = s_pk_all[lb_], *s_bad_raw = s_bad_all[lb_], *s_cmb_raw = s_cmb_all[lb_];
+    uint32_t *s_pk = s_pk_raw + (W0 & 3u), *s_bad = s_bad_raw + (BW0 & 3u), *s_cmb = s_cmb_raw + (BW0 & 3u);
+    const uint32_t bm_words = (n_bmw + (BW0 & 3u) + 3u) & ~3u;
+    mbar_wait(&s_bar[lb_], (tl >> 1) & 1u);
     for (uint32_t i = tid; i < bm_words; i += WIN_THREADS) s_cmb_raw[i] |= s_bad_raw[i];
     __syncthreads();
 
@@ -302,6 +333,15 @@ k_windows(const uint32_t *__restrict__ pk, const uint32_t *__restrict__ bad, con
             const bool ok = j >= 0 && (uint64_t)j + (k - 1) <= (uint64_t)n && bd == 0 && (bits & kmask) == 0;
             ok10 |= (ok ? 1u : 0u) << i;
         }
+        if (k > 66) {   // (block-uniform) the k-2 positions behind a window start span a second 64-bit word
+            const uint64_t cx = extract64(s_cmb, rel + 128);
+            const uint64_t kmask2 = (1ull << (k - 66)) - 1ull;      // k <= 128
+#pragma unroll
+            for (int i = 0; i < WPT + 2; i++) {
+                const uint64_t bits2 = i == 0 ? chi : ((chi >> i) | (cx << (64 - i)));
+                if (bits2 & kmask2) ok10 &= ~(1u << i);
+            }
+        }
     }
 
     // ---- E: split / segment-end flags of the thread's windows, F: in-order compaction (one block scan)
@@ -344,6 +384,10 @@ k_windows(const uint32_t *__restrict__ pk, const uint32_t *__restrict__ bad, con
         n_ent = tot & 0xFFFFu; n_s = tot >> 16;
     }
     __syncthreads();
+    if (WIN_TPC > 2 && tid == 0 && tl + 2 < (uint32_t)WIN_TPC) {   // this tile's landing buffer is free: start the copies of tile tl+2
+        fence_proxy_async_smem();
+        issue(tl + 2);
+    }
 
     // ---- G: per super-k-mer: bucket / orientation from its minimizer (assembler_minimizer_bucketing/src/lib.rs:218-238);
     //         the minimizer's position came out of the window reduction, nothing is searched
@@ -366,10 +410,10 @@ k_windows(const uint32_t *__restrict__ pk, const uint32_t *__restrict__ bad, con
         }
         ent[(uint64_t)tile * WIN_T + i] = e;
     }
-    if (tid == 0) {
-        tile_cnt[tile] = n_ent; tile_scnt[tile] = n_s;
-        if (s_nfirst) atomicAdd(seg_count, s_nfirst);     // SequencesSplitter::valid_bases bookkeeping (one atomic per tile)
-    }
+    if (tid == 0) { tile_cnt[tile] = n_ent; tile_scnt[tile] = n_s; }
+    if (WIN_TPC > 1) __syncthreads();     // s_v0 / s_fwd / s_ent are rewritten by the next tile
+    }   // tiles of this CTA
+    if (tid == 0 && s_nfirst) atomicAdd(seg_count, s_nfirst);     // SequencesSplitter::valid_bases bookkeeping (one atomic per CTA)
 }
 
 // ------------------------------------------------------------------------------------------------

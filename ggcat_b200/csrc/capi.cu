@@ -155,7 +155,7 @@ struct ggcat_b200_ctx {
     cudaStream_t stream = nullptr;
     int sm_count = 148;
     uint64_t max_batch = 1ull << 30;
-    uint64_t host_batch = 48ull << 20;   // push_reads(host): H2D of batch i+1 overlaps the kernels of batch i
+    uint64_t host_batch = 24ull << 20;   // push_reads(host): the H2D of batches i+1, i+2 overlaps the kernels of batch i (24 MB measured best on C2: 3.41 vs 3.54 ms at 48 MB)
     uint64_t part_kmers = 36ull << 20;   // merge_bucket_range(host): D2H of part j overlaps the merge of part j+1
     uint64_t part_kmers_dev = 192ull << 20;  // merge_bucket_range_device: bounds the per-part scratch (12 B / record + key partitions)
     double distinct_ratio = 1.0;         // distinct keys / records of the parts merged so far (sizes the key partitions)
@@ -164,8 +164,10 @@ struct ggcat_b200_ctx {
     uint64_t fin_cap = 0;                // entries the final table (out_keys2 / out_cf2 / out_hi2) can hold
     uint64_t final_hint = 0;             // survivors of the previous build of this context (sizes the next final table)
     cudaStream_t copy_stream = nullptr;
-    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr}, ev_part = nullptr;
-    DevBuf st_ascii[2], st_off[2], st_col[2];
+    static constexpr int N_STAGE = 3;    // H2D staging slots: the copy of batch i+2 never waits for the kernels of batch i
+    cudaEvent_t ev_h2d[N_STAGE] = {}, ev_free[N_STAGE] = {}, ev_part = nullptr;
+    DevBuf st_ascii[N_STAGE], st_off[N_STAGE], st_col[N_STAGE];
+    int part_scheme = 1;                 // GGCAT_B200_PART_SCHEME: 0 = shrinking parts (first = half), 1 = a small first part, then equal parts
     bool finished = false;
     bool timing = false;
     int merge_mode = 1;  // 1 = shared-memory hash table (default), 0 = LSD radix sort (GGCAT_B200_MERGE=sort)
@@ -193,6 +195,7 @@ struct ggcat_b200_ctx {
     DevBuf d_static_off;                   // wide path: static output regions of partitioned units
     DevBuf d_rkpos;                        // rabin-karp per-position tables
     DevBuf d_recfl;                        // flag bits of the wide path's partition records
+    uint32_t src_words = 2;                // rk128: 64-bit words of source bases per table entry = max(2, ceil(k / 32))
     DevBuf d_recsrc, out_src, out_src2, sort_idx;   // rk128: source locators of partition records, source bases (unsorted / final), sort index ping-pong
     DevBuf d_mstage;                       // merge uploads (views, work lists, unit_n, static_off) in one copy
     uint8_t *h_mstage = nullptr; size_t h_mstage_cap = 0;
@@ -350,9 +353,10 @@ int32_t bucket_batch_device(ggcat_b200_ctx *c, const uint8_t *d_data, const uint
     CU(c->tile_sbase.reserve(((uint64_t)n_tiles + 2) * 4));
     {
         LaunchTimer t(c, F_WINDOWS);
-        k_windows<<<n_tiles, WIN_THREADS, 0, st>>>(pkb, c->bad.as<uint32_t>(), c->brk.as<uint32_t>(),
+        k_windows<<<(n_tiles + WIN_TPC - 1) / WIN_TPC, WIN_THREADS, 0, st>>>(pkb, c->bad.as<uint32_t>(), c->brk.as<uint32_t>(),
                                                    (uint32_t)n, P, c->ent.as<uint64_t>(), c->tile_cnt.as<uint32_t>(),
-                                                   c->tile_sbase.as<uint32_t>(), ch->unit_cnt.as<uint32_t>() + P.n_units /* spare slot: segments */);
+                                                   c->tile_sbase.as<uint32_t>(), ch->unit_cnt.as<uint32_t>() + P.n_units /* spare slot: segments */,
+                                                   n_tiles);
     }
     CU(c->totals.reserve(8 * 8));
     {
@@ -655,7 +659,7 @@ int32_t final_reserve(ggcat_b200_ctx *c, uint64_t need, uint64_t keep, bool wide
     CU(grow(c->out_keys2, 8));
     CU(grow(c->out_cf2, 4));
     if (wide) CU(grow(c->out_hi2, 8));
-    if (with_src) CU(grow(c->out_src2, 16));
+    if (with_src) CU(grow(c->out_src2, 8 * (size_t)c->src_words));
     c->fin_cap = need;
     return 0;
 }
@@ -1158,7 +1162,7 @@ int32_t merge_range_device_wide(ggcat_b200_ctx *c, uint32_t first_bucket, uint32
     const uint64_t cap_all = cap + big_records;
     CU(c->out_keys.reserve(cap_all * 8)); CU(c->out_hi.reserve(cap_all * 8)); CU(c->out_cf.reserve(cap_all * 4));
     const bool with_src = c->wide_mode == MODE_RK128;
-    if (with_src) { CU(c->out_src.reserve(cap_all * 16)); CU(c->sort_idx.reserve(cap_all * 8)); }
+    if (with_src) { CU(c->out_src.reserve(cap_all * 8 * c->src_words)); CU(c->sort_idx.reserve(cap_all * 8)); }
     const uint64_t rec_total = std::max(cap, pb.cap_total);
     if (pb.ub == 0) {
         // coloured builds fold in one piece and need every (k-mer, colour) entry; the others grow with the survivors
@@ -1175,7 +1179,7 @@ int32_t merge_range_device_wide(ggcat_b200_ctx *c, uint32_t first_bucket, uint32
     out.keys_lo = c->out_keys.as<uint64_t>(); out.keys_hi = c->out_hi.as<uint64_t>(); out.count_flags = c->out_cf.as<uint32_t>();
     out.cursor = c->cursor.as<unsigned long long>(); out.unit_out_off = c->unit_out_off.as<uint64_t>();
     out.unit_out_cnt = c->unit_out_cnt.as<uint32_t>(); out.capacity = cap; out.overflow = c->overflow.as<uint32_t>();
-    out.src = with_src ? c->out_src.as<uint64_t>() : nullptr;
+    out.src = with_src ? c->out_src.as<uint64_t>() : nullptr; out.src_words = c->src_words; out.pad = 0;
     const ChunkView *dv = c->d_views.as<ChunkView>();
     const uint32_t nch = (uint32_t)views.size();
     if (c->wide_mode == MODE_SEQ128) { TRY(launch_hash128<MODE_SEQ128>(c, dv, nch, work, u0, out, large)); TRY(launch_partitions128<MODE_SEQ128>(c, dv, nch, u0, out, bp)); }
@@ -1197,7 +1201,7 @@ int32_t merge_range_device_wide(ggcat_b200_ctx *c, uint32_t first_bucket, uint32
                 c->unit_out_cnt.as<uint32_t>(), c->unit_final_off.as<uint64_t>() + pb.ub, c->out_keys2.as<uint64_t>(),
                 c->out_hi2.as<uint64_t>(), c->out_cf2.as<uint32_t>(), nu, 0u, end_bit, c->fin_cap, c->overflow.as<uint32_t>(),
                 with_src ? c->out_src.as<uint64_t>() : nullptr, with_src ? c->out_src2.as<uint64_t>() : nullptr,
-                with_src ? c->sort_idx.as<uint32_t>() : nullptr, with_src ? c->sort_idx.as<uint32_t>() + cap_all : nullptr);
+                with_src ? c->sort_idx.as<uint32_t>() : nullptr, with_src ? c->sort_idx.as<uint32_t>() + cap_all : nullptr, c->src_words);
         }
         CU(cudaGetLastError());
         if (c->wide_mode == MODE_COLOR || attempt > 0) break;   // sized for every record / already regrown
@@ -1294,7 +1298,10 @@ int32_t ggcat_b200_create(const ggcat_b200_params *params, ggcat_b200_ctx **out)
     if (p.hash_type == GGCAT_B200_HASH_AUTO) p.hash_type = p.k <= 64 ? GGCAT_B200_HASH_SEQ : GGCAT_B200_HASH_RK128;  // crates/api/src/utils.rs:17-26
     if (p.hash_type != GGCAT_B200_HASH_SEQ && p.hash_type != GGCAT_B200_HASH_RK128)
         return set_err(GGCAT_B200_ERR_INVALID, "hash_type=%u unsupported (1 = seq-hash, 4 = rabin-karp128)", p.hash_type);
-    if (p.k < 4 || p.k > 64) return set_err(GGCAT_B200_ERR_INVALID, "k=%u unsupported (4..64)", p.k);
+    // seq-hash keys hold at most 64 bases; longer k-mers take the non-invertible rabin-karp128 hash, as in the reference
+    // (crates/api/src/utils.rs:17-26), up to RK_MAXK bases
+    if (p.k < 4 || p.k > (uint32_t)RK_MAXK) return set_err(GGCAT_B200_ERR_INVALID, "k=%u unsupported (4..%d)", p.k, RK_MAXK);
+    if (p.k > 64 && p.hash_type != GGCAT_B200_HASH_RK128) return set_err(GGCAT_B200_ERR_INVALID, "k=%u needs hash_type rabin-karp128 (seq-hash keys hold <= 64 bases)", p.k);
     if (p.m < 2 || p.m > 32 || p.m >= p.k) return set_err(GGCAT_B200_ERR_INVALID, "m=%u invalid for k=%u", p.m, p.k);
     if (p.k - p.m < 2 || p.k - p.m > (uint32_t)WIN_WMAX) return set_err(GGCAT_B200_ERR_INVALID, "k-m=%u outside 2..%d", p.k - p.m, WIN_WMAX);
     if (p.buckets_count_log > 13) return set_err(GGCAT_B200_ERR_INVALID, "buckets_count_log > 13");  // config MAX_BUCKETS_COUNT_LOG
@@ -1338,19 +1345,20 @@ int32_t ggcat_b200_create(const ggcat_b200_params *params, ggcat_b200_ctx **out)
             c->rk.fwd[b] = to_k128(L[b]); c->rk.bkw[b] = to_k128(L[b ^ 2]);
             c->rk.fwd_mk[b] = to_k128(L[b] * mk1 * M); c->rk.bkw_mk1[b] = to_k128(L[b ^ 2] * mk1);
         }
-        // per-position terms L[b] M^j, j < 64
-        std::vector<K128> pos(2 * 64 * 4);
+        // per-position terms L[b] M^j, j < RK_MAXK
+        std::vector<K128> pos(2 * RK_MAXK * 4);
         u128 mj = 1;
-        for (int j = 0; j < 64; j++) {
-            for (int b = 0; b < 4; b++) { pos[j * 4 + b] = to_k128(L[b] * mj); pos[256 + j * 4 + b] = to_k128(L[b ^ 2] * mj); }
+        for (int j = 0; j < RK_MAXK; j++) {
+            for (int b = 0; b < 4; b++) { pos[j * 4 + b] = to_k128(L[b] * mj); pos[RK_MAXK * 4 + j * 4 + b] = to_k128(L[b ^ 2] * mj); }
             mj *= M;
         }
+        c->src_words = std::max<uint32_t>(2, (p.k + 31) / 32);
         if (c->d_rkpos.reserve(pos.size() * sizeof(K128)) != cudaSuccess ||
             cudaMemcpy(c->d_rkpos.p, pos.data(), pos.size() * sizeof(K128), cudaMemcpyHostToDevice) != cudaSuccess) {
             delete c;
             return set_err(GGCAT_B200_ERR_CUDA, "rabin-karp table upload failed");
         }
-        c->rk.pos_fwd = c->d_rkpos.as<K128>(); c->rk.pos_bkw = c->d_rkpos.as<K128>() + 256;
+        c->rk.pos_fwd = c->d_rkpos.as<K128>(); c->rk.pos_bkw = c->d_rkpos.as<K128>() + RK_MAXK * 4;
     }
     if (const char *np = getenv("GGCAT_B200_NO_PARTITION")) c->no_partition = atoi(np) != 0;
     if (const char *nt = getenv("GGCAT_B200_NO_TIERS")) c->no_tiers = atoi(nt) != 0;
@@ -1362,13 +1370,14 @@ int32_t ggcat_b200_create(const ggcat_b200_params *params, ggcat_b200_ctx **out)
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, p.device) == cudaSuccess) c->sm_count = prop.multiProcessorCount;
     if (const char *hb = getenv("GGCAT_B200_HOST_BATCH")) { uint64_t v = strtoull(hb, nullptr, 10); if (v >= 1024) c->host_batch = std::min<uint64_t>(v, c->max_batch); }
+    if (const char *ps = getenv("GGCAT_B200_PART_SCHEME")) c->part_scheme = atoi(ps);
     if (const char *pk = getenv("GGCAT_B200_PART_KMERS")) { uint64_t v = strtoull(pk, nullptr, 10); if (v >= 1024) c->part_kmers = v; }
     if (const char *pk = getenv("GGCAT_B200_PART_KMERS_DEV")) { uint64_t v = strtoull(pk, nullptr, 10); if (v >= 1024) { c->part_kmers_dev = v; c->part_dev_fixed = true; } }
     c->host_batch = std::min(c->host_batch, c->max_batch);
     bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaEventCreateWithFlags(&c->ev_part, cudaEventDisableTiming) == cudaSuccess;
-    for (int i = 0; i < 2 && ok; i++)
+    for (int i = 0; i < ggcat_b200_ctx::N_STAGE && ok; i++)
         ok = cudaEventCreateWithFlags(&c->ev_h2d[i], cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&c->ev_free[i], cudaEventDisableTiming) == cudaSuccess;
     if (!ok || cudaMallocHost((void **)&c->h_pinned, 16 * 8) != cudaSuccess) {
@@ -1416,7 +1425,7 @@ void ggcat_b200_destroy(ggcat_b200_ctx *c) {
     for (cudaEvent_t e : c->event_pool) cudaEventDestroy(e);
     for (HostTable *t : c->free_tables) { t->release(); delete t; }
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < ggcat_b200_ctx::N_STAGE; i++) {
         c->st_ascii[i].release(); c->st_off[i].release(); c->st_col[i].release();
         if (c->ev_h2d[i]) cudaEventDestroy(c->ev_h2d[i]);
         if (c->ev_free[i]) cudaEventDestroy(c->ev_free[i]);
@@ -1470,9 +1479,10 @@ int32_t ggcat_b200_push_reads(ggcat_b200_ctx *c, const uint8_t *data, const uint
         batches.push_back({r0, lo});
         r0 = lo;
     }
-    // double-buffered staging: copy stream fills slot (i+1)&1 while the compute stream works on slot i&1
+    // ring of staging slots: the copy stream fills the slots of batches i+1, i+2 while the compute stream works on batch i
+    constexpr int NS = ggcat_b200_ctx::N_STAGE;
     auto issue_copy = [&](size_t bi) -> int32_t {
-        const int sl = (int)(bi & 1);
+        const int sl = (int)(bi % NS);
         const uint64_t r0 = batches[bi].first, r1 = batches[bi].second;
         const uint64_t nb = offsets[r1] - offsets[r0], nr = r1 - r0;
         CU(cudaStreamWaitEvent(c->copy_stream, c->ev_free[sl], 0));
@@ -1493,9 +1503,10 @@ int32_t ggcat_b200_push_reads(ggcat_b200_ctx *c, const uint8_t *data, const uint
     tmark(c->copy_stream);
     auto issue_copy_t = [&](size_t bi) -> int32_t { tmark(c->copy_stream); TRY(issue_copy(bi)); tmark(c->copy_stream); return 0; };
     TRY(issue_copy_t(0));
+    if (batches.size() > 1) TRY(issue_copy_t(1));
     for (size_t bi = 0; bi < batches.size(); bi++) {
-        const int sl = (int)(bi & 1);
-        if (bi + 1 < batches.size()) TRY(issue_copy_t(bi + 1));
+        const int sl = (int)(bi % NS);
+        if (bi + 2 < batches.size()) TRY(issue_copy_t(bi + 2));
         const uint64_t r0 = batches[bi].first, r1 = batches[bi].second;
         CU(cudaStreamWaitEvent(c->stream, c->ev_h2d[sl], 0));
         tmark(c->stream);
@@ -1511,7 +1522,7 @@ int32_t ggcat_b200_push_reads(ggcat_b200_ctx *c, const uint8_t *data, const uint
         cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->copy_stream);
         fprintf(stderr, "[ggcat_b200 trace] push_reads: %zu batches; ms since first copy was queued:", batches.size());
         for (size_t i = 1; i < tev.size(); i++) { float ms = 0; cudaEventElapsedTime(&ms, tev[0], tev[i]); fprintf(stderr, " %.2f", ms); }
-        fprintf(stderr, "\n  order: c0s c0e c1s c1e k0s k0e [c2s c2e k1s k1e ...]\n");
+        fprintf(stderr, "\n  order: c0s c0e c1s c1e, then per batch i: [c(i+2)s c(i+2)e] k(i)s k(i)e\n");
         for (cudaEvent_t e : tev) cudaEventDestroy(e);
     }
     return 0;
@@ -2002,7 +2013,7 @@ int32_t ggcat_b200_device_table(ggcat_b200_ctx *c, ggcat_b200_table *out) {
     const FinalTable &f = c->fin;
     if (!f.unit_off || f.n_units == 0) return set_err(GGCAT_B200_ERR_STATE, "device_table before merge_bucket_range_device");
     out->n_entries = f.n_entries; out->keys_lo = f.keys_lo; out->keys_hi = f.keys_hi; out->count_flags = f.cf;
-    out->src_kmers = f.src; out->src_kmer_words = f.src ? 2 : 0;
+    out->src_kmers = f.src; out->src_kmer_words = f.src ? c->src_words : 0;
     out->first_unit = f.first_unit; out->n_units = f.n_units; out->unit_offsets = f.unit_off;
     out->color_offsets = f.color_off; out->colors = f.colors;   // color_offsets has n_entries entries on the device (the end is n_colors)
     out->total_kmers = f.total_kmers; out->unique_kmers = f.unique_kmers;
@@ -2017,12 +2028,12 @@ static int32_t host_table_reserve(ggcat_b200_ctx *c, HostTable *t, uint64_t need
     uint64_t *nk = nullptr, *nh = nullptr, *ns = nullptr; uint32_t *nc = nullptr;
     bool ok = cudaMallocHost((void **)&nk, cap * 8) == cudaSuccess && cudaMallocHost((void **)&nc, cap * 4) == cudaSuccess;
     if (ok && wide) ok = cudaMallocHost((void **)&nh, cap * 8) == cudaSuccess;
-    if (ok && t->with_src) ok = cudaMallocHost((void **)&ns, cap * 16) == cudaSuccess;
+    if (ok && t->with_src) ok = cudaMallocHost((void **)&ns, cap * 8 * c->src_words) == cudaSuccess;
     if (!ok) { cudaFreeHost(nk); cudaFreeHost(nc); cudaFreeHost(nh); cudaFreeHost(ns); return set_err(GGCAT_B200_ERR_CUDA, "pinned table allocation failed"); }
     if (copied) {
         memcpy(nk, t->keys, copied * 8); memcpy(nc, t->cf, copied * 4);
         if (wide) memcpy(nh, t->keys_hi, copied * 8);
-        if (t->with_src) memcpy(ns, t->src, copied * 16);
+        if (t->with_src) memcpy(ns, t->src, copied * 8 * c->src_words);
     }
     cudaFreeHost(t->keys); cudaFreeHost(t->cf); cudaFreeHost(t->keys_hi); cudaFreeHost(t->src);
     t->keys = nk; t->cf = nc; t->keys_hi = nh; t->src = ns; t->cap_entries = cap;
@@ -2052,7 +2063,22 @@ int32_t ggcat_b200_merge_bucket_range(ggcat_b200_ctx *c, uint32_t first_bucket, 
     }
     std::vector<std::pair<uint32_t, uint32_t>> parts;  // (first bucket, count)
     if (colored || tot <= c->part_kmers + c->part_kmers / 2) parts.push_back({first_bucket, n_buckets});
-    else {
+    else if (c->part_scheme == 1) {
+        // The D2H copies are the critical path (the merge produces the table faster than PCIe drains it): a small first part
+        // starts the copy engine early, equal parts of ~part_kmers keep it busy, bounded by the device part size
+        const uint64_t n_eq = std::max<uint64_t>(2, (tot + c->part_kmers - 1) / c->part_kmers);
+        const uint64_t eq = std::min<uint64_t>(c->part_kmers_dev, (tot + n_eq - 1) / n_eq);
+        uint32_t b0 = 0; uint64_t acc = 0, target = std::max<uint64_t>(eq / 2, 1);
+        for (uint32_t b = 0; b < n_buckets; b++) {
+            acc += bk[b];
+            if (acc >= target || b + 1 == n_buckets) { parts.push_back({first_bucket + b0, b + 1 - b0}); b0 = b + 1; acc = 0; target = eq; }
+        }
+        if (parts.size() >= 2) {   // a tiny last part only adds a host round trip: fold it into its predecessor
+            uint64_t last = 0;
+            for (uint32_t b = parts.back().first - first_bucket; b < n_buckets; b++) last += bk[b];
+            if (last < eq / 4) { const auto lp = parts.back(); parts.pop_back(); parts.back().second += lp.second; }
+        }
+    } else {
         // shrinking parts: every part costs a fixed host round trip and only the LAST part's D2H is exposed, so the
         // first part takes half of what is left (bounded by the device part size), the last ones ~part_kmers
         uint32_t b0 = 0; uint64_t acc = 0, left = tot;
@@ -2094,7 +2120,7 @@ int32_t ggcat_b200_merge_bucket_range(ggcat_b200_ctx *c, uint32_t first_bucket, 
                 cudaError_t e1 = cudaMemcpyAsync(t->keys + eb, f.keys_lo + eb, ne * 8, cudaMemcpyDeviceToHost, c->copy_stream);
                 if (e1 == cudaSuccess) e1 = cudaMemcpyAsync(t->cf + eb, f.cf + eb, ne * 4, cudaMemcpyDeviceToHost, c->copy_stream);
                 if (e1 == cudaSuccess && wide) e1 = cudaMemcpyAsync(t->keys_hi + eb, f.keys_hi + eb, ne * 8, cudaMemcpyDeviceToHost, c->copy_stream);
-                if (e1 == cudaSuccess && with_src) e1 = cudaMemcpyAsync(t->src + 2 * eb, f.src + 2 * eb, ne * 16, cudaMemcpyDeviceToHost, c->copy_stream);
+                if (e1 == cudaSuccess && with_src) e1 = cudaMemcpyAsync(t->src + (size_t)c->src_words * eb, f.src + (size_t)c->src_words * eb, ne * 8 * c->src_words, cudaMemcpyDeviceToHost, c->copy_stream);
                 if (e1 != cudaSuccess) return fail(set_err(GGCAT_B200_ERR_CUDA, "table copy failed: %s", cudaGetErrorString(e1)));
             }
             eb += ne;
@@ -2130,7 +2156,7 @@ int32_t ggcat_b200_merge_bucket_range(ggcat_b200_ctx *c, uint32_t first_bucket, 
     CU(cudaStreamSynchronize(c->copy_stream));
     if (colored) t->color_offsets[ne] = ncol;
     out->n_entries = ne; out->keys_lo = t->keys; out->keys_hi = wide ? t->keys_hi : nullptr; out->count_flags = t->cf;
-    out->src_kmers = with_src ? t->src : nullptr; out->src_kmer_words = with_src ? 2 : 0;
+    out->src_kmers = with_src ? t->src : nullptr; out->src_kmer_words = with_src ? c->src_words : 0;
     out->first_unit = first_bucket << P.b2; out->n_units = nu; out->unit_offsets = t->unit_offsets;
     out->color_offsets = colored ? t->color_offsets : nullptr; out->colors = colored ? t->colors : nullptr;
     out->total_kmers = tk; out->unique_kmers = uq; out->opaque = t;

@@ -29,6 +29,8 @@ struct __align__(16) K128 {
 };
 
 enum { MODE_SEQ128 = 0, MODE_RK128 = 1, MODE_COLOR = 2 };
+constexpr int RK_MAXK = 128;          // rabin-karp128 k-mer lengths (seq-hash keys hold at most 64 bases)
+constexpr int SRC_MAXW = RK_MAXK / 32;  // 64-bit words of source bases per entry
 
 // Rabin-Karp tables, indexed by 2-bit base code (A0 C1 T2 G3): cn_rkhash_base.rs:10-44 + cn_rkhash.rs:69-75.
 struct RkTables {
@@ -38,8 +40,8 @@ struct RkTables {
     K128 bkw[4];        // L[c ^ 2]
     K128 fwd_mk[4];     // L[c] * M^k        (leaving base, forward hash)
     K128 bkw_mk1[4];    // L[c ^ 2] * M^(k-1) (entering base, reverse hash)
-    const K128 *pos_fwd;  // device [64][4]: L[c] * M^j       -- the first k-mer of a super-k-mer is a sum of table terms
-    const K128 *pos_bkw;  // device [64][4]: L[c ^ 2] * M^j      (k 128-bit adds instead of k 128-bit multiplies)
+    const K128 *pos_fwd;  // device [RK_MAXK][4]: L[c] * M^j       -- the first k-mer of a super-k-mer is a sum of table terms
+    const K128 *pos_bkw;  // device [RK_MAXK][4]: L[c ^ 2] * M^j      (k 128-bit adds instead of k 128-bit multiplies)
 };
 
 __host__ __device__ __forceinline__ u128 to_u128(K128 v) { return ((u128)v.hi << 64) | (u128)v.lo; }
@@ -54,8 +56,9 @@ struct MergeOut128 {
     uint32_t *unit_out_cnt;
     uint64_t capacity;            // dynamic region [0, capacity); the static regions of partitioned units follow it
     uint32_t *overflow;
-    uint64_t *src;                // MODE_RK128: packed bases of one occurrence of every surviving key, 2 words per entry
+    uint64_t *src;                // MODE_RK128: packed bases of one occurrence of every surviving key, src_words words per entry
                                   // (the hash is not invertible: the reference keeps `saved_reads` for this, hashmap.rs:32-33,96-149)
+    uint32_t src_words, pad;      // ceil(k / 32), at least 2
 };
 
 // Key partitions of big units (same scheme as merge.cuh, 128-bit keys): k_partition_units128 expands a unit once and
@@ -184,17 +187,51 @@ constexpr size_t merge_hash128_smem_bytes() {
     return (size_t)TS_STATIC * slot_bytes128<MODE>() + 64;
 }
 
-// 2k bits of a packed super-k-mer starting at base i (k <= 64), reverse-complemented when rc: the bases whose FORWARD
-// hash is the table key.
-__device__ __forceinline__ u128 kmer_bases128(const uint32_t *__restrict__ pl, uint32_t i, uint32_t k, bool rc) {
-    const uint32_t w0 = i >> 4, sh = 2u * (i & 15u), nw = (sh + 2u * k + 31u) >> 5;   // <= 5 words, all inside the super-k-mer
-    u128 x = 0;
-    for (uint32_t w = 0; w < nw && w < 4; w++) x |= (u128)pl[w0 + w] << (32u * w);
-    x >>= sh;
-    if (nw > 4 && sh) x |= (u128)pl[w0 + 4] << (128u - sh);
-    if (k < 64) x &= (((u128)1) << (2u * k)) - 1;
-    if (rc) x = revcomp128(x) >> (128u - 2u * k);
-    return x;
+// The k bases of a packed super-k-mer starting at base i, reverse-complemented when rc -- the bases whose FORWARD hash is
+// the table key -- as `nwords` (= max(2, ceil(k / 32))) 64-bit words at dst (base j at bits 2(j % 32) of word j / 32).
+__device__ __forceinline__ void kmer_bases_store(const uint32_t *__restrict__ pl, uint32_t i, uint32_t k, bool rc, uint64_t *dst,
+                                                 uint32_t nwords) {
+    const uint32_t w0 = i >> 4, sh = 2u * (i & 15u), n32 = (sh + 2u * k + 31u) >> 5;   // 32-bit words read, all inside the super-k-mer
+    uint64_t v[SRC_MAXW];
+#pragma unroll
+    for (int q = 0; q < SRC_MAXW; q++) {
+        // 64 bits starting at bit sh + 64 q of the stream pl[w0 ...]
+        const uint32_t a = 2u * q < n32 ? pl[w0 + 2u * q] : 0u, b = 2u * q + 1u < n32 ? pl[w0 + 2u * q + 1u] : 0u,
+                       c = 2u * q + 2u < n32 ? pl[w0 + 2u * q + 2u] : 0u;
+        v[q] = ((uint64_t)__funnelshift_r(b, c, sh) << 32) | (uint64_t)__funnelshift_r(a, b, sh);
+    }
+    // clear everything above 2k bits
+#pragma unroll
+    for (int q = 0; q < SRC_MAXW; q++) {
+        const uint32_t lo = 64u * q;
+        if (2u * k <= lo) v[q] = 0;
+        else if (2u * k < lo + 64u) v[q] &= (1ull << (2u * k - lo)) - 1ull;
+    }
+    if (rc) {
+        // reverse complement of the 64 SRC_MAXW-bit string, then shift right by (64 SRC_MAXW - 2k) bits
+        uint64_t r[SRC_MAXW];
+#pragma unroll
+        for (int q = 0; q < SRC_MAXW; q++) r[q] = revcomp64(v[SRC_MAXW - 1 - q]);
+        const uint32_t s = 64u * SRC_MAXW - 2u * k, sw = s >> 6, sb = s & 63u;
+#pragma unroll
+        for (int q = 0; q < SRC_MAXW; q++) {
+            const uint32_t a = q + sw, b = a + 1u;
+            uint64_t lo = 0, hi = 0;
+#pragma unroll
+            for (int t = 0; t < SRC_MAXW; t++) { if ((uint32_t)t == a) lo = r[t]; if ((uint32_t)t == b) hi = r[t]; }
+            v[q] = sb ? ((lo >> sb) | (hi << (64u - sb))) : lo;
+        }
+        // revcomp64 complements the padding too: clear above 2k bits again
+#pragma unroll
+        for (int q = 0; q < SRC_MAXW; q++) {
+            const uint32_t lo = 64u * q;
+            if (2u * k <= lo) v[q] = 0;
+            else if (2u * k < lo + 64u) v[q] &= (1ull << (2u * k - lo)) - 1ull;
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < SRC_MAXW; q++)
+        if ((uint32_t)q < nwords) dst[q] = v[q];
 }
 
 // TS_STATIC > 0: table in shared memory (units with <= 3/4 TS_STATIC records).  TS_STATIC == 0: table in this CTA's
@@ -339,8 +376,8 @@ k_merge_hash128(const ChunkView *__restrict__ chunks, uint32_t n_chunks, const u
                     out.count_flags[gbase] = MODE == MODE_COLOR ? cc : (mult | (fl << 30));
                     if (WITH_SRC) {
                         const unsigned long long loc = s_special_src;
-                        const u128 b = kmer_bases128(chunks[loc >> 49].payload + (uint32_t)loc, (uint32_t)(loc >> 32) & 0xFFFFu, P.k, (loc >> 48) & 1u);
-                        out.src[2 * gbase] = (uint64_t)b; out.src[2 * gbase + 1] = (uint64_t)(b >> 64);
+                        kmer_bases_store(chunks[loc >> 49].payload + (uint32_t)loc, (uint32_t)(loc >> 32) & 0xFFFFu, P.k, (loc >> 48) & 1u,
+                                         out.src + (size_t)out.src_words * gbase, out.src_words);
                     }
                     first = 1;
                 }
@@ -376,8 +413,8 @@ k_merge_hash128(const ChunkView *__restrict__ chunks, uint32_t n_chunks, const u
                     out.keys_lo[o] = kk.lo; out.keys_hi[o] = kk.hi; out.count_flags[o] = cf;
                     if (WITH_SRC) {
                         const uint64_t loc = L[i];
-                        const u128 b = kmer_bases128(chunks[loc >> 49].payload + (uint32_t)loc, (uint32_t)(loc >> 32) & 0xFFFFu, P.k, (loc >> 48) & 1u);
-                        out.src[2 * o] = (uint64_t)b; out.src[2 * o + 1] = (uint64_t)(b >> 64);
+                        kmer_bases_store(chunks[loc >> 49].payload + (uint32_t)loc, (uint32_t)(loc >> 32) & 0xFFFFu, P.k, (loc >> 48) & 1u,
+                                         out.src + (size_t)out.src_words * o, out.src_words);
                     }
                 }
             }
@@ -527,7 +564,7 @@ k_sort_units128(uint64_t *__restrict__ src_lo, uint64_t *__restrict__ src_hi, ui
                 const uint64_t *__restrict__ unit_final_off, uint64_t *__restrict__ dst_lo, uint64_t *__restrict__ dst_hi,
                 uint32_t *__restrict__ dst_cf, uint32_t n_units, uint32_t first_bit, uint32_t end_bit, uint64_t capacity,
                 uint32_t *__restrict__ overflow, const uint64_t *__restrict__ src_bases, uint64_t *__restrict__ dst_bases,
-                uint32_t *__restrict__ idx_a, uint32_t *__restrict__ idx_b) {
+                uint32_t *__restrict__ idx_a, uint32_t *__restrict__ idx_b, uint32_t src_words) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     if (unit_final_off[n_units] > capacity) {   // the host enlarges the final table and launches the sort again
         if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(overflow, 4u);
@@ -555,7 +592,7 @@ k_sort_units128(uint64_t *__restrict__ src_lo, uint64_t *__restrict__ src_hi, ui
                 if (WITH_SRC) {
                     const uint64_t j = so + rv[i];
                     dst_cf[fo + i] = src_cf[j];
-                    dst_bases[2 * (fo + i)] = src_bases[2 * j]; dst_bases[2 * (fo + i) + 1] = src_bases[2 * j + 1];
+                    for (uint32_t q = 0; q < src_words; q++) dst_bases[(size_t)src_words * (fo + i) + q] = src_bases[(size_t)src_words * j + q];
                 } else dst_cf[fo + i] = rv[i];
             }
         } else if (WITH_SRC) {
@@ -568,7 +605,7 @@ k_sort_units128(uint64_t *__restrict__ src_lo, uint64_t *__restrict__ src_hi, ui
                 if (w == 0) { dst_lo[fo + i] = src_lo[so + i]; dst_hi[fo + i] = src_hi[so + i]; }
                 const uint64_t j = so + rv[i];
                 dst_cf[fo + i] = src_cf[j];
-                dst_bases[2 * (fo + i)] = src_bases[2 * j]; dst_bases[2 * (fo + i) + 1] = src_bases[2 * j + 1];
+                for (uint32_t q = 0; q < src_words; q++) dst_bases[(size_t)src_words * (fo + i) + q] = src_bases[(size_t)src_words * j + q];
             }
         } else {
             const int w = block_radix_sort128<THREADS>(src_lo + so, src_hi + so, src_cf + so, dst_lo + fo, dst_hi + fo, dst_cf + fo,

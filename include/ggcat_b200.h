@@ -42,13 +42,13 @@ typedef enum { GGCAT_B200_HASH_AUTO = 0, GGCAT_B200_HASH_SEQ = 1, GGCAT_B200_HAS
 /* The knobs of `ggcat build` that reach the hot path (crates/cmdline/src/main.rs:148-242,
  * crates/api/src/lib.rs:75-99): -k, --minimizer-length, -s, -b, -f, -w, -c. */
 typedef struct {
-    uint32_t k;                        /* k-mer length, 4 <= k <= 64 (k <= 31: 64-bit keys; else 128-bit keys) */
+    uint32_t k;                        /* k-mer length, 4 <= k <= 128 (odd k <= 31: 64-bit keys; else 128-bit keys; k > 64: rabin-karp128 only) */
     uint32_t m;                        /* minimizer length, 0 = compute_best_m(k) (crates/utils/src/lib.rs:29-40) */
     uint32_t min_multiplicity;         /* -s */
     uint32_t buckets_count_log;        /* first-level buckets = 1 << this (+1 duplicates bucket) */
     uint32_t second_buckets_count_log; /* sub-buckets per bucket = 1 << this (<= 8) */
     uint32_t forward_only;             /* -f */
-    uint32_t hash_type;                /* ggcat_b200_hash_type; AUTO = seq-hash (crates/api/src/utils.rs:17-26 for k <= 64) */
+    uint32_t hash_type;                /* ggcat_b200_hash_type; AUTO = seq-hash for k <= 64, rabin-karp128 above (crates/api/src/utils.rs:17-26) */
     uint32_t colors;                   /* -c : carry a colour id per record (seq-hash, k <= 48) */
     int32_t device;                    /* CUDA device ordinal */
     uint32_t reserved[7];
@@ -103,8 +103,9 @@ typedef struct {
     /* Non-invertible keys (rabin-karp128): the bases of one occurrence of every entry, so that the consumer can rebuild
      * sequence from a hash -- the role of the reference's `saved_reads` + `encoded_saved_reads_indexes`
      * (crates/assembler_kmers_merge/src/unitigs_extender/hashmap.rs:32-33,96-149 get_kmers, :413-431 add_sequence).
-     * Entry e owns words [e * src_kmer_words, (e + 1) * src_kmer_words); base j of the k-mer sits at bits 2(j % 32) of word
-     * j / 32 (A0 C1 T2 G3), in the orientation whose FORWARD hash equals the key.  NULL / 0 for invertible keys (seq-hash). */
+     * Entry e owns words [e * src_kmer_words, (e + 1) * src_kmer_words), src_kmer_words = max(2, ceil(k / 32)); base j of
+     * the k-mer sits at bits 2(j % 32) of word j / 32 (A0 C1 T2 G3), in the orientation whose FORWARD hash equals the key.
+     * NULL / 0 for invertible keys (seq-hash). */
     const uint64_t *src_kmers;
     uint32_t src_kmer_words;
     uint32_t reserved0;
@@ -130,7 +131,7 @@ void ggcat_b200_host_free(void *p);
  * (crates/io/src/sequences_reader.rs:106-179).  colors: one id per record or NULL.
  * The batch is normalised, N-split, hashed, split into super-k-mers and scattered into
  * device-resident buckets.  May be called repeatedly and from several host threads (calls are serialised on the
- * context); each call appends ONE bucket chunk: the host input travels in double-buffered H2D batches of <= 48 MB
+ * context); each call appends ONE bucket chunk: the host input travels through a ring of three H2D staging batches of <= 24 MB
  * (GGCAT_B200_HOST_BATCH) whose kernels overlap the next copy, and the batches of a call are scattered together. */
 int32_t ggcat_b200_push_reads(ggcat_b200_ctx *ctx, const uint8_t *data, const uint64_t *offsets, uint64_t n_reads,
                               const uint32_t *colors);

@@ -53,7 +53,7 @@ def _check_src_kmers(tab, sl, k, hash_type, limit=64):
     if hash_type != O.HASH_RK128:
         assert tab.src_kmers is None
         return
-    assert tab.src_kmers is not None and tab.src_kmers.shape == (tab.keys_lo.size, 2)
+    assert tab.src_kmers is not None and tab.src_kmers.shape == (tab.keys_lo.size, max(2, (k + 31) // 32))
     idx = list(range(sl.start, sl.stop))
     if len(idx) > limit:
         idx = idx[:: max(1, len(idx) // limit)]
@@ -61,8 +61,8 @@ def _check_src_kmers(tab, sl, k, hash_type, limit=64):
         seq = tab.src_kmer(e, k)
         lo, hi, _ = O.kmer_hashes(seq, k, O.HASH_RK128, True)
         assert (int(lo[0]), int(hi[0])) == (int(tab.keys_lo[e]), int(tab.keys_hi[e])), f"entry {e}: source bases {seq} do not hash to the key"
-        w0, w1 = int(tab.src_kmers[e][0]), int(tab.src_kmers[e][1])
-        assert ((w1 << 64) | w0) >> (2 * k) == 0, "bits above the k-mer must be clear"
+        full = sum(int(w) << (64 * q) for q, w in enumerate(tab.src_kmers[e]))
+        assert full >> (2 * k) == 0, "bits above the k-mer must be clear"
 
 
 def _check_tables(G, ctx, reads, sk, k, s, b1, b2, forward_only=False, ranges=None, hash_type=O.HASH_SEQ, colors=False):
@@ -463,6 +463,12 @@ def test_c2_full_size_properties():
     (32, 12, 2, 1, False, 2, O.HASH_SEQ),      # even k: 64-bit key needs the wide path (no room for flag bits)
     (64, 14, 1, 1, True, 1, O.HASH_SEQ),
     (47, 13, 2, 3, True, 3, O.HASH_SEQ),
+    (65, 16, 2, 1, False, 1, O.HASH_RK128),    # k > 64: the reference switches to rabin-karp128 (crates/api/src/utils.rs:17-26)
+    (67, 17, 2, 2, False, 2, O.HASH_RK128),    # k - 2 > 64: window validity spans two bitmap words
+    (96, 24, 2, 2, False, 2, O.HASH_RK128),
+    (101, 12, 1, 2, False, 1, O.HASH_RK128),   # k - m = 89 m-mers per window
+    (127, 32, 2, 1, True, 1, O.HASH_RK128),
+    (128, 32, 1, 1, False, 1, O.HASH_RK128),
 ])
 def test_wide_keys(k, m, b1, b2, fo, s, ht):
     """128-bit key path: seq-hash u128 and rabin-karp128, forward-only and canonical."""
@@ -505,7 +511,8 @@ def test_wide_unit_size_paths(n_bases, ht):
             ctx.close()
 
 
-@pytest.mark.parametrize("k,ht,s", [(63, O.HASH_RK128, 1), (63, O.HASH_RK128, 2), (41, O.HASH_SEQ, 2), (64, O.HASH_SEQ, 40)])
+@pytest.mark.parametrize("k,ht,s", [(63, O.HASH_RK128, 1), (63, O.HASH_RK128, 2), (41, O.HASH_SEQ, 2), (64, O.HASH_SEQ, 40),
+                                    (97, O.HASH_RK128, 1), (128, O.HASH_RK128, 2)])
 def test_wide_key_partitions_and_overflow_fallback(k, ht, s):
     """Wide path, units above the shared-table capacity: key partitions in HBM (k_partition_units128 ->
     k_merge_hash128<SRC_RECORDS>, survivors of all partitions contiguous in the unit's static region).  A tandem
@@ -725,7 +732,10 @@ def test_error_behaviour():
     with pytest.raises(G.GgcatB200Error):
         G.GGCATB200(G.Params(k=3))
     with pytest.raises(G.GgcatB200Error):
-        G.GGCATB200(G.Params(k=65))
+        G.GGCATB200(G.Params(k=129))
+    with pytest.raises(G.GgcatB200Error):
+        G.GGCATB200(G.Params(k=65, hash_type=O.HASH_SEQ))     # seq-hash keys hold at most 64 bases
+    G.GGCATB200(G.Params(k=65)).close()                       # AUTO -> rabin-karp128 above 64 (crates/api/src/utils.rs:17-26)
     with pytest.raises(G.GgcatB200Error):
         G.GGCATB200(G.Params(k=63, colors=True))
     with pytest.raises(G.GgcatB200Error):
