@@ -75,6 +75,8 @@ SYMBOLS = {
     "ggcat_b200_host_free": (None, [_vp]),
     "ggcat_b200_push_reads": (_i32, [_vp, _vp, _vp, _u64, _vp]),
     "ggcat_b200_push_reads_device": (_i32, [_vp, _vp, _vp, _u64, _u64, _vp]),
+    "ggcat_b200_push_reads_packed": (_i32, [_vp, _vp, _vp, _u64, _vp]),
+    "ggcat_b200_push_reads_packed_device": (_i32, [_vp, _vp, _vp, _u64, _u64, _vp]),
     "ggcat_b200_push_text": (_i32, [_vp, _vp, _u64, _i32, _u32, C.POINTER(_u64)]),
     "ggcat_b200_push_text_device": (_i32, [_vp, _vp, _u64, _i32, _u32, C.POINTER(_u64)]),
     "ggcat_b200_tokenize_device": (_i32, [_vp, _vp, _u64, _i32, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_u64), C.POINTER(_u64)]),

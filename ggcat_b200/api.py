@@ -188,6 +188,23 @@ class GGCATB200:
         """Host pointers (e.g. pinned buffers) without numpy wrapping."""
         _check(self._lib.ggcat_b200_push_reads(self._h, data_ptr, offsets_ptr, n_reads, colors_ptr))
 
+    def push_reads_packed(self, packed: np.ndarray, offsets: np.ndarray, colors: Optional[np.ndarray] = None):
+        """2-bit packed reads: one contiguous stream (base i at bits 2(i % 4) of byte i // 4), offsets in BASES."""
+        packed = np.ascontiguousarray(packed, np.uint8)
+        offsets = np.ascontiguousarray(offsets, np.uint64)
+        cp = None
+        if colors is not None:
+            colors = np.ascontiguousarray(colors, np.uint32)
+            cp = colors.ctypes.data
+        _check(self._lib.ggcat_b200_push_reads_packed(self._h, packed.ctypes.data, offsets.ctypes.data, offsets.size - 1, cp))
+
+    def push_reads_packed_ptr(self, packed_ptr: int, offsets_ptr: int, n_reads: int, colors_ptr: Optional[int] = None):
+        _check(self._lib.ggcat_b200_push_reads_packed(self._h, packed_ptr, offsets_ptr, n_reads, colors_ptr))
+
+    def push_reads_packed_device(self, d_packed_ptr: int, d_offsets_ptr: int, n_reads: int, n_bases: int,
+                                 d_colors_ptr: Optional[int] = None):
+        _check(self._lib.ggcat_b200_push_reads_packed_device(self._h, d_packed_ptr, d_offsets_ptr, n_reads, n_bases, d_colors_ptr))
+
     def push_reads_device(self, d_data_ptr: int, d_offsets_ptr: int, n_reads: int, n_bytes: int,
                           d_colors_ptr: Optional[int] = None):
         _check(self._lib.ggcat_b200_push_reads_device(self._h, d_data_ptr, d_offsets_ptr, n_reads, n_bytes, d_colors_ptr))

@@ -46,8 +46,8 @@ constexpr int WIN_NB = WIN_TPC > 1 ? 2 : 1; // landing buffers
 #define GGB_WIN_MINB 9
 #endif
 constexpr int WIN_MINB = GGB_WIN_MINB;      // resident CTAs per SM the register allocation must allow
-constexpr int WIN_WMAX = 128;     // max supported k - m (k <= 128)
-constexpr int WIN_NI = WIN_T + WIN_WMAX;  // m-mer items per tile (upper bound)
+constexpr int WIN_GROUP = 64;     // tiles per group of the two-level super-k-mer prefix (k_windows -> group scan -> k_emit)
+constexpr int WIN_WMAX = 128;     // max supported k - m (k <= 128); k_windows<64> serves k - m <= 64, k <= 66 with smaller buffers
 #define PADX(x) ((x) + ((x) >> 3))
 
 // entry bit layout (u64)
@@ -110,6 +110,29 @@ __global__ void __launch_bounds__(256) k_pack(const uint8_t *__restrict__ ascii,
     bad[g] = bd;
 }
 
+// k_repack: 2-bit packed input (the reference's CompressedRead layout, crates/io/src/compressed_read.rs:610-618: base i at
+// bits 2(i % 4) of byte i / 4) -> this batch's pk / bad.  The batch starts `shift` bases into the first source word; one
+// thread per 32 bases.  Packed input has no code for N (the host splits at N before packing, as the reference does), so
+// only the positions >= n are bad.
+__global__ void __launch_bounds__(256) k_repack(const uint32_t *__restrict__ src, uint32_t shift, uint64_t n, uint32_t *__restrict__ pk,
+                                                uint32_t *__restrict__ bad, uint64_t n_groups, uint64_t src_words) {
+    const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_groups) return;
+    const uint64_t base = g * 32;
+    uint32_t w0 = 0, w1 = 0, bd = 0xFFFFFFFFu;
+    if (base < n) {
+        const uint64_t bit = 2ull * (base + shift), w = bit >> 5;
+        const uint32_t sh = (uint32_t)bit & 31u;
+        const uint32_t a = w < src_words ? src[w] : 0u, b = w + 1 < src_words ? src[w + 1] : 0u, c = w + 2 < src_words ? src[w + 2] : 0u;
+        w0 = __funnelshift_r(a, b, sh); w1 = __funnelshift_r(b, c, sh);
+        const uint64_t left = n - base;          // valid bases in this group
+        bd = left >= 32 ? 0u : (0xFFFFFFFFu << (uint32_t)left);
+        if (left < 16) { w0 &= (1u << (2 * (uint32_t)left)) - 1u; w1 = 0; }
+        else if (left < 32) w1 &= left == 16 ? 0u : ((1u << (2 * ((uint32_t)left - 16))) - 1u);
+    }
+    pk[2 * g] = w0; pk[2 * g + 1] = w1; bad[g] = bd;
+}
+
 // k_mark: a record boundary is a segment boundary (each input record is processed independently,
 // crates/minimizer_bucketing/src/lib.rs:310-320).
 __global__ void k_mark(const uint64_t *__restrict__ offsets, uint64_t n_reads, uint64_t off0, uint64_t n,
@@ -147,13 +170,16 @@ __device__ __forceinline__ uint64_t bits64(const uint32_t *bm, uint32_t s, uint3
 //   D  M_x = comb(suffix[x], prefix[x+w-1])
 //   E  split-start / segment-end flags, F in-order compaction (one block scan) + bucket / orientation / minimizer offset
 //      of every super-k-mer start from the (minimum, argmin) pair its thread holds in registers, G copy-out
+template <int WMAX>
 __global__ void __launch_bounds__(WIN_THREADS, WIN_MINB)
 k_windows(const uint32_t *__restrict__ pk, const uint32_t *__restrict__ bad, const uint32_t *__restrict__ brk,
           uint32_t n /* bases in batch */, DevParams P, uint64_t *__restrict__ ent, uint32_t *__restrict__ tile_cnt,
-          uint32_t *__restrict__ tile_scnt, uint32_t *__restrict__ seg_count, uint32_t n_tiles) {
+          uint32_t *__restrict__ tile_scnt, uint32_t *__restrict__ seg_count, uint32_t n_tiles,
+          uint32_t *__restrict__ group_scnt /* super-k-mers per group of WIN_GROUP tiles (zeroed by the host) */) {
     // TMA landing buffers (16-byte aligned; the tile's first word sits at offset (W0 & 3) / (BW0 & 3) because the
     // bulk copy starts at the 16-byte boundary below it)
-    constexpr int PKW = (((WIN_T + 2 * WIN_WMAX + 64) / 16 + 12) + 3) & ~3, BMW = (((WIN_T + 2 * WIN_WMAX + 64) / 32 + 12) + 3) & ~3;
+    constexpr int WIN_NI = WIN_T + WMAX;  // m-mer items per tile (upper bound)
+    constexpr int PKW = (((WIN_T + 2 * WMAX + 64) / 16 + 12) + 3) & ~3, BMW = (((WIN_T + 2 * WMAX + 64) / 32 + 12) + 3) & ~3;
     __shared__ __align__(16) uint32_t s_pk_all[WIN_NB][PKW];
     __shared__ __align__(16) uint32_t s_bad_all[WIN_NB][BMW];
     __shared__ __align__(16) uint32_t s_cmb_all[WIN_NB][BMW];   // record starts, then bad | record-start
@@ -333,7 +359,7 @@ k_windows(const uint32_t *__restrict__ pk, const uint32_t *__restrict__ bad, con
             const bool ok = j >= 0 && (uint64_t)j + (k - 1) <= (uint64_t)n && bd == 0 && (bits & kmask) == 0;
             ok10 |= (ok ? 1u : 0u) << i;
         }
-        if (k > 66) {   // (block-uniform) the k-2 positions behind a window start span a second 64-bit word
+        if (WMAX > 64 && k > 66) {   // (block-uniform) the k-2 positions behind a window start span a second 64-bit word
             const uint64_t cx = extract64(s_cmb, rel + 128);
             const uint64_t kmask2 = (1ull << (k - 66)) - 1ull;      // k <= 128
 #pragma unroll
@@ -410,7 +436,10 @@ k_windows(const uint32_t *__restrict__ pk, const uint32_t *__restrict__ bad, con
         }
         ent[(uint64_t)tile * WIN_T + i] = e;
     }
-    if (tid == 0) { tile_cnt[tile] = n_ent; tile_scnt[tile] = n_s; }
+    if (tid == 0) {
+        tile_cnt[tile] = n_ent; tile_scnt[tile] = n_s;
+        if (n_s) atomicAdd(&group_scnt[tile / WIN_GROUP], n_s);   // the host scans the groups (n_tiles / 64 values), k_emit finishes the prefix
+    }
     if (WIN_TPC > 1) __syncthreads();     // s_v0 / s_fwd / s_ent are rewritten by the next tile
     }   // tiles of this CTA
     if (tid == 0 && s_nfirst) atomicAdd(seg_count, s_nfirst);     // SequencesSplitter::valid_bases bookkeeping (one atomic per CTA)
@@ -450,13 +479,27 @@ __global__ void __launch_bounds__(1024) k_exclusive_scan_u32(const uint32_t *in,
 // k_emit: entry -> super-k-mer descriptor in position order + per-unit histogram.
 // tmp descriptor: {start (position in the chunk's packed bases), len, meta, unit}.
 __global__ void __launch_bounds__(256)
-k_emit(const uint64_t *__restrict__ ent, const uint32_t *__restrict__ tile_cnt, const uint32_t *__restrict__ tile_sbase,
-       uint32_t n_tiles, DevParams P, uint4 *__restrict__ tmp, uint32_t *__restrict__ tmp_color,
+k_emit(const uint64_t *__restrict__ ent, const uint32_t *__restrict__ tile_cnt, const uint32_t *__restrict__ tile_scnt,
+       const uint32_t *__restrict__ group_sbase, uint32_t n_tiles, DevParams P, uint4 *__restrict__ tmp, uint32_t *__restrict__ tmp_color,
        uint32_t base /* position of the batch's first base inside the chunk's packed bases */,
        const uint64_t *__restrict__ offsets, uint64_t n_reads, uint64_t off0, const uint32_t *__restrict__ colors,
        uint32_t *__restrict__ unit_cnt, uint32_t *__restrict__ unit_words, uint32_t *__restrict__ unit_kmers) {
     const uint32_t tile = blockIdx.x;
     const uint32_t cnt = tile_cnt[tile];
+    if (cnt == 0) return;
+    // first super-k-mer of the tile = scanned total of the groups before + the tiles of this group before this one
+    __shared__ uint32_t s_sbase;
+    if (threadIdx.x < 32) {
+        const uint32_t g0 = (tile / WIN_GROUP) * WIN_GROUP, l = threadIdx.x;
+        uint32_t v = 0;
+#pragma unroll
+        for (int q = 0; q < WIN_GROUP / 32; q++) { const uint32_t t = g0 + l + 32u * q; if (t < tile) v += tile_scnt[t]; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (l == 0) s_sbase = group_sbase[tile / WIN_GROUP] + v;
+    }
+    __syncthreads();
+    const uint32_t tile_first_sk = s_sbase;
     const uint32_t posmask = (1u << ENT_POS_BITS) - 1;
     for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) {
         const uint64_t e = ent[(uint64_t)tile * WIN_T + i];
@@ -489,7 +532,7 @@ k_emit(const uint64_t *__restrict__ ent, const uint32_t *__restrict__ tile_cnt, 
         const uint32_t second = (uint32_t)(e >> ENT_SECOND_SHIFT) & 0xFFu;
         const uint32_t bucket = (uint32_t)(e >> ENT_BUCKET_SHIFT) & 0x3FFFu;
         const uint32_t unit = (bucket << P.b2) | second;
-        const uint32_t idx = tile_sbase[tile] + (uint32_t)((e >> ENT_SRANK_SHIFT) & 0xFFFFu);
+        const uint32_t idx = tile_first_sk + (uint32_t)((e >> ENT_SRANK_SHIFT) & 0xFFFFu);
         tmp[idx] = make_uint4(base + start, len, make_meta(mpos, flags, rc, second), unit);
         if (P.colors) {
             // record index = last r with offsets[r] <= start

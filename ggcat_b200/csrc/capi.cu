@@ -179,7 +179,7 @@ struct ggcat_b200_ctx {
     FinalTable fin;
     ggcat_b200_bucket_stats stats;
     // phase-1 workspace
-    DevBuf d_ascii, d_offsets, d_colors, pk, bad, brk, ent, tile_cnt, tile_sbase, tmp, tmp_color, cur_cnt, totals;
+    DevBuf d_ascii, d_offsets, d_colors, pk, bad, brk, ent, tile_cnt, tile_sbase, tile_group, tmp, tmp_color, cur_cnt, totals;
     std::vector<Chunk *> chunks;
     std::vector<Chunk *> chunk_pool;  // recycled local chunks (device buffers kept)
     Chunk *open_chunk = nullptr;      // chunk the batches of the current push accumulate into (closed by flush_open_chunk)
@@ -295,8 +295,10 @@ void abort_open_chunk(ggcat_b200_ctx *c) {   // an error in the middle of a push
 // one push call); flush_open_chunk() scatters them into ONE unit-sorted bucket chunk, so a push of any size makes one
 // chunk -- one slice per unit and source in the merge and in the exchange -- while the H2D copy of the next batch still
 // overlaps everything but that final scatter.  `reserve_bases`: bases the whole push will bring (sizes the buffers once).
+// packed_shift < 0: d_data holds n ASCII bases.  packed_shift = 0..15: d_data (4-byte aligned) is a 2-bit packed stream whose
+// base number packed_shift is the batch's first base (ggcat_b200_push_reads_packed).
 int32_t bucket_batch_device(ggcat_b200_ctx *c, const uint8_t *d_data, const uint64_t *d_offsets, uint64_t n_reads,
-                            uint64_t off0, uint64_t n, const uint32_t *d_colors, uint64_t reserve_bases) {
+                            uint64_t off0, uint64_t n, const uint32_t *d_colors, uint64_t reserve_bases, int packed_shift = -1) {
     const DevParams &P = c->P;
     cudaStream_t st = c->stream;
     if (n >= (1ull << 31)) return set_err(GGCAT_B200_ERR_INVALID, "batch of %llu bases exceeds 2^31", (unsigned long long)n);
@@ -345,23 +347,32 @@ int32_t bucket_batch_device(ggcat_b200_ctx *c, const uint8_t *d_data, const uint
     {
         LaunchTimer t(c, F_PACK, 2);
         const int aligned = ((uintptr_t)d_data & 15) == 0;
-        k_pack<<<(unsigned)((n_groups + 255) / 256), 256, 0, st>>>(d_data, n, pkb, c->bad.as<uint32_t>(), n_groups, aligned);
+        if (packed_shift >= 0)
+            k_repack<<<(unsigned)((n_groups + 255) / 256), 256, 0, st>>>(reinterpret_cast<const uint32_t *>(d_data), (uint32_t)packed_shift, n, pkb,
+                                                                          c->bad.as<uint32_t>(), n_groups, (2 * (n + packed_shift) + 31) / 32);
+        else
+            k_pack<<<(unsigned)((n_groups + 255) / 256), 256, 0, st>>>(d_data, n, pkb, c->bad.as<uint32_t>(), n_groups, aligned);
         k_mark<<<(unsigned)((n_reads + 255) / 256), 256, 0, st>>>(d_offsets, n_reads, off0, n, c->brk.as<uint32_t>());
     }
     CU(c->ent.reserve((uint64_t)n_tiles * WIN_T * 8));
     CU(c->tile_cnt.reserve(((uint64_t)n_tiles + 2) * 4));
     CU(c->tile_sbase.reserve(((uint64_t)n_tiles + 2) * 4));
+    const uint32_t n_tgroups = (n_tiles + WIN_GROUP - 1) / WIN_GROUP;
+    CU(c->tile_group.reserve(((uint64_t)n_tgroups + 2) * 4));
+    CU(cudaMemsetAsync(c->tile_group.p, 0, ((uint64_t)n_tgroups + 2) * 4, st));
     {
         LaunchTimer t(c, F_WINDOWS);
-        k_windows<<<(n_tiles + WIN_TPC - 1) / WIN_TPC, WIN_THREADS, 0, st>>>(pkb, c->bad.as<uint32_t>(), c->brk.as<uint32_t>(),
+        auto kwin = (P.w <= 64 && P.k <= 66) ? k_windows<64> : k_windows<WIN_WMAX>;
+        kwin<<<(n_tiles + WIN_TPC - 1) / WIN_TPC, WIN_THREADS, 0, st>>>(pkb, c->bad.as<uint32_t>(), c->brk.as<uint32_t>(),
                                                    (uint32_t)n, P, c->ent.as<uint64_t>(), c->tile_cnt.as<uint32_t>(),
                                                    c->tile_sbase.as<uint32_t>(), ch->unit_cnt.as<uint32_t>() + P.n_units /* spare slot: segments */,
-                                                   n_tiles);
+                                                   n_tiles, c->tile_group.as<uint32_t>());
     }
     CU(c->totals.reserve(8 * 8));
     {
         LaunchTimer t(c, F_SCAN);
-        k_exclusive_scan_u32<<<1, 1024, 0, st>>>(c->tile_sbase.as<uint32_t>(), c->tile_sbase.as<uint32_t>(), n_tiles,
+        // two-level prefix: only the per-group totals are scanned here (n_tiles / 64 values, one pass of one CTA)
+        k_exclusive_scan_u32<<<1, 1024, 0, st>>>(c->tile_group.as<uint32_t>(), c->tile_group.as<uint32_t>(), n_tgroups,
                                                  c->totals.as<unsigned long long>());
     }
     CU(cudaMemcpyAsync(c->h_pinned, c->totals.p, 8, cudaMemcpyDeviceToHost, st));
@@ -375,7 +386,7 @@ int32_t bucket_batch_device(ggcat_b200_ctx *c, const uint8_t *d_data, const uint
     {
         LaunchTimer t(c, F_EMIT);
         k_emit<<<n_tiles, 256, 0, st>>>(c->ent.as<uint64_t>(), c->tile_cnt.as<uint32_t>(), c->tile_sbase.as<uint32_t>(),
-                                        n_tiles, P, c->tmp.as<uint4>() + c->open_sk, c->tmp_color.as<uint32_t>() + c->open_sk, (uint32_t)base,
+                                        c->tile_group.as<uint32_t>(), n_tiles, P, c->tmp.as<uint4>() + c->open_sk, c->tmp_color.as<uint32_t>() + c->open_sk, (uint32_t)base,
                                         d_offsets, n_reads, off0, d_colors, ch->unit_cnt.as<uint32_t>(), ch->unit_words.as<uint32_t>(),
                                         ch->unit_kmers.as<uint32_t>());
     }
@@ -1413,7 +1424,7 @@ void ggcat_b200_destroy(ggcat_b200_ctx *c) {
     for (Chunk *ch : c->chunk_pool) { ch->release(); delete ch; }
     c->chunk_pool.clear();
     collect_timings(c);
-    for (DevBuf *b : {&c->d_ascii, &c->d_offsets, &c->d_colors, &c->pk, &c->bad, &c->brk, &c->ent, &c->tile_cnt, &c->tile_sbase,
+    for (DevBuf *b : {&c->d_ascii, &c->d_offsets, &c->d_colors, &c->pk, &c->bad, &c->brk, &c->ent, &c->tile_cnt, &c->tile_sbase, &c->tile_group,
                       &c->tmp, &c->tmp_color, &c->cur_cnt, &c->totals, &c->d_views, &c->d_work[0], &c->d_work[1],
                       &c->d_work[2], &c->d_scratch, &c->out_keys, &c->out_cf, &c->out_keys2, &c->out_cf2,
                       &c->d_rkpos, &c->d_recfl, &c->d_mstage, &c->d_static_off, &c->cursor, &c->unit_out_off, &c->unit_out_cnt, &c->unit_final_off, &c->overflow, &c->d_retry,
@@ -1450,8 +1461,20 @@ void ggcat_b200_destroy(ggcat_b200_ctx *c) {
     delete c;
 }
 
+static int32_t push_reads_host(ggcat_b200_ctx *c, const uint8_t *data, const uint64_t *offsets, uint64_t n_reads,
+                               const uint32_t *colors, bool packed);
 int32_t ggcat_b200_push_reads(ggcat_b200_ctx *c, const uint8_t *data, const uint64_t *offsets, uint64_t n_reads,
                               const uint32_t *colors) {
+    return push_reads_host(c, data, offsets, n_reads, colors, false);
+}
+int32_t ggcat_b200_push_reads_packed(ggcat_b200_ctx *c, const uint8_t *packed, const uint64_t *offsets, uint64_t n_reads,
+                                     const uint32_t *colors) {
+    return push_reads_host(c, packed, offsets, n_reads, colors, true);
+}
+// packed: `data` is one contiguous 2-bit stream and offsets count BASES; a batch of records [r0, r1) travels as the bytes
+// [offsets[r0] / 4, ceil(offsets[r1] / 4)) and starts offsets[r0] % 4 bases into its first byte.
+static int32_t push_reads_host(ggcat_b200_ctx *c, const uint8_t *data, const uint64_t *offsets, uint64_t n_reads,
+                               const uint32_t *colors, bool packed) {
     TRY(check_ctx(c));
     std::lock_guard<std::mutex> lock__(c->mu);
     if (c->finished) return set_err(GGCAT_B200_ERR_STATE, "push_reads after finish_bucketing");
@@ -1488,6 +1511,10 @@ int32_t ggcat_b200_push_reads(ggcat_b200_ctx *c, const uint8_t *data, const uint
         CU(cudaStreamWaitEvent(c->copy_stream, c->ev_free[sl], 0));
         CU(c->st_ascii[sl].reserve(nb + 64));
         CU(c->st_off[sl].reserve((nr + 1) * 8));
+        if (packed) {
+            const uint64_t b0 = offsets[r0] >> 2, b1 = (offsets[r1] + 3) >> 2;
+            CU(cudaMemcpyAsync(c->st_ascii[sl].p, data + b0, b1 - b0, cudaMemcpyHostToDevice, c->copy_stream));
+        } else
         CU(cudaMemcpyAsync(c->st_ascii[sl].p, data + offsets[r0], nb, cudaMemcpyHostToDevice, c->copy_stream));
         CU(cudaMemcpyAsync(c->st_off[sl].p, offsets + r0, (nr + 1) * 8, cudaMemcpyHostToDevice, c->copy_stream));
         if (colors) {
@@ -1512,7 +1539,7 @@ int32_t ggcat_b200_push_reads(ggcat_b200_ctx *c, const uint8_t *data, const uint
         tmark(c->stream);
         int32_t rc = bucket_batch_device(c, c->st_ascii[sl].as<uint8_t>(), c->st_off[sl].as<uint64_t>(), r1 - r0, offsets[r0],
                                          offsets[r1] - offsets[r0], colors ? c->st_col[sl].as<uint32_t>() : nullptr,
-                                         offsets[n_reads] - offsets[0]);
+                                         offsets[n_reads] - offsets[0], packed ? (int)(offsets[r0] & 3) : -1);
         if (rc) { abort_open_chunk(c); return rc; }
         CU(cudaEventRecord(c->ev_free[sl], c->stream));
         tmark(c->stream);
@@ -1526,6 +1553,20 @@ int32_t ggcat_b200_push_reads(ggcat_b200_ctx *c, const uint8_t *data, const uint
         for (cudaEvent_t e : tev) cudaEventDestroy(e);
     }
     return 0;
+}
+
+int32_t ggcat_b200_push_reads_packed_device(ggcat_b200_ctx *c, const uint8_t *d_packed, const uint64_t *d_offsets, uint64_t n_reads,
+                                            uint64_t n_bases, const uint32_t *d_colors) {
+    TRY(check_ctx(c));
+    std::lock_guard<std::mutex> lock__(c->mu);
+    if (c->finished) return set_err(GGCAT_B200_ERR_STATE, "push_reads after finish_bucketing");
+    if (n_reads == 0) return 0;
+    if (!d_packed || !d_offsets) return set_err(GGCAT_B200_ERR_INVALID, "null input");
+    if ((uintptr_t)d_packed & 3) return set_err(GGCAT_B200_ERR_INVALID, "packed device input must be 4-byte aligned");
+    if (n_bases > c->max_batch) return set_err(GGCAT_B200_ERR_INVALID, "device batch of %llu bases exceeds limit %llu", (unsigned long long)n_bases, (unsigned long long)c->max_batch);
+    int32_t rc = bucket_batch_device(c, d_packed, d_offsets, n_reads, 0, n_bases, c->P.colors ? d_colors : nullptr, n_bases, 0);
+    if (rc) { abort_open_chunk(c); return rc; }
+    return flush_open_chunk(c);
 }
 
 int32_t ggcat_b200_push_reads_device(ggcat_b200_ctx *c, const uint8_t *d_data, const uint64_t *d_offsets, uint64_t n_reads,

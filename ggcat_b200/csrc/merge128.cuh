@@ -254,7 +254,10 @@ k_merge_hash128(const ChunkView *__restrict__ chunks, uint32_t n_chunks, const u
     if (n_work_dev) n_work = min(n_work, *n_work_dev);   // device-side list (big units whose partitions overflowed)
     for (uint32_t wi = blockIdx.x; wi < n_work; wi += gridDim.x) {
         uint32_t unit = 0, n = 0;
+        uint32_t nx_n = 0;   // SRC_RECORDS: record count of this CTA's NEXT partition (loaded now, used after the inserts to
+                             // pull that partition's records into L2 while this one's table is scanned)
         if (SRC == SRC_RECORDS) {
+            if (wi + gridDim.x < n_work) nx_n = min(ps.pcount[wi + gridDim.x], ps.pcap);
             if (ps.big_ovf[ps.part_big[wi]]) continue;   // the whole unit is redone from its super-k-mers
             unit = ps.big_unit[ps.part_big[wi]];
             n = min(ps.pcount[wi], ps.pcap);
@@ -285,6 +288,15 @@ k_merge_hash128(const ChunkView *__restrict__ chunks, uint32_t n_chunks, const u
                 const uint32_t slot = hash_insert128(K, C, tmask, ((u128)ps.rec_hi[ro + i] << 64) | (u128)ps.rec_lo[ro + i],
                                                      ps.rec_fl[ro + i], &s_special, &claimed);
                 if (WITH_SRC && claimed) { if (slot == SLOT_SPECIAL) s_special_src = ps.rec_src[ro + i]; else L[slot] = ps.rec_src[ro + i]; }
+            }
+            if (nx_n) {   // 128-byte lines of the next partition's records (keys: 16 per line and array, flags: 128 per line)
+                const uint64_t rn = (uint64_t)(wi + gridDim.x) * ps.pcap;
+                const uint32_t kl = (nx_n + 15u) >> 4, fl = (nx_n + 127u) >> 7;
+                for (uint32_t q = tid; q < 2u * kl + fl; q += THREADS) {
+                    const void *pa = q < kl ? (const void *)(ps.rec_lo + rn + 16u * q)
+                                   : q < 2u * kl ? (const void *)(ps.rec_hi + rn + 16u * (q - kl)) : (const void *)(ps.rec_fl + rn + 128u * (q - 2u * kl));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(pa));
+                }
             }
         } else {
             for (uint32_t c = 0; c < n_chunks; c++) {

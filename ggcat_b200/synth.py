@@ -71,6 +71,19 @@ def reads_to_ascii_batch(codes2d: np.ndarray):
     return np.ascontiguousarray(data), offsets
 
 
+def pack_2bit(ascii_bases: np.ndarray) -> np.ndarray:
+    """ACGT bytes -> the reference's 2-bit stream (code = (c >> 1) & 3, base i at bits 2(i % 4) of byte i // 4,
+    crates/utils/src/lib.rs:44-46 + crates/io/src/compressed_read.rs:610-618).  Host-side helper for
+    ggcat_b200_push_reads_packed; the input must not contain N (split there first)."""
+    a = np.ascontiguousarray(ascii_bases, np.uint8)
+    codes = (a >> 1) & 3
+    pad = (-codes.size) % 4
+    if pad:
+        codes = np.concatenate([codes, np.zeros(pad, np.uint8)])
+    q = codes.reshape(-1, 4)
+    return np.ascontiguousarray(q[:, 0] | (q[:, 1] << 2) | (q[:, 2] << 4) | (q[:, 3] << 6)).astype(np.uint8)
+
+
 # ---- named BASELINE configs ---------------------------------------------------------------
 def config_c2(n_reads: int = 1_000_000, genome_len: int = 5_000_000, read_len: int = 150, err: float = 0.01,
               seed: int = 0xC2, first_read: int = 0):

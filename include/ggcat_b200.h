@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define GGCAT_B200_ABI_VERSION 7
+#define GGCAT_B200_ABI_VERSION 8
 
 typedef enum {
     GGCAT_B200_OK = 0,
@@ -138,6 +138,17 @@ int32_t ggcat_b200_push_reads(ggcat_b200_ctx *ctx, const uint8_t *data, const ui
 /* Same, with data/offsets/colors already resident in device memory of ctx's device. */
 int32_t ggcat_b200_push_reads_device(ggcat_b200_ctx *ctx, const uint8_t *d_data, const uint64_t *d_offsets,
                                      uint64_t n_reads, uint64_t n_bytes, const uint32_t *d_colors);
+/* 2-bit packed input (the `is_packed` form of SURVEY 8(b)): `packed` is ONE contiguous stream in the reference's
+ * CompressedRead layout (base i at bits 2(i % 4) of byte i / 4, A0 C1 T2 G3; crates/io/src/compressed_read.rs:610-618) and
+ * record r holds the bases [offsets[r], offsets[r+1]) of it -- offsets count bases, records need not start on a byte.
+ * The layout has no code for N: a host that packs reads splits them at N first, exactly as the reference does before it
+ * compresses a read (crates/minimizer_bucketing/src/sequences_splitter.rs:15-40).  A quarter of the H2D bytes of the ASCII
+ * form and no k_pack pass; everything downstream is identical.  The device variant wants a 4-byte aligned stream whose
+ * first base is offsets[0] = 0. */
+int32_t ggcat_b200_push_reads_packed(ggcat_b200_ctx *ctx, const uint8_t *packed, const uint64_t *offsets, uint64_t n_reads,
+                                     const uint32_t *colors);
+int32_t ggcat_b200_push_reads_packed_device(ggcat_b200_ctx *ctx, const uint8_t *d_packed, const uint64_t *d_offsets,
+                                            uint64_t n_reads, uint64_t n_bases, const uint32_t *d_colors);
 /* Input side on the device: raw FASTA / FASTQ TEXT instead of tokenised records.  Replaces the
  * reference's line reader and record state machines (crates/io/src/lines_reader.rs:140-175,
  * crates/io/src/sequences_reader.rs:106-179 process_fasta, :181-241 process_fastq): '>' lines start a record, ';' lines

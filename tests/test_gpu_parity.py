@@ -727,6 +727,49 @@ def test_c3_shape_colored_properties():
         ctx.close()
 
 
+@pytest.mark.parametrize("k,m,ht,batch", [(31, 12, O.HASH_SEQ, None), (31, 12, O.HASH_SEQ, 3000), (63, 14, O.HASH_RK128, 5000)])
+def test_packed_input_equals_ascii_input(k, m, ht, batch, monkeypatch):
+    """ggcat_b200_push_reads_packed (2-bit stream, offsets in bases, records of any length back to back) gives the same
+    super-k-mers and tables as the ASCII push of the same reads -- also when the host path cuts the stream into batches
+    that start in the middle of a byte -- and the device variant too."""
+    G = _gpu()
+    import torch
+
+    from ggcat_b200 import synth
+
+    if batch:
+        monkeypatch.setenv("GGCAT_B200_HOST_BATCH", str(batch))
+    rng = np.random.default_rng(99 + k)
+    g = util.rand_seq(rng, 4000)
+    seqs = []
+    for _ in range(120):
+        L = int(rng.integers(k - 3, 333))          # lengths not multiples of 4: records start anywhere inside a byte
+        a = int(rng.integers(0, len(g) - L))
+        r = g[a:a + L]
+        seqs.append(util.revcomp(r) if rng.random() < 0.5 else r)
+    seqs += [b"A" * 77, g[:k], b"", g[100:100 + k - 1], b"ACGT" * 40]
+    reads = O.Reads.from_list(seqs)
+    packed = synth.pack_2bit(reads.data)
+    b1, b2, s = 2, 2, 1
+    sk, _ = O.bucketing(reads, k, m, b1, b2)
+    want = _sk_records(reads, sk, k)
+    for mode in ("host", "device"):
+        ctx = G.GGCATB200(G.Params(k=k, m=m, min_multiplicity=s, buckets_count_log=b1, second_buckets_count_log=b2, hash_type=ht))
+        try:
+            if mode == "host":
+                ctx.push_reads_packed(packed, reads.offsets)
+            else:
+                dp = torch.from_numpy(np.concatenate([packed, np.zeros(8, np.uint8)])).cuda()
+                do = torch.from_numpy(reads.offsets.view(np.int64)).cuda()
+                ctx.push_reads_packed_device(dp.data_ptr(), do.data_ptr(), len(seqs), int(reads.data.size))
+            st = ctx.finish_bucketing()
+            assert st.n_superkmers == len(sk)
+            assert _gpu_records(ctx, (1 << b1) + 1) == want
+            _check_tables(G, ctx, reads, sk, k, s, b1, b2, hash_type=ht)
+        finally:
+            ctx.close()
+
+
 def test_error_behaviour():
     G = _gpu()
     with pytest.raises(G.GgcatB200Error):
