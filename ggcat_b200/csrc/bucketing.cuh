@@ -448,8 +448,19 @@ k_windows(const uint32_t *__restrict__ pk, const uint32_t *__restrict__ bad, con
 // ------------------------------------------------------------------------------------------------
 // Single-CTA exclusive scan of a u32 array (n up to a few million); out may alias in.
 // total (u64) written to *total_out.  Used for per-tile and per-unit offsets.
+__device__ __forceinline__ void exclusive_scan_u32_cta(const uint32_t *in, uint32_t *out, uint32_t n, unsigned long long *total_out);
 __global__ void __launch_bounds__(1024) k_exclusive_scan_u32(const uint32_t *in, uint32_t *out, uint32_t n,
                                                              unsigned long long *total_out) {
+    exclusive_scan_u32_cta(in, out, n, total_out);
+}
+// Several independent scans in ONE launch, one CTA each (the per-unit offsets of the slices an owner received: two arrays per
+// source rank and chunk).  The job list travels in the kernel parameters.
+constexpr int SCAN_MAX_JOBS = 64;
+struct ScanJobs { const uint32_t *in[SCAN_MAX_JOBS]; uint32_t *out[SCAN_MAX_JOBS]; uint32_t n; uint32_t pad; };
+__global__ void __launch_bounds__(1024) k_exclusive_scan_u32_jobs(const __grid_constant__ ScanJobs jobs) {
+    exclusive_scan_u32_cta(jobs.in[blockIdx.x], jobs.out[blockIdx.x], jobs.n, nullptr);
+}
+__device__ __forceinline__ void exclusive_scan_u32_cta(const uint32_t *in, uint32_t *out, uint32_t n, unsigned long long *total_out) {
     __shared__ uint32_t s_scan[1024 / 32 + 2];
     constexpr uint32_t IPT = 8;
     uint64_t running = 0;

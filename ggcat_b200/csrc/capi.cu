@@ -2473,6 +2473,18 @@ int32_t ggcat_b200_peer_exchange(ggcat_b200_ctx *c) {
     }
     const size_t stride = (size_t)(PEER_META_OFF + (uint64_t)guess * s_meta);
     CU(c->totals.reserve(8 * 8));
+    // per-unit offset scans of the received slices: they need only the counts (already here), so they run on the meta stream
+    // in batched launches while the bulk data is still in flight; the compute stream picks them up through ev_meta
+    ScanJobs sj;
+    uint32_t n_sj = 0;
+    sj.n = my_nu; sj.pad = 0;
+    auto flush_scans = [&]() -> int32_t {
+        if (!n_sj) return 0;
+        c->fam_launches[F_SCAN] += 1;
+        k_exclusive_scan_u32_jobs<<<n_sj, 1024, 0, ps.meta_stream>>>(sj);
+        n_sj = 0;
+        return 0;
+    };
     for (uint32_t s2 = 0; s2 < W; s2++) {
         if (s2 == me) continue;
         const uint8_t *hr = ps.h_recv + (size_t)s2 * stride;
@@ -2489,8 +2501,9 @@ int32_t ggcat_b200_peer_exchange(ggcat_b200_ctx *c) {
             ch->d_unit_cnt = dm; ch->d_unit_words = dm + my_nu; ch->d_unit_kmers = dm + 2 * (size_t)my_nu;
             uint32_t *uoff = reinterpret_cast<uint32_t *>(reg + PEER_META_OFF + (uint64_t)S * s_meta + (uint64_t)j * s_uoff);
             uint32_t *uwoff = uoff + (s_uoff / 8);
-            k_exclusive_scan_u32<<<1, 1024, 0, st>>>(dm, uoff, my_nu, c->totals.as<unsigned long long>() + 3);
-            k_exclusive_scan_u32<<<1, 1024, 0, st>>>(dm + my_nu, uwoff, my_nu, c->totals.as<unsigned long long>() + 4);
+            sj.in[n_sj] = dm; sj.out[n_sj] = uoff; ++n_sj;
+            sj.in[n_sj] = dm + my_nu; sj.out[n_sj] = uwoff; ++n_sj;
+            if (n_sj + 2 > (uint32_t)SCAN_MAX_JOBS) TRY(flush_scans());
             ch->d_unit_off = uoff; ch->d_unit_woff = uwoff;
             const uint32_t *hm = reinterpret_cast<const uint32_t *>(hr + PEER_META_OFF + (uint64_t)j * s_meta);
             const size_t nu = my_nu;
@@ -2514,6 +2527,9 @@ int32_t ggcat_b200_peer_exchange(ggcat_b200_ctx *c) {
             c->chunks.push_back(ch);
         }
     }
+    TRY(flush_scans());
+    CU(cudaEventRecord(ps.ev_meta, ps.meta_stream));
+    CU(cudaStreamWaitEvent(st, ps.ev_meta, 0));
     CU(cudaGetLastError());
     trace_host("peer_exchange: return");
     return 0;
