@@ -999,7 +999,7 @@ constexpr int W_SORT_THREADS = 512, W_SORT_CAP = 2048;
 
 template <int MODE>
 int32_t launch_hash128(ggcat_b200_ctx *c, const ChunkView *dv, uint32_t nch, std::vector<uint32_t> *work, uint32_t u0,
-                       const MergeOut128 &out, const std::vector<std::pair<uint64_t, uint32_t>> &large) {
+                       const MergeOut128 &out, const std::vector<std::pair<uint64_t, uint32_t>> &large, uint32_t *retry_base) {
     const DevParams &P = c->P;
     cudaStream_t st = c->stream;
     if (!work[0].empty()) {
@@ -1009,7 +1009,7 @@ int32_t launch_hash128(ggcat_b200_ctx *c, const ChunkView *dv, uint32_t nch, std
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const unsigned grid = (unsigned)std::min<size_t>(work[0].size(), (size_t)c->sm_count * 2 * 8);
         kern<<<grid, W_THREADS_S, smem, st>>>(dv, nch, c->d_work[0].as<uint32_t>(), (uint32_t)work[0].size(), u0, P, c->rk,
-                                               c->params.min_multiplicity, out, nullptr, 0, PartSrc128(), nullptr);
+                                               c->params.min_multiplicity, out, nullptr, 0, PartSrc128(), nullptr, retry_base);
     }
     if (!work[1].empty()) {
         LaunchTimer t(c, F_MERGE_HASH128);
@@ -1018,7 +1018,7 @@ int32_t launch_hash128(ggcat_b200_ctx *c, const ChunkView *dv, uint32_t nch, std
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const unsigned grid = (unsigned)std::min<size_t>(work[1].size(), (size_t)c->sm_count * 8);
         kern<<<grid, W_THREADS_L, smem, st>>>(dv, nch, c->d_work[1].as<uint32_t>(), (uint32_t)work[1].size(), u0, P, c->rk,
-                                               c->params.min_multiplicity, out, nullptr, 0, PartSrc128(), nullptr);
+                                               c->params.min_multiplicity, out, nullptr, 0, PartSrc128(), nullptr, retry_base);
     }
     // large units: table in a per-CTA slice of global scratch, biggest first, two tiers (see merge_range_device)
     const uint64_t TIER = 1ull << 20;
@@ -1036,7 +1036,7 @@ int32_t launch_hash128(ggcat_b200_ctx *c, const ChunkView *dv, uint32_t nch, std
         auto kern = k_merge_hash128<W_THREADS_L, 0, MODE>;
         kern<<<(unsigned)g, W_THREADS_L, merge_hash128_smem_bytes<W_THREADS_L, 0, MODE>(), st>>>(
             dv, nch, c->d_work[2].as<uint32_t>() + first, (uint32_t)count, u0, P, c->rk, c->params.min_multiplicity, out,
-            c->d_scratch.as<uint64_t>(), per_cta, PartSrc128(), nullptr);
+            c->d_scratch.as<uint64_t>(), per_cta, PartSrc128(), nullptr, nullptr);
     }
     CU(cudaGetLastError());
     return 0;
@@ -1054,7 +1054,7 @@ constexpr uint32_t W_PART_CAP = 3072, W_PART_TARGET = 2048;   // a partition fit
 
 template <int MODE>
 int32_t launch_partitions128(ggcat_b200_ctx *c, const ChunkView *dv, uint32_t nch, uint32_t u0, const MergeOut128 &out,
-                             const BigPlan128 &bp) {
+                             const BigPlan128 &bp, uint32_t *retry_base) {
     const DevParams &P = c->P;
     cudaStream_t st = c->stream;
     const size_t nbig = bp.unit.size();
@@ -1076,9 +1076,7 @@ int32_t launch_partitions128(ggcat_b200_ctx *c, const ChunkView *dv, uint32_t nc
     CU(c->d_recs.reserve(nrec * 16));
     CU(c->d_recfl.reserve(nrec));
     if (MODE == MODE_RK128) CU(c->d_recsrc.reserve(nrec * 8));
-    CU(c->d_retry.reserve((nbig + 2) * 4));
-    uint32_t *retry_cnt = c->d_retry.as<uint32_t>(), *retry = retry_cnt + 1;
-    CU(cudaMemsetAsync(retry_cnt, 0, 4, st));
+    uint32_t *retry_cnt = retry_base, *retry = retry_base + 1;   // shared with the shared-table kernels (merge_range_device_wide)
     uint64_t *rec_lo = c->d_recs.as<uint64_t>(), *rec_hi = rec_lo + nrec;
     {
         LaunchTimer t(c, F_PARTITION);
@@ -1098,19 +1096,29 @@ int32_t launch_partitions128(ggcat_b200_ctx *c, const ChunkView *dv, uint32_t nc
         const size_t smem = merge_hash128_smem_bytes<W_THREADS_S, W_TS_S, MODE>();
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const unsigned grid = (unsigned)std::min<size_t>(bp.n_parts, (size_t)c->sm_count * 2 * 8);
-        kern<<<grid, W_THREADS_S, smem, st>>>(dv, nch, nullptr, bp.n_parts, u0, P, c->rk, c->params.min_multiplicity, out, nullptr, 0, ps, nullptr);
+        kern<<<grid, W_THREADS_S, smem, st>>>(dv, nch, nullptr, bp.n_parts, u0, P, c->rk, c->params.min_multiplicity, out, nullptr, 0, ps, nullptr, nullptr);
     }
-    {   // units with an overflowed partition: global-table kernel over the device-side retry list
-        uint64_t per_cta = ((uint64_t)hash_table_slots_pow2((uint32_t)bp.nmax) * slot_bytes128<MODE>() + 15) / 16 * 2 + 2;
-        const uint64_t budget = 12ull << 30;
-        const uint64_t g = std::min<uint64_t>(std::min<uint64_t>(nbig, (uint64_t)c->sm_count * 2), std::max<uint64_t>(1, budget / (per_cta * 8)));
-        CU(c->d_scratch.reserve(per_cta * g * 8));
-        LaunchTimer t(c, F_MERGE_HASH128);
-        auto kern = k_merge_hash128<W_THREADS_L, 0, MODE>;
-        kern<<<(unsigned)g, W_THREADS_L, merge_hash128_smem_bytes<W_THREADS_L, 0, MODE>(), st>>>(
-            dv, nch, retry, (uint32_t)nbig, u0, P, c->rk, c->params.min_multiplicity, out, c->d_scratch.as<uint64_t>(), per_cta,
-            PartSrc128(), retry_cnt);
-    }
+    CU(cudaGetLastError());
+    return 0;
+}
+
+// Units that came back (a partition overflowed, or a shared table sized from the expected distinct keys filled up):
+// global-table kernel over the device-side retry list.
+template <int MODE>
+int32_t launch_retry128(ggcat_b200_ctx *c, const ChunkView *dv, uint32_t nch, uint32_t u0, const MergeOut128 &out, uint32_t *retry_base,
+                        uint64_t n_candidates, uint64_t nmax) {
+    if (!n_candidates) return 0;
+    const DevParams &P = c->P;
+    cudaStream_t st = c->stream;
+    uint64_t per_cta = ((uint64_t)hash_table_slots_pow2((uint32_t)nmax) * slot_bytes128<MODE>() + 15) / 16 * 2 + 2;
+    const uint64_t budget = 12ull << 30;
+    const uint64_t g = std::min<uint64_t>(std::min<uint64_t>(n_candidates, (uint64_t)c->sm_count * 2), std::max<uint64_t>(1, budget / (per_cta * 8)));
+    CU(c->d_scratch.reserve(per_cta * g * 8));
+    LaunchTimer t(c, F_MERGE_HASH128);
+    auto kern = k_merge_hash128<W_THREADS_L, 0, MODE>;
+    kern<<<(unsigned)g, W_THREADS_L, merge_hash128_smem_bytes<W_THREADS_L, 0, MODE>(), st>>>(
+        dv, nch, retry_base + 1, (uint32_t)n_candidates, u0, P, c->rk, c->params.min_multiplicity, out, c->d_scratch.as<uint64_t>(), per_cta,
+        PartSrc128(), retry_base, nullptr);
     CU(cudaGetLastError());
     return 0;
 }
@@ -1122,7 +1130,14 @@ int32_t merge_range_device_wide(ggcat_b200_ctx *c, uint32_t first_bucket, uint32
     const uint32_t u0 = first_bucket << P.b2, nu = n_buckets << P.b2;
     std::vector<uint32_t> work[3];
     std::vector<std::pair<uint64_t, uint32_t>> large, big;
-    uint64_t tot_kmers = 0;
+    uint64_t tot_kmers = 0, retry_nmax = 0;
+    // Opt-in (GGCAT_B200_WIDE_BY_KEYS=1): measured on the C5 slice (14 k-record units holding ~800 keys) the direct shared-table
+    // path takes 83.8 ms against 33.5 + 29.6 ms for key partitions + partition tables -- one super-k-mer per thread leaves the
+    // inserts as unbalanced as the rolling hashes, the partition pass balances them.  Kept for units of few, long super-k-mers.
+    const char *wbk = getenv("GGCAT_B200_WIDE_BY_KEYS");
+    const bool wide_by_keys = wbk && atoi(wbk) != 0;
+    const bool by_keys = wide_by_keys && c->wide_mode != MODE_COLOR && !c->no_tiers && c->distinct_ratio < 1.0;
+    const double keys_per_rec = std::min(1.0, 1.15 * c->distinct_ratio);
     for (uint32_t u = u0; u < u0 + nu; u++) {
         uint64_t n = 0;
         for (Chunk *ch : c->chunks)
@@ -1130,9 +1145,13 @@ int32_t merge_range_device_wide(ggcat_b200_ctx *c, uint32_t first_bucket, uint32
         if (n == 0) continue;
         if (n >= (1ull << 30)) return set_err(GGCAT_B200_ERR_INVALID, "unit %u holds %llu k-mers (> 2^30)", u, (unsigned long long)n);
         tot_kmers += n;
-        if (n <= W_TS_S * 3 / 4) work[0].push_back(u);
-        else if (n <= W_TS_L * 3 / 4) work[1].push_back(u);
-        else if (n <= (uint64_t)PART_MAXP * W_PART_TARGET && !c->no_partition) big.push_back({n, u});
+        // shared tables are sized by the distinct keys a unit should hold (distinct / records of what this context merged
+        // before, 15 % margin, load <= 1/2); inserts probe a bounded number of slots and a unit whose table fills up comes
+        // back through the retry list.  Coloured builds key by (k-mer, colour): every record may be a new key.
+        const double need_keys = (double)n * keys_per_rec;
+        if (n <= W_TS_S * 3 / 4 || (by_keys && need_keys <= W_TS_S / 2)) { work[0].push_back(u); retry_nmax = std::max(retry_nmax, n); }
+        else if (n <= W_TS_L * 3 / 4 || (by_keys && need_keys <= W_TS_L / 2)) { work[1].push_back(u); retry_nmax = std::max(retry_nmax, n); }
+        else if (n <= (uint64_t)PART_MAXP * W_PART_TARGET && !c->no_partition) { big.push_back({n, u}); retry_nmax = std::max(retry_nmax, n); }
         else large.push_back({n, u});
     }
     std::sort(large.begin(), large.end(), [](const auto &a, const auto &b) { return a.first > b.first; });
@@ -1193,9 +1212,21 @@ int32_t merge_range_device_wide(ggcat_b200_ctx *c, uint32_t first_bucket, uint32
     out.src = with_src ? c->out_src.as<uint64_t>() : nullptr; out.src_words = c->src_words; out.pad = 0;
     const ChunkView *dv = c->d_views.as<ChunkView>();
     const uint32_t nch = (uint32_t)views.size();
-    if (c->wide_mode == MODE_SEQ128) { TRY(launch_hash128<MODE_SEQ128>(c, dv, nch, work, u0, out, large)); TRY(launch_partitions128<MODE_SEQ128>(c, dv, nch, u0, out, bp)); }
-    else if (c->wide_mode == MODE_RK128) { TRY(launch_hash128<MODE_RK128>(c, dv, nch, work, u0, out, large)); TRY(launch_partitions128<MODE_RK128>(c, dv, nch, u0, out, bp)); }
-    else { TRY(launch_hash128<MODE_COLOR>(c, dv, nch, work, u0, out, large)); TRY(launch_partitions128<MODE_COLOR>(c, dv, nch, u0, out, bp)); }
+    // retry list shared by the shared-table kernels (table full) and the partition kernel (partition overflow)
+    CU(c->d_retry.reserve(((size_t)nu + 2) * 4));
+    uint32_t *retry_base = c->d_retry.as<uint32_t>();
+    CU(cudaMemsetAsync(retry_base, 0, 4, st));
+    const uint64_t n_cand = work[0].size() + work[1].size() + big.size();
+    if (c->wide_mode == MODE_SEQ128) {
+        TRY(launch_hash128<MODE_SEQ128>(c, dv, nch, work, u0, out, large, retry_base)); TRY(launch_partitions128<MODE_SEQ128>(c, dv, nch, u0, out, bp, retry_base));
+        TRY(launch_retry128<MODE_SEQ128>(c, dv, nch, u0, out, retry_base, n_cand, retry_nmax));
+    } else if (c->wide_mode == MODE_RK128) {
+        TRY(launch_hash128<MODE_RK128>(c, dv, nch, work, u0, out, large, retry_base)); TRY(launch_partitions128<MODE_RK128>(c, dv, nch, u0, out, bp, retry_base));
+        TRY(launch_retry128<MODE_RK128>(c, dv, nch, u0, out, retry_base, n_cand, retry_nmax));
+    } else {
+        TRY(launch_hash128<MODE_COLOR>(c, dv, nch, work, u0, out, large, retry_base)); TRY(launch_partitions128<MODE_COLOR>(c, dv, nch, u0, out, bp, retry_base));
+        TRY(launch_retry128<MODE_COLOR>(c, dv, nch, u0, out, retry_base, n_cand, retry_nmax));
+    }
     // ---- order every unit's entries by key into the unit-ordered layout
     uint32_t end_bit = 128;
     if (c->wide_mode == MODE_SEQ128) end_bit = std::min(128u, (2 * P.k + 7) & ~7u);
@@ -1262,6 +1293,8 @@ int32_t merge_range_device_wide(ggcat_b200_ctx *c, uint32_t first_bucket, uint32
     if (ovf) return set_err(GGCAT_B200_ERR_CAPACITY, "merge output overflow (code %u)", ovf);
     c->h_pinned[0] += c->h_pinned[3];   // entries of the dynamic region + entries of the partitioned units' regions
     uint64_t uq = c->h_pinned[1];
+    if (c->wide_mode != MODE_COLOR && c->h_pinned[2] >= (1ull << 20))
+        c->distinct_ratio = (double)c->h_pinned[1] / (double)c->h_pinned[2];   // sizes the shared tables of the next part / build
     if (c->wide_mode == MODE_COLOR) {
         c->fin.n_entries = c->h_pinned[4]; c->fin.n_colors = c->h_pinned[5];
         uq = 0;  // distinct (k-mer, colour) pairs are not the reference's distinct k-mers; not tracked for coloured builds

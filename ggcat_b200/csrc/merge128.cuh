@@ -91,9 +91,12 @@ __device__ __forceinline__ uint32_t mix128(unsigned long long lo, unsigned long 
 // MapEntry word beside the table that the scan treats as one more slot.
 // Returns the slot (SLOT_SPECIAL for the all-ones key); *claimed = this call created the entry (it then records where
 // the k-mer's bases can be found when the hash is not invertible).
-constexpr uint32_t SLOT_SPECIAL = 0xFFFFFFFFu;
+// Shared-memory tables are sized by the distinct keys a unit is EXPECTED to hold (host: distinct / records of what this
+// context merged before), so an insert probes a bounded number of slots; SLOT_FULL = give up, the unit is redone by the
+// global-table kernel (probe_limit 0 = unbounded: tables sized by the records themselves).
+constexpr uint32_t SLOT_SPECIAL = 0xFFFFFFFFu, SLOT_FULL = 0xFFFFFFFEu;
 __device__ __forceinline__ uint32_t hash_insert128(K128 *K, uint32_t *C, uint32_t mask, u128 key, uint32_t fb, uint32_t *special,
-                                                   bool *claimed) {
+                                                   bool *claimed, uint32_t probe_limit = 0) {
     const K128 want = to_k128(key);
     const K128 empty = K128{EMPTY64, EMPTY64};
     if (want.lo == EMPTY64 && want.hi == EMPTY64) {
@@ -102,10 +105,11 @@ __device__ __forceinline__ uint32_t hash_insert128(K128 *K, uint32_t *C, uint32_
         return SLOT_SPECIAL;
     }
     uint32_t slot = mix128(want.lo, want.hi) & mask;
-    while (true) {
+    for (uint32_t probes = 1;; ++probes) {
         const K128 old = atomicCAS(&K[slot], empty, want);
         if (old.lo == EMPTY64 && old.hi == EMPTY64) { *claimed = true; break; }
         if (old.lo == want.lo && old.hi == want.hi) { *claimed = false; break; }
+        if (probes == probe_limit) { *claimed = false; return SLOT_FULL; }
         slot = (slot + 1) & mask;
     }
     atomicAdd(&C[slot], 1u);
@@ -240,7 +244,8 @@ template <int THREADS, int TS_STATIC, int MODE, int SRC = SRC_SUPERKMERS>
 __global__ void __launch_bounds__(THREADS)
 k_merge_hash128(const ChunkView *__restrict__ chunks, uint32_t n_chunks, const uint32_t *__restrict__ work, uint32_t n_work,
                 uint32_t first_unit, DevParams P, RkTables T, uint32_t min_mult, MergeOut128 out,
-                uint64_t *__restrict__ scratch, uint64_t per_cta_u64, PartSrc128 ps, const uint32_t *__restrict__ n_work_dev) {
+                uint64_t *__restrict__ scratch, uint64_t per_cta_u64, PartSrc128 ps, const uint32_t *__restrict__ n_work_dev,
+                uint32_t *__restrict__ retry /* [0] = count, [1..] = units whose shared table filled up; may be NULL */) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr bool WITH_SRC = MODE == MODE_RK128;
     K128 *K = reinterpret_cast<K128 *>(smem_raw);
@@ -248,6 +253,9 @@ k_merge_hash128(const ChunkView *__restrict__ chunks, uint32_t n_chunks, const u
     uint32_t *C = reinterpret_cast<uint32_t *>(K + TS_STATIC) + (WITH_SRC ? 2 * TS_STATIC : 0);
     __shared__ uint32_t s_cnt[2];
     __shared__ uint32_t s_special;         // MapEntry word of the all-ones key (see hash_insert128)
+    __shared__ uint32_t s_full;            // an insert ran out of probes: the unit goes to the retry list
+    // bounded probing only where the table was sized from an expectation (shared tables fed by super-k-mers)
+    const uint32_t probe_limit = (TS_STATIC > 0 && SRC == SRC_SUPERKMERS && retry) ? 96u : 0u;
     __shared__ unsigned long long s_special_src;
     __shared__ unsigned long long s_base;
     const uint32_t tid = threadIdx.x;
@@ -279,7 +287,7 @@ k_merge_hash128(const ChunkView *__restrict__ chunks, uint32_t n_chunks, const u
         const uint32_t tmask = TS - 1;
         for (uint32_t i = tid; i < TS; i += THREADS) { K[i] = K128{EMPTY64, EMPTY64}; C[i] = 0u; }
         if (tid < 2) s_cnt[tid] = 0;
-        if (tid == 0) s_special = 0;
+        if (tid == 0) { s_special = 0; s_full = 0; }
         __syncthreads();
         if (SRC == SRC_RECORDS) {
             const uint64_t ro = (uint64_t)wi * ps.pcap;
@@ -310,16 +318,23 @@ k_merge_hash128(const ChunkView *__restrict__ chunks, uint32_t n_chunks, const u
                                            [&](u128 key, uint32_t fb, uint32_t ki, bool isf) {
                                                if (MODE == MODE_COLOR) key = (key << 32) | (u128)color;
                                                bool claimed;
-                                               const uint32_t slot = hash_insert128(K, C, tmask, key, fb, &s_special, &claimed);
+                                               const uint32_t slot = hash_insert128(K, C, tmask, key, fb, &s_special, &claimed, probe_limit);
+                                               if (slot == SLOT_FULL) { s_full = 1u; return; }
                                                if (WITH_SRC && claimed) {
                                                    const uint64_t loc = src_locator(c, d.x - cv.word_bias, ki, isf);
                                                    if (slot == SLOT_SPECIAL) s_special_src = loc; else L[slot] = loc;
                                                }
                                            });
+                    if (probe_limit && s_full) break;   // somebody found the table full: stop feeding it
                 }
             }
         }
         __syncthreads();
+        if (probe_limit && s_full) {   // block-uniform: nothing of this unit is written, the global-table kernel redoes it
+            if (tid == 0) retry[1u + atomicAdd(&retry[0], 1u)] = unit;
+            __syncthreads();           // s_full is reset at the top of the next work item
+            continue;
+        }
         // ---- pass 1 over the table: count survivors (MODE_COLOR: every occupied slot; the -s filter needs the
         //      per-k-mer fold, done after the sort)
         {

@@ -533,6 +533,30 @@ def test_wide_key_partitions_and_overflow_fallback(k, ht, s):
         ctx.close()
 
 
+@pytest.mark.parametrize("k,ht,ratio", [(63, O.HASH_RK128, "0.02"), (41, O.HASH_SEQ, "0.05"), (63, O.HASH_RK128, "0.5"), (97, O.HASH_RK128, "0.01")])
+def test_wide_tables_sized_by_distinct_keys_retry_when_wrong(k, ht, ratio, monkeypatch):
+    """Wide path: shared tables are sized by the distinct keys a unit is expected to hold.  Here the expectation is
+    forced far too low on all-distinct random sequence, so the bounded probing gives up and the units come back through
+    the retry list (global-table kernel); and forced moderately low, so that some units fit and some do not.  Same tables."""
+    G = _gpu()
+    monkeypatch.setenv("GGCAT_B200_DISTINCT_RATIO", ratio)
+    monkeypatch.setenv("GGCAT_B200_WIDE_BY_KEYS", "1")      # opt-in routing (the default routes the wide path by records)
+    rng = np.random.default_rng(1234 + k)
+    m, b1, b2, s = 14, 1, 1, 1
+    seqs = [util.rand_seq(rng, 30000), util.rand_seq(rng, 9000), util.rand_seq(rng, 2500)] + [util.rand_seq(rng, 400) for _ in range(30)]
+    seqs += [seqs[1][:5000]] * 3          # a repeated stretch: some units really are below the expectation
+    reads = O.Reads.from_list(seqs)
+    sk, _ = O.bucketing(reads, k, m, b1, b2)
+    ctx, st = G.minimizer_bucketing([(reads.data, reads.offsets)], b1, b2, k, m, min_multiplicity=s, hash_type=ht)
+    try:
+        _, km = ctx.unit_sizes()
+        assert (km > 6144).sum() >= 1 and (km < 3000).sum() >= 1
+        _check_tables(G, ctx, reads, sk, k, s, b1, b2, hash_type=ht)
+        _check_tables(G, ctx, reads, sk, k, s, b1, b2, hash_type=ht)      # second merge of the same context
+    finally:
+        ctx.close()
+
+
 def test_colored_big_units():
     """-c with units above the shared-table capacity (partition path of the wide kernels in MODE_COLOR)."""
     G = _gpu()
