@@ -1,5 +1,5 @@
 """Kernel timeline of one warm bench step (device path), N ranks: GGCAT_B200_TRACE prints every timed launch.
-   torchrun ... scratch/trace_step.py   (or plain python for N=1)"""
+   torchrun ... profiles/trace_step.py   (or plain python for N=1)"""
 import os, sys, time
 from pathlib import Path
 import numpy as np, torch, torch.distributed as dist
