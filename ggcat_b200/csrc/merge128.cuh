@@ -652,6 +652,9 @@ __device__ __forceinline__ bool same_kmer(uint64_t alo, uint64_t ahi, uint64_t b
 }
 
 // WRITE == false: per-unit counts of kept k-mers / kept colour entries.  WRITE == true: emit them.
+// A k-mer of a shared region carries one entry per colour (100 at C3), so the fold of a run is WARP-cooperative: every warp
+// takes 32 consecutive entries, finds the run heads among them with one ballot, and all 32 lanes then sum / OR / copy the
+// entries of each head's run together (a run may extend past the warp's 32 entries; its head's warp follows it).
 template <int THREADS, bool WRITE>
 __global__ void __launch_bounds__(THREADS)
 k_color_fold(const uint64_t *__restrict__ lo, const uint64_t *__restrict__ hi, const uint32_t *__restrict__ cf,
@@ -661,23 +664,41 @@ k_color_fold(const uint64_t *__restrict__ lo, const uint64_t *__restrict__ hi, c
              uint64_t *__restrict__ o_lo, uint64_t *__restrict__ o_hi, uint32_t *__restrict__ o_cf,
              uint64_t *__restrict__ o_coloff, uint32_t *__restrict__ o_colors) {
     __shared__ uint32_t s_scan[THREADS / 32 + 2];
-    const uint32_t tid = threadIdx.x;
+    const uint32_t tid = threadIdx.x, lane = lane_id();
     for (uint32_t u = blockIdx.x; u < n_units; u += gridDim.x) {
         const uint64_t b = unit_off[u], e = unit_off[u + 1];
         uint32_t run_keys = 0, run_cols = 0;  // running totals inside the unit (block-uniform)
         for (uint64_t base = b; base < e; base += THREADS) {
             const uint64_t i = base + tid;
             uint32_t keep = 0, ncol = 0, cfo = 0;
+            uint64_t l = 0, h = 0;
+            bool head = false;
             if (i < e) {
-                const uint64_t l = lo[i], h = hi[i];
-                if (i == b || !same_kmer(l, h, lo[i - 1], hi[i - 1])) {
-                    uint64_t cnt = 0;
-                    uint32_t fl = 0, len = 0;
-                    for (uint64_t j = i; j < e; ++j) {
-                        if (j > i && !same_kmer(l, h, lo[j], hi[j])) break;
-                        const uint32_t c = cf[j];
-                        cnt += c & 0x3FFFFFFFu; fl |= c >> 30; ++len;
-                    }
+                l = lo[i]; h = hi[i];
+                head = i == b || !same_kmer(l, h, lo[i - 1], hi[i - 1]);
+            }
+            // every head of this warp's 32 entries, in turn: all lanes fold its run
+            uint32_t heads = __ballot_sync(0xffffffffu, head);
+            while (heads) {
+                const uint32_t hl = __ffs(heads) - 1u;
+                heads &= heads - 1u;
+                const uint64_t hi0 = __shfl_sync(0xffffffffu, h, hl), lo0 = __shfl_sync(0xffffffffu, l, hl);
+                const uint64_t start = __shfl_sync(0xffffffffu, i, hl);
+                uint64_t cnt = 0;
+                uint32_t fl = 0, len = 0;
+                for (uint64_t j0 = start;; j0 += 32) {
+                    const uint64_t j = j0 + lane;
+                    const bool in = j < e && same_kmer(lo0, hi0, lo[j], hi[j]);
+                    if (in) { const uint32_t c = cf[j]; cnt += c & 0x3FFFFFFFu; fl |= c >> 30; ++len; }
+                    if (__ballot_sync(0xffffffffu, in) != 0xffffffffu) break;   // the run ends inside these 32 entries
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+                    fl |= __shfl_xor_sync(0xffffffffu, fl, o);
+                    len += __shfl_xor_sync(0xffffffffu, len, o);
+                }
+                if (lane == hl) {
                     const uint64_t mult = cnt >> ((fl == 3u) ? 1 : 0);  // map_entry.rs:79-84 on the folded entry
                     if (mult >= min_mult) { keep = 1; ncol = len; cfo = (uint32_t)(mult > 0x3FFFFFFFull ? 0x3FFFFFFFull : mult) | (fl << 30); }
                 }
@@ -685,14 +706,23 @@ k_color_fold(const uint64_t *__restrict__ lo, const uint64_t *__restrict__ hi, c
             uint32_t tk, tc;
             const uint32_t pk = block_exclusive_scan<THREADS>(keep, s_scan, &tk);
             const uint32_t pc = block_exclusive_scan<THREADS>(ncol, s_scan, &tc);
-            if (WRITE && keep) {
+            if (WRITE) {
                 const uint64_t ko = key_off[u] + run_keys + pk, co = col_off[u] + run_cols + pc;
-                const uint64_t l = lo[i], h = hi[i];
-                o_lo[ko] = (l >> 32) | (h << 32);
-                o_hi[ko] = h >> 32;
-                o_cf[ko] = cfo;
-                o_coloff[ko] = co;
-                for (uint32_t q = 0; q < ncol; q++) o_colors[co + q] = (uint32_t)lo[i + q];
+                if (keep) {
+                    o_lo[ko] = (l >> 32) | (h << 32);
+                    o_hi[ko] = h >> 32;
+                    o_cf[ko] = cfo;
+                    o_coloff[ko] = co;
+                }
+                // the colour lists of this warp's kept heads, copied by all lanes
+                uint32_t kept = __ballot_sync(0xffffffffu, keep != 0);
+                while (kept) {
+                    const uint32_t hl = __ffs(kept) - 1u;
+                    kept &= kept - 1u;
+                    const uint64_t src = __shfl_sync(0xffffffffu, i, hl), dst = __shfl_sync(0xffffffffu, co, hl);
+                    const uint32_t n = __shfl_sync(0xffffffffu, ncol, hl);
+                    for (uint32_t q = lane; q < n; q += 32) o_colors[dst + q] = (uint32_t)lo[src + q];
+                }
             }
             run_keys += tk; run_cols += tc;
         }
