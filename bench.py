@@ -176,12 +176,29 @@ def traffic_pass(timeout_s: float = 150.0):
     return {}, "unavailable"
 
 
+_GENOME_CACHE = {}
+
+
 def make_reads(rank: int, world: int, n_reads: int):
     from ggcat_b200 import synth
 
-    g = synth.genome_codes(0xC2, GENOME_PER_GPU * world)
-    r = synth.simulate_reads(g, n_reads, READ_LEN, ERR, 0xC2 + 1, first_read=rank * n_reads)
+    glen = GENOME_PER_GPU * world
+    if glen not in _GENOME_CACHE:          # the N-rank reference arm and the N > 1 parity check ask for every rank's slice
+        _GENOME_CACHE.clear()
+        _GENOME_CACHE[glen] = synth.genome_codes(0xC2, glen)
+    r = synth.simulate_reads(_GENOME_CACHE[glen], n_reads, READ_LEN, ERR, 0xC2 + 1, first_read=rank * n_reads)
     return synth.reads_to_ascii_batch(r)
+
+
+def make_reads_all(world: int, n_reads: int):
+    """The slices of all ranks (reference arm, N > 1 parity check), generated in threads (numpy releases the GIL)."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    first = make_reads(0, world, n_reads)          # fills the genome cache
+    if world == 1:
+        return [first]
+    with ThreadPoolExecutor(min(world - 1, os.cpu_count() or 1)) as ex:
+        return [first] + list(ex.map(lambda r: make_reads(r, world, n_reads), range(1, world)))
 
 
 # ------------------------------------------------------------------------------------------- reference arm
@@ -204,7 +221,7 @@ def run_reference(args):
         parts = [make_reads(0, world, args.sample_reads)]
         sample_note = f"{args.sample_reads} reads of rank 0's slice"
     else:
-        parts = [make_reads(r, world, per_gpu) for r in range(world)]
+        parts = make_reads_all(world, per_gpu)
         sample_note = f"all {world} x {per_gpu} reads of the workload"
     cores = os.cpu_count() or 1
     data = np.concatenate([d for d, _ in parts])
@@ -260,11 +277,14 @@ def multi_gpu_parity(args, ctx, owner, rank, world, b1, b2, n_reads, step_device
         return None
     from oracle import oracle as O
 
-    parts = [make_reads(r, world, n_reads) for r in range(world)]
+    parts = make_reads_all(world, n_reads)
     data = np.concatenate([d for d, _ in parts])
     offsets = np.arange(data.size // READ_LEN + 1, dtype=np.uint64) * np.uint64(READ_LEN)
     reads = O.Reads(data, offsets)
-    sk, _ = O.bucketing(reads, K, M, b1, b2)
+    sk, _ = O.bucketing_parallel(reads, K, M, b1, b2)
+    # merge_unit selects a unit's super-k-mers with a mask over the array it is given: hand it only the super-k-mers of the
+    # sampled units (one pass over the 10^8 rows instead of one per unit)
+    sk = sampled_superkmers(sk, [u for pl in gathered for u in pl["units"]], b2)
     checked, entries, bad = 0, 0, []
     for pl in gathered:
         for i, u in enumerate(pl["units"]):
@@ -280,6 +300,12 @@ def multi_gpu_parity(args, ctx, owner, rank, world, b1, b2, n_reads, step_device
                     bad.append({"rank": pl["rank"], "unit": int(u), "path": path})
     return {"ok": not bad, "units_checked": checked, "entries_checked": entries, "paths": sorted(gathered[0]["tables"].keys()),
             "oracle": "oracle/ggcat_oracle.c on the union of all ranks' reads", "mismatches": bad[:8]}
+
+
+def sampled_superkmers(sk, units, b2: int):
+    """The rows of an oracle super-k-mer array that belong to the given units (bucket << b2 | second_bucket)."""
+    uid = (sk["bucket"].astype(np.uint32) << np.uint32(b2)) | sk["second_bucket"].astype(np.uint32)
+    return np.ascontiguousarray(sk[np.isin(uid, np.asarray(sorted(set(int(u) for u in units)), np.uint32))])
 
 
 # ------------------------------------------------------------------------------------------- our arm

@@ -255,6 +255,32 @@ def bucketing(reads: Reads, k: int, m: int, b1: int, b2: int, forward_only: bool
         cap = n
 
 
+def bucketing_parallel(reads: Reads, k: int, m: int, b1: int, b2: int, forward_only: bool = False, n_threads: int = 0):
+    """bucketing() over contiguous read ranges in threads (records are independent, crates/minimizer_bucketing/src/lib.rs:
+    310-320; ctypes releases the GIL): the same rows in the same order, for checkers that need the super-k-mers of 10^7 reads."""
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+
+    n_threads = n_threads or (os.cpu_count() or 1)
+    n = reads.n
+    if n_threads <= 1 or n < 4 * n_threads:
+        return bucketing(reads, k, m, b1, b2, forward_only)
+    cuts = [n * t // n_threads for t in range(n_threads + 1)]
+
+    def part(t):
+        a, b = cuts[t], cuts[t + 1]
+        o0, o1 = int(reads.offsets[a]), int(reads.offsets[b])
+        sub = Reads(reads.data[o0:o1], reads.offsets[a:b + 1] - reads.offsets[a],
+                    reads.colors[a:b] if reads.colors is not None else None)
+        sk, vb = bucketing(sub, k, m, b1, b2, forward_only)
+        sk["read_index"] += np.uint32(a)
+        return sk, vb
+
+    with ThreadPoolExecutor(n_threads) as ex:
+        res = list(ex.map(part, range(n_threads)))
+    return np.concatenate([r[0] for r in res]), sum(r[1] for r in res)
+
+
 def superkmer_packed(reads: Reads, sk_row) -> bytes:
     row = np.array([sk_row], SUPERKMER_DTYPE)
     out = np.zeros(int(row["len"][0]) // 4 + 8, np.uint8)

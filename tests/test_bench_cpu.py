@@ -34,3 +34,25 @@ def test_torch_generators_match_numpy():
         a = synth.reads_to_ascii_batch(synth.simulate_reads(g, 2500, 150, err, 0xC5, first_read=12345))[0]
         b = synth.simulate_reads_torch(gt, 2500, 150, err, 0xC5, first_read=12345)
         assert np.array_equal(a, b.numpy())
+
+
+def test_sampled_superkmers_keep_the_units_merge_unit_needs():
+    """bench.multi_gpu_parity pre-filters the oracle's super-k-mers to the sampled units: merge_unit must see the same rows."""
+    import numpy as np
+
+    import bench
+    from oracle import oracle as O
+
+    data, offsets = bench.make_reads(0, 2, 3000)
+    d2, _ = bench.make_reads(1, 2, 3000)          # second slice from the cached genome
+    assert data.size == d2.size and not np.array_equal(data, d2)
+    reads = O.Reads(data, offsets)
+    b1, b2 = 3, 2
+    sk, _ = O.bucketing(reads, bench.K, bench.M, b1, b2)
+    units = [0, 5, 17, (8 << b2) | 1, 33]
+    small = bench.sampled_superkmers(sk, units, b2)
+    assert 0 < small.size < sk.size
+    for u in units:
+        a, _, ta = O.merge_unit(reads, sk, u >> b2, u & ((1 << b2) - 1), bench.K, bench.S)
+        b, _, tb = O.merge_unit(reads, small, u >> b2, u & ((1 << b2) - 1), bench.K, bench.S)
+        assert ta == tb and np.array_equal(a, b)

@@ -428,3 +428,12 @@ def test_reference_minqueue_invariant_10m(inject_duplicates):
         assert np.array_equal(got & mask, true_min & mask)
         count = ((win & mask) == (got & mask)[:, None]).sum(axis=1)
         assert np.array_equal(count > 1, (got & np.uint64(1)) == 0)
+
+
+def test_bucketing_parallel_equals_bucketing():
+    rng = np.random.default_rng(5)
+    seqs = [util.rand_seq(rng, int(rng.integers(20, 400))) for _ in range(200)] + [b"ACGTNNACGT" * 20, b"", b"A" * 100]
+    reads = O.Reads.from_list(seqs, colors=list(range(len(seqs))))
+    a, va = O.bucketing(reads, 31, 12, 3, 2)
+    b, vb = O.bucketing_parallel(reads, 31, 12, 3, 2, n_threads=5)
+    assert va == vb and np.array_equal(a, b)
