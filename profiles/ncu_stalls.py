@@ -41,7 +41,7 @@ def main(rep, out_json=None):
             top = max(((float(r[i] or 0), label) for i, label in stall if label not in ("selected",)), default=(0, "-"))
             lim[fam] = {"kind": "issue" if float(r[ia]) > 45 else "latency", "issue_active_pct": round(float(r[ia]), 1),
                         "dram_pct_of_peak": round(float(r[idr]), 1), "top_stall": top[1], "top_stall_warps_per_issue": round(top[0], 2),
-                        "source": "profiles/r02_ncu_full.md (ncu --set full, first launch of the family)"}
+                        "source": "profiles/r02z_ncu_full.md (ncu --set full, first launch of the family)"}
         json.dump(lim, open(out_json, "w"), indent=1)
 
 
