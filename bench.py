@@ -275,6 +275,12 @@ def multi_gpu_parity(args, ctx, owner, rank, world, b1, b2, n_reads, step_device
     dist.gather_object(payload, gathered, dst=0)
     if rank != 0:
         return None
+    return parity_against_oracle(gathered, world, n_reads, b1, b2)
+
+
+def parity_against_oracle(gathered, world: int, n_reads: int, b1: int, b2: int):
+    """Rank 0, host only: the oracle on the UNION of all ranks' reads against the sampled unit tables every rank sent
+    (payload = {"rank", "units", "tables": {path: [(keys, count_flags) per unit]}})."""
     from oracle import oracle as O
 
     parts = make_reads_all(world, n_reads)

@@ -56,3 +56,35 @@ def test_sampled_superkmers_keep_the_units_merge_unit_needs():
         a, _, ta = O.merge_unit(reads, sk, u >> b2, u & ((1 << b2) - 1), bench.K, bench.S)
         b, _, tb = O.merge_unit(reads, small, u >> b2, u & ((1 << b2) - 1), bench.K, bench.S)
         assert ta == tb and np.array_equal(a, b)
+
+
+def test_parity_against_oracle_accepts_oracle_tables_and_flags_a_corrupted_one():
+    """The host half of the bench's N > 1 parity object (rank 0: oracle on the union of all ranks' reads), fed with unit
+    tables made by the oracle itself: everything matches; one flipped count is reported."""
+    import numpy as np
+
+    import bench
+    from oracle import oracle as O
+
+    world, n_reads, b1, b2 = 2, 2500, 3, 2
+    parts = bench.make_reads_all(world, n_reads)
+    data = np.concatenate([d for d, _ in parts])
+    reads = O.Reads(data, np.arange(data.size // bench.READ_LEN + 1, dtype=np.uint64) * np.uint64(bench.READ_LEN))
+    sk, _ = O.bucketing(reads, bench.K, bench.M, b1, b2)
+
+    def table(u):
+        ref, _, _ = O.merge_unit(reads, sk, u >> b2, u & ((1 << b2) - 1), bench.K, bench.S)
+        ref = ref[ref["kept"] == 1]
+        cf = (ref["multiplicity"].astype(np.uint32) & np.uint32(0x3FFFFFFF)) | (ref["flags"].astype(np.uint32) << np.uint32(30))
+        return np.array(ref["key_lo"]), cf
+
+    gathered = []
+    for r, units in enumerate([[1, 6, 9], [17, 20, 30]]):
+        rows = [table(u) for u in units]
+        gathered.append({"rank": r, "units": units, "tables": {"device": rows, "host": [(k.copy(), c.copy()) for k, c in rows]}})
+    res = bench.parity_against_oracle(gathered, world, n_reads, b1, b2)
+    assert res["ok"] and res["units_checked"] == 12 and res["paths"] == ["device", "host"] and res["entries_checked"] > 0
+    victim = next(i for i, (k, c) in enumerate(gathered[1]["tables"]["host"]) if c.size)
+    gathered[1]["tables"]["host"][victim][1][0] ^= np.uint32(1)
+    res = bench.parity_against_oracle(gathered, world, n_reads, b1, b2)
+    assert not res["ok"] and res["mismatches"] == [{"rank": 1, "unit": gathered[1]["units"][victim], "path": "host"}]
